@@ -1,0 +1,23 @@
+"""Cheap deterministic stand-ins for the generator, shared by the golden generator and the tests.
+
+They obey the reference's model plug-in contract (process_full_tiles.py:338-340): ``m(x, training=False)`` with
+``x`` (B, I, I, 2) -> array (B, I, I, C); the last channel is the normalised SR DEM."""
+import numpy as np
+
+
+def identity(x, training=False):
+    """The reference's default model (process_full_tiles.py:143)."""
+    return x
+
+
+def wobble(x, training=False):
+    """Slot- and pixel-dependent perturbation of the normalised DEM so overlapping generations disagree
+    (non-zero std) and batch position matters.  Pure float32 numpy, elementwise, no transcendental functions
+    (bit-reproducible everywhere)."""
+    x = np.asarray(x, dtype=np.float32)
+    b = x.shape[0]
+    slot = (np.arange(b, dtype=np.float32) - np.float32(0.5 * (b - 1))) / np.float32(max(b, 1))
+    slot = slot.reshape(b, 1, 1)
+    ortho, dem = x[..., 0], x[..., 1]
+    y = dem * np.float32(0.875) + ortho * ortho * np.float32(0.0625) + slot * np.float32(0.03125)
+    return y[..., None].astype(np.float32)
