@@ -1,0 +1,142 @@
+/*
+ * moonsr.h -- C ABI of libmoonsr.so: the B200 (sm_100a) implementation of MoonSuperResolution's tiled full-DEM
+ * inference path.  This is the drop-in boundary: plain pointers and sizes, no torch / C++ types.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative MSR_E_* code otherwise; msr_last_error() gives the text of the
+ *     last failure on the calling thread.  No C++ exception crosses this boundary.
+ *   - pointers whose name starts with d_ are DEVICE pointers (cudaMalloc / torch-allocated), h_ are HOST pointers.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  All work is asynchronous on it unless
+ *     stated otherwise; no function allocates device memory except *_create / *_finalize.
+ *   - rasters are row-major (rows, cols) float32; activations are NHWC.
+ *   - (x, y) = (column, row).  I = image_size, S = stride, T = tile_size, p = purge = I / 16, off = I - S.
+ *
+ * Each entry point names the reference code it replaces (file:line in AntoineRichard/MoonSuperResolution).
+ */
+#ifndef MOONSR_H_
+#define MOONSR_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSR_OK 0
+#define MSR_E_INVALID (-1) /* bad argument */
+#define MSR_E_CUDA (-2)    /* CUDA runtime / driver error */
+#define MSR_E_STATE (-3)   /* call order violated (e.g. forward before finalize) */
+#define MSR_E_NOMEM (-4)
+
+#define MSR_ARCH_SPADE 0   /* GauGAN:   encoder -> Gaussian sampler -> SPADE generator (spade/models/model.py:564-567) */
+#define MSR_ARCH_CNN 1     /* CNNSpade: encoder -> mean + variance  -> SPADE generator (spade/models/model.py:789-791) */
+#define MSR_ARCH_PIX2PIX 2 /* Pix2Pix U-Net generator, training=False (pix2pix.py:64-108) */
+
+#define MSR_PRECISION_FP32 0 /* CUDA-core fp32 everywhere (parity mode, <= 1e-4) */
+#define MSR_PRECISION_BF16 1 /* tcgen05 implicit-GEMM convolutions, bf16 operands, fp32 accumulation */
+
+int msr_version(void);
+const char* msr_last_error(void);
+/* Device properties the host side needs; returns the SM count of the current device (or <0). */
+int msr_device_sm_count(void);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Tiling / blending  (process_full_tiles.py)
+ * ------------------------------------------------------------------------------------------------------------- */
+
+/* padInputs (process_full_tiles.py:246-267): fill both (CH, CW) canvases with no_value and paste the (H, W) rasters
+ * at [off, off + H) x [off, off + W). */
+int msr_pad_inputs(const float* d_dem, const float* d_img, int H, int W, float* d_dem_canvas, float* d_img_canvas,
+                   int CH, int CW, int off, float no_value, void* stream);
+
+/* getPatch's validity test (process_full_tiles.py:286-292), factored: summed-area table of the invalid mask
+ * (img <= no_value || dem <= no_value).  d_sat is int32 (CH + 1, CW + 1), first row / column zero. */
+int msr_validity_sat(const float* d_img_canvas, const float* d_dem_canvas, int CH, int CW, float no_value,
+                     int32_t* d_sat, void* stream);
+
+/* valid[k] = 1 iff the I x I window at canvas origin (xy[2k], xy[2k+1]) holds no invalid pixel (clipped to the canvas
+ * like a numpy slice).  Exact integer arithmetic. */
+int msr_patch_validity(const int32_t* d_sat, int CH, int CW, const int32_t* d_xy, int n, int I, uint8_t* d_valid,
+                       void* stream);
+
+/* normalize (process_full_tiles.py:295-311) for n patches: out[k] = (I, I, 2) float32, channel 0 = ortho, channel 1 =
+ * DEM, each ((v - min) / (max - min)) - 0.5 in float32 with IEEE division; minmax[k] = {img_min, img_max, dem_min,
+ * dem_max}.  A slot with origin (-1, -1) is a padding slot (process_full_tiles.py:468-474): all-zero output.
+ * d_partial is scratch of n * 32 * 4 floats. */
+int msr_gather_normalize(const float* d_img_canvas, const float* d_dem_canvas, int CH, int CW, const int32_t* d_xy,
+                         int n, int I, float* d_out_nhwc, float* d_minmax, float* d_partial, void* stream);
+
+/* rebuildTile (process_full_tiles.py:363-414) fused with the tile's paste + crop of rebuildMap (:541-545), in gather
+ * form: one thread per output pixel replays, in the reference's patch order, the Gaussian-weighted incremental
+ * mean / variance update with float64 intermediates and float32 state, then writes mean, std, good.
+ *   d_patch_ptr[k]   (I, I) prediction of patch k, float32 (or float64 where d_patch_f64[k] != 0; may be NULL)
+ *   d_patch_lohi[k]  {dem_min, dem_max} of patch k (float32)
+ *   d_patch_xy[k]    patch origin (x, y) relative to the tile's canvas origin, i.e. the reference's dict key
+ *   n                number of patches, in dict insertion order
+ *   d_lattice        NULL, or (G, G) int32 with d_lattice[gy * G + gx] = k for the patch whose key is (gx*S, gy*S), -1
+ *                    if none; legal only when keys lie on that lattice in row-major insertion order.  With NULL the
+ *                    kernel scans all n patches per pixel (any keys, any order).
+ *   d_weights        float64 (I - 2p, I - 2p): makeGaussianKernel() + 1e-7 cropped by p (:391-393)
+ *   add_half         1: predictions are raw network outputs, add 0.5f first (processBatch, :340); 0: already added
+ *   outputs          pixel (row, col) of the T x T tile centre goes to out[row * pitch + col] for row < rows,
+ *                    col < cols (rows, cols <= T clip the tile to the raster).  good is uint8.
+ */
+int msr_blend_tile(const void* const* d_patch_ptr, const uint8_t* d_patch_f64, const float* d_patch_lohi,
+                   const int32_t* d_patch_xy, int n, const int32_t* d_lattice, int G, const double* d_weights, int I,
+                   int S, int T, int add_half, float no_value, float* d_mean, float* d_std, uint8_t* d_good,
+                   int64_t pitch, int rows, int cols, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Generators  (spade/models/{networks,blocks,spade,sampling}.py, model.py:564-567 / 789-791, pix2pix.py:64-108)
+ * ------------------------------------------------------------------------------------------------------------- */
+
+typedef struct msr_generator msr_generator;
+
+/* Builds an empty model.  `batch_size` is the reference's batch (the unit over which SPADE's batch statistics are
+ * taken, spade.py:21); `max_groups` batches can be pushed through one forward call, each with its own statistics. */
+int msr_generator_create(msr_generator** out, int arch, int image_size, int batch_size, int max_groups, int precision);
+
+/* Supplies one tensor in Keras layout (names: moonsuperresolution_b200/weights.py).  Host float32, copied. */
+int msr_generator_set_weight(msr_generator* g, const char* name, const float* h_data, const int64_t* shape, int ndim);
+
+/* Checks that every tensor is present, repacks (gamma|beta concatenation, [N][K] bf16 ...), uploads, allocates the
+ * workspace and builds the TMA descriptors.  Synchronous. */
+int msr_generator_finalize(msr_generator* g);
+
+/* One forward pass over n_groups * batch_size patches.
+ *   d_source  (n_groups * B, I, I, 2) float32, as produced by msr_gather_normalize
+ *   d_eps     (n_groups * B, 256) float32 standard-normal draws for the Gaussian sampler (sampling.py:13-16);
+ *             required for MSR_ARCH_SPADE, ignored otherwise
+ *   d_out     (n_groups * B, I, I) float32: last (only) output channel, before the + 0.5 of processBatch */
+int msr_generator_forward(msr_generator* g, const float* d_source, const float* d_eps, float* d_out, int n_groups,
+                          void* stream);
+
+/* Number of kernel launches issued by the last forward call (for bench.py's gpu_launches). */
+int64_t msr_generator_last_launch_count(const msr_generator* g);
+
+/* Bytes of device memory held (weights + workspace). */
+int64_t msr_generator_device_bytes(const msr_generator* g);
+
+/* Debug / parity aid: copies a named intermediate of the last forward (e.g. "latent", "rb3.out") to the host as
+ * float32; *count receives the element count (call with h_dst == NULL to query).  Synchronous. */
+int msr_generator_read_activation(msr_generator* g, const char* name, float* h_dst, int64_t capacity, int64_t* count);
+
+int msr_generator_destroy(msr_generator* g);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Single operators, exported for the parity tests of the tensor-core kernels
+ * ------------------------------------------------------------------------------------------------------------- */
+
+/* 3x3 stride-1 SAME convolution as tcgen05 implicit GEMM.  d_x (n, r, r, cin) bf16 (uint16 bits), d_w (cout, 9*cin)
+ * bf16 with k = (ky*3 + kx)*cin + ci, d_bias (cout) float32 or NULL, d_y (n, r, r, cout) float32. */
+int msr_op_conv3x3_bf16(const uint16_t* d_x, const uint16_t* d_w, const float* d_bias, float* d_y, int n, int r,
+                        int cin, int cout, void* stream);
+
+/* Same operator on CUDA cores in float32 (the fp32-mode kernel); d_w (3, 3, cin, cout) Keras layout. */
+int msr_op_conv3x3_f32(const float* d_x, const float* d_w, const float* d_bias, float* d_y, int n, int r, int cin,
+                       int cout, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOONSR_H_ */

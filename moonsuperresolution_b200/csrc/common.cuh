@@ -1,0 +1,38 @@
+// Shared helpers for libmoonsr (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/moonsr.h"
+
+namespace msr {
+
+// thread-local last error text, surfaced through msr_last_error()
+void set_error(const std::string& s);
+int fail(int code, const std::string& s);
+
+#define MSR_CUDA_CHECK(expr)                                                                             \
+  do {                                                                                                   \
+    cudaError_t _e = (expr);                                                                             \
+    if (_e != cudaSuccess)                                                                               \
+      return ::msr::fail(MSR_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" __FILE__ ":" + \
+                                         std::to_string(__LINE__) + ")");                                \
+  } while (0)
+
+#define MSR_LAUNCH_CHECK() MSR_CUDA_CHECK(cudaGetLastError())
+
+#define MSR_REQUIRE(cond, msg)                                   \
+  do {                                                           \
+    if (!(cond)) return ::msr::fail(MSR_E_INVALID, (msg));       \
+  } while (0)
+
+static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// launch counter (per thread) so the generator can report gpu_launches
+extern thread_local int64_t g_launch_count;
+static inline void count_launch(int n = 1) { g_launch_count += n; }
+
+}  // namespace msr

@@ -1,0 +1,524 @@
+// 3x3 stride-1 SAME convolution as a tcgen05 / TMEM / TMA implicit GEMM for sm_100a (bf16 x bf16 -> fp32).
+//
+// Replaces the cuDNN calls behind every Conv2D(3, padding="same") of the SPADE generator:
+//   main convolutions   spade/models/blocks.py:19-26,30-36      (epilogue: + bias, + residual)
+//   gamma / beta convs  spade/models/spade.py:10-11,19-24       (epilogue: fused SPADE normalise-modulate-LeakyReLU)
+//
+// GEMM view: M = n*r*r output pixels, N = output columns, K = 9*cin with k = (ky*3 + kx)*cin + ci.
+//   * an M tile is 128 pixels = NB images x TH rows x TW columns of the NHWC tensor, so for tap (ky, kx) and channel
+//     block cb the A operand is ONE 4-D TMA box {64 ch, TW, TH, NB} at coordinates {64cb, w0+kx-1, h0+ky-1, b0}; the
+//     SAME-padding halo is the TMA's out-of-bounds zero fill (no im2col buffer, no predicates);
+//   * TMA writes the box as 128 rows of 128 bytes with the 128-byte swizzle = the canonical K-major UMMA layout;
+//   * B (weights, [N][K] K-major) is a 2-D TMA box {64, BN};
+//   * tcgen05.mma cta_group::1, M=128, N=BN, K=16, fp32 accumulators in TMEM, double buffered (2 x BN columns) so
+//     the epilogue of tile i overlaps the main loop of tile i+1;
+//   * persistent CTAs (one per SM), 6 warps: 0-3 epilogue (TMEM lane quarter = warp id), 4 TMA producer, 5 MMA issuer.
+#include <cuda.h>
+
+#include <mutex>
+
+#include "nn.cuh"
+
+namespace msr {
+
+namespace tc {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;                       // bf16 elements = 128 bytes = one swizzle row
+constexpr int kABytes = kBlockM * kBlockK * 2;    // 16 KB
+constexpr int kThreads = 192;
+
+template <int BN>
+struct Cfg {
+  static constexpr int kBBytes = BN * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kTmemCols = 2 * BN;        // two accumulator buffers
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct Geometry {
+  int n, r, cin, ncols;
+  int TW, TH, NB;            // tile = NB images x TH rows x TW cols (all powers of two, product 128)
+  int tiles_w, tiles_h, tiles_b, n_tiles_m, n_tiles_n;
+};
+
+struct EpiParams {
+  int mode;
+  const float* bias;
+  float* y;
+  const float* res;
+  int res_shift;
+  const float* sx;
+  int sx_shift;
+  const float* mean;
+  const float* rstd;
+  int samples_per_group;
+  float slope;
+  __nv_bfloat16* out_bf16;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must trap, never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("conv_tc: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrive once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte swizzle shared-memory matrix descriptor (tile rows of 128 bytes, 8-row atoms of 1024 bytes).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);        // start address, 16-byte units
+  d |= (uint64_t)1 << 16;                          // leading byte offset (unused for swizzled K-major; 1)
+  d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset: 8 rows * 128 B
+  d |= (uint64_t)1 << 46;                          // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=BN
+__host__ __device__ constexpr uint32_t make_idesc(int bn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+}
+
+// ---- the kernel -------------------------------------------------------------------------------------------------------
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                  const Geometry g, const EpiParams ep) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment for the 128-byte swizzle atoms
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + C::kStages * C::kStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C::kStages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * C::kStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * C::kStages + 2 + a); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + C::kStages * C::kStageBytes + 8 * (2 * C::kStages + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = g.n_tiles_m * g.n_tiles_n;
+  const int k_chunks_per_tap = g.cin / kBlockK;
+  const int k_chunks = 9 * k_chunks_per_tap;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+  }
+  if (warp == 5) tmem_alloc(smem_u32((const void*)tmem_slot), C::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto decode_tile = [&](int tile, int& b0, int& h0, int& w0, int& n0) {
+    const int mt = tile / g.n_tiles_n, nt = tile % g.n_tiles_n;
+    const int tw = mt % g.tiles_w, th = (mt / g.tiles_w) % g.tiles_h, tb = mt / (g.tiles_w * g.tiles_h);
+    b0 = tb * g.NB;
+    h0 = th * g.TH;
+    w0 = tw * g.TW;
+    n0 = nt * BN;
+  };
+
+  if (warp == 4) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int b0, h0, w0, n0;
+        decode_tile(tile, b0, h0, w0, n0);
+        for (int kc = 0; kc < k_chunks; ++kc) {
+          const int tap = kc / k_chunks_per_tap, cb = kc % k_chunks_per_tap;
+          const int ky = tap / 3, kx = tap % 3;
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = smem_base + stage * C::kStageBytes;
+          const uint32_t sb = sa + kABytes;
+          mbar_expect_tx(full_bar(stage), C::kStageBytes);
+          tma_load_4d(sa, &map_a, full_bar(stage), cb * kBlockK, w0 + kx - 1, h0 + ky - 1, b0);
+          tma_load_2d(sb, &map_b, full_bar(stage), tap * g.cin + cb * kBlockK, n0);
+          if (++stage == C::kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kc = 0; kc < k_chunks; ++kc) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * C::kStageBytes;
+          const uint64_t adesc = make_smem_desc(sa);
+          const uint64_t bdesc = make_smem_desc(sa + kABytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in 16-byte units
+            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kc | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));  // frees the smem stage when these MMAs retire
+          if (++stage == C::kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(tfull_bar(acc));       // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // ===================== epilogue warps 0..3 =====================
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int row = threadIdx.x;  // tile row == TMEM lane
+    const int wi = row % g.TW, hi = (row / g.TW) % g.TH, bi = row / (g.TW * g.TH);
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int b0, h0, w0, n0;
+      decode_tile(tile, b0, h0, w0, n0);
+      const int b = b0 + bi, h = h0 + hi, w = w0 + wi;
+      const bool row_ok = b < g.n;
+      const int64_t m = ((int64_t)b * g.r + h) * g.r + w;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN);
+      if (ep.mode == TC_EPI_BIAS_F32) {
+        int64_t res_row = 0;
+        if (ep.res != nullptr) {
+          const int rs = g.r >> ep.res_shift;
+          res_row = ((int64_t)b * rs + (h >> ep.res_shift)) * rs + (w >> ep.res_shift);
+        }
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(t_row + (uint32_t)c0, v);
+          tmem_ld_wait();
+          if (row_ok) {
+            const int col = n0 + c0;
+            float* dst = ep.y + m * g.ncols + col;
+            const float* rs_ptr = ep.res ? ep.res + res_row * g.ncols + col : nullptr;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 o;
+              o.x = __uint_as_float(v[j + 0]);
+              o.y = __uint_as_float(v[j + 1]);
+              o.z = __uint_as_float(v[j + 2]);
+              o.w = __uint_as_float(v[j + 3]);
+              if (ep.bias) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(ep.bias + col + j));
+                o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+              }
+              if (rs_ptr) {
+                const float4 rr = __ldg(reinterpret_cast<const float4*>(rs_ptr + j));
+                o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+              }
+              *reinterpret_cast<float4*>(dst + j) = o;
+            }
+          }
+        }
+      } else {
+        // fused SPADE: a 128-column group holds gamma (64) | beta (64) of channels ch0 .. ch0+63
+        const int Cc = g.ncols >> 1;
+        const int rs = g.r >> ep.sx_shift;
+        const int64_t x_row = ((int64_t)b * rs + (h >> ep.sx_shift)) * rs + (w >> ep.sx_shift);
+        const int grp = row_ok ? b / ep.samples_per_group : 0;
+#pragma unroll 1
+        for (int gc = 0; gc < BN; gc += 128) {
+          const int ch0 = ((n0 + gc) >> 7) * 64;
+#pragma unroll 1
+          for (int half = 0; half < 2; ++half) {
+            uint32_t ga[32], be[32];
+            tmem_ld32(t_row + (uint32_t)(gc + half * 32), ga);
+            tmem_ld32(t_row + (uint32_t)(gc + 64 + half * 32), be);
+            tmem_ld_wait();
+            if (row_ok) {
+              const int ch = ch0 + half * 32;
+              const float* xs = ep.sx + x_row * Cc + ch;
+              const float* mu = ep.mean + (int64_t)grp * Cc + ch;
+              const float* rsd = ep.rstd + (int64_t)grp * Cc + ch;
+              const float* bg = ep.bias + (n0 + gc) + half * 32;        // gamma bias
+              const float* bb = bg + 64;                                 // beta bias
+              __align__(16) __nv_bfloat16 o[32];
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 xv = __ldg(reinterpret_cast<const float4*>(xs + j));
+                const float4 m4 = __ldg(reinterpret_cast<const float4*>(mu + j));
+                const float4 r4 = __ldg(reinterpret_cast<const float4*>(rsd + j));
+                const float4 g4 = __ldg(reinterpret_cast<const float4*>(bg + j));
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(bb + j));
+                const float xa[4] = {xv.x, xv.y, xv.z, xv.w}, ma[4] = {m4.x, m4.y, m4.z, m4.w};
+                const float ra[4] = {r4.x, r4.y, r4.z, r4.w}, gba[4] = {g4.x, g4.y, g4.z, g4.w};
+                const float bba[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float gamma = __uint_as_float(ga[j + q]) + gba[q];
+                  const float beta = __uint_as_float(be[j + q]) + bba[q];
+                  float t = fmaf(gamma, (xa[q] - ma[q]) * ra[q], beta);
+                  t = t > 0.f ? t : t * ep.slope;
+                  o[j + q] = __float2bfloat16_rn(t);
+                }
+              }
+              uint4* dst = reinterpret_cast<uint4*>(ep.out_bf16 + m * Cc + ch);
+              const uint4* src = reinterpret_cast<const uint4*>(o);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) dst[q] = src[q];
+            }
+          }
+        }
+      }
+      // release the accumulator buffer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
+}  // namespace tc
+
+// ---- host side ----------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+struct ConvTC {
+  CUtensorMap map_a, map_b;
+  tc::Geometry g;
+  tc::EpiParams ep;
+  int bn;
+  int grid;
+};
+
+static int pow2_floor(int v) {
+  int p = 1;
+  while (p * 2 <= v) p *= 2;
+  return p;
+}
+
+int conv_tc_plan_create(ConvTC** out, const ConvTCArgs& a) {
+  MSR_REQUIRE(out && a.x && a.w, "conv_tc: null operand");
+  MSR_REQUIRE(a.n > 0 && a.r > 0 && (a.r & (a.r - 1)) == 0, "conv_tc: r must be a power of two");
+  MSR_REQUIRE(a.cin % 64 == 0 && a.cin >= 64, "conv_tc: cin must be a multiple of 64");
+  MSR_REQUIRE(a.ncols % 128 == 0, "conv_tc: output columns must be a multiple of 128");
+  MSR_REQUIRE((reinterpret_cast<uintptr_t>(a.x) & 127) == 0 && (reinterpret_cast<uintptr_t>(a.w) & 127) == 0,
+              "conv_tc: operands must be 128-byte aligned");
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail(MSR_E_CUDA, "conv_tc: cuTensorMapEncodeTiled entry point not available");
+  ConvTC* p = new ConvTC();
+  tc::Geometry& g = p->g;
+  g.n = a.n; g.r = a.r; g.cin = a.cin; g.ncols = a.ncols;
+  g.TW = std::min(a.r, 128);
+  g.TH = std::min(a.r, 128 / g.TW);
+  g.NB = 128 / (g.TW * g.TH);
+  g.tiles_w = a.r / g.TW;
+  g.tiles_h = a.r / g.TH;
+  g.tiles_b = ceil_div(a.n, g.NB);
+  g.n_tiles_m = g.tiles_w * g.tiles_h * g.tiles_b;
+  p->bn = (a.ncols % 256 == 0) ? 256 : 128;
+  g.n_tiles_n = a.ncols / p->bn;
+  (void)pow2_floor;
+
+  // A: 4-D NHWC tensor {C, W, H, N}
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)a.cin, (cuuint64_t)a.r, (cuuint64_t)a.r, (cuuint64_t)a.n};
+    cuuint64_t strides[3] = {(cuuint64_t)a.cin * 2, (cuuint64_t)a.r * a.cin * 2, (cuuint64_t)a.r * a.r * a.cin * 2};
+    cuuint32_t box[4] = {(cuuint32_t)tc::kBlockK, (cuuint32_t)g.TW, (cuuint32_t)g.TH, (cuuint32_t)g.NB};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&p->map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(a.x), dims, strides, box,
+                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      delete p;
+      return fail(MSR_E_CUDA, "conv_tc: cuTensorMapEncodeTiled(A) failed with " + std::to_string((int)r));
+    }
+  }
+  // B: 2-D weights {K, N}
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)9 * a.cin, (cuuint64_t)a.ncols};
+    cuuint64_t strides[1] = {(cuuint64_t)9 * a.cin * 2};
+    cuuint32_t box[2] = {(cuuint32_t)tc::kBlockK, (cuuint32_t)p->bn};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&p->map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(a.w), dims, strides, box,
+                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      delete p;
+      return fail(MSR_E_CUDA, "conv_tc: cuTensorMapEncodeTiled(B) failed with " + std::to_string((int)r));
+    }
+  }
+  tc::EpiParams& e = p->ep;
+  e.mode = a.epilogue;
+  e.bias = a.bias; e.y = a.y; e.res = a.res; e.res_shift = a.res_shift;
+  e.sx = a.sx; e.sx_shift = a.sx_shift; e.mean = a.mean; e.rstd = a.rstd;
+  e.samples_per_group = a.samples_per_group > 0 ? a.samples_per_group : 1;
+  e.slope = a.slope; e.out_bf16 = a.out_bf16;
+  if (a.epilogue == TC_EPI_BIAS_F32) {
+    if (!a.y) { delete p; return fail(MSR_E_INVALID, "conv_tc: y is null"); }
+  } else {
+    if (!(a.sx && a.mean && a.rstd && a.out_bf16 && a.bias)) {
+      delete p;
+      return fail(MSR_E_INVALID, "conv_tc: SPADE epilogue needs sx, mean, rstd, bias, out_bf16");
+    }
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  p->grid = std::min(g.n_tiles_m * g.n_tiles_n, sms);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e1 = cudaFuncSetAttribute(tc::conv3x3_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          tc::Cfg<128>::kSmemBytes);
+    cudaError_t e2 = cudaFuncSetAttribute(tc::conv3x3_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          tc::Cfg<256>::kSmemBytes);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) {
+      delete p;
+      return fail(MSR_E_CUDA, std::string("conv_tc: cudaFuncSetAttribute: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+    }
+    attr_set = true;
+  }
+  *out = p;
+  return MSR_OK;
+}
+
+int conv_tc_launch(const ConvTC* p, cudaStream_t st) {
+  MSR_REQUIRE(p, "conv_tc_launch: null plan");
+  if (p->bn == 256)
+    tc::conv3x3_tc_kernel<256><<<p->grid, tc::kThreads, tc::Cfg<256>::kSmemBytes, st>>>(p->map_a, p->map_b, p->g, p->ep);
+  else
+    tc::conv3x3_tc_kernel<128><<<p->grid, tc::kThreads, tc::Cfg<128>::kSmemBytes, st>>>(p->map_a, p->map_b, p->g, p->ep);
+  count_launch();
+  MSR_LAUNCH_CHECK();
+  return MSR_OK;
+}
+
+void conv_tc_plan_destroy(ConvTC* p) { delete p; }
+
+}  // namespace msr

@@ -1,0 +1,661 @@
+// Generator graphs: GauGAN / CNNSpade (encoder -> sampler -> SPADE generator) and the pix2pix U-Net, built from the
+// operators of nn_fp32.cu (fp32 mode) and conv_tc.cu (bf16 tensor-core mode).
+//
+// Reference: spade/models/networks.py:8-57, blocks.py:9-68, spade.py:5-25, sampling.py:5-17, model.py:564-567 and
+// 789-791, pix2pix.py:64-108.  Nearest x2 upsampling (networks.py:44-54) is never materialised: consumers index
+// (h >> 1, w >> 1), and the batch moments of an upsampled tensor equal those of its source.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "nn.cuh"
+
+using namespace msr;
+
+namespace {
+
+constexpr int kLatent = 256;
+constexpr int kHidden = 128;
+const int kRB[6] = {1024, 1024, 1024, 512, 256, 128};
+const int kEnc[5] = {64, 128, 256, 512, 512};
+const int kP2PDown[8] = {64, 128, 256, 512, 512, 512, 512, 512};
+const int kP2PUp[7] = {512, 512, 512, 512, 256, 128, 64};
+
+struct HostTensor {
+  std::vector<float> data;
+  std::vector<int64_t> shape;
+  int64_t numel() const {
+    int64_t n = 1;
+    for (auto s : shape) n *= s;
+    return n;
+  }
+};
+
+struct ActRef {
+  const void* ptr;
+  int64_t count;
+  int is_bf16;
+};
+
+struct SpadeW {
+  const float* conv_w = nullptr;   // [18][128]
+  const float* conv_b = nullptr;   // [128]
+  const float* gb_w = nullptr;     // fp32 [1152][2C]
+  const float* gb_b = nullptr;     // fp32 [2C] (gamma | beta)
+  const __nv_bfloat16* gb_wt = nullptr;  // bf16 [2C][1152], rows interleaved per 64 channels
+  const float* gb_bt = nullptr;          // fp32 [2C] in the interleaved order
+  int C = 0;
+};
+
+struct ConvW {
+  const float* w = nullptr;  // [9cin][cout]
+  const float* b = nullptr;
+  const __nv_bfloat16* wt = nullptr;  // bf16 [cout][9cin]
+  int cin = 0, cout = 0;
+};
+
+struct BlockW {
+  SpadeW s1, s2, s3;
+  ConvW c1, c2, c3;
+  bool learned = false;
+  int cin = 0, cout = 0;
+};
+
+}  // namespace
+
+struct msr_generator {
+  int arch = 0, I = 0, B = 0, maxG = 1, precision = 0;
+  bool finalized = false;
+  std::map<std::string, HostTensor> host;
+  std::vector<void*> allocs;
+  int64_t dev_bytes = 0;
+  int64_t last_launches = 0;
+  std::map<std::string, ActRef> acts;
+
+  // SPADE / CNN
+  const float* dense_w = nullptr; const float* dense_b = nullptr;
+  BlockW rb[6];
+  const float* out_w = nullptr; const float* out_b = nullptr;
+  const float* enc_w[5] = {}; const float* enc_g[5] = {}; const float* enc_bt[5] = {};
+  const float* enc_mean_w = nullptr; const float* enc_mean_b = nullptr;
+  const float* enc_var_w = nullptr; const float* enc_var_b = nullptr;
+  // pix2pix
+  const float* pd_w[8] = {}; const float* pd_mean[8] = {}; const float* pd_rstd[8] = {}; const float* pd_g[8] = {}; const float* pd_b[8] = {};
+  const float* pu_w[7] = {}; const float* pu_mean[7] = {}; const float* pu_rstd[7] = {}; const float* pu_g[7] = {}; const float* pu_b[7] = {};
+  const float* pl_w = nullptr; const float* pl_b = nullptr;
+
+  // workspace
+  float* enc_buf[2] = {};      // encoder ping-pong
+  float* enc_stats_mean = nullptr; float* enc_stats_rstd = nullptr;
+  float* lat_mean = nullptr; float* lat_var = nullptr; float* latent = nullptr;
+  float* dense_partial = nullptr; int64_t dense_partial_cap = 0;
+  double* stat_partial = nullptr;
+  float* xbuf[2] = {};         // residual stream ping-pong (fp32)
+  float* h1 = nullptr; float* s3 = nullptr;
+  float* st_mean[3] = {}; float* st_rstd[3] = {};   // stats of: x_prev, h1, (spare)
+  float* a_f32 = nullptr; float* gb_f32 = nullptr; float* act_f32 = nullptr;      // fp32 mode
+  __nv_bfloat16* a_bf16 = nullptr; __nv_bfloat16* act_bf16 = nullptr;               // bf16 mode
+  std::map<int, std::vector<ConvTC*>> plans;   // n_groups -> plans in launch order
+  // pix2pix workspace
+  float* cat[7] = {}; float* d8 = nullptr; float* p2p_raw = nullptr;
+
+  ~msr_generator() {
+    for (auto& kv : plans)
+      for (auto* p : kv.second) conv_tc_plan_destroy(p);
+    for (void* p : allocs) cudaFree(p);
+  }
+};
+
+namespace {
+
+int dev_alloc(msr_generator* g, void** out, int64_t bytes) {
+  if (bytes <= 0) bytes = 16;
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, (size_t)bytes);
+  if (e != cudaSuccess) return fail(MSR_E_NOMEM, std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e));
+  g->allocs.push_back(p);
+  g->dev_bytes += bytes;
+  *out = p;
+  return MSR_OK;
+}
+
+template <typename T>
+int upload(msr_generator* g, const std::vector<T>& h, const T** out) {
+  void* p = nullptr;
+  int rc = dev_alloc(g, &p, (int64_t)h.size() * sizeof(T));
+  if (rc) return rc;
+  MSR_CUDA_CHECK(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *out = reinterpret_cast<const T*>(p);
+  return MSR_OK;
+}
+
+int need(msr_generator* g, const std::string& name, std::vector<int64_t> shape, const HostTensor** out) {
+  auto it = g->host.find(name);
+  if (it == g->host.end()) return fail(MSR_E_STATE, "missing weight tensor " + name);
+  if (it->second.shape != shape) return fail(MSR_E_INVALID, "weight " + name + " has the wrong shape");
+  *out = &it->second;
+  return MSR_OK;
+}
+
+int upload_named(msr_generator* g, const std::string& name, std::vector<int64_t> shape, const float** out) {
+  const HostTensor* t;
+  int rc = need(g, name, shape, &t);
+  if (rc) return rc;
+  return upload(g, t->data, out);
+}
+
+uint16_t f2bf(float f) {  // round-to-nearest-even, like __float2bfloat16_rn
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+
+int upload_bf16(msr_generator* g, const std::vector<uint16_t>& h, const __nv_bfloat16** out) {
+  void* p = nullptr;
+  int rc = dev_alloc(g, &p, (int64_t)h.size() * 2);
+  if (rc) return rc;
+  MSR_CUDA_CHECK(cudaMemcpy(p, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
+  *out = reinterpret_cast<const __nv_bfloat16*>(p);
+  return MSR_OK;
+}
+
+int load_spade(msr_generator* g, const std::string& pre, int C, SpadeW* s) {
+  s->C = C;
+  int rc;
+  if ((rc = upload_named(g, pre + ".conv.kernel", {3, 3, 2, kHidden}, &s->conv_w))) return rc;
+  if ((rc = upload_named(g, pre + ".conv.bias", {kHidden}, &s->conv_b))) return rc;
+  const HostTensor *gw, *gbias, *bw, *bbias;
+  if ((rc = need(g, pre + ".conv_gamma.kernel", {3, 3, kHidden, C}, &gw))) return rc;
+  if ((rc = need(g, pre + ".conv_gamma.bias", {C}, &gbias))) return rc;
+  if ((rc = need(g, pre + ".conv_beta.kernel", {3, 3, kHidden, C}, &bw))) return rc;
+  if ((rc = need(g, pre + ".conv_beta.bias", {C}, &bbias))) return rc;
+  const int K = 9 * kHidden;
+  if (g->precision == MSR_PRECISION_FP32) {
+    std::vector<float> w((size_t)K * 2 * C), b(2 * C);
+    for (int k = 0; k < K; ++k) {
+      memcpy(&w[(size_t)k * 2 * C], &gw->data[(size_t)k * C], sizeof(float) * C);
+      memcpy(&w[(size_t)k * 2 * C + C], &bw->data[(size_t)k * C], sizeof(float) * C);
+    }
+    memcpy(&b[0], gbias->data.data(), sizeof(float) * C);
+    memcpy(&b[C], bbias->data.data(), sizeof(float) * C);
+    if ((rc = upload(g, w, &s->gb_w))) return rc;
+    if ((rc = upload(g, b, &s->gb_b))) return rc;
+  } else {
+    // rows: per block j of 64 channels, 64 gamma rows then 64 beta rows; each row K-major
+    std::vector<uint16_t> wt((size_t)2 * C * K);
+    std::vector<float> bt(2 * C);
+    for (int c = 0; c < C; ++c) {
+      const int j = c / 64, t = c % 64;
+      const size_t rg = (size_t)(128 * j + t), rbeta = (size_t)(128 * j + 64 + t);
+      for (int k = 0; k < K; ++k) {
+        wt[rg * K + k] = f2bf(gw->data[(size_t)k * C + c]);
+        wt[rbeta * K + k] = f2bf(bw->data[(size_t)k * C + c]);
+      }
+      bt[rg] = gbias->data[c];
+      bt[rbeta] = bbias->data[c];
+    }
+    if ((rc = upload_bf16(g, wt, &s->gb_wt))) return rc;
+    if ((rc = upload(g, bt, &s->gb_bt))) return rc;
+  }
+  return MSR_OK;
+}
+
+int load_conv(msr_generator* g, const std::string& pre, int cin, int cout, ConvW* c) {
+  c->cin = cin;
+  c->cout = cout;
+  const HostTensor *w, *b;
+  int rc;
+  if ((rc = need(g, pre + ".kernel", {3, 3, cin, cout}, &w))) return rc;
+  if ((rc = need(g, pre + ".bias", {cout}, &b))) return rc;
+  if ((rc = upload(g, b->data, &c->b))) return rc;
+  if (g->precision == MSR_PRECISION_FP32) return upload(g, w->data, &c->w);
+  const int K = 9 * cin;
+  std::vector<uint16_t> wt((size_t)cout * K);
+  for (int k = 0; k < K; ++k)
+    for (int co = 0; co < cout; ++co) wt[(size_t)co * K + k] = f2bf(w->data[(size_t)k * cout + co]);
+  return upload_bf16(g, wt, &c->wt);
+}
+
+template <typename T>
+int ws(msr_generator* g, T** out, int64_t count) {
+  void* p = nullptr;
+  int rc = dev_alloc(g, &p, count * (int64_t)sizeof(T));
+  if (rc) return rc;
+  *out = reinterpret_cast<T*>(p);
+  return MSR_OK;
+}
+
+int finalize_spade(msr_generator* g) {
+  const int I = g->I, sw = I / 64;
+  const int64_t N = (int64_t)g->B * g->maxG;
+  int rc;
+  if ((rc = upload_named(g, "gen.dense.kernel", {kLatent, 16 * sw * sw * 64}, &g->dense_w))) return rc;
+  if ((rc = upload_named(g, "gen.dense.bias", {16 * sw * sw * 64}, &g->dense_b))) return rc;
+  int cin = 1024;
+  for (int k = 0; k < 6; ++k) {
+    BlockW& b = g->rb[k];
+    const int cout = kRB[k];
+    b.cin = cin;
+    b.cout = cout;
+    b.learned = cin != cout;
+    const std::string pre = "gen.rb" + std::to_string(k + 1);
+    if ((rc = load_spade(g, pre + ".spade_1", cin, &b.s1))) return rc;
+    if ((rc = load_spade(g, pre + ".spade_2", cout, &b.s2))) return rc;
+    if ((rc = load_conv(g, pre + ".conv_1", cin, cout, &b.c1))) return rc;
+    if ((rc = load_conv(g, pre + ".conv_2", cout, cout, &b.c2))) return rc;
+    if (b.learned) {
+      if ((rc = load_spade(g, pre + ".spade_3", cin, &b.s3))) return rc;
+      if ((rc = load_conv(g, pre + ".conv_3", cin, cout, &b.c3))) return rc;
+    }
+    cin = cout;
+  }
+  if ((rc = upload_named(g, "gen.out.kernel", {4, 4, 128, 1}, &g->out_w))) return rc;
+  if ((rc = upload_named(g, "gen.out.bias", {1}, &g->out_b))) return rc;
+  int ec = 2;
+  for (int k = 0; k < 5; ++k) {
+    const std::string pre = "enc.down" + std::to_string(k + 1);
+    if ((rc = upload_named(g, pre + ".kernel", {3, 3, ec, kEnc[k]}, &g->enc_w[k]))) return rc;
+    if (k > 0) {
+      if ((rc = upload_named(g, pre + ".in_gamma", {kEnc[k]}, &g->enc_g[k]))) return rc;
+      if ((rc = upload_named(g, pre + ".in_beta", {kEnc[k]}, &g->enc_bt[k]))) return rc;
+    }
+    ec = kEnc[k];
+  }
+  const int64_t feat = (int64_t)(I / 32) * (I / 32) * 512;
+  if ((rc = upload_named(g, "enc.mean.kernel", {feat, kLatent}, &g->enc_mean_w))) return rc;
+  if ((rc = upload_named(g, "enc.mean.bias", {kLatent}, &g->enc_mean_b))) return rc;
+  if ((rc = upload_named(g, "enc.variance.kernel", {feat, kLatent}, &g->enc_var_w))) return rc;
+  if ((rc = upload_named(g, "enc.variance.bias", {kLatent}, &g->enc_var_b))) return rc;
+
+  // ---- workspace
+  const int64_t half = (int64_t)(I / 2) * (I / 2);
+  // encoder: largest activation is the first block's output (I/2)^2 * 64
+  if ((rc = ws(g, &g->enc_buf[0], N * half * 64))) return rc;
+  if ((rc = ws(g, &g->enc_buf[1], N * (half / 4) * 128))) return rc;
+  if ((rc = ws(g, &g->enc_stats_mean, N * 512))) return rc;
+  if ((rc = ws(g, &g->enc_stats_rstd, N * 512))) return rc;
+  if ((rc = ws(g, &g->lat_mean, N * kLatent))) return rc;
+  if ((rc = ws(g, &g->lat_var, N * kLatent))) return rc;
+  if ((rc = ws(g, &g->latent, N * kLatent))) return rc;
+  g->dense_partial_cap = std::max<int64_t>(64 * N * kLatent, N * 16 * sw * sw * 64);
+  if ((rc = ws(g, &g->dense_partial, g->dense_partial_cap))) return rc;
+  if ((rc = ws(g, &g->stat_partial, (int64_t)std::max<int64_t>(N, g->maxG) * kStatSplit * 1024 * 2))) return rc;
+  const int64_t stream_elems = N * half * 128;  // max over blocks of r^2 * cout (and r_prev^2 * cin)
+  if ((rc = ws(g, &g->xbuf[0], std::max<int64_t>(stream_elems, N * sw * sw * 1024)))) return rc;
+  if ((rc = ws(g, &g->xbuf[1], std::max<int64_t>(stream_elems, N * sw * sw * 1024)))) return rc;
+  if ((rc = ws(g, &g->h1, stream_elems))) return rc;
+  if ((rc = ws(g, &g->s3, stream_elems))) return rc;
+  for (int i = 0; i < 3; ++i) {
+    if ((rc = ws(g, &g->st_mean[i], (int64_t)g->maxG * 1024))) return rc;
+    if ((rc = ws(g, &g->st_rstd[i], (int64_t)g->maxG * 1024))) return rc;
+  }
+  if (g->precision == MSR_PRECISION_FP32) {
+    if ((rc = ws(g, &g->a_f32, N * half * kHidden))) return rc;
+    if ((rc = ws(g, &g->gb_f32, N * half * 512))) return rc;   // max r^2 * 2C = (I/2)^2 * 512
+    if ((rc = ws(g, &g->act_f32, N * half * 256))) return rc;  // max r^2 * C
+  } else {
+    if ((rc = ws(g, &g->a_bf16, N * half * kHidden))) return rc;
+    if ((rc = ws(g, &g->act_bf16, N * half * 256))) return rc;
+  }
+  return MSR_OK;
+}
+
+int finalize_pix2pix(msr_generator* g) {
+  const int64_t N = (int64_t)g->B * g->maxG;
+  int rc;
+  auto bn = [&](const std::string& pre, int c, const float** mean, const float** rstd, const float** gamma,
+                const float** beta) -> int {
+    const HostTensor *mm, *mv;
+    int r;
+    if ((r = upload_named(g, pre + ".bn.gamma", {c}, gamma))) return r;
+    if ((r = upload_named(g, pre + ".bn.beta", {c}, beta))) return r;
+    if ((r = need(g, pre + ".bn.moving_mean", {c}, &mm))) return r;
+    if ((r = need(g, pre + ".bn.moving_variance", {c}, &mv))) return r;
+    std::vector<float> rs(c);
+    for (int i = 0; i < c; ++i) rs[i] = (float)(1.0 / sqrt((double)mv->data[i] + 1e-3));  // Keras BN eps (App. B.7)
+    if ((r = upload(g, mm->data, mean))) return r;
+    return upload(g, rs, rstd);
+  };
+  int cin = 2;
+  for (int k = 0; k < 8; ++k) {
+    const std::string pre = "p2p.down" + std::to_string(k + 1);
+    if ((rc = upload_named(g, pre + ".kernel", {4, 4, cin, kP2PDown[k]}, &g->pd_w[k]))) return rc;
+    if (k > 0 && (rc = bn(pre, kP2PDown[k], &g->pd_mean[k], &g->pd_rstd[k], &g->pd_g[k], &g->pd_b[k]))) return rc;
+    cin = kP2PDown[k];
+  }
+  auto load_convT = [&](const std::string& name, int cout, int cin_, const float** out) -> int {
+    const HostTensor* w;
+    int r = need(g, name, {4, 4, cout, cin_}, &w);
+    if (r) return r;
+    std::vector<float> t((size_t)16 * cin_ * cout);
+    for (int tap = 0; tap < 16; ++tap)
+      for (int co = 0; co < cout; ++co)
+        for (int ci = 0; ci < cin_; ++ci)
+          t[((size_t)tap * cin_ + ci) * cout + co] = w->data[((size_t)tap * cout + co) * cin_ + ci];
+    return upload(g, t, out);
+  };
+  for (int k = 0; k < 7; ++k) {
+    const std::string pre = "p2p.up" + std::to_string(k + 1);
+    if ((rc = load_convT(pre + ".kernel", kP2PUp[k], cin, &g->pu_w[k]))) return rc;
+    if ((rc = bn(pre, kP2PUp[k], &g->pu_mean[k], &g->pu_rstd[k], &g->pu_g[k], &g->pu_b[k]))) return rc;
+    cin = kP2PUp[k] + kP2PDown[6 - k];
+  }
+  if ((rc = load_convT("p2p.last.kernel", 1, cin, &g->pl_w))) return rc;
+  if ((rc = upload_named(g, "p2p.last.bias", {1}, &g->pl_b))) return rc;
+  // concat buffers: cat[k] (k = 0..6) holds [up_{k+1} | down_{7-k}] at spatial 2^(k+1)
+  for (int k = 0; k < 7; ++k) {
+    const int s = 2 << k;
+    if ((rc = ws(g, &g->cat[k], N * s * s * (kP2PUp[k] + kP2PDown[6 - k])))) return rc;
+  }
+  if ((rc = ws(g, &g->d8, N * 512))) return rc;
+  return MSR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+struct Fwd {
+  msr_generator* g;
+  cudaStream_t st;
+  int groups;
+  int64_t N;
+  std::vector<ConvTC*>* plans = nullptr;
+  size_t plan_cursor = 0;
+  bool building = false;
+};
+
+int tc_conv(Fwd& f, const ConvTCArgs& a) {
+  if (f.building) {
+    ConvTC* p = nullptr;
+    int rc = conv_tc_plan_create(&p, a);
+    if (rc) return rc;
+    f.plans->push_back(p);
+  }
+  MSR_REQUIRE(f.plan_cursor < f.plans->size(), "internal: tensor-core plan list out of sync");
+  return conv_tc_launch((*f.plans)[f.plan_cursor++], f.st);
+}
+
+// SPADE + LeakyReLU(0.2): result in g->act_f32 (fp32 mode) or g->act_bf16 (bf16 mode)
+int run_spade(Fwd& f, const SpadeW& s, const float* source, const float* x, int x_shift, const float* mean,
+              const float* rstd, int r) {
+  msr_generator* g = f.g;
+  const int n = (int)f.N, I = g->I;
+  int rc;
+  if (g->precision == MSR_PRECISION_FP32) {
+    ConvF32 c;
+    c.x = source; c.w = s.conv_w; c.bias = s.conv_b; c.y = g->a_f32;
+    c.n = n; c.Hs = I; c.Ws = I; c.cin = 2; c.ldx = 2; c.Hv = r; c.Wv = r;
+    c.in_mul = I / r; c.in_add = (I / r) / 2; c.in_shift = 0;     // tf.image.resize nearest, half-pixel centres (App. B.3)
+    c.Ho = r; c.Wo = r; c.cout = kHidden; c.ldy = kHidden; c.act = ACT_RELU;
+    if ((rc = conv_f32(c, f.st))) return rc;
+    ConvF32 d;
+    d.x = g->a_f32; d.w = s.gb_w; d.bias = s.gb_b; d.y = g->gb_f32;
+    d.n = n; d.Hs = r; d.Ws = r; d.cin = kHidden; d.ldx = kHidden; d.Hv = r; d.Wv = r;
+    d.Ho = r; d.Wo = r; d.cout = 2 * s.C; d.ldy = 2 * s.C;
+    if ((rc = conv_f32(d, f.st))) return rc;
+    return spade_modulate_f32(g->gb_f32, x, x_shift, mean, rstd, g->act_f32, n, r, s.C, g->B, 0.2f, f.st);
+  }
+  if ((rc = mask_conv_bf16(source, I, s.conv_w, s.conv_b, g->a_bf16, n, r, f.st))) return rc;
+  ConvTCArgs a;
+  a.x = g->a_bf16; a.w = s.gb_wt; a.n = n; a.r = r; a.cin = kHidden; a.ncols = 2 * s.C;
+  a.epilogue = TC_EPI_SPADE_BF16; a.bias = s.gb_bt; a.sx = x; a.sx_shift = x_shift; a.mean = mean; a.rstd = rstd;
+  a.samples_per_group = g->B; a.slope = 0.2f; a.out_bf16 = g->act_bf16;
+  return tc_conv(f, a);
+}
+
+// main 3x3 conv on the SPADE output (act buffer) -> y (fp32), optional residual
+int run_conv(Fwd& f, const ConvW& w, int r, float* y, const float* res, int res_shift) {
+  msr_generator* g = f.g;
+  const int n = (int)f.N;
+  if (g->precision == MSR_PRECISION_FP32) {
+    ConvF32 c;
+    c.x = g->act_f32; c.w = w.w; c.bias = w.b; c.y = y;
+    c.n = n; c.Hs = r; c.Ws = r; c.cin = w.cin; c.ldx = w.cin; c.Hv = r; c.Wv = r;
+    c.Ho = r; c.Wo = r; c.cout = w.cout; c.ldy = w.cout;
+    c.res = res; c.res_shift = res_shift; c.ldres = w.cout;
+    return conv_f32(c, f.st);
+  }
+  ConvTCArgs a;
+  a.x = g->act_bf16; a.w = w.wt; a.n = n; a.r = r; a.cin = w.cin; a.ncols = w.cout;
+  a.epilogue = TC_EPI_BIAS_F32; a.bias = w.b; a.y = y; a.res = res; a.res_shift = res_shift;
+  return tc_conv(f, a);
+}
+
+int forward_spade(Fwd& f, const float* source, const float* eps, float* out) {
+  msr_generator* g = f.g;
+  const int I = g->I, sw = I / 64, n = (int)f.N;
+  cudaStream_t st = f.st;
+  int rc;
+  // ---- encoder (networks.py:8-34): conv3x3 s2, SAME pad (0, 1) on even inputs (App. B.2)
+  const float* ex = source;
+  int ecin = 2, er = I;
+  for (int k = 0; k < 5; ++k) {
+    float* ey = g->enc_buf[k & 1];
+    ConvF32 c;
+    c.x = ex; c.w = g->enc_w[k]; c.y = ey;
+    c.n = n; c.Hs = er; c.Ws = er; c.cin = ecin; c.ldx = ecin; c.Hv = er; c.Wv = er;
+    c.Ho = er / 2; c.Wo = er / 2; c.cout = kEnc[k]; c.ldy = kEnc[k];
+    c.stride = 2; c.pad_t = 0; c.pad_l = 0;
+    if (k == 0) { c.act = ACT_LRELU; c.act_slope = 0.2f; }
+    if ((rc = conv_f32(c, st))) return rc;
+    er /= 2;
+    if (k > 0) {  // tfa InstanceNormalization (eps 1e-3, per sample and channel) + LeakyReLU(0.2), blocks.py:62-65
+      const int64_t rows = (int64_t)er * er;
+      if ((rc = channel_stats_f32(ey, kEnc[k], n, rows, kEnc[k], 1e-3f, g->stat_partial, g->enc_stats_mean,
+                                  g->enc_stats_rstd, st))) return rc;
+      if ((rc = affine_act_f32(ey, kEnc[k], g->enc_stats_mean, g->enc_stats_rstd, g->enc_g[k], g->enc_bt[k], ey,
+                               kEnc[k], (int64_t)n * rows, kEnc[k], rows, ACT_LRELU, 0.2f, st))) return rc;
+    }
+    ex = ey;
+    ecin = kEnc[k];
+  }
+  const int feat = er * er * 512;
+  if ((rc = dense_f32(ex, g->enc_mean_w, g->enc_mean_b, g->lat_mean, n, feat, kLatent, g->dense_partial,
+                      g->dense_partial_cap, st))) return rc;
+  if ((rc = dense_f32(ex, g->enc_var_w, g->enc_var_b, g->lat_var, n, feat, kLatent, g->dense_partial,
+                      g->dense_partial_cap, st))) return rc;
+  // ---- sampler (sampling.py:11-17) or mean + variance (model.py:789-791)
+  if ((rc = sampler_f32(g->lat_mean, g->lat_var, g->arch == MSR_ARCH_SPADE ? eps : nullptr, g->latent,
+                        (int64_t)n * kLatent, st))) return rc;
+  g->acts["enc.mean"] = {g->lat_mean, (int64_t)n * kLatent, 0};
+  g->acts["enc.variance"] = {g->lat_var, (int64_t)n * kLatent, 0};
+  g->acts["latent"] = {g->latent, (int64_t)n * kLatent, 0};
+  // ---- generator (networks.py:37-57)
+  float* x = g->xbuf[0];
+  if ((rc = dense_f32(g->latent, g->dense_w, g->dense_b, x, n, kLatent, sw * sw * 1024, g->dense_partial,
+                      g->dense_partial_cap, st))) return rc;
+  g->acts["x0"] = {x, (int64_t)n * sw * sw * 1024, 0};
+  int r = sw, x_shift = 0;
+  // statistics of the block input (shared by spade_1 and spade_3; invariant under nearest upsampling)
+  if ((rc = channel_stats_f32(x, 1024, f.groups, (int64_t)g->B * sw * sw, 1024, 1e-5f, g->stat_partial, g->st_mean[0],
+                              g->st_rstd[0], st))) return rc;
+  for (int k = 0; k < 6; ++k) {
+    const BlockW& b = g->rb[k];
+    float* y = g->xbuf[(k + 1) & 1];
+    const int64_t rows = (int64_t)g->B * r * r;
+    // x = conv_1(lrelu(spade_1(in)))                                  blocks.py:29-30
+    if ((rc = run_spade(f, b.s1, source, x, x_shift, g->st_mean[0], g->st_rstd[0], r))) return rc;
+    if ((rc = run_conv(f, b.c1, r, g->h1, nullptr, 0))) return rc;
+    if ((rc = channel_stats_f32(g->h1, b.cout, f.groups, rows, b.cout, 1e-5f, g->stat_partial, g->st_mean[1],
+                                g->st_rstd[1], st))) return rc;
+    const float* res = x;
+    int res_shift = x_shift;
+    if (b.learned) {  // skip = conv_3(lrelu(spade_3(in)))             blocks.py:34-36
+      if ((rc = run_spade(f, b.s3, source, x, x_shift, g->st_mean[0], g->st_rstd[0], r))) return rc;
+      if ((rc = run_conv(f, b.c3, r, g->s3, nullptr, 0))) return rc;
+      res = g->s3;
+      res_shift = 0;
+    }
+    // x = conv_2(lrelu(spade_2(x))); out = skip + x                   blocks.py:31-32,38
+    if ((rc = run_spade(f, b.s2, source, g->h1, 0, g->st_mean[1], g->st_rstd[1], r))) return rc;
+    if ((rc = run_conv(f, b.c2, r, y, res, res_shift))) return rc;
+    g->acts["rb" + std::to_string(k + 1) + ".h1"] = {g->h1, (int64_t)n * r * r * b.cout, 0};
+    g->acts["rb" + std::to_string(k + 1) + ".out"] = {y, (int64_t)n * r * r * b.cout, 0};
+    if (k < 5) {
+      if ((rc = channel_stats_f32(y, b.cout, f.groups, rows, b.cout, 1e-5f, g->stat_partial, g->st_mean[0],
+                                  g->st_rstd[0], st))) return rc;
+    }
+    x = y;
+    x_shift = 1;  // UpSampling2D((2, 2)) after every block (networks.py:44-54), fused into the consumers
+    r *= 2;
+  }
+  // leaky_relu(0.2) + Conv2D(1, 4, 'same') on the upsampled rb6 output (networks.py:54-56)
+  if ((rc = final_conv_f32(x, g->out_w, g->out_b, out, n, r / 2, st))) return rc;
+  g->acts["out"] = {out, (int64_t)n * I * I, 0};
+  return MSR_OK;
+}
+
+int forward_pix2pix(Fwd& f, const float* source, float* out) {
+  msr_generator* g = f.g;
+  const int n = (int)f.N;
+  cudaStream_t st = f.st;
+  int rc;
+  // down path (pix2pix.py:64-72, 97-101): Conv4x4 s2 SAME (pad 1,1) no bias, BN (not first), LeakyReLU(0.3)
+  const float* x = source;
+  int cin = 2, ldx = 2, s = 256;
+  for (int k = 0; k < 8; ++k) {
+    const int cout = kP2PDown[k];
+    float* y;
+    int ldy;
+    if (k < 7) {  // skip d_{k+1} lives in cat[6-k] behind the up-sampled channels
+      y = g->cat[6 - k] + kP2PUp[6 - k];
+      ldy = kP2PUp[6 - k] + cout;
+    } else {
+      y = g->d8;
+      ldy = cout;
+    }
+    ConvF32 c;
+    c.x = x; c.w = g->pd_w[k]; c.y = y;
+    c.n = n; c.Hs = s; c.Ws = s; c.cin = cin; c.ldx = ldx; c.Hv = s; c.Wv = s;
+    c.Ho = s / 2; c.Wo = s / 2; c.cout = cout; c.ldy = ldy;
+    c.kh = 4; c.kw = 4; c.stride = 2; c.pad_t = 1; c.pad_l = 1;
+    if (k == 0) { c.act = ACT_LRELU; c.act_slope = 0.3f; }
+    if ((rc = conv_f32(c, st))) return rc;
+    s /= 2;
+    if (k > 0) {
+      const int64_t M = (int64_t)n * s * s;
+      if ((rc = affine_act_f32(y, ldy, g->pd_mean[k], g->pd_rstd[k], g->pd_g[k], g->pd_b[k], y, ldy, M, cout, M,
+                               ACT_LRELU, 0.3f, st))) return rc;
+    }
+    x = y; cin = cout; ldx = ldy;
+  }
+  // up path (pix2pix.py:74-86, 103-106): ConvT4x4 s2 SAME no bias, BN, ReLU, then Concatenate([up, skip])
+  for (int k = 0; k < 7; ++k) {
+    const int cout = kP2PUp[k];
+    const int ldy = cout + kP2PDown[6 - k];
+    float* y = g->cat[k];
+    ConvF32 c;
+    c.x = x; c.w = g->pu_w[k]; c.y = y;
+    c.n = n; c.Hs = s; c.Ws = s; c.cin = cin; c.ldx = ldx; c.Hv = s; c.Wv = s;
+    c.Ho = 2 * s; c.Wo = 2 * s; c.cout = cout; c.ldy = ldy;
+    c.kh = 4; c.kw = 4; c.stride = 2; c.pad_t = 1; c.pad_l = 1; c.transposed = 1;
+    if ((rc = conv_f32(c, st))) return rc;
+    s *= 2;
+    const int64_t M = (int64_t)n * s * s;
+    if ((rc = affine_act_f32(y, ldy, g->pu_mean[k], g->pu_rstd[k], g->pu_g[k], g->pu_b[k], y, ldy, M, cout, M,
+                             ACT_RELU, 0.f, st))) return rc;
+    x = y; cin = ldy; ldx = ldy;
+  }
+  ConvF32 c;
+  c.x = x; c.w = g->pl_w; c.bias = g->pl_b; c.y = out;
+  c.n = n; c.Hs = s; c.Ws = s; c.cin = cin; c.ldx = ldx; c.Hv = s; c.Wv = s;
+  c.Ho = 2 * s; c.Wo = 2 * s; c.cout = 1; c.ldy = 1;
+  c.kh = 4; c.kw = 4; c.stride = 2; c.pad_t = 1; c.pad_l = 1; c.transposed = 1; c.act = ACT_TANH;
+  if ((rc = conv_f32(c, st))) return rc;
+  g->acts["out"] = {out, (int64_t)n * 256 * 256, 0};
+  return MSR_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" int msr_generator_create(msr_generator** out, int arch, int image_size, int batch_size, int max_groups,
+                                    int precision) {
+  MSR_REQUIRE(out, "msr_generator_create: null out");
+  MSR_REQUIRE(arch == MSR_ARCH_SPADE || arch == MSR_ARCH_CNN || arch == MSR_ARCH_PIX2PIX, "unknown arch");
+  MSR_REQUIRE(precision == MSR_PRECISION_FP32 || precision == MSR_PRECISION_BF16, "unknown precision");
+  MSR_REQUIRE(batch_size > 0 && max_groups > 0, "batch_size and max_groups must be positive");
+  if (arch == MSR_ARCH_PIX2PIX) {
+    MSR_REQUIRE(image_size == 256, "pix2pix is fixed to 256x256 inputs (pix2pix.py:7)");
+    MSR_REQUIRE(precision == MSR_PRECISION_FP32, "pix2pix: only the fp32 path is implemented");
+  } else {
+    MSR_REQUIRE(image_size >= 64 && image_size % 64 == 0, "image_size must be a multiple of 64 (networks.py:40)");
+    if (precision == MSR_PRECISION_BF16)
+      MSR_REQUIRE((image_size & (image_size - 1)) == 0, "bf16 path needs a power-of-two image_size");
+  }
+  msr_generator* g = new msr_generator();
+  g->arch = arch; g->I = image_size; g->B = batch_size; g->maxG = max_groups; g->precision = precision;
+  *out = g;
+  return MSR_OK;
+}
+
+extern "C" int msr_generator_set_weight(msr_generator* g, const char* name, const float* h_data, const int64_t* shape,
+                                        int ndim) {
+  MSR_REQUIRE(g && name && h_data && shape && ndim > 0 && ndim <= 4, "msr_generator_set_weight: bad arguments");
+  if (g->finalized) return fail(MSR_E_STATE, "msr_generator_set_weight after finalize");
+  HostTensor t;
+  t.shape.assign(shape, shape + ndim);
+  const int64_t n = t.numel();
+  MSR_REQUIRE(n > 0, "empty tensor");
+  t.data.assign(h_data, h_data + n);
+  g->host[name] = std::move(t);
+  return MSR_OK;
+}
+
+extern "C" int msr_generator_finalize(msr_generator* g) {
+  MSR_REQUIRE(g, "null generator");
+  if (g->finalized) return fail(MSR_E_STATE, "already finalized");
+  int rc = (g->arch == MSR_ARCH_PIX2PIX) ? finalize_pix2pix(g) : finalize_spade(g);
+  if (rc) return rc;
+  MSR_CUDA_CHECK(cudaDeviceSynchronize());
+  g->host.clear();
+  g->finalized = true;
+  return MSR_OK;
+}
+
+extern "C" int msr_generator_forward(msr_generator* g, const float* d_source, const float* d_eps, float* d_out,
+                                     int n_groups, void* stream) {
+  MSR_REQUIRE(g && d_source && d_out, "msr_generator_forward: null pointer");
+  if (!g->finalized) return fail(MSR_E_STATE, "forward before finalize");
+  MSR_REQUIRE(n_groups >= 1 && n_groups <= g->maxG, "n_groups out of range");
+  if (g->arch == MSR_ARCH_SPADE) MSR_REQUIRE(d_eps, "GauGAN forward needs eps (sampling.py:13-16)");
+  Fwd f;
+  f.g = g; f.st = (cudaStream_t)stream; f.groups = n_groups; f.N = (int64_t)n_groups * g->B;
+  if (g->precision == MSR_PRECISION_BF16) {
+    auto it = g->plans.find(n_groups);
+    f.building = (it == g->plans.end());
+    f.plans = &g->plans[n_groups];
+  }
+  const int64_t before = g_launch_count;
+  int rc = (g->arch == MSR_ARCH_PIX2PIX) ? forward_pix2pix(f, d_source, d_out) : forward_spade(f, d_source, d_eps, d_out);
+  g->last_launches = g_launch_count - before;
+  if (rc && f.building) {  // never keep a half-built plan list
+    for (auto* p : *f.plans) conv_tc_plan_destroy(p);
+    g->plans.erase(n_groups);
+  }
+  return rc;
+}
+
+extern "C" int64_t msr_generator_last_launch_count(const msr_generator* g) { return g ? g->last_launches : -1; }
+extern "C" int64_t msr_generator_device_bytes(const msr_generator* g) { return g ? g->dev_bytes : -1; }
+
+extern "C" int msr_generator_read_activation(msr_generator* g, const char* name, float* h_dst, int64_t capacity,
+                                             int64_t* count) {
+  MSR_REQUIRE(g && name && count, "msr_generator_read_activation: bad arguments");
+  auto it = g->acts.find(name);
+  if (it == g->acts.end()) return fail(MSR_E_INVALID, std::string("unknown activation ") + name);
+  *count = it->second.count;
+  if (!h_dst) return MSR_OK;
+  MSR_REQUIRE(capacity >= it->second.count, "destination too small");
+  MSR_CUDA_CHECK(cudaDeviceSynchronize());
+  MSR_CUDA_CHECK(cudaMemcpy(h_dst, it->second.ptr, it->second.count * sizeof(float), cudaMemcpyDeviceToHost));
+  return MSR_OK;
+}
+
+extern "C" int msr_generator_destroy(msr_generator* g) {
+  delete g;
+  return MSR_OK;
+}

@@ -1,0 +1,92 @@
+// Device-side operator launchers shared by the generator graphs (declarations).
+#pragma once
+#include "common.cuh"
+
+namespace msr {
+
+enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_LRELU = 2, ACT_TANH = 3 };
+
+// Generic NHWC convolution on CUDA cores, fp32 (implicit GEMM, 64x64x16 tiles).
+struct ConvF32 {
+  const float* x = nullptr;  // stored input [n][Hs][Ws][ldx]
+  const float* w = nullptr;  // [kh*kw*cin][cout] row-major, k = (ky*kw + kx)*cin + ci
+  const float* bias = nullptr;
+  float* y = nullptr;        // [n][Ho][Wo][ldy]
+  int n = 0, Hs = 0, Ws = 0, cin = 0, ldx = 0;
+  int Hv = 0, Wv = 0;        // virtual input size; stored index = (v * in_mul + in_add) >> in_shift
+  int in_mul = 1, in_add = 0, in_shift = 0;
+  float in_slope = 1.f;      // leaky-relu slope applied to the input on load (1 = identity)
+  int Ho = 0, Wo = 0, cout = 0, ldy = 0;
+  int kh = 3, kw = 3, stride = 1, pad_t = 1, pad_l = 1;
+  int transposed = 0;        // 1: stride-`stride` transposed convolution (gather form)
+  int act = ACT_NONE;
+  float act_slope = 0.f;
+  const float* res = nullptr;  // optional residual [n][Ho >> res_shift][Wo >> res_shift][ldres]
+  int res_shift = 0, ldres = 0;
+};
+int conv_f32(const ConvF32& p, cudaStream_t st);
+
+// Per-(group, channel) mean and 1/sqrt(var + eps) over `rows` consecutive rows of x[groups*rows][ld] (biased variance).
+// `partial` is scratch of groups * kStatSplit * C * 2 doubles.
+constexpr int kStatSplit = 64;
+int channel_stats_f32(const float* x, int ld, int groups, int64_t rows, int C, float eps, double* partial, float* mean,
+                      float* rstd, cudaStream_t st);
+int channel_stats_bf16(const __nv_bfloat16* x, int ld, int groups, int64_t rows, int C, float eps, double* partial,
+                       float* mean, float* rstd, cudaStream_t st);
+
+// SPADE modulation (spade.py:21-24 + blocks.py:30-34): out[m][c] = lrelu(gamma * (x[src(m)][c] - mean) * rstd + beta)
+// gb [M][2C] = gamma | beta; x is [n][r >> x_shift][r >> x_shift][C]; statistics per group of rows_per_group rows of M.
+int spade_modulate_f32(const float* gb, const float* x, int x_shift, const float* mean, const float* rstd, float* out,
+                       int n, int r, int C, int samples_per_group, float slope, cudaStream_t st);
+
+// y[m][c] = act((x[m][c] - mean[g][c]) * rstd[g][c] * gamma[c] + beta[c]); g = m / rows_per_group (mean/rstd [G][C]).
+// gamma / beta may be null (1 / 0).  ldx / ldy are row pitches in elements.
+int affine_act_f32(const float* x, int ldx, const float* mean, const float* rstd, const float* gamma,
+                   const float* beta, float* y, int ldy, int64_t M, int C, int64_t rows_per_group, int act,
+                   float slope, cudaStream_t st);
+
+// out[m][n] = sum_k x[m][k] * w[k][n] + bias[n]; `partial` scratch of ksplit * M * N floats when K is split.
+int dense_f32(const float* x, const float* w, const float* bias, float* out, int M, int K, int N, float* partial,
+              int64_t partial_capacity, cudaStream_t st);
+
+// latent = mean + exp(0.5 * var) * eps (sampling.py:16) when eps != null, else mean + var (model.py:791).
+int sampler_f32(const float* mean, const float* var, const float* eps, float* latent, int64_t count, cudaStream_t st);
+
+// Final generator layer (networks.py:54-56): UpSampling2D(2) -> leaky_relu(0.2) -> Conv2D(1, 4, 'same') on
+// x [n][r][r][128] fp32 -> out [n][2r][2r] fp32.  w [4][4][128] (Keras [4,4,128,1]), bias scalar.
+int final_conv_f32(const float* x, const float* w, const float* bias, float* out, int n, int r, cudaStream_t st);
+
+// ---- tensor-core path (conv_tc.cu) -------------------------------------------------------------------------------
+struct ConvTC;  // opaque plan
+enum TcEpilogue {
+  TC_EPI_BIAS_F32 = 0,    // y_f32 = acc + bias (+ residual)
+  TC_EPI_SPADE_BF16 = 1,  // columns are gamma|beta interleaved per 64; out_bf16 = lrelu(gamma * xhat + beta)
+};
+struct ConvTCArgs {
+  const __nv_bfloat16* x = nullptr;  // [n][r][r][cin] bf16
+  const __nv_bfloat16* w = nullptr;  // [ncols][9*cin] bf16 (K-major)
+  int n = 0, r = 0, cin = 0, ncols = 0;
+  int epilogue = TC_EPI_BIAS_F32;
+  const float* bias = nullptr;       // [ncols]
+  // TC_EPI_BIAS_F32
+  float* y = nullptr;                // [n*r*r][ncols]
+  const float* res = nullptr;        // residual [n][r >> res_shift][r >> res_shift][ncols] or null
+  int res_shift = 0;
+  // TC_EPI_SPADE_BF16 (ncols = 2C, column tile of 128 = 64 gamma | 64 beta of the same channels)
+  const float* sx = nullptr;         // normalised tensor [n][r >> sx_shift][r >> sx_shift][C] fp32
+  int sx_shift = 0;
+  const float* mean = nullptr;       // [groups][C]
+  const float* rstd = nullptr;
+  int samples_per_group = 1;
+  float slope = 0.2f;
+  __nv_bfloat16* out_bf16 = nullptr; // [n*r*r][C]
+};
+int conv_tc_plan_create(ConvTC** plan, const ConvTCArgs& a);
+int conv_tc_launch(const ConvTC* plan, cudaStream_t st);
+void conv_tc_plan_destroy(ConvTC* plan);
+
+// small helpers for the bf16 path
+int mask_conv_bf16(const float* source, int I, const float* w, const float* bias, __nv_bfloat16* out, int n, int r,
+                   cudaStream_t st);  // nearest-resize + conv3x3 2->128 + relu -> bf16 [n][r][r][128]
+
+}  // namespace msr

@@ -1,0 +1,535 @@
+// fp32 CUDA-core operators of the generator graphs (parity mode, and the non-GEMM glue of the bf16 mode).
+//
+// Reference semantics: spade/models/{networks,blocks,spade,sampling}.py, pix2pix.py:64-108, and the TensorFlow rules of
+// SURVEY.md Appendix B (asymmetric SAME padding, half-pixel nearest resize, biased batch moments, ...).
+#include "nn.cuh"
+
+namespace msr {
+
+__device__ __forceinline__ float apply_act(float v, int act, float slope) {
+  switch (act) {
+    case ACT_RELU: return fmaxf(v, 0.f);
+    case ACT_LRELU: return v > 0.f ? v : v * slope;
+    case ACT_TANH: return tanhf(v);
+    default: return v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Generic NHWC conv as implicit GEMM: M = n*Ho*Wo, N = cout, K = kh*kw*cin.  64x64x16 tiles, 4x4 per thread.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int BM = 64, BN = 64, BK = 16;
+
+__global__ void __launch_bounds__(256) conv_f32_kernel(ConvF32 p) {
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  const int t = threadIdx.x;
+  const int64_t M = (int64_t)p.n * p.Ho * p.Wo;
+  const int K = p.kh * p.kw * p.cin;
+  const int64_t m0 = (int64_t)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+
+  // A-load role: one output pixel (row) and 4 consecutive k per thread
+  const int a_row = t >> 2, a_kq = (t & 3) * 4;
+  const int64_t am = m0 + a_row;
+  const bool a_ok = am < M;
+  int an = 0, aho = 0, awo = 0;
+  if (a_ok) {
+    an = (int)(am / ((int64_t)p.Ho * p.Wo));
+    const int rem = (int)(am % ((int64_t)p.Ho * p.Wo));
+    aho = rem / p.Wo;
+    awo = rem % p.Wo;
+  }
+  // B-load role
+  const int b_row = t >> 4, b_col = (t & 15) * 4;
+  // compute role
+  const int ty = t >> 4, tx = t & 15;
+  float acc[4][4] = {};
+  const bool vec_a = (p.cin % 4 == 0) && (p.ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.x) & 15) == 0);
+  const bool vec_b = (p.cout % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.w) & 15) == 0);
+
+  for (int k0 = 0; k0 < K; k0 += BK) {
+    // ---- A tile
+    float av[4] = {0.f, 0.f, 0.f, 0.f};
+    if (a_ok) {
+      const int kg = k0 + a_kq;
+      if (vec_a) {
+        if (kg < K) {
+          const int tap = kg / p.cin, ci = kg % p.cin;
+          const int ky = tap / p.kw, kx = tap % p.kw;
+          int vy, vx;
+          bool ok = true;
+          if (!p.transposed) {
+            vy = aho * p.stride - p.pad_t + ky;
+            vx = awo * p.stride - p.pad_l + kx;
+          } else {
+            const int ty2 = aho + p.pad_t - ky, tx2 = awo + p.pad_l - kx;
+            ok = (ty2 >= 0) && (tx2 >= 0) && (ty2 % p.stride == 0) && (tx2 % p.stride == 0);
+            vy = ty2 / p.stride;
+            vx = tx2 / p.stride;
+          }
+          if (ok && vy >= 0 && vy < p.Hv && vx >= 0 && vx < p.Wv) {
+            const int sy = (vy * p.in_mul + p.in_add) >> p.in_shift, sx = (vx * p.in_mul + p.in_add) >> p.in_shift;
+            const float4 v = *reinterpret_cast<const float4*>(p.x + (((int64_t)an * p.Hs + sy) * p.Ws + sx) * p.ldx + ci);
+            av[0] = v.x; av[1] = v.y; av[2] = v.z; av[3] = v.w;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int kgj = kg + j;
+          if (kgj >= K) continue;
+          const int tap = kgj / p.cin, ci = kgj % p.cin;
+          const int ky = tap / p.kw, kx = tap % p.kw;
+          int vy, vx;
+          bool ok = true;
+          if (!p.transposed) {
+            vy = aho * p.stride - p.pad_t + ky;
+            vx = awo * p.stride - p.pad_l + kx;
+          } else {
+            const int ty2 = aho + p.pad_t - ky, tx2 = awo + p.pad_l - kx;
+            ok = (ty2 >= 0) && (tx2 >= 0) && (ty2 % p.stride == 0) && (tx2 % p.stride == 0);
+            vy = ty2 / p.stride;
+            vx = tx2 / p.stride;
+          }
+          if (ok && vy >= 0 && vy < p.Hv && vx >= 0 && vx < p.Wv) {
+            const int sy = (vy * p.in_mul + p.in_add) >> p.in_shift, sx = (vx * p.in_mul + p.in_add) >> p.in_shift;
+            av[j] = p.x[(((int64_t)an * p.Hs + sy) * p.Ws + sx) * p.ldx + ci];
+          }
+        }
+      }
+      if (p.in_slope != 1.f) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) av[j] = av[j] > 0.f ? av[j] : av[j] * p.in_slope;
+      }
+    }
+    // ---- B tile
+    float bv[4] = {0.f, 0.f, 0.f, 0.f};
+    {
+      const int kg = k0 + b_row;
+      const int c = n0 + b_col;
+      if (kg < K) {
+        if (vec_b && c + 3 < p.cout) {
+          const float4 v = *reinterpret_cast<const float4*>(p.w + (int64_t)kg * p.cout + c);
+          bv[0] = v.x; bv[1] = v.y; bv[2] = v.z; bv[3] = v.w;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (c + j < p.cout) bv[j] = p.w[(int64_t)kg * p.cout + c + j];
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) As[a_kq + j][a_row] = av[j];
+    *reinterpret_cast<float4*>(&Bs[b_row][b_col]) = make_float4(bv[0], bv[1], bv[2], bv[3]);
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+  }
+  // ---- epilogue
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+    int64_t res_row = 0;
+    if (p.res) {
+      const int nn = (int)(m / ((int64_t)p.Ho * p.Wo));
+      const int rem = (int)(m % ((int64_t)p.Ho * p.Wo));
+      const int ho = rem / p.Wo, wo = rem % p.Wo;
+      const int rh = p.Ho >> p.res_shift, rw = p.Wo >> p.res_shift;
+      res_row = ((int64_t)nn * rh + (ho >> p.res_shift)) * rw + (wo >> p.res_shift);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = n0 + tx * 4 + j;
+      if (c >= p.cout) continue;
+      float v = acc[i][j];
+      if (p.bias) v += p.bias[c];
+      if (p.res) v += p.res[res_row * p.ldres + c];
+      p.y[m * p.ldy + c] = apply_act(v, p.act, p.act_slope);
+    }
+  }
+}
+
+int conv_f32(const ConvF32& p, cudaStream_t st) {
+  MSR_REQUIRE(p.x && p.w && p.y && p.n > 0 && p.cin > 0 && p.cout > 0, "conv_f32: bad arguments");
+  const int64_t M = (int64_t)p.n * p.Ho * p.Wo;
+  dim3 grid(ceil_div(M, BM), ceil_div(p.cout, BN));
+  conv_f32_kernel<<<grid, 256, 0, st>>>(p);
+  count_launch();
+  MSR_LAUNCH_CHECK();
+  return MSR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Channel statistics: deterministic two-stage reduction, fp64 partials.
+// ------------------------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float to_f32(T v);
+template <>
+__device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T>
+__global__ void __launch_bounds__(256) stats_partial_kernel(const T* __restrict__ x, int ld, int64_t rows, int C,
+                                                            double* __restrict__ partial) {
+  // grid (ceil(C/32), kStatSplit, groups); block = 32 channels x 8 row lanes
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  const int split = blockIdx.y, g = blockIdx.z;
+  const int64_t per = (rows + kStatSplit - 1) / kStatSplit;
+  const int64_t r0 = split * per, r1 = min(rows, r0 + per);
+  double s = 0.0, q = 0.0;
+  if (c < C) {
+    const T* base = x + ((int64_t)g * rows) * ld + c;
+    for (int64_t r = r0 + ry; r < r1; r += 8) {
+      const double v = (double)to_f32<T>(base[r * ld]);
+      s += v;
+      q += v * v;
+    }
+  }
+  __shared__ double sh[2][8][32];
+  sh[0][ry][cx] = s;
+  sh[1][ry][cx] = q;
+  __syncthreads();
+  if (ry == 0 && c < C) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+      s += sh[0][k][cx];
+      q += sh[1][k][cx];
+    }
+    double* o = partial + (((int64_t)g * kStatSplit + split) * C + c) * 2;
+    o[0] = s;
+    o[1] = q;
+  }
+}
+
+__global__ void stats_finalize_kernel(const double* __restrict__ partial, int C, int64_t rows, float eps,
+                                      float* __restrict__ mean, float* __restrict__ rstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int g = blockIdx.y;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int k = 0; k < kStatSplit; ++k) {
+    const double* o = partial + (((int64_t)g * kStatSplit + k) * C + c) * 2;
+    s += o[0];
+    q += o[1];
+  }
+  const double mu = s / (double)rows;
+  double var = q / (double)rows - mu * mu;
+  if (var < 0.0) var = 0.0;
+  mean[(int64_t)g * C + c] = (float)mu;
+  rstd[(int64_t)g * C + c] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+template <typename T>
+static int channel_stats_impl(const T* x, int ld, int groups, int64_t rows, int C, float eps, double* partial,
+                              float* mean, float* rstd, cudaStream_t st) {
+  MSR_REQUIRE(x && partial && mean && rstd && groups > 0 && rows > 0 && C > 0, "channel_stats: bad arguments");
+  stats_partial_kernel<T><<<dim3(ceil_div(C, 32), kStatSplit, groups), 256, 0, st>>>(x, ld, rows, C, partial);
+  MSR_LAUNCH_CHECK();
+  stats_finalize_kernel<<<dim3(ceil_div(C, 128), groups), 128, 0, st>>>(partial, C, rows, eps, mean, rstd);
+  MSR_LAUNCH_CHECK();
+  count_launch(2);
+  return MSR_OK;
+}
+int channel_stats_f32(const float* x, int ld, int groups, int64_t rows, int C, float eps, double* partial, float* mean,
+                      float* rstd, cudaStream_t st) {
+  return channel_stats_impl<float>(x, ld, groups, rows, C, eps, partial, mean, rstd, st);
+}
+int channel_stats_bf16(const __nv_bfloat16* x, int ld, int groups, int64_t rows, int C, float eps, double* partial,
+                       float* mean, float* rstd, cudaStream_t st) {
+  return channel_stats_impl<__nv_bfloat16>(x, ld, groups, rows, C, eps, partial, mean, rstd, st);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// SPADE modulation, fp32 path
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) spade_modulate_kernel(const float* __restrict__ gb, const float* __restrict__ x,
+                                                             int x_shift, const float* __restrict__ mean,
+                                                             const float* __restrict__ rstd, float* __restrict__ out,
+                                                             int n, int r, int C, int samples_per_group, float slope) {
+  const int64_t total = (int64_t)n * r * r * (C / 4);
+  const int c4n = C / 4;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e % c4n) * 4;
+    const int64_t m = e / c4n;
+    const int nn = (int)(m / ((int64_t)r * r));
+    const int rem = (int)(m % ((int64_t)r * r));
+    const int h = rem / r, w = rem % r;
+    const int rs = r >> x_shift;
+    const int64_t xr = ((int64_t)nn * rs + (h >> x_shift)) * rs + (w >> x_shift);
+    const int g = nn / samples_per_group;
+    const float4 xv = *reinterpret_cast<const float4*>(x + xr * C + c);
+    const float4 mu = *reinterpret_cast<const float4*>(mean + (int64_t)g * C + c);
+    const float4 rs4 = *reinterpret_cast<const float4*>(rstd + (int64_t)g * C + c);
+    const float4 ga = *reinterpret_cast<const float4*>(gb + m * 2 * C + c);
+    const float4 be = *reinterpret_cast<const float4*>(gb + m * 2 * C + C + c);
+    float4 o;
+    o.x = ga.x * ((xv.x - mu.x) * rs4.x) + be.x;
+    o.y = ga.y * ((xv.y - mu.y) * rs4.y) + be.y;
+    o.z = ga.z * ((xv.z - mu.z) * rs4.z) + be.z;
+    o.w = ga.w * ((xv.w - mu.w) * rs4.w) + be.w;
+    o.x = o.x > 0.f ? o.x : o.x * slope;
+    o.y = o.y > 0.f ? o.y : o.y * slope;
+    o.z = o.z > 0.f ? o.z : o.z * slope;
+    o.w = o.w > 0.f ? o.w : o.w * slope;
+    *reinterpret_cast<float4*>(out + m * C + c) = o;
+  }
+}
+
+int spade_modulate_f32(const float* gb, const float* x, int x_shift, const float* mean, const float* rstd, float* out,
+                       int n, int r, int C, int samples_per_group, float slope, cudaStream_t st) {
+  MSR_REQUIRE(gb && x && mean && rstd && out && C % 4 == 0, "spade_modulate: bad arguments");
+  const int64_t total = (int64_t)n * r * r * (C / 4);
+  const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 32);
+  spade_modulate_kernel<<<blocks, 256, 0, st>>>(gb, x, x_shift, mean, rstd, out, n, r, C, samples_per_group, slope);
+  count_launch();
+  MSR_LAUNCH_CHECK();
+  return MSR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Normalise + affine + activation (tfa InstanceNormalization / Keras BatchNormalization at inference)
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) affine_act_kernel(const float* __restrict__ x, int ldx,
+                                                         const float* __restrict__ mean,
+                                                         const float* __restrict__ rstd,
+                                                         const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, float* __restrict__ y, int ldy,
+                                                         int64_t M, int C, int64_t rows_per_group, int act,
+                                                         float slope) {
+  const int64_t total = M * C;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e % C);
+    const int64_t m = e / C;
+    float v = x[m * ldx + c];
+    if (mean) {
+      const int64_t g = m / rows_per_group;
+      v = (v - mean[g * C + c]) * rstd[g * C + c];
+    }
+    if (gamma) v *= gamma[c];
+    if (beta) v += beta[c];
+    y[m * ldy + c] = apply_act(v, act, slope);
+  }
+}
+
+int affine_act_f32(const float* x, int ldx, const float* mean, const float* rstd, const float* gamma,
+                   const float* beta, float* y, int ldy, int64_t M, int C, int64_t rows_per_group, int act,
+                   float slope, cudaStream_t st) {
+  MSR_REQUIRE(x && y && M > 0 && C > 0 && rows_per_group > 0, "affine_act: bad arguments");
+  const int64_t total = M * C;
+  const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 32);
+  affine_act_kernel<<<blocks, 256, 0, st>>>(x, ldx, mean, rstd, gamma, beta, y, ldy, M, C, rows_per_group, act, slope);
+  count_launch();
+  MSR_LAUNCH_CHECK();
+  return MSR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Dense layer for small M (latent projection, encoder heads): split-K, deterministic two-stage sum.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kDenseMB = 8;
+
+__global__ void __launch_bounds__(128) dense_partial_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                            float* __restrict__ partial, int M, int K, int N,
+                                                            int kchunk) {
+  const int nidx = blockIdx.x * 128 + threadIdx.x;
+  const int split = blockIdx.y;
+  const int m0 = blockIdx.z * kDenseMB;
+  const int k0 = split * kchunk, k1 = min(K, k0 + kchunk);
+  float acc[kDenseMB];
+#pragma unroll
+  for (int i = 0; i < kDenseMB; ++i) acc[i] = 0.f;
+  if (nidx < N) {
+    for (int k = k0; k < k1; ++k) {
+      const float wv = __ldg(w + (int64_t)k * N + nidx);
+#pragma unroll
+      for (int i = 0; i < kDenseMB; ++i)
+        if (m0 + i < M) acc[i] = fmaf(__ldg(x + (int64_t)(m0 + i) * K + k), wv, acc[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < kDenseMB; ++i)
+      if (m0 + i < M) partial[((int64_t)split * M + m0 + i) * N + nidx] = acc[i];
+  }
+}
+
+__global__ void dense_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ bias,
+                                    float* __restrict__ out, int M, int N, int ksplit) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= (int64_t)M * N) return;
+  float s = 0.f;
+  for (int k = 0; k < ksplit; ++k) s += partial[(int64_t)k * M * N + e];
+  if (bias) s += bias[e % N];
+  out[e] = s;
+}
+
+int dense_f32(const float* x, const float* w, const float* bias, float* out, int M, int K, int N, float* partial,
+              int64_t partial_capacity, cudaStream_t st) {
+  MSR_REQUIRE(x && w && out && partial && M > 0 && K > 0 && N > 0, "dense: bad arguments");
+  int ksplit = std::max(1, std::min(64, K / 512));
+  while ((int64_t)ksplit * M * N > partial_capacity && ksplit > 1) --ksplit;
+  MSR_REQUIRE((int64_t)ksplit * M * N <= partial_capacity, "dense: partial scratch too small");
+  const int kchunk = ceil_div(K, ksplit);
+  dense_partial_kernel<<<dim3(ceil_div(N, 128), ksplit, ceil_div(M, kDenseMB)), 128, 0, st>>>(x, w, partial, M, K, N,
+                                                                                             kchunk);
+  MSR_LAUNCH_CHECK();
+  dense_reduce_kernel<<<ceil_div((int64_t)M * N, 256), 256, 0, st>>>(partial, bias, out, M, N, ksplit);
+  MSR_LAUNCH_CHECK();
+  count_launch(2);
+  return MSR_OK;
+}
+
+__global__ void sampler_kernel(const float* __restrict__ mean, const float* __restrict__ var,
+                               const float* __restrict__ eps, float* __restrict__ latent, int64_t count) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= count) return;
+  latent[e] = eps ? mean[e] + expf(0.5f * var[e]) * eps[e] : mean[e] + var[e];
+}
+
+int sampler_f32(const float* mean, const float* var, const float* eps, float* latent, int64_t count, cudaStream_t st) {
+  MSR_REQUIRE(mean && var && latent && count > 0, "sampler: bad arguments");
+  sampler_kernel<<<ceil_div(count, 256), 256, 0, st>>>(mean, var, eps, latent, count);
+  count_launch();
+  MSR_LAUNCH_CHECK();
+  return MSR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Final layer: upsample x2 -> leaky_relu(0.2) -> conv 4x4 SAME (pad 1 before, 2 after) -> 1 channel.
+// Block = 16x16 output pixels; the (10 x 10) low-res halo tile is staged in shared memory after the leaky relu; each
+// warp walks output pixels with lanes over channels (4 per lane) and reduces with shuffles.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int FC_TX = 16, FC_TY = 8;   // output tile (x, y)
+constexpr int FC_LX = FC_TX / 2 + 2;   // low-res tile incl. halo (rows (o-1)>>1 .. (o+2)>>1)
+constexpr int FC_LY = FC_TY / 2 + 2;
+
+__global__ void __launch_bounds__(256) final_conv_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                         const float* __restrict__ bias, float* __restrict__ out,
+                                                         int n, int r) {
+  __shared__ float4 tile[FC_LY * FC_LX][32];  // [low-res pixel][lane] -> 4 channels per lane
+  const int R = 2 * r;
+  const int img = blockIdx.z, oy0 = blockIdx.y * FC_TY, ox0 = blockIdx.x * FC_TX;
+  const int ly0 = (oy0 >> 1) - 1, lx0 = (ox0 >> 1) - 1;  // low-res origin of the tile (may be -1)
+  for (int e = threadIdx.x; e < FC_LY * FC_LX * 32; e += 256) {
+    const int lane = e & 31, pix = e >> 5;
+    const int ly = ly0 + pix / FC_LX, lx = lx0 + pix % FC_LX;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ly >= 0 && ly < r && lx >= 0 && lx < r) {
+      v = *reinterpret_cast<const float4*>(x + (((int64_t)img * r + ly) * r + lx) * 128 + lane * 4);
+      v.x = v.x > 0.f ? v.x : 0.2f * v.x;
+      v.y = v.y > 0.f ? v.y : 0.2f * v.y;
+      v.z = v.z > 0.f ? v.z : 0.2f * v.z;
+      v.w = v.w > 0.f ? v.w : 0.2f * v.w;
+    }
+    tile[pix][lane] = v;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4 wr[16];
+#pragma unroll
+  for (int tp = 0; tp < 16; ++tp) wr[tp] = *reinterpret_cast<const float4*>(w + tp * 128 + lane * 4);
+  __syncthreads();
+  const float b = bias ? bias[0] : 0.f;
+  for (int px = warp; px < FC_TY * FC_TX; px += 8) {
+    const int oy = oy0 + px / FC_TX, ox = ox0 + px % FC_TX;
+    float acc = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 4; ++ky) {
+      const int uy = oy - 1 + ky;  // upsampled-row index, SAME pad (1, 2)
+      if (uy < 0 || uy >= R) continue;
+      const int ty = (uy >> 1) - ly0;
+#pragma unroll
+      for (int kx = 0; kx < 4; ++kx) {
+        const int ux = ox - 1 + kx;
+        if (ux < 0 || ux >= R) continue;
+        const int tx = (ux >> 1) - lx0;
+        const float4 v = tile[ty * FC_LX + tx][lane];
+        const float4 ww = wr[ky * 4 + kx];
+        acc = fmaf(v.x, ww.x, acc);
+        acc = fmaf(v.y, ww.y, acc);
+        acc = fmaf(v.z, ww.z, acc);
+        acc = fmaf(v.w, ww.w, acc);
+      }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    if (lane == 0) out[((int64_t)img * R + oy) * R + ox] = acc + b;
+  }
+}
+
+int final_conv_f32(const float* x, const float* w, const float* bias, float* out, int n, int r, cudaStream_t st) {
+  MSR_REQUIRE(x && w && out && n > 0 && r > 0, "final_conv: bad arguments");
+  MSR_REQUIRE((2 * r) % FC_TX == 0, "final_conv: output side must be a multiple of 16");
+  final_conv_kernel<<<dim3(2 * r / FC_TX, 2 * r / FC_TY, n), 256, 0, st>>>(x, w, bias, out, n, r);
+  count_launch();
+  MSR_LAUNCH_CHECK();
+  return MSR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// SPADE's shared 2 -> 128 conv (spade.py:9,17-18) for the bf16 path: nearest-resize (half-pixel centres) of the
+// (I, I, 2) source to (r, r), conv3x3 SAME, bias, relu, bf16 NHWC out.  One thread per (pixel, 8 channels).
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) mask_conv_kernel(const float* __restrict__ src, int I,
+                                                        const float* __restrict__ w, const float* __restrict__ bias,
+                                                        __nv_bfloat16* __restrict__ out, int n, int r) {
+  __shared__ float ws[18 * 128];
+  __shared__ float bs[128];
+  for (int e = threadIdx.x; e < 18 * 128; e += 256) ws[e] = w[e];
+  if (threadIdx.x < 128) bs[threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const int f = I / r, half = f >> 1;
+  const int64_t total = (int64_t)n * r * r * 16;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(e & 15);
+    const int64_t m = e >> 4;
+    const int nn = (int)(m / ((int64_t)r * r));
+    const int rem = (int)(m % ((int64_t)r * r));
+    const int h = rem / r, x = rem % r;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = bs[cg * 8 + j];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int hh = h + ky - 1;
+      if (hh < 0 || hh >= r) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int xx = x + kx - 1;
+        if (xx < 0 || xx >= r) continue;
+        const float2 s = *reinterpret_cast<const float2*>(src + (((int64_t)nn * I + hh * f + half) * I + xx * f + half) * 2);
+        const float* w0 = ws + ((ky * 3 + kx) * 2 + 0) * 128 + cg * 8;
+        const float* w1 = w0 + 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(s.x, w0[j], fmaf(s.y, w1[j], acc[j]));
+      }
+    }
+    __align__(16) __nv_bfloat16 o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = __float2bfloat16_rn(fmaxf(acc[j], 0.f));
+    *reinterpret_cast<uint4*>(out + m * 128 + cg * 8) = *reinterpret_cast<const uint4*>(o);
+  }
+}
+
+int mask_conv_bf16(const float* source, int I, const float* w, const float* bias, __nv_bfloat16* out, int n, int r,
+                   cudaStream_t st) {
+  MSR_REQUIRE(source && w && bias && out && r > 0 && I % r == 0, "mask_conv: bad arguments");
+  const int64_t total = (int64_t)n * r * r * 16;
+  const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 16);
+  mask_conv_kernel<<<blocks, 256, 0, st>>>(source, I, w, bias, out, n, r);
+  count_launch();
+  MSR_LAUNCH_CHECK();
+  return MSR_OK;
+}
+
+}  // namespace msr

@@ -1,0 +1,398 @@
+// Tiling / blending kernels of the tiled full-DEM inference path (HBM-bound byte / fp32 / fp64 work).
+//
+// Reference: process_full_tiles.py  padInputs :246-267, getPatch :269-293, normalize :295-311,
+//            makeGaussianKernel :347-361, rebuildTile :363-414, rebuildMap :541-545.
+// All arithmetic that the reference performs in numpy is reproduced with explicitly rounded IEEE operations
+// (__fsub_rn / __fdiv_rn / __dmul_rn ...) so that no FMA contraction changes a bit.
+#include "common.cuh"
+
+namespace msr {
+
+// ------------------------------------------------------------------------------------------------------------------
+// K0  padInputs: canvas = no_value everywhere, raster pasted at (off, off).  One float4 store per thread.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pad_inputs_kernel(const float* __restrict__ dem, const float* __restrict__ img,
+                                                         int H, int W, float* __restrict__ dem_c,
+                                                         float* __restrict__ img_c, int CH, int CW, int off, float nv) {
+  const int64_t quads_per_row = (CW + 3) / 4;
+  const int64_t total = quads_per_row * CH;
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
+    const int y = (int)(q / quads_per_row);
+    const int x0 = (int)(q % quads_per_row) * 4;
+    const int sy = y - off;
+    const bool row_in = (sy >= 0) && (sy < H);
+    float d[4], m[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int sx = x0 + j - off;
+      const bool in = row_in && sx >= 0 && sx < W;
+      d[j] = in ? __ldg(dem + (int64_t)sy * W + sx) : nv;
+      m[j] = in ? __ldg(img + (int64_t)sy * W + sx) : nv;
+    }
+    const int64_t o = (int64_t)y * CW + x0;
+    if ((CW & 3) == 0) {
+      *reinterpret_cast<float4*>(dem_c + o) = make_float4(d[0], d[1], d[2], d[3]);
+      *reinterpret_cast<float4*>(img_c + o) = make_float4(m[0], m[1], m[2], m[3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (x0 + j < CW) {
+          dem_c[o + j] = d[j];
+          img_c[o + j] = m[j];
+        }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K1  validity summed-area table.  Pass A: per-row inclusive prefix of the invalid mask into sat[y+1][x+1];
+//     pass B: per-column running sum.  int32, exact.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sat_rows_kernel(const float* __restrict__ img, const float* __restrict__ dem,
+                                                       int CH, int CW, float nv, int32_t* __restrict__ sat) {
+  const int y = blockIdx.x;
+  if (y >= CH) return;
+  __shared__ int warp_sums[8];
+  __shared__ int carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int32_t* out = sat + (int64_t)(y + 1) * (CW + 1);
+  if (threadIdx.x == 0) out[0] = 0;
+  const float* irow = img + (int64_t)y * CW;
+  const float* drow = dem + (int64_t)y * CW;
+  __syncthreads();
+  for (int base = 0; base < CW; base += 256 * 4) {
+    const int x0 = base + threadIdx.x * 4;
+    int v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int x = x0 + j;
+      v[j] = (x < CW) ? ((irow[x] <= nv) || (drow[x] <= nv) ? 1 : 0) : 0;
+    }
+    int local = v[0] + v[1] + v[2] + v[3];
+    int incl = local;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    int wprefix = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (k < warp) wprefix += warp_sums[k];
+    int run = carry_s + wprefix + incl - local;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      run += v[j];
+      if (x0 + j < CW) out[x0 + j + 1] = run;
+    }
+    __syncthreads();
+    if (threadIdx.x == 255) carry_s = run;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) sat_cols_kernel(int CH, int CW, int32_t* __restrict__ sat) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x > CW) return;
+  const int64_t pitch = CW + 1;
+  sat[x] = 0;
+  int acc = 0;
+  int y = 1;
+  for (; y + 7 <= CH; y += 8) {
+    int t[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t[j] = sat[(int64_t)(y + j) * pitch + x];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      acc += t[j];
+      sat[(int64_t)(y + j) * pitch + x] = acc;
+    }
+  }
+  for (; y <= CH; ++y) {
+    acc += sat[(int64_t)y * pitch + x];
+    sat[(int64_t)y * pitch + x] = acc;
+  }
+}
+
+__global__ void patch_validity_kernel(const int32_t* __restrict__ sat, int CH, int CW, const int32_t* __restrict__ xy,
+                                      int n, int I, uint8_t* __restrict__ valid) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  int x0 = xy[2 * k], y0 = xy[2 * k + 1];
+  int x1 = min(x0 + I, CW), y1 = min(y0 + I, CH);
+  x0 = max(x0, 0);
+  y0 = max(y0, 0);
+  if (x1 <= x0 || y1 <= y0) {  // empty window: numpy's .any() of an empty slice is False -> "valid"
+    valid[k] = 1;
+    return;
+  }
+  const int64_t pitch = CW + 1;
+  const int s = sat[(int64_t)y1 * pitch + x1] - sat[(int64_t)y0 * pitch + x1] - sat[(int64_t)y1 * pitch + x0] +
+                sat[(int64_t)y0 * pitch + x0];
+  valid[k] = (s == 0) ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K2  gather + normalise.  Pass A: 32 row-chunks per patch reduce (min, max) of both rasters; pass B: reduce the 32
+//     partials, then write float2 {ortho, dem} = ((v - lo) / (hi - lo)) - 0.5  (IEEE fp32, process_full_tiles.py:307-310)
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kMinMaxSplit = 32;
+
+__global__ void __launch_bounds__(256) patch_minmax_kernel(const float* __restrict__ img,
+                                                           const float* __restrict__ dem, int CW,
+                                                           const int32_t* __restrict__ xy, int I,
+                                                           float* __restrict__ partial) {
+  const int k = blockIdx.x, split = blockIdx.y;
+  const int x0 = xy[2 * k], y0 = xy[2 * k + 1];
+  float v[4] = {INFINITY, -INFINITY, INFINITY, -INFINITY};
+  if (x0 >= 0 && y0 >= 0) {
+    const int rows_per = (I + kMinMaxSplit - 1) / kMinMaxSplit;
+    const int r0 = split * rows_per, r1 = min(I, r0 + rows_per);
+    const int count = (r1 - r0) * I;
+    for (int e = threadIdx.x; e < count; e += blockDim.x) {
+      const int r = r0 + e / I, c = e % I;
+      const int64_t o = (int64_t)(y0 + r) * CW + x0 + c;
+      const float a = __ldg(img + o), b = __ldg(dem + o);
+      v[0] = fminf(v[0], a);
+      v[1] = fmaxf(v[1], a);
+      v[2] = fminf(v[2], b);
+      v[3] = fmaxf(v[3], b);
+    }
+  }
+  __shared__ float red[8][4];
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    v[0] = fminf(v[0], __shfl_xor_sync(0xffffffffu, v[0], d));
+    v[1] = fmaxf(v[1], __shfl_xor_sync(0xffffffffu, v[1], d));
+    v[2] = fminf(v[2], __shfl_xor_sync(0xffffffffu, v[2], d));
+    v[3] = fmaxf(v[3], __shfl_xor_sync(0xffffffffu, v[3], d));
+  }
+  if ((threadIdx.x & 31) == 0)
+    for (int j = 0; j < 4; ++j) red[threadIdx.x >> 5][j] = v[j];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) {
+      v[0] = fminf(v[0], red[w][0]);
+      v[1] = fmaxf(v[1], red[w][1]);
+      v[2] = fminf(v[2], red[w][2]);
+      v[3] = fmaxf(v[3], red[w][3]);
+    }
+    float* p = partial + ((int64_t)k * kMinMaxSplit + split) * 4;
+    p[0] = v[0];
+    p[1] = v[1];
+    p[2] = v[2];
+    p[3] = v[3];
+  }
+}
+
+__global__ void __launch_bounds__(256) patch_normalize_kernel(const float* __restrict__ img,
+                                                              const float* __restrict__ dem, int CW,
+                                                              const int32_t* __restrict__ xy, int I,
+                                                              const float* __restrict__ partial,
+                                                              float* __restrict__ out, float* __restrict__ minmax) {
+  const int k = blockIdx.x;
+  const int x0 = xy[2 * k], y0 = xy[2 * k + 1];
+  float2* o = reinterpret_cast<float2*>(out) + (int64_t)k * I * I;
+  const int chunk = (I * I + gridDim.y - 1) / gridDim.y;
+  const int e0 = blockIdx.y * chunk, e1 = min(I * I, e0 + chunk);
+  if (x0 < 0 || y0 < 0) {  // padding slot (process_full_tiles.py:472): zeros
+    for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) o[e] = make_float2(0.f, 0.f);
+    if (blockIdx.y == 0 && threadIdx.x < 4) minmax[4 * k + threadIdx.x] = 0.f;
+    return;
+  }
+  float lo_i = INFINITY, hi_i = -INFINITY, lo_d = INFINITY, hi_d = -INFINITY;
+  const float* p = partial + (int64_t)k * kMinMaxSplit * 4;
+#pragma unroll 4
+  for (int s = 0; s < kMinMaxSplit; ++s) {
+    lo_i = fminf(lo_i, p[4 * s + 0]);
+    hi_i = fmaxf(hi_i, p[4 * s + 1]);
+    lo_d = fminf(lo_d, p[4 * s + 2]);
+    hi_d = fmaxf(hi_d, p[4 * s + 3]);
+  }
+  if (blockIdx.y == 0 && threadIdx.x == 0) {
+    minmax[4 * k + 0] = lo_i;
+    minmax[4 * k + 1] = hi_i;
+    minmax[4 * k + 2] = lo_d;
+    minmax[4 * k + 3] = hi_d;
+  }
+  const float range_i = __fsub_rn(hi_i, lo_i), range_d = __fsub_rn(hi_d, lo_d);
+  for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+    const int r = e / I, c = e % I;
+    const int64_t src = (int64_t)(y0 + r) * CW + x0 + c;
+    const float a = __ldg(img + src), b = __ldg(dem + src);
+    float2 v;
+    v.x = __fsub_rn(__fdiv_rn(__fsub_rn(a, lo_i), range_i), 0.5f);
+    v.y = __fsub_rn(__fdiv_rn(__fsub_rn(b, lo_d), range_d), 0.5f);
+    o[e] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K9  rebuildTile in gather form (+ finalize + paste).  One thread per output pixel of the T x T tile centre.
+// ------------------------------------------------------------------------------------------------------------------
+struct BlendState {
+  float wsum, mean, s;
+};
+
+__device__ __forceinline__ void blend_update(BlendState& st, double w, bool is_f64, float d32, double d64) {
+  // w_sum[...] += w                                   (:398)  f32 <- f64(f32) + f64
+  st.wsum = __double2float_rn(__dadd_rn((double)st.wsum, w));
+  // mean = mean_old + (w / w_sum) * (d - mean_old)    (:401)
+  const double delta_old = is_f64 ? __dsub_rn(d64, (double)st.mean) : (double)__fsub_rn(d32, st.mean);
+  const double ratio = __ddiv_rn(w, (double)st.wsum);
+  st.mean = __double2float_rn(__dadd_rn((double)st.mean, __dmul_rn(ratio, delta_old)));
+  // S += w * (d - mean_new) * (d - mean_new)          (:402; `mean_old` there is a view that already holds mean_new)
+  const double delta_new = is_f64 ? __dsub_rn(d64, (double)st.mean) : (double)__fsub_rn(d32, st.mean);
+  st.s = __double2float_rn(__dadd_rn((double)st.s, __dmul_rn(__dmul_rn(w, delta_new), delta_new)));
+}
+
+__device__ __forceinline__ void blend_contribution(BlendState& st, const void* const* __restrict__ ptrs,
+                                                   const uint8_t* __restrict__ f64flags,
+                                                   const float* __restrict__ lohi, const double* __restrict__ wtab,
+                                                   int k, int ry, int rx, int I, int p, int add_half) {
+  // (ry, rx) = position inside patch k, already known to be in [p, I - p)
+  const float lo = lohi[2 * k], hi = lohi[2 * k + 1];
+  const float range = __fsub_rn(hi, lo);
+  const double w = wtab[(int64_t)(ry - p) * (I - 2 * p) + (rx - p)];
+  const bool is_f64 = f64flags != nullptr && f64flags[k] != 0;
+  float d32 = 0.f;
+  double d64 = 0.0;
+  if (is_f64) {
+    double v = reinterpret_cast<const double*>(ptrs[k])[(int64_t)ry * I + rx];
+    if (add_half) v = __dadd_rn(v, 0.5);
+    d64 = __dadd_rn(__dmul_rn(v, (double)range), (double)lo);  // f64 array * f32 scalar + f32 scalar (:396)
+  } else {
+    float v = reinterpret_cast<const float*>(ptrs[k])[(int64_t)ry * I + rx];
+    if (add_half) v = __fadd_rn(v, 0.5f);                      // processBatch :340
+    d32 = __fadd_rn(__fmul_rn(v, range), lo);                  // :396
+  }
+  blend_update(st, w, is_f64, d32, d64);
+}
+
+__global__ void __launch_bounds__(256) blend_tile_kernel(const void* const* __restrict__ ptrs,
+                                                         const uint8_t* __restrict__ f64flags,
+                                                         const float* __restrict__ lohi,
+                                                         const int32_t* __restrict__ pxy, int n,
+                                                         const int32_t* __restrict__ lattice, int G,
+                                                         const double* __restrict__ wtab, int I, int S, int T,
+                                                         int add_half, float nv, float* __restrict__ mean_out,
+                                                         float* __restrict__ std_out, uint8_t* __restrict__ good_out,
+                                                         int64_t pitch, int rows, int cols) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = blockIdx.y;
+  if (col >= cols || row >= rows) return;
+  const int off = I - S, p = I / 16;
+  const int Y = row + off, X = col + off;  // accumulator coordinates (:386, :404)
+  BlendState st = {0.f, 0.f, 0.f};
+  if (lattice != nullptr) {
+    // patches covering Y: ky*S + p <= Y < ky*S + I - p
+    int gy0 = (Y - (I - p) + S) / S;  // ceil((Y - (I-p) + 1) / S) for non-negative numerators
+    if (Y - (I - p) + 1 <= 0) gy0 = 0;
+    int gy1 = (Y - p) / S;
+    if (Y - p < 0) gy1 = -1;
+    int gx0 = (X - (I - p) + S) / S;
+    if (X - (I - p) + 1 <= 0) gx0 = 0;
+    int gx1 = (X - p) / S;
+    if (X - p < 0) gx1 = -1;
+    gy1 = min(gy1, G - 1);
+    gx1 = min(gx1, G - 1);
+    for (int gy = gy0; gy <= gy1; ++gy) {
+      for (int gx = gx0; gx <= gx1; ++gx) {
+        const int k = lattice[gy * G + gx];
+        if (k < 0) continue;
+        blend_contribution(st, ptrs, f64flags, lohi, wtab, k, Y - gy * S, X - gx * S, I, p, add_half);
+      }
+    }
+  } else {
+    for (int k = 0; k < n; ++k) {
+      const int ry = Y - pxy[2 * k + 1], rx = X - pxy[2 * k];
+      if (ry < p || ry >= I - p || rx < p || rx >= I - p) continue;
+      blend_contribution(st, ptrs, f64flags, lohi, wtab, k, ry, rx, I, p, add_half);
+    }
+  }
+  const bool good = st.wsum > 0.f;                                    // :409
+  const float sd = __fsqrt_rn(__fdiv_rn(st.s, st.wsum));              // :411
+  const int64_t o = (int64_t)row * pitch + col;
+  mean_out[o] = good ? st.mean : nv;                                  // :412
+  std_out[o] = good ? sd : nv;                                        // :413
+  good_out[o] = good ? 1 : 0;
+}
+
+}  // namespace msr
+
+using namespace msr;
+
+extern "C" int msr_pad_inputs(const float* d_dem, const float* d_img, int H, int W, float* d_dem_canvas,
+                              float* d_img_canvas, int CH, int CW, int off, float no_value, void* stream) {
+  MSR_REQUIRE(d_dem && d_img && d_dem_canvas && d_img_canvas, "msr_pad_inputs: null pointer");
+  MSR_REQUIRE(H > 0 && W > 0 && off >= 0 && CH >= H + off && CW >= W + off, "msr_pad_inputs: bad geometry");
+  const int64_t quads = (int64_t)((CW + 3) / 4) * CH;
+  const int blocks = (int)std::min<int64_t>((quads + 255) / 256, 148 * 16);
+  pad_inputs_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_dem, d_img, H, W, d_dem_canvas, d_img_canvas, CH, CW,
+                                                              off, no_value);
+  count_launch();
+  MSR_LAUNCH_CHECK();
+  return MSR_OK;
+}
+
+extern "C" int msr_validity_sat(const float* d_img_canvas, const float* d_dem_canvas, int CH, int CW, float no_value,
+                                int32_t* d_sat, void* stream) {
+  MSR_REQUIRE(d_img_canvas && d_dem_canvas && d_sat && CH > 0 && CW > 0, "msr_validity_sat: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  sat_rows_kernel<<<CH, 256, 0, st>>>(d_img_canvas, d_dem_canvas, CH, CW, no_value, d_sat);
+  MSR_LAUNCH_CHECK();
+  sat_cols_kernel<<<ceil_div(CW + 1, 256), 256, 0, st>>>(CH, CW, d_sat);
+  MSR_LAUNCH_CHECK();
+  count_launch(2);
+  return MSR_OK;
+}
+
+extern "C" int msr_patch_validity(const int32_t* d_sat, int CH, int CW, const int32_t* d_xy, int n, int I,
+                                  uint8_t* d_valid, void* stream) {
+  MSR_REQUIRE(d_sat && d_xy && d_valid && n >= 0 && I > 0, "msr_patch_validity: bad arguments");
+  if (n == 0) return MSR_OK;
+  patch_validity_kernel<<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(d_sat, CH, CW, d_xy, n, I, d_valid);
+  count_launch();
+  MSR_LAUNCH_CHECK();
+  return MSR_OK;
+}
+
+extern "C" int msr_gather_normalize(const float* d_img_canvas, const float* d_dem_canvas, int CH, int CW,
+                                    const int32_t* d_xy, int n, int I, float* d_out_nhwc, float* d_minmax,
+                                    float* d_partial, void* stream) {
+  MSR_REQUIRE(d_img_canvas && d_dem_canvas && d_xy && d_out_nhwc && d_minmax && d_partial,
+              "msr_gather_normalize: null pointer");
+  MSR_REQUIRE(n >= 0 && I > 0 && CH >= I && CW >= I, "msr_gather_normalize: bad geometry");
+  if (n == 0) return MSR_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  patch_minmax_kernel<<<dim3(n, kMinMaxSplit), 256, 0, st>>>(d_img_canvas, d_dem_canvas, CW, d_xy, I, d_partial);
+  MSR_LAUNCH_CHECK();
+  const int ysplit = std::max(1, std::min(64, (I * I) / 2048));
+  patch_normalize_kernel<<<dim3(n, ysplit), 256, 0, st>>>(d_img_canvas, d_dem_canvas, CW, d_xy, I, d_partial,
+                                                          d_out_nhwc, d_minmax);
+  MSR_LAUNCH_CHECK();
+  count_launch(2);
+  return MSR_OK;
+}
+
+extern "C" int msr_blend_tile(const void* const* d_patch_ptr, const uint8_t* d_patch_f64, const float* d_patch_lohi,
+                              const int32_t* d_patch_xy, int n, const int32_t* d_lattice, int G,
+                              const double* d_weights, int I, int S, int T, int add_half, float no_value,
+                              float* d_mean, float* d_std, uint8_t* d_good, int64_t pitch, int rows, int cols,
+                              void* stream) {
+  MSR_REQUIRE(d_weights && d_mean && d_std && d_good, "msr_blend_tile: null pointer");
+  MSR_REQUIRE(n == 0 || (d_patch_ptr && d_patch_lohi && d_patch_xy), "msr_blend_tile: null patch tables");
+  MSR_REQUIRE(I >= 16 && S > 0 && S <= I && T > 0, "msr_blend_tile: need I >= 16 (purge >= 1), 0 < S <= I");
+  MSR_REQUIRE(rows >= 0 && cols >= 0 && rows <= T && cols <= T && pitch >= cols, "msr_blend_tile: bad output window");
+  MSR_REQUIRE(d_lattice == nullptr || G > 0, "msr_blend_tile: lattice needs G > 0");
+  if (rows == 0 || cols == 0) return MSR_OK;
+  blend_tile_kernel<<<dim3(ceil_div(cols, 256), rows), 256, 0, (cudaStream_t)stream>>>(
+      d_patch_ptr, d_patch_f64, d_patch_lohi, d_patch_xy, n, d_lattice, G, d_weights, I, S, T, add_half, no_value,
+      d_mean, d_std, d_good, pitch, rows, cols);
+  count_launch();
+  MSR_LAUNCH_CHECK();
+  return MSR_OK;
+}
