@@ -41,13 +41,36 @@ const char* msr_last_error(void);
 int msr_device_sm_count(void);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Per-kernel-family timing (measurement aid for bench.py; adds a cudaEvent pair around every launch group while on)
+ * ------------------------------------------------------------------------------------------------------------- */
+#define MSR_PROF_CONV_TC 0   /* tcgen05 implicit-GEMM convolutions (main convs + fused SPADE gamma/beta convs) */
+#define MSR_PROF_CONV_F32 1  /* CUDA-core fp32 convolutions (encoder, fp32 mode, pix2pix) */
+#define MSR_PROF_MASK_CONV 2 /* SPADE's 2->128 mask conv (bf16 mode) */
+#define MSR_PROF_STATS 3     /* batch / instance statistics */
+#define MSR_PROF_ELEMWISE 4  /* SPADE modulation (fp32 mode), affine+activation, sampler */
+#define MSR_PROF_DENSE 5     /* dense layers */
+#define MSR_PROF_FINAL_CONV 6
+#define MSR_PROF_PAD 7
+#define MSR_PROF_VALIDITY 8
+#define MSR_PROF_GATHER 9    /* gather + normalise */
+#define MSR_PROF_BLEND 10
+#define MSR_PROF_COUNT 11
+
+/* Turns event timing on (clears the counters) or off. */
+int msr_profile_enable(int on);
+/* Synchronises the device and returns, per family f < MSR_PROF_COUNT: ms[f] summed event time, work[f] summed
+ * algorithmic work (FLOPs for the convolution / dense families, bytes for the others), launches[f]. */
+int msr_profile_read(double* ms, double* work, int64_t* launches);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Tiling / blending  (process_full_tiles.py)
  * ------------------------------------------------------------------------------------------------------------- */
 
 /* padInputs (process_full_tiles.py:246-267): fill both (CH, CW) canvases with no_value and paste the (H, W) rasters
- * at [off, off + H) x [off, off + W). */
+ * at rows [off_y, off_y + H) x columns [off_x, off_x + W), clipped to the canvas.  The reference has off_y = off_x =
+ * off; a rank that holds only a band of canvas rows passes the band's row offset (off_y may be negative). */
 int msr_pad_inputs(const float* d_dem, const float* d_img, int H, int W, float* d_dem_canvas, float* d_img_canvas,
-                   int CH, int CW, int off, float no_value, void* stream);
+                   int CH, int CW, int off_y, int off_x, float no_value, void* stream);
 
 /* getPatch's validity test (process_full_tiles.py:286-292), factored: summed-area table of the invalid mask
  * (img <= no_value || dem <= no_value).  d_sat is int32 (CH + 1, CW + 1), first row / column zero. */

@@ -1,5 +1,6 @@
 // C-ABI glue: error reporting, device queries and the single-operator entry points used by the parity tests.
 #include <algorithm>
+#include <vector>
 
 #include "nn.cuh"
 
@@ -11,9 +12,75 @@ int fail(int code, const std::string& s) {
   g_last_error = s;
   return code;
 }
+
+// ---- profiler -----------------------------------------------------------------------------------------------------
+bool g_profiling = false;
+namespace {
+struct ProfRecord {
+  int family;
+  cudaEvent_t e0, e1;
+  double work;
+  int launches;
+};
+std::vector<ProfRecord> g_records;
+std::vector<cudaEvent_t> g_open;  // begin events of the scopes in flight (scopes nest at most a few deep)
+}  // namespace
+void profile_begin(int family, cudaStream_t st) {
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  cudaEventRecord(e, st);
+  g_open.push_back(e);
+}
+void profile_end(int family, cudaStream_t st, double work, int launches) {
+  if (g_open.empty()) return;
+  ProfRecord r;
+  r.family = family;
+  r.e0 = g_open.back();
+  g_open.pop_back();
+  cudaEventCreate(&r.e1);
+  cudaEventRecord(r.e1, st);
+  r.work = work;
+  r.launches = launches;
+  g_records.push_back(r);
+}
+static void profile_clear() {
+  for (auto& r : g_records) {
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  g_records.clear();
+  for (auto e : g_open) cudaEventDestroy(e);
+  g_open.clear();
+}
 }  // namespace msr
 
 using namespace msr;
+
+extern "C" int msr_profile_enable(int on) {
+  profile_clear();
+  g_profiling = on != 0;
+  return MSR_OK;
+}
+
+extern "C" int msr_profile_read(double* ms, double* work, int64_t* launches) {
+  MSR_REQUIRE(ms && work && launches, "msr_profile_read: null pointer");
+  MSR_CUDA_CHECK(cudaDeviceSynchronize());
+  for (int f = 0; f < MSR_PROF_COUNT; ++f) {
+    ms[f] = 0.0;
+    work[f] = 0.0;
+    launches[f] = 0;
+  }
+  for (auto& r : g_records) {
+    float t = 0.f;
+    MSR_CUDA_CHECK(cudaEventElapsedTime(&t, r.e0, r.e1));
+    if (r.family >= 0 && r.family < MSR_PROF_COUNT) {
+      ms[r.family] += t;
+      work[r.family] += r.work;
+      launches[r.family] += r.launches;
+    }
+  }
+  return MSR_OK;
+}
 
 extern "C" int msr_version(void) { return 100; }
 extern "C" const char* msr_last_error(void) { return g_last_error.c_str(); }

@@ -35,4 +35,20 @@ static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b)
 extern thread_local int64_t g_launch_count;
 static inline void count_launch(int n = 1) { g_launch_count += n; }
 
+// ---- per-family event timing (msr_profile_enable / msr_profile_read) ---------------------------------------------
+extern bool g_profiling;
+void profile_begin(int family, cudaStream_t st);
+void profile_end(int family, cudaStream_t st, double work, int launches);
+struct ProfileScope {
+  int family, launches;
+  cudaStream_t st;
+  double work;
+  ProfileScope(int f, cudaStream_t s, double w, int n = 1) : family(f), launches(n), st(s), work(w) {
+    if (g_profiling) profile_begin(family, st);
+  }
+  ~ProfileScope() {
+    if (g_profiling) profile_end(family, st, work, launches);
+  }
+};
+
 }  // namespace msr

@@ -510,6 +510,7 @@ int conv_tc_plan_create(ConvTC** out, const ConvTCArgs& a) {
 
 int conv_tc_launch(const ConvTC* p, cudaStream_t st) {
   MSR_REQUIRE(p, "conv_tc_launch: null plan");
+  ProfileScope prof(MSR_PROF_CONV_TC, st, 2.0 * (double)p->g.n * p->g.r * p->g.r * p->g.ncols * 9.0 * p->g.cin);
   if (p->bn == 256)
     tc::conv3x3_tc_kernel<256><<<p->grid, tc::kThreads, tc::Cfg<256>::kSmemBytes, st>>>(p->map_a, p->map_b, p->g, p->ep);
   else

@@ -164,6 +164,7 @@ int conv_f32(const ConvF32& p, cudaStream_t st) {
   MSR_REQUIRE(p.x && p.w && p.y && p.n > 0 && p.cin > 0 && p.cout > 0, "conv_f32: bad arguments");
   const int64_t M = (int64_t)p.n * p.Ho * p.Wo;
   dim3 grid(ceil_div(M, BM), ceil_div(p.cout, BN));
+  ProfileScope prof(MSR_PROF_CONV_F32, st, 2.0 * (double)M * p.cout * p.kh * p.kw * p.cin / (p.transposed ? p.stride * p.stride : 1));
   conv_f32_kernel<<<grid, 256, 0, st>>>(p);
   count_launch();
   MSR_LAUNCH_CHECK();
@@ -236,6 +237,7 @@ template <typename T>
 static int channel_stats_impl(const T* x, int ld, int groups, int64_t rows, int C, float eps, double* partial,
                               float* mean, float* rstd, cudaStream_t st) {
   MSR_REQUIRE(x && partial && mean && rstd && groups > 0 && rows > 0 && C > 0, "channel_stats: bad arguments");
+  ProfileScope prof(MSR_PROF_STATS, st, (double)groups * rows * C * sizeof(T), 2);
   stats_partial_kernel<T><<<dim3(ceil_div(C, 32), kStatSplit, groups), 256, 0, st>>>(x, ld, rows, C, partial);
   MSR_LAUNCH_CHECK();
   stats_finalize_kernel<<<dim3(ceil_div(C, 128), groups), 128, 0, st>>>(partial, C, rows, eps, mean, rstd);
@@ -291,6 +293,7 @@ __global__ void __launch_bounds__(256) spade_modulate_kernel(const float* __rest
 int spade_modulate_f32(const float* gb, const float* x, int x_shift, const float* mean, const float* rstd, float* out,
                        int n, int r, int C, int samples_per_group, float slope, cudaStream_t st) {
   MSR_REQUIRE(gb && x && mean && rstd && out && C % 4 == 0, "spade_modulate: bad arguments");
+  ProfileScope prof(MSR_PROF_ELEMWISE, st, (double)n * r * r * C * 4.0 * 4.0);
   const int64_t total = (int64_t)n * r * r * (C / 4);
   const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 32);
   spade_modulate_kernel<<<blocks, 256, 0, st>>>(gb, x, x_shift, mean, rstd, out, n, r, C, samples_per_group, slope);
@@ -328,6 +331,7 @@ int affine_act_f32(const float* x, int ldx, const float* mean, const float* rstd
                    const float* beta, float* y, int ldy, int64_t M, int C, int64_t rows_per_group, int act,
                    float slope, cudaStream_t st) {
   MSR_REQUIRE(x && y && M > 0 && C > 0 && rows_per_group > 0, "affine_act: bad arguments");
+  ProfileScope prof(MSR_PROF_ELEMWISE, st, (double)M * C * 8.0);
   const int64_t total = M * C;
   const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 32);
   affine_act_kernel<<<blocks, 256, 0, st>>>(x, ldx, mean, rstd, gamma, beta, y, ldy, M, C, rows_per_group, act, slope);
@@ -377,6 +381,7 @@ __global__ void dense_reduce_kernel(const float* __restrict__ partial, const flo
 int dense_f32(const float* x, const float* w, const float* bias, float* out, int M, int K, int N, float* partial,
               int64_t partial_capacity, cudaStream_t st) {
   MSR_REQUIRE(x && w && out && partial && M > 0 && K > 0 && N > 0, "dense: bad arguments");
+  ProfileScope prof(MSR_PROF_DENSE, st, 2.0 * M * (double)K * N, 2);
   int ksplit = std::max(1, std::min(64, K / 512));
   while ((int64_t)ksplit * M * N > partial_capacity && ksplit > 1) --ksplit;
   MSR_REQUIRE((int64_t)ksplit * M * N <= partial_capacity, "dense: partial scratch too small");
@@ -399,6 +404,7 @@ __global__ void sampler_kernel(const float* __restrict__ mean, const float* __re
 
 int sampler_f32(const float* mean, const float* var, const float* eps, float* latent, int64_t count, cudaStream_t st) {
   MSR_REQUIRE(mean && var && latent && count > 0, "sampler: bad arguments");
+  ProfileScope prof(MSR_PROF_ELEMWISE, st, (double)count * 16.0);
   sampler_kernel<<<ceil_div(count, 256), 256, 0, st>>>(mean, var, eps, latent, count);
   count_launch();
   MSR_LAUNCH_CHECK();
@@ -470,6 +476,7 @@ __global__ void __launch_bounds__(256) final_conv_kernel(const float* __restrict
 int final_conv_f32(const float* x, const float* w, const float* bias, float* out, int n, int r, cudaStream_t st) {
   MSR_REQUIRE(x && w && out && n > 0 && r > 0, "final_conv: bad arguments");
   MSR_REQUIRE((2 * r) % FC_TX == 0, "final_conv: output side must be a multiple of 16");
+  ProfileScope prof(MSR_PROF_FINAL_CONV, st, (double)n * r * r * 128 * 4.0 + (double)n * 4.0 * r * r * 4.0);
   final_conv_kernel<<<dim3(2 * r / FC_TX, 2 * r / FC_TY, n), 256, 0, st>>>(x, w, bias, out, n, r);
   count_launch();
   MSR_LAUNCH_CHECK();
@@ -524,6 +531,7 @@ __global__ void __launch_bounds__(256) mask_conv_kernel(const float* __restrict_
 int mask_conv_bf16(const float* source, int I, const float* w, const float* bias, __nv_bfloat16* out, int n, int r,
                    cudaStream_t st) {
   MSR_REQUIRE(source && w && bias && out && r > 0 && I % r == 0, "mask_conv: bad arguments");
+  ProfileScope prof(MSR_PROF_MASK_CONV, st, (double)n * r * r * (8.0 + 256.0));
   const int64_t total = (int64_t)n * r * r * 16;
   const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 16);
   mask_conv_kernel<<<blocks, 256, 0, st>>>(source, I, w, bias, out, n, r);

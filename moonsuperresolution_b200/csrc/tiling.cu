@@ -13,18 +13,19 @@ namespace msr {
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) pad_inputs_kernel(const float* __restrict__ dem, const float* __restrict__ img,
                                                          int H, int W, float* __restrict__ dem_c,
-                                                         float* __restrict__ img_c, int CH, int CW, int off, float nv) {
+                                                         float* __restrict__ img_c, int CH, int CW, int off_y,
+                                                         int off_x, float nv) {
   const int64_t quads_per_row = (CW + 3) / 4;
   const int64_t total = quads_per_row * CH;
   for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
     const int y = (int)(q / quads_per_row);
     const int x0 = (int)(q % quads_per_row) * 4;
-    const int sy = y - off;
+    const int sy = y - off_y;
     const bool row_in = (sy >= 0) && (sy < H);
     float d[4], m[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int sx = x0 + j - off;
+      const int sx = x0 + j - off_x;
       const bool in = row_in && sx >= 0 && sx < W;
       d[j] = in ? __ldg(dem + (int64_t)sy * W + sx) : nv;
       m[j] = in ? __ldg(img + (int64_t)sy * W + sx) : nv;
@@ -326,13 +327,15 @@ __global__ void __launch_bounds__(256) blend_tile_kernel(const void* const* __re
 using namespace msr;
 
 extern "C" int msr_pad_inputs(const float* d_dem, const float* d_img, int H, int W, float* d_dem_canvas,
-                              float* d_img_canvas, int CH, int CW, int off, float no_value, void* stream) {
+                              float* d_img_canvas, int CH, int CW, int off_y, int off_x, float no_value,
+                              void* stream) {
   MSR_REQUIRE(d_dem && d_img && d_dem_canvas && d_img_canvas, "msr_pad_inputs: null pointer");
-  MSR_REQUIRE(H > 0 && W > 0 && off >= 0 && CH >= H + off && CW >= W + off, "msr_pad_inputs: bad geometry");
+  MSR_REQUIRE(H > 0 && W > 0 && CH > 0 && CW > 0 && off_x >= 0 && CW >= W + off_x, "msr_pad_inputs: bad geometry");
   const int64_t quads = (int64_t)((CW + 3) / 4) * CH;
+  ProfileScope prof(MSR_PROF_PAD, (cudaStream_t)stream, 8.0 * ((double)H * W + (double)CH * CW));
   const int blocks = (int)std::min<int64_t>((quads + 255) / 256, 148 * 16);
   pad_inputs_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_dem, d_img, H, W, d_dem_canvas, d_img_canvas, CH, CW,
-                                                              off, no_value);
+                                                              off_y, off_x, no_value);
   count_launch();
   MSR_LAUNCH_CHECK();
   return MSR_OK;
@@ -342,7 +345,8 @@ extern "C" int msr_validity_sat(const float* d_img_canvas, const float* d_dem_ca
                                 int32_t* d_sat, void* stream) {
   MSR_REQUIRE(d_img_canvas && d_dem_canvas && d_sat && CH > 0 && CW > 0, "msr_validity_sat: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
-  sat_rows_kernel<<<CH, 256, 0, st>>>(d_img_canvas, d_dem_canvas, CH, CW, no_value, d_sat);
+  sat_rows_kernel
+<<<CH, 256, 0, st>>>(d_img_canvas, d_dem_canvas, CH, CW, no_value, d_sat);
   MSR_LAUNCH_CHECK();
   sat_cols_kernel<<<ceil_div(CW + 1, 256), 256, 0, st>>>(CH, CW, d_sat);
   MSR_LAUNCH_CHECK();
@@ -354,7 +358,8 @@ extern "C" int msr_patch_validity(const int32_t* d_sat, int CH, int CW, const in
                                   uint8_t* d_valid, void* stream) {
   MSR_REQUIRE(d_sat && d_xy && d_valid && n >= 0 && I > 0, "msr_patch_validity: bad arguments");
   if (n == 0) return MSR_OK;
-  patch_validity_kernel<<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(d_sat, CH, CW, d_xy, n, I, d_valid);
+  patch_validity_kernel
+<<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(d_sat, CH, CW, d_xy, n, I, d_valid);
   count_launch();
   MSR_LAUNCH_CHECK();
   return MSR_OK;
@@ -368,6 +373,7 @@ extern "C" int msr_gather_normalize(const float* d_img_canvas, const float* d_de
   MSR_REQUIRE(n >= 0 && I > 0 && CH >= I && CW >= I, "msr_gather_normalize: bad geometry");
   if (n == 0) return MSR_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  ProfileScope prof(MSR_PROF_GATHER, st, (double)n * I * I * (8.0 + 8.0 + 8.0), 2);
   patch_minmax_kernel<<<dim3(n, kMinMaxSplit), 256, 0, st>>>(d_img_canvas, d_dem_canvas, CW, d_xy, I, d_partial);
   MSR_LAUNCH_CHECK();
   const int ysplit = std::max(1, std::min(64, (I * I) / 2048));
@@ -389,6 +395,8 @@ extern "C" int msr_blend_tile(const void* const* d_patch_ptr, const uint8_t* d_p
   MSR_REQUIRE(rows >= 0 && cols >= 0 && rows <= T && cols <= T && pitch >= cols, "msr_blend_tile: bad output window");
   MSR_REQUIRE(d_lattice == nullptr || G > 0, "msr_blend_tile: lattice needs G > 0");
   if (rows == 0 || cols == 0) return MSR_OK;
+  ProfileScope prof(MSR_PROF_BLEND, (cudaStream_t)stream,
+                    (double)n * (I - 2 * (I / 16)) * (I - 2 * (I / 16)) * 4.0 + (double)rows * cols * 9.0);
   blend_tile_kernel<<<dim3(ceil_div(cols, 256), rows), 256, 0, (cudaStream_t)stream>>>(
       d_patch_ptr, d_patch_f64, d_patch_lohi, d_patch_xy, n, d_lattice, G, d_weights, I, S, T, add_half, no_value,
       d_mean, d_std, d_good, pitch, rows, cols);

@@ -1,0 +1,548 @@
+"""Tiled full-DEM super-resolution engine: a drop-in for ``DEMSuperResolution`` of the reference
+(process_full_tiles.py:129-587) whose pixel work runs in libmoonsr.so on a B200.
+
+Same class name, constructor ``(config, model=callable)``, attribute names and method names as the reference, same tile
+/ overlap parameters and output layout (mean SR DEM, weighted population std, good mask; no_value outside ``good``).
+What differs is where the data lives:
+
+  * ``padInputs`` uploads the rasters once and builds the no_value canvases, the validity summed-area table and the
+    validity of every patch of every tile ON THE DEVICE (process_full_tiles.py:246-293);
+  * ``processTile`` gathers + normalises patches, runs the generator and blends, all on the device; the tile result is
+    written straight into the (H, W) output rasters, which fuses the paste + crop of ``rebuildMap``
+    (process_full_tiles.py:431-479, 541-545).  Per-tile TIFFs -- the reference's RAM-spill mechanism -- are written only
+    when ``save_tiles`` is set;
+  * a model that is one of this package's generators (``models.GauGAN`` ...) is called through its device entry point;
+    any other callable obeying the reference's plug-in contract ``m(x, training=False)`` is fed host numpy batches
+    exactly as the reference would (including the float64 promotion of zero-padded batches, :472).
+
+Multi-GPU (mode A): ``rank`` / ``world_size`` give each process a contiguous band of tile rows; a rank
+holds only the canvas rows its band needs; tiles are self-sufficient so no data crosses ranks on the path.
+
+There is no CPU fallback: without libmoonsr.so or a CUDA device the engine raises.
+"""
+from __future__ import annotations
+
+import dataclasses
+import os
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+from . import _lib
+from .models import _Generator
+from .distributed import band_of_rank, gather_bands
+from .planner import PAD_SLOT, Plan
+
+
+@dataclasses.dataclass
+class DSRConfig:
+    """process_full_tiles.py:53-66, field for field; the trailing fields are additions whose defaults reproduce the
+    reference's behaviour."""
+    image_size: int = 256
+    stride: int = 32
+    batch_size: int = 16
+    tile_size: int = 1024
+    no_value: float = -32768.0
+    upsample_factor: float = 1.0
+    map_name: str = None
+    save_path: str = None
+    source_folder_path: str = None
+    ortho_image_name: str = "run-DRG.tif"
+    dem_name: str = "run-DEM.tif"
+    model_path: str = None
+    # ---- additions ----
+    save_tiles: bool = False        # write the per-tile TIFFs of saveTile (process_full_tiles.py:416-429)
+    groups_per_call: int = 0        # batches pushed through one generator call (0 = the model's max_groups)
+    seed: int = 0                   # seeds the Gaussian sampler's noise (the reference's is unseeded)
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise _lib.MoonSRError("no CUDA device: DEMSuperResolution runs only on the GPU (there is no CPU fallback)")
+    return torch
+
+
+def _identity(x, training=False):
+    return x
+
+
+class DEMSuperResolution:
+    """See the module docstring.  Reference: process_full_tiles.py:129-155."""
+
+    def __init__(self, config: DSRConfig, model=_identity, rank: int = 0, world_size: int = 1, device=None) -> None:
+        self.map_name = config.map_name
+        self.save_path = config.save_path
+        self.folder_path = config.source_folder_path
+        self.left_image_name = config.ortho_image_name
+        self.dem_name = config.dem_name
+        self.no_value = config.no_value
+        self.stride = config.stride
+        self.image_size = config.image_size
+        self.batch_size = config.batch_size
+        self.upsample_factor = 1
+        self.tile_size = config.tile_size
+        self.model = model
+        # ---- additions
+        self.save_tiles = bool(getattr(config, "save_tiles", False))
+        self.seed = int(getattr(config, "seed", 0))
+        self.rank, self.world_size = int(rank), int(world_size)
+        self._groups_cfg = int(getattr(config, "groups_per_call", 0))
+        self._lib = _lib.lib()
+        torch = _torch()
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.dem = self.img = None
+        self.geo_transform = self.geo_projection = None
+        self.plan: Optional[Plan] = None
+        self.launches = 0              # kernel launches issued through the C ABI by this engine (excluding the model)
+        self.model_launches = 0
+        self.slots_executed = 0
+        self._weights_dev = None
+
+    # ---------------------------------------------------------------------------------------------------------------
+    # inputs
+    # ---------------------------------------------------------------------------------------------------------------
+    def setRasters(self, dem: np.ndarray, img: np.ndarray, geo_transform=None, geo_projection=None) -> None:
+        """In-memory equivalent of loadImages (process_full_tiles.py:158-182).  Accepts host numpy arrays (uploaded by
+        padInputs) or float32 CUDA tensors that are already resident on this engine's device."""
+        if hasattr(dem, "is_cuda"):
+            if not (dem.is_cuda and img.is_cuda and str(dem.dtype) == "torch.float32" and str(img.dtype) == "torch.float32"):
+                raise ValueError("tensor rasters must be float32 CUDA tensors")
+        else:
+            dem = np.ascontiguousarray(dem, dtype=np.float32)
+            img = np.ascontiguousarray(img, dtype=np.float32)
+        if dem.ndim != 2 or tuple(img.shape) != tuple(dem.shape):
+            raise ValueError("dem and ortho-image must be 2-D arrays of the same shape")
+        self.dem, self.img = dem, img
+        self.geo_transform, self.geo_projection = geo_transform, geo_projection
+        self.dem_shape, self.img_shape = tuple(dem.shape), tuple(img.shape)
+
+    def loadImages(self) -> None:
+        """process_full_tiles.py:158-182 -- band 1 of both GeoTIFFs as float32 plus the DEM's geo-referencing."""
+        from . import geotiff
+        img_path = os.path.join(self.folder_path, self.left_image_name)
+        dem_path = os.path.join(self.folder_path, self.dem_name)
+        if not os.path.exists(img_path):
+            raise ValueError("The path given for the ortho-image does not exist. Provided path is: " + img_path)
+        if not os.path.exists(dem_path):
+            raise ValueError("The path given for the dem does not exist. Provided path is: " + dem_path)
+        img, _ = geotiff.read(img_path)
+        dem, geo = geotiff.read(dem_path)
+        self.setRasters(dem.astype(np.float32), img.astype(np.float32), geo, geo)
+
+    def preprocess(self) -> None:
+        """process_full_tiles.py:226-244 (hole filling + /16 blur of the DEM) is the step BEFORE the hot path and is
+        out of scope of this build; inputs are taken as already pre-filtered."""
+        return
+
+    # ---------------------------------------------------------------------------------------------------------------
+    # padInputs (+ validity of every patch)
+    # ---------------------------------------------------------------------------------------------------------------
+    def _band(self) -> Tuple[List[Tuple[int, int]], int, int]:
+        """Tiles of this rank and the canvas row range [c0, c1) they read."""
+        plan = self.plan
+        tiles, _, _ = band_of_rank(plan, self.world_size, self.rank)
+        if not tiles:
+            return [], 0, 0
+        y0 = min(yy for _, yy in tiles)
+        y1 = max(yy for _, yy in tiles)
+        return tiles, y0, min(plan.canvas_h, y1 + plan.tile_size + 2 * plan.off)
+
+    def padInputs(self) -> None:
+        """process_full_tiles.py:246-267 on the device, for this rank's band of canvas rows."""
+        torch = _torch()
+        if self.dem is None or self.img is None:
+            raise ValueError("no rasters loaded: call loadImages() or setRasters() first")
+        h, w = self.dem_shape
+        self.plan = plan = Plan(h, w, self.image_size, self.stride, self.tile_size, self.batch_size)
+        self.pad_x, self.pad_y = plan.pad_x, plan.pad_y
+        self.dem_padded_shape = self.img_padded_shape = (plan.canvas_h, plan.canvas_w)
+        self.my_tiles, c0, c1 = self._band()
+        self._c0, self._ch = c0, max(c1 - c0, 0)
+        st = _lib.stream_ptr()
+        nv = float(np.float32(self.no_value))
+        if self._ch > 0:
+            # raster rows that fall inside canvas rows [c0, c1): canvas row = raster row + off
+            r0, r1 = max(0, c0 - plan.off), min(h, c1 - plan.off)
+            self._r0 = r0
+            if torch.is_tensor(self.dem):
+                d_dem, d_img = self.dem[r0:r1].contiguous(), self.img[r0:r1].contiguous()
+            else:
+                d_dem = torch.from_numpy(self.dem[r0:r1]).to(self.device, non_blocking=True)
+                d_img = torch.from_numpy(self.img[r0:r1]).to(self.device, non_blocking=True)
+            self.dem_padded = torch.empty((self._ch, plan.canvas_w), dtype=torch.float32, device=self.device)
+            self.img_padded = torch.empty_like(self.dem_padded)
+            if r1 > r0:
+                _lib.check(self._lib.msr_pad_inputs(d_dem.data_ptr(), d_img.data_ptr(), r1 - r0, w,
+                                                    self.dem_padded.data_ptr(), self.img_padded.data_ptr(), self._ch,
+                                                    plan.canvas_w, r0 + plan.off - c0, plan.off, nv, st),
+                           "msr_pad_inputs")
+                self.launches += 1
+            else:
+                self.dem_padded.fill_(nv)
+                self.img_padded.fill_(nv)
+            self._sat = torch.empty((self._ch + 1, plan.canvas_w + 1), dtype=torch.int32, device=self.device)
+            _lib.check(self._lib.msr_validity_sat(self.img_padded.data_ptr(), self.dem_padded.data_ptr(), self._ch,
+                                                  plan.canvas_w, nv, self._sat.data_ptr(), st), "msr_validity_sat")
+            self.launches += 2
+        # the reference releases the originals here (:265-266)
+        self.dem = None
+        self.img = None
+        self._plan_tiles()
+        # output rasters of this rank's band (rows [out_r0, out_r1) of the (H, W) result)
+        if self.my_tiles:
+            self._out_r0 = min(yy for _, yy in self.my_tiles)
+            self._out_r1 = min(h, max(yy for _, yy in self.my_tiles) + plan.tile_size)
+        else:
+            self._out_r0 = self._out_r1 = 0
+        rows = self._out_r1 - self._out_r0
+        self.mean_out = torch.zeros((rows, w), dtype=torch.float32, device=self.device)
+        self.std_out = torch.zeros((rows, w), dtype=torch.float32, device=self.device)
+        self.good_out = torch.zeros((rows, w), dtype=torch.uint8, device=self.device)
+        return
+
+    def _plan_tiles(self) -> None:
+        """Validity of every patch of every tile of the band (getPatch, process_full_tiles.py:286-292) in one kernel
+        call, then the host-side batch plan (process_full_tiles.py:459-474)."""
+        torch = _torch()
+        plan = self.plan
+        self._tile_plan: Dict[Tuple[int, int], dict] = {}
+        if not self.my_tiles:
+            return
+        origins = [plan.tile_patch_origins(px, py) for px, py in self.my_tiles]
+        all_xy = np.concatenate(origins, axis=0)
+        local = all_xy.copy()
+        local[:, 1] -= self._c0
+        d_xy = torch.from_numpy(local).to(self.device)
+        d_valid = torch.empty((local.shape[0],), dtype=torch.uint8, device=self.device)
+        _lib.check(self._lib.msr_patch_validity(self._sat.data_ptr(), self._ch, plan.canvas_w, d_xy.data_ptr(),
+                                                local.shape[0], plan.image_size, d_valid.data_ptr(),
+                                                _lib.stream_ptr()), "msr_patch_validity")
+        self.launches += 1
+        valid = d_valid.cpu().numpy().astype(bool)
+        g2 = plan.lattice_side ** 2
+        for t, (px, py) in enumerate(self.my_tiles):
+            v = valid[t * g2:(t + 1) * g2]
+            idx = np.nonzero(v)[0]
+            lattice = np.full((g2,), -1, np.int32)
+            lattice[idx] = np.arange(idx.size, dtype=np.int32)
+            self._tile_plan[(px, py)] = dict(xy=origins[t][idx], lattice=lattice, n_valid=int(idx.size))
+
+    # ---------------------------------------------------------------------------------------------------------------
+    # reference-compatible per-patch helpers
+    # ---------------------------------------------------------------------------------------------------------------
+    def getPatch(self, px: int, py: int):
+        """process_full_tiles.py:269-293 -- (valid, img_patch, dem_patch) as numpy arrays (a D2H copy; the fast path
+        never calls this)."""
+        i = self.image_size
+        ly = py - self._c0
+        img = self.img_padded[ly:ly + i, px:px + i].cpu().numpy()
+        dem = self.dem_padded[ly:ly + i, px:px + i].cpu().numpy()
+        valid = not ((img <= self.no_value).any() or (dem <= self.no_value).any())
+        return valid, img, dem
+
+    def normalize(self, img_patch: np.ndarray, dem_patch: np.ndarray):
+        """process_full_tiles.py:295-311 through the device kernel (patches are uploaded as a 1-patch canvas)."""
+        torch = _torch()
+        i = self.image_size
+        d_img = torch.from_numpy(np.ascontiguousarray(img_patch, dtype=np.float32)).to(self.device)
+        d_dem = torch.from_numpy(np.ascontiguousarray(dem_patch, dtype=np.float32)).to(self.device)
+        xy = torch.zeros((1, 2), dtype=torch.int32, device=self.device)
+        out = torch.empty((1, i, i, 2), dtype=torch.float32, device=self.device)
+        mm = torch.empty((1, 4), dtype=torch.float32, device=self.device)
+        part = torch.empty((1 * 32 * 4,), dtype=torch.float32, device=self.device)
+        _lib.check(self._lib.msr_gather_normalize(d_img.data_ptr(), d_dem.data_ptr(), i, i, xy.data_ptr(), 1, i,
+                                                  out.data_ptr(), mm.data_ptr(), part.data_ptr(), _lib.stream_ptr()),
+                   "msr_gather_normalize")
+        self.launches += 2
+        mmh = mm.cpu().numpy()[0]
+        return out.cpu().numpy()[0], (np.float32(mmh[2]), np.float32(mmh[3]))
+
+    def generateTileList(self) -> List[Tuple[int, int]]:
+        """process_full_tiles.py:313-325 (all tiles, not only this rank's)."""
+        if self.plan is not None:
+            return self.plan.tiles()
+        return [(xx, yy) for yy in range(0, self.dem_shape[0], self.tile_size)
+                for xx in range(0, self.dem_shape[1], self.tile_size)]
+
+    def processBatch(self, batch, batch_index, patches: dict) -> None:
+        """process_full_tiles.py:327-345, host-array form (compatibility; processTile does not use it)."""
+        pred_dems = self.model(np.array(batch), training=False)
+        pred_dems = np.array(pred_dems)[:, :, :, -1] + 0.5
+        for pred_dem, pred_idx in zip(pred_dems, batch_index):
+            if pred_idx != PAD_SLOT:
+                patches[pred_idx] = pred_dem
+
+    def makeGaussianKernel(self) -> np.ndarray:
+        """process_full_tiles.py:347-361 -- float64 host table (built once per run, I*I doubles)."""
+        i = self.image_size
+        s = i / 5
+
+        def gaus2d(x=0, y=0, mx=0, my=0, sx=1, sy=1):
+            return 1. / (2. * np.pi * sx * sy) * np.exp(-((x - mx) ** 2. / (2. * sx ** 2.) + (y - my) ** 2. / (2. * sy ** 2.)))
+        x = np.linspace(-i / 2, i / 2, i)
+        y = np.linspace(-i / 2, i / 2, i)
+        x, y = np.meshgrid(x, y)
+        kern = gaus2d(x, y, sx=s, sy=s)
+        return (kern - kern.min()) / (kern.max() - kern.min())
+
+    def _blend_weights(self):
+        """makeGaussianKernel() + 1e-7, purge-cropped (process_full_tiles.py:391-393), resident on the device."""
+        if self._weights_dev is None:
+            torch = _torch()
+            p = self.image_size // 16
+            w = self.makeGaussianKernel() + 1e-7
+            w = np.ascontiguousarray(w[p:-p, p:-p])
+            self._weights_dev = torch.from_numpy(w).to(self.device)
+        return self._weights_dev
+
+    # ---------------------------------------------------------------------------------------------------------------
+    # blend
+    # ---------------------------------------------------------------------------------------------------------------
+    def _blend(self, ptrs, f64flags, lohi, pxy, n, lattice, add_half, mean, std, good, pitch, rows, cols) -> None:
+        plan_i, plan_s, plan_t = self.image_size, self.stride, self.tile_size
+        g = -(-(plan_t + plan_i - plan_s) // plan_s)
+        _lib.check(self._lib.msr_blend_tile(_lib.ptr(ptrs), _lib.ptr(f64flags), _lib.ptr(lohi), _lib.ptr(pxy), n,
+                                            _lib.ptr(lattice), g, self._blend_weights().data_ptr(), plan_i, plan_s,
+                                            plan_t, int(add_half), float(np.float32(self.no_value)), mean, std, good,
+                                            pitch, rows, cols, _lib.stream_ptr()), "msr_blend_tile")
+        self.launches += 1
+
+    def rebuildTile(self, generated_dems: dict, generated_minmax: dict):
+        """process_full_tiles.py:363-414 -- same signature: dicts keyed by (x, y) relative to the tile origin, values
+        (I, I) predictions (after the + 0.5) and (min, max); returns (mean, std, good) of the full T x T tile as numpy
+        arrays.  The arithmetic runs in msr_blend_tile."""
+        torch = _torch()
+        t, i = self.tile_size, self.image_size
+        keys = list(generated_dems.keys())
+        n = len(keys)
+        mean = torch.empty((t, t), dtype=torch.float32, device=self.device)
+        std = torch.empty_like(mean)
+        good = torch.empty((t, t), dtype=torch.uint8, device=self.device)
+        keep, ptrs, flags = [], [], []
+        for k in keys:
+            a = np.asarray(generated_dems[k])
+            if a.dtype != np.float64:
+                a = a.astype(np.float32, copy=False)
+            d = torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
+            keep.append(d)
+            ptrs.append(d.data_ptr())
+            flags.append(1 if a.dtype == np.float64 else 0)
+        if n:
+            d_ptrs = torch.tensor(ptrs, dtype=torch.int64, device=self.device)
+            d_flags = torch.tensor(flags, dtype=torch.uint8, device=self.device)
+            lohi = np.array([[np.float32(generated_minmax[k][0]), np.float32(generated_minmax[k][1])] for k in keys],
+                            dtype=np.float32)
+            d_lohi = torch.from_numpy(lohi).to(self.device)
+            d_xy = torch.tensor([[k[0], k[1]] for k in keys], dtype=torch.int32, device=self.device)
+        else:
+            d_ptrs = d_flags = d_lohi = d_xy = None
+        self._blend(d_ptrs, d_flags, d_lohi, d_xy, n, None, 0, mean.data_ptr(), std.data_ptr(), good.data_ptr(), t, t, t)
+        torch.cuda.current_stream().synchronize()
+        return mean.cpu().numpy(), std.cpu().numpy(), good.cpu().numpy()
+
+    def saveTile(self, mean: np.ndarray, std: np.ndarray, good: np.ndarray, name: str) -> None:
+        """process_full_tiles.py:416-429 -- same directory / file names."""
+        from . import geotiff
+        d = os.path.join(self.save_path, "tile_" + name)
+        os.makedirs(d, exist_ok=True)
+        geotiff.write(os.path.join(d, "tile_" + name + "_mean.tif"), np.asarray(mean))
+        geotiff.write(os.path.join(d, "tile_" + name + "_std.tif"), np.asarray(std))
+        geotiff.write(os.path.join(d, "tile_" + name + "_correct.tif"), np.asarray(good))
+
+    # ---------------------------------------------------------------------------------------------------------------
+    # processTile
+    # ---------------------------------------------------------------------------------------------------------------
+    def _gather(self, d_slot_xy, n, out, minmax, partial) -> None:
+        plan = self.plan
+        _lib.check(self._lib.msr_gather_normalize(self.img_padded.data_ptr(), self.dem_padded.data_ptr(), self._ch,
+                                                  plan.canvas_w, d_slot_xy.data_ptr(), n, plan.image_size,
+                                                  out.data_ptr(), minmax.data_ptr(), partial.data_ptr(),
+                                                  _lib.stream_ptr()), "msr_gather_normalize")
+        self.launches += 2
+
+    def processTile(self, px: int, py: int, eps=None) -> None:
+        """process_full_tiles.py:431-479.  ``eps`` optionally supplies the sampler noise for every slot of the tile,
+        shape (slots, 256) (parity tests); by default a seeded per-tile stream is drawn on the device."""
+        torch = _torch()
+        plan = self.plan
+        if (px, py) not in self._tile_plan:
+            raise ValueError(f"tile ({px}, {py}) is not owned by rank {self.rank}")
+        tp = self._tile_plan[(px, py)]
+        i, b, t = plan.image_size, plan.batch_size, plan.tile_size
+        n_valid = tp["n_valid"]
+        slots = plan.batch_slots(n_valid)
+        rows, cols = plan.tile_window(px, py)
+        dev = self.device
+        out_off = (py - self._out_r0) * plan.width + px
+        mean_p = self.mean_out.data_ptr() + 4 * out_off
+        std_p = self.std_out.data_ptr() + 4 * out_off
+        good_p = self.good_out.data_ptr() + out_off
+        tile_bufs = None
+        if self.save_tiles:
+            tile_bufs = (torch.empty((t, t), dtype=torch.float32, device=dev),
+                         torch.empty((t, t), dtype=torch.float32, device=dev),
+                         torch.empty((t, t), dtype=torch.uint8, device=dev))
+        if n_valid == 0:
+            self._blend(None, None, None, None, 0, None, 0, mean_p, std_p, good_p, plan.width, rows, cols)
+            if tile_bufs:
+                self._blend(None, None, None, None, 0, None, 0, tile_bufs[0].data_ptr(), tile_bufs[1].data_ptr(),
+                            tile_bufs[2].data_ptr(), t, t, t)
+                self._save_tile_bufs(tile_bufs, px, py)
+            return
+        slot_xy = np.full((slots, 2), -1, np.int32)
+        slot_xy[:n_valid] = tp["xy"]
+        slot_xy[:n_valid, 1] -= self._c0
+        d_slot_xy = torch.from_numpy(slot_xy).to(dev, non_blocking=True)
+        key_xy = tp["xy"].copy()
+        key_xy[:, 0] -= px
+        key_xy[:, 1] -= py
+        d_key_xy = torch.from_numpy(key_xy).to(dev, non_blocking=True)
+        d_lattice = torch.from_numpy(tp["lattice"]).to(dev, non_blocking=True)
+        minmax = torch.empty((slots, 4), dtype=torch.float32, device=dev)
+        device_model = isinstance(self.model, _Generator)
+        if device_model:
+            groups = self._groups_cfg or self.model.max_groups
+            groups = max(1, min(groups, self.model.max_groups))
+            chunk = groups * b
+            pred = torch.empty((slots, i, i), dtype=torch.float32, device=dev)
+            src = torch.empty((min(chunk, slots), i, i, 2), dtype=torch.float32, device=dev)
+            partial = torch.empty((min(chunk, slots) * 32 * 4,), dtype=torch.float32, device=dev)
+            if self.model.arch == "spade":
+                if eps is None:
+                    gen = torch.Generator(device=dev)
+                    gen.manual_seed((self.seed * 1000003 + py * 131071 + px) & 0x7FFFFFFFFFFF)
+                    d_eps = torch.randn((slots, 256), generator=gen, dtype=torch.float32, device=dev)
+                else:
+                    d_eps = torch.as_tensor(np.ascontiguousarray(eps, dtype=np.float32)).to(dev)
+                    if tuple(d_eps.shape) != (slots, 256):
+                        raise ValueError(f"eps must have shape {(slots, 256)}")
+            else:
+                d_eps = None
+            for s0 in range(0, slots, chunk):
+                n = min(chunk, slots - s0)
+                self._gather(d_slot_xy[s0:s0 + n], n, src, minmax[s0:s0 + n], partial)
+                self.model.forward_device(src[:n], pred[s0:s0 + n], None if d_eps is None else d_eps[s0:s0 + n],
+                                          n // b)
+                self.model_launches += self.model.last_launch_count
+            ptrs = pred.data_ptr() + torch.arange(n_valid, dtype=torch.int64, device=dev) * (i * i * 4)
+            flags, add_half, keep = None, 1, [pred]
+        else:
+            ptrs, flags, keep = self._run_host_model(d_slot_xy, slots, n_valid, minmax)
+            add_half = 0
+        lohi = minmax[:n_valid, 2:4].contiguous()
+        self.slots_executed += slots
+        self._blend(ptrs, flags, lohi, d_key_xy, n_valid, d_lattice, add_half, mean_p, std_p, good_p, plan.width, rows,
+                    cols)
+        if tile_bufs:
+            self._blend(ptrs, flags, lohi, d_key_xy, n_valid, d_lattice, add_half, tile_bufs[0].data_ptr(),
+                        tile_bufs[1].data_ptr(), tile_bufs[2].data_ptr(), t, t, t)
+            self._save_tile_bufs(tile_bufs, px, py)
+        del keep
+
+    def _run_host_model(self, d_slot_xy, slots, n_valid, minmax):
+        """Generic ``model=`` callable: numpy batches on the host, exactly the reference's data flow
+        (process_full_tiles.py:327-345, 468-474)."""
+        torch = _torch()
+        plan = self.plan
+        i, b, dev = plan.image_size, plan.batch_size, self.device
+        src = torch.empty((b, i, i, 2), dtype=torch.float32, device=dev)
+        partial = torch.empty((b * 32 * 4,), dtype=torch.float32, device=dev)
+        keep, ptrs, flags = [], [], []
+        for s0 in range(0, slots, b):
+            self._gather(d_slot_xy[s0:s0 + b], b, src, minmax[s0:s0 + b], partial)
+            batch = src.cpu().numpy()
+            n_real = min(b, n_valid - s0)
+            if n_real < b:
+                batch = batch.astype(np.float64)          # np.array(batch) with float64 zero pads (:472) promotes
+            pred = self.model(batch, training=False)
+            pred = np.array(pred)[:, :, :, -1] + 0.5       # :340
+            if pred.dtype != np.float64:
+                pred = pred.astype(np.float32, copy=False)
+            d = torch.from_numpy(np.ascontiguousarray(pred[:n_real])).to(dev)
+            keep.append(d)
+            itemsize = 8 if pred.dtype == np.float64 else 4
+            for k in range(n_real):
+                ptrs.append(d.data_ptr() + k * i * i * itemsize)
+                flags.append(1 if itemsize == 8 else 0)
+        d_ptrs = torch.tensor(ptrs, dtype=torch.int64, device=dev)
+        d_flags = torch.tensor(flags, dtype=torch.uint8, device=dev)
+        return d_ptrs, d_flags, keep
+
+    def _save_tile_bufs(self, bufs, px, py) -> None:
+        m, s, g = (x.cpu().numpy() for x in bufs)
+        self.saveTile(m, s, g, str(px) + "_" + str(py))
+
+    # ---------------------------------------------------------------------------------------------------------------
+    # outputs
+    # ---------------------------------------------------------------------------------------------------------------
+    def saveGTiff(self, data: np.ndarray, data_type, name: str) -> None:
+        """process_full_tiles.py:481-531 -- same naming, same dtype promotion (uint8 -> UInt16), NoData = no_value,
+        geo-referencing of the input DEM; the container is written by geotiff.write (no GDAL)."""
+        from . import geotiff
+        if data_type == np.float32:
+            pass
+        elif data_type == np.uint8:
+            data = data.astype(np.uint16)
+        elif data_type == np.uint16:
+            pass
+        else:
+            raise ValueError("Unsupported data-type.")
+        if len(data.shape) < 2:
+            raise ValueError("Data is of incorrect shape. The array must be 2-dimensional at least.")
+        elif len(data.shape) > 3:
+            raise ValueError("Data is of incorrect shape")
+        geotiff.write(os.path.join(self.save_path, self.map_name + "_" + name + ".tiff"), data, geo=self.geo_transform
+                      if isinstance(self.geo_transform, dict) else None, nodata=self.no_value)
+
+    def results(self):
+        """(mean f32, std f32, good u8) of this rank's band as numpy arrays plus the band's first raster row."""
+        _torch().cuda.current_stream().synchronize()
+        return self.mean_out.cpu().numpy(), self.std_out.cpu().numpy(), self.good_out.cpu().numpy(), self._out_r0
+
+    def gatherResults(self):
+        """Full (H, W) rasters on rank 0 (None elsewhere).  Bands are disjoint row ranges, so this is a plain
+        gather of the output rows -- no arithmetic crosses ranks."""
+        mean, std, good, r0 = self.results()
+        res = gather_bands([mean, std, good], r0, self.plan.height, self.plan.width, self.rank, self.world_size)
+        return None if res is None else tuple(res)
+
+    def rebuildMap(self) -> None:
+        """process_full_tiles.py:533-566 -- the assembled rasters already exist on the device (processTile pasted and
+        cropped); fetch them and write the three GeoTIFFs."""
+        res = self.gatherResults()
+        if res is None:
+            return
+        mean, std, good = res
+        self.saveGTiff(mean, mean.dtype, "mean")
+        self.saveGTiff(std, std.dtype, "std")
+        self.saveGTiff(good, good.dtype, "good")
+
+    def processTiles(self) -> None:
+        """Every tile of this rank's band, in tile-list order (process_full_tiles.py:579-581)."""
+        for tile in self.my_tiles:
+            self.processTile(*tile)
+
+    def processMap(self) -> None:
+        """process_full_tiles.py:568-587."""
+        self.loadImages()
+        self.preprocess()
+        self.padInputs()
+        tile_list = self.generateTileList()
+        print("Cutting the image in", self.dem_shape[1] // self.tile_size + 1, "by",
+              self.dem_shape[0] // self.tile_size + 1, "tiles.")
+        for tile in tile_list:
+            if tuple(tile) in self._tile_plan:
+                print("Processing tile", tile[0], tile[1])
+                self.processTile(*tile)
+        self.dem_padded = None
+        self.img_padded = None
+        self.rebuildMap()
+        return
+
+    def run(self, dem: np.ndarray, img: np.ndarray):
+        """In-memory processMap: rasters in, (mean, std, good) of this rank's band out (numpy)."""
+        self.setRasters(dem, img)
+        self.padInputs()
+        self.processTiles()
+        return self.results()[:3]

@@ -1,0 +1,167 @@
+"""Minimal TIFF / BigTIFF raster container I/O for the engine's boundary (no GDAL in this stack).
+
+The reference reads band 1 of two GeoTIFFs with GDAL (process_full_tiles.py:158-182) and writes LZW GeoTIFFs
+(process_full_tiles.py:481-531).  This module covers the container only -- single-band, stripped, uncompressed,
+little-endian, classic TIFF below 4 GiB and BigTIFF above -- and carries the GeoTIFF tags of the input DEM through to
+the outputs verbatim.  Compression (LZW + predictor 2) is a later row of SURVEY.md section 8f.
+"""
+from __future__ import annotations
+
+import struct
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+
+# tags carried from the input DEM to the outputs (GeoTIFF + GDAL metadata)
+GEO_TAGS = (33550, 33922, 34264, 34735, 34736, 34737)
+TAG_GDAL_NODATA = 42113
+
+_TYPE_SIZE = {1: 1, 2: 1, 3: 2, 4: 4, 5: 8, 6: 1, 7: 1, 8: 2, 9: 4, 10: 8, 11: 4, 12: 8, 16: 8, 17: 8, 18: 8}
+_SAMPLE = {  # numpy dtype -> (SampleFormat, BitsPerSample)
+    np.dtype(np.uint8): (1, 8), np.dtype(np.uint16): (1, 16), np.dtype(np.int16): (2, 16),
+    np.dtype(np.uint32): (1, 32), np.dtype(np.int32): (2, 32), np.dtype(np.float32): (3, 32),
+    np.dtype(np.float64): (3, 64),
+}
+
+
+def write(path: str, data: np.ndarray, geo: Optional[Dict[int, Tuple[int, int, bytes]]] = None,
+          nodata: Optional[float] = None, rows_per_strip: int = 256) -> None:
+    """Writes a 2-D array as a single-band uncompressed TIFF (BigTIFF when it would not fit in 4 GiB)."""
+    a = np.ascontiguousarray(data)
+    if a.ndim == 3 and a.shape[2] == 1:
+        a = a[:, :, 0]
+    if a.ndim != 2:
+        raise ValueError("only single-band 2-D rasters are supported")
+    if a.dtype not in _SAMPLE:
+        raise ValueError(f"unsupported dtype {a.dtype}")
+    a = a.astype(a.dtype.newbyteorder("<"), copy=False)
+    fmt, bits = _SAMPLE[np.dtype(a.dtype.name)]
+    h, w = a.shape
+    n_strips = -(-h // rows_per_strip)
+    row_bytes = w * a.dtype.itemsize
+    big = a.nbytes + 65536 + 16 * n_strips >= (1 << 32)
+    off_t, off_code = ("<Q", 16) if big else ("<I", 4)
+    osz = 8 if big else 4
+    header = 16 if big else 8
+    counts = [min(rows_per_strip, h - s * rows_per_strip) * row_bytes for s in range(n_strips)]
+    offsets, cur = [], header
+    for c in counts:
+        offsets.append(cur)
+        cur += c
+    data_end = cur
+
+    entries = []  # (tag, type, count, payload bytes)
+
+    def short(tag, v):
+        entries.append((tag, 3, 1, struct.pack("<H", v)))
+
+    def long_(tag, v):
+        entries.append((tag, 4, 1, struct.pack("<I", v)))
+
+    long_(256, w)
+    long_(257, h)
+    short(258, bits)
+    short(259, 1)        # no compression
+    short(262, 1)        # BlackIsZero
+    entries.append((273, off_code, n_strips, b"".join(struct.pack(off_t, o) for o in offsets)))
+    short(277, 1)
+    long_(278, rows_per_strip)
+    entries.append((279, off_code, n_strips, b"".join(struct.pack(off_t, c) for c in counts)))
+    short(284, 1)
+    short(339, fmt)
+    if geo:
+        for tag in GEO_TAGS:
+            if tag in geo:
+                typ, cnt, payload = geo[tag]
+                entries.append((tag, typ, cnt, payload))
+    if nodata is not None:
+        txt = (repr(float(nodata)) if float(nodata) != int(nodata) else str(int(nodata))).encode() + b"\0"
+        entries.append((TAG_GDAL_NODATA, 2, len(txt), txt))
+    entries.sort(key=lambda e: e[0])
+
+    ifd_off = data_end + (data_end & 1)
+    entry_sz = 20 if big else 12
+    ifd_len = (8 if big else 2) + entry_sz * len(entries) + osz
+    extra_off = ifd_off + ifd_len
+    extra = b""
+    ifd = struct.pack("<Q" if big else "<H", len(entries))
+    for tag, typ, cnt, payload in entries:
+        if len(payload) <= osz:
+            field = payload + b"\0" * (osz - len(payload))
+        else:
+            if (extra_off + len(extra)) & 1:
+                extra += b"\0"
+            field = struct.pack(off_t, extra_off + len(extra))
+            extra += payload
+        ifd += struct.pack("<HH", tag, typ) + struct.pack("<Q" if big else "<I", cnt) + field
+    ifd += struct.pack(off_t, 0)
+
+    with open(path, "wb") as f:
+        if big:
+            f.write(b"II" + struct.pack("<HHHQ", 43, 8, 0, ifd_off))
+        else:
+            f.write(b"II" + struct.pack("<HI", 42, ifd_off))
+        f.write(a.tobytes() if a.nbytes < (1 << 28) else memoryview(a).cast("B"))
+        if data_end & 1:
+            f.write(b"\0")
+        f.write(ifd)
+        f.write(extra)
+
+
+def read(path: str):
+    """Reads band 1 of a little-endian, uncompressed, stripped TIFF / BigTIFF.  Returns (array, geo) where geo maps the
+    GeoTIFF tag numbers present to (type, count, payload bytes)."""
+    with open(path, "rb") as f:
+        buf = f.read()
+    if buf[:2] != b"II":
+        raise ValueError("only little-endian TIFF is supported")
+    magic = struct.unpack_from("<H", buf, 2)[0]
+    if magic == 42:
+        big, ifd_off = False, struct.unpack_from("<I", buf, 4)[0]
+    elif magic == 43:
+        big, ifd_off = True, struct.unpack_from("<Q", buf, 8)[0]
+    else:
+        raise ValueError("not a TIFF file")
+    osz = 8 if big else 4
+    n = struct.unpack_from("<Q" if big else "<H", buf, ifd_off)[0]
+    pos = ifd_off + (8 if big else 2)
+    tags = {}
+    for _ in range(n):
+        tag, typ = struct.unpack_from("<HH", buf, pos)
+        cnt = struct.unpack_from("<Q" if big else "<I", buf, pos + 4)[0]
+        fpos = pos + (12 if big else 8)
+        size = _TYPE_SIZE[typ] * cnt
+        if size > osz:
+            fpos = struct.unpack_from("<Q" if big else "<I", buf, fpos)[0]
+        tags[tag] = (typ, cnt, bytes(buf[fpos:fpos + size]))
+        pos += 20 if big else 12
+
+    def ints(tag, default=None):
+        if tag not in tags:
+            return default
+        typ, cnt, payload = tags[tag]
+        code = {1: "B", 3: "H", 4: "I", 16: "Q"}[typ]
+        return list(struct.unpack("<" + code * cnt, payload))
+
+    w, h = ints(256)[0], ints(257)[0]
+    if ints(259, [1])[0] != 1:
+        raise ValueError("compressed TIFFs are not supported yet (SURVEY.md section 8f)")
+    if 322 in tags:
+        raise ValueError("tiled TIFFs are not supported yet")
+    spp = ints(277, [1])[0]
+    if spp != 1 and ints(284, [1])[0] != 2:
+        raise ValueError("only band-sequential or single-band rasters are supported")
+    bits, fmt = ints(258)[0], ints(339, [1])[0]
+    dtype = {v: k for k, v in _SAMPLE.items()}[(fmt, bits)]
+    rps = ints(278, [h])[0]
+    offs, cnts = ints(273), ints(279)
+    out = np.empty((h, w), dtype)
+    flat = out.reshape(-1).view(np.uint8)
+    row_bytes = w * dtype.itemsize
+    strips_per_band = -(-h // rps)
+    for s in range(strips_per_band):
+        r0 = s * rps
+        nb = min(rps, h - r0) * row_bytes
+        flat[r0 * row_bytes:r0 * row_bytes + nb] = np.frombuffer(buf, np.uint8, nb, offs[s])
+    geo = {t: tags[t] for t in GEO_TAGS + (TAG_GDAL_NODATA,) if t in tags}
+    return out, geo

@@ -1,0 +1,148 @@
+"""Parity of the CUDA generators (through the C ABI) with the torch-CPU oracle on identical weights / inputs / eps.
+Tolerances (BASELINE.json north_star): fp32 mode <= 1e-4, bf16 tensor-core mode <= 1e-2, max abs error on the
+normalised output (outputs are O(1))."""
+import numpy as np
+import pytest
+
+from moonsuperresolution_b200 import weights as W
+from oracle import generator as OG
+
+pytestmark = pytest.mark.gpu
+
+TOL_FP32 = 1e-4
+TOL_BF16 = 1e-2
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+    assert torch.cuda.is_available()
+    return torch
+
+
+@pytest.fixture(scope="module")
+def msr(torch):
+    import moonsuperresolution_b200 as m
+    return m
+
+
+def bf16_round(a, torch):
+    return torch.from_numpy(a).to(torch.bfloat16).to(torch.float32).numpy()
+
+
+@pytest.mark.parametrize("n,r,cin,cout", [(1, 8, 64, 128), (2, 16, 128, 256), (3, 4, 128, 128), (1, 32, 256, 384),
+                                           (5, 2, 64, 128), (1, 128, 64, 128), (2, 1, 128, 256)])
+def test_conv3x3_tensor_core_operator(torch, n, r, cin, cout):
+    """tcgen05 implicit GEMM vs torch fp32 convolution on bf16-rounded operands."""
+    from moonsuperresolution_b200 import _lib
+    rng = np.random.default_rng(n * 1000 + r)
+    x = bf16_round(rng.standard_normal((n, r, r, cin)).astype(np.float32), torch)
+    w = bf16_round((rng.standard_normal((3, 3, cin, cout)) / np.sqrt(9 * cin)).astype(np.float32), torch)
+    b = rng.standard_normal(cout).astype(np.float32)
+    want = OG.conv2d_same(torch.from_numpy(x).permute(0, 3, 1, 2), w, b).permute(0, 2, 3, 1).numpy()
+    d_x = torch.from_numpy(x).cuda().to(torch.bfloat16).contiguous()
+    wt = np.ascontiguousarray(w.reshape(9 * cin, cout).T)                     # [cout][9*cin], k = tap*cin + ci
+    d_w = torch.from_numpy(wt).cuda().to(torch.bfloat16).contiguous()
+    d_b = torch.from_numpy(b).cuda()
+    d_y = torch.zeros((n, r, r, cout), dtype=torch.float32, device="cuda")
+    _lib.check(_lib.lib().msr_op_conv3x3_bf16(d_x.data_ptr(), d_w.data_ptr(), d_b.data_ptr(), d_y.data_ptr(), n, r, cin,
+                                              cout, _lib.stream_ptr()), "msr_op_conv3x3_bf16")
+    torch.cuda.synchronize()
+    got = d_y.cpu().numpy()
+    assert np.abs(got - want).max() < 2e-3, np.abs(got - want).max()
+
+
+@pytest.mark.parametrize("n,r,cin,cout", [(2, 8, 5, 7), (1, 16, 64, 33), (3, 4, 128, 128)])
+def test_conv3x3_fp32_operator(torch, n, r, cin, cout):
+    from moonsuperresolution_b200 import _lib
+    rng = np.random.default_rng(7)
+    x = rng.standard_normal((n, r, r, cin)).astype(np.float32)
+    w = (rng.standard_normal((3, 3, cin, cout)) / np.sqrt(9 * cin)).astype(np.float32)
+    b = rng.standard_normal(cout).astype(np.float32)
+    want = OG.conv2d_same(torch.from_numpy(x).permute(0, 3, 1, 2), w, b).permute(0, 2, 3, 1).numpy()
+    d_x, d_w, d_b = (torch.from_numpy(a).cuda() for a in (x, w, b))
+    d_y = torch.zeros((n, r, r, cout), dtype=torch.float32, device="cuda")
+    _lib.check(_lib.lib().msr_op_conv3x3_f32(d_x.data_ptr(), d_w.data_ptr(), d_b.data_ptr(), d_y.data_ptr(), n, r, cin,
+                                             cout, _lib.stream_ptr()), "msr_op_conv3x3_f32")
+    torch.cuda.synchronize()
+    assert np.abs(d_y.cpu().numpy() - want).max() < 1e-5
+
+
+def inputs(i, b, seed=0):
+    rng = np.random.default_rng(seed)
+    x = rng.uniform(-0.5, 0.5, (b, i, i, 2)).astype(np.float32)
+    x[-1] = 0.0                                    # a zero padding slot takes part in the batch statistics (:468-474)
+    eps = rng.standard_normal((b, 256)).astype(np.float32)
+    return x, eps
+
+
+@pytest.mark.parametrize("arch,i,b", [("cnn", 64, 3), ("spade", 64, 2), ("spade", 128, 2)])
+def test_spade_generator_fp32_mode(msr, arch, i, b):
+    w = W.random_init(arch, i, seed=11, perturb_affine=True)
+    x, eps = inputs(i, b)
+    want, want_latent = OG.gaugan_call(x, w, eps, arch, return_latent=True)
+    cls = msr.GauGAN if arch == "spade" else msr.CNNSpade
+    model = cls(i, b, precision="fp32", weights=w)
+    got = model(x, training=False, eps=eps)
+    assert got.shape == want.shape == (b, i, i, 1)
+    lat = model.read_activation("latent").reshape(b, 256)
+    assert np.abs(lat - want_latent).max() < 1e-4 * max(1.0, np.abs(want_latent).max())
+    err = np.abs(got - want).max()
+    assert err <= TOL_FP32 * max(1.0, np.abs(want).max()), err
+
+
+@pytest.mark.parametrize("arch,i,b", [("cnn", 64, 3), ("spade", 128, 2), ("cnn", 256, 1)])
+def test_spade_generator_bf16_tensor_core_mode(msr, arch, i, b):
+    w = W.random_init(arch, i, seed=12, perturb_affine=True)
+    x, eps = inputs(i, b, seed=1)
+    want = OG.gaugan_call(x, w, eps, arch)
+    cls = msr.GauGAN if arch == "spade" else msr.CNNSpade
+    model = cls(i, b, precision="bf16", weights=w)
+    got = model(x, training=False, eps=eps)
+    err = np.abs(got - want).max()
+    assert err <= TOL_BF16 * max(1.0, np.abs(want).max()), err
+
+
+def test_groups_have_independent_batch_statistics(msr, torch):
+    """Two batches pushed through one forward call (max_groups = 2) equal two separate calls."""
+    i, b = 64, 2
+    w = W.random_init("cnn", i, seed=3)
+    x, _ = inputs(i, 2 * b, seed=2)
+    one = msr.CNNSpade(i, b, precision="fp32", weights=w)
+    two = msr.CNNSpade(i, b, precision="fp32", weights=w, max_groups=2)
+    sep = np.concatenate([one(x[:b]), one(x[b:])])
+    src = torch.from_numpy(x).cuda()
+    out = torch.empty((2 * b, i, i), dtype=torch.float32, device="cuda")
+    two.forward_device(src, out, None, 2)
+    np.testing.assert_allclose(out.cpu().numpy()[..., None], sep, atol=1e-6)
+
+
+def test_pix2pix_generator(msr):
+    w = W.random_init("pix2pix", 256, seed=4, perturb_affine=True)
+    x, _ = inputs(256, 2, seed=3)
+    want = OG.pix2pix_call(x, w)
+    got = msr.Pix2Pix(batch_size=2, weights=w)(x, training=False)
+    assert np.abs(got - want).max() <= TOL_FP32
+
+
+def test_engine_with_device_model_matches_oracle_pipeline(msr):
+    """Full path with the CUDA generator plugged in vs the oracle pipeline with the oracle generator."""
+    from oracle import tiling as OT
+    i, s, b, t = 64, 32, 4, 128
+    rng = np.random.default_rng(0)
+    h, w_ = 150, 170
+    dem = np.cumsum(np.cumsum(rng.standard_normal((h, w_)), 0), 1).astype(np.float32)
+    img = rng.uniform(1, 255, (h, w_)).astype(np.float32)
+    dem[60:63, 80:90] = -32768.0
+    weights = W.random_init("cnn", i, seed=1, perturb_affine=True)
+    cfg = msr.DSRConfig(image_size=i, stride=s, batch_size=b, tile_size=t)
+    ref = OT.process_map(dem, img, i, s, b, t, cfg.no_value, OG.OracleModel("cnn", weights))
+    scale = float(dem[dem > -32768].max() - dem[dem > -32768].min())
+    for precision, tol in (("fp32", TOL_FP32), ("bf16", TOL_BF16)):
+        eng = msr.DEMSuperResolution(cfg, model=msr.CNNSpade(i, b, precision=precision, weights=weights, max_groups=3))
+        mean, std, good = eng.run(dem, img)
+        np.testing.assert_array_equal(good, ref[2])
+        g = good.astype(bool)
+        assert np.abs(mean[g] - ref[0][g]).max() / scale <= 4 * tol
+        assert np.abs(std[g] - ref[1][g]).max() / scale <= 4 * tol
+        assert (mean[~g] == cfg.no_value).all()

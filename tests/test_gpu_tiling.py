@@ -1,0 +1,180 @@
+"""Parity of the tiling / blending kernels (through the C ABI and the reference-shaped engine) with the CPU oracle and
+the golden fixtures produced by the reference's own class.  Bar: bit-exact."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import golden_inputs
+import toy_models
+from oracle import tiling as OT
+
+pytestmark = pytest.mark.gpu
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+    assert torch.cuda.is_available()
+    return torch
+
+
+@pytest.fixture(scope="module")
+def msr(torch):
+    import moonsuperresolution_b200 as m
+    from moonsuperresolution_b200 import _lib
+    m._lib = _lib
+    return m
+
+
+def engine_for(msr, case, model, **kw):
+    cfg = msr.DSRConfig(image_size=case["I"], stride=case["S"], batch_size=case["B"], tile_size=case["T"],
+                        no_value=case["NV"])
+    return msr.DEMSuperResolution(cfg, model=model, **kw)
+
+
+@pytest.mark.parametrize("name", ["wobble_200x260", "wobble_I48_S16"])
+def test_pad_validity_normalize_bit_exact(msr, torch, name):
+    case = golden_inputs.CASES[name]
+    dem, img = golden_inputs.make_rasters(case)
+    geo = OT.Geometry(case["H"], case["W"], case["I"], case["S"], case["T"])
+    eng = engine_for(msr, case, toy_models.identity)
+    eng.setRasters(dem, img)
+    eng.padInputs()
+    dem_c, img_c = OT.pad_inputs(dem, img, geo, case["NV"])
+    # the engine keeps only the canvas rows its tiles read (all of them end at last tile row + T + 2 off)
+    ch = eng.dem_padded.shape[0]
+    assert ch == min(geo.canvas_h, OT.tile_list(geo)[-1][1] + case["T"] + 2 * geo.off)
+    np.testing.assert_array_equal(eng.dem_padded.cpu().numpy(), dem_c[:ch])
+    np.testing.assert_array_equal(eng.img_padded.cpu().numpy(), img_c[:ch])
+    # summed-area table of the invalid mask
+    inv = ((img_c[:ch] <= case["NV"]) | (dem_c[:ch] <= case["NV"])).astype(np.int64)
+    sat = np.zeros((ch + 1, geo.canvas_w + 1), np.int64)
+    sat[1:, 1:] = inv.cumsum(0).cumsum(1)
+    np.testing.assert_array_equal(eng._sat.cpu().numpy().astype(np.int64), sat)
+    # validity + normalisation of every patch of every tile
+    i = case["I"]
+    for (px, py) in OT.tile_list(geo):
+        tp = eng._tile_plan[(px, py)]
+        want = [(x, y) for (x, y) in OT.patch_origins(geo, px, py) if OT.patch_is_valid(dem_c, img_c, x, y, i, case["NV"])]
+        assert [tuple(r) for r in tp["xy"]] == want
+    px, py = OT.tile_list(geo)[0]
+    tp = eng._tile_plan[(px, py)]
+    n = min(7, tp["n_valid"])
+    assert n > 0
+    xy = np.full((n + 1, 2), -1, np.int32)
+    xy[:n] = tp["xy"][:n]
+    d_xy = torch.from_numpy(xy).cuda()
+    out = torch.empty((n + 1, i, i, 2), dtype=torch.float32, device="cuda")
+    mm = torch.empty((n + 1, 4), dtype=torch.float32, device="cuda")
+    part = torch.empty(((n + 1) * 128,), dtype=torch.float32, device="cuda")
+    eng._gather(d_xy, n + 1, out, mm, part)
+    out, mm = out.cpu().numpy(), mm.cpu().numpy()
+    for k in range(n):
+        x, y = xy[k]
+        want, (lo, hi) = OT.normalize_patch(img_c[y:y + i, x:x + i], dem_c[y:y + i, x:x + i])
+        np.testing.assert_array_equal(out[k], want)
+        assert mm[k, 2] == lo and mm[k, 3] == hi
+    assert (out[n] == 0).all()                      # padding slot: all-zero input (process_full_tiles.py:472)
+    # reference-shaped per-patch helpers
+    x, y = (int(v) for v in xy[0])
+    valid, ip, dp = eng.getPatch(x, y)
+    assert valid and np.array_equal(dp, dem_c[y:y + i, x:x + i])
+    norm, lohi = eng.normalize(ip, dp)
+    want, wl = OT.normalize_patch(ip, dp)
+    np.testing.assert_array_equal(norm, want)
+    assert tuple(lohi) == tuple(wl)
+
+
+@pytest.mark.parametrize("name", list(golden_inputs.CASES))
+def test_engine_bit_exact_vs_reference_golden(msr, golden, name):
+    """Whole path with the toy plug-in models: pad -> validity -> gather/normalise -> model -> blend -> assemble must
+    reproduce the rasters the reference's own DEMSuperResolution produced (tests/golden/make_golden.py)."""
+    case = golden_inputs.CASES[name]
+    dem, img = golden_inputs.make_rasters(case)
+    eng = engine_for(msr, case, getattr(toy_models, case["model"]))
+    mean, std, good = eng.run(dem, img)
+    assert mean.shape == (case["H"], case["W"])
+    assert int(good.sum()) == int(golden[f"{name}/good_count"])
+    assert sha(good) == str(golden[f"{name}/sha_good"])
+    if case.get("store_full"):
+        np.testing.assert_array_equal(mean, golden[f"{name}/mean"])
+        np.testing.assert_array_equal(std, golden[f"{name}/std"])
+    assert sha(mean) == str(golden[f"{name}/sha_mean"])
+    assert sha(std) == str(golden[f"{name}/sha_std"])
+
+
+def test_rebuild_tile_api_matches_oracle(msr):
+    """rebuildTile(generated_dems, generated_minmax) with arbitrary keys / order and mixed float32 / float64
+    predictions (the scan form of msr_blend_tile)."""
+    case = dict(H=300, W=300, I=32, S=8, B=4, T=128, NV=-32768.0)
+    eng = engine_for(msr, case, toy_models.identity)
+    geo = OT.Geometry(300, 300, 32, 8, 128)
+    rng = np.random.default_rng(5)
+    keys = [(int(x) * 8, int(y) * 8) for x, y in rng.integers(0, 19, (40, 2))]
+    keys = list(dict.fromkeys(keys))
+    gen, mm = {}, {}
+    for n, k in enumerate(keys):
+        a = rng.uniform(0, 1, (32, 32))
+        gen[k] = a if n % 3 == 0 else a.astype(np.float32)
+        lo = np.float32(rng.uniform(-50, 50))
+        mm[k] = (lo, np.float32(lo + rng.uniform(1, 30)))
+    mean, std, good = eng.rebuildTile(gen, mm)
+    with np.errstate(all="ignore"):
+        wm, ws, wg = OT.rebuild_tile(gen, mm, geo, case["NV"])
+    np.testing.assert_array_equal(good, wg)
+    np.testing.assert_array_equal(mean, wm)
+    np.testing.assert_array_equal(std, ws)
+    # empty input: nothing reconstructed
+    mean, std, good = eng.rebuildTile({}, {})
+    assert (good == 0).all() and (mean == case["NV"]).all() and (std == case["NV"]).all()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_band_sharding_is_bit_identical(msr, world):
+    """Mode A of SURVEY.md 8e: ranks own bands of tile rows and hold only their canvas rows; stitched bands equal the
+    single-process result bit for bit (ranks emulated one after the other on one GPU)."""
+    case = golden_inputs.CASES["wobble_1100x1300"]
+    dem, img = golden_inputs.make_rasters(case)
+    model = getattr(toy_models, case["model"])
+    full = engine_for(msr, case, model).run(dem, img)
+    from moonsuperresolution_b200.distributed import assemble_bands
+    parts = []
+    for r in range(world):
+        eng = engine_for(msr, case, model, rank=r, world_size=world)
+        eng.setRasters(dem, img)
+        eng.padInputs()
+        assert eng.dem_padded.shape[0] < eng.plan.canvas_h
+        eng.processTiles()
+        parts.append(eng.results())
+    for k in range(3):
+        got = assemble_bands([(p[3], p[k]) for p in parts], case["H"], case["W"], full[k].dtype)
+        np.testing.assert_array_equal(got, full[k])
+
+
+def test_save_tiles_and_geotiff_layout(msr, tmp_path):
+    """Output layout of saveTile / saveGTiff (process_full_tiles.py:416-429, 481-531): names, dtypes, NoData."""
+    from moonsuperresolution_b200 import geotiff
+    case = golden_inputs.CASES["wobble_200x260"]
+    dem, img = golden_inputs.make_rasters(case)
+    geotiff.write(str(tmp_path / "run-DEM.tif"), dem)
+    geotiff.write(str(tmp_path / "run-DRG.tif"), img)
+    cfg = msr.DSRConfig(image_size=case["I"], stride=case["S"], batch_size=case["B"], tile_size=case["T"],
+                        no_value=case["NV"], map_name="m", save_path=str(tmp_path / "out"),
+                        source_folder_path=str(tmp_path), save_tiles=True)
+    (tmp_path / "out").mkdir()
+    eng = msr.DEMSuperResolution(cfg, model=toy_models.wobble)
+    eng.processMap()
+    mean, _ = geotiff.read(str(tmp_path / "out" / "m_mean.tiff"))
+    good, _ = geotiff.read(str(tmp_path / "out" / "m_good.tiff"))
+    assert mean.dtype == np.float32 and good.dtype == np.uint16 and mean.shape == dem.shape
+    ref = OT.process_map(dem, img, case["I"], case["S"], case["B"], case["T"], case["NV"], toy_models.wobble)
+    np.testing.assert_array_equal(mean, ref[0])
+    np.testing.assert_array_equal(good, ref[2].astype(np.uint16))
+    tile, _ = geotiff.read(str(tmp_path / "out" / "tile_128_0" / "tile_128_0_mean.tif"))
+    assert tile.shape == (case["T"], case["T"])
+    np.testing.assert_array_equal(tile[:, :case["W"] - 128], ref[0][:case["T"], 128:])
