@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""Benchmark of the tiled full-DEM super-resolution path (BASELINE.json: "SR megapixels/sec (SPADE-512, N=16 samples)").
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one process per GPU under torchrun)
+  python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle port of the reference graph, host cores
+
+A step = one pass of the whole path (pad -> validity -> gather/normalise -> GauGAN-512 generator -> blend -> assembled
+mean / std / good rasters) over the workload raster: configs[2] of BASELINE.json, SPADE-512 over 8192 x 8192 with
+stride 128 (nominal N = 16 generations per pixel), batch 16, tile 1024.  With N GPUs the raster is N bands of 8192 rows
+(8192*N x 8192), one band per rank (weak scaling; tiles are self-sufficient, no data-path collective).
+
+`value`  : megapixels of input raster per second, inputs already resident in HBM, timed with CUDA events, max over ranks.
+`e2e`    : same metric through DEMSuperResolution with HOST rasters: H2D of the inputs and D2H of the three output
+           rasters inside the timed region.
+`roofline`: tcgen05 convolution kernel (the dominant kernel): algorithmic conv FLOPs / its CUDA-event time, measured in
+           an extra instrumented step after the timed region, against MEASURED_PEAKS.json.
+`cpu_baseline`: the torch-CPU oracle port of the reference graph on a bounded sample, extrapolated by slot count.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "SR megapixels/sec (SPADE-512, N=16 samples)"
+UNIT = "MP/s"
+GF_PER_SLOT = {("spade", 512): 702.61, ("cnn", 512): 702.61, ("spade", 256): 175.65, ("cnn", 256): 175.65,
+               ("pix2pix", 256): 11.93}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--arch", default="spade", choices=["spade", "cnn", "pix2pix"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--image-size", type=int, default=512)
+    ap.add_argument("--stride", type=int, default=128)
+    ap.add_argument("--batch-size", type=int, default=16)
+    ap.add_argument("--tile-size", type=int, default=1024)
+    ap.add_argument("--rows-per-gpu", type=int, default=8192)
+    ap.add_argument("--cols", type=int, default=8192)
+    ap.add_argument("--groups", type=int, default=1, help="batches per generator call")
+    ap.add_argument("--e2e-steps", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=2, help="patches per CPU-baseline sample batch")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(tflops=float(d["bf16_tflops_sustained"]), tflops_burst=float(d["bf16_tflops"]),
+                    hbm=float(d["hbm_gbs"]), source="measured")
+    return dict(tflops=1400.0, tflops_burst=1590.0, hbm=6650.0, source="fallback")
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# synthetic rasters (analytic in global coordinates, so any rank can build any rows)
+# ------------------------------------------------------------------------------------------------------------------
+def synth_rows(torch, r0, r1, width, device):
+    y = torch.arange(r0, r1, device=device, dtype=torch.float32)[:, None]
+    x = torch.arange(0, width, device=device, dtype=torch.float32)[None, :]
+    dem = 1000.0 * (torch.sin(x / 97.3) * torch.cos(y / 131.7) + 0.5 * torch.sin((x + 2 * y) / 41.1)
+                    + 0.25 * torch.cos((3 * x - y) / 17.9))
+    yi = torch.arange(r0, r1, device=device, dtype=torch.int64)[:, None]
+    xi = torch.arange(0, width, device=device, dtype=torch.int64)[None, :]
+    hsh = ((xi * 73856093) ^ (yi * 19349663) ^ ((xi + yi) * 83492791)) & 0xFFFFFF
+    u = hsh.to(torch.float32) / float(1 << 24)
+    dem = dem + 3.0 * (u - 0.5)
+    hsh2 = ((xi * 2654435761) ^ (yi * 40503) ^ 0x9E3779B9) & 0xFFFFFF
+    img = 1.0 + 254.0 * (hsh2.to(torch.float32) / float(1 << 24)) * (0.6 + 0.4 * torch.sin(x / 53.0 + y / 71.0) ** 2)
+    img = img.clamp(1.0, 254.9)
+    return dem.contiguous(), img.contiguous()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        pw = [float(r[2]) for r in self.rows if len(r) >= 7 and r[2].replace(".", "").isdigit()]
+        reasons = []
+        for k, name in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
+            if any(len(r) >= 7 and r[3 + k].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
+
+
+def workload(args, n):
+    from moonsuperresolution_b200.planner import Plan
+    h, w = args.rows_per_gpu * n, args.cols
+    plan = Plan(h, w, args.image_size, args.stride, args.tile_size, args.batch_size)
+    return h, w, plan
+
+
+def slots_all_valid(plan):
+    """Slots executed on an all-valid raster (mirrors processTile's loop; border windows touch no_value)."""
+    i, s = plan.image_size, plan.stride
+    total = 0
+    for (px, py) in plan.tiles():
+        xy = plan.tile_patch_origins(px, py)
+        ok = ((xy[:, 0] >= plan.off) & (xy[:, 0] + i <= plan.off + plan.width) &
+              (xy[:, 1] >= plan.off) & (xy[:, 1] + i <= plan.off + plan.height))
+        total += plan.batch_slots(int(ok.sum()))
+    return total
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference graph on the host cores
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_sample_seconds_per_slot(args, weights, repeats=1):
+    """Times the torch-CPU oracle (restatement of spade/models/*.py) on one batch of `cpu_sample` patches plus the numpy
+    restatement of the host loop (normalise + blend) per patch.  Returns (seconds per slot, cores, description)."""
+    import torch
+    from oracle import generator as OG
+    from oracle import tiling as OT
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    i, cb = args.image_size, args.cpu_sample
+    rng = np.random.default_rng(0)
+    x = rng.uniform(-0.5, 0.5, (cb, i, i, 2)).astype(np.float32)
+    eps = rng.standard_normal((cb, 256)).astype(np.float32)
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        if args.arch == "pix2pix":
+            y = OG.pix2pix_call(x, weights)
+        else:
+            y = OG.gaugan_call(x, weights, eps, args.arch)
+        t_net = (time.perf_counter() - t0) / cb
+        best = t_net if best is None else min(best, t_net)
+    # host loop of the reference per patch: validity + normalise + weighted-Welford blend (incremental cost of a patch)
+    geo = OT.Geometry(i * 2, i * 2, i, args.stride, args.tile_size)
+    dem = np.cumsum(rng.standard_normal((i, i)), 0).astype(np.float32)
+    img = rng.uniform(1, 255, (i, i)).astype(np.float32)
+    t0 = time.perf_counter()
+    OT.patch_is_valid(dem, img, 0, 0, i, -32768.0)
+    xn, lohi = OT.normalize_patch(img, dem)
+    t_norm = time.perf_counter() - t0
+    pred = (y[0, :, :, -1] + 0.5).astype(np.float32)
+    keys = [(k * args.stride, 0) for k in range(8)]
+    t0 = time.perf_counter()
+    OT.rebuild_tile({}, {}, geo, -32768.0)
+    t_empty = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    OT.rebuild_tile({k: pred for k in keys}, {k: lohi for k in keys}, geo, -32768.0)
+    t_host = t_norm + max(time.perf_counter() - t0 - t_empty, 0.0) / len(keys)
+    desc = (f"oracle port (torch fp32 CPU restatement of the reference graph + numpy host loop): one batch of {cb} "
+            f"{args.arch}-{i} patches, {cores} threads, extrapolated by slot count")
+    return best + t_host, cores, desc
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's TensorFlow path cannot run (no TF, model.py does not parse); the CPU arm is the
+    oracle port, all host threads, each step a bounded sample of the same workload."""
+    if rank != 0:
+        return
+    from moonsuperresolution_b200 import weights as W
+    h, w, plan = workload(args, args.gpus)
+    slots = slots_all_valid(plan)
+    weights = W.random_init(args.arch, args.image_size, seed=0)
+    per_slot = []
+    cores, desc = 1, ""
+    for s in range(args.warmup + args.steps):
+        t, cores, desc = cpu_sample_seconds_per_slot(args, weights)
+        if s >= args.warmup:
+            per_slot.append(t)
+    sec_per_slot = float(np.mean(per_slot))
+    total_s = sec_per_slot * slots
+    value = (h * w / 1e6) / total_s
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_s * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(args, args.gpus, plan, slots),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc,
+                             "seconds_per_slot": sec_per_slot},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def config_dict(args, n, plan, slots):
+    return {"workload": f"{args.arch.upper()}-{args.image_size} tiled inference over {plan.height}x{plan.width} "
+                        f"(= {n} band(s) of {args.rows_per_gpu} rows, one per GPU), stride {args.stride} "
+                        f"(nominal N={(args.image_size // args.stride) ** 2} generations/pixel), batch "
+                        f"{args.batch_size}, tile {args.tile_size}; BASELINE.json configs[2]",
+            "raster": [plan.height, plan.width], "image_size": args.image_size, "stride": args.stride,
+            "batch_size": args.batch_size, "tile_size": args.tile_size, "tiles": len(plan.tiles()),
+            "slots_per_step": slots, "gflop_per_slot": GF_PER_SLOT.get((args.arch, args.image_size)),
+            "mode": "reference-faithful (halo patches recomputed per tile)", "precision": args.precision,
+            "parallelism": f"tile-row bands x{n}", "groups_per_call": args.groups,
+            "l2": "inputs larger than L2 (raster 2 x %.0f MB per band; activations >> 126 MB)" %
+                  (args.rows_per_gpu * plan.width * 4 / 1e6)}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n = world
+    from moonsuperresolution_b200 import DEMSuperResolution, DSRConfig, _lib
+    from moonsuperresolution_b200 import models as M
+    from moonsuperresolution_b200 import weights as W
+
+    h, w, plan = workload(args, n)
+    slots_total = slots_all_valid(plan)
+    weights = W.random_init(args.arch, args.image_size, seed=0)
+    cls = {"spade": M.GauGAN, "cnn": M.CNNSpade}.get(args.arch)
+    if args.arch == "pix2pix":
+        model = M.Pix2Pix(batch_size=args.batch_size, weights=weights, max_groups=args.groups)
+    else:
+        model = cls(args.image_size, args.batch_size, precision=args.precision, weights=weights, max_groups=args.groups)
+    cfg = DSRConfig(image_size=args.image_size, stride=args.stride, batch_size=args.batch_size,
+                    tile_size=args.tile_size, groups_per_call=args.groups)
+    eng = DEMSuperResolution(cfg, model=model, rank=rank, world_size=world, device=dev)
+    r0, r1 = eng.rowsNeeded(h, w)
+    d_dem, d_img = synth_rows(torch, r0, r1, w, dev)
+
+    def step_resident():
+        eng.setRasters(d_dem, d_img, row_offset=r0, full_height=h)
+        eng.padInputs()
+        eng.processTiles()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_resident()
+    sync_all()
+    clocks = ClockSampler(local)
+    clocks.start()
+    l0, m0, s0 = eng.launches, eng.model_launches, eng.slots_executed
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_resident()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    clock_info = clocks.stop()
+    sync_all()
+    launches = torch.tensor([eng.launches - l0 + eng.model_launches - m0, eng.slots_executed - s0], dtype=torch.int64,
+                            device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(launches, op=dist.ReduceOp.SUM)
+    ms_total = float(ms.item())
+    ms_per_step = ms_total / args.steps
+    mp = h * w / 1e6
+    value = mp / (ms_per_step / 1e3)
+
+    # ---- end to end through the public API with host rasters (H2D + D2H inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        h_dem = torch.empty(d_dem.shape, dtype=torch.float32, pin_memory=True).copy_(d_dem).numpy()
+        h_img = torch.empty(d_img.shape, dtype=torch.float32, pin_memory=True).copy_(d_img).numpy()
+        eng.run(h_dem, h_img, row_offset=r0, full_height=h)          # warm (pinned staging, allocator)
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            out = eng.run(h_dem, h_img, row_offset=r0, full_height=h)
+        torch.cuda.synchronize()
+        t = torch.tensor([(time.perf_counter() - t0) / args.e2e_steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        h2d = 2 * h_dem.nbytes
+        d2h = sum(o.nbytes for o in out)
+        bytes_t = torch.tensor([h2d, d2h], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(bytes_t, op=dist.ReduceOp.SUM)
+        e2e = {"value": mp / float(t.item()), "unit": UNIT, "h2d_bytes_per_step": int(bytes_t[0].item()),
+               "d2h_bytes_per_step": int(bytes_t[1].item()), "steps": args.e2e_steps,
+               "ms_per_step": float(t.item()) * 1e3}
+        del h_dem, h_img, out
+
+    # ---- instrumented step: per-kernel-family CUDA-event times (not part of `value`)
+    sync_all()
+    _lib.profile_enable(True)
+    step_resident()
+    prof = _lib.profile_read()
+    _lib.profile_enable(False)
+    pk = peaks()
+    tc = prof["conv_tc"]
+    roofline = None
+    if tc["launches"] > 0 and tc["ms"] > 0:
+        achieved = tc["work"] / (tc["ms"] * 1e-3) / 1e12
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "conv_tc_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        roofline = {"bound": "tensor", "kernel": "conv3x3_tc_kernel (tcgen05 implicit GEMM, all launches of one step)",
+                    "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
+                    "peak_source": f"MEASURED_PEAKS.json bf16 sustained ({pk['source']})", "traffic": traffic,
+                    "launches": tc["launches"], "avg_launch_ms": tc["ms"] / tc["launches"],
+                    "flops_per_launch_avg": tc["work"] / tc["launches"]}
+    total_prof_ms = sum(v["ms"] for v in prof.values())
+    breakdown = {k: {"ms": round(v["ms"], 3), "launches": v["launches"],
+                     "share": round(v["ms"] / total_prof_ms, 4) if total_prof_ms else None,
+                     "rate": (v["work"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 else None}
+                 for k, v in prof.items() if v["launches"]}
+    hbm_kernels = {}
+    for fam in ("blend", "gather", "stats", "mask_conv", "final_conv"):
+        v = prof[fam]
+        if v["launches"] and v["ms"] > 0:
+            gbs = v["work"] / (v["ms"] * 1e-3) / 1e9
+            hbm_kernels[fam] = {"achieved_gbs": gbs, "frac_of_measured_hbm": gbs / pk["hbm"]}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sec, cores, desc = cpu_sample_seconds_per_slot(args, weights)
+        cpu_baseline = {"value": mp / (sec * slots_total), "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": desc, "seconds_per_slot": sec}
+
+    if rank == 0:
+        gf = GF_PER_SLOT.get((args.arch, args.image_size))
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+                "config": config_dict(args, n, plan, slots_total), "clocks": clock_info, "e2e": e2e,
+                "gpu_launches": int(launches[0].item()), "slots_executed": int(launches[1].item()),
+                "model_tflops": (int(launches[1].item()) * gf / 1e3) / (ms_total / 1e3) if gf else None,
+                "roofline": roofline, "hbm_kernels": hbm_kernels, "cpu_baseline": cpu_baseline,
+                "breakdown_instrumented_step": breakdown}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -92,6 +92,7 @@ class DEMSuperResolution:
         torch = _torch()
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.dem = self.img = None
+        self._row_offset = 0
         self.geo_transform = self.geo_projection = None
         self.plan: Optional[Plan] = None
         self.launches = 0              # kernel launches issued through the C ABI by this engine (excluding the model)
@@ -102,9 +103,12 @@ class DEMSuperResolution:
     # ---------------------------------------------------------------------------------------------------------------
     # inputs
     # ---------------------------------------------------------------------------------------------------------------
-    def setRasters(self, dem: np.ndarray, img: np.ndarray, geo_transform=None, geo_projection=None) -> None:
+    def setRasters(self, dem, img, geo_transform=None, geo_projection=None, row_offset: int = 0,
+                   full_height: Optional[int] = None) -> None:
         """In-memory equivalent of loadImages (process_full_tiles.py:158-182).  Accepts host numpy arrays (uploaded by
-        padInputs) or float32 CUDA tensors that are already resident on this engine's device."""
+        padInputs) or float32 CUDA tensors already resident on this engine's device.  A rank may hold only the rows
+        [row_offset, row_offset + rows) of a raster that is ``full_height`` rows tall (inputs loaded sharded); they
+        must cover the rows its band of tiles reads."""
         if hasattr(dem, "is_cuda"):
             if not (dem.is_cuda and img.is_cuda and str(dem.dtype) == "torch.float32" and str(img.dtype) == "torch.float32"):
                 raise ValueError("tensor rasters must be float32 CUDA tensors")
@@ -115,7 +119,11 @@ class DEMSuperResolution:
             raise ValueError("dem and ortho-image must be 2-D arrays of the same shape")
         self.dem, self.img = dem, img
         self.geo_transform, self.geo_projection = geo_transform, geo_projection
-        self.dem_shape, self.img_shape = tuple(dem.shape), tuple(img.shape)
+        self._row_offset = int(row_offset)
+        h = int(full_height) if full_height is not None else int(dem.shape[0]) + self._row_offset
+        if self._row_offset < 0 or self._row_offset + dem.shape[0] > h:
+            raise ValueError("row_offset / full_height do not contain the given rows")
+        self.dem_shape = self.img_shape = (h, int(dem.shape[1]))
 
     def loadImages(self) -> None:
         """process_full_tiles.py:158-182 -- band 1 of both GeoTIFFs as float32 plus the DEM's geo-referencing."""
@@ -165,11 +173,15 @@ class DEMSuperResolution:
             # raster rows that fall inside canvas rows [c0, c1): canvas row = raster row + off
             r0, r1 = max(0, c0 - plan.off), min(h, c1 - plan.off)
             self._r0 = r0
+            ro = self._row_offset
+            if r1 > r0 and (r0 < ro or r1 > ro + self.dem.shape[0]):
+                raise ValueError(f"rank {self.rank} needs raster rows [{r0}, {r1}) but holds "
+                                 f"[{ro}, {ro + self.dem.shape[0]})")
             if torch.is_tensor(self.dem):
-                d_dem, d_img = self.dem[r0:r1].contiguous(), self.img[r0:r1].contiguous()
+                d_dem, d_img = self.dem[r0 - ro:r1 - ro].contiguous(), self.img[r0 - ro:r1 - ro].contiguous()
             else:
-                d_dem = torch.from_numpy(self.dem[r0:r1]).to(self.device, non_blocking=True)
-                d_img = torch.from_numpy(self.img[r0:r1]).to(self.device, non_blocking=True)
+                d_dem = torch.from_numpy(self.dem[r0 - ro:r1 - ro]).to(self.device, non_blocking=True)
+                d_img = torch.from_numpy(self.img[r0 - ro:r1 - ro]).to(self.device, non_blocking=True)
             self.dem_padded = torch.empty((self._ch, plan.canvas_w), dtype=torch.float32, device=self.device)
             self.img_padded = torch.empty_like(self.dem_padded)
             if r1 > r0:
@@ -540,9 +552,19 @@ class DEMSuperResolution:
         self.rebuildMap()
         return
 
-    def run(self, dem: np.ndarray, img: np.ndarray):
+    def rowsNeeded(self, height: int, width: int) -> Tuple[int, int]:
+        """Raster rows [r0, r1) this rank's band reads (its tiles plus the I - S halo), before any data is loaded."""
+        plan = Plan(height, width, self.image_size, self.stride, self.tile_size, self.batch_size)
+        tiles, _, _ = band_of_rank(plan, self.world_size, self.rank)
+        if not tiles:
+            return 0, 0
+        c0 = min(yy for _, yy in tiles)
+        c1 = min(plan.canvas_h, max(yy for _, yy in tiles) + plan.tile_size + 2 * plan.off)
+        return max(0, c0 - plan.off), min(height, c1 - plan.off)
+
+    def run(self, dem, img, row_offset: int = 0, full_height: Optional[int] = None):
         """In-memory processMap: rasters in, (mean, std, good) of this rank's band out (numpy)."""
-        self.setRasters(dem, img)
+        self.setRasters(dem, img, row_offset=row_offset, full_height=full_height)
         self.padInputs()
         self.processTiles()
         return self.results()[:3]
