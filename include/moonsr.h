@@ -155,6 +155,16 @@ int msr_generator_destroy(msr_generator* g);
 int msr_op_conv3x3_bf16(const uint16_t* d_x, const uint16_t* d_w, const float* d_bias, float* d_y, int n, int r,
                         int cin, int cout, void* stream);
 
+/* General form of the tensor-core convolution (taps = 9: 3x3, taps = 1: 1x1; stride 1 or 2; input coordinate of tap
+ * (ky, kx) for output (h, w) = (h*stride + ky - pad, w*stride + kx - pad), zero outside).  d_x (n, r_out*stride,
+ * r_out*stride, cin) bf16, d_w (cout, taps*cin) bf16.  Exactly one of d_y_f32 (n, r_out, r_out, cout; acc + bias) and
+ * d_y_bf16 (act(acc + bias), act: 0 none, 1 relu, 2 leaky-relu(slope)) is non-NULL.  d_stat_pairs (optional, with
+ * d_y_f32, needs r_out^2 >= 128): (n*r_out^2/128*4, cout, 2) float32 per-(128-pixel tile, warp) column sums and sums of
+ * squares, the fused form of SPADE's batch moments (spade.py:21). */
+int msr_op_conv_tc(const uint16_t* d_x, const uint16_t* d_w, const float* d_bias, float* d_y_f32, uint16_t* d_y_bf16,
+                   int n, int r_out, int cin, int cout, int taps, int stride, int pad, int act, float slope,
+                   float* d_stat_pairs, void* stream);
+
 /* Same operator on CUDA cores in float32 (the fp32-mode kernel); d_w (3, 3, cin, cout) Keras layout. */
 int msr_op_conv3x3_f32(const float* d_x, const float* d_w, const float* d_bias, float* d_y, int n, int r, int cin,
                        int cout, void* stream);

@@ -108,6 +108,28 @@ extern "C" int msr_op_conv3x3_bf16(const uint16_t* d_x, const uint16_t* d_w, con
   return rc;
 }
 
+extern "C" int msr_op_conv_tc(const uint16_t* d_x, const uint16_t* d_w, const float* d_bias, float* d_y_f32,
+                              uint16_t* d_y_bf16, int n, int r_out, int cin, int cout, int taps, int stride, int pad,
+                              int act, float slope, float* d_stat_pairs, void* stream) {
+  MSR_REQUIRE((d_y_f32 != nullptr) != (d_y_bf16 != nullptr), "msr_op_conv_tc: exactly one output must be given");
+  ConvTCArgs a;
+  a.x = reinterpret_cast<const __nv_bfloat16*>(d_x);
+  a.w = reinterpret_cast<const __nv_bfloat16*>(d_w);
+  a.n = n; a.r = r_out; a.cin = cin; a.ncols = cout; a.taps = taps; a.stride = stride; a.pad = pad;
+  a.bias = d_bias;
+  if (d_y_f32) {
+    a.epilogue = TC_EPI_BIAS_F32; a.y = d_y_f32; a.stat_pairs = reinterpret_cast<float2*>(d_stat_pairs);
+  } else {
+    a.epilogue = TC_EPI_ACT_BF16; a.out_bf16 = reinterpret_cast<__nv_bfloat16*>(d_y_bf16); a.act = act; a.slope = slope;
+  }
+  ConvTC* plan = nullptr;
+  int rc = conv_tc_plan_create(&plan, a);
+  if (rc) return rc;
+  rc = conv_tc_launch(plan, (cudaStream_t)stream);
+  conv_tc_plan_destroy(plan);
+  return rc;
+}
+
 extern "C" int msr_op_conv3x3_f32(const float* d_x, const float* d_w, const float* d_bias, float* d_y, int n, int r,
                                   int cin, int cout, void* stream) {
   ConvF32 c;

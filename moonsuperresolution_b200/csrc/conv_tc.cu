@@ -32,13 +32,15 @@ template <int BN>
 struct Cfg {
   static constexpr int kBBytes = BN * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
-  static constexpr int kTmemCols = 2 * BN;        // two accumulator buffers
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kTmemCols = 2 * BN;        // two accumulator buffers (power of two >= 32)
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 struct Geometry {
-  int n, r, cin, ncols;
+  int n, r, cin, ncols;      // r = OUTPUT side; the input side is r * stride
+  int taps;                  // 9 (3x3) or 1 (1x1)
+  int stride, pad;           // input coordinate of tap (ky, kx) for output (h, w): (h*stride + ky - pad, w*stride + kx - pad)
   int TW, TH, NB;            // tile = NB images x TH rows x TW cols (all powers of two, product 128)
   int tiles_w, tiles_h, tiles_b, n_tiles_m, n_tiles_n;
 };
@@ -49,14 +51,31 @@ struct EpiParams {
   float* y;
   const float* res;
   int res_shift;
+  float2* stat_pairs;        // TC_EPI_BIAS_F32: optional per-(M tile, warp) column (sum, sum of squares) partials
   const float* sx;
   int sx_shift;
   const float* mean;
   const float* rstd;
   int samples_per_group;
   float slope;
+  int act;
   __nv_bfloat16* out_bf16;
 };
+
+// Sum over the 32 lanes of t[j] for every j; afterwards lane l holds the total of element l in t[0].  31 shuffles.
+__device__ __forceinline__ float warp_transpose_reduce(float (&t)[32], int lane) {
+#pragma unroll
+  for (int step = 16, n = 32; step >= 1; step >>= 1, n >>= 1) {
+    const bool upper = (lane & step) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const float send = upper ? t[i] : t[i + n / 2];
+      const float keep = upper ? t[i + n / 2] : t[i];
+      t[i] = keep + __shfl_xor_sync(0xffffffffu, send, step);
+    }
+  }
+  return t[0];
+}
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -183,7 +202,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = g.n_tiles_m * g.n_tiles_n;
   const int k_chunks_per_tap = g.cin / kBlockK;
-  const int k_chunks = 9 * k_chunks_per_tap;
+  const int k_chunks = g.taps * k_chunks_per_tap;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::kStages; ++s) {
@@ -225,12 +244,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         decode_tile(tile, b0, h0, w0, n0);
         for (int kc = 0; kc < k_chunks; ++kc) {
           const int tap = kc / k_chunks_per_tap, cb = kc % k_chunks_per_tap;
-          const int ky = tap / 3, kx = tap % 3;
+          const int ky = tap / 3, kx = tap % 3;   // taps == 1: (0, 0)
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * C::kStageBytes;
           const uint32_t sb = sa + kABytes;
           mbar_expect_tx(full_bar(stage), C::kStageBytes);
-          tma_load_4d(sa, &map_a, full_bar(stage), cb * kBlockK, w0 + kx - 1, h0 + ky - 1, b0);
+          tma_load_4d(sa, &map_a, full_bar(stage), cb * kBlockK, w0 * g.stride + kx - g.pad, h0 * g.stride + ky - g.pad,
+                      b0);
           tma_load_2d(sb, &map_b, full_bar(stage), tap * g.cin + cb * kBlockK, n0);
           if (++stage == C::kStages) {
             stage = 0;
@@ -294,6 +314,55 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           const int rs = g.r >> ep.res_shift;
           res_row = ((int64_t)b * rs + (h >> ep.res_shift)) * rs + (w >> ep.res_shift);
         }
+        const int mt = tile / g.n_tiles_n;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(t_row + (uint32_t)c0, v);
+          tmem_ld_wait();
+          const int col = n0 + c0;
+          float o[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(v[j]);
+          if (ep.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(ep.bias + col + j));
+              o[j] += bb.x; o[j + 1] += bb.y; o[j + 2] += bb.z; o[j + 3] += bb.w;
+            }
+          }
+          if (row_ok) {
+            if (ep.res) {
+              const float* rs_ptr = ep.res + res_row * g.ncols + col;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 rr = __ldg(reinterpret_cast<const float4*>(rs_ptr + j));
+                o[j] += rr.x; o[j + 1] += rr.y; o[j + 2] += rr.z; o[j + 3] += rr.w;
+              }
+            }
+            float* dst = ep.y + m * g.ncols + col;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(dst + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+          }
+          if (ep.stat_pairs != nullptr) {   // per-channel batch statistics of the output (spade.py:21), fused
+            float t[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) t[j] = row_ok ? o[j] : 0.f;
+            const float sum = warp_transpose_reduce(t, lane);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) t[j] = row_ok ? o[j] * o[j] : 0.f;
+            const float sq = warp_transpose_reduce(t, lane);
+            ep.stat_pairs[((int64_t)mt * 4 + warp) * g.ncols + col + lane] = make_float2(sum, sq);
+          }
+        }
+      } else if (ep.mode == TC_EPI_ACT_BF16) {
+        // out_bf16 = act(acc + bias (+ residual)), NHWC bf16: the A operand of a following convolution
+        int64_t res_row = 0;
+        if (ep.res != nullptr) {
+          const int rs = g.r >> ep.res_shift;
+          res_row = ((int64_t)b * rs + (h >> ep.res_shift)) * rs + (w >> ep.res_shift);
+        }
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
           uint32_t v[32];
@@ -301,15 +370,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           tmem_ld_wait();
           if (row_ok) {
             const int col = n0 + c0;
-            float* dst = ep.y + m * g.ncols + col;
             const float* rs_ptr = ep.res ? ep.res + res_row * g.ncols + col : nullptr;
+            __align__(16) __nv_bfloat16 ob[32];
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              float4 o;
-              o.x = __uint_as_float(v[j + 0]);
-              o.y = __uint_as_float(v[j + 1]);
-              o.z = __uint_as_float(v[j + 2]);
-              o.w = __uint_as_float(v[j + 3]);
+              float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                     __uint_as_float(v[j + 3]));
               if (ep.bias) {
                 const float4 bb = __ldg(reinterpret_cast<const float4*>(ep.bias + col + j));
                 o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
@@ -318,12 +384,37 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 const float4 rr = __ldg(reinterpret_cast<const float4*>(rs_ptr + j));
                 o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
               }
-              *reinterpret_cast<float4*>(dst + j) = o;
+              if (ep.act == ACT_RELU) {
+                o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+              } else if (ep.act == ACT_LRELU) {
+                o.x = o.x > 0.f ? o.x : o.x * ep.slope; o.y = o.y > 0.f ? o.y : o.y * ep.slope;
+                o.z = o.z > 0.f ? o.z : o.z * ep.slope; o.w = o.w > 0.f ? o.w : o.w * ep.slope;
+              }
+              ob[j] = __float2bfloat16_rn(o.x); ob[j + 1] = __float2bfloat16_rn(o.y);
+              ob[j + 2] = __float2bfloat16_rn(o.z); ob[j + 3] = __float2bfloat16_rn(o.w);
             }
+            uint4* dst = reinterpret_cast<uint4*>(ep.out_bf16 + m * g.ncols + col);
+            const uint4* src = reinterpret_cast<const uint4*>(ob);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) dst[q] = src[q];
           }
+        }
+      } else if (ep.mode == TC_EPI_PHASE_F32) {
+        // final generator layer as a 3x3 convolution to 4 sub-pixel phases (columns 0..3 = (py, px)) + pixel shuffle:
+        // y[b][2h + py][2w + px] = acc[py*2 + px] + bias[0]
+        uint32_t v[32];
+        tmem_ld32(t_row, v);
+        tmem_ld_wait();
+        if (row_ok && n0 == 0) {
+          const float b0f = ep.bias ? __ldg(ep.bias) : 0.f;
+          const int R = 2 * g.r;
+          float* dst = ep.y + ((int64_t)b * R + 2 * h) * R + 2 * w;
+          *reinterpret_cast<float2*>(dst) = make_float2(__uint_as_float(v[0]) + b0f, __uint_as_float(v[1]) + b0f);
+          *reinterpret_cast<float2*>(dst + R) = make_float2(__uint_as_float(v[2]) + b0f, __uint_as_float(v[3]) + b0f);
         }
       } else {
         // fused SPADE: a 128-column group holds gamma (64) | beta (64) of channels ch0 .. ch0+63
+        if constexpr (BN >= 128) {
         const int Cc = g.ncols >> 1;
         const int rs = g.r >> ep.sx_shift;
         const int64_t x_row = ((int64_t)b * rs + (h >> ep.sx_shift)) * rs + (w >> ep.sx_shift);
@@ -371,6 +462,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             }
           }
         }
+        }  // BN >= 128
       }
       // release the accumulator buffer
       tc_fence_before();
@@ -417,17 +509,13 @@ struct ConvTC {
   int grid;
 };
 
-static int pow2_floor(int v) {
-  int p = 1;
-  while (p * 2 <= v) p *= 2;
-  return p;
-}
-
 int conv_tc_plan_create(ConvTC** out, const ConvTCArgs& a) {
   MSR_REQUIRE(out && a.x && a.w, "conv_tc: null operand");
   MSR_REQUIRE(a.n > 0 && a.r > 0 && (a.r & (a.r - 1)) == 0, "conv_tc: r must be a power of two");
   MSR_REQUIRE(a.cin % 64 == 0 && a.cin >= 64, "conv_tc: cin must be a multiple of 64");
-  MSR_REQUIRE(a.ncols % 128 == 0, "conv_tc: output columns must be a multiple of 128");
+  MSR_REQUIRE(a.ncols % 32 == 0 && a.ncols >= 32, "conv_tc: output columns must be a multiple of 32");
+  MSR_REQUIRE(a.taps == 9 || a.taps == 1, "conv_tc: taps must be 9 (3x3) or 1 (1x1)");
+  MSR_REQUIRE(a.stride == 1 || a.stride == 2, "conv_tc: stride must be 1 or 2");
   MSR_REQUIRE((reinterpret_cast<uintptr_t>(a.x) & 127) == 0 && (reinterpret_cast<uintptr_t>(a.w) & 127) == 0,
               "conv_tc: operands must be 128-byte aligned");
   EncodeTiledFn enc = get_encode_fn();
@@ -435,6 +523,7 @@ int conv_tc_plan_create(ConvTC** out, const ConvTCArgs& a) {
   ConvTC* p = new ConvTC();
   tc::Geometry& g = p->g;
   g.n = a.n; g.r = a.r; g.cin = a.cin; g.ncols = a.ncols;
+  g.taps = a.taps; g.stride = a.stride; g.pad = a.taps == 1 ? 0 : a.pad;
   g.TW = std::min(a.r, 128);
   g.TH = std::min(a.r, 128 / g.TW);
   g.NB = 128 / (g.TW * g.TH);
@@ -442,16 +531,18 @@ int conv_tc_plan_create(ConvTC** out, const ConvTCArgs& a) {
   g.tiles_h = a.r / g.TH;
   g.tiles_b = ceil_div(a.n, g.NB);
   g.n_tiles_m = g.tiles_w * g.tiles_h * g.tiles_b;
-  p->bn = (a.ncols % 256 == 0) ? 256 : 128;
+  p->bn = (a.ncols % 256 == 0) ? 256 : (a.ncols % 128 == 0) ? 128 : (a.ncols % 64 == 0) ? 64 : 32;
+  if (a.epilogue == TC_EPI_PHASE_F32) p->bn = 32;
   g.n_tiles_n = a.ncols / p->bn;
-  (void)pow2_floor;
+  const int rin = a.r * a.stride;
 
-  // A: 4-D NHWC tensor {C, W, H, N}
+  // A: 4-D NHWC tensor {C, W, H, N}; a stride-2 convolution walks W and H with element stride 2
   {
-    cuuint64_t dims[4] = {(cuuint64_t)a.cin, (cuuint64_t)a.r, (cuuint64_t)a.r, (cuuint64_t)a.n};
-    cuuint64_t strides[3] = {(cuuint64_t)a.cin * 2, (cuuint64_t)a.r * a.cin * 2, (cuuint64_t)a.r * a.r * a.cin * 2};
-    cuuint32_t box[4] = {(cuuint32_t)tc::kBlockK, (cuuint32_t)g.TW, (cuuint32_t)g.TH, (cuuint32_t)g.NB};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
+    cuuint64_t dims[4] = {(cuuint64_t)a.cin, (cuuint64_t)rin, (cuuint64_t)rin, (cuuint64_t)a.n};
+    cuuint64_t strides[3] = {(cuuint64_t)a.cin * 2, (cuuint64_t)rin * a.cin * 2, (cuuint64_t)rin * rin * a.cin * 2};
+    cuuint32_t box[4] = {(cuuint32_t)tc::kBlockK, (cuuint32_t)(g.TW * a.stride), (cuuint32_t)(g.TH * a.stride),
+                         (cuuint32_t)g.NB};
+    cuuint32_t estr[4] = {1, (cuuint32_t)a.stride, (cuuint32_t)a.stride, 1};
     CUresult r = enc(&p->map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(a.x), dims, strides, box,
                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -462,8 +553,8 @@ int conv_tc_plan_create(ConvTC** out, const ConvTCArgs& a) {
   }
   // B: 2-D weights {K, N}
   {
-    cuuint64_t dims[2] = {(cuuint64_t)9 * a.cin, (cuuint64_t)a.ncols};
-    cuuint64_t strides[1] = {(cuuint64_t)9 * a.cin * 2};
+    cuuint64_t dims[2] = {(cuuint64_t)a.taps * a.cin, (cuuint64_t)a.ncols};
+    cuuint64_t strides[1] = {(cuuint64_t)a.taps * a.cin * 2};
     cuuint32_t box[2] = {(cuuint32_t)tc::kBlockK, (cuuint32_t)p->bn};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(&p->map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(a.w), dims, strides, box,
@@ -476,17 +567,27 @@ int conv_tc_plan_create(ConvTC** out, const ConvTCArgs& a) {
   }
   tc::EpiParams& e = p->ep;
   e.mode = a.epilogue;
-  e.bias = a.bias; e.y = a.y; e.res = a.res; e.res_shift = a.res_shift;
+  e.bias = a.bias; e.y = a.y; e.res = a.res; e.res_shift = a.res_shift; e.stat_pairs = a.stat_pairs;
   e.sx = a.sx; e.sx_shift = a.sx_shift; e.mean = a.mean; e.rstd = a.rstd;
   e.samples_per_group = a.samples_per_group > 0 ? a.samples_per_group : 1;
-  e.slope = a.slope; e.out_bf16 = a.out_bf16;
+  e.slope = a.slope; e.act = a.act; e.out_bf16 = a.out_bf16;
+  const char* bad = nullptr;
   if (a.epilogue == TC_EPI_BIAS_F32) {
-    if (!a.y) { delete p; return fail(MSR_E_INVALID, "conv_tc: y is null"); }
+    if (!a.y) bad = "conv_tc: y is null";
+    if (a.stat_pairs && g.NB != 1) bad = "conv_tc: fused statistics need r*r >= 128";
+  } else if (a.epilogue == TC_EPI_SPADE_BF16) {
+    if (!(a.sx && a.mean && a.rstd && a.out_bf16 && a.bias)) bad = "conv_tc: SPADE epilogue needs sx, mean, rstd, bias, out_bf16";
+    if (a.ncols % 128 != 0) bad = "conv_tc: SPADE epilogue needs a multiple of 128 columns";
+  } else if (a.epilogue == TC_EPI_ACT_BF16) {
+    if (!a.out_bf16) bad = "conv_tc: out_bf16 is null";
+  } else if (a.epilogue == TC_EPI_PHASE_F32) {
+    if (!a.y || a.ncols != 32) bad = "conv_tc: phase epilogue needs y and exactly 32 (padded) columns";
   } else {
-    if (!(a.sx && a.mean && a.rstd && a.out_bf16 && a.bias)) {
-      delete p;
-      return fail(MSR_E_INVALID, "conv_tc: SPADE epilogue needs sx, mean, rstd, bias, out_bf16");
-    }
+    bad = "conv_tc: unknown epilogue";
+  }
+  if (bad) {
+    delete p;
+    return fail(MSR_E_INVALID, bad);
   }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -498,10 +599,15 @@ int conv_tc_plan_create(ConvTC** out, const ConvTCArgs& a) {
                                           tc::Cfg<128>::kSmemBytes);
     cudaError_t e2 = cudaFuncSetAttribute(tc::conv3x3_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           tc::Cfg<256>::kSmemBytes);
-    if (e1 != cudaSuccess || e2 != cudaSuccess) {
-      delete p;
-      return fail(MSR_E_CUDA, std::string("conv_tc: cudaFuncSetAttribute: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
-    }
+    cudaError_t e3 = cudaFuncSetAttribute(tc::conv3x3_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          tc::Cfg<64>::kSmemBytes);
+    cudaError_t e4 = cudaFuncSetAttribute(tc::conv3x3_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          tc::Cfg<32>::kSmemBytes);
+    for (cudaError_t ee : {e1, e2, e3, e4})
+      if (ee != cudaSuccess) {
+        delete p;
+        return fail(MSR_E_CUDA, std::string("conv_tc: cudaFuncSetAttribute: ") + cudaGetErrorString(ee));
+      }
     attr_set = true;
   }
   *out = p;
@@ -510,11 +616,20 @@ int conv_tc_plan_create(ConvTC** out, const ConvTCArgs& a) {
 
 int conv_tc_launch(const ConvTC* p, cudaStream_t st) {
   MSR_REQUIRE(p, "conv_tc_launch: null plan");
-  ProfileScope prof(MSR_PROF_CONV_TC, st, 2.0 * (double)p->g.n * p->g.r * p->g.r * p->g.ncols * 9.0 * p->g.cin);
-  if (p->bn == 256)
-    tc::conv3x3_tc_kernel<256><<<p->grid, tc::kThreads, tc::Cfg<256>::kSmemBytes, st>>>(p->map_a, p->map_b, p->g, p->ep);
-  else
-    tc::conv3x3_tc_kernel<128><<<p->grid, tc::kThreads, tc::Cfg<128>::kSmemBytes, st>>>(p->map_a, p->map_b, p->g, p->ep);
+  ProfileScope prof(MSR_PROF_CONV_TC, st, 2.0 * (double)p->g.n * p->g.r * p->g.r * p->g.ncols * p->g.taps * p->g.cin);
+  switch (p->bn) {
+    case 256:
+      tc::conv3x3_tc_kernel<256><<<p->grid, tc::kThreads, tc::Cfg<256>::kSmemBytes, st>>>(p->map_a, p->map_b, p->g, p->ep);
+      break;
+    case 128:
+      tc::conv3x3_tc_kernel<128><<<p->grid, tc::kThreads, tc::Cfg<128>::kSmemBytes, st>>>(p->map_a, p->map_b, p->g, p->ep);
+      break;
+    case 64:
+      tc::conv3x3_tc_kernel<64><<<p->grid, tc::kThreads, tc::Cfg<64>::kSmemBytes, st>>>(p->map_a, p->map_b, p->g, p->ep);
+      break;
+    default:
+      tc::conv3x3_tc_kernel<32><<<p->grid, tc::kThreads, tc::Cfg<32>::kSmemBytes, st>>>(p->map_a, p->map_b, p->g, p->ep);
+  }
   count_launch();
   MSR_LAUNCH_CHECK();
   return MSR_OK;

@@ -47,6 +47,7 @@ struct SpadeW {
   const float* gb_b = nullptr;     // fp32 [2C] (gamma | beta)
   const __nv_bfloat16* gb_wt = nullptr;  // bf16 [2C][1152], rows interleaved per 64 channels
   const float* gb_bt = nullptr;          // fp32 [2C] in the interleaved order
+  const __nv_bfloat16* conv_wt = nullptr;  // bf16 [128][64]: k = (ky*3+kx)*2 + c for k < 18, zero beyond (im2col GEMM)
   int C = 0;
 };
 
@@ -82,6 +83,17 @@ struct msr_generator {
   const float* enc_w[5] = {}; const float* enc_g[5] = {}; const float* enc_bt[5] = {};
   const float* enc_mean_w = nullptr; const float* enc_mean_b = nullptr;
   const float* enc_var_w = nullptr; const float* enc_var_b = nullptr;
+  // bf16 mode extras
+  const __nv_bfloat16* dense_wt = nullptr;       // [256][sw*sw*1024]
+  const __nv_bfloat16* out_wt = nullptr;         // [32][9*128] sub-pixel phase weights of the final 4x4 conv
+  const __nv_bfloat16* enc1_wt = nullptr;        // [64][64] im2col weights of encoder block 1
+  const __nv_bfloat16* enc_wt[5] = {};           // [cout][9*cin] for blocks 2..5
+  const __nv_bfloat16* enc_head_wt = nullptr;    // [feat][512] = mean | variance
+  const float* enc_head_b = nullptr;             // [512]
+  __nv_bfloat16* patches = nullptr;              // im2col'd source [n][r][r][64]
+  __nv_bfloat16* enc_b0 = nullptr; __nv_bfloat16* enc_b1 = nullptr; float* enc_y = nullptr; float* enc_feat = nullptr;
+  float* lat_mv = nullptr;                       // [n][512] mean | variance
+  float2* stat_pairs = nullptr;
   // pix2pix
   const float* pd_w[8] = {}; const float* pd_mean[8] = {}; const float* pd_rstd[8] = {}; const float* pd_g[8] = {}; const float* pd_b[8] = {};
   const float* pu_w[7] = {}; const float* pu_mean[7] = {}; const float* pu_rstd[7] = {}; const float* pu_g[7] = {}; const float* pu_b[7] = {};
@@ -201,6 +213,12 @@ int load_spade(msr_generator* g, const std::string& pre, int C, SpadeW* s) {
     }
     if ((rc = upload_bf16(g, wt, &s->gb_wt))) return rc;
     if ((rc = upload(g, bt, &s->gb_bt))) return rc;
+    const HostTensor* cw;
+    if ((rc = need(g, pre + ".conv.kernel", {3, 3, 2, kHidden}, &cw))) return rc;
+    std::vector<uint16_t> cwt((size_t)kHidden * 64, 0);
+    for (int k = 0; k < 18; ++k)
+      for (int co = 0; co < kHidden; ++co) cwt[(size_t)co * 64 + k] = f2bf(cw->data[(size_t)k * kHidden + co]);
+    if ((rc = upload_bf16(g, cwt, &s->conv_wt))) return rc;
   }
   return MSR_OK;
 }
@@ -230,11 +248,93 @@ int ws(msr_generator* g, T** out, int64_t count) {
   return MSR_OK;
 }
 
+// bf16 mode: repacked weights for the tensor-core encoder / dense / final layer and their workspace
+int finalize_spade_bf16_extras(msr_generator* g) {
+  const int I = g->I, sw = I / 64;
+  const int64_t N = (int64_t)g->B * g->maxG;
+  const int64_t half = (int64_t)(I / 2) * (I / 2);
+  int rc;
+  const HostTensor* t;
+  {  // generator dense [256][sw*sw*1024]
+    const int64_t nout = 16 * sw * sw * 64;
+    if ((rc = need(g, "gen.dense.kernel", {kLatent, nout}, &t))) return rc;
+    std::vector<uint16_t> w((size_t)kLatent * nout);
+    for (size_t e = 0; e < w.size(); ++e) w[e] = f2bf(t->data[e]);
+    if ((rc = upload_bf16(g, w, &g->dense_wt))) return rc;
+  }
+  {  // final Conv2D(1, 4, 'same') on the x2-upsampled tensor == 3x3 conv to 4 sub-pixel phases on the low-res tensor:
+     // output row 2h+py reads upsampled rows 2h+py-1+ky (pad before = 1), i.e. low-res rows h + ((py-1+ky) >> 1)
+    if ((rc = need(g, "gen.out.kernel", {4, 4, 128, 1}, &t))) return rc;
+    std::vector<float> acc((size_t)32 * 9 * 128, 0.f);
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px)
+        for (int ky = 0; ky < 4; ++ky)
+          for (int kx = 0; kx < 4; ++kx) {
+            const int ty = ((py - 1 + ky) >> 1) + 1, tx = ((px - 1 + kx) >> 1) + 1;  // arithmetic shift: -1 >> 1 = -1
+            for (int c = 0; c < 128; ++c)
+              acc[((size_t)(py * 2 + px) * 9 + ty * 3 + tx) * 128 + c] += t->data[((size_t)ky * 4 + kx) * 128 + c];
+          }
+    std::vector<uint16_t> w(acc.size());
+    for (size_t e = 0; e < w.size(); ++e) w[e] = f2bf(acc[e]);
+    if ((rc = upload_bf16(g, w, &g->out_wt))) return rc;
+  }
+  {  // encoder block 1: im2col GEMM weights [64][64]
+    if ((rc = need(g, "enc.down1.kernel", {3, 3, 2, kEnc[0]}, &t))) return rc;
+    std::vector<uint16_t> w((size_t)kEnc[0] * 64, 0);
+    for (int k = 0; k < 18; ++k)
+      for (int co = 0; co < kEnc[0]; ++co) w[(size_t)co * 64 + k] = f2bf(t->data[(size_t)k * kEnc[0] + co]);
+    if ((rc = upload_bf16(g, w, &g->enc1_wt))) return rc;
+  }
+  for (int k = 1; k < 5; ++k) {
+    const int cin = kEnc[k - 1], cout = kEnc[k], K = 9 * cin;
+    if ((rc = need(g, "enc.down" + std::to_string(k + 1) + ".kernel", {3, 3, cin, cout}, &t))) return rc;
+    std::vector<uint16_t> w((size_t)cout * K);
+    for (int kk = 0; kk < K; ++kk)
+      for (int co = 0; co < cout; ++co) w[(size_t)co * K + kk] = f2bf(t->data[(size_t)kk * cout + co]);
+    if ((rc = upload_bf16(g, w, &g->enc_wt[k]))) return rc;
+  }
+  {  // heads: [feat][512] = mean | variance
+    const int64_t feat = (int64_t)(I / 32) * (I / 32) * 512;
+    const HostTensor *wm, *wv, *bm, *bv;
+    if ((rc = need(g, "enc.mean.kernel", {feat, kLatent}, &wm))) return rc;
+    if ((rc = need(g, "enc.variance.kernel", {feat, kLatent}, &wv))) return rc;
+    if ((rc = need(g, "enc.mean.bias", {kLatent}, &bm))) return rc;
+    if ((rc = need(g, "enc.variance.bias", {kLatent}, &bv))) return rc;
+    std::vector<uint16_t> w((size_t)feat * 2 * kLatent);
+    for (int64_t f = 0; f < feat; ++f)
+      for (int c = 0; c < kLatent; ++c) {
+        w[(size_t)f * 2 * kLatent + c] = f2bf(wm->data[(size_t)f * kLatent + c]);
+        w[(size_t)f * 2 * kLatent + kLatent + c] = f2bf(wv->data[(size_t)f * kLatent + c]);
+      }
+    std::vector<float> b(2 * kLatent);
+    for (int c = 0; c < kLatent; ++c) {
+      b[c] = bm->data[c];
+      b[kLatent + c] = bv->data[c];
+    }
+    if ((rc = upload_bf16(g, w, &g->enc_head_wt))) return rc;
+    if ((rc = upload(g, b, &g->enc_head_b))) return rc;
+  }
+  if ((rc = ws(g, &g->patches, N * half * 64))) return rc;
+  if ((rc = ws(g, &g->enc_b0, N * half * 64))) return rc;
+  if ((rc = ws(g, &g->enc_b1, N * (half / 4) * 128))) return rc;
+  if ((rc = ws(g, &g->enc_y, N * (half / 4) * 128))) return rc;
+  if ((rc = ws(g, &g->enc_feat, N * (int64_t)(I / 32) * (I / 32) * 512))) return rc;
+  if ((rc = ws(g, &g->lat_mv, N * 2 * kLatent))) return rc;
+  if ((rc = ws(g, &g->stat_pairs, 4 * N * half))) return rc;
+  const int64_t need_partial = std::max<int64_t>(296 * N * 2 * kLatent, 4 * N * 16 * sw * sw * 64);
+  if (need_partial > g->dense_partial_cap) {
+    g->dense_partial_cap = need_partial;
+    if ((rc = ws(g, &g->dense_partial, need_partial))) return rc;
+  }
+  return MSR_OK;
+}
+
 int finalize_spade(msr_generator* g) {
   const int I = g->I, sw = I / 64;
   const int64_t N = (int64_t)g->B * g->maxG;
   int rc;
-  if ((rc = upload_named(g, "gen.dense.kernel", {kLatent, 16 * sw * sw * 64}, &g->dense_w))) return rc;
+  const bool fp32 = g->precision == MSR_PRECISION_FP32;
+  if (fp32 && (rc = upload_named(g, "gen.dense.kernel", {kLatent, 16 * sw * sw * 64}, &g->dense_w))) return rc;
   if ((rc = upload_named(g, "gen.dense.bias", {16 * sw * sw * 64}, &g->dense_b))) return rc;
   int cin = 1024;
   for (int k = 0; k < 6; ++k) {
@@ -254,12 +354,12 @@ int finalize_spade(msr_generator* g) {
     }
     cin = cout;
   }
-  if ((rc = upload_named(g, "gen.out.kernel", {4, 4, 128, 1}, &g->out_w))) return rc;
+  if (fp32 && (rc = upload_named(g, "gen.out.kernel", {4, 4, 128, 1}, &g->out_w))) return rc;
   if ((rc = upload_named(g, "gen.out.bias", {1}, &g->out_b))) return rc;
   int ec = 2;
   for (int k = 0; k < 5; ++k) {
     const std::string pre = "enc.down" + std::to_string(k + 1);
-    if ((rc = upload_named(g, pre + ".kernel", {3, 3, ec, kEnc[k]}, &g->enc_w[k]))) return rc;
+    if (fp32 && (rc = upload_named(g, pre + ".kernel", {3, 3, ec, kEnc[k]}, &g->enc_w[k]))) return rc;
     if (k > 0) {
       if ((rc = upload_named(g, pre + ".in_gamma", {kEnc[k]}, &g->enc_g[k]))) return rc;
       if ((rc = upload_named(g, pre + ".in_beta", {kEnc[k]}, &g->enc_bt[k]))) return rc;
@@ -267,16 +367,20 @@ int finalize_spade(msr_generator* g) {
     ec = kEnc[k];
   }
   const int64_t feat = (int64_t)(I / 32) * (I / 32) * 512;
-  if ((rc = upload_named(g, "enc.mean.kernel", {feat, kLatent}, &g->enc_mean_w))) return rc;
-  if ((rc = upload_named(g, "enc.mean.bias", {kLatent}, &g->enc_mean_b))) return rc;
-  if ((rc = upload_named(g, "enc.variance.kernel", {feat, kLatent}, &g->enc_var_w))) return rc;
-  if ((rc = upload_named(g, "enc.variance.bias", {kLatent}, &g->enc_var_b))) return rc;
+  if (fp32) {
+    if ((rc = upload_named(g, "enc.mean.kernel", {feat, kLatent}, &g->enc_mean_w))) return rc;
+    if ((rc = upload_named(g, "enc.mean.bias", {kLatent}, &g->enc_mean_b))) return rc;
+    if ((rc = upload_named(g, "enc.variance.kernel", {feat, kLatent}, &g->enc_var_w))) return rc;
+    if ((rc = upload_named(g, "enc.variance.bias", {kLatent}, &g->enc_var_b))) return rc;
+  }
 
   // ---- workspace
   const int64_t half = (int64_t)(I / 2) * (I / 2);
   // encoder: largest activation is the first block's output (I/2)^2 * 64
-  if ((rc = ws(g, &g->enc_buf[0], N * half * 64))) return rc;
-  if ((rc = ws(g, &g->enc_buf[1], N * (half / 4) * 128))) return rc;
+  if (fp32) {
+    if ((rc = ws(g, &g->enc_buf[0], N * half * 64))) return rc;
+    if ((rc = ws(g, &g->enc_buf[1], N * (half / 4) * 128))) return rc;
+  }
   if ((rc = ws(g, &g->enc_stats_mean, N * 512))) return rc;
   if ((rc = ws(g, &g->enc_stats_rstd, N * 512))) return rc;
   if ((rc = ws(g, &g->lat_mean, N * kLatent))) return rc;
@@ -293,6 +397,9 @@ int finalize_spade(msr_generator* g) {
   for (int i = 0; i < 3; ++i) {
     if ((rc = ws(g, &g->st_mean[i], (int64_t)g->maxG * 1024))) return rc;
     if ((rc = ws(g, &g->st_rstd[i], (int64_t)g->maxG * 1024))) return rc;
+  }
+  if (g->precision == MSR_PRECISION_BF16) {
+    if ((rc = finalize_spade_bf16_extras(g))) return rc;
   }
   if (g->precision == MSR_PRECISION_FP32) {
     if ((rc = ws(g, &g->a_f32, N * half * kHidden))) return rc;
@@ -508,6 +615,135 @@ int forward_spade(Fwd& f, const float* source, const float* eps, float* out) {
   return MSR_OK;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// bf16 tensor-core mode: every convolution and the im2col'd 2-channel convolutions run in conv_tc.cu
+// ------------------------------------------------------------------------------------------------------------------
+int spade_bf16(Fwd& f, const SpadeW& s, const float* x, int x_shift, const float* mean, const float* rstd, int r) {
+  msr_generator* g = f.g;
+  const int n = (int)f.N;
+  int rc;
+  // a = relu(conv3x3(resized mask)) as a K = 64 GEMM on the im2col'd source (spade.py:17-18)
+  ConvTCArgs m;
+  m.x = g->patches; m.w = s.conv_wt; m.n = n; m.r = r; m.cin = 64; m.ncols = kHidden; m.taps = 1; m.pad = 0;
+  m.epilogue = TC_EPI_ACT_BF16; m.bias = s.conv_b; m.act = ACT_RELU; m.out_bf16 = g->a_bf16;
+  if ((rc = tc_conv(f, m))) return rc;
+  // gamma | beta convolution with the fused normalise - modulate - LeakyReLU epilogue (spade.py:19-24, blocks.py:30)
+  ConvTCArgs a;
+  a.x = g->a_bf16; a.w = s.gb_wt; a.n = n; a.r = r; a.cin = kHidden; a.ncols = 2 * s.C;
+  a.epilogue = TC_EPI_SPADE_BF16; a.bias = s.gb_bt; a.sx = x; a.sx_shift = x_shift; a.mean = mean; a.rstd = rstd;
+  a.samples_per_group = g->B; a.slope = 0.2f; a.out_bf16 = g->act_bf16;
+  return tc_conv(f, a);
+}
+
+// main conv on act_bf16 -> y fp32 (+ residual) and the batch statistics of y into (mean, rstd) when requested
+int conv_bf16(Fwd& f, const ConvW& w, int r, float* y, const float* res, int res_shift, float* mean, float* rstd) {
+  msr_generator* g = f.g;
+  const int n = (int)f.N;
+  int rc;
+  const bool fused = mean != nullptr && r * r >= 128;
+  ConvTCArgs a;
+  a.x = g->act_bf16; a.w = w.wt; a.n = n; a.r = r; a.cin = w.cin; a.ncols = w.cout;
+  a.epilogue = TC_EPI_BIAS_F32; a.bias = w.b; a.y = y; a.res = res; a.res_shift = res_shift;
+  a.stat_pairs = fused ? g->stat_pairs : nullptr;
+  if ((rc = tc_conv(f, a))) return rc;
+  if (mean == nullptr) return MSR_OK;
+  if (fused) {
+    const int64_t rows_p = (int64_t)g->B * (r * r / 128) * 4;
+    return channel_stats_from_pairs(g->stat_pairs, f.groups, rows_p, (int64_t)g->B * r * r, w.cout, 1e-5f,
+                                    g->stat_partial, mean, rstd, f.st);
+  }
+  return channel_stats_f32(y, w.cout, f.groups, (int64_t)g->B * r * r, w.cout, 1e-5f, g->stat_partial, mean, rstd, f.st);
+}
+
+int forward_spade_bf16(Fwd& f, const float* source, const float* eps, float* out) {
+  msr_generator* g = f.g;
+  const int I = g->I, sw = I / 64, n = (int)f.N;
+  cudaStream_t st = f.st;
+  int rc;
+  // ---- encoder (networks.py:8-34)
+  // block 1: conv3x3 s2 (2 -> 64, no bias, no norm) + LeakyReLU(0.2) as an im2col GEMM
+  if ((rc = source_patches_bf16(source, I, g->patches, n, I / 2, 1, st))) return rc;
+  {
+    ConvTCArgs a;
+    a.x = g->patches; a.w = g->enc1_wt; a.n = n; a.r = I / 2; a.cin = 64; a.ncols = kEnc[0]; a.taps = 1; a.pad = 0;
+    a.epilogue = TC_EPI_ACT_BF16; a.act = ACT_LRELU; a.slope = 0.2f; a.out_bf16 = g->enc_b0;
+    if ((rc = tc_conv(f, a))) return rc;
+  }
+  const __nv_bfloat16* ex = g->enc_b0;
+  int er = I / 2;
+  for (int k = 1; k < 5; ++k) {   // blocks 2..5: conv3x3 s2 SAME pad (0, 1) -> InstanceNorm (eps 1e-3) -> LeakyReLU(0.2)
+    er /= 2;
+    ConvTCArgs a;
+    a.x = ex; a.w = g->enc_wt[k]; a.n = n; a.r = er; a.cin = kEnc[k - 1]; a.ncols = kEnc[k]; a.stride = 2; a.pad = 0;
+    a.epilogue = TC_EPI_BIAS_F32; a.y = g->enc_y;
+    if ((rc = tc_conv(f, a))) return rc;
+    const int64_t rows = (int64_t)er * er;
+    if ((rc = channel_stats_f32(g->enc_y, kEnc[k], n, rows, kEnc[k], 1e-3f, g->stat_partial, g->enc_stats_mean,
+                                g->enc_stats_rstd, st))) return rc;
+    __nv_bfloat16* eb = (k & 1) ? g->enc_b1 : g->enc_b0;
+    if ((rc = affine_act_bf16out(g->enc_y, kEnc[k], g->enc_stats_mean, g->enc_stats_rstd, g->enc_g[k], g->enc_bt[k],
+                                 k < 4 ? eb : nullptr, k == 4 ? g->enc_feat : nullptr, (int64_t)n * rows, kEnc[k], rows,
+                                 ACT_LRELU, 0.2f, st))) return rc;
+    ex = eb;
+  }
+  const int feat = er * er * 512;
+  if ((rc = dense_bf16w(g->enc_feat, g->enc_head_wt, g->enc_head_b, g->lat_mv, n, feat, 2 * kLatent, g->dense_partial,
+                        g->dense_partial_cap, st))) return rc;
+  // ---- sampler (sampling.py:11-17) or mean + variance (model.py:789-791); mean | variance interleaved per row
+  if ((rc = sampler_strided_f32(g->lat_mv, 2 * kLatent, g->arch == MSR_ARCH_SPADE ? eps : nullptr, g->latent, n, kLatent,
+                                st))) return rc;
+  g->acts["latent"] = {g->latent, (int64_t)n * kLatent, 0};
+  // ---- generator (networks.py:37-57)
+  float* x = g->xbuf[0];
+  if ((rc = dense_bf16w(g->latent, g->dense_wt, g->dense_b, x, n, kLatent, sw * sw * 1024, g->dense_partial,
+                        g->dense_partial_cap, st))) return rc;
+  g->acts["x0"] = {x, (int64_t)n * sw * sw * 1024, 0};
+  int r = sw, x_shift = 0;
+  if ((rc = channel_stats_f32(x, 1024, f.groups, (int64_t)g->B * sw * sw, 1024, 1e-5f, g->stat_partial, g->st_mean[0],
+                              g->st_rstd[0], st))) return rc;
+  for (int k = 0; k < 6; ++k) {
+    const BlockW& b = g->rb[k];
+    float* y = g->xbuf[(k + 1) & 1];
+    if ((rc = source_patches_bf16(source, I, g->patches, n, r, 0, st))) return rc;   // shared by the block's SPADEs
+    // x = conv_1(lrelu(spade_1(in)))                                  blocks.py:29-30
+    if ((rc = spade_bf16(f, b.s1, x, x_shift, g->st_mean[0], g->st_rstd[0], r))) return rc;
+    if ((rc = conv_bf16(f, b.c1, r, g->h1, nullptr, 0, g->st_mean[1], g->st_rstd[1]))) return rc;
+    const float* res = x;
+    int res_shift = x_shift;
+    if (b.learned) {  // skip = conv_3(lrelu(spade_3(in)))             blocks.py:34-36
+      if ((rc = spade_bf16(f, b.s3, x, x_shift, g->st_mean[0], g->st_rstd[0], r))) return rc;
+      if ((rc = conv_bf16(f, b.c3, r, g->s3, nullptr, 0, nullptr, nullptr))) return rc;
+      res = g->s3;
+      res_shift = 0;
+    }
+    // x = conv_2(lrelu(spade_2(x))); out = skip + x                   blocks.py:31-32,38
+    if ((rc = spade_bf16(f, b.s2, g->h1, 0, g->st_mean[1], g->st_rstd[1], r))) return rc;
+    if (k < 5) {
+      if ((rc = conv_bf16(f, b.c2, r, y, res, res_shift, g->st_mean[0], g->st_rstd[0]))) return rc;
+      g->acts["rb" + std::to_string(k + 1) + ".out"] = {y, (int64_t)n * r * r * b.cout, 0};
+    } else {
+      // last block: its output only feeds leaky_relu(0.2) + the final conv (networks.py:54-56): emit that directly
+      ConvTCArgs a;
+      a.x = g->act_bf16; a.w = b.c2.wt; a.n = n; a.r = r; a.cin = b.c2.cin; a.ncols = b.c2.cout;
+      a.epilogue = TC_EPI_ACT_BF16; a.bias = b.c2.b; a.res = res; a.res_shift = res_shift; a.act = ACT_LRELU;
+      a.slope = 0.2f; a.out_bf16 = g->a_bf16;
+      if ((rc = tc_conv(f, a))) return rc;
+    }
+    x = y;
+    x_shift = 1;  // UpSampling2D((2, 2)) after every block (networks.py:44-54), fused into the consumers
+    r *= 2;
+  }
+  // UpSampling2D -> leaky_relu(0.2) -> Conv2D(1, 4, 'same') == 3x3 conv to 4 sub-pixel phases on the low-res tensor
+  {
+    ConvTCArgs a;
+    a.x = g->a_bf16; a.w = g->out_wt; a.n = n; a.r = r / 2; a.cin = 128; a.ncols = 32;
+    a.epilogue = TC_EPI_PHASE_F32; a.bias = g->out_b; a.y = out;
+    if ((rc = tc_conv(f, a))) return rc;
+  }
+  g->acts["out"] = {out, (int64_t)n * I * I, 0};
+  return MSR_OK;
+}
+
 int forward_pix2pix(Fwd& f, const float* source, float* out) {
   msr_generator* g = f.g;
   const int n = (int)f.N;
@@ -630,7 +866,9 @@ extern "C" int msr_generator_forward(msr_generator* g, const float* d_source, co
     f.plans = &g->plans[n_groups];
   }
   const int64_t before = g_launch_count;
-  int rc = (g->arch == MSR_ARCH_PIX2PIX) ? forward_pix2pix(f, d_source, d_out) : forward_spade(f, d_source, d_eps, d_out);
+  int rc = (g->arch == MSR_ARCH_PIX2PIX)          ? forward_pix2pix(f, d_source, d_out)
+           : (g->precision == MSR_PRECISION_BF16) ? forward_spade_bf16(f, d_source, d_eps, d_out)
+                                                  : forward_spade(f, d_source, d_eps, d_out);
   g->last_launches = g_launch_count - before;
   if (rc && f.building) {  // never keep a half-built plan list
     for (auto* p : *f.plans) conv_tc_plan_destroy(p);

@@ -52,6 +52,9 @@ int dense_f32(const float* x, const float* w, const float* bias, float* out, int
 // latent = mean + exp(0.5 * var) * eps (sampling.py:16) when eps != null, else mean + var (model.py:791).
 int sampler_f32(const float* mean, const float* var, const float* eps, float* latent, int64_t count, cudaStream_t st);
 
+// same, with mean | variance stored side by side in rows of pitch ld (mean at [0, L), variance at [L, 2L))
+int sampler_strided_f32(const float* mv, int ld, const float* eps, float* latent, int n, int L, cudaStream_t st);
+
 // Final generator layer (networks.py:54-56): UpSampling2D(2) -> leaky_relu(0.2) -> Conv2D(1, 4, 'same') on
 // x [n][r][r][128] fp32 -> out [n][2r][2r] fp32.  w [4][4][128] (Keras [4,4,128,1]), bias scalar.
 int final_conv_f32(const float* x, const float* w, const float* bias, float* out, int n, int r, cudaStream_t st);
@@ -59,19 +62,24 @@ int final_conv_f32(const float* x, const float* w, const float* bias, float* out
 // ---- tensor-core path (conv_tc.cu) -------------------------------------------------------------------------------
 struct ConvTC;  // opaque plan
 enum TcEpilogue {
-  TC_EPI_BIAS_F32 = 0,    // y_f32 = acc + bias (+ residual)
+  TC_EPI_BIAS_F32 = 0,    // y_f32 = acc + bias (+ residual); optional fused per-channel statistics partials
   TC_EPI_SPADE_BF16 = 1,  // columns are gamma|beta interleaved per 64; out_bf16 = lrelu(gamma * xhat + beta)
+  TC_EPI_ACT_BF16 = 2,    // out_bf16 = act(acc + bias (+ residual))
+  TC_EPI_PHASE_F32 = 3,   // 4 sub-pixel phase columns -> y[b][2h+py][2w+px] (final generator layer)
 };
 struct ConvTCArgs {
-  const __nv_bfloat16* x = nullptr;  // [n][r][r][cin] bf16
-  const __nv_bfloat16* w = nullptr;  // [ncols][9*cin] bf16 (K-major)
-  int n = 0, r = 0, cin = 0, ncols = 0;
+  const __nv_bfloat16* x = nullptr;  // [n][r*stride][r*stride][cin] bf16
+  const __nv_bfloat16* w = nullptr;  // [ncols][taps*cin] bf16 (K-major), k = tap*cin + ci
+  int n = 0, r = 0, cin = 0, ncols = 0;   // r = output side
+  int taps = 9;                      // 9: 3x3, 1: 1x1
+  int stride = 1, pad = 1;           // input coordinate = out*stride + k - pad
   int epilogue = TC_EPI_BIAS_F32;
   const float* bias = nullptr;       // [ncols]
-  // TC_EPI_BIAS_F32
-  float* y = nullptr;                // [n*r*r][ncols]
-  const float* res = nullptr;        // residual [n][r >> res_shift][r >> res_shift][ncols] or null
+  // TC_EPI_BIAS_F32 / TC_EPI_PHASE_F32
+  float* y = nullptr;                // [n*r*r][ncols]  (PHASE: [n][2r][2r])
+  const float* res = nullptr;        // residual [n][r >> res_shift][r >> res_shift][ncols] or null (also ACT_BF16)
   int res_shift = 0;
+  float2* stat_pairs = nullptr;      // [n*r*r/128 * 4][ncols] (sum, sumsq) partials; requires r*r >= 128
   // TC_EPI_SPADE_BF16 (ncols = 2C, column tile of 128 = 64 gamma | 64 beta of the same channels)
   const float* sx = nullptr;         // normalised tensor [n][r >> sx_shift][r >> sx_shift][C] fp32
   int sx_shift = 0;
@@ -79,13 +87,35 @@ struct ConvTCArgs {
   const float* rstd = nullptr;
   int samples_per_group = 1;
   float slope = 0.2f;
-  __nv_bfloat16* out_bf16 = nullptr; // [n*r*r][C]
+  int act = ACT_NONE;                // TC_EPI_ACT_BF16
+  __nv_bfloat16* out_bf16 = nullptr; // [n*r*r][C] (SPADE) / [n*r*r][ncols] (ACT)
 };
 int conv_tc_plan_create(ConvTC** plan, const ConvTCArgs& a);
 int conv_tc_launch(const ConvTC* plan, cudaStream_t st);
 void conv_tc_plan_destroy(ConvTC* plan);
 
-// small helpers for the bf16 path
+// ---- small helpers for the bf16 path (nn_bf16.cu) -----------------------------------------------------------------
+// im2col of the 2-channel source for a 3x3 convolution at output side r: out [n][r][r][64] bf16, channel (ky*3+kx)*2+c
+// for c in {ortho, dem}, channels 18..63 zero.  mode 0: SPADE's mask path = nearest resize (half-pixel centres,
+// spade.py:17) to r x r followed by SAME padding (1, 1); mode 1: encoder block 1 = stride-2 taps on the full
+// resolution source with SAME padding (0, 1) (r = I / 2, blocks.py:53-60).
+int source_patches_bf16(const float* source, int I, __nv_bfloat16* out, int n, int r, int mode, cudaStream_t st);
+
+// out[m][n] = sum_k x[m][k] * w[k][n] + bias[n], bf16 weights, fp32 activations / accumulation.  ldo = row pitch of
+// out.  `partial` scratch of ksplit * M * N floats.
+int dense_bf16w(const float* x, const __nv_bfloat16* w, const float* bias, float* out, int M, int K, int N,
+                float* partial, int64_t partial_capacity, cudaStream_t st);
+
+// (x - mean) * rstd * gamma + beta -> activation -> bf16 (and / or fp32) output; same conventions as affine_act_f32.
+int affine_act_bf16out(const float* x, int ldx, const float* mean, const float* rstd, const float* gamma,
+                       const float* beta, __nv_bfloat16* y_bf16, float* y_f32, int64_t M, int C, int64_t rows_per_group,
+                       int act, float slope, cudaStream_t st);
+
+// statistics from the fused (sum, sumsq) pairs written by the tensor-core epilogue: pairs [groups*rows_p][C]
+int channel_stats_from_pairs(const float2* pairs, int groups, int64_t rows_p, int64_t count_per_group, int C, float eps,
+                             double* partial, float* mean, float* rstd, cudaStream_t st);
+
+// legacy CUDA-core mask conv (kept for the operator tests)
 int mask_conv_bf16(const float* source, int I, const float* w, const float* bias, __nv_bfloat16* out, int n, int r,
                    cudaStream_t st);  // nearest-resize + conv3x3 2->128 + relu -> bf16 [n][r][r][128]
 

@@ -1,0 +1,275 @@
+// Bandwidth-bound helpers of the bf16 tensor-core mode: everything around the tcgen05 convolutions that is not a GEMM.
+//
+// Reference semantics: spade/models/spade.py:17-18 (mask resize + 2->128 conv input), blocks.py:53-65 (encoder block),
+// networks.py:31-33,41 (dense layers), spade.py:21 (batch moments).
+#include "nn.cuh"
+
+namespace msr {
+
+// ------------------------------------------------------------------------------------------------------------------
+// im2col of the 2-channel source: one thread per output pixel writes one 128-byte row (18 bf16 taps + zeros), so the
+// 2->128 (SPADE mask) and 2->64 (encoder block 1) 3x3 convolutions become K = 64 GEMMs on the tensor cores.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) source_patches_kernel(const float* __restrict__ src, int I,
+                                                             __nv_bfloat16* __restrict__ out, int n, int r, int mode) {
+  const int64_t total = (int64_t)n * r * r;
+  const int f = I / r, half = f >> 1;
+  for (int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; m < total; m += (int64_t)gridDim.x * blockDim.x) {
+    const int nn = (int)(m / ((int64_t)r * r));
+    const int rem = (int)(m % ((int64_t)r * r));
+    const int h = rem / r, x = rem % r;
+    __align__(16) __nv_bfloat16 row[64];
+#pragma unroll
+    for (int j = 18; j < 64; ++j) row[j] = __float2bfloat16_rn(0.f);
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        float2 s = make_float2(0.f, 0.f);
+        if (mode == 0) {  // resized-mask coordinates, SAME pad (1, 1); nearest resize with half-pixel centres (App. B.3)
+          const int hh = h + ky - 1, xx = x + kx - 1;
+          if (hh >= 0 && hh < r && xx >= 0 && xx < r)
+            s = __ldg(reinterpret_cast<const float2*>(src + (((int64_t)nn * I + hh * f + half) * I + xx * f + half) * 2));
+        } else {          // stride-2 taps on the full-resolution source, SAME pad (0, 1) (App. B.2)
+          const int sy = 2 * h + ky, sx = 2 * x + kx;
+          if (sy < I && sx < I) s = __ldg(reinterpret_cast<const float2*>(src + (((int64_t)nn * I + sy) * I + sx) * 2));
+        }
+        row[(ky * 3 + kx) * 2 + 0] = __float2bfloat16_rn(s.x);
+        row[(ky * 3 + kx) * 2 + 1] = __float2bfloat16_rn(s.y);
+      }
+    }
+    uint4* dst = reinterpret_cast<uint4*>(out + m * 64);
+    const uint4* sp = reinterpret_cast<const uint4*>(row);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) dst[q] = sp[q];
+  }
+}
+
+int source_patches_bf16(const float* source, int I, __nv_bfloat16* out, int n, int r, int mode, cudaStream_t st) {
+  MSR_REQUIRE(source && out && n > 0 && r > 0 && I % r == 0, "source_patches: bad arguments");
+  MSR_REQUIRE(mode == 0 || (mode == 1 && r * 2 == I), "source_patches: mode 1 needs r = I / 2");
+  const int64_t total = (int64_t)n * r * r;
+  ProfileScope prof(MSR_PROF_MASK_CONV, st, (double)total * (128.0 + 8.0));
+  const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 16);
+  source_patches_kernel<<<blocks, 256, 0, st>>>(source, I, out, n, r, mode);
+  count_launch();
+  MSR_LAUNCH_CHECK();
+  return MSR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Dense layer with bf16 weights for small M (<= 16 rows per pass): weight-bandwidth bound.  Block = 128 threads, each
+// owning 4 consecutive output columns; the K range is split across blockIdx.y (deterministic two-stage sum).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kDM = 16;    // rows per pass
+constexpr int kDKT = 32;   // k rows staged per iteration
+
+__global__ void __launch_bounds__(128) dense_bf16w_partial_kernel(const float* __restrict__ x,
+                                                                  const __nv_bfloat16* __restrict__ w,
+                                                                  float* __restrict__ partial, int M, int K, int N,
+                                                                  int kchunk, int m0) {
+  __shared__ float xs[kDM][kDKT + 4];
+  const int n4 = (blockIdx.x * 128 + threadIdx.x) * 4;
+  const int split = blockIdx.y;
+  const int k0 = split * kchunk, k1 = min(K, k0 + kchunk);
+  const int mrows = min(kDM, M - m0);
+  float acc[kDM][4];
+#pragma unroll
+  for (int i = 0; i < kDM; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+  for (int kb = k0; kb < k1; kb += kDKT) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < kDM * kDKT; e += 128) {
+      const int mi = e / kDKT, kk = e % kDKT;
+      xs[mi][kk] = (mi < mrows && kb + kk < k1) ? __ldg(x + (int64_t)(m0 + mi) * K + kb + kk) : 0.f;
+    }
+    __syncthreads();
+    if (n4 < N) {
+      uint2 wv[kDKT];
+#pragma unroll
+      for (int kk = 0; kk < kDKT; ++kk)
+        wv[kk] = (kb + kk < k1) ? __ldg(reinterpret_cast<const uint2*>(w + (int64_t)(kb + kk) * N + n4))
+                                : make_uint2(0u, 0u);
+#pragma unroll
+      for (int kk = 0; kk < kDKT; ++kk) {
+        const float w0 = __uint_as_float(wv[kk].x << 16), w1 = __uint_as_float(wv[kk].x & 0xffff0000u);
+        const float w2 = __uint_as_float(wv[kk].y << 16), w3 = __uint_as_float(wv[kk].y & 0xffff0000u);
+#pragma unroll
+        for (int i = 0; i < kDM; ++i) {
+          const float xv = xs[i][kk];
+          acc[i][0] = fmaf(xv, w0, acc[i][0]);
+          acc[i][1] = fmaf(xv, w1, acc[i][1]);
+          acc[i][2] = fmaf(xv, w2, acc[i][2]);
+          acc[i][3] = fmaf(xv, w3, acc[i][3]);
+        }
+      }
+    }
+  }
+  if (n4 < N) {
+#pragma unroll
+    for (int i = 0; i < kDM; ++i)
+      if (i < mrows)
+        *reinterpret_cast<float4*>(partial + ((int64_t)split * M + m0 + i) * N + n4) =
+            make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+  }
+}
+
+__global__ void dense_bf16w_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ bias,
+                                          float* __restrict__ out, int M, int N, int ksplit) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= (int64_t)M * N) return;
+  float s = 0.f;
+  for (int k = 0; k < ksplit; ++k) s += partial[(int64_t)k * M * N + e];
+  if (bias) s += bias[e % N];
+  out[e] = s;
+}
+
+int dense_bf16w(const float* x, const __nv_bfloat16* w, const float* bias, float* out, int M, int K, int N,
+                float* partial, int64_t partial_capacity, cudaStream_t st) {
+  MSR_REQUIRE(x && w && out && partial && M > 0 && K > 0 && N > 0 && N % 4 == 0, "dense_bf16w: bad arguments");
+  ProfileScope prof(MSR_PROF_DENSE, st, 2.0 * M * (double)K * N, 2);
+  const int gx = ceil_div(N, 512);
+  int ksplit = std::max(1, std::min(ceil_div(K, kDKT), (2 * 148) / gx));
+  while ((int64_t)ksplit * M * N > partial_capacity && ksplit > 1) --ksplit;
+  MSR_REQUIRE((int64_t)ksplit * M * N <= partial_capacity, "dense_bf16w: partial scratch too small");
+  int kchunk = ceil_div(K, ksplit);
+  kchunk = ceil_div(kchunk, kDKT) * kDKT;
+  ksplit = ceil_div(K, kchunk);
+  for (int m0 = 0; m0 < M; m0 += kDM) {
+    dense_bf16w_partial_kernel<<<dim3(gx, ksplit), 128, 0, st>>>(x, w, partial, M, K, N, kchunk, m0);
+    MSR_LAUNCH_CHECK();
+    count_launch();
+  }
+  dense_bf16w_reduce_kernel<<<ceil_div((int64_t)M * N, 256), 256, 0, st>>>(partial, bias, out, M, N, ksplit);
+  MSR_LAUNCH_CHECK();
+  count_launch();
+  return MSR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// normalise + affine + activation with bf16 (and optionally fp32) output, 4 channels per thread
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) affine_act_bf16_kernel(const float* __restrict__ x, int ldx,
+                                                              const float* __restrict__ mean,
+                                                              const float* __restrict__ rstd,
+                                                              const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta,
+                                                              __nv_bfloat16* __restrict__ yb, float* __restrict__ yf,
+                                                              int64_t M, int C, int64_t rows_per_group, int act,
+                                                              float slope) {
+  const int c4n = C / 4;
+  const int64_t total = M * c4n;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e % c4n) * 4;
+    const int64_t m = e / c4n;
+    const float4 xv = *reinterpret_cast<const float4*>(x + m * ldx + c);
+    float v[4] = {xv.x, xv.y, xv.z, xv.w};
+    if (mean) {
+      const int64_t g = m / rows_per_group;
+      const float4 mu = *reinterpret_cast<const float4*>(mean + g * C + c);
+      const float4 rs = *reinterpret_cast<const float4*>(rstd + g * C + c);
+      v[0] = (v[0] - mu.x) * rs.x; v[1] = (v[1] - mu.y) * rs.y; v[2] = (v[2] - mu.z) * rs.z; v[3] = (v[3] - mu.w) * rs.w;
+    }
+    if (gamma) {
+      const float4 ga = *reinterpret_cast<const float4*>(gamma + c);
+      v[0] *= ga.x; v[1] *= ga.y; v[2] *= ga.z; v[3] *= ga.w;
+    }
+    if (beta) {
+      const float4 be = *reinterpret_cast<const float4*>(beta + c);
+      v[0] += be.x; v[1] += be.y; v[2] += be.z; v[3] += be.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (act == ACT_RELU) v[j] = fmaxf(v[j], 0.f);
+      else if (act == ACT_LRELU) v[j] = v[j] > 0.f ? v[j] : v[j] * slope;
+    }
+    if (yf) *reinterpret_cast<float4*>(yf + m * C + c) = make_float4(v[0], v[1], v[2], v[3]);
+    if (yb) {
+      __align__(8) __nv_bfloat16 o[4] = {__float2bfloat16_rn(v[0]), __float2bfloat16_rn(v[1]),
+                                          __float2bfloat16_rn(v[2]), __float2bfloat16_rn(v[3])};
+      *reinterpret_cast<uint2*>(yb + m * C + c) = *reinterpret_cast<const uint2*>(o);
+    }
+  }
+}
+
+int affine_act_bf16out(const float* x, int ldx, const float* mean, const float* rstd, const float* gamma,
+                       const float* beta, __nv_bfloat16* y_bf16, float* y_f32, int64_t M, int C, int64_t rows_per_group,
+                       int act, float slope, cudaStream_t st) {
+  MSR_REQUIRE(x && (y_bf16 || y_f32) && M > 0 && C > 0 && C % 4 == 0 && ldx % 4 == 0 && rows_per_group > 0,
+              "affine_act_bf16out: bad arguments");
+  ProfileScope prof(MSR_PROF_ELEMWISE, st, (double)M * C * (4.0 + (y_bf16 ? 2.0 : 0.0) + (y_f32 ? 4.0 : 0.0)));
+  const int64_t total = M * (C / 4);
+  const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 16);
+  affine_act_bf16_kernel<<<blocks, 256, 0, st>>>(x, ldx, mean, rstd, gamma, beta, y_bf16, y_f32, M, C, rows_per_group,
+                                                 act, slope);
+  count_launch();
+  MSR_LAUNCH_CHECK();
+  return MSR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// batch statistics from the (sum, sumsq) pairs emitted by the tensor-core epilogue (deterministic, fp64 second stage)
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) stats_pairs_partial_kernel(const float2* __restrict__ pairs, int64_t rows_p, int C,
+                                                                  double* __restrict__ partial) {
+  // grid (ceil(C/32), kStatSplit, groups); block = 32 channels x 8 row lanes
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  const int split = blockIdx.y, g = blockIdx.z;
+  const int64_t per = (rows_p + kStatSplit - 1) / kStatSplit;
+  const int64_t r0 = split * per, r1 = min(rows_p, r0 + per);
+  double s = 0.0, q = 0.0;
+  if (c < C) {
+    const float2* base = pairs + ((int64_t)g * rows_p) * C + c;
+    for (int64_t r = r0 + ry; r < r1; r += 8) {
+      const float2 v = __ldg(base + r * C);
+      s += (double)v.x;
+      q += (double)v.y;
+    }
+  }
+  __shared__ double sh[2][8][32];
+  sh[0][ry][cx] = s;
+  sh[1][ry][cx] = q;
+  __syncthreads();
+  if (ry == 0 && c < C) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+      s += sh[0][k][cx];
+      q += sh[1][k][cx];
+    }
+    double* o = partial + (((int64_t)g * kStatSplit + split) * C + c) * 2;
+    o[0] = s;
+    o[1] = q;
+  }
+}
+
+__global__ void stats_pairs_finalize_kernel(const double* __restrict__ partial, int C, int64_t count, float eps,
+                                            float* __restrict__ mean, float* __restrict__ rstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int g = blockIdx.y;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int k = 0; k < kStatSplit; ++k) {
+    const double* o = partial + (((int64_t)g * kStatSplit + k) * C + c) * 2;
+    s += o[0];
+    q += o[1];
+  }
+  const double mu = s / (double)count;
+  double var = q / (double)count - mu * mu;
+  if (var < 0.0) var = 0.0;
+  mean[(int64_t)g * C + c] = (float)mu;
+  rstd[(int64_t)g * C + c] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+int channel_stats_from_pairs(const float2* pairs, int groups, int64_t rows_p, int64_t count_per_group, int C, float eps,
+                             double* partial, float* mean, float* rstd, cudaStream_t st) {
+  MSR_REQUIRE(pairs && partial && mean && rstd && groups > 0 && rows_p > 0 && C > 0, "stats_from_pairs: bad arguments");
+  ProfileScope prof(MSR_PROF_STATS, st, (double)groups * rows_p * C * 8.0, 2);
+  stats_pairs_partial_kernel<<<dim3(ceil_div(C, 32), kStatSplit, groups), 256, 0, st>>>(pairs, rows_p, C, partial);
+  MSR_LAUNCH_CHECK();
+  stats_pairs_finalize_kernel<<<dim3(ceil_div(C, 128), groups), 128, 0, st>>>(partial, C, count_per_group, eps, mean, rstd);
+  MSR_LAUNCH_CHECK();
+  count_launch(2);
+  return MSR_OK;
+}
+
+}  // namespace msr

@@ -411,6 +411,24 @@ int sampler_f32(const float* mean, const float* var, const float* eps, float* la
   return MSR_OK;
 }
 
+__global__ void sampler_strided_kernel(const float* __restrict__ mv, int ld, const float* __restrict__ eps,
+                                       float* __restrict__ latent, int n, int L) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= (int64_t)n * L) return;
+  const int row = (int)(e / L), c = (int)(e % L);
+  const float m = mv[(int64_t)row * ld + c], v = mv[(int64_t)row * ld + L + c];
+  latent[e] = eps ? m + expf(0.5f * v) * eps[e] : m + v;
+}
+
+int sampler_strided_f32(const float* mv, int ld, const float* eps, float* latent, int n, int L, cudaStream_t st) {
+  MSR_REQUIRE(mv && latent && n > 0 && L > 0 && ld >= 2 * L, "sampler: bad arguments");
+  ProfileScope prof(MSR_PROF_ELEMWISE, st, (double)n * L * 16.0);
+  sampler_strided_kernel<<<ceil_div((int64_t)n * L, 256), 256, 0, st>>>(mv, ld, eps, latent, n, L);
+  count_launch();
+  MSR_LAUNCH_CHECK();
+  return MSR_OK;
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // Final layer: upsample x2 -> leaky_relu(0.2) -> conv 4x4 SAME (pad 1 before, 2 after) -> 1 channel.
 // Block = 16x16 output pixels; the (10 x 10) low-res halo tile is staged in shared memory after the leaky relu; each

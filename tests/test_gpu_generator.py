@@ -52,6 +52,58 @@ def test_conv3x3_tensor_core_operator(torch, n, r, cin, cout):
     assert np.abs(got - want).max() < 2e-3, np.abs(got - want).max()
 
 
+@pytest.mark.parametrize("n,r_out,cin,cout,taps,stride,pad,act", [
+    (2, 16, 64, 128, 9, 2, 0, 0),      # encoder block: 3x3 stride 2, SAME pad (0, 1)
+    (1, 64, 128, 256, 9, 2, 0, 0),
+    (3, 8, 64, 64, 1, 1, 0, 2),        # 1x1 (im2col GEMM), leaky-relu, bf16 out, 64 columns
+    (2, 32, 64, 128, 1, 1, 0, 1),      # 1x1, relu, bf16 out
+    (1, 16, 128, 32, 9, 1, 1, 0),      # 32 columns
+    (2, 16, 64, 128, 9, 1, 1, 0),      # fp32 out + fused statistics
+])
+def test_conv_tc_general_operator(torch, n, r_out, cin, cout, taps, stride, pad, act):
+    from moonsuperresolution_b200 import _lib
+    import torch.nn.functional as F
+    rng = np.random.default_rng(r_out * 7 + cout)
+    rin = r_out * stride
+    ks = 3 if taps == 9 else 1
+    x = bf16_round(rng.standard_normal((n, rin, rin, cin)).astype(np.float32), torch)
+    w = bf16_round((rng.standard_normal((ks, ks, cin, cout)) / np.sqrt(taps * cin)).astype(np.float32), torch)
+    b = rng.standard_normal(cout).astype(np.float32)
+    xt = torch.from_numpy(x).permute(0, 3, 1, 2)
+    if taps == 9:
+        after = (r_out - 1) * stride + 3 - pad - rin       # zero rows / cols needed after the last input element
+        xt = F.pad(xt, (pad, max(after, 0), pad, max(after, 0)))
+    wt_t = torch.from_numpy(w).permute(3, 2, 0, 1)
+    want = F.conv2d(xt, wt_t, torch.from_numpy(b), stride=stride).permute(0, 2, 3, 1).numpy()
+    assert want.shape == (n, r_out, r_out, cout)
+    d_x = torch.from_numpy(x).cuda().to(torch.bfloat16).contiguous()
+    d_w = torch.from_numpy(np.ascontiguousarray(w.reshape(taps * cin, cout).T)).cuda().to(torch.bfloat16).contiguous()
+    d_b = torch.from_numpy(b).cuda()
+    bf16_out = taps == 1
+    use_stats = (not bf16_out) and stride == 1 and r_out * r_out >= 128 and cout == 128
+    d_y = torch.zeros((n, r_out, r_out, cout), dtype=torch.bfloat16 if bf16_out else torch.float32, device="cuda")
+    pairs = torch.zeros((n * r_out * r_out // 128 * 4, cout, 2), dtype=torch.float32, device="cuda") if use_stats else None
+    _lib.check(_lib.lib().msr_op_conv_tc(d_x.data_ptr(), d_w.data_ptr(), d_b.data_ptr(),
+                                         None if bf16_out else d_y.data_ptr(), d_y.data_ptr() if bf16_out else None,
+                                         n, r_out, cin, cout, taps, stride, pad, act, 0.2, _lib.ptr(pairs),
+                                         _lib.stream_ptr()), "msr_op_conv_tc")
+    torch.cuda.synchronize()
+    got = d_y.float().cpu().numpy()
+    if act == 1:
+        want = np.maximum(want, 0)
+    elif act == 2:
+        want = np.where(want > 0, want, 0.2 * want)
+    tol = 2e-2 if bf16_out else 2e-3
+    assert np.abs(got - want).max() < tol, np.abs(got - want).max()
+    if use_stats:
+        p = pairs.cpu().numpy().astype(np.float64)
+        flat = got.reshape(-1, cout).astype(np.float64)
+        np.testing.assert_allclose(p[:, :, 0].sum(0), flat.sum(0), rtol=1e-5, atol=1e-3)
+        np.testing.assert_allclose(p[:, :, 1].sum(0), (flat ** 2).sum(0), rtol=1e-5, atol=1e-3)
+        # each (tile, warp) row covers 32 consecutive pixels
+        np.testing.assert_allclose(p[5, :, 0], flat[5 * 32:6 * 32].sum(0), rtol=1e-5, atol=1e-4)
+
+
 @pytest.mark.parametrize("n,r,cin,cout", [(2, 8, 5, 7), (1, 16, 64, 33), (3, 4, 128, 128)])
 def test_conv3x3_fp32_operator(torch, n, r, cin, cout):
     from moonsuperresolution_b200 import _lib
