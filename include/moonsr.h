@@ -61,6 +61,9 @@ int msr_profile_enable(int on);
 /* Synchronises the device and returns, per family f < MSR_PROF_COUNT: ms[f] summed event time, work[f] summed
  * algorithmic work (FLOPs for the convolution / dense families, bytes for the others), launches[f]. */
 int msr_profile_read(double* ms, double* work, int64_t* launches);
+/* Per-launch-group records of one family, in launch order: fills up to `capacity` entries of ms / work and returns the
+ * total number of records in *count. */
+int msr_profile_records(int family, double* ms, double* work, int64_t capacity, int64_t* count);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Tiling / blending  (process_full_tiles.py)

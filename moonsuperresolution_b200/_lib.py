@@ -28,6 +28,7 @@ SIGNATURES: Dict[str, tuple] = {
     "msr_device_sm_count": (_i, []),
     "msr_profile_enable": (_i, [_i]),
     "msr_profile_read": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_i64)]),
+    "msr_profile_records": (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_double), _i64, C.POINTER(_i64)]),
     "msr_pad_inputs": (_i, [_vp, _vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "msr_validity_sat": (_i, [_vp, _vp, _i, _i, _f, _vp, _vp]),
     "msr_patch_validity": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _vp]),
@@ -98,6 +99,15 @@ def profile_read() -> Dict[str, dict]:
     ms, work, cnt = (C.c_double * n)(), (C.c_double * n)(), (_i64 * n)()
     check(lib().msr_profile_read(ms, work, cnt), "msr_profile_read")
     return {f: {"ms": ms[k], "work": work[k], "launches": int(cnt[k])} for k, f in enumerate(PROFILE_FAMILIES)}
+
+
+def profile_records(family: str, capacity: int = 1 << 16):
+    """[(ms, work)] per launch group of ``family`` in launch order."""
+    ms, work, cnt = (C.c_double * capacity)(), (C.c_double * capacity)(), _i64(0)
+    check(lib().msr_profile_records(PROFILE_FAMILIES.index(family), ms, work, capacity, C.byref(cnt)),
+          "msr_profile_records")
+    n = min(int(cnt.value), capacity)
+    return [(ms[k], work[k]) for k in range(n)]
 
 
 def last_error() -> str:

@@ -108,6 +108,24 @@ extern "C" int msr_op_conv3x3_bf16(const uint16_t* d_x, const uint16_t* d_w, con
   return rc;
 }
 
+extern "C" int msr_profile_records(int family, double* ms, double* work, int64_t capacity, int64_t* count) {
+  MSR_REQUIRE(ms && work && count && capacity >= 0, "msr_profile_records: bad arguments");
+  MSR_CUDA_CHECK(cudaDeviceSynchronize());
+  int64_t k = 0;
+  for (auto& r : g_records) {
+    if (r.family != family) continue;
+    if (k < capacity) {
+      float t = 0.f;
+      MSR_CUDA_CHECK(cudaEventElapsedTime(&t, r.e0, r.e1));
+      ms[k] = t;
+      work[k] = r.work;
+    }
+    ++k;
+  }
+  *count = k;
+  return MSR_OK;
+}
+
 extern "C" int msr_op_conv_tc(const uint16_t* d_x, const uint16_t* d_w, const float* d_bias, float* d_y_f32,
                               uint16_t* d_y_bf16, int n, int r_out, int cin, int cout, int taps, int stride, int pad,
                               int act, float slope, float* d_stat_pairs, void* stream) {
