@@ -12,7 +12,8 @@
 //   * B (weights, [N][K] K-major) is a 2-D TMA box {64, BN};
 //   * tcgen05.mma cta_group::1, M=128, N=BN, K=16, fp32 accumulators in TMEM, double buffered (2 x BN columns) so
 //     the epilogue of tile i overlaps the main loop of tile i+1;
-//   * persistent CTAs (one per SM), 6 warps: 0-3 epilogue (TMEM lane quarter = warp id), 4 TMA producer, 5 MMA issuer.
+//   * persistent CTAs (one per SM), 10 warps: 0-7 epilogue (TMEM lane quarter = warp % 4, the two warps of a quarter
+//     take alternate 32-column chunks), 8 TMA producer, 9 MMA issuer.
 #include <cuda.h>
 
 #include <mutex>
@@ -26,7 +27,8 @@ namespace tc {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                       // bf16 elements = 128 bytes = one swizzle row
 constexpr int kABytes = kBlockM * kBlockK * 2;    // 16 KB
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;                      // two per TMEM lane quarter: they split the accumulator columns
+constexpr int kThreads = (kEpiWarps + 2) * 32;   // + TMA producer warp + MMA issuer warp
 
 template <int BN>
 struct Cfg {
@@ -40,6 +42,7 @@ struct Cfg {
 struct Geometry {
   int n, r, cin, ncols;      // r = OUTPUT side; the input side is r * stride
   int taps;                  // 9 (3x3) or 1 (1x1)
+  int split;                 // split-bf16 operands: A has 2*cin channels (hi | lo), B has 3*cin columns per tap
   int stride, pad;           // input coordinate of tap (ky, kx) for output (h, w): (h*stride + ky - pad, w*stride + kx - pad)
   int TW, TH, NB;            // tile = NB images x TH rows x TW cols (all powers of two, product 128)
   int tiles_w, tiles_h, tiles_b, n_tiles_m, n_tiles_n;
@@ -59,6 +62,7 @@ struct EpiParams {
   int samples_per_group;
   float slope;
   int act;
+  int split_out;             // TC_EPI_ACT_BF16: write hi | lo halves (row pitch 2 * ncols)
   __nv_bfloat16* out_bf16;
 };
 
@@ -201,7 +205,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = g.n_tiles_m * g.n_tiles_n;
-  const int k_chunks_per_tap = g.cin / kBlockK;
+  const int chunks_per_part = g.cin / kBlockK;
+  const int k_chunks_per_tap = (g.split ? 3 : 1) * chunks_per_part;
   const int k_chunks = g.taps * k_chunks_per_tap;
 
   if (threadIdx.x == 0) {
@@ -211,15 +216,15 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);  // one arrive per epilogue warp
+      mbar_init(tempty_bar(a), kEpiWarps);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
-  if (warp == 4 && lane == 0) {
+  if (warp == kEpiWarps && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
   }
-  if (warp == 5) tmem_alloc(smem_u32((const void*)tmem_slot), C::kTmemCols);
+  if (warp == kEpiWarps + 1) tmem_alloc(smem_u32((const void*)tmem_slot), C::kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -234,7 +239,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     n0 = nt * BN;
   };
 
-  if (warp == 4) {
+  if (warp == kEpiWarps) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
@@ -249,9 +254,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           const uint32_t sa = smem_base + stage * C::kStageBytes;
           const uint32_t sb = sa + kABytes;
           mbar_expect_tx(full_bar(stage), C::kStageBytes);
-          tma_load_4d(sa, &map_a, full_bar(stage), cb * kBlockK, w0 * g.stride + kx - g.pad, h0 * g.stride + ky - g.pad,
-                      b0);
-          tma_load_2d(sb, &map_b, full_bar(stage), tap * g.cin + cb * kBlockK, n0);
+          // split-bf16: parts (x_hi, x_hi, x_lo) of A pair with (w_hi, w_lo, w_hi) of B
+          const int a_chan = g.split ? ((cb / chunks_per_part == 2) ? g.cin : 0) + (cb % chunks_per_part) * kBlockK
+                                     : cb * kBlockK;
+          tma_load_4d(sa, &map_a, full_bar(stage), a_chan, w0 * g.stride + kx - g.pad, h0 * g.stride + ky - g.pad, b0);
+          tma_load_2d(sb, &map_b, full_bar(stage), (tap * k_chunks_per_tap + cb) * kBlockK, n0);
           if (++stage == C::kStages) {
             stage = 0;
             phase ^= 1u;
@@ -259,7 +266,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kEpiWarps + 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BN);
@@ -294,10 +301,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       }
     }
   } else {
-    // ===================== epilogue warps 0..3 =====================
+    // ===================== epilogue warps 0..7 =====================
+    // warp w reads TMEM lanes 32*(w % 4) .. +31 (hardware rule); warps w and w + 4 take alternate 32-column chunks
     int acc = 0;
     uint32_t acc_phase = 0;
-    const int row = threadIdx.x;  // tile row == TMEM lane
+    const int quarter = warp & 3, csel = warp >> 2;
+    const int row = quarter * 32 + lane;  // tile row == TMEM lane
     const int wi = row % g.TW, hi = (row / g.TW) % g.TH, bi = row / (g.TW * g.TH);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       int b0, h0, w0, n0;
@@ -307,7 +316,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       const int64_t m = ((int64_t)b * g.r + h) * g.r + w;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN);
+      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
       if (ep.mode == TC_EPI_BIAS_F32) {
         int64_t res_row = 0;
         if (ep.res != nullptr) {
@@ -316,7 +325,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         }
         const int mt = tile / g.n_tiles_n;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = csel * 32; c0 < BN; c0 += 64) {
           uint32_t v[32];
           tmem_ld32(t_row + (uint32_t)c0, v);
           tmem_ld_wait();
@@ -353,7 +362,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 32; ++j) t[j] = row_ok ? o[j] * o[j] : 0.f;
             const float sq = warp_transpose_reduce(t, lane);
-            ep.stat_pairs[((int64_t)mt * 4 + warp) * g.ncols + col + lane] = make_float2(sum, sq);
+            ep.stat_pairs[((int64_t)mt * 4 + quarter) * g.ncols + col + lane] = make_float2(sum, sq);
           }
         }
       } else if (ep.mode == TC_EPI_ACT_BF16) {
@@ -364,7 +373,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           res_row = ((int64_t)b * rs + (h >> ep.res_shift)) * rs + (w >> ep.res_shift);
         }
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = csel * 32; c0 < BN; c0 += 64) {
           uint32_t v[32];
           tmem_ld32(t_row + (uint32_t)c0, v);
           tmem_ld_wait();
@@ -393,19 +402,43 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
               ob[j] = __float2bfloat16_rn(o.x); ob[j + 1] = __float2bfloat16_rn(o.y);
               ob[j + 2] = __float2bfloat16_rn(o.z); ob[j + 3] = __float2bfloat16_rn(o.w);
             }
-            uint4* dst = reinterpret_cast<uint4*>(ep.out_bf16 + m * g.ncols + col);
-            const uint4* src = reinterpret_cast<const uint4*>(ob);
+            if (!ep.split_out) {
+              uint4* dst = reinterpret_cast<uint4*>(ep.out_bf16 + m * g.ncols + col);
+              const uint4* src = reinterpret_cast<const uint4*>(ob);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) dst[q] = src[q];
+              for (int q = 0; q < 4; ++q) dst[q] = src[q];
+            } else {
+              uint4* dst = reinterpret_cast<uint4*>(ep.out_bf16 + m * 2 * g.ncols + col);
+              const uint4* src = reinterpret_cast<const uint4*>(ob);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) dst[q] = src[q];
+              // lo half: recompute the activation value and subtract its bf16 rounding
+              __align__(16) __nv_bfloat16 lb[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                float o = __uint_as_float(v[j]);
+                if (ep.bias) o += __ldg(ep.bias + col + j);
+                if (rs_ptr) o += __ldg(rs_ptr + j);
+                if (ep.act == ACT_RELU) o = fmaxf(o, 0.f);
+                else if (ep.act == ACT_LRELU) o = o > 0.f ? o : o * ep.slope;
+                lb[j] = __float2bfloat16_rn(o - __bfloat162float(ob[j]));
+              }
+              uint4* dl = reinterpret_cast<uint4*>(ep.out_bf16 + m * 2 * g.ncols + g.ncols + col);
+              const uint4* sl = reinterpret_cast<const uint4*>(lb);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) dl[q] = sl[q];
+            }
           }
         }
       } else if (ep.mode == TC_EPI_PHASE_F32) {
         // final generator layer as a 3x3 convolution to 4 sub-pixel phases (columns 0..3 = (py, px)) + pixel shuffle:
         // y[b][2h + py][2w + px] = acc[py*2 + px] + bias[0]
         uint32_t v[32];
-        tmem_ld32(t_row, v);
-        tmem_ld_wait();
-        if (row_ok && n0 == 0) {
+        if (csel == 0) {
+          tmem_ld32(t_row, v);
+          tmem_ld_wait();
+        }
+        if (csel == 0 && row_ok && n0 == 0) {
           const float b0f = ep.bias ? __ldg(ep.bias) : 0.f;
           const int R = 2 * g.r;
           float* dst = ep.y + ((int64_t)b * R + 2 * h) * R + 2 * w;
@@ -422,8 +455,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll 1
         for (int gc = 0; gc < BN; gc += 128) {
           const int ch0 = ((n0 + gc) >> 7) * 64;
-#pragma unroll 1
-          for (int half = 0; half < 2; ++half) {
+          {
+            const int half = csel;
             uint32_t ga[32], be[32];
             tmem_ld32(t_row + (uint32_t)(gc + half * 32), ga);
             tmem_ld32(t_row + (uint32_t)(gc + 64 + half * 32), be);
@@ -475,7 +508,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == kEpiWarps + 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, C::kTmemCols);
   }
@@ -523,7 +556,7 @@ int conv_tc_plan_create(ConvTC** out, const ConvTCArgs& a) {
   ConvTC* p = new ConvTC();
   tc::Geometry& g = p->g;
   g.n = a.n; g.r = a.r; g.cin = a.cin; g.ncols = a.ncols;
-  g.taps = a.taps; g.stride = a.stride; g.pad = a.taps == 1 ? 0 : a.pad;
+  g.taps = a.taps; g.stride = a.stride; g.pad = a.taps == 1 ? 0 : a.pad; g.split = a.split3 ? 1 : 0;
   g.TW = std::min(a.r, 128);
   g.TH = std::min(a.r, 128 / g.TW);
   g.NB = 128 / (g.TW * g.TH);
@@ -538,8 +571,9 @@ int conv_tc_plan_create(ConvTC** out, const ConvTCArgs& a) {
 
   // A: 4-D NHWC tensor {C, W, H, N}; a stride-2 convolution walks W and H with element stride 2
   {
-    cuuint64_t dims[4] = {(cuuint64_t)a.cin, (cuuint64_t)rin, (cuuint64_t)rin, (cuuint64_t)a.n};
-    cuuint64_t strides[3] = {(cuuint64_t)a.cin * 2, (cuuint64_t)rin * a.cin * 2, (cuuint64_t)rin * rin * a.cin * 2};
+    const cuuint64_t ca = (cuuint64_t)a.cin * (a.split3 ? 2 : 1);
+    cuuint64_t dims[4] = {ca, (cuuint64_t)rin, (cuuint64_t)rin, (cuuint64_t)a.n};
+    cuuint64_t strides[3] = {ca * 2, (cuuint64_t)rin * ca * 2, (cuuint64_t)rin * rin * ca * 2};
     cuuint32_t box[4] = {(cuuint32_t)tc::kBlockK, (cuuint32_t)(g.TW * a.stride), (cuuint32_t)(g.TH * a.stride),
                          (cuuint32_t)g.NB};
     cuuint32_t estr[4] = {1, (cuuint32_t)a.stride, (cuuint32_t)a.stride, 1};
@@ -553,8 +587,9 @@ int conv_tc_plan_create(ConvTC** out, const ConvTCArgs& a) {
   }
   // B: 2-D weights {K, N}
   {
-    cuuint64_t dims[2] = {(cuuint64_t)a.taps * a.cin, (cuuint64_t)a.ncols};
-    cuuint64_t strides[1] = {(cuuint64_t)a.taps * a.cin * 2};
+    const cuuint64_t kb = (cuuint64_t)a.taps * a.cin * (a.split3 ? 3 : 1);
+    cuuint64_t dims[2] = {kb, (cuuint64_t)a.ncols};
+    cuuint64_t strides[1] = {kb * 2};
     cuuint32_t box[2] = {(cuuint32_t)tc::kBlockK, (cuuint32_t)p->bn};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(&p->map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(a.w), dims, strides, box,
@@ -570,7 +605,7 @@ int conv_tc_plan_create(ConvTC** out, const ConvTCArgs& a) {
   e.bias = a.bias; e.y = a.y; e.res = a.res; e.res_shift = a.res_shift; e.stat_pairs = a.stat_pairs;
   e.sx = a.sx; e.sx_shift = a.sx_shift; e.mean = a.mean; e.rstd = a.rstd;
   e.samples_per_group = a.samples_per_group > 0 ? a.samples_per_group : 1;
-  e.slope = a.slope; e.act = a.act; e.out_bf16 = a.out_bf16;
+  e.slope = a.slope; e.act = a.act; e.split_out = a.split_out; e.out_bf16 = a.out_bf16;
   const char* bad = nullptr;
   if (a.epilogue == TC_EPI_BIAS_F32) {
     if (!a.y) bad = "conv_tc: y is null";

@@ -159,6 +159,14 @@ int upload_named(msr_generator* g, const std::string& name, std::vector<int64_t>
   return upload(g, t->data, out);
 }
 
+float bf2f(uint16_t h) {
+  uint32_t u = (uint32_t)h << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+uint16_t f2bf(float f);
 uint16_t f2bf(float f) {  // round-to-nearest-even, like __float2bfloat16_rn
   uint32_t u;
   memcpy(&u, &f, 4);
@@ -215,9 +223,15 @@ int load_spade(msr_generator* g, const std::string& pre, int C, SpadeW* s) {
     if ((rc = upload(g, bt, &s->gb_bt))) return rc;
     const HostTensor* cw;
     if ((rc = need(g, pre + ".conv.kernel", {3, 3, 2, kHidden}, &cw))) return rc;
-    std::vector<uint16_t> cwt((size_t)kHidden * 64, 0);
+    std::vector<uint16_t> cwt((size_t)kHidden * 64, 0);   // split-bf16: [w_hi | w_lo | w_hi] against (x_hi, x_hi, x_lo)
     for (int k = 0; k < 18; ++k)
-      for (int co = 0; co < kHidden; ++co) cwt[(size_t)co * 64 + k] = f2bf(cw->data[(size_t)k * kHidden + co]);
+      for (int co = 0; co < kHidden; ++co) {
+        const float v = cw->data[(size_t)k * kHidden + co];
+        const uint16_t hi = f2bf(v);
+        cwt[(size_t)co * 64 + k] = hi;
+        cwt[(size_t)co * 64 + 18 + k] = f2bf(v - bf2f(hi));
+        cwt[(size_t)co * 64 + 36 + k] = hi;
+      }
     if ((rc = upload_bf16(g, cwt, &s->conv_wt))) return rc;
   }
   return MSR_OK;
@@ -255,13 +269,6 @@ int finalize_spade_bf16_extras(msr_generator* g) {
   const int64_t half = (int64_t)(I / 2) * (I / 2);
   int rc;
   const HostTensor* t;
-  {  // generator dense [256][sw*sw*1024]
-    const int64_t nout = 16 * sw * sw * 64;
-    if ((rc = need(g, "gen.dense.kernel", {kLatent, nout}, &t))) return rc;
-    std::vector<uint16_t> w((size_t)kLatent * nout);
-    for (size_t e = 0; e < w.size(); ++e) w[e] = f2bf(t->data[e]);
-    if ((rc = upload_bf16(g, w, &g->dense_wt))) return rc;
-  }
   {  // final Conv2D(1, 4, 'same') on the x2-upsampled tensor == 3x3 conv to 4 sub-pixel phases on the low-res tensor:
      // output row 2h+py reads upsampled rows 2h+py-1+ky (pad before = 1), i.e. low-res rows h + ((py-1+ky) >> 1)
     if ((rc = need(g, "gen.out.kernel", {4, 4, 128, 1}, &t))) return rc;
@@ -282,46 +289,39 @@ int finalize_spade_bf16_extras(msr_generator* g) {
     if ((rc = need(g, "enc.down1.kernel", {3, 3, 2, kEnc[0]}, &t))) return rc;
     std::vector<uint16_t> w((size_t)kEnc[0] * 64, 0);
     for (int k = 0; k < 18; ++k)
-      for (int co = 0; co < kEnc[0]; ++co) w[(size_t)co * 64 + k] = f2bf(t->data[(size_t)k * kEnc[0] + co]);
+      for (int co = 0; co < kEnc[0]; ++co) {
+        const float v = t->data[(size_t)k * kEnc[0] + co];
+        const uint16_t hi = f2bf(v);
+        w[(size_t)co * 64 + k] = hi;
+        w[(size_t)co * 64 + 18 + k] = f2bf(v - bf2f(hi));
+        w[(size_t)co * 64 + 36 + k] = hi;
+      }
     if ((rc = upload_bf16(g, w, &g->enc1_wt))) return rc;
   }
   for (int k = 1; k < 5; ++k) {
     const int cin = kEnc[k - 1], cout = kEnc[k], K = 9 * cin;
     if ((rc = need(g, "enc.down" + std::to_string(k + 1) + ".kernel", {3, 3, cin, cout}, &t))) return rc;
-    std::vector<uint16_t> w((size_t)cout * K);
-    for (int kk = 0; kk < K; ++kk)
-      for (int co = 0; co < cout; ++co) w[(size_t)co * K + kk] = f2bf(t->data[(size_t)kk * cout + co]);
+    // split-bf16 (the encoder feeds the latent, whose error reaches every later layer): per tap [w_hi | w_lo | w_hi]
+    std::vector<uint16_t> w((size_t)cout * 3 * K);
+    for (int tap = 0; tap < 9; ++tap)
+      for (int ci = 0; ci < cin; ++ci)
+        for (int co = 0; co < cout; ++co) {
+          const float v = t->data[((size_t)tap * cin + ci) * cout + co];
+          const uint16_t hi = f2bf(v);
+          uint16_t* row = &w[(size_t)co * 3 * K + (size_t)tap * 3 * cin];
+          row[ci] = hi;
+          row[cin + ci] = f2bf(v - bf2f(hi));
+          row[2 * cin + ci] = hi;
+        }
     if ((rc = upload_bf16(g, w, &g->enc_wt[k]))) return rc;
   }
-  {  // heads: [feat][512] = mean | variance
-    const int64_t feat = (int64_t)(I / 32) * (I / 32) * 512;
-    const HostTensor *wm, *wv, *bm, *bv;
-    if ((rc = need(g, "enc.mean.kernel", {feat, kLatent}, &wm))) return rc;
-    if ((rc = need(g, "enc.variance.kernel", {feat, kLatent}, &wv))) return rc;
-    if ((rc = need(g, "enc.mean.bias", {kLatent}, &bm))) return rc;
-    if ((rc = need(g, "enc.variance.bias", {kLatent}, &bv))) return rc;
-    std::vector<uint16_t> w((size_t)feat * 2 * kLatent);
-    for (int64_t f = 0; f < feat; ++f)
-      for (int c = 0; c < kLatent; ++c) {
-        w[(size_t)f * 2 * kLatent + c] = f2bf(wm->data[(size_t)f * kLatent + c]);
-        w[(size_t)f * 2 * kLatent + kLatent + c] = f2bf(wv->data[(size_t)f * kLatent + c]);
-      }
-    std::vector<float> b(2 * kLatent);
-    for (int c = 0; c < kLatent; ++c) {
-      b[c] = bm->data[c];
-      b[kLatent + c] = bv->data[c];
-    }
-    if ((rc = upload_bf16(g, w, &g->enc_head_wt))) return rc;
-    if ((rc = upload(g, b, &g->enc_head_b))) return rc;
-  }
   if ((rc = ws(g, &g->patches, N * half * 64))) return rc;
-  if ((rc = ws(g, &g->enc_b0, N * half * 64))) return rc;
-  if ((rc = ws(g, &g->enc_b1, N * (half / 4) * 128))) return rc;
+  if ((rc = ws(g, &g->enc_b0, N * half * 128))) return rc;          // hi | lo halves
+  if ((rc = ws(g, &g->enc_b1, N * (half / 4) * 256))) return rc;
   if ((rc = ws(g, &g->enc_y, N * (half / 4) * 128))) return rc;
   if ((rc = ws(g, &g->enc_feat, N * (int64_t)(I / 32) * (I / 32) * 512))) return rc;
-  if ((rc = ws(g, &g->lat_mv, N * 2 * kLatent))) return rc;
   if ((rc = ws(g, &g->stat_pairs, 4 * N * half))) return rc;
-  const int64_t need_partial = std::max<int64_t>(296 * N * 2 * kLatent, 4 * N * 16 * sw * sw * 64);
+  const int64_t need_partial = std::max<int64_t>(296 * N * kLatent, 4 * N * 16 * sw * sw * 64);
   if (need_partial > g->dense_partial_cap) {
     g->dense_partial_cap = need_partial;
     if ((rc = ws(g, &g->dense_partial, need_partial))) return rc;
@@ -334,7 +334,8 @@ int finalize_spade(msr_generator* g) {
   const int64_t N = (int64_t)g->B * g->maxG;
   int rc;
   const bool fp32 = g->precision == MSR_PRECISION_FP32;
-  if (fp32 && (rc = upload_named(g, "gen.dense.kernel", {kLatent, 16 * sw * sw * 64}, &g->dense_w))) return rc;
+  // the dense layers are weight-bandwidth bound and tiny: fp32 weights in both modes
+  if ((rc = upload_named(g, "gen.dense.kernel", {kLatent, 16 * sw * sw * 64}, &g->dense_w))) return rc;
   if ((rc = upload_named(g, "gen.dense.bias", {16 * sw * sw * 64}, &g->dense_b))) return rc;
   int cin = 1024;
   for (int k = 0; k < 6; ++k) {
@@ -367,12 +368,10 @@ int finalize_spade(msr_generator* g) {
     ec = kEnc[k];
   }
   const int64_t feat = (int64_t)(I / 32) * (I / 32) * 512;
-  if (fp32) {
-    if ((rc = upload_named(g, "enc.mean.kernel", {feat, kLatent}, &g->enc_mean_w))) return rc;
-    if ((rc = upload_named(g, "enc.mean.bias", {kLatent}, &g->enc_mean_b))) return rc;
-    if ((rc = upload_named(g, "enc.variance.kernel", {feat, kLatent}, &g->enc_var_w))) return rc;
-    if ((rc = upload_named(g, "enc.variance.bias", {kLatent}, &g->enc_var_b))) return rc;
-  }
+  if ((rc = upload_named(g, "enc.mean.kernel", {feat, kLatent}, &g->enc_mean_w))) return rc;
+  if ((rc = upload_named(g, "enc.mean.bias", {kLatent}, &g->enc_mean_b))) return rc;
+  if ((rc = upload_named(g, "enc.variance.kernel", {feat, kLatent}, &g->enc_var_w))) return rc;
+  if ((rc = upload_named(g, "enc.variance.bias", {kLatent}, &g->enc_var_b))) return rc;
 
   // ---- workspace
   const int64_t half = (int64_t)(I / 2) * (I / 2);
@@ -386,7 +385,7 @@ int finalize_spade(msr_generator* g) {
   if ((rc = ws(g, &g->lat_mean, N * kLatent))) return rc;
   if ((rc = ws(g, &g->lat_var, N * kLatent))) return rc;
   if ((rc = ws(g, &g->latent, N * kLatent))) return rc;
-  g->dense_partial_cap = std::max<int64_t>(64 * N * kLatent, N * 16 * sw * sw * 64);
+  g->dense_partial_cap = std::max<int64_t>(296 * N * kLatent, 4 * N * 16 * sw * sw * 64);
   if ((rc = ws(g, &g->dense_partial, g->dense_partial_cap))) return rc;
   if ((rc = ws(g, &g->stat_partial, (int64_t)std::max<int64_t>(N, g->maxG) * kStatSplit * 1024 * 2))) return rc;
   const int64_t stream_elems = N * half * 128;  // max over blocks of r^2 * cout (and r_prev^2 * cin)
@@ -560,10 +559,10 @@ int forward_spade(Fwd& f, const float* source, const float* eps, float* out) {
     ecin = kEnc[k];
   }
   const int feat = er * er * 512;
-  if ((rc = dense_f32(ex, g->enc_mean_w, g->enc_mean_b, g->lat_mean, n, feat, kLatent, g->dense_partial,
-                      g->dense_partial_cap, st))) return rc;
-  if ((rc = dense_f32(ex, g->enc_var_w, g->enc_var_b, g->lat_var, n, feat, kLatent, g->dense_partial,
-                      g->dense_partial_cap, st))) return rc;
+  if ((rc = dense_f32w(ex, g->enc_mean_w, g->enc_mean_b, g->lat_mean, n, feat, kLatent, g->dense_partial,
+                       g->dense_partial_cap, st))) return rc;
+  if ((rc = dense_f32w(ex, g->enc_var_w, g->enc_var_b, g->lat_var, n, feat, kLatent, g->dense_partial,
+                       g->dense_partial_cap, st))) return rc;
   // ---- sampler (sampling.py:11-17) or mean + variance (model.py:789-791)
   if ((rc = sampler_f32(g->lat_mean, g->lat_var, g->arch == MSR_ARCH_SPADE ? eps : nullptr, g->latent,
                         (int64_t)n * kLatent, st))) return rc;
@@ -572,8 +571,8 @@ int forward_spade(Fwd& f, const float* source, const float* eps, float* out) {
   g->acts["latent"] = {g->latent, (int64_t)n * kLatent, 0};
   // ---- generator (networks.py:37-57)
   float* x = g->xbuf[0];
-  if ((rc = dense_f32(g->latent, g->dense_w, g->dense_b, x, n, kLatent, sw * sw * 1024, g->dense_partial,
-                      g->dense_partial_cap, st))) return rc;
+  if ((rc = dense_f32w(g->latent, g->dense_w, g->dense_b, x, n, kLatent, sw * sw * 1024, g->dense_partial,
+                       g->dense_partial_cap, st))) return rc;
   g->acts["x0"] = {x, (int64_t)n * sw * sw * 1024, 0};
   int r = sw, x_shift = 0;
   // statistics of the block input (shared by spade_1 and spade_3; invariant under nearest upsampling)
@@ -666,7 +665,7 @@ int forward_spade_bf16(Fwd& f, const float* source, const float* eps, float* out
   {
     ConvTCArgs a;
     a.x = g->patches; a.w = g->enc1_wt; a.n = n; a.r = I / 2; a.cin = 64; a.ncols = kEnc[0]; a.taps = 1; a.pad = 0;
-    a.epilogue = TC_EPI_ACT_BF16; a.act = ACT_LRELU; a.slope = 0.2f; a.out_bf16 = g->enc_b0;
+    a.epilogue = TC_EPI_ACT_BF16; a.act = ACT_LRELU; a.slope = 0.2f; a.out_bf16 = g->enc_b0; a.split_out = 1;
     if ((rc = tc_conv(f, a))) return rc;
   }
   const __nv_bfloat16* ex = g->enc_b0;
@@ -675,6 +674,7 @@ int forward_spade_bf16(Fwd& f, const float* source, const float* eps, float* out
     er /= 2;
     ConvTCArgs a;
     a.x = ex; a.w = g->enc_wt[k]; a.n = n; a.r = er; a.cin = kEnc[k - 1]; a.ncols = kEnc[k]; a.stride = 2; a.pad = 0;
+    a.split3 = 1;
     a.epilogue = TC_EPI_BIAS_F32; a.y = g->enc_y;
     if ((rc = tc_conv(f, a))) return rc;
     const int64_t rows = (int64_t)er * er;
@@ -683,20 +683,22 @@ int forward_spade_bf16(Fwd& f, const float* source, const float* eps, float* out
     __nv_bfloat16* eb = (k & 1) ? g->enc_b1 : g->enc_b0;
     if ((rc = affine_act_bf16out(g->enc_y, kEnc[k], g->enc_stats_mean, g->enc_stats_rstd, g->enc_g[k], g->enc_bt[k],
                                  k < 4 ? eb : nullptr, k == 4 ? g->enc_feat : nullptr, (int64_t)n * rows, kEnc[k], rows,
-                                 ACT_LRELU, 0.2f, st))) return rc;
+                                 ACT_LRELU, 0.2f, 1, st))) return rc;
     ex = eb;
   }
   const int feat = er * er * 512;
-  if ((rc = dense_bf16w(g->enc_feat, g->enc_head_wt, g->enc_head_b, g->lat_mv, n, feat, 2 * kLatent, g->dense_partial,
-                        g->dense_partial_cap, st))) return rc;
-  // ---- sampler (sampling.py:11-17) or mean + variance (model.py:789-791); mean | variance interleaved per row
-  if ((rc = sampler_strided_f32(g->lat_mv, 2 * kLatent, g->arch == MSR_ARCH_SPADE ? eps : nullptr, g->latent, n, kLatent,
-                                st))) return rc;
+  if ((rc = dense_f32w(g->enc_feat, g->enc_mean_w, g->enc_mean_b, g->lat_mean, n, feat, kLatent, g->dense_partial,
+                       g->dense_partial_cap, st))) return rc;
+  if ((rc = dense_f32w(g->enc_feat, g->enc_var_w, g->enc_var_b, g->lat_var, n, feat, kLatent, g->dense_partial,
+                       g->dense_partial_cap, st))) return rc;
+  // ---- sampler (sampling.py:11-17) or mean + variance (model.py:789-791)
+  if ((rc = sampler_f32(g->lat_mean, g->lat_var, g->arch == MSR_ARCH_SPADE ? eps : nullptr, g->latent,
+                        (int64_t)n * kLatent, st))) return rc;
   g->acts["latent"] = {g->latent, (int64_t)n * kLatent, 0};
   // ---- generator (networks.py:37-57)
   float* x = g->xbuf[0];
-  if ((rc = dense_bf16w(g->latent, g->dense_wt, g->dense_b, x, n, kLatent, sw * sw * 1024, g->dense_partial,
-                        g->dense_partial_cap, st))) return rc;
+  if ((rc = dense_f32w(g->latent, g->dense_w, g->dense_b, x, n, kLatent, sw * sw * 1024, g->dense_partial,
+                       g->dense_partial_cap, st))) return rc;
   g->acts["x0"] = {x, (int64_t)n * sw * sw * 1024, 0};
   int r = sw, x_shift = 0;
   if ((rc = channel_stats_f32(x, 1024, f.groups, (int64_t)g->B * sw * sw, 1024, 1e-5f, g->stat_partial, g->st_mean[0],

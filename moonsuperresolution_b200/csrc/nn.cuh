@@ -72,6 +72,9 @@ struct ConvTCArgs {
   const __nv_bfloat16* w = nullptr;  // [ncols][taps*cin] bf16 (K-major), k = tap*cin + ci
   int n = 0, r = 0, cin = 0, ncols = 0;   // r = output side
   int taps = 9;                      // 9: 3x3, 1: 1x1
+  int split3 = 0;                    // 1: split-bf16 operands (~fp32 products): x has 2*cin channels (hi | lo), w has
+                                     //    3*cin columns per tap (w_hi | w_lo | w_hi) pairing with (x_hi, x_hi, x_lo)
+  int split_out = 0;                 // TC_EPI_ACT_BF16: also write lo = bf16(v - hi) at column ncols + c (pitch 2*ncols)
   int stride = 1, pad = 1;           // input coordinate = out*stride + k - pad
   int epilogue = TC_EPI_BIAS_F32;
   const float* bias = nullptr;       // [ncols]
@@ -105,11 +108,14 @@ int source_patches_bf16(const float* source, int I, __nv_bfloat16* out, int n, i
 // out.  `partial` scratch of ksplit * M * N floats.
 int dense_bf16w(const float* x, const __nv_bfloat16* w, const float* bias, float* out, int M, int K, int N,
                 float* partial, int64_t partial_capacity, cudaStream_t st);
+int dense_f32w(const float* x, const float* w, const float* bias, float* out, int M, int K, int N, float* partial,
+               int64_t partial_capacity, cudaStream_t st);
 
 // (x - mean) * rstd * gamma + beta -> activation -> bf16 (and / or fp32) output; same conventions as affine_act_f32.
 int affine_act_bf16out(const float* x, int ldx, const float* mean, const float* rstd, const float* gamma,
                        const float* beta, __nv_bfloat16* y_bf16, float* y_f32, int64_t M, int C, int64_t rows_per_group,
-                       int act, float slope, cudaStream_t st);
+                       int act, float slope, int split, cudaStream_t st);
+// split = 1: y_bf16 has row pitch 2C and receives hi = bf16(v) at [0, C) and lo = bf16(v - hi) at [C, 2C)
 
 // statistics from the fused (sum, sumsq) pairs written by the tensor-core epilogue: pairs [groups*rows_p][C]
 int channel_stats_from_pairs(const float2* pairs, int groups, int64_t rows_p, int64_t count_per_group, int C, float eps,

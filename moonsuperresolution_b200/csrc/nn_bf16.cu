@@ -18,9 +18,11 @@ __global__ void __launch_bounds__(256) source_patches_kernel(const float* __rest
     const int nn = (int)(m / ((int64_t)r * r));
     const int rem = (int)(m % ((int64_t)r * r));
     const int h = rem / r, x = rem % r;
+    // split-bf16 operand: channels [0,18) = hi, [18,36) = hi again, [36,54) = lo (v = hi + lo to ~2^-17); the matching
+    // weight rows are [w_hi | w_lo | w_hi], so the GEMM evaluates a_hi*w_hi + a_hi*w_lo + a_lo*w_hi ~ fp32 product
     __align__(16) __nv_bfloat16 row[64];
 #pragma unroll
-    for (int j = 18; j < 64; ++j) row[j] = __float2bfloat16_rn(0.f);
+    for (int j = 54; j < 64; ++j) row[j] = __float2bfloat16_rn(0.f);
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
@@ -34,8 +36,14 @@ __global__ void __launch_bounds__(256) source_patches_kernel(const float* __rest
           const int sy = 2 * h + ky, sx = 2 * x + kx;
           if (sy < I && sx < I) s = __ldg(reinterpret_cast<const float2*>(src + (((int64_t)nn * I + sy) * I + sx) * 2));
         }
-        row[(ky * 3 + kx) * 2 + 0] = __float2bfloat16_rn(s.x);
-        row[(ky * 3 + kx) * 2 + 1] = __float2bfloat16_rn(s.y);
+        const int j = (ky * 3 + kx) * 2;
+        const __nv_bfloat16 hx = __float2bfloat16_rn(s.x), hy = __float2bfloat16_rn(s.y);
+        row[j] = hx;
+        row[j + 1] = hy;
+        row[18 + j] = hx;
+        row[18 + j + 1] = hy;
+        row[36 + j] = __float2bfloat16_rn(s.x - __bfloat162float(hx));
+        row[36 + j + 1] = __float2bfloat16_rn(s.y - __bfloat162float(hy));
       }
     }
     uint4* dst = reinterpret_cast<uint4*>(out + m * 64);
@@ -64,10 +72,17 @@ int source_patches_bf16(const float* source, int I, __nv_bfloat16* out, int n, i
 constexpr int kDM = 16;    // rows per pass
 constexpr int kDKT = 32;   // k rows staged per iteration
 
-__global__ void __launch_bounds__(128) dense_bf16w_partial_kernel(const float* __restrict__ x,
-                                                                  const __nv_bfloat16* __restrict__ w,
-                                                                  float* __restrict__ partial, int M, int K, int N,
-                                                                  int kchunk, int m0) {
+__device__ __forceinline__ float4 load_w4(const __nv_bfloat16* p) {
+  const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+  return make_float4(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u), __uint_as_float(v.y << 16),
+                     __uint_as_float(v.y & 0xffff0000u));
+}
+__device__ __forceinline__ float4 load_w4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+template <typename WT>
+__global__ void __launch_bounds__(128) dense_partial_kernel(const float* __restrict__ x, const WT* __restrict__ w,
+                                                            float* __restrict__ partial, int M, int K, int N,
+                                                            int kchunk, int m0) {
   __shared__ float xs[kDM][kDKT + 4];
   const int n4 = (blockIdx.x * 128 + threadIdx.x) * 4;
   const int split = blockIdx.y;
@@ -84,22 +99,22 @@ __global__ void __launch_bounds__(128) dense_bf16w_partial_kernel(const float* _
     }
     __syncthreads();
     if (n4 < N) {
-      uint2 wv[kDKT];
 #pragma unroll
-      for (int kk = 0; kk < kDKT; ++kk)
-        wv[kk] = (kb + kk < k1) ? __ldg(reinterpret_cast<const uint2*>(w + (int64_t)(kb + kk) * N + n4))
-                                : make_uint2(0u, 0u);
+      for (int kq = 0; kq < kDKT; kq += 8) {
+        float4 wv[8];
 #pragma unroll
-      for (int kk = 0; kk < kDKT; ++kk) {
-        const float w0 = __uint_as_float(wv[kk].x << 16), w1 = __uint_as_float(wv[kk].x & 0xffff0000u);
-        const float w2 = __uint_as_float(wv[kk].y << 16), w3 = __uint_as_float(wv[kk].y & 0xffff0000u);
+        for (int kk = 0; kk < 8; ++kk)
+          wv[kk] = (kb + kq + kk < k1) ? load_w4(w + (int64_t)(kb + kq + kk) * N + n4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int i = 0; i < kDM; ++i) {
-          const float xv = xs[i][kk];
-          acc[i][0] = fmaf(xv, w0, acc[i][0]);
-          acc[i][1] = fmaf(xv, w1, acc[i][1]);
-          acc[i][2] = fmaf(xv, w2, acc[i][2]);
-          acc[i][3] = fmaf(xv, w3, acc[i][3]);
+        for (int kk = 0; kk < 8; ++kk) {
+#pragma unroll
+          for (int i = 0; i < kDM; ++i) {
+            const float xv = xs[i][kq + kk];
+            acc[i][0] = fmaf(xv, wv[kk].x, acc[i][0]);
+            acc[i][1] = fmaf(xv, wv[kk].y, acc[i][1]);
+            acc[i][2] = fmaf(xv, wv[kk].z, acc[i][2]);
+            acc[i][3] = fmaf(xv, wv[kk].w, acc[i][3]);
+          }
         }
       }
     }
@@ -123,19 +138,20 @@ __global__ void dense_bf16w_reduce_kernel(const float* __restrict__ partial, con
   out[e] = s;
 }
 
-int dense_bf16w(const float* x, const __nv_bfloat16* w, const float* bias, float* out, int M, int K, int N,
-                float* partial, int64_t partial_capacity, cudaStream_t st) {
-  MSR_REQUIRE(x && w && out && partial && M > 0 && K > 0 && N > 0 && N % 4 == 0, "dense_bf16w: bad arguments");
+template <typename WT>
+static int dense_small_m(const float* x, const WT* w, const float* bias, float* out, int M, int K, int N,
+                         float* partial, int64_t partial_capacity, cudaStream_t st) {
+  MSR_REQUIRE(x && w && out && partial && M > 0 && K > 0 && N > 0 && N % 4 == 0, "dense: bad arguments");
   ProfileScope prof(MSR_PROF_DENSE, st, 2.0 * M * (double)K * N, 2);
   const int gx = ceil_div(N, 512);
   int ksplit = std::max(1, std::min(ceil_div(K, kDKT), (2 * 148) / gx));
   while ((int64_t)ksplit * M * N > partial_capacity && ksplit > 1) --ksplit;
-  MSR_REQUIRE((int64_t)ksplit * M * N <= partial_capacity, "dense_bf16w: partial scratch too small");
+  MSR_REQUIRE((int64_t)ksplit * M * N <= partial_capacity, "dense: partial scratch too small");
   int kchunk = ceil_div(K, ksplit);
   kchunk = ceil_div(kchunk, kDKT) * kDKT;
   ksplit = ceil_div(K, kchunk);
   for (int m0 = 0; m0 < M; m0 += kDM) {
-    dense_bf16w_partial_kernel<<<dim3(gx, ksplit), 128, 0, st>>>(x, w, partial, M, K, N, kchunk, m0);
+    dense_partial_kernel<WT><<<dim3(gx, ksplit), 128, 0, st>>>(x, w, partial, M, K, N, kchunk, m0);
     MSR_LAUNCH_CHECK();
     count_launch();
   }
@@ -143,6 +159,15 @@ int dense_bf16w(const float* x, const __nv_bfloat16* w, const float* bias, float
   MSR_LAUNCH_CHECK();
   count_launch();
   return MSR_OK;
+}
+
+int dense_bf16w(const float* x, const __nv_bfloat16* w, const float* bias, float* out, int M, int K, int N,
+                float* partial, int64_t partial_capacity, cudaStream_t st) {
+  return dense_small_m<__nv_bfloat16>(x, w, bias, out, M, K, N, partial, partial_capacity, st);
+}
+int dense_f32w(const float* x, const float* w, const float* bias, float* out, int M, int K, int N, float* partial,
+               int64_t partial_capacity, cudaStream_t st) {
+  return dense_small_m<float>(x, w, bias, out, M, K, N, partial, partial_capacity, st);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -155,7 +180,7 @@ __global__ void __launch_bounds__(256) affine_act_bf16_kernel(const float* __res
                                                               const float* __restrict__ beta,
                                                               __nv_bfloat16* __restrict__ yb, float* __restrict__ yf,
                                                               int64_t M, int C, int64_t rows_per_group, int act,
-                                                              float slope) {
+                                                              float slope, int split) {
   const int c4n = C / 4;
   const int64_t total = M * c4n;
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
@@ -186,21 +211,29 @@ __global__ void __launch_bounds__(256) affine_act_bf16_kernel(const float* __res
     if (yb) {
       __align__(8) __nv_bfloat16 o[4] = {__float2bfloat16_rn(v[0]), __float2bfloat16_rn(v[1]),
                                           __float2bfloat16_rn(v[2]), __float2bfloat16_rn(v[3])};
-      *reinterpret_cast<uint2*>(yb + m * C + c) = *reinterpret_cast<const uint2*>(o);
+      if (!split) {
+        *reinterpret_cast<uint2*>(yb + m * C + c) = *reinterpret_cast<const uint2*>(o);
+      } else {  // hi | lo halves of a split-bf16 operand, row pitch 2C
+        __align__(8) __nv_bfloat16 l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) l[j] = __float2bfloat16_rn(v[j] - __bfloat162float(o[j]));
+        *reinterpret_cast<uint2*>(yb + m * 2 * C + c) = *reinterpret_cast<const uint2*>(o);
+        *reinterpret_cast<uint2*>(yb + m * 2 * C + C + c) = *reinterpret_cast<const uint2*>(l);
+      }
     }
   }
 }
 
 int affine_act_bf16out(const float* x, int ldx, const float* mean, const float* rstd, const float* gamma,
                        const float* beta, __nv_bfloat16* y_bf16, float* y_f32, int64_t M, int C, int64_t rows_per_group,
-                       int act, float slope, cudaStream_t st) {
+                       int act, float slope, int split, cudaStream_t st) {
   MSR_REQUIRE(x && (y_bf16 || y_f32) && M > 0 && C > 0 && C % 4 == 0 && ldx % 4 == 0 && rows_per_group > 0,
               "affine_act_bf16out: bad arguments");
   ProfileScope prof(MSR_PROF_ELEMWISE, st, (double)M * C * (4.0 + (y_bf16 ? 2.0 : 0.0) + (y_f32 ? 4.0 : 0.0)));
   const int64_t total = M * (C / 4);
   const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 16);
   affine_act_bf16_kernel<<<blocks, 256, 0, st>>>(x, ldx, mean, rstd, gamma, beta, y_bf16, y_f32, M, C, rows_per_group,
-                                                 act, slope);
+                                                 act, slope, split);
   count_launch();
   MSR_LAUNCH_CHECK();
   return MSR_OK;

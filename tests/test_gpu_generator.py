@@ -147,10 +147,13 @@ def test_spade_generator_fp32_mode(msr, arch, i, b):
 def test_spade_generator_bf16_tensor_core_mode(msr, arch, i, b):
     w = W.random_init(arch, i, seed=12, perturb_affine=True)
     x, eps = inputs(i, b, seed=1)
-    want = OG.gaugan_call(x, w, eps, arch)
+    want, want_latent = OG.gaugan_call(x, w, eps, arch, return_latent=True)
     cls = msr.GauGAN if arch == "spade" else msr.CNNSpade
     model = cls(i, b, precision="bf16", weights=w)
     got = model(x, training=False, eps=eps)
+    # the encoder runs with split-bf16 operands (~fp32 products): the latent must be far inside the bf16 tolerance
+    lat = model.read_activation("latent").reshape(b, 256)
+    assert np.abs(lat - want_latent).max() < 1e-3 * max(1.0, np.abs(want_latent).max())
     err = np.abs(got - want).max()
     assert err <= TOL_BF16 * max(1.0, np.abs(want).max()), err
 
