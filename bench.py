@@ -49,7 +49,7 @@ def parse():
     ap.add_argument("--tile-size", type=int, default=1024)
     ap.add_argument("--rows-per-gpu", type=int, default=8192)
     ap.add_argument("--cols", type=int, default=8192)
-    ap.add_argument("--groups", type=int, default=1, help="batches per generator call")
+    ap.add_argument("--groups", type=int, default=8, help="batches per generator call")
     ap.add_argument("--e2e-steps", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

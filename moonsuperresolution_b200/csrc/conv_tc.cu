@@ -16,6 +16,7 @@
 //     take alternate 32-column chunks), 8 TMA producer, 9 MMA issuer.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <mutex>
 
 #include "nn.cuh"
@@ -30,11 +31,13 @@ constexpr int kABytes = kBlockM * kBlockK * 2;    // 16 KB
 constexpr int kEpiWarps = 8;                      // two per TMEM lane quarter: they split the accumulator columns
 constexpr int kThreads = (kEpiWarps + 2) * 32;   // + TMA producer warp + MMA issuer warp
 
-template <int BN>
+// CTAS = 2: a CTA pair (cluster of 2, cta_group::2) computes a 256 x BN tile; each CTA stages its own 128 rows of A and
+// only HALF of the B tile, which cuts the L2 -> shared-memory traffic per FLOP (the measured limiter) by a third.
+template <int BN, int CTAS = 1>
 struct Cfg {
-  static constexpr int kBBytes = BN * kBlockK * 2;
+  static constexpr int kBBytes = (BN / CTAS) * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kStages = (kStageBytes >= 48 * 1024) ? 4 : (kStageBytes >= 32 * 1024 ? 6 : 8);
   static constexpr int kTmemCols = 2 * BN;        // two accumulator buffers (power of two >= 32)
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
@@ -136,6 +139,61 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 
+// ---- CTA-pair (cta_group::2) variants -----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t cta) {  // same variable in CTA `cta` of the cluster
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA loads of a CTA pair: the bytes land in the executing CTA's shared memory, the transaction count is reported to
+// the mbarrier at `bar` (a shared::cluster address -- the leader CTA's barrier)
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                                 int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at this shared-memory offset in BOTH CTAs of the pair once the issued MMAs have completed
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -182,16 +240,21 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   return d;
 }
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=BN
-__host__ __device__ constexpr uint32_t make_idesc(int bn) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc(int bn, int m = kBlockM) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 // ---- the kernel -------------------------------------------------------------------------------------------------------
-template <int BN>
+template <int BN, int CTAS>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                   const Geometry g, const EpiParams ep) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, CTAS>;
+  const uint32_t cta_rank = (CTAS == 2) ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  // work unit: a 128 x BN tile (CTAS == 1) or a 256 x BN tile shared by the pair (CTAS == 2)
+  const int unit = (CTAS == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int n_units = (CTAS == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128-byte swizzle atoms
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -204,7 +267,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + C::kStages * C::kStageBytes + 8 * (2 * C::kStages + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_tiles = g.n_tiles_m * g.n_tiles_n;
+  const int total_tiles = (g.n_tiles_m / CTAS) * g.n_tiles_n;
   const int chunks_per_part = g.cin / kBlockK;
   const int k_chunks_per_tap = (g.split ? 3 : 1) * chunks_per_part;
   const int k_chunks = g.taps * k_chunks_per_tap;
@@ -216,7 +279,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), kEpiWarps);  // one arrive per epilogue warp
+      mbar_init(tempty_bar(a), kEpiWarps * CTAS);  // one arrive per epilogue warp (of both CTAs of a pair)
     }
     fence_barrier_init();
   }
@@ -224,14 +287,18 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
   }
-  if (warp == kEpiWarps + 1) tmem_alloc(smem_u32((const void*)tmem_slot), C::kTmemCols);
+  if (warp == kEpiWarps + 1) {
+    if constexpr (CTAS == 2) tmem_alloc_pair(smem_u32((const void*)tmem_slot), C::kTmemCols);
+    else tmem_alloc(smem_u32((const void*)tmem_slot), C::kTmemCols);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CTAS == 2) cluster_sync_all();   // the peer's barriers must be initialised before any remote arrive
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   auto decode_tile = [&](int tile, int& b0, int& h0, int& w0, int& n0) {
-    const int mt = tile / g.n_tiles_n, nt = tile % g.n_tiles_n;
+    const int mt = (tile / g.n_tiles_n) * CTAS + (int)cta_rank, nt = tile % g.n_tiles_n;
     const int tw = mt % g.tiles_w, th = (mt / g.tiles_w) % g.tiles_h, tb = mt / (g.tiles_w * g.tiles_h);
     b0 = tb * g.NB;
     h0 = th * g.TH;
@@ -244,7 +311,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = unit; tile < total_tiles; tile += n_units) {
         int b0, h0, w0, n0;
         decode_tile(tile, b0, h0, w0, n0);
         for (int kc = 0; kc < k_chunks; ++kc) {
@@ -253,12 +320,21 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * C::kStageBytes;
           const uint32_t sb = sa + kABytes;
-          mbar_expect_tx(full_bar(stage), C::kStageBytes);
           // split-bf16: parts (x_hi, x_hi, x_lo) of A pair with (w_hi, w_lo, w_hi) of B
           const int a_chan = g.split ? ((cb / chunks_per_part == 2) ? g.cin : 0) + (cb % chunks_per_part) * kBlockK
                                      : cb * kBlockK;
-          tma_load_4d(sa, &map_a, full_bar(stage), a_chan, w0 * g.stride + kx - g.pad, h0 * g.stride + ky - g.pad, b0);
-          tma_load_2d(sb, &map_b, full_bar(stage), (tap * k_chunks_per_tap + cb) * kBlockK, n0);
+          if constexpr (CTAS == 2) {
+            // both CTAs report their bytes to the leader's barrier; each loads its own A rows and its half of B
+            if (leader) mbar_expect_tx(full_bar(stage), 2 * C::kStageBytes);
+            const uint32_t lead_bar = mapa_shared(full_bar(stage), 0);
+            tma_load_4d_pair(sa, &map_a, lead_bar, a_chan, w0 * g.stride + kx - g.pad, h0 * g.stride + ky - g.pad, b0);
+            tma_load_2d_pair(sb, &map_b, lead_bar, (tap * k_chunks_per_tap + cb) * kBlockK,
+                             n0 + (int)cta_rank * (BN / 2));
+          } else {
+            mbar_expect_tx(full_bar(stage), C::kStageBytes);
+            tma_load_4d(sa, &map_a, full_bar(stage), a_chan, w0 * g.stride + kx - g.pad, h0 * g.stride + ky - g.pad, b0);
+            tma_load_2d(sb, &map_b, full_bar(stage), (tap * k_chunks_per_tap + cb) * kBlockK, n0);
+          }
           if (++stage == C::kStages) {
             stage = 0;
             phase ^= 1u;
@@ -268,13 +344,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     }
   } else if (warp == kEpiWarps + 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BN);
+    if (lane == 0 && leader) {   // in a pair only the leader CTA issues (for both)
+      constexpr uint32_t idesc = make_idesc(BN, kBlockM * CTAS);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = unit; tile < total_tiles; tile += n_units) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -287,15 +363,22 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
             // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in 16-byte units
-            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kc | k) != 0 ? 1u : 0u);
+            if constexpr (CTAS == 2)
+              umma_bf16_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kc | k) != 0 ? 1u : 0u);
+            else
+              umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kc | k) != 0 ? 1u : 0u);
           }
-          umma_commit(empty_bar(stage));  // frees the smem stage when these MMAs retire
+          // frees the smem stage (in both CTAs of a pair) when these MMAs retire
+          if constexpr (CTAS == 2) umma_commit_pair(empty_bar(stage));
+          else umma_commit(empty_bar(stage));
           if (++stage == C::kStages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit(tfull_bar(acc));       // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs)
+        if constexpr (CTAS == 2) umma_commit_pair(tfull_bar(acc));
+        else umma_commit(tfull_bar(acc));
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
@@ -308,7 +391,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int quarter = warp & 3, csel = warp >> 2;
     const int row = quarter * 32 + lane;  // tile row == TMEM lane
     const int wi = row % g.TW, hi = (row / g.TW) % g.TH, bi = row / (g.TW * g.TH);
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = unit; tile < total_tiles; tile += n_units) {
       int b0, h0, w0, n0;
       decode_tile(tile, b0, h0, w0, n0);
       const int b = b0 + bi, h = h0 + hi, w = w0 + wi;
@@ -323,7 +406,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           const int rs = g.r >> ep.res_shift;
           res_row = ((int64_t)b * rs + (h >> ep.res_shift)) * rs + (w >> ep.res_shift);
         }
-        const int mt = tile / g.n_tiles_n;
+        const int mt = (tile / g.n_tiles_n) * CTAS + (int)cta_rank;
 #pragma unroll 1
         for (int c0 = csel * 32; c0 < BN; c0 += 64) {
           uint32_t v[32];
@@ -500,17 +583,22 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       // release the accumulator buffer
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        if constexpr (CTAS == 2) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));   // the leader's MMA warp waits
+        else mbar_arrive(tempty_bar(acc));
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CTAS == 2) cluster_sync_all();   // no CTA of the pair may exit while its peer can still signal it
+  else __syncthreads();
   if (warp == kEpiWarps + 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::kTmemCols);
+    if constexpr (CTAS == 2) tmem_dealloc_pair(tmem_base, C::kTmemCols);
+    else tmem_dealloc(tmem_base, C::kTmemCols);
   }
 }
 
@@ -534,11 +622,18 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+// MSR_TC_PAIRS=0 in the environment forces single-CTA tiles (A/B comparison of the two schedules)
+static const bool g_disable_pairs = [] {
+  const char* e = getenv("MSR_TC_PAIRS");
+  return e != nullptr && e[0] == '0';
+}();
+
 struct ConvTC {
   CUtensorMap map_a, map_b;
   tc::Geometry g;
   tc::EpiParams ep;
   int bn;
+  int ctas;   // 1, or 2 = CTA pairs (cluster launch)
   int grid;
 };
 
@@ -567,6 +662,8 @@ int conv_tc_plan_create(ConvTC** out, const ConvTCArgs& a) {
   p->bn = (a.ncols % 256 == 0) ? 256 : (a.ncols % 128 == 0) ? 128 : (a.ncols % 64 == 0) ? 64 : 32;
   if (a.epilogue == TC_EPI_PHASE_F32) p->bn = 32;
   g.n_tiles_n = a.ncols / p->bn;
+  // CTA pairs when the layer is large enough to fill the chip with 256-row tiles
+  p->ctas = (p->bn >= 128 && g.n_tiles_m % 2 == 0 && (g.n_tiles_m / 2) * g.n_tiles_n >= 74 && !g_disable_pairs) ? 2 : 1;
   const int rin = a.r * a.stride;
 
   // A: 4-D NHWC tensor {C, W, H, N}; a stride-2 convolution walks W and H with element stride 2
@@ -590,7 +687,7 @@ int conv_tc_plan_create(ConvTC** out, const ConvTCArgs& a) {
     const cuuint64_t kb = (cuuint64_t)a.taps * a.cin * (a.split3 ? 3 : 1);
     cuuint64_t dims[2] = {kb, (cuuint64_t)a.ncols};
     cuuint64_t strides[1] = {kb * 2};
-    cuuint32_t box[2] = {(cuuint32_t)tc::kBlockK, (cuuint32_t)p->bn};
+    cuuint32_t box[2] = {(cuuint32_t)tc::kBlockK, (cuuint32_t)(p->bn / p->ctas)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(&p->map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(a.w), dims, strides, box,
                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -627,18 +724,23 @@ int conv_tc_plan_create(ConvTC** out, const ConvTCArgs& a) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  p->grid = std::min(g.n_tiles_m * g.n_tiles_n, sms);
+  if (p->ctas == 2) p->grid = 2 * std::min((g.n_tiles_m / 2) * g.n_tiles_n, sms / 2);
+  else p->grid = std::min(g.n_tiles_m * g.n_tiles_n, sms);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e1 = cudaFuncSetAttribute(tc::conv3x3_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          tc::Cfg<128>::kSmemBytes);
-    cudaError_t e2 = cudaFuncSetAttribute(tc::conv3x3_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          tc::Cfg<256>::kSmemBytes);
-    cudaError_t e3 = cudaFuncSetAttribute(tc::conv3x3_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          tc::Cfg<64>::kSmemBytes);
-    cudaError_t e4 = cudaFuncSetAttribute(tc::conv3x3_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          tc::Cfg<32>::kSmemBytes);
-    for (cudaError_t ee : {e1, e2, e3, e4})
+    cudaError_t e1 = cudaFuncSetAttribute(tc::conv3x3_tc_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          tc::Cfg<128, 1>::kSmemBytes);
+    cudaError_t e2 = cudaFuncSetAttribute(tc::conv3x3_tc_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          tc::Cfg<256, 1>::kSmemBytes);
+    cudaError_t e3 = cudaFuncSetAttribute(tc::conv3x3_tc_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          tc::Cfg<64, 1>::kSmemBytes);
+    cudaError_t e4 = cudaFuncSetAttribute(tc::conv3x3_tc_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          tc::Cfg<32, 1>::kSmemBytes);
+    cudaError_t e5 = cudaFuncSetAttribute(tc::conv3x3_tc_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          tc::Cfg<128, 2>::kSmemBytes);
+    cudaError_t e6 = cudaFuncSetAttribute(tc::conv3x3_tc_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          tc::Cfg<256, 2>::kSmemBytes);
+    for (cudaError_t ee : {e1, e2, e3, e4, e5, e6})
       if (ee != cudaSuccess) {
         delete p;
         return fail(MSR_E_CUDA, std::string("conv_tc: cudaFuncSetAttribute: ") + cudaGetErrorString(ee));
@@ -652,18 +754,39 @@ int conv_tc_plan_create(ConvTC** out, const ConvTCArgs& a) {
 int conv_tc_launch(const ConvTC* p, cudaStream_t st) {
   MSR_REQUIRE(p, "conv_tc_launch: null plan");
   ProfileScope prof(MSR_PROF_CONV_TC, st, 2.0 * (double)p->g.n * p->g.r * p->g.r * p->g.ncols * p->g.taps * p->g.cin);
-  switch (p->bn) {
-    case 256:
-      tc::conv3x3_tc_kernel<256><<<p->grid, tc::kThreads, tc::Cfg<256>::kSmemBytes, st>>>(p->map_a, p->map_b, p->g, p->ep);
-      break;
-    case 128:
-      tc::conv3x3_tc_kernel<128><<<p->grid, tc::kThreads, tc::Cfg<128>::kSmemBytes, st>>>(p->map_a, p->map_b, p->g, p->ep);
-      break;
-    case 64:
-      tc::conv3x3_tc_kernel<64><<<p->grid, tc::kThreads, tc::Cfg<64>::kSmemBytes, st>>>(p->map_a, p->map_b, p->g, p->ep);
-      break;
-    default:
-      tc::conv3x3_tc_kernel<32><<<p->grid, tc::kThreads, tc::Cfg<32>::kSmemBytes, st>>>(p->map_a, p->map_b, p->g, p->ep);
+  if (p->ctas == 2) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(p->grid);
+    cfg.blockDim = dim3(tc::kThreads);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (p->bn == 256) {
+      cfg.dynamicSmemBytes = tc::Cfg<256, 2>::kSmemBytes;
+      MSR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc::conv3x3_tc_kernel<256, 2>, p->map_a, p->map_b, p->g, p->ep));
+    } else {
+      cfg.dynamicSmemBytes = tc::Cfg<128, 2>::kSmemBytes;
+      MSR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc::conv3x3_tc_kernel<128, 2>, p->map_a, p->map_b, p->g, p->ep));
+    }
+  } else {
+    switch (p->bn) {
+      case 256:
+        tc::conv3x3_tc_kernel<256, 1><<<p->grid, tc::kThreads, tc::Cfg<256, 1>::kSmemBytes, st>>>(p->map_a, p->map_b, p->g, p->ep);
+        break;
+      case 128:
+        tc::conv3x3_tc_kernel<128, 1><<<p->grid, tc::kThreads, tc::Cfg<128, 1>::kSmemBytes, st>>>(p->map_a, p->map_b, p->g, p->ep);
+        break;
+      case 64:
+        tc::conv3x3_tc_kernel<64, 1><<<p->grid, tc::kThreads, tc::Cfg<64, 1>::kSmemBytes, st>>>(p->map_a, p->map_b, p->g, p->ep);
+        break;
+      default:
+        tc::conv3x3_tc_kernel<32, 1><<<p->grid, tc::kThreads, tc::Cfg<32, 1>::kSmemBytes, st>>>(p->map_a, p->map_b, p->g, p->ep);
+    }
   }
   count_launch();
   MSR_LAUNCH_CHECK();

@@ -84,11 +84,10 @@ struct msr_generator {
   const float* enc_mean_w = nullptr; const float* enc_mean_b = nullptr;
   const float* enc_var_w = nullptr; const float* enc_var_b = nullptr;
   // bf16 mode extras
-  const __nv_bfloat16* dense_wt = nullptr;       // [256][sw*sw*1024]
   const __nv_bfloat16* out_wt = nullptr;         // [32][9*128] sub-pixel phase weights of the final 4x4 conv
   const __nv_bfloat16* enc1_wt = nullptr;        // [64][64] im2col weights of encoder block 1
   const __nv_bfloat16* enc_wt[5] = {};           // [cout][9*cin] for blocks 2..5
-  const __nv_bfloat16* enc_head_wt = nullptr;    // [feat][512] = mean | variance
+  const float* enc_head_w = nullptr;             // [feat][512] = mean | variance
   const float* enc_head_b = nullptr;             // [512]
   __nv_bfloat16* patches = nullptr;              // im2col'd source [n][r][r][64]
   __nv_bfloat16* enc_b0 = nullptr; __nv_bfloat16* enc_b1 = nullptr; float* enc_y = nullptr; float* enc_feat = nullptr;
@@ -315,13 +314,31 @@ int finalize_spade_bf16_extras(msr_generator* g) {
         }
     if ((rc = upload_bf16(g, w, &g->enc_wt[k]))) return rc;
   }
+  {  // encoder heads merged into one weight-bandwidth-bound pass: [feat][512] = mean | variance (fp32 weights)
+    const int64_t feat = (int64_t)(I / 32) * (I / 32) * 512;
+    const HostTensor *wm, *wv, *bm, *bv;
+    if ((rc = need(g, "enc.mean.kernel", {feat, kLatent}, &wm))) return rc;
+    if ((rc = need(g, "enc.variance.kernel", {feat, kLatent}, &wv))) return rc;
+    if ((rc = need(g, "enc.mean.bias", {kLatent}, &bm))) return rc;
+    if ((rc = need(g, "enc.variance.bias", {kLatent}, &bv))) return rc;
+    std::vector<float> w((size_t)feat * 2 * kLatent), b(2 * kLatent);
+    for (int64_t f = 0; f < feat; ++f) {
+      memcpy(&w[(size_t)f * 2 * kLatent], &wm->data[(size_t)f * kLatent], sizeof(float) * kLatent);
+      memcpy(&w[(size_t)f * 2 * kLatent + kLatent], &wv->data[(size_t)f * kLatent], sizeof(float) * kLatent);
+    }
+    memcpy(&b[0], bm->data.data(), sizeof(float) * kLatent);
+    memcpy(&b[kLatent], bv->data.data(), sizeof(float) * kLatent);
+    if ((rc = upload(g, w, &g->enc_head_w))) return rc;
+    if ((rc = upload(g, b, &g->enc_head_b))) return rc;
+  }
+  if ((rc = ws(g, &g->lat_mv, N * 2 * kLatent))) return rc;
   if ((rc = ws(g, &g->patches, N * half * 64))) return rc;
   if ((rc = ws(g, &g->enc_b0, N * half * 128))) return rc;          // hi | lo halves
   if ((rc = ws(g, &g->enc_b1, N * (half / 4) * 256))) return rc;
   if ((rc = ws(g, &g->enc_y, N * (half / 4) * 128))) return rc;
   if ((rc = ws(g, &g->enc_feat, N * (int64_t)(I / 32) * (I / 32) * 512))) return rc;
   if ((rc = ws(g, &g->stat_pairs, 4 * N * half))) return rc;
-  const int64_t need_partial = std::max<int64_t>(296 * N * kLatent, 4 * N * 16 * sw * sw * 64);
+  const int64_t need_partial = std::max<int64_t>(296 * N * 2 * kLatent, 4 * N * 16 * sw * sw * 64);
   if (need_partial > g->dense_partial_cap) {
     g->dense_partial_cap = need_partial;
     if ((rc = ws(g, &g->dense_partial, need_partial))) return rc;
@@ -368,10 +385,12 @@ int finalize_spade(msr_generator* g) {
     ec = kEnc[k];
   }
   const int64_t feat = (int64_t)(I / 32) * (I / 32) * 512;
-  if ((rc = upload_named(g, "enc.mean.kernel", {feat, kLatent}, &g->enc_mean_w))) return rc;
-  if ((rc = upload_named(g, "enc.mean.bias", {kLatent}, &g->enc_mean_b))) return rc;
-  if ((rc = upload_named(g, "enc.variance.kernel", {feat, kLatent}, &g->enc_var_w))) return rc;
-  if ((rc = upload_named(g, "enc.variance.bias", {kLatent}, &g->enc_var_b))) return rc;
+  if (fp32) {
+    if ((rc = upload_named(g, "enc.mean.kernel", {feat, kLatent}, &g->enc_mean_w))) return rc;
+    if ((rc = upload_named(g, "enc.mean.bias", {kLatent}, &g->enc_mean_b))) return rc;
+    if ((rc = upload_named(g, "enc.variance.kernel", {feat, kLatent}, &g->enc_var_w))) return rc;
+    if ((rc = upload_named(g, "enc.variance.bias", {kLatent}, &g->enc_var_b))) return rc;
+  }
 
   // ---- workspace
   const int64_t half = (int64_t)(I / 2) * (I / 2);
@@ -687,13 +706,11 @@ int forward_spade_bf16(Fwd& f, const float* source, const float* eps, float* out
     ex = eb;
   }
   const int feat = er * er * 512;
-  if ((rc = dense_f32w(g->enc_feat, g->enc_mean_w, g->enc_mean_b, g->lat_mean, n, feat, kLatent, g->dense_partial,
+  if ((rc = dense_f32w(g->enc_feat, g->enc_head_w, g->enc_head_b, g->lat_mv, n, feat, 2 * kLatent, g->dense_partial,
                        g->dense_partial_cap, st))) return rc;
-  if ((rc = dense_f32w(g->enc_feat, g->enc_var_w, g->enc_var_b, g->lat_var, n, feat, kLatent, g->dense_partial,
-                       g->dense_partial_cap, st))) return rc;
-  // ---- sampler (sampling.py:11-17) or mean + variance (model.py:789-791)
-  if ((rc = sampler_f32(g->lat_mean, g->lat_var, g->arch == MSR_ARCH_SPADE ? eps : nullptr, g->latent,
-                        (int64_t)n * kLatent, st))) return rc;
+  // ---- sampler (sampling.py:11-17) or mean + variance (model.py:789-791); rows hold mean | variance
+  if ((rc = sampler_strided_f32(g->lat_mv, 2 * kLatent, g->arch == MSR_ARCH_SPADE ? eps : nullptr, g->latent, n, kLatent,
+                                st))) return rc;
   g->acts["latent"] = {g->latent, (int64_t)n * kLatent, 0};
   // ---- generator (networks.py:37-57)
   float* x = g->xbuf[0];

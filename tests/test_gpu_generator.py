@@ -31,7 +31,8 @@ def bf16_round(a, torch):
 
 
 @pytest.mark.parametrize("n,r,cin,cout", [(1, 8, 64, 128), (2, 16, 128, 256), (3, 4, 128, 128), (1, 32, 256, 384),
-                                           (5, 2, 64, 128), (1, 128, 64, 128), (2, 1, 128, 256)])
+                                           (5, 2, 64, 128), (1, 128, 64, 128), (2, 1, 128, 256),
+                                           (2, 128, 64, 256), (8, 64, 64, 128), (3, 128, 64, 512)])   # CTA-pair schedule
 def test_conv3x3_tensor_core_operator(torch, n, r, cin, cout):
     """tcgen05 implicit GEMM vs torch fp32 convolution on bf16-rounded operands."""
     from moonsuperresolution_b200 import _lib
