@@ -168,6 +168,12 @@ int msr_op_conv_tc(const uint16_t* d_x, const uint16_t* d_w, const float* d_bias
                    int n, int r_out, int cin, int cout, int taps, int stride, int pad, int act, float slope,
                    float* d_stat_pairs, void* stream);
 
+/* Optimisation aid: when d_counters != NULL (148 * 8 int64, zero-initialised by the caller), every tensor-core convolution
+ * planned afterwards records per-CTA cycle counts: [0] producer wait on empty stages, [1] producer total, [2] MMA issuer
+ * wait on full stages, [3] MMA issuer wait on free accumulators, [4] MMA issuer total, [5] epilogue wait on accumulators.
+ * Pass NULL to switch off. */
+int msr_debug_tc_counters(long long* d_counters);
+
 /* Same operator on CUDA cores in float32 (the fp32-mode kernel); d_w (3, 3, cin, cout) Keras layout. */
 int msr_op_conv3x3_f32(const float* d_x, const float* d_w, const float* d_bias, float* d_y, int n, int r, int cin,
                        int cout, void* stream);

@@ -126,6 +126,12 @@ extern "C" int msr_profile_records(int family, double* ms, double* work, int64_t
   return MSR_OK;
 }
 
+namespace msr { extern long long* g_tc_dbg; }
+extern "C" int msr_debug_tc_counters(long long* d_counters) {
+  msr::g_tc_dbg = d_counters;
+  return MSR_OK;
+}
+
 extern "C" int msr_op_conv_tc(const uint16_t* d_x, const uint16_t* d_w, const float* d_bias, float* d_y_f32,
                               uint16_t* d_y_bf16, int n, int r_out, int cin, int cout, int taps, int stride, int pad,
                               int act, float slope, float* d_stat_pairs, void* stream) {

@@ -38,7 +38,8 @@ struct Cfg {
   static constexpr int kBBytes = (BN / CTAS) * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (kStageBytes >= 48 * 1024) ? 4 : (kStageBytes >= 32 * 1024 ? 6 : 8);
-  static constexpr int kTmemCols = 2 * BN;        // two accumulator buffers (power of two >= 32)
+  static constexpr int kAcc = (BN >= 256) ? 2 : 4;   // accumulator buffers in TMEM (epilogue of tile i overlaps i+1..)
+  static constexpr int kTmemCols = (kAcc * BN < 32) ? 32 : kAcc * BN;   // power of two >= 32, <= 512
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -67,6 +68,7 @@ struct EpiParams {
   int act;
   int split_out;             // TC_EPI_ACT_BF16: write hi | lo halves (row pitch 2 * ncols)
   __nv_bfloat16* out_bf16;
+  long long* dbg;            // optional per-CTA cycle counters (msr_debug_tc_counters): 8 values per CTA
 };
 
 // Sum over the 32 lanes of t[j] for every j; afterwards lane l holds the total of element l in t[0].  31 shuffles.
@@ -117,6 +119,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       __trap();
     }
   }
+}
+__device__ __forceinline__ long long mbar_wait_timed(uint32_t bar, uint32_t parity, bool timed) {
+  if (!timed) {
+    mbar_wait(bar, parity);
+    return 0;
+  }
+  const long long t0 = clock64();
+  mbar_wait(bar, parity);
+  return clock64() - t0;
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -229,6 +240,22 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// 256-bit global accesses (sm_100): one full 32-byte sector per lane per instruction
+__device__ __forceinline__ void st_global_v8(void* p, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4,
+                                             uint32_t a5, uint32_t a6, uint32_t a7) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a0), "r"(a1), "r"(a2), "r"(a3),
+               "r"(a4), "r"(a5), "r"(a6), "r"(a7)
+               : "memory");
+}
+__device__ __forceinline__ void ld_global_nc_v8(const void* p, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p));
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
+}
+
 // K-major, 128-byte swizzle shared-memory matrix descriptor (tile rows of 128 bytes, 8-row atoms of 1024 bytes).
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   uint64_t d = 0;
@@ -263,8 +290,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (C::kStages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * C::kStages + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * C::kStages + 2 + a); };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + C::kStages * C::kStageBytes + 8 * (2 * C::kStages + 4));
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * C::kStages + C::kAcc + a); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + C::kStages * C::kStageBytes + 8 * (2 * C::kStages + 2 * C::kAcc));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = (g.n_tiles_m / CTAS) * g.n_tiles_n;
@@ -277,7 +304,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < C::kAcc; ++a) {
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), kEpiWarps * CTAS);  // one arrive per epilogue warp (of both CTAs of a pair)
     }
@@ -311,35 +338,51 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      const bool timed = ep.dbg != nullptr;
+      long long t_empty = 0, t_start = timed ? clock64() : 0;
+      // (no integer divisions in the steady-state loop: this single thread's issue rate bounds the whole pipeline)
+      const uint32_t lead_full0 = (CTAS == 2) ? mapa_shared(full_bar(0), 0) : 0u;
+      const int n_parts = g.split ? 3 : 1;
+      const int ksz = (g.taps == 9) ? 3 : 1;
       for (int tile = unit; tile < total_tiles; tile += n_units) {
         int b0, h0, w0, n0;
         decode_tile(tile, b0, h0, w0, n0);
-        for (int kc = 0; kc < k_chunks; ++kc) {
-          const int tap = kc / k_chunks_per_tap, cb = kc % k_chunks_per_tap;
-          const int ky = tap / 3, kx = tap % 3;   // taps == 1: (0, 0)
-          mbar_wait(empty_bar(stage), phase ^ 1u);
-          const uint32_t sa = smem_base + stage * C::kStageBytes;
-          const uint32_t sb = sa + kABytes;
-          // split-bf16: parts (x_hi, x_hi, x_lo) of A pair with (w_hi, w_lo, w_hi) of B
-          const int a_chan = g.split ? ((cb / chunks_per_part == 2) ? g.cin : 0) + (cb % chunks_per_part) * kBlockK
-                                     : cb * kBlockK;
-          if constexpr (CTAS == 2) {
-            // both CTAs report their bytes to the leader's barrier; each loads its own A rows and its half of B
-            if (leader) mbar_expect_tx(full_bar(stage), 2 * C::kStageBytes);
-            const uint32_t lead_bar = mapa_shared(full_bar(stage), 0);
-            tma_load_4d_pair(sa, &map_a, lead_bar, a_chan, w0 * g.stride + kx - g.pad, h0 * g.stride + ky - g.pad, b0);
-            tma_load_2d_pair(sb, &map_b, lead_bar, (tap * k_chunks_per_tap + cb) * kBlockK,
-                             n0 + (int)cta_rank * (BN / 2));
-          } else {
-            mbar_expect_tx(full_bar(stage), C::kStageBytes);
-            tma_load_4d(sa, &map_a, full_bar(stage), a_chan, w0 * g.stride + kx - g.pad, h0 * g.stride + ky - g.pad, b0);
-            tma_load_2d(sb, &map_b, full_bar(stage), (tap * k_chunks_per_tap + cb) * kBlockK, n0);
-          }
-          if (++stage == C::kStages) {
-            stage = 0;
-            phase ^= 1u;
+        const int nb = n0 + ((CTAS == 2) ? (int)cta_rank * (BN / 2) : 0);
+        int kcol = 0;   // K coordinate of the weight tile
+        for (int ky = 0; ky < ksz; ++ky) {
+          const int ch = h0 * g.stride + ky - g.pad;
+          for (int kx = 0; kx < ksz; ++kx) {
+            const int cw = w0 * g.stride + kx - g.pad;
+            for (int part = 0; part < n_parts; ++part) {
+              // split-bf16: parts (x_hi, x_hi, x_lo) of A pair with (w_hi, w_lo, w_hi) of B
+              const int a_base = (part == 2) ? g.cin : 0;
+              for (int cb = 0; cb < chunks_per_part; ++cb, kcol += kBlockK) {
+                t_empty += mbar_wait_timed(empty_bar(stage), phase ^ 1u, timed);
+                const uint32_t sa = smem_base + stage * C::kStageBytes;
+                const uint32_t sb = sa + kABytes;
+                if constexpr (CTAS == 2) {
+                  // both CTAs report their bytes to the leader's barrier; each loads its own A rows and its half of B
+                  if (leader) mbar_expect_tx(full_bar(stage), 2 * C::kStageBytes);
+                  const uint32_t lead_bar = lead_full0 + 8u * stage;
+                  tma_load_4d_pair(sa, &map_a, lead_bar, a_base + cb * kBlockK, cw, ch, b0);
+                  tma_load_2d_pair(sb, &map_b, lead_bar, kcol, nb);
+                } else {
+                  mbar_expect_tx(full_bar(stage), C::kStageBytes);
+                  tma_load_4d(sa, &map_a, full_bar(stage), a_base + cb * kBlockK, cw, ch, b0);
+                  tma_load_2d(sb, &map_b, full_bar(stage), kcol, nb);
+                }
+                if (++stage == C::kStages) {
+                  stage = 0;
+                  phase ^= 1u;
+                }
+              }
+            }
           }
         }
+      }
+      if (timed) {
+        ep.dbg[blockIdx.x * 8 + 0] = t_empty;
+        ep.dbg[blockIdx.x * 8 + 1] = clock64() - t_start;
       }
     }
   } else if (warp == kEpiWarps + 1) {
@@ -350,12 +393,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      const bool timed = ep.dbg != nullptr;
+      long long t_full = 0, t_tempty = 0, t_start = timed ? clock64() : 0;
       for (int tile = unit; tile < total_tiles; tile += n_units) {
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        t_tempty += mbar_wait_timed(tempty_bar(acc), acc_phase ^ 1u, timed);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
         for (int kc = 0; kc < k_chunks; ++kc) {
-          mbar_wait(full_bar(stage), phase);
+          t_full += mbar_wait_timed(full_bar(stage), phase, timed);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * C::kStageBytes;
           const uint64_t adesc = make_smem_desc(sa);
@@ -379,8 +424,15 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         // accumulator complete -> epilogue (of both CTAs)
         if constexpr (CTAS == 2) umma_commit_pair(tfull_bar(acc));
         else umma_commit(tfull_bar(acc));
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1u;
+        if (++acc == C::kAcc) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
+      }
+      if (timed) {
+        ep.dbg[blockIdx.x * 8 + 2] = t_full;
+        ep.dbg[blockIdx.x * 8 + 3] = t_tempty;
+        ep.dbg[blockIdx.x * 8 + 4] = clock64() - t_start;
       }
     }
   } else {
@@ -397,7 +449,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       const int b = b0 + bi, h = h0 + hi, w = w0 + wi;
       const bool row_ok = b < g.n;
       const int64_t m = ((int64_t)b * g.r + h) * g.r + w;
+      const bool timed = ep.dbg != nullptr && threadIdx.x == 0;
+      const long long tw0 = timed ? clock64() : 0;
       mbar_wait(tfull_bar(acc), acc_phase);
+      if (timed) ep.dbg[blockIdx.x * 8 + 5] += clock64() - tw0;
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
       if (ep.mode == TC_EPI_BIAS_F32) {
@@ -427,15 +482,19 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             if (ep.res) {
               const float* rs_ptr = ep.res + res_row * g.ncols + col;
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 rr = __ldg(reinterpret_cast<const float4*>(rs_ptr + j));
-                o[j] += rr.x; o[j + 1] += rr.y; o[j + 2] += rr.z; o[j + 3] += rr.w;
+              for (int j = 0; j < 32; j += 8) {
+                float rr[8];
+                ld_global_nc_v8(rs_ptr + j, rr);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) o[j + q] += rr[q];
               }
             }
             float* dst = ep.y + m * g.ncols + col;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(dst + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+            for (int j = 0; j < 32; j += 8)
+              st_global_v8(dst + j, __float_as_uint(o[j]), __float_as_uint(o[j + 1]), __float_as_uint(o[j + 2]),
+                           __float_as_uint(o[j + 3]), __float_as_uint(o[j + 4]), __float_as_uint(o[j + 5]),
+                           __float_as_uint(o[j + 6]), __float_as_uint(o[j + 7]));
           }
           if (ep.stat_pairs != nullptr) {   // per-channel batch statistics of the output (spade.py:21), fused
             float t[32];
@@ -486,10 +545,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
               ob[j + 2] = __float2bfloat16_rn(o.z); ob[j + 3] = __float2bfloat16_rn(o.w);
             }
             if (!ep.split_out) {
-              uint4* dst = reinterpret_cast<uint4*>(ep.out_bf16 + m * g.ncols + col);
-              const uint4* src = reinterpret_cast<const uint4*>(ob);
+              __nv_bfloat16* dst = ep.out_bf16 + m * g.ncols + col;
+              const uint32_t* src = reinterpret_cast<const uint32_t*>(ob);
 #pragma unroll
-              for (int q = 0; q < 4; ++q) dst[q] = src[q];
+              for (int q = 0; q < 2; ++q)
+                st_global_v8(dst + 16 * q, src[8 * q], src[8 * q + 1], src[8 * q + 2], src[8 * q + 3], src[8 * q + 4],
+                             src[8 * q + 5], src[8 * q + 6], src[8 * q + 7]);
             } else {
               uint4* dst = reinterpret_cast<uint4*>(ep.out_bf16 + m * 2 * g.ncols + col);
               const uint4* src = reinterpret_cast<const uint4*>(ob);
@@ -552,9 +613,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
               const float* bg = ep.bias + (n0 + gc) + half * 32;        // gamma bias
               const float* bb = bg + 64;                                 // beta bias
               __align__(16) __nv_bfloat16 o[32];
+              float xall[32];
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) ld_global_nc_v8(xs + j, *reinterpret_cast<float(*)[8]>(&xall[j]));
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
-                const float4 xv = __ldg(reinterpret_cast<const float4*>(xs + j));
+                const float4 xv = make_float4(xall[j], xall[j + 1], xall[j + 2], xall[j + 3]);
                 const float4 m4 = __ldg(reinterpret_cast<const float4*>(mu + j));
                 const float4 r4 = __ldg(reinterpret_cast<const float4*>(rsd + j));
                 const float4 g4 = __ldg(reinterpret_cast<const float4*>(bg + j));
@@ -571,10 +635,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                   o[j + q] = __float2bfloat16_rn(t);
                 }
               }
-              uint4* dst = reinterpret_cast<uint4*>(ep.out_bf16 + m * Cc + ch);
-              const uint4* src = reinterpret_cast<const uint4*>(o);
+              __nv_bfloat16* dst = ep.out_bf16 + m * Cc + ch;
+              const uint32_t* src = reinterpret_cast<const uint32_t*>(o);
 #pragma unroll
-              for (int q = 0; q < 4; ++q) dst[q] = src[q];
+              for (int q = 0; q < 2; ++q)
+                st_global_v8(dst + 16 * q, src[8 * q], src[8 * q + 1], src[8 * q + 2], src[8 * q + 3], src[8 * q + 4],
+                             src[8 * q + 5], src[8 * q + 6], src[8 * q + 7]);
             }
           }
         }
@@ -587,8 +653,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         if constexpr (CTAS == 2) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));   // the leader's MMA warp waits
         else mbar_arrive(tempty_bar(acc));
       }
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1u;
+      if (++acc == C::kAcc) {
+        acc = 0;
+        acc_phase ^= 1u;
+      }
     }
   }
 
@@ -628,6 +696,8 @@ static const bool g_disable_pairs = [] {
   return e != nullptr && e[0] == '0';
 }();
 
+long long* g_tc_dbg = nullptr;   // msr_debug_tc_counters
+
 struct ConvTC {
   CUtensorMap map_a, map_b;
   tc::Geometry g;
@@ -663,7 +733,10 @@ int conv_tc_plan_create(ConvTC** out, const ConvTCArgs& a) {
   if (a.epilogue == TC_EPI_PHASE_F32) p->bn = 32;
   g.n_tiles_n = a.ncols / p->bn;
   // CTA pairs when the layer is large enough to fill the chip with 256-row tiles
-  p->ctas = (p->bn >= 128 && g.n_tiles_m % 2 == 0 && (g.n_tiles_m / 2) * g.n_tiles_n >= 74 && !g_disable_pairs) ? 2 : 1;
+  // (and the K loop long enough to amortise the cross-CTA handshakes)
+  const int k_chunks = a.taps * (a.split3 ? 3 : 1) * (a.cin / 64);
+  p->ctas = (p->bn >= 128 && g.n_tiles_m % 2 == 0 && (g.n_tiles_m / 2) * g.n_tiles_n >= 74 && k_chunks >= 8 &&
+             !g_disable_pairs) ? 2 : 1;
   const int rin = a.r * a.stride;
 
   // A: 4-D NHWC tensor {C, W, H, N}; a stride-2 convolution walks W and H with element stride 2
@@ -703,6 +776,7 @@ int conv_tc_plan_create(ConvTC** out, const ConvTCArgs& a) {
   e.sx = a.sx; e.sx_shift = a.sx_shift; e.mean = a.mean; e.rstd = a.rstd;
   e.samples_per_group = a.samples_per_group > 0 ? a.samples_per_group : 1;
   e.slope = a.slope; e.act = a.act; e.split_out = a.split_out; e.out_bf16 = a.out_bf16;
+  e.dbg = g_tc_dbg;
   const char* bad = nullptr;
   if (a.epilogue == TC_EPI_BIAS_F32) {
     if (!a.y) bad = "conv_tc: y is null";
