@@ -168,6 +168,15 @@ int msr_op_conv_tc(const uint16_t* d_x, const uint16_t* d_w, const float* d_bias
                    int n, int r_out, int cin, int cout, int taps, int stride, int pad, int act, float slope,
                    float* d_stat_pairs, void* stream);
 
+/* The fused SPADE operator (spade.py:19-24 + blocks.py:30): gamma | beta 3x3 convolution of the 128-channel mask
+ * features d_a (n, r, r, 128) bf16 with d_w (2C, 1152) bf16 whose rows are interleaved per 64 channels (64 gamma rows,
+ * 64 beta rows, ...) and d_bias (2C) in the same order; epilogue out = leaky_relu(gamma * (x - mean) * rstd + beta, 0.2)
+ * as bf16 (n, r, r, C), with x = d_x (n, r >> x_shift, r >> x_shift, C) float32 read at (h >> x_shift, w >> x_shift)
+ * (nearest upsampling fused) and d_mean / d_rstd (n / samples_per_group, C). */
+int msr_op_spade_tc(const uint16_t* d_a, const uint16_t* d_w, const float* d_bias, const float* d_x, int x_shift,
+                    const float* d_mean, const float* d_rstd, int samples_per_group, uint16_t* d_out, int n, int r,
+                    int C, void* stream);
+
 /* Optimisation aid: when d_counters != NULL (148 * 8 int64, zero-initialised by the caller), every tensor-core convolution
  * planned afterwards records per-CTA cycle counts: [0] producer wait on empty stages, [1] producer total, [2] MMA issuer
  * wait on full stages, [3] MMA issuer wait on free accumulators, [4] MMA issuer total, [5] epilogue wait on accumulators.

@@ -126,6 +126,23 @@ extern "C" int msr_profile_records(int family, double* ms, double* work, int64_t
   return MSR_OK;
 }
 
+extern "C" int msr_op_spade_tc(const uint16_t* d_a, const uint16_t* d_w, const float* d_bias, const float* d_x,
+                               int x_shift, const float* d_mean, const float* d_rstd, int samples_per_group,
+                               uint16_t* d_out, int n, int r, int C, void* stream) {
+  ConvTCArgs a;
+  a.x = reinterpret_cast<const __nv_bfloat16*>(d_a);
+  a.w = reinterpret_cast<const __nv_bfloat16*>(d_w);
+  a.n = n; a.r = r; a.cin = 128; a.ncols = 2 * C;
+  a.epilogue = TC_EPI_SPADE_BF16; a.bias = d_bias; a.sx = d_x; a.sx_shift = x_shift; a.mean = d_mean; a.rstd = d_rstd;
+  a.samples_per_group = samples_per_group; a.slope = 0.2f; a.out_bf16 = reinterpret_cast<__nv_bfloat16*>(d_out);
+  ConvTC* plan = nullptr;
+  int rc = conv_tc_plan_create(&plan, a);
+  if (rc) return rc;
+  rc = conv_tc_launch(plan, (cudaStream_t)stream);
+  conv_tc_plan_destroy(plan);
+  return rc;
+}
+
 namespace msr { extern long long* g_tc_dbg; }
 extern "C" int msr_debug_tc_counters(long long* d_counters) {
   msr::g_tc_dbg = d_counters;

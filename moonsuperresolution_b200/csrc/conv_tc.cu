@@ -37,7 +37,9 @@ template <int BN, int CTAS = 1>
 struct Cfg {
   static constexpr int kBBytes = (BN / CTAS) * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (kStageBytes >= 48 * 1024) ? 4 : (kStageBytes >= 32 * 1024 ? 6 : 8);
+  // as many stages as fit in 227 KB (the TMA latency of ~3000 cycles must be covered by stages x MMA time per stage)
+  static constexpr int kStagesFit = (227 * 1024 - 1024 - 256) / kStageBytes;
+  static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
   static constexpr int kAcc = (BN >= 256) ? 2 : 4;   // accumulator buffers in TMEM (epilogue of tile i overlaps i+1..)
   static constexpr int kTmemCols = (kAcc * BN < 32) ? 32 : kAcc * BN;   // power of two >= 32, <= 512
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -93,10 +95,14 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+  // relaxed: the bytes are written by the async proxy (TMA) and tracked by complete_tx; a release would only add a
+  // MEMBAR to the single producer thread whose issue rate bounds the pipeline
+  asm volatile("mbarrier.arrive.expect_tx.relaxed.cta.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+  // relaxed: the accumulator hand-back is ordered by tcgen05.wait::ld + tcgen05.fence::before_thread_sync; a release
+  // arrive would make every epilogue warp drain its global stores (MEMBAR + ERRBAR, ~30 % of the stall samples)
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
@@ -166,7 +172,7 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA loads of a CTA pair: the bytes land in the executing CTA's shared memory, the transaction count is reported to
 // the mbarrier at `bar` (a shared::cluster address -- the leader CTA's barrier)

@@ -105,6 +105,49 @@ def test_conv_tc_general_operator(torch, n, r_out, cin, cout, taps, stride, pad,
         np.testing.assert_allclose(p[5, :, 0], flat[5 * 32:6 * 32].sum(0), rtol=1e-5, atol=1e-4)
 
 
+@pytest.mark.parametrize("n,r,C,x_shift,spg", [(4, 16, 128, 1, 2), (2, 64, 256, 0, 2), (2, 128, 128, 1, 1), (3, 4, 64, 0, 3)])
+def test_fused_spade_operator(torch, n, r, C, x_shift, spg):
+    """gamma|beta conv + normalise + modulate + LeakyReLU(0.2) (spade.py:19-24, blocks.py:30) with the nearest x2
+    upsampling of x fused (x stored at r >> x_shift)."""
+    from moonsuperresolution_b200 import _lib
+    rng = np.random.default_rng(r + C)
+    a = bf16_round(np.maximum(rng.standard_normal((n, r, r, 128)), 0).astype(np.float32), torch)
+    wg = bf16_round((rng.standard_normal((3, 3, 128, C)) / np.sqrt(1152)).astype(np.float32), torch)
+    wb = bf16_round((rng.standard_normal((3, 3, 128, C)) / np.sqrt(1152)).astype(np.float32), torch)
+    bg, bb = rng.standard_normal(C).astype(np.float32), rng.standard_normal(C).astype(np.float32)
+    rs = r >> x_shift
+    x = rng.standard_normal((n, rs, rs, C)).astype(np.float32) * 2 + 1
+    groups = n // spg
+    mean = rng.standard_normal((groups, C)).astype(np.float32)
+    rstd = rng.uniform(0.5, 2.0, (groups, C)).astype(np.float32)
+    at = torch.from_numpy(a).permute(0, 3, 1, 2)
+    gamma = OG.conv2d_same(at, wg, bg).permute(0, 2, 3, 1).numpy()
+    beta = OG.conv2d_same(at, wb, bb).permute(0, 2, 3, 1).numpy()
+    xu = x.repeat(1 << x_shift, axis=1).repeat(1 << x_shift, axis=2)
+    gi = np.arange(n) // spg
+    t = gamma * ((xu - mean[gi][:, None, None, :]) * rstd[gi][:, None, None, :]) + beta
+    want = np.where(t > 0, t, 0.2 * t)
+    # interleave rows per 64 channels: [64 gamma | 64 beta] ...
+    K = 1152
+    wt = np.zeros((2 * C, K), np.float32)
+    bias = np.zeros(2 * C, np.float32)
+    for c in range(C):
+        j, q = divmod(c, 64)
+        wt[128 * j + q] = wg.reshape(K, C)[:, c]
+        wt[128 * j + 64 + q] = wb.reshape(K, C)[:, c]
+        bias[128 * j + q], bias[128 * j + 64 + q] = bg[c], bb[c]
+    d_a = torch.from_numpy(a).cuda().to(torch.bfloat16).contiguous()
+    d_w = torch.from_numpy(wt).cuda().to(torch.bfloat16).contiguous()
+    d_b, d_x, d_m, d_r = (torch.from_numpy(v).cuda() for v in (bias, x, mean, rstd))
+    d_o = torch.zeros((n, r, r, C), dtype=torch.bfloat16, device="cuda")
+    _lib.check(_lib.lib().msr_op_spade_tc(d_a.data_ptr(), d_w.data_ptr(), d_b.data_ptr(), d_x.data_ptr(), x_shift,
+                                          d_m.data_ptr(), d_r.data_ptr(), spg, d_o.data_ptr(), n, r, C,
+                                          _lib.stream_ptr()), "msr_op_spade_tc")
+    torch.cuda.synchronize()
+    got = d_o.float().cpu().numpy()
+    assert np.abs(got - want).max() <= 0.02 * max(1.0, np.abs(want).max())      # bf16 output rounding
+
+
 @pytest.mark.parametrize("n,r,cin,cout", [(2, 8, 5, 7), (1, 16, 64, 33), (3, 4, 128, 128)])
 def test_conv3x3_fp32_operator(torch, n, r, cin, cout):
     from moonsuperresolution_b200 import _lib

@@ -31,3 +31,31 @@ for (n, r, cin, cout, taps) in shapes:
     flops = 2.0 * n * r * r * cout * taps * cin
     print(f"n={n} r={r} cin={cin} cout={cout} taps={taps}: {ms:.3f} ms {flops/ms/1e9:.0f} TFLOP/s | producer: wait_empty {d[act,0].mean():.0f} of {d[act,1].mean():.0f} cyc"
           f" | mma: wait_full {d[lead,2].mean():.0f} wait_acc {d[lead,3].mean():.0f} of {d[lead,4].mean():.0f} cyc | epi wait_acc {d[act,5].mean():.0f}", flush=True)
+
+# fused SPADE epilogue (the real gamma | beta layers): rb6 spade_1 (C = 256, x at r/2), rb5 spade_1 (C = 512)
+for (n, r, C) in [(16, 256, 256), (16, 128, 512), (16, 256, 128)]:
+    a = torch.randn((n, r, r, 128), device="cuda").clamp_(min=0).to(torch.bfloat16)
+    w = (torch.randn((2 * C, 1152), device="cuda") * 0.03).to(torch.bfloat16)
+    b = torch.zeros(2 * C, device="cuda")
+    x = torch.randn((n, r // 2, r // 2, C), device="cuda")
+    mean = torch.zeros((1, C), device="cuda"); rstd = torch.ones((1, C), device="cuda")
+    out = torch.empty((n, r, r, C), device="cuda", dtype=torch.bfloat16)
+    st = _lib.stream_ptr()
+    def launch():
+        _lib.check(L.msr_op_spade_tc(a.data_ptr(), w.data_ptr(), b.data_ptr(), x.data_ptr(), 1, mean.data_ptr(),
+                                     rstd.data_ptr(), n, out.data_ptr(), n, r, C, st))
+    L.msr_debug_tc_counters(None)
+    for _ in range(10):
+        launch()
+    torch.cuda.synchronize()
+    dbg.zero_()
+    L.msr_debug_tc_counters(dbg.data_ptr())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); launch(); e1.record(); torch.cuda.synchronize()
+    L.msr_debug_tc_counters(None)
+    d = dbg.view(148, 8).double().cpu()
+    act = d[:, 1] > 0; lead = d[:, 4] > 0
+    ms = e0.elapsed_time(e1)
+    flops = 2.0 * n * r * r * 2 * C * 1152
+    print(f"SPADE n={n} r={r} C={C}: {ms:.3f} ms {flops/ms/1e9:.0f} TFLOP/s | producer: wait_empty {d[act,0].mean():.0f} of {d[act,1].mean():.0f} cyc"
+          f" | mma: wait_full {d[lead,2].mean():.0f} wait_acc {d[lead,3].mean():.0f} of {d[lead,4].mean():.0f} cyc | epi wait_acc {d[act,5].mean():.0f}", flush=True)
