@@ -52,6 +52,9 @@ struct Geometry {
   int stride, pad;           // input coordinate of tap (ky, kx) for output (h, w): (h*stride + ky - pad, w*stride + kx - pad)
   int TW, TH, NB;            // tile = NB images x TH rows x TW cols (all powers of two, product 128)
   int tiles_w, tiles_h, tiles_b, n_tiles_m, n_tiles_n;
+  int lw, lh;                // log2(tiles_w), log2(tiles_h) (both are powers of two)
+  int pref_boxes;            // > 0: L2-prefetch the next tile's input window with this many channel boxes (map_p)
+  int pref_chan;             // channels per prefetch box
 };
 
 struct EpiParams {
@@ -151,6 +154,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
+}
+// L2 prefetch of a box (no shared memory involved): hides the HBM first-touch latency of the NEXT tile's input rows
+__device__ __forceinline__ void tma_prefetch_l2_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(map), "r"(c0), "r"(c1),
+               "r"(c2), "r"(c3)
+               : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -281,7 +290,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int bn, int m = kBlockM) {
 template <int BN, int CTAS>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                  const Geometry g, const EpiParams ep) {
+                  const __grid_constant__ CUtensorMap map_p, const Geometry g, const EpiParams ep) {
   using C = Cfg<BN, CTAS>;
   const uint32_t cta_rank = (CTAS == 2) ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
@@ -330,30 +339,61 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  auto decode_tile = [&](int tile, int& b0, int& h0, int& w0, int& n0) {
-    const int mt = (tile / g.n_tiles_n) * CTAS + (int)cta_rank, nt = tile % g.n_tiles_n;
-    const int tw = mt % g.tiles_w, th = (mt / g.tiles_w) % g.tiles_h, tb = mt / (g.tiles_w * g.tiles_h);
+  // tile -> (M tile, N tile) without divisions in the loops: every role thread walks the same sequence
+  // tile = unit, unit + n_units, ... and keeps (mq, nt) = (tile / n_tiles_n, tile % n_tiles_n) incrementally
+  const int step_m = n_units / g.n_tiles_n, step_n = n_units % g.n_tiles_n;
+  struct TileIter {
+    int mq, nt;
+  };
+  auto tile_first = [&]() {
+    TileIter it;
+    it.mq = unit / g.n_tiles_n;
+    it.nt = unit % g.n_tiles_n;
+    return it;
+  };
+  auto tile_next = [&](TileIter& it) {
+    it.mq += step_m;
+    it.nt += step_n;
+    if (it.nt >= g.n_tiles_n) {
+      it.nt -= g.n_tiles_n;
+      it.mq += 1;
+    }
+  };
+  auto decode_tile = [&](const TileIter& it, int& b0, int& h0, int& w0, int& n0) {
+    const int mt = it.mq * CTAS + (int)cta_rank;
+    const int tw = mt & (g.tiles_w - 1), th = (mt >> g.lw) & (g.tiles_h - 1), tb = mt >> (g.lw + g.lh);
     b0 = tb * g.NB;
     h0 = th * g.TH;
     w0 = tw * g.TW;
-    n0 = nt * BN;
+    n0 = it.nt * BN;
   };
 
   if (warp == kEpiWarps) {
     // ===================== TMA producer =====================
+    // (one thread issues both operands: a second producer warp was measured to be slower)
     if (lane == 0) {
+      constexpr bool is_a = true;
       int stage = 0;
       uint32_t phase = 0;
-      const bool timed = ep.dbg != nullptr;
+      const bool timed = ep.dbg != nullptr && is_a;
       long long t_empty = 0, t_start = timed ? clock64() : 0;
-      // (no integer divisions in the steady-state loop: this single thread's issue rate bounds the whole pipeline)
+      // (no integer divisions in the steady-state loop)
       const uint32_t lead_full0 = (CTAS == 2) ? mapa_shared(full_bar(0), 0) : 0u;
       const int n_parts = g.split ? 3 : 1;
       const int ksz = (g.taps == 9) ? 3 : 1;
-      for (int tile = unit; tile < total_tiles; tile += n_units) {
+      TileIter it = tile_first();
+      for (int tile = unit; tile < total_tiles; tile += n_units, tile_next(it)) {
         int b0, h0, w0, n0;
-        decode_tile(tile, b0, h0, w0, n0);
+        decode_tile(it, b0, h0, w0, n0);
         const int nb = n0 + ((CTAS == 2) ? (int)cta_rank * (BN / 2) : 0);
+        if (is_a && g.pref_boxes > 0 && tile + n_units < total_tiles) {
+          TileIter nx = it;
+          tile_next(nx);
+          int pb0, ph0, pw0, pn0;
+          decode_tile(nx, pb0, ph0, pw0, pn0);
+          for (int pc = 0; pc < g.pref_boxes; ++pc)
+            tma_prefetch_l2_4d(&map_p, pc * g.pref_chan, pw0 * g.stride, ph0 * g.stride - g.pad, pb0);
+        }
         int kcol = 0;   // K coordinate of the weight tile
         for (int ky = 0; ky < ksz; ++ky) {
           const int ch = h0 * g.stride + ky - g.pad;
@@ -365,17 +405,16 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
               for (int cb = 0; cb < chunks_per_part; ++cb, kcol += kBlockK) {
                 t_empty += mbar_wait_timed(empty_bar(stage), phase ^ 1u, timed);
                 const uint32_t sa = smem_base + stage * C::kStageBytes;
-                const uint32_t sb = sa + kABytes;
                 if constexpr (CTAS == 2) {
                   // both CTAs report their bytes to the leader's barrier; each loads its own A rows and its half of B
-                  if (leader) mbar_expect_tx(full_bar(stage), 2 * C::kStageBytes);
                   const uint32_t lead_bar = lead_full0 + 8u * stage;
+                  if (leader) mbar_expect_tx(full_bar(stage), 2 * C::kStageBytes);
                   tma_load_4d_pair(sa, &map_a, lead_bar, a_base + cb * kBlockK, cw, ch, b0);
-                  tma_load_2d_pair(sb, &map_b, lead_bar, kcol, nb);
+                  tma_load_2d_pair(sa + kABytes, &map_b, lead_bar, kcol, nb);
                 } else {
                   mbar_expect_tx(full_bar(stage), C::kStageBytes);
                   tma_load_4d(sa, &map_a, full_bar(stage), a_base + cb * kBlockK, cw, ch, b0);
-                  tma_load_2d(sb, &map_b, full_bar(stage), kcol, nb);
+                  tma_load_2d(sa + kABytes, &map_b, full_bar(stage), kcol, nb);
                 }
                 if (++stage == C::kStages) {
                   stage = 0;
@@ -449,9 +488,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int quarter = warp & 3, csel = warp >> 2;
     const int row = quarter * 32 + lane;  // tile row == TMEM lane
     const int wi = row % g.TW, hi = (row / g.TW) % g.TH, bi = row / (g.TW * g.TH);
-    for (int tile = unit; tile < total_tiles; tile += n_units) {
+    TileIter it = tile_first();
+    for (int tile = unit; tile < total_tiles; tile += n_units, tile_next(it)) {
       int b0, h0, w0, n0;
-      decode_tile(tile, b0, h0, w0, n0);
+      decode_tile(it, b0, h0, w0, n0);
       const int b = b0 + bi, h = h0 + hi, w = w0 + wi;
       const bool row_ok = b < g.n;
       const int64_t m = ((int64_t)b * g.r + h) * g.r + w;
@@ -467,7 +507,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           const int rs = g.r >> ep.res_shift;
           res_row = ((int64_t)b * rs + (h >> ep.res_shift)) * rs + (w >> ep.res_shift);
         }
-        const int mt = (tile / g.n_tiles_n) * CTAS + (int)cta_rank;
+        const int mt = it.mq * CTAS + (int)cta_rank;
 #pragma unroll 1
         for (int c0 = csel * 32; c0 < BN; c0 += 64) {
           uint32_t v[32];
@@ -697,6 +737,11 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // MSR_TC_PAIRS=0 in the environment forces single-CTA tiles (A/B comparison of the two schedules)
+// MSR_TC_PREFETCH=1 switches the L2 prefetch of the next tile's input window on (measured: no gain, slight loss)
+static const bool g_disable_prefetch = [] {
+  const char* e = getenv("MSR_TC_PREFETCH");
+  return !(e != nullptr && e[0] == '1');
+}();
 static const bool g_disable_pairs = [] {
   const char* e = getenv("MSR_TC_PAIRS");
   return e != nullptr && e[0] == '0';
@@ -705,7 +750,7 @@ static const bool g_disable_pairs = [] {
 long long* g_tc_dbg = nullptr;   // msr_debug_tc_counters
 
 struct ConvTC {
-  CUtensorMap map_a, map_b;
+  CUtensorMap map_a, map_b, map_p;
   tc::Geometry g;
   tc::EpiParams ep;
   int bn;
@@ -735,6 +780,10 @@ int conv_tc_plan_create(ConvTC** out, const ConvTCArgs& a) {
   g.tiles_h = a.r / g.TH;
   g.tiles_b = ceil_div(a.n, g.NB);
   g.n_tiles_m = g.tiles_w * g.tiles_h * g.tiles_b;
+  g.lw = 0;
+  while ((1 << g.lw) < g.tiles_w) ++g.lw;
+  g.lh = 0;
+  while ((1 << g.lh) < g.tiles_h) ++g.lh;
   p->bn = (a.ncols % 256 == 0) ? 256 : (a.ncols % 128 == 0) ? 128 : (a.ncols % 64 == 0) ? 64 : 32;
   if (a.epilogue == TC_EPI_PHASE_F32) p->bn = 32;
   g.n_tiles_n = a.ncols / p->bn;
@@ -759,6 +808,26 @@ int conv_tc_plan_create(ConvTC** out, const ConvTCArgs& a) {
     if (r != CUDA_SUCCESS) {
       delete p;
       return fail(MSR_E_CUDA, "conv_tc: cuTensorMapEncodeTiled(A) failed with " + std::to_string((int)r));
+    }
+  }
+  // L2 prefetch window of one tile: all rows its taps touch x its columns x a block of channels
+  g.pref_boxes = 0;
+  g.pref_chan = 0;
+  p->map_p = p->map_a;
+  if (a.stride == 1 && !g_disable_prefetch) {
+    const cuuint64_t ca = (cuuint64_t)a.cin * (a.split3 ? 2 : 1);
+    const int pc = (int)std::min<cuuint64_t>(ca, 256);
+    cuuint64_t dims[4] = {ca, (cuuint64_t)rin, (cuuint64_t)rin, (cuuint64_t)a.n};
+    cuuint64_t strides[3] = {ca * 2, (cuuint64_t)rin * ca * 2, (cuuint64_t)rin * rin * ca * 2};
+    cuuint32_t box[4] = {(cuuint32_t)pc, (cuuint32_t)g.TW, (cuuint32_t)std::min(256, g.TH + (a.taps == 9 ? 2 : 0)),
+                         (cuuint32_t)g.NB};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&p->map_p, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(a.x), dims, strides, box,
+                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_SUCCESS) {
+      g.pref_boxes = (int)((ca + pc - 1) / pc);
+      g.pref_chan = pc;
     }
   }
   // B: 2-D weights {K, N}
@@ -848,24 +917,24 @@ int conv_tc_launch(const ConvTC* p, cudaStream_t st) {
     cfg.numAttrs = 1;
     if (p->bn == 256) {
       cfg.dynamicSmemBytes = tc::Cfg<256, 2>::kSmemBytes;
-      MSR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc::conv3x3_tc_kernel<256, 2>, p->map_a, p->map_b, p->g, p->ep));
+      MSR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc::conv3x3_tc_kernel<256, 2>, p->map_a, p->map_b, p->map_p, p->g, p->ep));
     } else {
       cfg.dynamicSmemBytes = tc::Cfg<128, 2>::kSmemBytes;
-      MSR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc::conv3x3_tc_kernel<128, 2>, p->map_a, p->map_b, p->g, p->ep));
+      MSR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc::conv3x3_tc_kernel<128, 2>, p->map_a, p->map_b, p->map_p, p->g, p->ep));
     }
   } else {
     switch (p->bn) {
       case 256:
-        tc::conv3x3_tc_kernel<256, 1><<<p->grid, tc::kThreads, tc::Cfg<256, 1>::kSmemBytes, st>>>(p->map_a, p->map_b, p->g, p->ep);
+        tc::conv3x3_tc_kernel<256, 1><<<p->grid, tc::kThreads, tc::Cfg<256, 1>::kSmemBytes, st>>>(p->map_a, p->map_b, p->map_p, p->g, p->ep);
         break;
       case 128:
-        tc::conv3x3_tc_kernel<128, 1><<<p->grid, tc::kThreads, tc::Cfg<128, 1>::kSmemBytes, st>>>(p->map_a, p->map_b, p->g, p->ep);
+        tc::conv3x3_tc_kernel<128, 1><<<p->grid, tc::kThreads, tc::Cfg<128, 1>::kSmemBytes, st>>>(p->map_a, p->map_b, p->map_p, p->g, p->ep);
         break;
       case 64:
-        tc::conv3x3_tc_kernel<64, 1><<<p->grid, tc::kThreads, tc::Cfg<64, 1>::kSmemBytes, st>>>(p->map_a, p->map_b, p->g, p->ep);
+        tc::conv3x3_tc_kernel<64, 1><<<p->grid, tc::kThreads, tc::Cfg<64, 1>::kSmemBytes, st>>>(p->map_a, p->map_b, p->map_p, p->g, p->ep);
         break;
       default:
-        tc::conv3x3_tc_kernel<32, 1><<<p->grid, tc::kThreads, tc::Cfg<32, 1>::kSmemBytes, st>>>(p->map_a, p->map_b, p->g, p->ep);
+        tc::conv3x3_tc_kernel<32, 1><<<p->grid, tc::kThreads, tc::Cfg<32, 1>::kSmemBytes, st>>>(p->map_a, p->map_b, p->map_p, p->g, p->ep);
     }
   }
   count_launch();
