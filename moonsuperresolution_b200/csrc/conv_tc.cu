@@ -33,10 +33,18 @@ constexpr int kThreads = (kEpiWarps + 2) * 32;   // + TMA producer warp + MMA is
 
 // CTAS = 2: a CTA pair (cluster of 2, cta_group::2) computes a 256 x BN tile; each CTA stages its own 128 rows of A and
 // only HALF of the B tile, which cuts the L2 -> shared-memory traffic per FLOP (the measured limiter) by a third.
-template <int BN, int CTAS = 1>
+// STRIP: for tiles that are 128 consecutive pixels of ONE image row (r >= 128), a stage holds the 130-pixel input strip
+// of one (ky, channel block) and the three weight tiles of kx = 0, 1, 2; the three taps read the SAME strip through
+// shared-memory descriptors shifted by kx rows, which cuts the A-operand L2 -> smem traffic (the measured limiter of the
+// K = 1152 / 2304 layers) by 3.
+constexpr int kStripRows = kBlockM + 2;
+constexpr int kStripBytes = ((kStripRows * 128 + 1023) / 1024) * 1024;   // 17 KB, keeps the weight tiles 1024-aligned
+template <int BN, int CTAS = 1, bool STRIP = false>
 struct Cfg {
   static constexpr int kBBytes = (BN / CTAS) * kBlockK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kAStage = STRIP ? kStripBytes : kABytes;
+  static constexpr int kStageBytes = kAStage + (STRIP ? 3 : 1) * kBBytes;
+  static constexpr int kTxBytes = (STRIP ? kStripRows * 128 : kABytes) + (STRIP ? 3 : 1) * kBBytes;   // bytes TMA reports
   // as many stages as fit in 227 KB (the TMA latency of ~3000 cycles must be covered by stages x MMA time per stage)
   static constexpr int kStagesFit = (227 * 1024 - 1024 - 256) / kStageBytes;
   static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
@@ -53,6 +61,7 @@ struct Geometry {
   int TW, TH, NB;            // tile = NB images x TH rows x TW cols (all powers of two, product 128)
   int tiles_w, tiles_h, tiles_b, n_tiles_m, n_tiles_n;
   int lw, lh;                // log2(tiles_w), log2(tiles_h) (both are powers of two)
+  int strip_base_offset;     // STRIP: 1 = put the start row's swizzle phase into the descriptor base-offset field
   int pref_boxes;            // > 0: L2-prefetch the next tile's input window with this many channel boxes (map_p)
   int pref_chan;             // channels per prefetch box
 };
@@ -272,8 +281,8 @@ __device__ __forceinline__ void ld_global_nc_v8(const void* p, float (&v)[8]) {
 }
 
 // K-major, 128-byte swizzle shared-memory matrix descriptor (tile rows of 128 bytes, 8-row atoms of 1024 bytes).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-  uint64_t d = 0;
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t base_offset = 0) {
+  uint64_t d = (uint64_t)(base_offset & 7u) << 49;   // start row inside the 8-row swizzle atom (start not 1024-aligned)
   d |= (uint64_t)((saddr & 0x3FFFF) >> 4);        // start address, 16-byte units
   d |= (uint64_t)1 << 16;                          // leading byte offset (unused for swizzled K-major; 1)
   d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset: 8 rows * 128 B
@@ -287,11 +296,11 @@ __host__ __device__ constexpr uint32_t make_idesc(int bn, int m = kBlockM) {
 }
 
 // ---- the kernel -------------------------------------------------------------------------------------------------------
-template <int BN, int CTAS>
+template <int BN, int CTAS, bool STRIP>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                   const __grid_constant__ CUtensorMap map_p, const Geometry g, const EpiParams ep) {
-  using C = Cfg<BN, CTAS>;
+  using C = Cfg<BN, CTAS, STRIP>;
   const uint32_t cta_rank = (CTAS == 2) ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
   // work unit: a 128 x BN tile (CTAS == 1) or a 256 x BN tile shared by the pair (CTAS == 2)
@@ -312,7 +321,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   const int total_tiles = (g.n_tiles_m / CTAS) * g.n_tiles_n;
   const int chunks_per_part = g.cin / kBlockK;
   const int k_chunks_per_tap = (g.split ? 3 : 1) * chunks_per_part;
-  const int k_chunks = g.taps * k_chunks_per_tap;
+  const int k_chunks = STRIP ? 3 * chunks_per_part : g.taps * k_chunks_per_tap;   // pipeline stages per tile
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::kStages; ++s) {
@@ -394,31 +403,62 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           for (int pc = 0; pc < g.pref_boxes; ++pc)
             tma_prefetch_l2_4d(&map_p, pc * g.pref_chan, pw0 * g.stride, ph0 * g.stride - g.pad, pb0);
         }
-        int kcol = 0;   // K coordinate of the weight tile
-        for (int ky = 0; ky < ksz; ++ky) {
-          const int ch = h0 * g.stride + ky - g.pad;
-          for (int kx = 0; kx < ksz; ++kx) {
-            const int cw = w0 * g.stride + kx - g.pad;
-            for (int part = 0; part < n_parts; ++part) {
-              // split-bf16: parts (x_hi, x_hi, x_lo) of A pair with (w_hi, w_lo, w_hi) of B
-              const int a_base = (part == 2) ? g.cin : 0;
-              for (int cb = 0; cb < chunks_per_part; ++cb, kcol += kBlockK) {
-                t_empty += mbar_wait_timed(empty_bar(stage), phase ^ 1u, timed);
-                const uint32_t sa = smem_base + stage * C::kStageBytes;
-                if constexpr (CTAS == 2) {
-                  // both CTAs report their bytes to the leader's barrier; each loads its own A rows and its half of B
-                  const uint32_t lead_bar = lead_full0 + 8u * stage;
-                  if (leader) mbar_expect_tx(full_bar(stage), 2 * C::kStageBytes);
-                  tma_load_4d_pair(sa, &map_a, lead_bar, a_base + cb * kBlockK, cw, ch, b0);
-                  tma_load_2d_pair(sa + kABytes, &map_b, lead_bar, kcol, nb);
-                } else {
-                  mbar_expect_tx(full_bar(stage), C::kStageBytes);
-                  tma_load_4d(sa, &map_a, full_bar(stage), a_base + cb * kBlockK, cw, ch, b0);
-                  tma_load_2d(sa + kABytes, &map_b, full_bar(stage), kcol, nb);
-                }
-                if (++stage == C::kStages) {
-                  stage = 0;
-                  phase ^= 1u;
+        if constexpr (STRIP) {
+          // stage = (ky, channel block): the 130-pixel strip [w0 - 1, w0 + 129) of input row h0 + ky - 1 (out-of-range
+          // pixels / rows arrive as zeros = SAME padding) + the weight tiles of kx = 0, 1, 2
+          for (int ky = 0; ky < 3; ++ky) {
+            const int ch = h0 + ky - 1;
+            for (int cb = 0; cb < chunks_per_part; ++cb) {
+              t_empty += mbar_wait_timed(empty_bar(stage), phase ^ 1u, timed);
+              const uint32_t sa = smem_base + stage * C::kStageBytes;
+              const int kb = ky * 3 * g.cin + cb * kBlockK;
+              if constexpr (CTAS == 2) {
+                if (leader) mbar_expect_tx(full_bar(stage), 2 * C::kTxBytes);
+                const uint32_t lead_bar = lead_full0 + 8u * stage;
+                tma_load_4d_pair(sa, &map_a, lead_bar, cb * kBlockK, w0 - 1, ch, b0);
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx)
+                  tma_load_2d_pair(sa + C::kAStage + kx * C::kBBytes, &map_b, lead_bar, kb + kx * g.cin, nb);
+              } else {
+                mbar_expect_tx(full_bar(stage), C::kTxBytes);
+                tma_load_4d(sa, &map_a, full_bar(stage), cb * kBlockK, w0 - 1, ch, b0);
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx)
+                  tma_load_2d(sa + C::kAStage + kx * C::kBBytes, &map_b, full_bar(stage), kb + kx * g.cin, nb);
+              }
+              if (++stage == C::kStages) {
+                stage = 0;
+                phase ^= 1u;
+              }
+            }
+          }
+        } else {
+          int kcol = 0;   // K coordinate of the weight tile
+          for (int ky = 0; ky < ksz; ++ky) {
+            const int ch = h0 * g.stride + ky - g.pad;
+            for (int kx = 0; kx < ksz; ++kx) {
+              const int cw = w0 * g.stride + kx - g.pad;
+              for (int part = 0; part < n_parts; ++part) {
+                // split-bf16: parts (x_hi, x_hi, x_lo) of A pair with (w_hi, w_lo, w_hi) of B
+                const int a_base = (part == 2) ? g.cin : 0;
+                for (int cb = 0; cb < chunks_per_part; ++cb, kcol += kBlockK) {
+                  t_empty += mbar_wait_timed(empty_bar(stage), phase ^ 1u, timed);
+                  const uint32_t sa = smem_base + stage * C::kStageBytes;
+                  if constexpr (CTAS == 2) {
+                    // both CTAs report their bytes to the leader's barrier; each loads its own A rows and its half of B
+                    const uint32_t lead_bar = lead_full0 + 8u * stage;
+                    if (leader) mbar_expect_tx(full_bar(stage), 2 * C::kTxBytes);
+                    tma_load_4d_pair(sa, &map_a, lead_bar, a_base + cb * kBlockK, cw, ch, b0);
+                    tma_load_2d_pair(sa + kABytes, &map_b, lead_bar, kcol, nb);
+                  } else {
+                    mbar_expect_tx(full_bar(stage), C::kTxBytes);
+                    tma_load_4d(sa, &map_a, full_bar(stage), a_base + cb * kBlockK, cw, ch, b0);
+                    tma_load_2d(sa + kABytes, &map_b, full_bar(stage), kcol, nb);
+                  }
+                  if (++stage == C::kStages) {
+                    stage = 0;
+                    phase ^= 1u;
+                  }
                 }
               }
             }
@@ -448,15 +488,34 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           t_full += mbar_wait_timed(full_bar(stage), phase, timed);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * C::kStageBytes;
-          const uint64_t adesc = make_smem_desc(sa);
-          const uint64_t bdesc = make_smem_desc(sa + kABytes);
+          if constexpr (STRIP) {
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in 16-byte units
-            if constexpr (CTAS == 2)
-              umma_bf16_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kc | k) != 0 ? 1u : 0u);
-            else
-              umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kc | k) != 0 ? 1u : 0u);
+            for (int kx = 0; kx < 3; ++kx) {
+              // tap kx reads strip rows kx .. kx + 127: same buffer, start shifted by kx rows of 128 bytes (the hardware
+              // swizzle XORs address bits [4,7) with [7,10), so a 128-byte-aligned shifted start needs nothing else)
+              const uint64_t adesc = make_smem_desc(sa + kx * 128, g.strip_base_offset ? (uint32_t)kx : 0u);
+              const uint64_t bdesc = make_smem_desc(sa + C::kAStage + kx * C::kBBytes);
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k) {
+                if constexpr (CTAS == 2)
+                  umma_bf16_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                                 (kc | kx | k) != 0 ? 1u : 0u);
+                else
+                  umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                            (kc | kx | k) != 0 ? 1u : 0u);
+              }
+            }
+          } else {
+            const uint64_t adesc = make_smem_desc(sa);
+            const uint64_t bdesc = make_smem_desc(sa + kABytes);
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in 16-byte units
+              if constexpr (CTAS == 2)
+                umma_bf16_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kc | k) != 0 ? 1u : 0u);
+              else
+                umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kc | k) != 0 ? 1u : 0u);
+            }
           }
           // frees the smem stage (in both CTAs of a pair) when these MMAs retire
           if constexpr (CTAS == 2) umma_commit_pair(empty_bar(stage));
@@ -742,6 +801,13 @@ static const bool g_disable_prefetch = [] {
   const char* e = getenv("MSR_TC_PREFETCH");
   return !(e != nullptr && e[0] == '1');
 }();
+// MSR_TC_STRIP: 0 = off, 1 (default) = on; 2 = on AND the start row's phase in the descriptor base-offset field (measured
+// on B200: wrong results -- the 128B swizzle is a pure function of the shared-memory address bits, so shifted starts
+// need no base offset)
+static const int g_strip_mode = [] {
+  const char* e = getenv("MSR_TC_STRIP");
+  return e != nullptr ? atoi(e) : 1;
+}();
 static const bool g_disable_pairs = [] {
   const char* e = getenv("MSR_TC_PAIRS");
   return e != nullptr && e[0] == '0';
@@ -755,6 +821,7 @@ struct ConvTC {
   tc::EpiParams ep;
   int bn;
   int ctas;   // 1, or 2 = CTA pairs (cluster launch)
+  int strip;  // 1 = strip mode (one 130-pixel input strip serves the three kx taps)
   int grid;
 };
 
@@ -793,14 +860,18 @@ int conv_tc_plan_create(ConvTC** out, const ConvTCArgs& a) {
   p->ctas = (p->bn >= 128 && g.n_tiles_m % 2 == 0 && (g.n_tiles_m / 2) * g.n_tiles_n >= 74 && k_chunks >= 8 &&
              !g_disable_pairs) ? 2 : 1;
   const int rin = a.r * a.stride;
+  // strip mode: 3x3 stride-1 convolutions whose M tile is 128 pixels of one image row, on CTA pairs
+  p->strip = (g_strip_mode != 0 && p->ctas == 2 && a.taps == 9 && a.stride == 1 && a.pad == 1 && !a.split3 && g.TH == 1 &&
+              g.NB == 1 && g.TW == 128) ? 1 : 0;
+  g.strip_base_offset = (g_strip_mode == 2) ? 1 : 0;
 
   // A: 4-D NHWC tensor {C, W, H, N}; a stride-2 convolution walks W and H with element stride 2
   {
     const cuuint64_t ca = (cuuint64_t)a.cin * (a.split3 ? 2 : 1);
     cuuint64_t dims[4] = {ca, (cuuint64_t)rin, (cuuint64_t)rin, (cuuint64_t)a.n};
     cuuint64_t strides[3] = {ca * 2, (cuuint64_t)rin * ca * 2, (cuuint64_t)rin * rin * ca * 2};
-    cuuint32_t box[4] = {(cuuint32_t)tc::kBlockK, (cuuint32_t)(g.TW * a.stride), (cuuint32_t)(g.TH * a.stride),
-                         (cuuint32_t)g.NB};
+    cuuint32_t box[4] = {(cuuint32_t)tc::kBlockK, (cuuint32_t)(p->strip ? tc::kStripRows : g.TW * a.stride),
+                         (cuuint32_t)(g.TH * a.stride), (cuuint32_t)g.NB};
     cuuint32_t estr[4] = {1, (cuuint32_t)a.stride, (cuuint32_t)a.stride, 1};
     CUresult r = enc(&p->map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(a.x), dims, strides, box,
                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -877,19 +948,23 @@ int conv_tc_plan_create(ConvTC** out, const ConvTCArgs& a) {
   else p->grid = std::min(g.n_tiles_m * g.n_tiles_n, sms);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e1 = cudaFuncSetAttribute(tc::conv3x3_tc_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e1 = cudaFuncSetAttribute(tc::conv3x3_tc_kernel<128, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           tc::Cfg<128, 1>::kSmemBytes);
-    cudaError_t e2 = cudaFuncSetAttribute(tc::conv3x3_tc_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e2 = cudaFuncSetAttribute(tc::conv3x3_tc_kernel<256, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           tc::Cfg<256, 1>::kSmemBytes);
-    cudaError_t e3 = cudaFuncSetAttribute(tc::conv3x3_tc_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e3 = cudaFuncSetAttribute(tc::conv3x3_tc_kernel<64, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           tc::Cfg<64, 1>::kSmemBytes);
-    cudaError_t e4 = cudaFuncSetAttribute(tc::conv3x3_tc_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e4 = cudaFuncSetAttribute(tc::conv3x3_tc_kernel<32, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           tc::Cfg<32, 1>::kSmemBytes);
-    cudaError_t e5 = cudaFuncSetAttribute(tc::conv3x3_tc_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e5 = cudaFuncSetAttribute(tc::conv3x3_tc_kernel<128, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           tc::Cfg<128, 2>::kSmemBytes);
-    cudaError_t e6 = cudaFuncSetAttribute(tc::conv3x3_tc_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e6 = cudaFuncSetAttribute(tc::conv3x3_tc_kernel<256, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           tc::Cfg<256, 2>::kSmemBytes);
-    for (cudaError_t ee : {e1, e2, e3, e4, e5, e6})
+    cudaError_t e7 = cudaFuncSetAttribute(tc::conv3x3_tc_kernel<128, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          tc::Cfg<128, 2, true>::kSmemBytes);
+    cudaError_t e8 = cudaFuncSetAttribute(tc::conv3x3_tc_kernel<256, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          tc::Cfg<256, 2, true>::kSmemBytes);
+    for (cudaError_t ee : {e1, e2, e3, e4, e5, e6, e7, e8})
       if (ee != cudaSuccess) {
         delete p;
         return fail(MSR_E_CUDA, std::string("conv_tc: cudaFuncSetAttribute: ") + cudaGetErrorString(ee));
@@ -915,26 +990,32 @@ int conv_tc_launch(const ConvTC* p, cudaStream_t st) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (p->bn == 256) {
+    if (p->strip && p->bn == 256) {
+      cfg.dynamicSmemBytes = tc::Cfg<256, 2, true>::kSmemBytes;
+      MSR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc::conv3x3_tc_kernel<256, 2, true>, p->map_a, p->map_b, p->map_p, p->g, p->ep));
+    } else if (p->strip) {
+      cfg.dynamicSmemBytes = tc::Cfg<128, 2, true>::kSmemBytes;
+      MSR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc::conv3x3_tc_kernel<128, 2, true>, p->map_a, p->map_b, p->map_p, p->g, p->ep));
+    } else if (p->bn == 256) {
       cfg.dynamicSmemBytes = tc::Cfg<256, 2>::kSmemBytes;
-      MSR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc::conv3x3_tc_kernel<256, 2>, p->map_a, p->map_b, p->map_p, p->g, p->ep));
+      MSR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc::conv3x3_tc_kernel<256, 2, false>, p->map_a, p->map_b, p->map_p, p->g, p->ep));
     } else {
       cfg.dynamicSmemBytes = tc::Cfg<128, 2>::kSmemBytes;
-      MSR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc::conv3x3_tc_kernel<128, 2>, p->map_a, p->map_b, p->map_p, p->g, p->ep));
+      MSR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc::conv3x3_tc_kernel<128, 2, false>, p->map_a, p->map_b, p->map_p, p->g, p->ep));
     }
   } else {
     switch (p->bn) {
       case 256:
-        tc::conv3x3_tc_kernel<256, 1><<<p->grid, tc::kThreads, tc::Cfg<256, 1>::kSmemBytes, st>>>(p->map_a, p->map_b, p->map_p, p->g, p->ep);
+        tc::conv3x3_tc_kernel<256, 1, false><<<p->grid, tc::kThreads, tc::Cfg<256, 1>::kSmemBytes, st>>>(p->map_a, p->map_b, p->map_p, p->g, p->ep);
         break;
       case 128:
-        tc::conv3x3_tc_kernel<128, 1><<<p->grid, tc::kThreads, tc::Cfg<128, 1>::kSmemBytes, st>>>(p->map_a, p->map_b, p->map_p, p->g, p->ep);
+        tc::conv3x3_tc_kernel<128, 1, false><<<p->grid, tc::kThreads, tc::Cfg<128, 1>::kSmemBytes, st>>>(p->map_a, p->map_b, p->map_p, p->g, p->ep);
         break;
       case 64:
-        tc::conv3x3_tc_kernel<64, 1><<<p->grid, tc::kThreads, tc::Cfg<64, 1>::kSmemBytes, st>>>(p->map_a, p->map_b, p->map_p, p->g, p->ep);
+        tc::conv3x3_tc_kernel<64, 1, false><<<p->grid, tc::kThreads, tc::Cfg<64, 1>::kSmemBytes, st>>>(p->map_a, p->map_b, p->map_p, p->g, p->ep);
         break;
       default:
-        tc::conv3x3_tc_kernel<32, 1><<<p->grid, tc::kThreads, tc::Cfg<32, 1>::kSmemBytes, st>>>(p->map_a, p->map_b, p->map_p, p->g, p->ep);
+        tc::conv3x3_tc_kernel<32, 1, false><<<p->grid, tc::kThreads, tc::Cfg<32, 1>::kSmemBytes, st>>>(p->map_a, p->map_b, p->map_p, p->g, p->ep);
     }
   }
   count_launch();
