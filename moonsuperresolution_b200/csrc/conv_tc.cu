@@ -296,7 +296,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int bn, int m = kBlockM) {
 }
 
 // ---- the kernel -------------------------------------------------------------------------------------------------------
-template <int BN, int CTAS, bool STRIP>
+template <int BN, int CTAS, bool STRIP, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                   const __grid_constant__ CUtensorMap map_p, const Geometry g, const EpiParams ep) {
@@ -560,7 +560,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       if (timed) ep.dbg[blockIdx.x * 8 + 5] += clock64() - tw0;
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
-      if (ep.mode == TC_EPI_BIAS_F32) {
+      if constexpr (EPI == TC_EPI_BIAS_F32) {
         int64_t res_row = 0;
         if (ep.res != nullptr) {
           const int rs = g.r >> ep.res_shift;
@@ -612,8 +612,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             ep.stat_pairs[((int64_t)mt * 4 + quarter) * g.ncols + col + lane] = make_float2(sum, sq);
           }
         }
-      } else if (ep.mode == TC_EPI_ACT_BF16) {
-        // out_bf16 = act(acc + bias (+ residual)), NHWC bf16: the A operand of a following convolution
+      } else if constexpr (EPI == TC_EPI_ACT_BF16) {
+        // out_bf16 = act(acc + bias (+ residual)), NHWC bf16: the A operand of a following convolution.  The optional
+        // steps are whole loops behind warp-uniform branches (no predicated-off instructions in the issue stream: the
+        // epilogue warps are instruction-latency bound).
         int64_t res_row = 0;
         if (ep.res != nullptr) {
           const int rs = g.r >> ep.res_shift;
@@ -626,60 +628,62 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           tmem_ld_wait();
           if (row_ok) {
             const int col = n0 + c0;
-            const float* rs_ptr = ep.res ? ep.res + res_row * g.ncols + col : nullptr;
-            __align__(16) __nv_bfloat16 ob[32];
+            float o[32];
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                     __uint_as_float(v[j + 3]));
-              if (ep.bias) {
+            for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(v[j]);
+            if (ep.bias != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
                 const float4 bb = __ldg(reinterpret_cast<const float4*>(ep.bias + col + j));
-                o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+                o[j] += bb.x; o[j + 1] += bb.y; o[j + 2] += bb.z; o[j + 3] += bb.w;
               }
-              if (rs_ptr) {
-                const float4 rr = __ldg(reinterpret_cast<const float4*>(rs_ptr + j));
-                o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
-              }
-              if (ep.act == ACT_RELU) {
-                o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
-              } else if (ep.act == ACT_LRELU) {
-                o.x = o.x > 0.f ? o.x : o.x * ep.slope; o.y = o.y > 0.f ? o.y : o.y * ep.slope;
-                o.z = o.z > 0.f ? o.z : o.z * ep.slope; o.w = o.w > 0.f ? o.w : o.w * ep.slope;
-              }
-              ob[j] = __float2bfloat16_rn(o.x); ob[j + 1] = __float2bfloat16_rn(o.y);
-              ob[j + 2] = __float2bfloat16_rn(o.z); ob[j + 3] = __float2bfloat16_rn(o.w);
             }
-            if (!ep.split_out) {
-              __nv_bfloat16* dst = ep.out_bf16 + m * g.ncols + col;
-              const uint32_t* src = reinterpret_cast<const uint32_t*>(ob);
+            if (ep.res != nullptr) {
+              const float* rs_ptr = ep.res + res_row * g.ncols + col;
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                float rr[8];
+                ld_global_nc_v8(rs_ptr + j, rr);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) o[j + q] += rr[q];
+              }
+            }
+            if (ep.act == ACT_RELU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) o[j] = fmaxf(o[j], 0.f);
+            } else if (ep.act == ACT_LRELU) {
+              const float sl = ep.slope;   // 0 < slope < 1: leaky_relu(x) = max(x, slope * x)
+#pragma unroll
+              for (int j = 0; j < 32; ++j) o[j] = fmaxf(o[j], o[j] * sl);
+            }
+            uint32_t pk[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const __nv_bfloat162 t2 = __floats2bfloat162_rn(o[2 * j], o[2 * j + 1]);
+              pk[j] = *reinterpret_cast<const uint32_t*>(&t2);
+            }
+            const int64_t pitch = ep.split_out ? 2 * (int64_t)g.ncols : (int64_t)g.ncols;
+            __nv_bfloat16* dst = ep.out_bf16 + m * pitch + col;
+#pragma unroll
+            for (int q = 0; q < 2; ++q)
+              st_global_v8(dst + 16 * q, pk[8 * q], pk[8 * q + 1], pk[8 * q + 2], pk[8 * q + 3], pk[8 * q + 4],
+                           pk[8 * q + 5], pk[8 * q + 6], pk[8 * q + 7]);
+            if (ep.split_out) {   // lo half of a split-bf16 operand: v - bf16(v)
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&pk[j]);
+                const float2 hf = __bfloat1622float2(h2);
+                const __nv_bfloat162 l2 = __floats2bfloat162_rn(o[2 * j] - hf.x, o[2 * j + 1] - hf.y);
+                pk[j] = *reinterpret_cast<const uint32_t*>(&l2);
+              }
 #pragma unroll
               for (int q = 0; q < 2; ++q)
-                st_global_v8(dst + 16 * q, src[8 * q], src[8 * q + 1], src[8 * q + 2], src[8 * q + 3], src[8 * q + 4],
-                             src[8 * q + 5], src[8 * q + 6], src[8 * q + 7]);
-            } else {
-              uint4* dst = reinterpret_cast<uint4*>(ep.out_bf16 + m * 2 * g.ncols + col);
-              const uint4* src = reinterpret_cast<const uint4*>(ob);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) dst[q] = src[q];
-              // lo half: recompute the activation value and subtract its bf16 rounding
-              __align__(16) __nv_bfloat16 lb[32];
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                float o = __uint_as_float(v[j]);
-                if (ep.bias) o += __ldg(ep.bias + col + j);
-                if (rs_ptr) o += __ldg(rs_ptr + j);
-                if (ep.act == ACT_RELU) o = fmaxf(o, 0.f);
-                else if (ep.act == ACT_LRELU) o = o > 0.f ? o : o * ep.slope;
-                lb[j] = __float2bfloat16_rn(o - __bfloat162float(ob[j]));
-              }
-              uint4* dl = reinterpret_cast<uint4*>(ep.out_bf16 + m * 2 * g.ncols + g.ncols + col);
-              const uint4* sl = reinterpret_cast<const uint4*>(lb);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) dl[q] = sl[q];
+                st_global_v8(dst + g.ncols + 16 * q, pk[8 * q], pk[8 * q + 1], pk[8 * q + 2], pk[8 * q + 3], pk[8 * q + 4],
+                             pk[8 * q + 5], pk[8 * q + 6], pk[8 * q + 7]);
             }
           }
         }
-      } else if (ep.mode == TC_EPI_PHASE_F32) {
+      } else if constexpr (EPI == TC_EPI_PHASE_F32) {
         // final generator layer as a 3x3 convolution to 4 sub-pixel phases (columns 0..3 = (py, px)) + pixel shuffle:
         // y[b][2h + py][2w + px] = acc[py*2 + px] + bias[0]
         uint32_t v[32];
@@ -861,8 +865,9 @@ int conv_tc_plan_create(ConvTC** out, const ConvTCArgs& a) {
              !g_disable_pairs) ? 2 : 1;
   const int rin = a.r * a.stride;
   // strip mode: 3x3 stride-1 convolutions whose M tile is 128 pixels of one image row, on CTA pairs
-  p->strip = (g_strip_mode != 0 && p->ctas == 2 && a.taps == 9 && a.stride == 1 && a.pad == 1 && !a.split3 && g.TH == 1 &&
-              g.NB == 1 && g.TW == 128) ? 1 : 0;
+  // (single-CTA strip tiles exist only for the final sub-pixel layer, whose 32-column tiles are A-traffic bound)
+  p->strip = (g_strip_mode != 0 && (p->ctas == 2 || a.epilogue == TC_EPI_PHASE_F32) && a.taps == 9 && a.stride == 1 &&
+              a.pad == 1 && !a.split3 && g.TH == 1 && g.NB == 1 && g.TW == 128) ? 1 : 0;
   g.strip_base_offset = (g_strip_mode == 2) ? 1 : 0;
 
   // A: 4-D NHWC tensor {C, W, H, N}; a stride-2 convolution walks W and H with element stride 2
@@ -946,78 +951,75 @@ int conv_tc_plan_create(ConvTC** out, const ConvTCArgs& a) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (p->ctas == 2) p->grid = 2 * std::min((g.n_tiles_m / 2) * g.n_tiles_n, sms / 2);
   else p->grid = std::min(g.n_tiles_m * g.n_tiles_n, sms);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e1 = cudaFuncSetAttribute(tc::conv3x3_tc_kernel<128, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          tc::Cfg<128, 1>::kSmemBytes);
-    cudaError_t e2 = cudaFuncSetAttribute(tc::conv3x3_tc_kernel<256, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          tc::Cfg<256, 1>::kSmemBytes);
-    cudaError_t e3 = cudaFuncSetAttribute(tc::conv3x3_tc_kernel<64, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          tc::Cfg<64, 1>::kSmemBytes);
-    cudaError_t e4 = cudaFuncSetAttribute(tc::conv3x3_tc_kernel<32, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          tc::Cfg<32, 1>::kSmemBytes);
-    cudaError_t e5 = cudaFuncSetAttribute(tc::conv3x3_tc_kernel<128, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          tc::Cfg<128, 2>::kSmemBytes);
-    cudaError_t e6 = cudaFuncSetAttribute(tc::conv3x3_tc_kernel<256, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          tc::Cfg<256, 2>::kSmemBytes);
-    cudaError_t e7 = cudaFuncSetAttribute(tc::conv3x3_tc_kernel<128, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          tc::Cfg<128, 2, true>::kSmemBytes);
-    cudaError_t e8 = cudaFuncSetAttribute(tc::conv3x3_tc_kernel<256, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          tc::Cfg<256, 2, true>::kSmemBytes);
-    for (cudaError_t ee : {e1, e2, e3, e4, e5, e6, e7, e8})
-      if (ee != cudaSuccess) {
-        delete p;
-        return fail(MSR_E_CUDA, std::string("conv_tc: cudaFuncSetAttribute: ") + cudaGetErrorString(ee));
-      }
-    attr_set = true;
-  }
   *out = p;
   return MSR_OK;
+}
+
+// one instantiation per (tile width, CTAs per tile, strip mode, epilogue) that the graphs actually use
+template <int BN, int CTAS, bool STRIP, int EPI>
+static int launch_variant(const ConvTC* p, cudaStream_t st) {
+  using C = tc::Cfg<BN, CTAS, STRIP>;
+  auto kernel = tc::conv3x3_tc_kernel<BN, CTAS, STRIP, EPI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MSR_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(p->grid);
+  cfg.blockDim = dim3(tc::kThreads);
+  cfg.dynamicSmemBytes = C::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CTAS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CTAS == 2 ? 1 : 0;
+  MSR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, p->map_a, p->map_b, p->map_p, p->g, p->ep));
+  return MSR_OK;
+}
+
+template <int BN, int EPI>
+static int launch_schedule(const ConvTC* p, cudaStream_t st) {
+  if constexpr (BN >= 128 && EPI != TC_EPI_PHASE_F32) {
+    if (p->ctas == 2 && p->strip) return launch_variant<BN, 2, true, EPI>(p, st);
+    if (p->ctas == 2) return launch_variant<BN, 2, false, EPI>(p, st);
+  }
+  if constexpr (EPI == TC_EPI_PHASE_F32) {
+    if (p->strip) return launch_variant<BN, 1, true, EPI>(p, st);
+  }
+  return launch_variant<BN, 1, false, EPI>(p, st);
+}
+
+template <int EPI>
+static int launch_width(const ConvTC* p, cudaStream_t st) {
+  if constexpr (EPI == TC_EPI_PHASE_F32) {
+    return launch_schedule<32, EPI>(p, st);
+  } else if constexpr (EPI == TC_EPI_SPADE_BF16) {
+    return p->bn == 256 ? launch_schedule<256, EPI>(p, st) : launch_schedule<128, EPI>(p, st);
+  } else {
+    switch (p->bn) {
+      case 256: return launch_schedule<256, EPI>(p, st);
+      case 128: return launch_schedule<128, EPI>(p, st);
+      case 64: return launch_schedule<64, EPI>(p, st);
+      default: return launch_schedule<32, EPI>(p, st);
+    }
+  }
 }
 
 int conv_tc_launch(const ConvTC* p, cudaStream_t st) {
   MSR_REQUIRE(p, "conv_tc_launch: null plan");
   ProfileScope prof(MSR_PROF_CONV_TC, st, 2.0 * (double)p->g.n * p->g.r * p->g.r * p->g.ncols * p->g.taps * p->g.cin);
-  if (p->ctas == 2) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(p->grid);
-    cfg.blockDim = dim3(tc::kThreads);
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    if (p->strip && p->bn == 256) {
-      cfg.dynamicSmemBytes = tc::Cfg<256, 2, true>::kSmemBytes;
-      MSR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc::conv3x3_tc_kernel<256, 2, true>, p->map_a, p->map_b, p->map_p, p->g, p->ep));
-    } else if (p->strip) {
-      cfg.dynamicSmemBytes = tc::Cfg<128, 2, true>::kSmemBytes;
-      MSR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc::conv3x3_tc_kernel<128, 2, true>, p->map_a, p->map_b, p->map_p, p->g, p->ep));
-    } else if (p->bn == 256) {
-      cfg.dynamicSmemBytes = tc::Cfg<256, 2>::kSmemBytes;
-      MSR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc::conv3x3_tc_kernel<256, 2, false>, p->map_a, p->map_b, p->map_p, p->g, p->ep));
-    } else {
-      cfg.dynamicSmemBytes = tc::Cfg<128, 2>::kSmemBytes;
-      MSR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc::conv3x3_tc_kernel<128, 2, false>, p->map_a, p->map_b, p->map_p, p->g, p->ep));
-    }
-  } else {
-    switch (p->bn) {
-      case 256:
-        tc::conv3x3_tc_kernel<256, 1, false><<<p->grid, tc::kThreads, tc::Cfg<256, 1>::kSmemBytes, st>>>(p->map_a, p->map_b, p->map_p, p->g, p->ep);
-        break;
-      case 128:
-        tc::conv3x3_tc_kernel<128, 1, false><<<p->grid, tc::kThreads, tc::Cfg<128, 1>::kSmemBytes, st>>>(p->map_a, p->map_b, p->map_p, p->g, p->ep);
-        break;
-      case 64:
-        tc::conv3x3_tc_kernel<64, 1, false><<<p->grid, tc::kThreads, tc::Cfg<64, 1>::kSmemBytes, st>>>(p->map_a, p->map_b, p->map_p, p->g, p->ep);
-        break;
-      default:
-        tc::conv3x3_tc_kernel<32, 1, false><<<p->grid, tc::kThreads, tc::Cfg<32, 1>::kSmemBytes, st>>>(p->map_a, p->map_b, p->map_p, p->g, p->ep);
-    }
+  int rc;
+  switch (p->ep.mode) {
+    case TC_EPI_BIAS_F32: rc = launch_width<TC_EPI_BIAS_F32>(p, st); break;
+    case TC_EPI_SPADE_BF16: rc = launch_width<TC_EPI_SPADE_BF16>(p, st); break;
+    case TC_EPI_ACT_BF16: rc = launch_width<TC_EPI_ACT_BF16>(p, st); break;
+    default: rc = launch_width<TC_EPI_PHASE_F32>(p, st);
   }
+  if (rc) return rc;
   count_launch();
   MSR_LAUNCH_CHECK();
   return MSR_OK;
