@@ -99,6 +99,7 @@ class DEMSuperResolution:
         self.model_launches = 0
         self.slots_executed = 0
         self._weights_dev = None
+        self._host_out = None
 
     # ---------------------------------------------------------------------------------------------------------------
     # inputs
@@ -508,9 +509,19 @@ class DEMSuperResolution:
                       if isinstance(self.geo_transform, dict) else None, nodata=self.no_value)
 
     def results(self):
-        """(mean f32, std f32, good u8) of this rank's band as numpy arrays plus the band's first raster row."""
-        _torch().cuda.current_stream().synchronize()
-        return self.mean_out.cpu().numpy(), self.std_out.cpu().numpy(), self.good_out.cpu().numpy(), self._out_r0
+        """(mean f32, std f32, good u8) of this rank's band as numpy arrays plus the band's first raster row.  The arrays
+        are views of pinned host buffers owned by the engine (reused by the next call; copy them to keep them)."""
+        torch = _torch()
+        outs = []
+        for k, t in enumerate((self.mean_out, self.std_out, self.good_out)):
+            buf = self._host_out[k] if self._host_out is not None else None
+            if buf is None or buf.shape != t.shape or buf.dtype != t.dtype:
+                buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            buf.copy_(t, non_blocking=True)
+            outs.append(buf)
+        self._host_out = outs
+        torch.cuda.current_stream().synchronize()
+        return outs[0].numpy(), outs[1].numpy(), outs[2].numpy(), self._out_r0
 
     def gatherResults(self):
         """Full (H, W) rasters on rank 0 (None elsewhere).  Bands are disjoint row ranges, so this is a plain
