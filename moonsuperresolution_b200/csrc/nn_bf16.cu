@@ -161,12 +161,114 @@ static int dense_small_m(const float* x, const WT* w, const float* bias, float* 
   return MSR_OK;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Dense layer for 16 < M <= 128 rows (several batches per generator call): a split-K SGEMM whose 128 x 128 block tile
+// covers ALL rows, so every weight is read from HBM exactly once.  256 threads, 8 x 8 outputs per thread.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kGM = 128, kGN = 128, kGK = 16;
+
+__global__ void __launch_bounds__(256) dense_gemm_partial_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                 const float* __restrict__ bias, float* __restrict__ dst,
+                                                                 int M, int K, int N, int kchunk, int direct) {
+  __shared__ float xs[kGK][kGM + 4];
+  __shared__ float ws[kGK][kGN + 4];
+  const int t = threadIdx.x, ty = t >> 4, tx = t & 15;
+  const int n0 = blockIdx.x * kGN, split = blockIdx.y;
+  const int k0 = split * kchunk, k1 = min(K, k0 + kchunk);
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  // loader roles: x tile = 128 rows x 16 k (thread -> row t >> 1, 8 consecutive k); w tile = 16 k x 128 cols
+  const int xr = t >> 1, xk = (t & 1) * 8;
+  const int wk = t >> 4, wc = (t & 15) * 8;
+  for (int kb = k0; kb < k1; kb += kGK) {
+    float xv[8], wv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = kb + xk + j;
+      xv[j] = (xr < M && k < k1) ? __ldg(x + (int64_t)xr * K + k) : 0.f;
+    }
+    {
+      const int k = kb + wk;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) wv[j] = (k < k1 && n0 + wc + j < N) ? __ldg(w + (int64_t)k * N + n0 + wc + j) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) xs[xk + j][xr] = xv[j];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ws[wk][wc + j] = wv[j];
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < kGK; ++kk) {
+      float a[8], b[8];
+      const float4 a0 = *reinterpret_cast<const float4*>(&xs[kk][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&xs[kk][ty * 8 + 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&ws[kk][tx * 8]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&ws[kk][tx * 8 + 4]);
+      a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+      b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = ty * 8 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = n0 + tx * 8 + j;
+      if (n >= N) continue;
+      if (direct) dst[(int64_t)m * N + n] = acc[i][j] + (bias ? bias[n] : 0.f);
+      else dst[((int64_t)split * M + m) * N + n] = acc[i][j];
+    }
+  }
+}
+
+static int dense_gemm_m128(const float* x, const float* w, const float* bias, float* out, int M, int K, int N,
+                           float* partial, int64_t partial_capacity, cudaStream_t st) {
+  ProfileScope prof(MSR_PROF_DENSE, st, 2.0 * M * (double)K * N, 2);
+  const int gx = ceil_div(N, kGN);
+  int ksplit = std::max(1, std::min(ceil_div(K, 4 * kGK), (2 * 148) / gx));
+  while ((int64_t)ksplit * M * N > partial_capacity && ksplit > 1) --ksplit;
+  int kchunk = ceil_div(ceil_div(K, ksplit), kGK) * kGK;
+  ksplit = ceil_div(K, kchunk);
+  if (ksplit == 1) {
+    dense_gemm_partial_kernel<<<dim3(gx, 1), 256, 0, st>>>(x, w, bias, out, M, K, N, kchunk, 1);
+    MSR_LAUNCH_CHECK();
+    count_launch();
+    return MSR_OK;
+  }
+  MSR_REQUIRE((int64_t)ksplit * M * N <= partial_capacity, "dense: partial scratch too small");
+  dense_gemm_partial_kernel<<<dim3(gx, ksplit), 256, 0, st>>>(x, w, nullptr, partial, M, K, N, kchunk, 0);
+  MSR_LAUNCH_CHECK();
+  dense_bf16w_reduce_kernel<<<ceil_div((int64_t)M * N, 256), 256, 0, st>>>(partial, bias, out, M, N, ksplit);
+  MSR_LAUNCH_CHECK();
+  count_launch(2);
+  return MSR_OK;
+}
+
 int dense_bf16w(const float* x, const __nv_bfloat16* w, const float* bias, float* out, int M, int K, int N,
                 float* partial, int64_t partial_capacity, cudaStream_t st) {
   return dense_small_m<__nv_bfloat16>(x, w, bias, out, M, K, N, partial, partial_capacity, st);
 }
 int dense_f32w(const float* x, const float* w, const float* bias, float* out, int M, int K, int N, float* partial,
                int64_t partial_capacity, cudaStream_t st) {
+  MSR_REQUIRE(x && w && out && partial && M > 0 && K > 0 && N > 0, "dense: bad arguments");
+  if (M > 16) {   // several batches per call: all rows share one pass over the weights (chunks of 128 rows)
+    for (int m0 = 0; m0 < M; m0 += kGM) {
+      const int rows = std::min(kGM, M - m0);
+      int rc = dense_gemm_m128(x + (int64_t)m0 * K, w, bias, out + (int64_t)m0 * N, rows, K, N, partial,
+                               partial_capacity, st);
+      if (rc) return rc;
+    }
+    return MSR_OK;
+  }
   return dense_small_m<float>(x, w, bias, out, M, K, N, partial, partial_capacity, st);
 }
 

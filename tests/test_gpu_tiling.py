@@ -156,6 +156,20 @@ def test_band_sharding_is_bit_identical(msr, world):
         np.testing.assert_array_equal(got, full[k])
 
 
+def test_large_tile_size_matches_oracle(msr):
+    """tile_size is a free parameter of the reference (process_full_tiles.py:58,104-106): one 2048-pixel tile covers the
+    whole raster here, so no halo patch is generated twice; still bit-exact against the oracle with the same T."""
+    case = dict(H=1100, W=1500, I=64, S=16, B=16, T=2048, NV=-32768.0, model="wobble", seed=7, holes=True)
+    dem, img = golden_inputs.make_rasters(case)
+    eng = engine_for(msr, case, toy_models.wobble)
+    mean, std, good = eng.run(dem, img)
+    with np.errstate(all="ignore"):
+        ref = OT.process_map(dem, img, case["I"], case["S"], case["B"], case["T"], case["NV"], toy_models.wobble)
+    np.testing.assert_array_equal(good, ref[2])
+    np.testing.assert_array_equal(mean, ref[0])
+    np.testing.assert_array_equal(std, ref[1])
+
+
 def test_save_tiles_and_geotiff_layout(msr, tmp_path):
     """Output layout of saveTile / saveGTiff (process_full_tiles.py:416-429, 481-531): names, dtypes, NoData."""
     from moonsuperresolution_b200 import geotiff
