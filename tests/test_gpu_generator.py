@@ -202,10 +202,10 @@ def test_spade_generator_bf16_tensor_core_mode(msr, arch, i, b):
     assert err <= TOL_BF16 * max(1.0, np.abs(want).max()), err
 
 
-@pytest.mark.parametrize("b,precision,atol", [(2, "fp32", 1e-6), (9, "fp32", 1e-5), (9, "bf16", 1e-5)])
+@pytest.mark.parametrize("b,precision,atol", [(2, "fp32", 1e-6), (9, "fp32", 1e-5), (9, "bf16", 5e-3)])
 def test_groups_have_independent_batch_statistics(msr, torch, b, precision, atol):
     """Two batches pushed through one forward call (max_groups = 2) equal two separate calls (b = 9: 18 rows go through
-    the many-row dense kernel)."""
+    the many-row dense kernel, whose different summation order flips a few bf16 roundings downstream)."""
     i = 64
     w = W.random_init("cnn", i, seed=3)
     x, _ = inputs(i, 2 * b, seed=2)
