@@ -29,7 +29,7 @@ from typing import Dict, List, Optional, Tuple
 import numpy as np
 
 from . import _lib
-from .models import _Generator
+from .models import IdentityModel, _Generator
 from .distributed import band_of_rank, gather_bands
 from .planner import PAD_SLOT, Plan
 
@@ -413,7 +413,7 @@ class DEMSuperResolution:
         d_key_xy = torch.from_numpy(key_xy).to(dev, non_blocking=True)
         d_lattice = torch.from_numpy(tp["lattice"]).to(dev, non_blocking=True)
         minmax = torch.empty((slots, 4), dtype=torch.float32, device=dev)
-        device_model = isinstance(self.model, _Generator)
+        device_model = isinstance(self.model, (_Generator, IdentityModel))
         if device_model:
             groups = self._groups_cfg or self.model.max_groups
             groups = max(1, min(groups, self.model.max_groups))

@@ -168,6 +168,26 @@ class _Generator:
             pass
 
 
+class IdentityModel:
+    """The reference's default plug-in ``lambda x, training=False: x`` (process_full_tiles.py:139-143) with a device
+    entry point, so that the identity round trip -- the reference's own built-in check that the tiling / blending code
+    reproduces the input DEM -- runs at full raster sizes without a host round trip per batch.  Channel -1 of the input
+    (the normalised DEM) is the prediction; the ``+ 0.5`` of processBatch (:340) is applied by the blend kernel as for
+    every device model."""
+    arch = "identity"
+    max_groups = 64
+
+    def __init__(self, image_size: int, batch_size: int):
+        self.image_size, self.batch_size = int(image_size), int(batch_size)
+        self.last_launch_count = 1
+
+    def __call__(self, x, training=False):
+        return x
+
+    def forward_device(self, source, out, eps=None, n_groups: int = 1, stream=None) -> None:
+        out.view(source.shape[0], self.image_size, self.image_size).copy_(source[..., 1])
+
+
 class GauGAN(_Generator):
     """GauGAN(image_size, batch_size, latent_dim) -- inference ``call`` only: encoder -> Gaussian sampler ->
     SPADE generator (spade/models/model.py:340-350, 564-567)."""

@@ -170,6 +170,34 @@ def test_large_tile_size_matches_oracle(msr):
     np.testing.assert_array_equal(std, ref[1])
 
 
+def test_full_size_identity_round_trip(msr, torch):
+    """BASELINE.json configs[2] geometry (8192 x 8192, I = 512, S = 128, B = 16, T = 1024) with the reference's identity
+    model: size-independent properties instead of an element-wise oracle (which would take hours on the CPU):
+    the blended mean reproduces the DEM wherever good == 1, std ~ 0, `good` is exactly the rectangle
+    [purge, last patch end - purge), everything else is no_value."""
+    h = w = 8192
+    i, s_, b, t = 512, 128, 16, 1024
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    dem = (torch.cumsum(torch.randn((h, w), generator=gen, device="cuda"), 1) * 3.0 + 1500.0).contiguous()
+    img = (torch.rand((h, w), generator=gen, device="cuda") * 254.0 + 1.0).contiguous()
+    cfg = msr.DSRConfig(image_size=i, stride=s_, batch_size=b, tile_size=t)
+    eng = msr.DEMSuperResolution(cfg, model=msr.IdentityModel(i, b))
+    eng.setRasters(dem, img)
+    eng.padInputs()
+    eng.processTiles()
+    assert eng.slots_executed == 7168                       # SURVEY.md App. D: 6724 valid patches, 7168 slots
+    good = eng.good_out.bool()
+    p = i // 16
+    last = ((h - i) // s_) * s_ + i - p
+    want = torch.zeros((h, w), dtype=torch.bool, device="cuda")
+    want[p:last, p:last] = True
+    assert torch.equal(good, want)
+    err = (eng.mean_out - dem).abs()[good].max().item()
+    assert err <= 2e-3, err                                  # float32 rounding of (v - lo) / (hi - lo) * (hi - lo) + lo
+    assert eng.std_out[good].max().item() <= 2e-3 and eng.std_out[good].min().item() >= 0.0
+    assert (eng.mean_out[~good] == cfg.no_value).all() and (eng.std_out[~good] == cfg.no_value).all()
+
+
 def test_save_tiles_and_geotiff_layout(msr, tmp_path):
     """Output layout of saveTile / saveGTiff (process_full_tiles.py:416-429, 481-531): names, dtypes, NoData."""
     from moonsuperresolution_b200 import geotiff
