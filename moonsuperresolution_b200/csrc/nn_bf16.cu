@@ -12,42 +12,44 @@ namespace msr {
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) source_patches_kernel(const float* __restrict__ src, int I,
                                                              __nv_bfloat16* __restrict__ out, int n, int r, int mode) {
-  // 8 threads per output pixel, each writes one 16-byte piece of the 128-byte row (coalesced 128-byte rows per 8 lanes).
-  // split-bf16 operand: channels [0,18) = hi, [18,36) = hi again, [36,54) = lo (v = hi + lo to ~2^-17), rest zero; the
-  // matching weight rows are [w_hi | w_lo | w_hi], so the GEMM evaluates a_hi*w_hi + a_hi*w_lo + a_lo*w_hi ~ fp32 product
-  const int64_t total = (int64_t)n * r * r * 8;
+  const int64_t total = (int64_t)n * r * r;
   const int f = I / r, half = f >> 1;
-  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int piece = (int)(e & 7);
-    const int64_t m = e >> 3;
+  for (int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; m < total; m += (int64_t)gridDim.x * blockDim.x) {
     const int nn = (int)(m / ((int64_t)r * r));
     const int rem = (int)(m % ((int64_t)r * r));
     const int h = rem / r, x = rem % r;
-    __align__(16) __nv_bfloat16 o[8];
+    // split-bf16 operand: channels [0,18) = hi, [18,36) = hi again, [36,54) = lo (v = hi + lo to ~2^-17); the matching
+    // weight rows are [w_hi | w_lo | w_hi], so the GEMM evaluates a_hi*w_hi + a_hi*w_lo + a_lo*w_hi ~ fp32 product
+    __align__(16) __nv_bfloat16 row[64];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int c = piece * 8 + q;          // channel 0..63
-      float v = 0.f;
-      bool lo = false;
-      int k = -1;                            // tap-channel index 0..17
-      if (c < 18) k = c;
-      else if (c < 36) k = c - 18;
-      else if (c < 54) { k = c - 36; lo = true; }
-      if (k >= 0) {
-        const int tap = k >> 1, ch = k & 1, ky = tap / 3, kx = tap - 3 * ky;
+    for (int j = 54; j < 64; ++j) row[j] = __float2bfloat16_rn(0.f);
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        float2 s = make_float2(0.f, 0.f);
         if (mode == 0) {  // resized-mask coordinates, SAME pad (1, 1); nearest resize with half-pixel centres (App. B.3)
           const int hh = h + ky - 1, xx = x + kx - 1;
           if (hh >= 0 && hh < r && xx >= 0 && xx < r)
-            v = __ldg(src + (((int64_t)nn * I + hh * f + half) * I + xx * f + half) * 2 + ch);
+            s = __ldg(reinterpret_cast<const float2*>(src + (((int64_t)nn * I + hh * f + half) * I + xx * f + half) * 2));
         } else {          // stride-2 taps on the full-resolution source, SAME pad (0, 1) (App. B.2)
           const int sy = 2 * h + ky, sx = 2 * x + kx;
-          if (sy < I && sx < I) v = __ldg(src + (((int64_t)nn * I + sy) * I + sx) * 2 + ch);
+          if (sy < I && sx < I) s = __ldg(reinterpret_cast<const float2*>(src + (((int64_t)nn * I + sy) * I + sx) * 2));
         }
+        const int j = (ky * 3 + kx) * 2;
+        const __nv_bfloat16 hx = __float2bfloat16_rn(s.x), hy = __float2bfloat16_rn(s.y);
+        row[j] = hx;
+        row[j + 1] = hy;
+        row[18 + j] = hx;
+        row[18 + j + 1] = hy;
+        row[36 + j] = __float2bfloat16_rn(s.x - __bfloat162float(hx));
+        row[36 + j + 1] = __float2bfloat16_rn(s.y - __bfloat162float(hy));
       }
-      const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-      o[q] = lo ? __float2bfloat16_rn(v - __bfloat162float(hi)) : hi;
     }
-    *reinterpret_cast<uint4*>(out + m * 64 + piece * 8) = *reinterpret_cast<const uint4*>(o);
+    uint4* dst = reinterpret_cast<uint4*>(out + m * 64);
+    const uint4* sp = reinterpret_cast<const uint4*>(row);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) dst[q] = sp[q];
   }
 }
 
@@ -56,7 +58,7 @@ int source_patches_bf16(const float* source, int I, __nv_bfloat16* out, int n, i
   MSR_REQUIRE(mode == 0 || (mode == 1 && r * 2 == I), "source_patches: mode 1 needs r = I / 2");
   const int64_t total = (int64_t)n * r * r;
   ProfileScope prof(MSR_PROF_MASK_CONV, st, (double)total * (128.0 + 8.0));
-  const int blocks = (int)std::min<int64_t>((total * 8 + 255) / 256, 148 * 32);
+  const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 16);
   source_patches_kernel<<<blocks, 256, 0, st>>>(source, I, out, n, r, mode);
   count_launch();
   MSR_LAUNCH_CHECK();
