@@ -113,6 +113,30 @@ int msr_blend_tile(const void* const* d_patch_ptr, const uint8_t* d_patch_f64, c
                    int64_t pitch, int rows, int cols, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Raster container codec (host side, multi-threaded): what GDAL does for the reference when it reads band 1 of the input
+ * GeoTIFFs (process_full_tiles.py:158-182) and writes 'COMPRESS=LZW', 'PREDICTOR=2' GeoTIFFs (:481-531).  The IFD / tags
+ * are handled by moonsuperresolution_b200/geotiff.py; these functions only transform strip / tile bytes.
+ * ------------------------------------------------------------------------------------------------------------- */
+
+/* Upper bound of the LZW output for raw_bytes of input. */
+int64_t msr_tiff_lzw_bound(int64_t raw_bytes);
+
+/* Compress a (rows, row_bytes) host raster as strips of rows_per_strip rows.  compression: 1 none, 5 LZW; predictor: 1
+ * none, 2 horizontal differencing on sample_bytes-wide integers.  h_out holds one slot of slot_bytes per strip; h_sizes
+ * receives the compressed byte count of every strip. */
+int msr_tiff_encode_strips(const uint8_t* h_raster, int64_t row_bytes, int rows, int rows_per_strip, int sample_bytes,
+                           int compression, int predictor, uint8_t* h_out, int64_t slot_bytes, int64_t* h_sizes,
+                           int n_threads);
+
+/* Decode n_chunks strips or tiles of a TIFF file image into a (rows, row_bytes) host raster.  Chunk i occupies file
+ * bytes [offsets[i], offsets[i] + counts[i]), decodes to chunk_rows x chunk_row_bytes and is pasted at raster row
+ * dst_row[i], byte column dst_col[i] (clipped).  compression: 1 none, 5 LZW; predictor: 1, 2 (horizontal), 3 (float). */
+int msr_tiff_decode_chunks(const uint8_t* h_file, int64_t file_bytes, const int64_t* offsets, const int64_t* counts,
+                           const int64_t* dst_row, const int64_t* dst_col, int n_chunks, int chunk_rows,
+                           int64_t chunk_row_bytes, int sample_bytes, int compression, int predictor, uint8_t* h_raster,
+                           int64_t row_bytes, int64_t rows, int n_threads);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Generators  (spade/models/{networks,blocks,spade,sampling}.py, model.py:564-567 / 789-791, pix2pix.py:64-108)
  * ------------------------------------------------------------------------------------------------------------- */
 

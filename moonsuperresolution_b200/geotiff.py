@@ -1,16 +1,21 @@
-"""Minimal TIFF / BigTIFF raster container I/O for the engine's boundary (no GDAL in this stack).
+"""TIFF / BigTIFF raster container I/O for the engine's boundary (no GDAL in this stack).
 
-The reference reads band 1 of two GeoTIFFs with GDAL (process_full_tiles.py:158-182) and writes LZW GeoTIFFs
-(process_full_tiles.py:481-531).  This module covers the container only -- single-band, stripped, uncompressed,
-little-endian, classic TIFF below 4 GiB and BigTIFF above -- and carries the GeoTIFF tags of the input DEM through to
-the outputs verbatim.  Compression (LZW + predictor 2) is a later row of SURVEY.md section 8f.
+The reference reads band 1 of two GeoTIFFs with GDAL (process_full_tiles.py:158-182) and writes
+``COMPRESS=LZW, PREDICTOR=2`` GeoTIFFs (process_full_tiles.py:481-531).  This module handles the container --
+single-band, little-endian, classic TIFF below 4 GiB and BigTIFF above, strips or tiles on read, strips on write -- and
+carries the GeoTIFF tags of the input DEM through to the outputs verbatim.  The byte transforms (LZW, horizontal and
+floating-point predictors) run multi-threaded in libmoonsr.so (csrc/tiff_codec.cu, ``msr_tiff_*``).
 """
 from __future__ import annotations
 
+import ctypes as C
+import os
 import struct
 from typing import Dict, Optional, Tuple
 
 import numpy as np
+
+from . import _lib
 
 # tags carried from the input DEM to the outputs (GeoTIFF + GDAL metadata)
 GEO_TAGS = (33550, 33922, 34264, 34735, 34736, 34737)
@@ -24,26 +29,44 @@ _SAMPLE = {  # numpy dtype -> (SampleFormat, BitsPerSample)
 }
 
 
+def _threads() -> int:
+    return max(1, len(os.sched_getaffinity(0)))
+
+
 def write(path: str, data: np.ndarray, geo: Optional[Dict[int, Tuple[int, int, bytes]]] = None,
-          nodata: Optional[float] = None, rows_per_strip: int = 256) -> None:
-    """Writes a 2-D array as a single-band uncompressed TIFF (BigTIFF when it would not fit in 4 GiB)."""
+          nodata: Optional[float] = None, rows_per_strip: int = 64, compress: str = "lzw", predictor: int = 2) -> None:
+    """Writes a 2-D array as a single-band stripped TIFF (BigTIFF when it would not fit in 4 GiB).  Defaults follow the
+    reference's GDAL options ``COMPRESS=LZW, PREDICTOR=2`` (process_full_tiles.py:521); ``compress="none"`` writes raw
+    strips."""
     a = np.ascontiguousarray(data)
     if a.ndim == 3 and a.shape[2] == 1:
-        a = a[:, :, 0]
+        a = np.ascontiguousarray(a[:, :, 0])
     if a.ndim != 2:
         raise ValueError("only single-band 2-D rasters are supported")
-    if a.dtype not in _SAMPLE:
+    if np.dtype(a.dtype.name) not in _SAMPLE:
         raise ValueError(f"unsupported dtype {a.dtype}")
-    a = a.astype(a.dtype.newbyteorder("<"), copy=False)
+    if compress not in ("lzw", "none"):
+        raise ValueError("compress must be 'lzw' or 'none'")
+    a = np.ascontiguousarray(a.astype(a.dtype.newbyteorder("<"), copy=False))
     fmt, bits = _SAMPLE[np.dtype(a.dtype.name)]
     h, w = a.shape
     n_strips = -(-h // rows_per_strip)
     row_bytes = w * a.dtype.itemsize
-    big = a.nbytes + 65536 + 16 * n_strips >= (1 << 32)
+    compression = 5 if compress == "lzw" else 1
+    if compression == 1:
+        predictor = 1
+    lib = _lib.lib()
+    slot = int(lib.msr_tiff_lzw_bound(rows_per_strip * row_bytes)) if compression == 5 else rows_per_strip * row_bytes
+    packed = np.empty((n_strips, slot), np.uint8)
+    sizes = np.zeros(n_strips, np.int64)
+    _lib.check(lib.msr_tiff_encode_strips(a.ctypes.data, row_bytes, h, rows_per_strip, a.dtype.itemsize, compression,
+                                          predictor, packed.ctypes.data, slot, sizes.ctypes.data, _threads()),
+               "msr_tiff_encode_strips")
+    counts = [int(c) for c in sizes]
+    big = sum(counts) + 65536 + 16 * n_strips >= (1 << 32)
     off_t, off_code = ("<Q", 16) if big else ("<I", 4)
     osz = 8 if big else 4
     header = 16 if big else 8
-    counts = [min(rows_per_strip, h - s * rows_per_strip) * row_bytes for s in range(n_strips)]
     offsets, cur = [], header
     for c in counts:
         offsets.append(cur)
@@ -61,13 +84,15 @@ def write(path: str, data: np.ndarray, geo: Optional[Dict[int, Tuple[int, int, b
     long_(256, w)
     long_(257, h)
     short(258, bits)
-    short(259, 1)        # no compression
+    short(259, compression)
     short(262, 1)        # BlackIsZero
     entries.append((273, off_code, n_strips, b"".join(struct.pack(off_t, o) for o in offsets)))
     short(277, 1)
     long_(278, rows_per_strip)
     entries.append((279, off_code, n_strips, b"".join(struct.pack(off_t, c) for c in counts)))
     short(284, 1)
+    if predictor != 1:
+        short(317, predictor)
     short(339, fmt)
     if geo:
         for tag in GEO_TAGS:
@@ -101,7 +126,8 @@ def write(path: str, data: np.ndarray, geo: Optional[Dict[int, Tuple[int, int, b
             f.write(b"II" + struct.pack("<HHHQ", 43, 8, 0, ifd_off))
         else:
             f.write(b"II" + struct.pack("<HI", 42, ifd_off))
-        f.write(a.tobytes() if a.nbytes < (1 << 28) else memoryview(a).cast("B"))
+        for s_, c in enumerate(counts):
+            f.write(memoryview(packed[s_, :c]))
         if data_end & 1:
             f.write(b"\0")
         f.write(ifd)
@@ -109,8 +135,8 @@ def write(path: str, data: np.ndarray, geo: Optional[Dict[int, Tuple[int, int, b
 
 
 def read(path: str):
-    """Reads band 1 of a little-endian, uncompressed, stripped TIFF / BigTIFF.  Returns (array, geo) where geo maps the
-    GeoTIFF tag numbers present to (type, count, payload bytes)."""
+    """Reads band 1 of a little-endian TIFF / BigTIFF: strips or tiles, uncompressed or LZW, predictor 1 / 2 / 3.
+    Returns (array, geo) where geo maps the GeoTIFF tag numbers present to (type, count, payload bytes)."""
     with open(path, "rb") as f:
         buf = f.read()
     if buf[:2] != b"II":
@@ -144,24 +170,41 @@ def read(path: str):
         return list(struct.unpack("<" + code * cnt, payload))
 
     w, h = ints(256)[0], ints(257)[0]
-    if ints(259, [1])[0] != 1:
-        raise ValueError("compressed TIFFs are not supported yet (SURVEY.md section 8f)")
-    if 322 in tags:
-        raise ValueError("tiled TIFFs are not supported yet")
+    compression = ints(259, [1])[0]
+    if compression not in (1, 5):
+        raise ValueError(f"TIFF compression {compression} is not supported (only none and LZW)")
+    predictor = ints(317, [1])[0]
     spp = ints(277, [1])[0]
     if spp != 1 and ints(284, [1])[0] != 2:
         raise ValueError("only band-sequential or single-band rasters are supported")
     bits, fmt = ints(258)[0], ints(339, [1])[0]
     dtype = {v: k for k, v in _SAMPLE.items()}[(fmt, bits)]
-    rps = ints(278, [h])[0]
-    offs, cnts = ints(273), ints(279)
+    itemsize = dtype.itemsize
+    tiled = 322 in tags
+    if tiled:
+        tw, th = ints(322)[0], ints(323)[0]
+        offs, cnts = ints(324), ints(325)
+        across, down = -(-w // tw), -(-h // th)
+        n = across * down                      # band 1 only
+        rows0 = [(k // across) * th for k in range(n)]
+        cols0 = [(k % across) * tw * itemsize for k in range(n)]
+        chunk_rows, chunk_row_bytes = th, tw * itemsize
+    else:
+        rps = min(ints(278, [h])[0], h)
+        offs, cnts = ints(273), ints(279)
+        n = -(-h // rps)
+        rows0 = [k * rps for k in range(n)]
+        cols0 = [0] * n
+        chunk_rows, chunk_row_bytes = rps, w * itemsize
     out = np.empty((h, w), dtype)
-    flat = out.reshape(-1).view(np.uint8)
-    row_bytes = w * dtype.itemsize
-    strips_per_band = -(-h // rps)
-    for s in range(strips_per_band):
-        r0 = s * rps
-        nb = min(rps, h - r0) * row_bytes
-        flat[r0 * row_bytes:r0 * row_bytes + nb] = np.frombuffer(buf, np.uint8, nb, offs[s])
+    fbuf = np.frombuffer(buf, np.uint8)
+    a_off = np.asarray(offs[:n], np.int64)
+    a_cnt = np.asarray(cnts[:n], np.int64)
+    a_row = np.asarray(rows0, np.int64)
+    a_col = np.asarray(cols0, np.int64)
+    _lib.check(_lib.lib().msr_tiff_decode_chunks(fbuf.ctypes.data, fbuf.size, a_off.ctypes.data, a_cnt.ctypes.data,
+                                                 a_row.ctypes.data, a_col.ctypes.data, n, chunk_rows, chunk_row_bytes,
+                                                 itemsize, compression, predictor, out.ctypes.data, w * itemsize, h,
+                                                 _threads()), "msr_tiff_decode_chunks")
     geo = {t: tags[t] for t in GEO_TAGS + (TAG_GDAL_NODATA,) if t in tags}
     return out, geo
