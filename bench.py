@@ -344,7 +344,7 @@ def main():
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "conv_tc_traffic.json")
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")   # ncu capture of a 16-patch forward
         roofline = {"bound": "tensor", "kernel": "conv3x3_tc_kernel (tcgen05 implicit GEMM, all launches of one step)",
                     "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
                     "peak_source": f"MEASURED_PEAKS.json bf16 sustained ({pk['source']})", "traffic": traffic,

@@ -247,3 +247,25 @@ def test_engine_with_device_model_matches_oracle_pipeline(msr):
         assert np.abs(mean[g] - ref[0][g]).max() / scale <= 4 * tol
         assert np.abs(std[g] - ref[1][g]).max() / scale <= 4 * tol
         assert (mean[~g] == cfg.no_value).all()
+
+
+def test_pix2pix_tiled_pipeline_matches_oracle(msr):
+    """BASELINE.json configs[1] in miniature: pix2pix-256, stride 32, batch 16, tile 1024 over a 448 x 480 raster (49
+    valid patches, last batch padded) against the oracle pipeline with the oracle generator."""
+    from oracle import tiling as OT
+    i, s, b, t = 256, 32, 16, 1024
+    rng = np.random.default_rng(4)
+    h, w_ = 448, 480
+    dem = np.cumsum(np.cumsum(rng.standard_normal((h, w_)), 0), 1).astype(np.float32)
+    img = rng.uniform(1, 255, (h, w_)).astype(np.float32)
+    weights = W.random_init("pix2pix", i, seed=5, perturb_affine=True)
+    cfg = msr.DSRConfig(image_size=i, stride=s, batch_size=b, tile_size=t)
+    ref = OT.process_map(dem, img, i, s, b, t, cfg.no_value, OG.OracleModel("pix2pix", weights))
+    eng = msr.DEMSuperResolution(cfg, model=msr.Pix2Pix(batch_size=b, weights=weights))
+    mean, std, good = eng.run(dem, img)
+    np.testing.assert_array_equal(good, ref[2])
+    g = good.astype(bool)
+    assert g.any()
+    scale = float(dem.max() - dem.min())
+    assert np.abs(mean[g] - ref[0][g]).max() / scale <= 4 * TOL_FP32
+    assert np.abs(std[g] - ref[1][g]).max() / scale <= 4 * TOL_FP32
