@@ -344,10 +344,13 @@ def main():
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "conv_tc_traffic.json")
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")   # ncu capture of a 16-patch forward
+            # ncu capture of a forward over 16 patches; a bench launch covers groups * batch patches
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch") * (args.groups * args.batch_size / 16.0)
         roofline = {"bound": "tensor", "kernel": "conv3x3_tc_kernel (tcgen05 implicit GEMM, all launches of one step)",
                     "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
                     "peak_source": f"MEASURED_PEAKS.json bf16 sustained ({pk['source']})", "traffic": traffic,
+                    "traffic_note": "DRAM bytes per launch from profiles/conv_tc_traffic.json (ncu --set full, mean over the "
+                                    "rb4..final launches of a 16-patch forward) scaled to the patches per bench launch",
                     "launches": tc["launches"], "avg_launch_ms": tc["ms"] / tc["launches"],
                     "flops_per_launch_avg": tc["work"] / tc["launches"]}
     total_prof_ms = sum(v["ms"] for v in prof.values())
