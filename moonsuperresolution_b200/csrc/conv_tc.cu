@@ -1025,6 +1025,14 @@ int conv_tc_launch(const ConvTC* p, cudaStream_t st) {
   return MSR_OK;
 }
 
+// The tensor maps of a cached plan capture x and w (internal, stable buffers); every other pointer is re-read from the
+// arguments at each launch, because the caller's output buffer changes from call to call.
+void conv_tc_update_pointers(ConvTC* p, const ConvTCArgs& a) {
+  tc::EpiParams& e = p->ep;
+  e.bias = a.bias; e.y = a.y; e.res = a.res; e.stat_pairs = a.stat_pairs;
+  e.sx = a.sx; e.mean = a.mean; e.rstd = a.rstd; e.out_bf16 = a.out_bf16;
+}
+
 void conv_tc_plan_destroy(ConvTC* p) { delete p; }
 
 }  // namespace msr

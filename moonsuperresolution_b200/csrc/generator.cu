@@ -500,7 +500,9 @@ int tc_conv(Fwd& f, const ConvTCArgs& a) {
     f.plans->push_back(p);
   }
   MSR_REQUIRE(f.plan_cursor < f.plans->size(), "internal: tensor-core plan list out of sync");
-  return conv_tc_launch((*f.plans)[f.plan_cursor++], f.st);
+  ConvTC* p = (*f.plans)[f.plan_cursor++];
+  if (!f.building) conv_tc_update_pointers(p, a);   // e.g. the caller's output buffer differs from call to call
+  return conv_tc_launch(p, f.st);
 }
 
 // SPADE + LeakyReLU(0.2): result in g->act_f32 (fp32 mode) or g->act_bf16 (bf16 mode)

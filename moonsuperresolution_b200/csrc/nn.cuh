@@ -95,6 +95,7 @@ struct ConvTCArgs {
 };
 int conv_tc_plan_create(ConvTC** plan, const ConvTCArgs& a);
 int conv_tc_launch(const ConvTC* plan, cudaStream_t st);
+void conv_tc_update_pointers(ConvTC* plan, const ConvTCArgs& a);   // refresh the epilogue pointers of a cached plan
 void conv_tc_plan_destroy(ConvTC* plan);
 
 // ---- small helpers for the bf16 path (nn_bf16.cu) -----------------------------------------------------------------

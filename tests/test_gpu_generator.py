@@ -269,3 +269,21 @@ def test_pix2pix_tiled_pipeline_matches_oracle(msr):
     scale = float(dem.max() - dem.min())
     assert np.abs(mean[g] - ref[0][g]).max() / scale <= 4 * TOL_FP32
     assert np.abs(std[g] - ref[1][g]).max() / scale <= 4 * TOL_FP32
+
+
+def test_repeated_forward_calls_honour_new_output_buffers(msr, torch):
+    """The tensor-core plans are cached after the first call; a later call with different output / eps buffers must
+    write there (regression: the cached plan of the final layer kept the first call's output pointer)."""
+    i, b = 64, 4
+    w = W.random_init("spade", i, seed=8)
+    model = msr.GauGAN(i, b, precision="bf16", weights=w)
+    x, eps = inputs(i, b, seed=5)
+    src = torch.from_numpy(x).cuda()
+    e = torch.from_numpy(eps).cuda()
+    out1 = torch.full((b, i, i), 7.0, device="cuda")
+    out2 = torch.full((b, i, i), 7.0, device="cuda")
+    model.forward_device(src, out1, e, 1)
+    model.forward_device(src, out2, e, 1)
+    torch.cuda.synchronize()
+    assert not (out2 == 7.0).any()
+    assert torch.equal(out1, out2)
