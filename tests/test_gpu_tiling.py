@@ -170,6 +170,47 @@ def test_large_tile_size_matches_oracle(msr):
     np.testing.assert_array_equal(std, ref[1])
 
 
+@pytest.mark.parametrize("case", [
+    dict(H=40, W=50, I=64, S=8, B=4, T=256, holes=False),        # raster smaller than a patch: nothing is reconstructed
+    dict(H=130, W=70, I=64, S=16, B=1, T=128, holes=True),       # batch of one, narrow raster, NV stripes
+    dict(H=200, W=200, I=32, S=32, B=3, T=128, holes=False),     # stride == image_size: no overlap at all
+    dict(H=90, W=300, I=16, S=4, B=16, T=64, holes=True),        # smallest legal image_size (purge = 1)
+])
+def test_edge_geometries_match_oracle(msr, case):
+    """Ragged / degenerate inputs the reference handles implicitly: empty patch sets, B = 1, S = I, I = 16, NV stripes."""
+    c = dict(case, NV=-32768.0, model="wobble", seed=11)
+    dem, img = golden_inputs.make_rasters(c)
+    eng = engine_for(msr, c, toy_models.wobble)
+    mean, std, good = eng.run(dem, img)
+    with np.errstate(all="ignore"):
+        ref = OT.process_map(dem, img, c["I"], c["S"], c["B"], c["T"], c["NV"], toy_models.wobble)
+    np.testing.assert_array_equal(good, ref[2])
+    np.testing.assert_array_equal(mean, ref[0])
+    np.testing.assert_array_equal(std, ref[1])
+    if c["H"] < c["I"]:
+        assert good.sum() == 0 and (mean == c["NV"]).all()
+
+
+def test_all_no_value_raster_and_bad_parameters(msr):
+    case = dict(H=100, W=120, I=32, S=8, B=4, T=128, NV=-32768.0)
+    dem = np.full((100, 120), -32768.0, np.float32)
+    eng = engine_for(msr, case, toy_models.identity)
+    mean, std, good = eng.run(dem, dem.copy())
+    assert good.sum() == 0 and (mean == -32768.0).all() and (std == -32768.0).all()
+    # parameter combinations that crash the reference half-way (SURVEY.md App. C.5) are rejected up front
+    bad = msr.DEMSuperResolution(msr.DSRConfig(image_size=256, stride=224, tile_size=1024, batch_size=2), model=toy_models.identity)
+    bad.setRasters(np.ones((300, 300), np.float32), np.ones((300, 300), np.float32))
+    with pytest.raises(ValueError):
+        bad.padInputs()
+    with pytest.raises(ValueError):
+        engine_for(msr, case, toy_models.identity).padInputs()          # no rasters loaded
+    cfg = msr.DSRConfig(source_folder_path="/nonexistent", map_name="m", save_path="/tmp")
+    with pytest.raises(ValueError):
+        msr.DEMSuperResolution(cfg).loadImages()                         # process_full_tiles.py:167-170
+    with pytest.raises(AssertionError):
+        msr.load_GAN_model("/nonexistent/", 64, 2)                       # process_full_tiles.py:27
+
+
 def test_full_size_identity_round_trip(msr, torch):
     """BASELINE.json configs[2] geometry (8192 x 8192, I = 512, S = 128, B = 16, T = 1024) with the reference's identity
     model: size-independent properties instead of an element-wise oracle (which would take hours on the CPU):
