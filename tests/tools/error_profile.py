@@ -1,7 +1,7 @@
 """Stage-by-stage error of the CUDA generator against the fp64 oracle (accuracy diagnostic, GPU box only)."""
 import os, sys
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import torch.nn.functional as F
 from moonsuperresolution_b200 import CNNSpade, GauGAN
