@@ -525,12 +525,7 @@ int run_spade(Fwd& f, const SpadeW& s, const float* source, const float* x, int 
     if ((rc = conv_f32(d, f.st))) return rc;
     return spade_modulate_f32(g->gb_f32, x, x_shift, mean, rstd, g->act_f32, n, r, s.C, g->B, 0.2f, f.st);
   }
-  if ((rc = mask_conv_bf16(source, I, s.conv_w, s.conv_b, g->a_bf16, n, r, f.st))) return rc;
-  ConvTCArgs a;
-  a.x = g->a_bf16; a.w = s.gb_wt; a.n = n; a.r = r; a.cin = kHidden; a.ncols = 2 * s.C;
-  a.epilogue = TC_EPI_SPADE_BF16; a.bias = s.gb_bt; a.sx = x; a.sx_shift = x_shift; a.mean = mean; a.rstd = rstd;
-  a.samples_per_group = g->B; a.slope = 0.2f; a.out_bf16 = g->act_bf16;
-  return tc_conv(f, a);
+  return fail(MSR_E_STATE, "internal: run_spade is the fp32-mode operator");
 }
 
 // main 3x3 conv on the SPADE output (act buffer) -> y (fp32), optional residual
@@ -545,10 +540,7 @@ int run_conv(Fwd& f, const ConvW& w, int r, float* y, const float* res, int res_
     c.res = res; c.res_shift = res_shift; c.ldres = w.cout;
     return conv_f32(c, f.st);
   }
-  ConvTCArgs a;
-  a.x = g->act_bf16; a.w = w.wt; a.n = n; a.r = r; a.cin = w.cin; a.ncols = w.cout;
-  a.epilogue = TC_EPI_BIAS_F32; a.bias = w.b; a.y = y; a.res = res; a.res_shift = res_shift;
-  return tc_conv(f, a);
+  return fail(MSR_E_STATE, "internal: run_conv is the fp32-mode operator");
 }
 
 int forward_spade(Fwd& f, const float* source, const float* eps, float* out) {

@@ -31,8 +31,6 @@ int conv_f32(const ConvF32& p, cudaStream_t st);
 constexpr int kStatSplit = 64;
 int channel_stats_f32(const float* x, int ld, int groups, int64_t rows, int C, float eps, double* partial, float* mean,
                       float* rstd, cudaStream_t st);
-int channel_stats_bf16(const __nv_bfloat16* x, int ld, int groups, int64_t rows, int C, float eps, double* partial,
-                       float* mean, float* rstd, cudaStream_t st);
 
 // SPADE modulation (spade.py:21-24 + blocks.py:30-34): out[m][c] = lrelu(gamma * (x[src(m)][c] - mean) * rstd + beta)
 // gb [M][2C] = gamma | beta; x is [n][r >> x_shift][r >> x_shift][C]; statistics per group of rows_per_group rows of M.
@@ -45,9 +43,6 @@ int affine_act_f32(const float* x, int ldx, const float* mean, const float* rstd
                    const float* beta, float* y, int ldy, int64_t M, int C, int64_t rows_per_group, int act,
                    float slope, cudaStream_t st);
 
-// out[m][n] = sum_k x[m][k] * w[k][n] + bias[n]; `partial` scratch of ksplit * M * N floats when K is split.
-int dense_f32(const float* x, const float* w, const float* bias, float* out, int M, int K, int N, float* partial,
-              int64_t partial_capacity, cudaStream_t st);
 
 // latent = mean + exp(0.5 * var) * eps (sampling.py:16) when eps != null, else mean + var (model.py:791).
 int sampler_f32(const float* mean, const float* var, const float* eps, float* latent, int64_t count, cudaStream_t st);
@@ -107,8 +102,6 @@ int source_patches_bf16(const float* source, int I, __nv_bfloat16* out, int n, i
 
 // out[m][n] = sum_k x[m][k] * w[k][n] + bias[n], bf16 weights, fp32 activations / accumulation.  ldo = row pitch of
 // out.  `partial` scratch of ksplit * M * N floats.
-int dense_bf16w(const float* x, const __nv_bfloat16* w, const float* bias, float* out, int M, int K, int N,
-                float* partial, int64_t partial_capacity, cudaStream_t st);
 int dense_f32w(const float* x, const float* w, const float* bias, float* out, int M, int K, int N, float* partial,
                int64_t partial_capacity, cudaStream_t st);
 
@@ -121,9 +114,5 @@ int affine_act_bf16out(const float* x, int ldx, const float* mean, const float* 
 // statistics from the fused (sum, sumsq) pairs written by the tensor-core epilogue: pairs [groups*rows_p][C]
 int channel_stats_from_pairs(const float2* pairs, int groups, int64_t rows_p, int64_t count_per_group, int C, float eps,
                              double* partial, float* mean, float* rstd, cudaStream_t st);
-
-// legacy CUDA-core mask conv (kept for the operator tests)
-int mask_conv_bf16(const float* source, int I, const float* w, const float* bias, __nv_bfloat16* out, int n, int r,
-                   cudaStream_t st);  // nearest-resize + conv3x3 2->128 + relu -> bf16 [n][r][r][128]
 
 }  // namespace msr

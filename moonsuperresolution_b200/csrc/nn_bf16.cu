@@ -253,10 +253,6 @@ static int dense_gemm_m128(const float* x, const float* w, const float* bias, fl
   return MSR_OK;
 }
 
-int dense_bf16w(const float* x, const __nv_bfloat16* w, const float* bias, float* out, int M, int K, int N,
-                float* partial, int64_t partial_capacity, cudaStream_t st) {
-  return dense_small_m<__nv_bfloat16>(x, w, bias, out, M, K, N, partial, partial_capacity, st);
-}
 int dense_f32w(const float* x, const float* w, const float* bias, float* out, int M, int K, int N, float* partial,
                int64_t partial_capacity, cudaStream_t st) {
   MSR_REQUIRE(x && w && out && partial && M > 0 && K > 0 && N > 0, "dense: bad arguments");

@@ -249,10 +249,6 @@ int channel_stats_f32(const float* x, int ld, int groups, int64_t rows, int C, f
                       float* rstd, cudaStream_t st) {
   return channel_stats_impl<float>(x, ld, groups, rows, C, eps, partial, mean, rstd, st);
 }
-int channel_stats_bf16(const __nv_bfloat16* x, int ld, int groups, int64_t rows, int C, float eps, double* partial,
-                       float* mean, float* rstd, cudaStream_t st) {
-  return channel_stats_impl<__nv_bfloat16>(x, ld, groups, rows, C, eps, partial, mean, rstd, st);
-}
 
 // ------------------------------------------------------------------------------------------------------------------
 // SPADE modulation, fp32 path
@@ -337,61 +333,6 @@ int affine_act_f32(const float* x, int ldx, const float* mean, const float* rstd
   affine_act_kernel<<<blocks, 256, 0, st>>>(x, ldx, mean, rstd, gamma, beta, y, ldy, M, C, rows_per_group, act, slope);
   count_launch();
   MSR_LAUNCH_CHECK();
-  return MSR_OK;
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// Dense layer for small M (latent projection, encoder heads): split-K, deterministic two-stage sum.
-// ------------------------------------------------------------------------------------------------------------------
-constexpr int kDenseMB = 8;
-
-__global__ void __launch_bounds__(128) dense_partial_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                            float* __restrict__ partial, int M, int K, int N,
-                                                            int kchunk) {
-  const int nidx = blockIdx.x * 128 + threadIdx.x;
-  const int split = blockIdx.y;
-  const int m0 = blockIdx.z * kDenseMB;
-  const int k0 = split * kchunk, k1 = min(K, k0 + kchunk);
-  float acc[kDenseMB];
-#pragma unroll
-  for (int i = 0; i < kDenseMB; ++i) acc[i] = 0.f;
-  if (nidx < N) {
-    for (int k = k0; k < k1; ++k) {
-      const float wv = __ldg(w + (int64_t)k * N + nidx);
-#pragma unroll
-      for (int i = 0; i < kDenseMB; ++i)
-        if (m0 + i < M) acc[i] = fmaf(__ldg(x + (int64_t)(m0 + i) * K + k), wv, acc[i]);
-    }
-#pragma unroll
-    for (int i = 0; i < kDenseMB; ++i)
-      if (m0 + i < M) partial[((int64_t)split * M + m0 + i) * N + nidx] = acc[i];
-  }
-}
-
-__global__ void dense_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ bias,
-                                    float* __restrict__ out, int M, int N, int ksplit) {
-  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (e >= (int64_t)M * N) return;
-  float s = 0.f;
-  for (int k = 0; k < ksplit; ++k) s += partial[(int64_t)k * M * N + e];
-  if (bias) s += bias[e % N];
-  out[e] = s;
-}
-
-int dense_f32(const float* x, const float* w, const float* bias, float* out, int M, int K, int N, float* partial,
-              int64_t partial_capacity, cudaStream_t st) {
-  MSR_REQUIRE(x && w && out && partial && M > 0 && K > 0 && N > 0, "dense: bad arguments");
-  ProfileScope prof(MSR_PROF_DENSE, st, 2.0 * M * (double)K * N, 2);
-  int ksplit = std::max(1, std::min(64, K / 512));
-  while ((int64_t)ksplit * M * N > partial_capacity && ksplit > 1) --ksplit;
-  MSR_REQUIRE((int64_t)ksplit * M * N <= partial_capacity, "dense: partial scratch too small");
-  const int kchunk = ceil_div(K, ksplit);
-  dense_partial_kernel<<<dim3(ceil_div(N, 128), ksplit, ceil_div(M, kDenseMB)), 128, 0, st>>>(x, w, partial, M, K, N,
-                                                                                             kchunk);
-  MSR_LAUNCH_CHECK();
-  dense_reduce_kernel<<<ceil_div((int64_t)M * N, 256), 256, 0, st>>>(partial, bias, out, M, N, ksplit);
-  MSR_LAUNCH_CHECK();
-  count_launch(2);
   return MSR_OK;
 }
 
@@ -496,63 +437,6 @@ int final_conv_f32(const float* x, const float* w, const float* bias, float* out
   MSR_REQUIRE((2 * r) % FC_TX == 0, "final_conv: output side must be a multiple of 16");
   ProfileScope prof(MSR_PROF_FINAL_CONV, st, (double)n * r * r * 128 * 4.0 + (double)n * 4.0 * r * r * 4.0);
   final_conv_kernel<<<dim3(2 * r / FC_TX, 2 * r / FC_TY, n), 256, 0, st>>>(x, w, bias, out, n, r);
-  count_launch();
-  MSR_LAUNCH_CHECK();
-  return MSR_OK;
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// SPADE's shared 2 -> 128 conv (spade.py:9,17-18) for the bf16 path: nearest-resize (half-pixel centres) of the
-// (I, I, 2) source to (r, r), conv3x3 SAME, bias, relu, bf16 NHWC out.  One thread per (pixel, 8 channels).
-// ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) mask_conv_kernel(const float* __restrict__ src, int I,
-                                                        const float* __restrict__ w, const float* __restrict__ bias,
-                                                        __nv_bfloat16* __restrict__ out, int n, int r) {
-  __shared__ float ws[18 * 128];
-  __shared__ float bs[128];
-  for (int e = threadIdx.x; e < 18 * 128; e += 256) ws[e] = w[e];
-  if (threadIdx.x < 128) bs[threadIdx.x] = bias[threadIdx.x];
-  __syncthreads();
-  const int f = I / r, half = f >> 1;
-  const int64_t total = (int64_t)n * r * r * 16;
-  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int cg = (int)(e & 15);
-    const int64_t m = e >> 4;
-    const int nn = (int)(m / ((int64_t)r * r));
-    const int rem = (int)(m % ((int64_t)r * r));
-    const int h = rem / r, x = rem % r;
-    float acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = bs[cg * 8 + j];
-#pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-      const int hh = h + ky - 1;
-      if (hh < 0 || hh >= r) continue;
-#pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const int xx = x + kx - 1;
-        if (xx < 0 || xx >= r) continue;
-        const float2 s = *reinterpret_cast<const float2*>(src + (((int64_t)nn * I + hh * f + half) * I + xx * f + half) * 2);
-        const float* w0 = ws + ((ky * 3 + kx) * 2 + 0) * 128 + cg * 8;
-        const float* w1 = w0 + 128;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = fmaf(s.x, w0[j], fmaf(s.y, w1[j], acc[j]));
-      }
-    }
-    __align__(16) __nv_bfloat16 o[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = __float2bfloat16_rn(fmaxf(acc[j], 0.f));
-    *reinterpret_cast<uint4*>(out + m * 128 + cg * 8) = *reinterpret_cast<const uint4*>(o);
-  }
-}
-
-int mask_conv_bf16(const float* source, int I, const float* w, const float* bias, __nv_bfloat16* out, int n, int r,
-                   cudaStream_t st) {
-  MSR_REQUIRE(source && w && bias && out && r > 0 && I % r == 0, "mask_conv: bad arguments");
-  ProfileScope prof(MSR_PROF_MASK_CONV, st, (double)n * r * r * (8.0 + 256.0));
-  const int64_t total = (int64_t)n * r * r * 16;
-  const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 16);
-  mask_conv_kernel<<<blocks, 256, 0, st>>>(source, I, w, bias, out, n, r);
   count_launch();
   MSR_LAUNCH_CHECK();
   return MSR_OK;

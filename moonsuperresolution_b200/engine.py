@@ -56,6 +56,49 @@ class DSRConfig:
     seed: int = 0                   # seeds the Gaussian sampler's noise (the reference's is unseeded)
 
 
+def parse_args(argv=None) -> DSRConfig:
+    """process_full_tiles.py:68-127 -- same flags, defaults and help texts' meaning; unknown flags are ignored
+    (parse_known_args, :114).  Additions: --save_tiles, --groups_per_call, --seed, --model (gan | cnn | identity)."""
+    import argparse
+    parser = argparse.ArgumentParser("DEM Super Resolution config parser.")
+    parser.add_argument("--source_folder_path", type=str, required=True, default=None,
+                        help="The path to the folder containing both the ortho image and the DEM.")
+    parser.add_argument("--map_name", type=str, required=True, default=None, help="The name of the map to be processes.")
+    parser.add_argument("--save_path", type=str, required=True, default=None,
+                        help="The path to the folder where the reconstructed map will be stored.")
+    parser.add_argument("--ortho_image_name", type=str, default="run-DRG.tif", help="The name of the ortho image.")
+    parser.add_argument("--dem_name", type=str, default="run-DEM.tif", help="The name of the DEM image.")
+    parser.add_argument("--model_path", type=str, default=None,
+                        help="The path to the model. Do not specify to run indentity processing.")
+    parser.add_argument("--image_size", type=int, default=256, help="The size of the images the model can process.")
+    parser.add_argument("--stride", type=int, default=32, help="The amount of displacement between two images.")
+    parser.add_argument("--batch_size", type=int, default=16, help="The batch size of the model.")
+    parser.add_argument("--tile_size", type=int, default=1024, help="The size of the tiles.")
+    parser.add_argument("--no_value", type=int, default=-32768.0, help="The value marking points without data.")
+    parser.add_argument("--upsample_factor", type=float, default=1.0, help="Not used for now.")
+    parser.add_argument("--save_tiles", action="store_true", help="Also write the per-tile TIFFs of saveTile.")
+    parser.add_argument("--groups_per_call", type=int, default=0, help="Batches per generator call (0 = model's maximum).")
+    parser.add_argument("--seed", type=int, default=0, help="Seed of the Gaussian sampler's noise.")
+    args, _unknown = parser.parse_known_args(argv)
+    return DSRConfig(source_folder_path=args.source_folder_path, map_name=args.map_name, save_path=args.save_path,
+                     ortho_image_name=args.ortho_image_name, dem_name=args.dem_name, model_path=args.model_path,
+                     image_size=args.image_size, stride=args.stride, batch_size=args.batch_size,
+                     tile_size=args.tile_size, no_value=args.no_value, upsample_factor=args.upsample_factor,
+                     save_tiles=args.save_tiles, groups_per_call=args.groups_per_call, seed=args.seed)
+
+
+def main(argv=None) -> None:
+    """process_full_tiles.py:589-594; without --model_path the identity model runs (the reference's own CLI cannot reach
+    its identity mode)."""
+    from .models import IdentityModel, load_GAN_model
+    cfg = parse_args(argv)
+    if cfg.model_path is None:
+        model = IdentityModel(cfg.image_size, cfg.batch_size)
+    else:
+        model = load_GAN_model(cfg.model_path, cfg.image_size, cfg.batch_size, max_groups=max(1, cfg.groups_per_call or 8))
+    DEMSuperResolution(cfg, model=model).processMap()
+
+
 def _torch():
     import torch
     if not torch.cuda.is_available():

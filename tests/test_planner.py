@@ -90,3 +90,19 @@ def test_bands_cover_the_raster_once():
     parts = [(0, np.ones((3, 4), np.float32)), (3, 2 * np.ones((2, 4), np.float32))]
     out = assemble_bands(parts, 5, 4, np.float32)
     assert out[:3].min() == 1 and out[3:].min() == 2
+
+
+def test_parse_args_mirrors_the_reference_cli():
+    """Flag names and defaults of process_full_tiles.py:68-127; unknown flags are ignored (:114)."""
+    from moonsuperresolution_b200 import DSRConfig, parse_args
+    cfg = parse_args(["--source_folder_path", "in", "--map_name", "m", "--save_path", "out", "--whatever", "1"])
+    ref = DSRConfig()
+    for f in ("image_size", "stride", "batch_size", "tile_size", "no_value", "upsample_factor", "ortho_image_name",
+              "dem_name", "model_path"):
+        assert getattr(cfg, f) == getattr(ref, f)
+    assert (cfg.image_size, cfg.stride, cfg.batch_size, cfg.tile_size, cfg.no_value) == (256, 32, 16, 1024, -32768.0)
+    cfg = parse_args(["--source_folder_path", "in", "--map_name", "m", "--save_path", "out", "--image_size", "512",
+                      "--stride", "64", "--batch_size", "12", "--model_path", "w/"])
+    assert (cfg.image_size, cfg.stride, cfg.batch_size, cfg.model_path) == (512, 64, 12, "w/")
+    with pytest.raises(SystemExit):
+        parse_args(["--map_name", "m"])                     # required flags, as in the reference
