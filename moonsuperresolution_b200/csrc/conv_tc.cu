@@ -55,7 +55,7 @@ struct Cfg {
 
 struct Geometry {
   int n, r, cin, ncols;      // r = OUTPUT side; the input side is r * stride
-  int taps;                  // 9 (3x3) or 1 (1x1)
+  int taps;                  // 9 (3x3), 16 (4x4) or 1 (1x1)
   int split;                 // split-bf16 operands: A has 2*cin channels (hi | lo), B has 3*cin columns per tap
   int stride, pad;           // input coordinate of tap (ky, kx) for output (h, w): (h*stride + ky - pad, w*stride + kx - pad)
   int TW, TH, NB;            // tile = NB images x TH rows x TW cols (all powers of two, product 128)
@@ -81,6 +81,9 @@ struct EpiParams {
   float slope;
   int act;
   int split_out;             // TC_EPI_ACT_BF16: write hi | lo halves (row pitch 2 * ncols)
+  const float* scale;        // optional per-column scale applied before the bias (folded BatchNorm): acc * scale + bias
+  int out_pitch;             // TC_EPI_ACT_BF16 / PHASE_ACT: channels per output pixel in memory (0 = ncols resp. cout)
+  int phase_cout;            // TC_EPI_PHASE_ACT_BF16: channels per phase (ncols = 4 * phase_cout)
   __nv_bfloat16* out_bf16;
   long long* dbg;            // optional per-CTA cycle counters (msr_debug_tc_counters): 8 values per CTA
 };
@@ -389,7 +392,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       // (no integer divisions in the steady-state loop)
       const uint32_t lead_full0 = (CTAS == 2) ? mapa_shared(full_bar(0), 0) : 0u;
       const int n_parts = g.split ? 3 : 1;
-      const int ksz = (g.taps == 9) ? 3 : 1;
+      const int ksz = (g.taps == 9) ? 3 : (g.taps == 16 ? 4 : 1);
       TileIter it = tile_first();
       for (int tile = unit; tile < total_tiles; tile += n_units, tile_next(it)) {
         int b0, h0, w0, n0;
@@ -631,6 +634,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             float o[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(v[j]);
+            if (ep.scale != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 ss = __ldg(reinterpret_cast<const float4*>(ep.scale + col + j));
+                o[j] *= ss.x; o[j + 1] *= ss.y; o[j + 2] *= ss.z; o[j + 3] *= ss.w;
+              }
+            }
             if (ep.bias != nullptr) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
@@ -662,7 +672,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
               const __nv_bfloat162 t2 = __floats2bfloat162_rn(o[2 * j], o[2 * j + 1]);
               pk[j] = *reinterpret_cast<const uint32_t*>(&t2);
             }
-            const int64_t pitch = ep.split_out ? 2 * (int64_t)g.ncols : (int64_t)g.ncols;
+            const int64_t pitch = ep.out_pitch > 0 ? (int64_t)ep.out_pitch
+                                                   : (ep.split_out ? 2 * (int64_t)g.ncols : (int64_t)g.ncols);
             __nv_bfloat16* dst = ep.out_bf16 + m * pitch + col;
 #pragma unroll
             for (int q = 0; q < 2; ++q)
@@ -684,8 +695,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           }
         }
       } else if constexpr (EPI == TC_EPI_PHASE_F32) {
-        // final generator layer as a 3x3 convolution to 4 sub-pixel phases (columns 0..3 = (py, px)) + pixel shuffle:
-        // y[b][2h + py][2w + px] = acc[py*2 + px] + bias[0]
+        // a 4x4 conv on the x2-upsampled tensor, or a 4x4 stride-2 transposed conv, as a 3x3 convolution to 4 sub-pixel
+        // phases (columns 0..3 = (py, px)) + pixel shuffle:  y[b][2h + py][2w + px] = act(acc[py*2 + px] + bias[0])
         uint32_t v[32];
         if (csel == 0) {
           tmem_ld32(t_row, v);
@@ -693,10 +704,65 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         }
         if (csel == 0 && row_ok && n0 == 0) {
           const float b0f = ep.bias ? __ldg(ep.bias) : 0.f;
+          float o4[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            o4[q] = __uint_as_float(v[q]) + b0f;
+            if (ep.act == ACT_TANH) o4[q] = tanhf(o4[q]);
+          }
           const int R = 2 * g.r;
           float* dst = ep.y + ((int64_t)b * R + 2 * h) * R + 2 * w;
-          *reinterpret_cast<float2*>(dst) = make_float2(__uint_as_float(v[0]) + b0f, __uint_as_float(v[1]) + b0f);
-          *reinterpret_cast<float2*>(dst + R) = make_float2(__uint_as_float(v[2]) + b0f, __uint_as_float(v[3]) + b0f);
+          *reinterpret_cast<float2*>(dst) = make_float2(o4[0], o4[1]);
+          *reinterpret_cast<float2*>(dst + R) = make_float2(o4[2], o4[3]);
+        }
+      } else if constexpr (EPI == TC_EPI_PHASE_ACT_BF16) {
+        // transposed 4x4 stride-2 convolution with cout channels as a 3x3 convolution to 4 * cout phase columns
+        // (column = (py*2 + px) * cout + c); out[b][2h+py][2w+px][c] = act(acc * scale[c] + bias[c]) as bf16 into a
+        // tensor of side 2r with out_pitch channels per pixel (pix2pix.py:74-86: ConvT -> BatchNorm -> ReLU)
+        const int cout = ep.phase_cout;
+        const int R = 2 * g.r;
+        const int64_t opitch = ep.out_pitch > 0 ? ep.out_pitch : cout;
+#pragma unroll 1
+        for (int c0 = csel * 32; c0 < BN; c0 += 64) {
+          uint32_t v[32];
+          tmem_ld32(t_row + (uint32_t)c0, v);
+          tmem_ld_wait();
+          if (row_ok) {
+            const int col = n0 + c0;
+            const int phase = col / cout, ch = col - phase * cout;   // a 32-column chunk never straddles phases (cout % 32 == 0)
+            float o[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(v[j]);
+            if (ep.scale != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 ss = __ldg(reinterpret_cast<const float4*>(ep.scale + ch + j));
+                o[j] *= ss.x; o[j + 1] *= ss.y; o[j + 2] *= ss.z; o[j + 3] *= ss.w;
+              }
+            }
+            if (ep.bias != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(ep.bias + ch + j));
+                o[j] += bb.x; o[j + 1] += bb.y; o[j + 2] += bb.z; o[j + 3] += bb.w;
+              }
+            }
+            if (ep.act == ACT_RELU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) o[j] = fmaxf(o[j], 0.f);
+            }
+            uint32_t pk[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const __nv_bfloat162 t2 = __floats2bfloat162_rn(o[2 * j], o[2 * j + 1]);
+              pk[j] = *reinterpret_cast<const uint32_t*>(&t2);
+            }
+            __nv_bfloat16* dst = ep.out_bf16 + (((int64_t)b * R + 2 * h + (phase >> 1)) * R + 2 * w + (phase & 1)) * opitch + ch;
+#pragma unroll
+            for (int q = 0; q < 2; ++q)
+              st_global_v8(dst + 16 * q, pk[8 * q], pk[8 * q + 1], pk[8 * q + 2], pk[8 * q + 3], pk[8 * q + 4],
+                           pk[8 * q + 5], pk[8 * q + 6], pk[8 * q + 7]);
+          }
         }
       } else {
         // fused SPADE: a 128-column group holds gamma (64) | beta (64) of channels ch0 .. ch0+63
@@ -834,10 +900,11 @@ int conv_tc_plan_create(ConvTC** out, const ConvTCArgs& a) {
   MSR_REQUIRE(a.n > 0 && a.r > 0 && (a.r & (a.r - 1)) == 0, "conv_tc: r must be a power of two");
   MSR_REQUIRE(a.cin % 64 == 0 && a.cin >= 64, "conv_tc: cin must be a multiple of 64");
   MSR_REQUIRE(a.ncols % 32 == 0 && a.ncols >= 32, "conv_tc: output columns must be a multiple of 32");
-  MSR_REQUIRE(a.taps == 9 || a.taps == 1, "conv_tc: taps must be 9 (3x3) or 1 (1x1)");
+  MSR_REQUIRE(a.taps == 9 || a.taps == 1 || a.taps == 16, "conv_tc: taps must be 9 (3x3), 16 (4x4) or 1 (1x1)");
   MSR_REQUIRE(a.stride == 1 || a.stride == 2, "conv_tc: stride must be 1 or 2");
-  MSR_REQUIRE((reinterpret_cast<uintptr_t>(a.x) & 127) == 0 && (reinterpret_cast<uintptr_t>(a.w) & 127) == 0,
-              "conv_tc: operands must be 128-byte aligned");
+  MSR_REQUIRE((reinterpret_cast<uintptr_t>(a.x) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.w) & 127) == 0,
+              "conv_tc: x must be 16-byte and w 128-byte aligned");
+  MSR_REQUIRE(a.x_pitch == 0 || (a.x_pitch >= a.cin && a.x_pitch % 8 == 0), "conv_tc: bad x_pitch");
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return fail(MSR_E_CUDA, "conv_tc: cuTensorMapEncodeTiled entry point not available");
   ConvTC* p = new ConvTC();
@@ -873,8 +940,10 @@ int conv_tc_plan_create(ConvTC** out, const ConvTCArgs& a) {
   // A: 4-D NHWC tensor {C, W, H, N}; a stride-2 convolution walks W and H with element stride 2
   {
     const cuuint64_t ca = (cuuint64_t)a.cin * (a.split3 ? 2 : 1);
+    const cuuint64_t cp = a.x_pitch > 0 ? (cuuint64_t)a.x_pitch : ca;   // channels per pixel in memory (>= ca: a channel
+                                                                         // slice of a wider NHWC tensor, e.g. a concat buffer)
     cuuint64_t dims[4] = {ca, (cuuint64_t)rin, (cuuint64_t)rin, (cuuint64_t)a.n};
-    cuuint64_t strides[3] = {ca * 2, (cuuint64_t)rin * ca * 2, (cuuint64_t)rin * rin * ca * 2};
+    cuuint64_t strides[3] = {cp * 2, (cuuint64_t)rin * cp * 2, (cuuint64_t)rin * rin * cp * 2};
     cuuint32_t box[4] = {(cuuint32_t)tc::kBlockK, (cuuint32_t)(p->strip ? tc::kStripRows : g.TW * a.stride),
                          (cuuint32_t)(g.TH * a.stride), (cuuint32_t)g.NB};
     cuuint32_t estr[4] = {1, (cuuint32_t)a.stride, (cuuint32_t)a.stride, 1};
@@ -927,6 +996,7 @@ int conv_tc_plan_create(ConvTC** out, const ConvTCArgs& a) {
   e.sx = a.sx; e.sx_shift = a.sx_shift; e.mean = a.mean; e.rstd = a.rstd;
   e.samples_per_group = a.samples_per_group > 0 ? a.samples_per_group : 1;
   e.slope = a.slope; e.act = a.act; e.split_out = a.split_out; e.out_bf16 = a.out_bf16;
+  e.scale = a.scale; e.out_pitch = a.out_pitch; e.phase_cout = a.phase_cout;
   e.dbg = g_tc_dbg;
   const char* bad = nullptr;
   if (a.epilogue == TC_EPI_BIAS_F32) {
@@ -939,6 +1009,9 @@ int conv_tc_plan_create(ConvTC** out, const ConvTCArgs& a) {
     if (!a.out_bf16) bad = "conv_tc: out_bf16 is null";
   } else if (a.epilogue == TC_EPI_PHASE_F32) {
     if (!a.y || a.ncols != 32) bad = "conv_tc: phase epilogue needs y and exactly 32 (padded) columns";
+  } else if (a.epilogue == TC_EPI_PHASE_ACT_BF16) {
+    if (!a.out_bf16 || a.phase_cout < 32 || a.phase_cout % 32 != 0 || a.ncols != 4 * a.phase_cout)
+      bad = "conv_tc: phase-act epilogue needs out_bf16 and ncols = 4 * phase_cout, phase_cout a multiple of 32";
   } else {
     bad = "conv_tc: unknown epilogue";
   }
@@ -997,7 +1070,7 @@ template <int EPI>
 static int launch_width(const ConvTC* p, cudaStream_t st) {
   if constexpr (EPI == TC_EPI_PHASE_F32) {
     return launch_schedule<32, EPI>(p, st);
-  } else if constexpr (EPI == TC_EPI_SPADE_BF16) {
+  } else if constexpr (EPI == TC_EPI_SPADE_BF16 || EPI == TC_EPI_PHASE_ACT_BF16) {
     return p->bn == 256 ? launch_schedule<256, EPI>(p, st) : launch_schedule<128, EPI>(p, st);
   } else {
     switch (p->bn) {
@@ -1017,6 +1090,7 @@ int conv_tc_launch(const ConvTC* p, cudaStream_t st) {
     case TC_EPI_BIAS_F32: rc = launch_width<TC_EPI_BIAS_F32>(p, st); break;
     case TC_EPI_SPADE_BF16: rc = launch_width<TC_EPI_SPADE_BF16>(p, st); break;
     case TC_EPI_ACT_BF16: rc = launch_width<TC_EPI_ACT_BF16>(p, st); break;
+    case TC_EPI_PHASE_ACT_BF16: rc = launch_width<TC_EPI_PHASE_ACT_BF16>(p, st); break;
     default: rc = launch_width<TC_EPI_PHASE_F32>(p, st);
   }
   if (rc) return rc;
@@ -1030,7 +1104,7 @@ int conv_tc_launch(const ConvTC* p, cudaStream_t st) {
 void conv_tc_update_pointers(ConvTC* p, const ConvTCArgs& a) {
   tc::EpiParams& e = p->ep;
   e.bias = a.bias; e.y = a.y; e.res = a.res; e.stat_pairs = a.stat_pairs;
-  e.sx = a.sx; e.mean = a.mean; e.rstd = a.rstd; e.out_bf16 = a.out_bf16;
+  e.sx = a.sx; e.mean = a.mean; e.rstd = a.rstd; e.out_bf16 = a.out_bf16; e.scale = a.scale;
 }
 
 void conv_tc_plan_destroy(ConvTC* p) { delete p; }

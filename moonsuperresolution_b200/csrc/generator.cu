@@ -112,6 +112,11 @@ struct msr_generator {
   std::map<int, std::vector<ConvTC*>> plans;   // n_groups -> plans in launch order
   // pix2pix workspace
   float* cat[7] = {}; float* d8 = nullptr; float* p2p_raw = nullptr;
+  // pix2pix, bf16 tensor-core mode: weights [N][K] bf16, BatchNorm folded into per-channel scale / shift
+  const __nv_bfloat16* pdt_w[8] = {}; const float* pdt_scale[8] = {}; const float* pdt_shift[8] = {};
+  const __nv_bfloat16* put_w[7] = {}; const float* put_scale[7] = {}; const float* put_shift[7] = {};
+  const __nv_bfloat16* plt_w = nullptr;
+  __nv_bfloat16* catb[7] = {}; __nv_bfloat16* d8b = nullptr;
 
   ~msr_generator() {
     for (auto& kv : plans)
@@ -430,7 +435,98 @@ int finalize_spade(msr_generator* g) {
   return MSR_OK;
 }
 
+// pix2pix in bf16 tensor-core mode: every (transposed) convolution runs in conv_tc.cu.
+//   down k (pix2pix.py:64-72):  Conv4x4 s2 SAME -> BN -> LeakyReLU(0.3) = 16-tap stride-2 implicit GEMM, BN folded into
+//                               the epilogue's per-channel scale / shift; block 1 (2 input channels) is an im2col GEMM
+//   up k (pix2pix.py:74-86):    ConvT4x4 s2 SAME -> BN -> ReLU = 3x3 convolution to 4 sub-pixel phases x cout columns
+//                               (output row 2y+py reads input rows y-1 (ky=3), y (ky=1) for py=0; y (ky=2), y+1 (ky=0)
+//                               for py=1) + pixel shuffle in the epilogue; the skip concat is the channel layout of
+//                               the cat buffers
+int finalize_pix2pix_bf16(msr_generator* g) {
+  const int64_t N = (int64_t)g->B * g->maxG;
+  int rc;
+  auto fold_bn = [&](const std::string& pre, int c, const float** scale, const float** shift) -> int {
+    const HostTensor *ga, *be, *mm, *mv;
+    int r;
+    if ((r = need(g, pre + ".bn.gamma", {c}, &ga))) return r;
+    if ((r = need(g, pre + ".bn.beta", {c}, &be))) return r;
+    if ((r = need(g, pre + ".bn.moving_mean", {c}, &mm))) return r;
+    if ((r = need(g, pre + ".bn.moving_variance", {c}, &mv))) return r;
+    std::vector<float> sc(c), sh(c);
+    for (int i = 0; i < c; ++i) {
+      const double rs = 1.0 / sqrt((double)mv->data[i] + 1e-3);   // Keras BN eps (App. B.7)
+      sc[i] = (float)(rs * ga->data[i]);
+      sh[i] = (float)(be->data[i] - mm->data[i] * rs * ga->data[i]);
+    }
+    if ((r = upload(g, sc, scale))) return r;
+    return upload(g, sh, shift);
+  };
+  const HostTensor* t;
+  {  // block 1: [64][64], columns [w | w] against (x_hi | x_lo), k = (ky*4 + kx)*2 + c
+    if ((rc = need(g, "p2p.down1.kernel", {4, 4, 2, kP2PDown[0]}, &t))) return rc;
+    std::vector<uint16_t> w((size_t)kP2PDown[0] * 64);
+    for (int k = 0; k < 32; ++k)
+      for (int co = 0; co < kP2PDown[0]; ++co) {
+        const uint16_t v = f2bf(t->data[(size_t)k * kP2PDown[0] + co]);
+        w[(size_t)co * 64 + k] = v;
+        w[(size_t)co * 64 + 32 + k] = v;
+      }
+    if ((rc = upload_bf16(g, w, &g->pdt_w[0]))) return rc;
+  }
+  int cin = kP2PDown[0];
+  for (int k = 1; k < 8; ++k) {
+    const int cout = kP2PDown[k], K = 16 * cin;
+    const std::string pre = "p2p.down" + std::to_string(k + 1);
+    if ((rc = need(g, pre + ".kernel", {4, 4, cin, cout}, &t))) return rc;
+    std::vector<uint16_t> w((size_t)cout * K);
+    for (int kk = 0; kk < K; ++kk)
+      for (int co = 0; co < cout; ++co) w[(size_t)co * K + kk] = f2bf(t->data[(size_t)kk * cout + co]);
+    if ((rc = upload_bf16(g, w, &g->pdt_w[k]))) return rc;
+    if ((rc = fold_bn(pre, cout, &g->pdt_scale[k], &g->pdt_shift[k]))) return rc;
+    cin = cout;
+  }
+  // transposed convs: Keras kernel [ky][kx][cout][cin] -> phase weights [(py*2+px)*cout + co][(ty*3+tx)*cin + ci]
+  auto phase_weights = [&](const std::string& name, int cout, int cin_, int rows_padded, const __nv_bfloat16** out) -> int {
+    const HostTensor* w;
+    int r = need(g, name, {4, 4, cout, cin_}, &w);
+    if (r) return r;
+    const size_t K = (size_t)9 * cin_;
+    std::vector<uint16_t> pw((size_t)rows_padded * K, 0);
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px)
+        for (int ty = 0; ty < 3; ++ty)
+          for (int tx = 0; tx < 3; ++tx) {
+            // input row y + ty - 1 feeds output row 2y + py through kernel row ky = py + 1 - 2 * (ty - 1)
+            const int ky = py + 1 - 2 * (ty - 1), kx = px + 1 - 2 * (tx - 1);
+            if (ky < 0 || ky > 3 || kx < 0 || kx > 3) continue;
+            for (int co = 0; co < cout; ++co) {
+              const float* src = &w->data[(((size_t)ky * 4 + kx) * cout + co) * cin_];
+              uint16_t* dst = &pw[((size_t)(py * 2 + px) * cout + co) * K + (size_t)(ty * 3 + tx) * cin_];
+              for (int ci = 0; ci < cin_; ++ci) dst[ci] = f2bf(src[ci]);
+            }
+          }
+    return upload_bf16(g, pw, out);
+  };
+  for (int k = 0; k < 7; ++k) {
+    const std::string pre = "p2p.up" + std::to_string(k + 1);
+    if ((rc = phase_weights(pre + ".kernel", kP2PUp[k], cin, 4 * kP2PUp[k], &g->put_w[k]))) return rc;
+    if ((rc = fold_bn(pre, kP2PUp[k], &g->put_scale[k], &g->put_shift[k]))) return rc;
+    cin = kP2PUp[k] + kP2PDown[6 - k];
+  }
+  if ((rc = phase_weights("p2p.last.kernel", 1, cin, 32, &g->plt_w))) return rc;
+  if ((rc = upload_named(g, "p2p.last.bias", {1}, &g->pl_b))) return rc;
+  // cat[k] (k = 0..6) holds [up_{k+1} | down_{7-k}] at spatial side 2^(k+1), bf16
+  for (int k = 0; k < 7; ++k) {
+    const int s = 2 << k;
+    if ((rc = ws(g, &g->catb[k], N * s * s * (kP2PUp[k] + kP2PDown[6 - k])))) return rc;
+  }
+  if ((rc = ws(g, &g->d8b, N * 512))) return rc;
+  if ((rc = ws(g, &g->patches, N * 128 * 128 * 64))) return rc;
+  return MSR_OK;
+}
+
 int finalize_pix2pix(msr_generator* g) {
+  if (g->precision == MSR_PRECISION_BF16) return finalize_pix2pix_bf16(g);
   const int64_t N = (int64_t)g->B * g->maxG;
   int rc;
   auto bn = [&](const std::string& pre, int c, const float** mean, const float** rstd, const float** gamma,
@@ -818,6 +914,56 @@ int forward_pix2pix(Fwd& f, const float* source, float* out) {
   return MSR_OK;
 }
 
+int forward_pix2pix_bf16(Fwd& f, const float* source, float* out) {
+  msr_generator* g = f.g;
+  const int n = (int)f.N;
+  cudaStream_t st = f.st;
+  int rc;
+  // ---- down path; skip d_{k+1} lives in cat[6-k] behind the up-sampled channels
+  if ((rc = source_patches_bf16(source, 256, g->patches, n, 128, 2, st))) return rc;
+  const __nv_bfloat16* x = g->patches;
+  int cin = 64, x_pitch = 64, s = 256;
+  for (int k = 0; k < 8; ++k) {
+    const int cout = kP2PDown[k];
+    __nv_bfloat16* y;
+    int pitch;
+    if (k < 7) {
+      y = g->catb[6 - k] + kP2PUp[6 - k];
+      pitch = kP2PUp[6 - k] + cout;
+    } else {
+      y = g->d8b;
+      pitch = cout;
+    }
+    ConvTCArgs a;
+    a.x = x; a.w = g->pdt_w[k]; a.n = n; a.r = s / 2; a.cin = cin; a.x_pitch = x_pitch; a.ncols = cout;
+    if (k == 0) { a.taps = 1; a.pad = 0; } else { a.taps = 16; a.stride = 2; a.pad = 1; }
+    a.epilogue = TC_EPI_ACT_BF16; a.scale = g->pdt_scale[k]; a.bias = g->pdt_shift[k];   // null for block 1 (no BN)
+    a.act = ACT_LRELU; a.slope = 0.3f; a.out_bf16 = y; a.out_pitch = pitch;
+    if ((rc = tc_conv(f, a))) return rc;
+    s /= 2;
+    x = y; cin = cout; x_pitch = pitch;
+  }
+  // ---- up path: ConvT -> BN -> ReLU written in front of the skip inside cat[k]
+  for (int k = 0; k < 7; ++k) {
+    const int cout = kP2PUp[k];
+    const int pitch = cout + kP2PDown[6 - k];
+    ConvTCArgs a;
+    a.x = x; a.w = g->put_w[k]; a.n = n; a.r = s; a.cin = cin; a.x_pitch = x_pitch; a.ncols = 4 * cout;
+    a.epilogue = TC_EPI_PHASE_ACT_BF16; a.scale = g->put_scale[k]; a.bias = g->put_shift[k]; a.act = ACT_RELU;
+    a.phase_cout = cout; a.out_bf16 = g->catb[k]; a.out_pitch = pitch;
+    if ((rc = tc_conv(f, a))) return rc;
+    s *= 2;
+    x = g->catb[k]; cin = pitch; x_pitch = pitch;
+  }
+  // ---- last ConvT(1, 4, s2) + bias + tanh
+  ConvTCArgs a;
+  a.x = x; a.w = g->plt_w; a.n = n; a.r = s; a.cin = cin; a.x_pitch = x_pitch; a.ncols = 32;
+  a.epilogue = TC_EPI_PHASE_F32; a.bias = g->pl_b; a.act = ACT_TANH; a.y = out;
+  if ((rc = tc_conv(f, a))) return rc;
+  g->acts["out"] = {out, (int64_t)n * 256 * 256, 0};
+  return MSR_OK;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -829,7 +975,6 @@ extern "C" int msr_generator_create(msr_generator** out, int arch, int image_siz
   MSR_REQUIRE(batch_size > 0 && max_groups > 0, "batch_size and max_groups must be positive");
   if (arch == MSR_ARCH_PIX2PIX) {
     MSR_REQUIRE(image_size == 256, "pix2pix is fixed to 256x256 inputs (pix2pix.py:7)");
-    MSR_REQUIRE(precision == MSR_PRECISION_FP32, "pix2pix: only the fp32 path is implemented");
   } else {
     MSR_REQUIRE(image_size >= 64 && image_size % 64 == 0, "image_size must be a multiple of 64 (networks.py:40)");
     if (precision == MSR_PRECISION_BF16)
@@ -879,7 +1024,8 @@ extern "C" int msr_generator_forward(msr_generator* g, const float* d_source, co
     f.plans = &g->plans[n_groups];
   }
   const int64_t before = g_launch_count;
-  int rc = (g->arch == MSR_ARCH_PIX2PIX)          ? forward_pix2pix(f, d_source, d_out)
+  int rc = (g->arch == MSR_ARCH_PIX2PIX)          ? (g->precision == MSR_PRECISION_BF16 ? forward_pix2pix_bf16(f, d_source, d_out)
+                                                                                          : forward_pix2pix(f, d_source, d_out))
            : (g->precision == MSR_PRECISION_BF16) ? forward_spade_bf16(f, d_source, d_eps, d_out)
                                                   : forward_spade(f, d_source, d_eps, d_out);
   g->last_launches = g_launch_count - before;

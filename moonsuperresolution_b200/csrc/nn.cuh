@@ -61,12 +61,14 @@ enum TcEpilogue {
   TC_EPI_SPADE_BF16 = 1,  // columns are gamma|beta interleaved per 64; out_bf16 = lrelu(gamma * xhat + beta)
   TC_EPI_ACT_BF16 = 2,    // out_bf16 = act(acc + bias (+ residual))
   TC_EPI_PHASE_F32 = 3,   // 4 sub-pixel phase columns -> y[b][2h+py][2w+px] (final generator layer)
+  TC_EPI_PHASE_ACT_BF16 = 4,  // 4 * cout phase columns -> out_bf16[b][2h+py][2w+px][c] (transposed 4x4 s2 convolution)
 };
 struct ConvTCArgs {
   const __nv_bfloat16* x = nullptr;  // [n][r*stride][r*stride][cin] bf16
   const __nv_bfloat16* w = nullptr;  // [ncols][taps*cin] bf16 (K-major), k = tap*cin + ci
   int n = 0, r = 0, cin = 0, ncols = 0;   // r = output side
-  int taps = 9;                      // 9: 3x3, 1: 1x1
+  int taps = 9;                      // 9: 3x3, 16: 4x4, 1: 1x1
+  int x_pitch = 0;                   // channels per pixel of x in memory (0 = cin): x may be a slice of a wider tensor
   int split3 = 0;                    // 1: split-bf16 operands (~fp32 products): x has 2*cin channels (hi | lo), w has
                                      //    3*cin columns per tap (w_hi | w_lo | w_hi) pairing with (x_hi, x_hi, x_lo)
   int split_out = 0;                 // TC_EPI_ACT_BF16: also write lo = bf16(v - hi) at column ncols + c (pitch 2*ncols)
@@ -85,7 +87,10 @@ struct ConvTCArgs {
   const float* rstd = nullptr;
   int samples_per_group = 1;
   float slope = 0.2f;
-  int act = ACT_NONE;                // TC_EPI_ACT_BF16
+  int act = ACT_NONE;                // TC_EPI_ACT_BF16 / PHASE epilogues
+  const float* scale = nullptr;      // optional per-column scale before the bias (folded BatchNorm)
+  int out_pitch = 0;                 // channels per output pixel in memory (0 = dense)
+  int phase_cout = 0;                // TC_EPI_PHASE_ACT_BF16: channels per phase
   __nv_bfloat16* out_bf16 = nullptr; // [n*r*r][C] (SPADE) / [n*r*r][ncols] (ACT)
 };
 int conv_tc_plan_create(ConvTC** plan, const ConvTCArgs& a);
@@ -97,7 +102,8 @@ void conv_tc_plan_destroy(ConvTC* plan);
 // im2col of the 2-channel source for a 3x3 convolution at output side r: out [n][r][r][64] bf16, channel (ky*3+kx)*2+c
 // for c in {ortho, dem}, channels 18..63 zero.  mode 0: SPADE's mask path = nearest resize (half-pixel centres,
 // spade.py:17) to r x r followed by SAME padding (1, 1); mode 1: encoder block 1 = stride-2 taps on the full
-// resolution source with SAME padding (0, 1) (r = I / 2, blocks.py:53-60).
+// resolution source with SAME padding (0, 1) (r = I / 2, blocks.py:53-60); mode 2: pix2pix block 1 = 4x4 stride-2 taps
+// with SAME padding (1, 1), 32 values as hi (channels 0..31) | lo (32..63) (pix2pix.py:64-72).
 int source_patches_bf16(const float* source, int I, __nv_bfloat16* out, int n, int r, int mode, cudaStream_t st);
 
 // out[m][n] = sum_k x[m][k] * w[k][n] + bias[n], bf16 weights, fp32 activations / accumulation.  ldo = row pitch of

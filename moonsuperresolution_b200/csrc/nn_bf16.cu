@@ -53,13 +53,48 @@ __global__ void __launch_bounds__(256) source_patches_kernel(const float* __rest
   }
 }
 
+// pix2pix block 1 (pix2pix.py:64-72): Conv2D(64, 4, strides=2, 'same') on the 2-channel source = taps (2y + ky - 1,
+// 2x + kx - 1), ky, kx in 0..3.  Row = 32 tap-channel values as hi (channels 0..31) | lo (32..63); with weight rows
+// [w | w] the GEMM evaluates (x_hi + x_lo) * w, i.e. the exact input against bf16 weights.
+__global__ void __launch_bounds__(256) source_patches4_kernel(const float* __restrict__ src, int I,
+                                                              __nv_bfloat16* __restrict__ out, int n, int r) {
+  const int64_t total = (int64_t)n * r * r;
+  for (int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; m < total; m += (int64_t)gridDim.x * blockDim.x) {
+    const int nn = (int)(m / ((int64_t)r * r));
+    const int rem = (int)(m % ((int64_t)r * r));
+    const int h = rem / r, x = rem % r;
+    __align__(16) __nv_bfloat16 row[64];
+#pragma unroll
+    for (int ky = 0; ky < 4; ++ky) {
+#pragma unroll
+      for (int kx = 0; kx < 4; ++kx) {
+        float2 s = make_float2(0.f, 0.f);
+        const int sy = 2 * h + ky - 1, sx = 2 * x + kx - 1;
+        if (sy >= 0 && sy < I && sx >= 0 && sx < I)
+          s = __ldg(reinterpret_cast<const float2*>(src + (((int64_t)nn * I + sy) * I + sx) * 2));
+        const int j = (ky * 4 + kx) * 2;
+        const __nv_bfloat16 hx = __float2bfloat16_rn(s.x), hy = __float2bfloat16_rn(s.y);
+        row[j] = hx;
+        row[j + 1] = hy;
+        row[32 + j] = __float2bfloat16_rn(s.x - __bfloat162float(hx));
+        row[32 + j + 1] = __float2bfloat16_rn(s.y - __bfloat162float(hy));
+      }
+    }
+    uint4* dst = reinterpret_cast<uint4*>(out + m * 64);
+    const uint4* sp = reinterpret_cast<const uint4*>(row);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) dst[q] = sp[q];
+  }
+}
+
 int source_patches_bf16(const float* source, int I, __nv_bfloat16* out, int n, int r, int mode, cudaStream_t st) {
   MSR_REQUIRE(source && out && n > 0 && r > 0 && I % r == 0, "source_patches: bad arguments");
-  MSR_REQUIRE(mode == 0 || (mode == 1 && r * 2 == I), "source_patches: mode 1 needs r = I / 2");
+  MSR_REQUIRE(mode == 0 || ((mode == 1 || mode == 2) && r * 2 == I), "source_patches: modes 1, 2 need r = I / 2");
   const int64_t total = (int64_t)n * r * r;
   ProfileScope prof(MSR_PROF_MASK_CONV, st, (double)total * (128.0 + 8.0));
   const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 16);
-  source_patches_kernel<<<blocks, 256, 0, st>>>(source, I, out, n, r, mode);
+  if (mode == 2) source_patches4_kernel<<<blocks, 256, 0, st>>>(source, I, out, n, r);
+  else source_patches_kernel<<<blocks, 256, 0, st>>>(source, I, out, n, r, mode);
   count_launch();
   MSR_LAUNCH_CHECK();
   return MSR_OK;

@@ -218,12 +218,16 @@ def test_groups_have_independent_batch_statistics(msr, torch, b, precision, atol
     np.testing.assert_allclose(out.cpu().numpy()[..., None], sep, atol=atol)
 
 
-def test_pix2pix_generator(msr):
+@pytest.mark.parametrize("precision,tol", [("fp32", TOL_FP32), ("bf16", TOL_BF16)])
+def test_pix2pix_generator(msr, precision, tol):
+    """pix2pix U-Net (pix2pix.py:64-108); bf16 = every (transposed) convolution on the tcgen05 kernel (4x4 stride-2
+    implicit GEMMs, transposed convs as sub-pixel phases, BatchNorm folded into the epilogue)."""
     w = W.random_init("pix2pix", 256, seed=4, perturb_affine=True)
     x, _ = inputs(256, 2, seed=3)
     want = OG.pix2pix_call(x, w)
-    got = msr.Pix2Pix(batch_size=2, weights=w)(x, training=False)
-    assert np.abs(got - want).max() <= TOL_FP32
+    got = msr.Pix2Pix(batch_size=2, weights=w, precision=precision)(x, training=False)
+    assert got.shape == want.shape
+    assert np.abs(got - want).max() <= tol, np.abs(got - want).max()
 
 
 def test_engine_with_device_model_matches_oracle_pipeline(msr):
