@@ -263,7 +263,7 @@ def main():
     weights = W.random_init(args.arch, args.image_size, seed=0)
     cls = {"spade": M.GauGAN, "cnn": M.CNNSpade}.get(args.arch)
     if args.arch == "pix2pix":
-        model = M.Pix2Pix(batch_size=args.batch_size, weights=weights, max_groups=args.groups)
+        model = M.Pix2Pix(batch_size=args.batch_size, weights=weights, max_groups=args.groups, precision=args.precision)
     else:
         model = cls(args.image_size, args.batch_size, precision=args.precision, weights=weights, max_groups=args.groups)
     cfg = DSRConfig(image_size=args.image_size, stride=args.stride, batch_size=args.batch_size,
@@ -345,7 +345,7 @@ def main():
         achieved = tc["work"] / (tc["ms"] * 1e-3) / 1e12
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "conv_tc_traffic.json")
-        if os.path.exists(tpath):
+        if os.path.exists(tpath) and args.arch in ("spade", "cnn") and args.image_size == 512:
             # ncu capture of a forward over 16 patches; a bench launch covers groups * batch patches
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch") * (args.groups * args.batch_size / 16.0)
         roofline = {"bound": "tensor", "kernel": "conv3x3_tc_kernel (tcgen05 implicit GEMM, all launches of one step)",
