@@ -187,8 +187,9 @@ def test_spade_generator_fp32_mode(msr, arch, i, b):
     assert err <= TOL_FP32 * max(1.0, np.abs(want).max()), err
 
 
-@pytest.mark.parametrize("arch,i,b", [("cnn", 64, 3), ("spade", 128, 2), ("cnn", 256, 1)])
+@pytest.mark.parametrize("arch,i,b", [("cnn", 64, 3), ("spade", 128, 2), ("cnn", 256, 1), ("spade", 512, 2)])
 def test_spade_generator_bf16_tensor_core_mode(msr, arch, i, b):
+    """(spade, 512, 2) is BASELINE.json's model size: its r = 128 / 256 layers run the CTA-pair + strip-mode schedule."""
     w = W.random_init(arch, i, seed=12, perturb_affine=True)
     x, eps = inputs(i, b, seed=1)
     want, want_latent = OG.gaugan_call(x, w, eps, arch, return_latent=True)
