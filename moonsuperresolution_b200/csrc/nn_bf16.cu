@@ -6,6 +6,13 @@
 
 namespace msr {
 
+// 256-bit global store (sm_100): one full 32-byte sector per lane per instruction
+__device__ __forceinline__ void st_row_v8(void* p, const uint32_t* v) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+               "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // im2col of the 2-channel source: one thread per output pixel writes one 128-byte row (18 bf16 taps + zeros), so the
 // 2->128 (SPADE mask) and 2->64 (encoder block 1) 3x3 convolutions become K = 64 GEMMs on the tensor cores.
@@ -46,10 +53,9 @@ __global__ void __launch_bounds__(256) source_patches_kernel(const float* __rest
         row[36 + j + 1] = __float2bfloat16_rn(s.y - __bfloat162float(hy));
       }
     }
-    uint4* dst = reinterpret_cast<uint4*>(out + m * 64);
-    const uint4* sp = reinterpret_cast<const uint4*>(row);
+    const uint32_t* sp = reinterpret_cast<const uint32_t*>(row);
 #pragma unroll
-    for (int q = 0; q < 8; ++q) dst[q] = sp[q];
+    for (int q = 0; q < 4; ++q) st_row_v8(out + m * 64 + q * 16, sp + q * 8);
   }
 }
 
@@ -80,10 +86,9 @@ __global__ void __launch_bounds__(256) source_patches4_kernel(const float* __res
         row[32 + j + 1] = __float2bfloat16_rn(s.y - __bfloat162float(hy));
       }
     }
-    uint4* dst = reinterpret_cast<uint4*>(out + m * 64);
-    const uint4* sp = reinterpret_cast<const uint4*>(row);
+    const uint32_t* sp = reinterpret_cast<const uint32_t*>(row);
 #pragma unroll
-    for (int q = 0; q < 8; ++q) dst[q] = sp[q];
+    for (int q = 0; q < 4; ++q) st_row_v8(out + m * 64 + q * 16, sp + q * 8);
   }
 }
 

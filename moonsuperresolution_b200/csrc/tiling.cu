@@ -152,15 +152,30 @@ __global__ void __launch_bounds__(256) patch_minmax_kernel(const float* __restri
   if (x0 >= 0 && y0 >= 0) {
     const int rows_per = (I + kMinMaxSplit - 1) / kMinMaxSplit;
     const int r0 = split * rows_per, r1 = min(I, r0 + rows_per);
-    const int count = (r1 - r0) * I;
-    for (int e = threadIdx.x; e < count; e += blockDim.x) {
-      const int r = r0 + e / I, c = e % I;
-      const int64_t o = (int64_t)(y0 + r) * CW + x0 + c;
-      const float a = __ldg(img + o), b = __ldg(dem + o);
-      v[0] = fminf(v[0], a);
-      v[1] = fmaxf(v[1], a);
-      v[2] = fminf(v[2], b);
-      v[3] = fmaxf(v[3], b);
+    if (((x0 | I | CW) & 3) == 0) {   // 128-bit path: patch rows are 16-byte aligned
+      const int q = I >> 2;           // float4 per patch row
+      const int count = (r1 - r0) * q;
+      for (int e = threadIdx.x; e < count; e += blockDim.x) {
+        const int r = r0 + e / q, c = (e - (e / q) * q) << 2;
+        const int64_t o = (int64_t)(y0 + r) * CW + x0 + c;
+        const float4 a = __ldg(reinterpret_cast<const float4*>(img + o));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(dem + o));
+        v[0] = fminf(fminf(v[0], a.x), fminf(fminf(a.y, a.z), a.w));
+        v[1] = fmaxf(fmaxf(v[1], a.x), fmaxf(fmaxf(a.y, a.z), a.w));
+        v[2] = fminf(fminf(v[2], b.x), fminf(fminf(b.y, b.z), b.w));
+        v[3] = fmaxf(fmaxf(v[3], b.x), fmaxf(fmaxf(b.y, b.z), b.w));
+      }
+    } else {
+      const int count = (r1 - r0) * I;
+      for (int e = threadIdx.x; e < count; e += blockDim.x) {
+        const int r = r0 + e / I, c = e % I;
+        const int64_t o = (int64_t)(y0 + r) * CW + x0 + c;
+        const float a = __ldg(img + o), b = __ldg(dem + o);
+        v[0] = fminf(v[0], a);
+        v[1] = fmaxf(v[1], a);
+        v[2] = fminf(v[2], b);
+        v[3] = fmaxf(v[3], b);
+      }
     }
   }
   __shared__ float red[8][4];
@@ -199,8 +214,14 @@ __global__ void __launch_bounds__(256) patch_normalize_kernel(const float* __res
   float2* o = reinterpret_cast<float2*>(out) + (int64_t)k * I * I;
   const int chunk = (I * I + gridDim.y - 1) / gridDim.y;
   const int e0 = blockIdx.y * chunk, e1 = min(I * I, e0 + chunk);
+  const bool vec = (((x0 | I | CW | chunk) & 3) == 0);
   if (x0 < 0 || y0 < 0) {  // padding slot (process_full_tiles.py:472): zeros
-    for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) o[e] = make_float2(0.f, 0.f);
+    if (((I | chunk) & 3) == 0) {
+      float4* o4 = reinterpret_cast<float4*>(o);
+      for (int e = (e0 >> 1) + threadIdx.x; e < (e1 >> 1); e += blockDim.x) o4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) o[e] = make_float2(0.f, 0.f);
+    }
     if (blockIdx.y == 0 && threadIdx.x < 4) minmax[4 * k + threadIdx.x] = 0.f;
     return;
   }
@@ -220,6 +241,28 @@ __global__ void __launch_bounds__(256) patch_normalize_kernel(const float* __res
     minmax[4 * k + 3] = hi_d;
   }
   const float range_i = __fsub_rn(hi_i, lo_i), range_d = __fsub_rn(hi_d, lo_d);
+  if (vec) {   // 4 pixels per thread: two 128-bit loads, two 128-bit stores of interleaved {ortho, dem} pairs
+    const int q = I >> 2;
+    float4* o4 = reinterpret_cast<float4*>(o);
+    for (int e = (e0 >> 2) + threadIdx.x; e < (e1 >> 2); e += blockDim.x) {
+      const int r = e / q, c = (e - r * q) << 2;
+      const int64_t src = (int64_t)(y0 + r) * CW + x0 + c;
+      const float4 a = __ldg(reinterpret_cast<const float4*>(img + src));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(dem + src));
+      float4 u, w;
+      u.x = __fsub_rn(__fdiv_rn(__fsub_rn(a.x, lo_i), range_i), 0.5f);
+      u.y = __fsub_rn(__fdiv_rn(__fsub_rn(b.x, lo_d), range_d), 0.5f);
+      u.z = __fsub_rn(__fdiv_rn(__fsub_rn(a.y, lo_i), range_i), 0.5f);
+      u.w = __fsub_rn(__fdiv_rn(__fsub_rn(b.y, lo_d), range_d), 0.5f);
+      w.x = __fsub_rn(__fdiv_rn(__fsub_rn(a.z, lo_i), range_i), 0.5f);
+      w.y = __fsub_rn(__fdiv_rn(__fsub_rn(b.z, lo_d), range_d), 0.5f);
+      w.z = __fsub_rn(__fdiv_rn(__fsub_rn(a.w, lo_i), range_i), 0.5f);
+      w.w = __fsub_rn(__fdiv_rn(__fsub_rn(b.w, lo_d), range_d), 0.5f);
+      o4[2 * (int64_t)e] = u;
+      o4[2 * (int64_t)e + 1] = w;
+    }
+    return;
+  }
   for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
     const int r = e / I, c = e % I;
     const int64_t src = (int64_t)(y0 + r) * CW + x0 + c;
