@@ -382,34 +382,42 @@ int affine_act_bf16out(const float* x, int ldx, const float* mean, const float* 
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) stats_pairs_partial_kernel(const float2* __restrict__ pairs, int64_t rows_p, int C,
                                                                   double* __restrict__ partial) {
-  // grid (ceil(C/32), kStatSplit, groups); block = 32 channels x 8 row lanes
+  // grid (ceil(C/64), kStatSplit, groups); block = 32 channel pairs x 8 row lanes; one 128-bit load = 2 (sum, sumsq) pairs
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cx;
+  const int c = (blockIdx.x * 32 + cx) * 2;
   const int split = blockIdx.y, g = blockIdx.z;
   const int64_t per = (rows_p + kStatSplit - 1) / kStatSplit;
   const int64_t r0 = split * per, r1 = min(rows_p, r0 + per);
-  double s = 0.0, q = 0.0;
+  double s0 = 0.0, q0 = 0.0, s1 = 0.0, q1 = 0.0;
   if (c < C) {
     const float2* base = pairs + ((int64_t)g * rows_p) * C + c;
     for (int64_t r = r0 + ry; r < r1; r += 8) {
-      const float2 v = __ldg(base + r * C);
-      s += (double)v.x;
-      q += (double)v.y;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(base + r * C));
+      s0 += (double)v.x;
+      q0 += (double)v.y;
+      s1 += (double)v.z;
+      q1 += (double)v.w;
     }
   }
-  __shared__ double sh[2][8][32];
-  sh[0][ry][cx] = s;
-  sh[1][ry][cx] = q;
+  __shared__ double sh[4][8][32];
+  sh[0][ry][cx] = s0;
+  sh[1][ry][cx] = q0;
+  sh[2][ry][cx] = s1;
+  sh[3][ry][cx] = q1;
   __syncthreads();
   if (ry == 0 && c < C) {
 #pragma unroll
     for (int k = 1; k < 8; ++k) {
-      s += sh[0][k][cx];
-      q += sh[1][k][cx];
+      s0 += sh[0][k][cx];
+      q0 += sh[1][k][cx];
+      s1 += sh[2][k][cx];
+      q1 += sh[3][k][cx];
     }
     double* o = partial + (((int64_t)g * kStatSplit + split) * C + c) * 2;
-    o[0] = s;
-    o[1] = q;
+    o[0] = s0;
+    o[1] = q0;
+    o[2] = s1;
+    o[3] = q1;
   }
 }
 
@@ -435,7 +443,7 @@ int channel_stats_from_pairs(const float2* pairs, int groups, int64_t rows_p, in
                              double* partial, float* mean, float* rstd, cudaStream_t st) {
   MSR_REQUIRE(pairs && partial && mean && rstd && groups > 0 && rows_p > 0 && C > 0, "stats_from_pairs: bad arguments");
   ProfileScope prof(MSR_PROF_STATS, st, (double)groups * rows_p * C * 8.0, 2);
-  stats_pairs_partial_kernel<<<dim3(ceil_div(C, 32), kStatSplit, groups), 256, 0, st>>>(pairs, rows_p, C, partial);
+  stats_pairs_partial_kernel<<<dim3(ceil_div(C, 64), kStatSplit, groups), 256, 0, st>>>(pairs, rows_p, C, partial);
   MSR_LAUNCH_CHECK();
   stats_pairs_finalize_kernel<<<dim3(ceil_div(C, 128), groups), 128, 0, st>>>(partial, C, count_per_group, eps, mean, rstd);
   MSR_LAUNCH_CHECK();

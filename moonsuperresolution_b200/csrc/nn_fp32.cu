@@ -174,44 +174,49 @@ int conv_f32(const ConvF32& p, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------------------------------
 // Channel statistics: deterministic two-stage reduction, fp64 partials.
 // ------------------------------------------------------------------------------------------------------------------
-template <typename T>
-__device__ __forceinline__ float to_f32(T v);
-template <>
-__device__ __forceinline__ float to_f32<float>(float v) { return v; }
-template <>
-__device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
-
+// grid (ceil(C/128), kStatSplit, groups); block = 32 channel quads x 8 row lanes; 128-bit loads (C % 4 == 0, ld % 4 == 0)
 template <typename T>
 __global__ void __launch_bounds__(256) stats_partial_kernel(const T* __restrict__ x, int ld, int64_t rows, int C,
                                                             double* __restrict__ partial) {
-  // grid (ceil(C/32), kStatSplit, groups); block = 32 channels x 8 row lanes
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cx;
+  const int c = (blockIdx.x * 32 + cx) * 4;
   const int split = blockIdx.y, g = blockIdx.z;
   const int64_t per = (rows + kStatSplit - 1) / kStatSplit;
   const int64_t r0 = split * per, r1 = min(rows, r0 + per);
-  double s = 0.0, q = 0.0;
+  double s[4] = {0.0, 0.0, 0.0, 0.0}, q[4] = {0.0, 0.0, 0.0, 0.0};
   if (c < C) {
     const T* base = x + ((int64_t)g * rows) * ld + c;
     for (int64_t r = r0 + ry; r < r1; r += 8) {
-      const double v = (double)to_f32<T>(base[r * ld]);
-      s += v;
-      q += v * v;
+      const float4 v4 = __ldg(reinterpret_cast<const float4*>(base + r * ld));
+      const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double d = (double)v[j];
+        s[j] += d;
+        q[j] += d * d;
+      }
     }
   }
-  __shared__ double sh[2][8][32];
-  sh[0][ry][cx] = s;
-  sh[1][ry][cx] = q;
+  __shared__ double sh[2][8][128];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    sh[0][ry][cx * 4 + j] = s[j];
+    sh[1][ry][cx * 4 + j] = q[j];
+  }
   __syncthreads();
   if (ry == 0 && c < C) {
 #pragma unroll
-    for (int k = 1; k < 8; ++k) {
-      s += sh[0][k][cx];
-      q += sh[1][k][cx];
+    for (int j = 0; j < 4; ++j) {
+      double ss = s[j], qq = q[j];
+#pragma unroll
+      for (int k = 1; k < 8; ++k) {
+        ss += sh[0][k][cx * 4 + j];
+        qq += sh[1][k][cx * 4 + j];
+      }
+      double* o = partial + (((int64_t)g * kStatSplit + split) * C + c + j) * 2;
+      o[0] = ss;
+      o[1] = qq;
     }
-    double* o = partial + (((int64_t)g * kStatSplit + split) * C + c) * 2;
-    o[0] = s;
-    o[1] = q;
   }
 }
 
@@ -237,8 +242,9 @@ template <typename T>
 static int channel_stats_impl(const T* x, int ld, int groups, int64_t rows, int C, float eps, double* partial,
                               float* mean, float* rstd, cudaStream_t st) {
   MSR_REQUIRE(x && partial && mean && rstd && groups > 0 && rows > 0 && C > 0, "channel_stats: bad arguments");
+  MSR_REQUIRE(C % 4 == 0 && ld % 4 == 0, "channel_stats: channel count and pitch must be multiples of 4");
   ProfileScope prof(MSR_PROF_STATS, st, (double)groups * rows * C * sizeof(T), 2);
-  stats_partial_kernel<T><<<dim3(ceil_div(C, 32), kStatSplit, groups), 256, 0, st>>>(x, ld, rows, C, partial);
+  stats_partial_kernel<T><<<dim3(ceil_div(C, 128), kStatSplit, groups), 256, 0, st>>>(x, ld, rows, C, partial);
   MSR_LAUNCH_CHECK();
   stats_finalize_kernel<<<dim3(ceil_div(C, 128), groups), 128, 0, st>>>(partial, C, rows, eps, mean, rstd);
   MSR_LAUNCH_CHECK();
