@@ -211,6 +211,22 @@ def test_all_no_value_raster_and_bad_parameters(msr):
         msr.load_GAN_model("/nonexistent/", 64, 2)                       # process_full_tiles.py:27
 
 
+@pytest.mark.parametrize("name", ["wobble_200x260", "wobble_1100x1300", "identity_700x900"])
+def test_device_model_blend_path_is_bit_exact(msr, name):
+    """Device models keep float32 predictions on the GPU and go through the batched-load branch of msr_blend_tile; with
+    the device identity model the result must equal the oracle driven by a float32 identity, bit for bit."""
+    case = golden_inputs.CASES[name]
+    dem, img = golden_inputs.make_rasters(case)
+    eng = engine_for(msr, case, msr.IdentityModel(case["I"], case["B"]))
+    mean, std, good = eng.run(dem, img)
+    f32_identity = lambda x, training=False: np.asarray(x, dtype=np.float32)
+    with np.errstate(all="ignore"):
+        ref = OT.process_map(dem, img, case["I"], case["S"], case["B"], case["T"], case["NV"], f32_identity)
+    np.testing.assert_array_equal(good, ref[2])
+    np.testing.assert_array_equal(mean, ref[0])
+    np.testing.assert_array_equal(std, ref[1])
+
+
 def test_full_size_identity_round_trip(msr, torch):
     """BASELINE.json configs[2] geometry (8192 x 8192, I = 512, S = 128, B = 16, T = 1024) with the reference's identity
     model: size-independent properties instead of an element-wise oracle (which would take hours on the CPU):
