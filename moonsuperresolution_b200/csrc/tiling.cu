@@ -343,44 +343,13 @@ __global__ void __launch_bounds__(256) blend_tile_kernel(const void* const* __re
     if (X - p < 0) gx1 = -1;
     gy1 = min(gy1, G - 1);
     gx1 = min(gx1, G - 1);
-    if (f64flags == nullptr && gx1 - gx0 < 8) {
-      // device-model path: the (up to 8) contributions of one lattice row are fetched first -- lattice entry -> patch
-      // pointer / (min, max) -> prediction and weight are dependent loads, but independent across contributions --
-      // and only then folded into the sequential Welford chain, in the reference's order (gy outer, gx inner)
-      for (int gy = gy0; gy <= gy1; ++gy) {
-        const int ry = Y - gy * S;
-        float dv[8];
-        double wv[8];
-        bool ok[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int gx = gx0 + j;
-          int k = -1;
-          if (gx <= gx1) k = __ldg(lattice + gy * G + gx);
-          ok[j] = k >= 0;
-          dv[j] = 0.f;
-          wv[j] = 0.0;
-          if (ok[j]) {
-            const int rx = X - gx * S;
-            const float lo = __ldg(lohi + 2 * k), hi = __ldg(lohi + 2 * k + 1);
-            const float range = __fsub_rn(hi, lo);
-            float v = __ldg(reinterpret_cast<const float*>(ptrs[k]) + (int64_t)ry * I + rx);
-            if (add_half) v = __fadd_rn(v, 0.5f);                      // processBatch :340
-            dv[j] = __fadd_rn(__fmul_rn(v, range), lo);                // :396
-            wv[j] = __ldg(wtab + (int64_t)(ry - p) * (I - 2 * p) + (rx - p));
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (ok[j]) blend_update(st, wv[j], false, dv[j], 0.0);
-      }
-    } else {
-      for (int gy = gy0; gy <= gy1; ++gy) {
-        for (int gx = gx0; gx <= gx1; ++gx) {
-          const int k = lattice[gy * G + gx];
-          if (k < 0) continue;
-          blend_contribution(st, ptrs, f64flags, lohi, wtab, k, Y - gy * S, X - gx * S, I, p, add_half);
-        }
+    // (measured: fetching a lattice row's contributions before the sequential float64 Welford chain is SLOWER -- the
+    // kernel is bound by the float64 division / conversion chain that bit-exactness with numpy requires, not by loads)
+    for (int gy = gy0; gy <= gy1; ++gy) {
+      for (int gx = gx0; gx <= gx1; ++gx) {
+        const int k = lattice[gy * G + gx];
+        if (k < 0) continue;
+        blend_contribution(st, ptrs, f64flags, lohi, wtab, k, Y - gy * S, X - gx * S, I, p, add_half);
       }
     }
   } else {

@@ -213,8 +213,8 @@ def test_all_no_value_raster_and_bad_parameters(msr):
 
 @pytest.mark.parametrize("name", ["wobble_200x260", "wobble_1100x1300", "identity_700x900"])
 def test_device_model_blend_path_is_bit_exact(msr, name):
-    """Device models keep float32 predictions on the GPU and go through the batched-load branch of msr_blend_tile; with
-    the device identity model the result must equal the oracle driven by a float32 identity, bit for bit."""
+    """Device models keep float32 predictions on the GPU (no host round trip, `+ 0.5` applied inside msr_blend_tile);
+    with the device identity model the result must equal the oracle driven by a float32 identity, bit for bit."""
     case = golden_inputs.CASES[name]
     dem, img = golden_inputs.make_rasters(case)
     eng = engine_for(msr, case, msr.IdentityModel(case["I"], case["B"]))
