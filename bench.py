@@ -230,7 +230,8 @@ def config_dict(args, n, plan, slots):
             "batch_size": args.batch_size, "tile_size": args.tile_size, "tiles": len(plan.tiles()),
             "slots_per_step": slots, "gflop_per_slot": GF_PER_SLOT.get((args.arch, args.image_size)),
             "mode": "reference-faithful (halo patches recomputed per tile)", "precision": args.precision,
-            "parallelism": f"tile-row bands x{n}", "groups_per_call": args.groups,
+            "parallelism": f"tile-row bands x{n}" + (", inputs loaded sharded, I-S halo rows by NCCL send/recv" if n > 1 else ""),
+            "groups_per_call": args.groups,
             "l2": "inputs larger than L2 (raster 2 x %.0f MB per band; activations >> 126 MB)" %
                   (args.rows_per_gpu * plan.width * 4 / 1e6)}
 
@@ -270,10 +271,22 @@ def main():
                     tile_size=args.tile_size, groups_per_call=args.groups)
     eng = DEMSuperResolution(cfg, model=model, rank=rank, world_size=world, device=dev)
     r0, r1 = eng.rowsNeeded(h, w)
-    d_dem, d_img = synth_rows(torch, r0, r1, w, dev)
+    if world > 1:
+        # sharded inputs: a rank holds only the rows of its own band; the I - S halo rows its border tiles read come from
+        # the neighbouring ranks by NCCL send / recv inside every step (the one exchange of the path)
+        o0, o1 = eng.ownedRows(h, w)
+        d_dem, d_img = synth_rows(torch, o0, o1, w, dev)
+    else:
+        d_dem, d_img = synth_rows(torch, r0, r1, w, dev)
+
+    def load_resident(e):
+        if world > 1:
+            e.setOwnedRows(d_dem, d_img, h)
+        else:
+            e.setRasters(d_dem, d_img, row_offset=r0, full_height=h)
 
     def step_resident():
-        eng.setRasters(d_dem, d_img, row_offset=r0, full_height=h)
+        load_resident(eng)
         eng.padInputs()
         eng.processTiles()
 
@@ -313,11 +326,20 @@ def main():
     if not args.no_e2e:
         h_dem = torch.empty(d_dem.shape, dtype=torch.float32, pin_memory=True).copy_(d_dem).numpy()
         h_img = torch.empty(d_img.shape, dtype=torch.float32, pin_memory=True).copy_(d_img).numpy()
-        eng.run(h_dem, h_img, row_offset=r0, full_height=h)          # warm (pinned staging, allocator)
+        def step_e2e():
+            if world > 1:   # H2D of the owned rows, halo exchange on the device, tiles, D2H of the three rasters
+                eng.setOwnedRows(torch.from_numpy(h_dem).to(dev, non_blocking=True),
+                                 torch.from_numpy(h_img).to(dev, non_blocking=True), h)
+                eng.padInputs()
+                eng.processTiles()
+                return eng.results()[:3]
+            return eng.run(h_dem, h_img, row_offset=r0, full_height=h)
+
+        step_e2e()                                                    # warm (pinned staging, allocator)
         sync_all()
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
-            out = eng.run(h_dem, h_img, row_offset=r0, full_height=h)
+            out = step_e2e()
         torch.cuda.synchronize()
         t = torch.tensor([(time.perf_counter() - t0) / args.e2e_steps], dtype=torch.float64, device=dev)
         if world > 1:
@@ -377,7 +399,7 @@ def main():
             eng2 = DEMSuperResolution(cfg2, model=model, rank=rank, world_size=world, device=dev)
 
             def step_alt():
-                eng2.setRasters(d_dem, d_img, row_offset=r0, full_height=h)
+                load_resident(eng2)
                 eng2.padInputs()
                 eng2.processTiles()
             step_alt()

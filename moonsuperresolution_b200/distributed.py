@@ -27,6 +27,64 @@ def band_of_rank(plan: Plan, world_size: int, rank: int) -> Tuple[List[Tuple[int
     return own, r0, r1
 
 
+def rows_read_by_band(plan: Plan, world_size: int, rank: int) -> Tuple[int, int]:
+    """Raster rows [n0, n1) the tiles of ``rank`` read: its own rows plus the I - S halo on both sides, clipped."""
+    tiles, _, _ = band_of_rank(plan, world_size, rank)
+    if not tiles:
+        return 0, 0
+    c0 = min(yy for _, yy in tiles)
+    c1 = min(plan.canvas_h, max(yy for _, yy in tiles) + plan.tile_size + 2 * plan.off)
+    return max(0, c0 - plan.off), min(plan.height, c1 - plan.off)
+
+
+def exchange_halo_rows(own, plan: Plan, rank: int, world_size: int, group=None):
+    """Input-halo exchange for rasters that are loaded sharded (mode A): every rank holds exactly
+    the raster rows of its own band of tiles (``own``: torch tensor (r1 - r0, W), CUDA with the NCCL backend, CPU with
+    gloo) and receives the ``I - S`` halo rows its border tiles read from the neighbouring ranks by point-to-point
+    send / recv -- over NVLink with NCCL.  Returns a tensor with rows [n0, n1) = ``rows_read_by_band``.
+
+    This is the only data that ever crosses ranks on the path; the outputs of different bands are disjoint."""
+    import torch
+    import torch.distributed as dist
+    bounds = [band_of_rank(plan, world_size, r)[1:] for r in range(world_size)]
+    needs = [rows_read_by_band(plan, world_size, r) for r in range(world_size)]
+    r0, r1 = bounds[rank]
+    n0, n1 = needs[rank]
+    if tuple(own.shape) != (r1 - r0, plan.width):
+        raise ValueError(f"rank {rank} must hold rows [{r0}, {r1}) x {plan.width}, got {tuple(own.shape)}")
+    out = torch.empty((n1 - n0, plan.width), dtype=own.dtype, device=own.device)
+    if r1 > r0:
+        out[r0 - n0:r1 - n0] = own
+    if world_size == 1:
+        return out
+    ops, keep = [], []
+    for peer in range(world_size):
+        if peer == rank:
+            continue
+        p0, p1 = bounds[peer]
+        q0, q1 = needs[peer]
+        # rows of mine that the peer reads
+        s0, s1 = max(r0, q0), min(r1, q1)
+        if s1 > s0 and p1 > p0:
+            t = own[s0 - r0:s1 - r0].contiguous()
+            keep.append(t)
+            ops.append(dist.P2POp(dist.isend, t, peer, group))
+        # rows of the peer that I read
+        g0, g1 = max(p0, n0), min(p1, n1)
+        if g1 > g0 and r1 > r0:
+            t = torch.empty((g1 - g0, plan.width), dtype=own.dtype, device=own.device)
+            keep.append((t, g0, g1))
+            ops.append(dist.P2POp(dist.irecv, t, peer, group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    for item in keep:
+        if isinstance(item, tuple):
+            t, g0, g1 = item
+            out[g0 - n0:g1 - n0] = t
+    return out
+
+
 def assemble_bands(parts: Sequence[Tuple[int, np.ndarray]], height: int, width: int, dtype) -> np.ndarray:
     """Stacks (first_row, band) pieces into the (H, W) raster; bands are disjoint row ranges."""
     out = np.zeros((height, width), dtype)

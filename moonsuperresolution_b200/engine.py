@@ -30,7 +30,7 @@ import numpy as np
 
 from . import _lib
 from .models import IdentityModel, _Generator
-from .distributed import band_of_rank, gather_bands
+from .distributed import band_of_rank, exchange_halo_rows, gather_bands
 from .planner import PAD_SLOT, Plan
 
 
@@ -168,6 +168,22 @@ class DEMSuperResolution:
         if self._row_offset < 0 or self._row_offset + dem.shape[0] > h:
             raise ValueError("row_offset / full_height do not contain the given rows")
         self.dem_shape = self.img_shape = (h, int(dem.shape[1]))
+
+    def setOwnedRows(self, dem_rows, img_rows, full_height: int) -> None:
+        """Sharded loading: this rank supplies exactly the raster rows of its own band of tiles (float32 tensors, CUDA
+        with NCCL / CPU with gloo); the I - S halo rows its border tiles read are fetched from the neighbouring ranks
+        (distributed.exchange_halo_rows) -- the one exchange step of the path."""
+        plan = Plan(int(full_height), int(dem_rows.shape[1]), self.image_size, self.stride, self.tile_size, self.batch_size)
+        dem = exchange_halo_rows(dem_rows, plan, self.rank, self.world_size)
+        img = exchange_halo_rows(img_rows, plan, self.rank, self.world_size)
+        n0, _ = self.rowsNeeded(plan.height, plan.width)
+        self.setRasters(dem if dem.is_cuda else dem.numpy(), img if img.is_cuda else img.numpy(), row_offset=n0,
+                        full_height=plan.height)
+
+    def ownedRows(self, height: int, width: int) -> Tuple[int, int]:
+        """Raster rows [r0, r1) of this rank's own band of tiles (what setOwnedRows expects)."""
+        plan = Plan(height, width, self.image_size, self.stride, self.tile_size, self.batch_size)
+        return band_of_rank(plan, self.world_size, self.rank)[1:]
 
     def loadImages(self) -> None:
         """process_full_tiles.py:158-182 -- band 1 of both GeoTIFFs as float32 plus the DEM's geo-referencing."""
