@@ -251,8 +251,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: one JSON line only
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's banner / logs off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=dev)
     n = world
     from moonsuperresolution_b200 import DEMSuperResolution, DSRConfig, _lib
