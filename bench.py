@@ -365,13 +365,17 @@ def main():
     if tc["launches"] > 0 and tc["ms"] > 0:
         achieved = tc["work"] / (tc["ms"] * 1e-3) / 1e12
         traffic = None
+        tensor_pct = None
         tpath = os.path.join(ROOT, "profiles", "conv_tc_traffic.json")
         if os.path.exists(tpath) and args.arch in ("spade", "cnn") and args.image_size == 512:
             # ncu capture of a forward over 16 patches; a bench launch covers groups * batch patches
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch") * (args.groups * args.batch_size / 16.0)
+            tj = json.load(open(tpath))
+            traffic = tj.get("dram_bytes_per_launch") * (args.groups * args.batch_size / 16.0)
+            tensor_pct = tj.get("tensor_pipe_active_pct_time_weighted")
         roofline = {"bound": "tensor", "kernel": "conv3x3_tc_kernel (tcgen05 implicit GEMM, all launches of one step)",
                     "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
                     "peak_source": f"MEASURED_PEAKS.json bf16 sustained ({pk['source']})", "traffic": traffic,
+                    "ncu_tensor_pipe_active_pct": tensor_pct,
                     "traffic_note": "DRAM bytes per launch from profiles/conv_tc_traffic.json (ncu --set full, mean over the "
                                     "rb4..final launches of a 16-patch forward) scaled to the patches per bench launch",
                     "launches": tc["launches"], "avg_launch_ms": tc["ms"] / tc["launches"],
