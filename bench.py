@@ -56,6 +56,8 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=2, help="patches per CPU-baseline sample batch")
     ap.add_argument("--alt-tile-size", type=int, default=8192,
                     help="also time one step with this tile_size (0 = skip); reported beside, never as, the headline")
+    ap.add_argument("--no-dedup", action="store_true",
+                    help="skip the extra step in dedup mode (every patch position generated once; SURVEY 8e mode B)")
     return ap.parse_args()
 
 
@@ -426,6 +428,54 @@ def main():
         except Exception as ex:   # an optional extra must never cost the headline line
             alt = {"tile_size": args.alt_tile_size, "error": str(ex)[:200]}
 
+    # ---- dedup mode (mode B): every position of the global patch lattice generated once, accumulators
+    # continued across ranks through the seam strips (NCCL send / recv inside the step).  Same raster, stride, batch and
+    # nominal N generations per pixel; reported beside the headline, never as it.
+    dedup = None
+    if not args.no_dedup and args.tile_size % args.stride == 0:
+        try:
+            cfg3 = DSRConfig(image_size=args.image_size, stride=args.stride, batch_size=args.batch_size,
+                             tile_size=args.tile_size, groups_per_call=args.groups, mode="dedup")
+            eng3 = DEMSuperResolution(cfg3, model=model, rank=rank, world_size=world, device=dev)
+            q0, q1 = eng3.rowsNeeded(h, w)
+            if world > 1:
+                w0, w1 = eng3.ownedRows(h, w)
+                dd_dem, dd_img = synth_rows(torch, w0, w1, w, dev)
+            else:
+                dd_dem, dd_img = synth_rows(torch, q0, q1, w, dev)
+
+            def step_dedup():
+                if world > 1:
+                    eng3.setOwnedRows(dd_dem, dd_img, h)
+                else:
+                    eng3.setRasters(dd_dem, dd_img, row_offset=q0, full_height=h)
+                eng3.padInputs()
+                eng3.processTiles()
+            step_dedup()
+            sync_all()
+            s_before = eng3.slots_executed
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            step_dedup()
+            a1.record()
+            torch.cuda.synchronize()
+            t_dd = torch.tensor([a0.elapsed_time(a1)], dtype=torch.float64, device=dev)
+            sl = torch.tensor([eng3.slots_executed - s_before], dtype=torch.int64, device=dev)
+            if world > 1:
+                dist.all_reduce(t_dd, op=dist.ReduceOp.MAX)
+                dist.all_reduce(sl, op=dist.ReduceOp.SUM)
+            gf3 = GF_PER_SLOT.get((args.arch, args.image_size))
+            dedup = {"value": mp / (float(t_dd.item()) / 1e3), "unit": UNIT, "ms_per_step": float(t_dd.item()),
+                     "slots_per_step": int(sl.item()), "steps": 1,
+                     "model_tflops": (int(sl.item()) * gf3 / 1e3) / (float(t_dd.item()) / 1e3) if gf3 else None,
+                     "note": "mode='dedup': each global patch position generated once (batches run along the lattice "
+                             "rows of a band, not per tile), blended by msr_blend_accumulate in the reference's order; "
+                             "bit-identical to the tile-by-tile path for per-sample models "
+                             "(tests/test_gpu_dedup.py), same-batch-plan oracle parity for SPADE"}
+            del eng3, dd_dem, dd_img
+        except Exception as ex:   # an optional extra must never cost the headline line
+            dedup = {"error": str(ex)[:300]}
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sec, cores, desc = cpu_sample_seconds_per_slot(args, weights)
@@ -441,7 +491,7 @@ def main():
                 "gpu_launches": int(launches[0].item()), "slots_executed": int(launches[1].item()),
                 "model_tflops": (int(launches[1].item()) * gf / 1e3) / (ms_total / 1e3) if gf else None,
                 "roofline": roofline, "hbm_kernels": hbm_kernels, "cpu_baseline": cpu_baseline,
-                "alt_tile_size": alt,
+                "alt_tile_size": alt, "dedup_mode": dedup,
                 "breakdown_instrumented_step": breakdown}
         print(json.dumps(line))
     if world > 1:

@@ -112,6 +112,31 @@ int msr_blend_tile(const void* const* d_patch_ptr, const uint8_t* d_patch_f64, c
                    int S, int T, int add_half, float no_value, float* d_mean, float* d_std, uint8_t* d_good,
                    int64_t pitch, int rows, int cols, void* stream);
 
+/* Dedup mode (mode B: every patch position of the global stride lattice is generated once).
+ * The state of rebuildTile's loop (process_full_tiles.py:386-402) -- float32 w_sum, mean, S -- lives in canvas-shaped
+ * accumulators (acc_rows, pitch) whose row 0 is canvas row acc_y0; one call replays the loop body (:395-402, float64
+ * intermediates, float32 stores) for the patches [k0, k0 + n) of a band:
+ *   d_pred      (n, I, I) float32 predictions of those patches (raw network outputs when add_half = 1)
+ *   d_lohi      (n, 2) {dem_min, dem_max}
+ *   d_lattice   (GY, GX) int32: index of the patch at canvas origin (gx*S, lattice_y0 + gy*S) in the band's visit order
+ *               (y outer, x inner, process_full_tiles.py:453-454), -1 where the position holds no valid patch
+ *   gy_lo/gy_hi lattice rows (inclusive) that contain patches [k0, k0 + n)
+ *   row_lo/hi   only canvas rows [row_lo, row_hi) are updated (a rank defers the rows that first need its neighbour's
+ *               contributions: the update is order-dependent, :400-402)
+ * Calls must be issued in visit order; then every pixel receives its patches in the reference's order and the result
+ * is bit-identical to rebuildTile for the same predictions. */
+int msr_blend_accumulate(const float* d_pred, const float* d_lohi, int k0, int n, const int32_t* d_lattice, int GY,
+                         int GX, int gy_lo, int gy_hi, int lattice_y0, const double* d_weights, int I, int S,
+                         int add_half, float* d_wsum, float* d_mean, float* d_s, int64_t pitch, int acc_y0,
+                         int acc_rows, int cols, int row_lo, int row_hi, void* stream);
+
+/* rebuildTile's tail (process_full_tiles.py:404-413) on a (rows, cols) window of the accumulators (pointers already
+ * offset to the window's first pixel): good = w_sum > 0, std = sqrt(S / w_sum) in float32, mean / std = no_value where
+ * not good; written to (rows, out_pitch) rasters -- the crop of rebuildMap (:541-545) is the choice of window. */
+int msr_blend_finalize(const float* d_wsum, const float* d_mean_acc, const float* d_s, int64_t acc_pitch, int rows,
+                       int cols, float no_value, float* d_mean, float* d_std, uint8_t* d_good, int64_t out_pitch,
+                       void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * Raster container codec (host side, multi-threaded): what GDAL does for the reference when it reads band 1 of the input
  * GeoTIFFs (process_full_tiles.py:158-182) and writes 'COMPRESS=LZW', 'PREDICTOR=2' GeoTIFFs (:481-531).  The IFD / tags

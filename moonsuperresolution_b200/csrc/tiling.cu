@@ -367,6 +367,86 @@ __global__ void __launch_bounds__(256) blend_tile_kernel(const void* const* __re
   good_out[o] = good ? 1 : 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// K10  dedup mode (mode B): the same update as K9, but the float32 state (w_sum, mean, S) lives in
+//      canvas-shaped accumulators between calls, exactly like the reference's numpy arrays live between two iterations
+//      of rebuildTile's loop (:395-402).  One call adds the patches [k0, k0 + n) of a band's lattice; calls are issued
+//      in lattice order, so every pixel sees its patches in the reference's order (y outer, x inner).
+//      One thread per accumulator pixel of the rows the call touches.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) blend_accumulate_kernel(
+    const float* __restrict__ pred, const float* __restrict__ lohi, const int32_t* __restrict__ lattice, int GX,
+    int gy_lo, int gy_hi, int lat_y0, int k0, int n, const double* __restrict__ wtab, int I, int S, int add_half,
+    float* __restrict__ wsum, float* __restrict__ mean, float* __restrict__ sacc, int64_t pitch, int acc_y0, int y_lo,
+    int cols) {
+  const int X = blockIdx.x * blockDim.x + threadIdx.x;
+  if (X >= cols) return;
+  const int Y = y_lo + blockIdx.y;  // canvas row
+  const int p = I / 16;
+  const int ry = Y - lat_y0;        // row relative to the band's first lattice row
+  // lattice rows covering Y: gy*S + p <= ry < gy*S + I - p
+  int gy0 = (ry - (I - p) + 1 <= 0) ? 0 : (ry - (I - p) + S) / S;
+  int gy1 = (ry - p < 0) ? -1 : (ry - p) / S;
+  gy0 = max(gy0, gy_lo);
+  gy1 = min(gy1, gy_hi);
+  int gx0 = (X - (I - p) + 1 <= 0) ? 0 : (X - (I - p) + S) / S;
+  int gx1 = (X - p < 0) ? -1 : (X - p) / S;
+  gx1 = min(gx1, GX - 1);
+  if (gy1 < gy0 || gx1 < gx0) return;
+  const int64_t a = (int64_t)(Y - acc_y0) * pitch + X;
+  BlendState st;
+  bool touched = false;
+  const int64_t II = (int64_t)I * I;
+  const int wp = I - 2 * p;
+  for (int gy = gy0; gy <= gy1; ++gy) {
+    const int py = ry - gy * S;
+    for (int gx = gx0; gx <= gx1; ++gx) {
+      const int k = __ldg(lattice + (int64_t)gy * GX + gx) - k0;
+      if (k < 0 || k >= n) continue;
+      if (!touched) {
+        st.wsum = wsum[a];
+        st.mean = mean[a];
+        st.s = sacc[a];
+        touched = true;
+      }
+      const int px = X - gx * S;
+      const float lo = __ldg(lohi + 2 * k), hi = __ldg(lohi + 2 * k + 1);
+      float v = __ldg(pred + k * II + (int64_t)py * I + px);
+      if (add_half) v = __fadd_rn(v, 0.5f);                                  // processBatch :340
+      const float d = __fadd_rn(__fmul_rn(v, __fsub_rn(hi, lo)), lo);       // :396
+      blend_update(st, __ldg(wtab + (int64_t)(py - p) * wp + (px - p)), false, d, 0.0);
+    }
+  }
+  if (touched) {
+    wsum[a] = st.wsum;
+    mean[a] = st.mean;
+    sacc[a] = st.s;
+  }
+}
+
+// rebuildTile's tail (:404-413) over a window of the accumulators: good = w_sum > 0, std = sqrt(S / w_sum) in float32,
+// mean / std <- no_value where not good.
+__global__ void __launch_bounds__(256) blend_finalize_kernel(const float* __restrict__ wsum,
+                                                             const float* __restrict__ mean,
+                                                             const float* __restrict__ sacc, int64_t acc_pitch,
+                                                             int rows, int cols, float nv, float* __restrict__ mean_out,
+                                                             float* __restrict__ std_out, uint8_t* __restrict__ good_out,
+                                                             int64_t out_pitch) {
+  const int64_t total = (int64_t)rows * cols;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(e / cols), c = (int)(e % cols);
+    const int64_t a = (int64_t)r * acc_pitch + c;
+    const float w = __ldg(wsum + a);
+    const bool good = w > 0.f;                                          // :409
+    const float sd = __fsqrt_rn(__fdiv_rn(__ldg(sacc + a), w));         // :411
+    const int64_t o = (int64_t)r * out_pitch + c;
+    mean_out[o] = good ? __ldg(mean + a) : nv;                          // :412
+    std_out[o] = good ? sd : nv;                                        // :413
+    good_out[o] = good ? 1 : 0;
+  }
+}
+
 }  // namespace msr
 
 using namespace msr;
@@ -445,6 +525,47 @@ extern "C" int msr_blend_tile(const void* const* d_patch_ptr, const uint8_t* d_p
   blend_tile_kernel<<<dim3(ceil_div(cols, 256), rows), 256, 0, (cudaStream_t)stream>>>(
       d_patch_ptr, d_patch_f64, d_patch_lohi, d_patch_xy, n, d_lattice, G, d_weights, I, S, T, add_half, no_value,
       d_mean, d_std, d_good, pitch, rows, cols);
+  count_launch();
+  MSR_LAUNCH_CHECK();
+  return MSR_OK;
+}
+
+extern "C" int msr_blend_accumulate(const float* d_pred, const float* d_lohi, int k0, int n, const int32_t* d_lattice,
+                                    int GY, int GX, int gy_lo, int gy_hi, int lattice_y0, const double* d_weights, int I,
+                                    int S, int add_half, float* d_wsum, float* d_mean, float* d_s, int64_t pitch,
+                                    int acc_y0, int acc_rows, int cols, int row_lo, int row_hi, void* stream) {
+  MSR_REQUIRE(d_pred && d_lohi && d_lattice && d_weights && d_wsum && d_mean && d_s, "msr_blend_accumulate: null pointer");
+  MSR_REQUIRE(I >= 16 && S > 0 && S <= I, "msr_blend_accumulate: need I >= 16 (purge >= 1), 0 < S <= I");
+  MSR_REQUIRE(GY > 0 && GX > 0 && gy_lo >= 0 && gy_hi < GY && n >= 0 && k0 >= 0, "msr_blend_accumulate: bad lattice range");
+  MSR_REQUIRE(acc_rows > 0 && cols > 0 && pitch >= cols, "msr_blend_accumulate: bad accumulator geometry");
+  if (n == 0 || gy_hi < gy_lo) return MSR_OK;
+  const int p = I / 16;
+  // rows the patches of lattice rows [gy_lo, gy_hi] can touch, clipped to the caller's window and the accumulators
+  int y0 = lattice_y0 + gy_lo * S + p, y1 = lattice_y0 + gy_hi * S + I - p;
+  y0 = std::max(std::max(y0, row_lo), acc_y0);
+  y1 = std::min(std::min(y1, row_hi), acc_y0 + acc_rows);
+  if (y1 <= y0) return MSR_OK;
+  const int wp = I - 2 * p;
+  ProfileScope prof(MSR_PROF_BLEND, (cudaStream_t)stream, (double)n * wp * wp * (4.0 + 24.0));
+  blend_accumulate_kernel<<<dim3(ceil_div(cols, 256), y1 - y0), 256, 0, (cudaStream_t)stream>>>(
+      d_pred, d_lohi, d_lattice, GX, gy_lo, gy_hi, lattice_y0, k0, n, d_weights, I, S, add_half, d_wsum, d_mean, d_s,
+      pitch, acc_y0, y0, cols);
+  count_launch();
+  MSR_LAUNCH_CHECK();
+  return MSR_OK;
+}
+
+extern "C" int msr_blend_finalize(const float* d_wsum, const float* d_mean_acc, const float* d_s, int64_t acc_pitch,
+                                  int rows, int cols, float no_value, float* d_mean, float* d_std, uint8_t* d_good,
+                                  int64_t out_pitch, void* stream) {
+  MSR_REQUIRE(d_wsum && d_mean_acc && d_s && d_mean && d_std && d_good, "msr_blend_finalize: null pointer");
+  MSR_REQUIRE(rows >= 0 && cols >= 0 && acc_pitch >= cols && out_pitch >= cols, "msr_blend_finalize: bad geometry");
+  if (rows == 0 || cols == 0) return MSR_OK;
+  const int64_t total = (int64_t)rows * cols;
+  ProfileScope prof(MSR_PROF_BLEND, (cudaStream_t)stream, (double)total * 21.0);
+  const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 32);
+  blend_finalize_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_wsum, d_mean_acc, d_s, acc_pitch, rows, cols,
+                                                                  no_value, d_mean, d_std, d_good, out_pitch);
   count_launch();
   MSR_LAUNCH_CHECK();
   return MSR_OK;

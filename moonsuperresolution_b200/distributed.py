@@ -37,17 +37,20 @@ def rows_read_by_band(plan: Plan, world_size: int, rank: int) -> Tuple[int, int]
     return max(0, c0 - plan.off), min(plan.height, c1 - plan.off)
 
 
-def exchange_halo_rows(own, plan: Plan, rank: int, world_size: int, group=None):
+def exchange_halo_rows(own, plan: Plan, rank: int, world_size: int, group=None, bounds=None, needs=None):
     """Input-halo exchange for rasters that are loaded sharded (mode A): every rank holds exactly
     the raster rows of its own band of tiles (``own``: torch tensor (r1 - r0, W), CUDA with the NCCL backend, CPU with
     gloo) and receives the ``I - S`` halo rows its border tiles read from the neighbouring ranks by point-to-point
     send / recv -- over NVLink with NCCL.  Returns a tensor with rows [n0, n1) = ``rows_read_by_band``.
+    ``bounds`` / ``needs`` (per-rank [r0, r1) lists) override the mode-A row ranges (dedup mode has its own).
 
     This is the only data that ever crosses ranks on the path; the outputs of different bands are disjoint."""
     import torch
     import torch.distributed as dist
-    bounds = [band_of_rank(plan, world_size, r)[1:] for r in range(world_size)]
-    needs = [rows_read_by_band(plan, world_size, r) for r in range(world_size)]
+    if bounds is None:
+        bounds = [band_of_rank(plan, world_size, r)[1:] for r in range(world_size)]
+    if needs is None:
+        needs = [rows_read_by_band(plan, world_size, r) for r in range(world_size)]
     r0, r1 = bounds[rank]
     n0, n1 = needs[rank]
     if tuple(own.shape) != (r1 - r0, plan.width):

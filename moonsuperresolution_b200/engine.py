@@ -54,11 +54,13 @@ class DSRConfig:
     save_tiles: bool = False        # write the per-tile TIFFs of saveTile (process_full_tiles.py:416-429)
     groups_per_call: int = 0        # batches pushed through one generator call (0 = the model's max_groups)
     seed: int = 0                   # seeds the Gaussian sampler's noise (the reference's is unseeded)
+    mode: str = "faithful"          # "faithful": tile by tile like the reference (halo patches recomputed per tile);
+                                    # "dedup": every position of the global patch lattice generated once
 
 
 def parse_args(argv=None) -> DSRConfig:
     """process_full_tiles.py:68-127 -- same flags, defaults and help texts' meaning; unknown flags are ignored
-    (parse_known_args, :114).  Additions: --save_tiles, --groups_per_call, --seed, --model (gan | cnn | identity)."""
+    (parse_known_args, :114).  Additions: --save_tiles, --groups_per_call, --seed, --mode."""
     import argparse
     parser = argparse.ArgumentParser("DEM Super Resolution config parser.")
     parser.add_argument("--source_folder_path", type=str, required=True, default=None,
@@ -79,12 +81,14 @@ def parse_args(argv=None) -> DSRConfig:
     parser.add_argument("--save_tiles", action="store_true", help="Also write the per-tile TIFFs of saveTile.")
     parser.add_argument("--groups_per_call", type=int, default=0, help="Batches per generator call (0 = model's maximum).")
     parser.add_argument("--seed", type=int, default=0, help="Seed of the Gaussian sampler's noise.")
+    parser.add_argument("--mode", type=str, default="faithful", choices=["faithful", "dedup"],
+                        help="faithful: tile by tile like the reference; dedup: every patch position generated once.")
     args, _unknown = parser.parse_known_args(argv)
     return DSRConfig(source_folder_path=args.source_folder_path, map_name=args.map_name, save_path=args.save_path,
                      ortho_image_name=args.ortho_image_name, dem_name=args.dem_name, model_path=args.model_path,
                      image_size=args.image_size, stride=args.stride, batch_size=args.batch_size,
                      tile_size=args.tile_size, no_value=args.no_value, upsample_factor=args.upsample_factor,
-                     save_tiles=args.save_tiles, groups_per_call=args.groups_per_call, seed=args.seed)
+                     save_tiles=args.save_tiles, groups_per_call=args.groups_per_call, seed=args.seed, mode=args.mode)
 
 
 def main(argv=None) -> None:
@@ -131,6 +135,11 @@ class DEMSuperResolution:
         self.seed = int(getattr(config, "seed", 0))
         self.rank, self.world_size = int(rank), int(world_size)
         self._groups_cfg = int(getattr(config, "groups_per_call", 0))
+        self.mode = str(getattr(config, "mode", "faithful"))
+        if self.mode not in ("faithful", "dedup"):
+            raise ValueError("mode must be 'faithful' or 'dedup'")
+        if self.mode == "dedup" and self.save_tiles:
+            raise ValueError("save_tiles needs mode='faithful': dedup mode has no per-tile accumulators to save")
         self._lib = _lib.lib()
         torch = _torch()
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
@@ -174,8 +183,12 @@ class DEMSuperResolution:
         with NCCL / CPU with gloo); the I - S halo rows its border tiles read are fetched from the neighbouring ranks
         (distributed.exchange_halo_rows) -- the one exchange step of the path."""
         plan = Plan(int(full_height), int(dem_rows.shape[1]), self.image_size, self.stride, self.tile_size, self.batch_size)
-        dem = exchange_halo_rows(dem_rows, plan, self.rank, self.world_size)
-        img = exchange_halo_rows(img_rows, plan, self.rank, self.world_size)
+        bounds = needs = None
+        if self.mode == "dedup":
+            bounds = [self._rows_dedup(plan, r)[0] for r in range(self.world_size)]
+            needs = [self._rows_dedup(plan, r)[1] for r in range(self.world_size)]
+        dem = exchange_halo_rows(dem_rows, plan, self.rank, self.world_size, bounds=bounds, needs=needs)
+        img = exchange_halo_rows(img_rows, plan, self.rank, self.world_size, bounds=bounds, needs=needs)
         n0, _ = self.rowsNeeded(plan.height, plan.width)
         self.setRasters(dem if dem.is_cuda else dem.numpy(), img if img.is_cuda else img.numpy(), row_offset=n0,
                         full_height=plan.height)
@@ -183,7 +196,18 @@ class DEMSuperResolution:
     def ownedRows(self, height: int, width: int) -> Tuple[int, int]:
         """Raster rows [r0, r1) of this rank's own band of tiles (what setOwnedRows expects)."""
         plan = Plan(height, width, self.image_size, self.stride, self.tile_size, self.batch_size)
+        if self.mode == "dedup":
+            return self._rows_dedup(plan, self.rank)[0]
         return band_of_rank(plan, self.world_size, self.rank)[1:]
+
+    def _rows_dedup(self, plan: Plan, rank: int):
+        """Dedup mode: (raster rows this rank finalises, raster rows its patches read -- a superset)."""
+        band = plan.dedup_band(self.world_size, rank)
+        own = band.raster_rows(band.out, plan.off, plan.height)
+        need = band.raster_rows(band.read, plan.off, plan.height)
+        if own[1] > own[0]:
+            need = (min(need[0], own[0]), max(need[1], own[1])) if need[1] > need[0] else own
+        return own, need
 
     def loadImages(self) -> None:
         """process_full_tiles.py:158-182 -- band 1 of both GeoTIFFs as float32 plus the DEM's geo-referencing."""
@@ -225,7 +249,12 @@ class DEMSuperResolution:
         self.plan = plan = Plan(h, w, self.image_size, self.stride, self.tile_size, self.batch_size)
         self.pad_x, self.pad_y = plan.pad_x, plan.pad_y
         self.dem_padded_shape = self.img_padded_shape = (plan.canvas_h, plan.canvas_w)
-        self.my_tiles, c0, c1 = self._band()
+        if self.mode == "dedup":
+            self._dband = plan.dedup_band(self.world_size, self.rank)
+            self.my_tiles = []
+            c0, c1 = self._dband.read
+        else:
+            self.my_tiles, c0, c1 = self._band()
         self._c0, self._ch = c0, max(c1 - c0, 0)
         st = _lib.stream_ptr()
         nv = float(np.float32(self.no_value))
@@ -260,6 +289,16 @@ class DEMSuperResolution:
         # the reference releases the originals here (:265-266)
         self.dem = None
         self.img = None
+        if self.mode == "dedup":
+            self._plan_band()
+            self._out_r0, self._out_r1 = self._dband.raster_rows(self._dband.out, plan.off, h)
+            rows = self._out_r1 - self._out_r0
+            self.mean_out = torch.empty((rows, w), dtype=torch.float32, device=self.device)
+            self.std_out = torch.empty((rows, w), dtype=torch.float32, device=self.device)
+            self.good_out = torch.empty((rows, w), dtype=torch.uint8, device=self.device)
+            # rebuildTile's accumulators (:386-390) for the canvas rows this band's patches touch
+            self._acc = torch.zeros((3, self._ch, plan.canvas_w), dtype=torch.float32, device=self.device)
+            return
         self._plan_tiles()
         # output rasters of this rank's band (rows [out_r0, out_r1) of the (H, W) result)
         if self.my_tiles:
@@ -541,6 +580,179 @@ class DEMSuperResolution:
         d_flags = torch.tensor(flags, dtype=torch.uint8, device=dev)
         return d_ptrs, d_flags, keep
 
+    # ---------------------------------------------------------------------------------------------------------------
+    # dedup mode (mode B)
+    # ---------------------------------------------------------------------------------------------------------------
+    def _plan_band(self) -> None:
+        """Validity (getPatch, process_full_tiles.py:286-292) of every lattice position of this rank's band and the
+        visit order of the valid ones: y outer, x inner (:453-454), over the whole band instead of tile by tile."""
+        torch = _torch()
+        plan, band = self.plan, self._dband
+        rows, gx, s = band.j1 - band.j0, band.gx, plan.stride
+        self._band_plan = dict(xy=np.zeros((0, 2), np.int32), lattice=np.full((max(rows * gx, 1),), -1, np.int32),
+                               n_valid=0, row_of=np.zeros((0,), np.int32))
+        if rows <= 0 or self._ch <= 0:
+            return
+        xs = np.tile(np.arange(gx, dtype=np.int32) * s, rows)
+        ys = np.repeat((np.arange(rows, dtype=np.int32) + band.j0) * s, gx)
+        xy = np.stack([xs, ys - self._c0], axis=1).astype(np.int32)          # rows local to the canvas band
+        d_xy = torch.from_numpy(xy).to(self.device)
+        d_valid = torch.empty((xy.shape[0],), dtype=torch.uint8, device=self.device)
+        _lib.check(self._lib.msr_patch_validity(self._sat.data_ptr(), self._ch, plan.canvas_w, d_xy.data_ptr(),
+                                                xy.shape[0], plan.image_size, d_valid.data_ptr(), _lib.stream_ptr()),
+                   "msr_patch_validity")
+        self.launches += 1
+        idx = np.nonzero(d_valid.cpu().numpy())[0]
+        lattice = np.full((rows * gx,), -1, np.int32)
+        lattice[idx] = np.arange(idx.size, dtype=np.int32)
+        self._band_plan = dict(xy=xy[idx], lattice=lattice, n_valid=int(idx.size), row_of=(idx // gx).astype(np.int32))
+
+    def _accumulate(self, pred, lohi, k0: int, n: int, gy_lo: int, gy_hi: int, add_half: int, row_lo: int,
+                    row_hi: int) -> None:
+        plan, band = self.plan, self._dband
+        acc = self._acc
+        _lib.check(self._lib.msr_blend_accumulate(pred.data_ptr(), lohi.data_ptr(), k0, n, self._d_lattice.data_ptr(),
+                                                  band.j1 - band.j0, band.gx, gy_lo, gy_hi, band.j0 * plan.stride,
+                                                  self._blend_weights().data_ptr(), plan.image_size, plan.stride,
+                                                  int(add_half), acc[0].data_ptr(), acc[1].data_ptr(),
+                                                  acc[2].data_ptr(), plan.canvas_w, self._c0, self._ch, plan.canvas_w,
+                                                  row_lo, row_hi, _lib.stream_ptr()), "msr_blend_accumulate")
+        self.launches += 1
+
+    def bandSlots(self) -> int:
+        """Generator slots this rank executes in dedup mode (valid patches rounded up to whole batches)."""
+        return self.plan.batch_slots(self._band_plan["n_valid"])
+
+    def processBandMain(self, eps=None) -> None:
+        """Dedup mode, phase 1: generate every valid patch of the band once, in visit order, and blend it into the
+        accumulators -- except the rows that the previous rank's patches also touch (``seam_in``): rebuildTile's update
+        is order-dependent (process_full_tiles.py:400-402), so those rows wait for the neighbour's accumulator strip
+        and the predictions that reach into them are kept for phase 2.  ``eps``: optional (bandSlots(), 256) noise."""
+        torch = _torch()
+        plan, band, bp = self.plan, self._dband, self._band_plan
+        i, b, dev = plan.image_size, plan.batch_size, self.device
+        n_valid = bp["n_valid"]
+        slots = plan.batch_slots(n_valid)
+        self._retained = []
+        self._d_lattice = torch.from_numpy(bp["lattice"]).to(dev, non_blocking=True)
+        if n_valid == 0:
+            return
+        main_lo = band.seam_in[1] if band.seam_in is not None else 0
+        # lattice rows (relative to the band) whose patches reach above main_lo
+        seam_rows = 0 if band.seam_in is None else -(-(plan.off - 2 * plan.purge) // plan.stride)
+        slot_xy = np.full((slots, 2), -1, np.int32)
+        slot_xy[:n_valid] = bp["xy"]
+        d_slot_xy = torch.from_numpy(slot_xy).to(dev, non_blocking=True)
+        minmax = torch.empty((slots, 4), dtype=torch.float32, device=dev)
+        row_of = bp["row_of"]
+        device_model = isinstance(self.model, (_Generator, IdentityModel))
+        if device_model:
+            groups = max(1, min(self._groups_cfg or self.model.max_groups, self.model.max_groups))
+            chunk = groups * b
+            add_half = 1
+        else:
+            chunk, add_half = b, 0
+        src = torch.empty((min(chunk, slots), i, i, 2), dtype=torch.float32, device=dev)
+        partial = torch.empty((min(chunk, slots) * 32 * 4,), dtype=torch.float32, device=dev)
+        d_eps = None
+        if device_model and self.model.arch == "spade":
+            if eps is None:
+                gen = torch.Generator(device=dev)
+                gen.manual_seed((self.seed * 1000003 + band.j0 * 8191 + 17) & 0x7FFFFFFFFFFF)
+                d_eps = torch.randn((slots, 256), generator=gen, dtype=torch.float32, device=dev)
+            else:
+                d_eps = torch.as_tensor(np.ascontiguousarray(eps, dtype=np.float32)).to(dev)
+                if tuple(d_eps.shape) != (slots, 256):
+                    raise ValueError(f"eps must have shape {(slots, 256)}")
+        for s0 in range(0, slots, chunk):
+            n = min(chunk, slots - s0)
+            n_real = min(n, n_valid - s0)
+            self._gather(d_slot_xy[s0:s0 + n], n, src, minmax[s0:s0 + n], partial)
+            if device_model:
+                pred = torch.empty((n, i, i), dtype=torch.float32, device=dev)
+                self.model.forward_device(src[:n], pred, None if d_eps is None else d_eps[s0:s0 + n], n // b)
+                self.model_launches += self.model.last_launch_count
+            else:
+                y = self.model(src[:n].cpu().numpy(), training=False)                 # plug-in contract (:338)
+                y = (np.array(y)[:, :, :, -1] + 0.5).astype(np.float32, copy=False)   # :340
+                pred = torch.from_numpy(np.ascontiguousarray(y)).to(dev)
+            self.slots_executed += n
+            lohi = minmax[s0:s0 + n_real, 2:4].contiguous()
+            gy_lo, gy_hi = int(row_of[s0]), int(row_of[s0 + n_real - 1])
+            self._accumulate(pred, lohi, s0, n_real, gy_lo, gy_hi, add_half, main_lo, plan.canvas_h)
+            if gy_lo < seam_rows:
+                self._retained.append((pred, lohi, s0, n_real, gy_lo, min(gy_hi, seam_rows - 1), add_half))
+
+    def seamOut(self):
+        """Accumulator rows this rank's patches share with the NEXT rank's: a (3, rows, canvas_w) float32 view
+        (w_sum, mean, S), complete after processBandMain; None for the last rank."""
+        band = self._dband
+        if band.seam_out is None:
+            return None
+        a, b = band.seam_out[0] - self._c0, min(band.seam_out[1], self._c0 + self._ch) - self._c0
+        return self._acc[:, a:b, :]
+
+    def seamIn(self, strip) -> None:
+        """Installs the previous rank's accumulator strip as the starting state of this rank's ``seam_in`` rows."""
+        band = self._dband
+        if band.seam_in is None:
+            return
+        a, b = band.seam_in[0] - self._c0, band.seam_in[1] - self._c0
+        if tuple(strip.shape) != (3, b - a, self.plan.canvas_w):
+            raise ValueError(f"seam strip must have shape {(3, b - a, self.plan.canvas_w)}, got {tuple(strip.shape)}")
+        self._acc[:, a:b, :].copy_(strip)
+
+    def _exchange_seams(self) -> None:
+        """The one exchange step of dedup mode: accumulator strips travel from every rank to the next one by
+        point-to-point send / recv (NCCL over NVLink on the GPUs).  No strip depends on another rank's strip (bands are
+        taller than the overlap), so all transfers are posted at once."""
+        if self.world_size == 1:
+            return
+        torch = _torch()
+        import torch.distributed as dist
+        band = self._dband
+        ops, recv = [], None
+        out = self.seamOut()
+        if out is not None:
+            send = out.contiguous()
+            ops.append(dist.P2POp(dist.isend, send, self.rank + 1))
+        if band.seam_in is not None:
+            recv = torch.empty((3, band.seam_in[1] - band.seam_in[0], self.plan.canvas_w), dtype=torch.float32,
+                               device=self.device)
+            ops.append(dist.P2POp(dist.irecv, recv, self.rank - 1))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        if recv is not None:
+            self.seamIn(recv)
+
+    def processBandFinish(self) -> None:
+        """Dedup mode, phase 2: blend the kept predictions into the seam rows (now holding the previous rank's state),
+        then rebuildTile's tail (:404-413) and the crop of rebuildMap (:541-545) for this rank's output rows."""
+        plan, band = self.plan, self._dband
+        if band.seam_in is not None:
+            for pred, lohi, k0, n, gy_lo, gy_hi, add_half in self._retained:
+                self._accumulate(pred, lohi, k0, n, gy_lo, gy_hi, add_half, band.seam_in[0], band.seam_in[1])
+        self._retained = []
+        rows = self._out_r1 - self._out_r0
+        if rows > 0:
+            acc = self._acc
+            first = ((self._out_r0 + plan.off - self._c0) * plan.canvas_w + plan.off) * 4
+            _lib.check(self._lib.msr_blend_finalize(acc[0].data_ptr() + first, acc[1].data_ptr() + first,
+                                                    acc[2].data_ptr() + first, plan.canvas_w, rows, plan.width,
+                                                    float(np.float32(self.no_value)), self.mean_out.data_ptr(),
+                                                    self.std_out.data_ptr(), self.good_out.data_ptr(), plan.width,
+                                                    _lib.stream_ptr()), "msr_blend_finalize")
+            self.launches += 1
+
+    def processBand(self, eps=None) -> None:
+        """Dedup mode: the whole band of this rank (the counterpart of the processTile loop)."""
+        if self.mode != "dedup":
+            raise ValueError("processBand needs mode='dedup'")
+        self.processBandMain(eps)
+        self._exchange_seams()
+        self.processBandFinish()
+
     def _save_tile_bufs(self, bufs, px, py) -> None:
         m, s, g = (x.cpu().numpy() for x in bufs)
         self.saveTile(m, s, g, str(px) + "_" + str(py))
@@ -601,7 +813,11 @@ class DEMSuperResolution:
         self.saveGTiff(good, good.dtype, "good")
 
     def processTiles(self) -> None:
-        """Every tile of this rank's band, in tile-list order (process_full_tiles.py:579-581)."""
+        """Every tile of this rank's band, in tile-list order (process_full_tiles.py:579-581); in dedup mode the band
+        of the global patch lattice."""
+        if self.mode == "dedup":
+            self.processBand()
+            return
         for tile in self.my_tiles:
             self.processTile(*tile)
 
@@ -613,6 +829,10 @@ class DEMSuperResolution:
         tile_list = self.generateTileList()
         print("Cutting the image in", self.dem_shape[1] // self.tile_size + 1, "by",
               self.dem_shape[0] // self.tile_size + 1, "tiles.")
+        if self.mode == "dedup":
+            print("Processing lattice rows", self._dband.j0, "to", self._dband.j1, "(dedup mode)")
+            self.processBand()
+            tile_list = []
         for tile in tile_list:
             if tuple(tile) in self._tile_plan:
                 print("Processing tile", tile[0], tile[1])
@@ -625,6 +845,8 @@ class DEMSuperResolution:
     def rowsNeeded(self, height: int, width: int) -> Tuple[int, int]:
         """Raster rows [r0, r1) this rank's band reads (its tiles plus the I - S halo), before any data is loaded."""
         plan = Plan(height, width, self.image_size, self.stride, self.tile_size, self.batch_size)
+        if self.mode == "dedup":
+            return self._rows_dedup(plan, self.rank)[1]
         tiles, _, _ = band_of_rank(plan, self.world_size, self.rank)
         if not tiles:
             return 0, 0

@@ -11,7 +11,7 @@ Restates, as closed-form integer arithmetic, the loop structure of the reference
 from __future__ import annotations
 
 import dataclasses
-from typing import List, Sequence, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -99,6 +99,66 @@ class Plan:
     def tile_window(self, px: int, py: int) -> Tuple[int, int]:
         """(rows, cols) of tile (px, py) that survive the crop of rebuildMap (process_full_tiles.py:541-545)."""
         return min(self.tile_size, self.height - py), min(self.tile_size, self.width - px)
+
+
+    # ---- dedup mode (SURVEY.md section 8e, mode B) --------------------------------------------------------------------
+    def lattice_counts(self) -> Tuple[int, int]:
+        """(GY, GX): patch origins per axis of the union of all tiles' windows (process_full_tiles.py:453-454 over the
+        tile list :313-325).  Needs S | T so that the lattices of neighbouring tiles coincide."""
+        s, t = self.stride, self.tile_size
+        if t % s != 0:
+            raise ValueError("dedup mode needs stride | tile_size (the tiles' patch lattices must coincide)")
+        n_ty, n_tx = -(-self.height // t), -(-self.width // t)
+        return len(range(0, n_ty * t + self.off, s)), len(range(0, n_tx * t + self.off, s))
+
+    def dedup_band(self, world_size: int, rank: int) -> "DedupBand":
+        """Band of lattice rows owned by ``rank`` and everything that follows from it (all in canvas rows unless the
+        name says raster).  Rows are split evenly; a band must be at least as tall as the overlap so that only
+        adjacent ranks share accumulator rows."""
+        if world_size <= 0 or not (0 <= rank < world_size):
+            raise ValueError("bad rank / world_size")
+        gy, gx = self.lattice_counts()
+        i, s, p, off = self.image_size, self.stride, self.purge, self.off
+        # lattice rows whose patches lie inside the raster rows carry the work (the others see only no_value padding):
+        # cut so that every rank gets the same number of those
+        inside = [1 if (j * s >= off and j * s + i <= off + self.height) else 0 for j in range(gy)]
+        total = sum(inside)
+        first_in = inside.index(1) if total else 0
+        cuts = [0] + [first_in + (r * total) // world_size for r in range(1, world_size)] + [gy]
+        j0, j1 = cuts[rank], cuts[rank + 1]
+        if world_size > 1 and min(b - a for a, b in zip(cuts[:-1], cuts[1:])) < max(1, -(-(i - 2 * p) // s)):
+            raise ValueError(f"{world_size} ranks leave fewer lattice rows per band than one patch spans "
+                             f"({gy} rows in total): use fewer ranks for this raster")
+        first, last = rank == 0, rank == world_size - 1
+        # A band finalises canvas rows [j0*S + q, j1*S + q): no patch of the NEXT band reaches above j1*S + p, and the
+        # patches of the PREVIOUS band reach down to j0*S + off - p -- the seam, present iff that lies below j0*S + q.
+        q = min(p, off)
+        overlap = off - p > q
+        return DedupBand(
+            j0=j0, j1=j1, gx=gx,
+            read=(j0 * s, min(self.canvas_h, (j1 - 1) * s + i)),
+            out=(0 if first else j0 * s + q, self.canvas_h if last else j1 * s + q),
+            seam_in=None if first or not overlap else (j0 * s + q, j0 * s + off - p),
+            seam_out=None if last or not overlap else (j1 * s + q, j1 * s + off - p))
+
+
+@dataclasses.dataclass(frozen=True)
+class DedupBand:
+    """One rank's share of the global patch lattice in dedup mode.  ``read``: canvas rows its patches read (= rows of its
+    accumulators); ``out``: canvas rows it finalises; ``seam_in`` / ``seam_out``: accumulator rows received from the
+    previous / sent to the next rank (None at the ends or without overlap)."""
+    j0: int
+    j1: int
+    gx: int
+    read: Tuple[int, int]
+    out: Tuple[int, int]
+    seam_in: Optional[Tuple[int, int]]
+    seam_out: Optional[Tuple[int, int]]
+
+    def raster_rows(self, rows: Tuple[int, int], off: int, height: int) -> Tuple[int, int]:
+        """Canvas row range -> raster row range, clipped to the raster."""
+        r0 = min(max(rows[0] - off, 0), height)
+        return r0, max(r0, min(rows[1] - off, height))
 
 
 def plan_batches(valid_keys: Sequence[Tuple[int, int]], batch_size: int) -> List[List[Tuple[int, int]]]:

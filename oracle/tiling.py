@@ -126,6 +126,26 @@ def denormalize(pred01: np.ndarray, lo: np.float32, hi: np.float32) -> np.ndarra
     return pred01 * f32(f32(hi) - f32(lo)) + f32(lo)
 
 
+def accumulate_patch(w_sum: np.ndarray, mean: np.ndarray, s_acc: np.ndarray, pred: np.ndarray, lohi, kx: int, ky: int,
+                     w: np.ndarray, i: int, p: int) -> None:
+    """One iteration of rebuildTile's loop (process_full_tiles.py:395-402) on float32 accumulators of any extent:
+    the patch whose origin is (kx, ky) in accumulator coordinates updates rows [ky+p, ky+I-p) x cols [kx+p, kx+I-p)."""
+    f32, f64 = np.float32, np.float64
+    lo, hi = lohi
+    d = denormalize(pred, lo, hi)[p:i - p, p:i - p]                                      # float32 (or float64)
+    ys, xs = slice(ky + p, ky + i - p), slice(kx + p, kx + i - p)
+    w_sum[ys, xs] = (w_sum[ys, xs].astype(f64) + w).astype(f32)                          # :398
+    m_old = mean[ys, xs].copy()
+    delta_old = d - m_old                                                                # dtype of d
+    m_new = (m_old.astype(f64) + (w / w_sum[ys, xs].astype(f64)) * delta_old.astype(f64)).astype(f32)  # :401
+    mean[ys, xs] = m_new
+    # :400 binds ``mean_old`` to a *view* of ``mean``; after the store of :401 that view already shows the
+    # new mean, so :402 really evaluates  w * (d - mean_new) * (d - mean_new)  -- the textbook
+    # (d - mean_old)(d - mean_new) product never happens.  Reproduced because parity is against the code.
+    delta_new = d - m_new                                                                # dtype of d
+    s_acc[ys, xs] = (s_acc[ys, xs].astype(f64) + (w * delta_new.astype(f64)) * delta_new.astype(f64)).astype(f32)  # :402
+
+
 def rebuild_tile(generated: Dict[Tuple[int, int], np.ndarray],
                  minmax: Dict[Tuple[int, int], Tuple[np.float32, np.float32]],
                  geo: Geometry, no_value: float,
@@ -146,19 +166,7 @@ def rebuild_tile(generated: Dict[Tuple[int, int], np.ndarray],
     mean = np.zeros((a, a), f32)
     s_acc = np.zeros((a, a), f32)
     for (kx, ky), pred in generated.items():
-        lo, hi = minmax[(kx, ky)]
-        d = denormalize(np.asarray(pred), lo, hi)[p:i - p, p:i - p]                     # float32 (or float64)
-        ys, xs = slice(ky + p, ky + i - p), slice(kx + p, kx + i - p)
-        w_sum[ys, xs] = (w_sum[ys, xs].astype(f64) + w).astype(f32)                      # :398
-        m_old = mean[ys, xs].copy()
-        delta_old = d - m_old                                                            # dtype of d
-        m_new = (m_old.astype(f64) + (w / w_sum[ys, xs].astype(f64)) * delta_old.astype(f64)).astype(f32)  # :401
-        mean[ys, xs] = m_new
-        # :400 binds ``mean_old`` to a *view* of ``mean``; after the store of :401 that view already shows the
-        # new mean, so :402 really evaluates  w * (d - mean_new) * (d - mean_new)  -- the textbook
-        # (d - mean_old)(d - mean_new) product never happens.  Reproduced because parity is against the code.
-        delta_new = d - m_new                                                            # dtype of d
-        s_acc[ys, xs] = (s_acc[ys, xs].astype(f64) + (w * delta_new.astype(f64)) * delta_new.astype(f64)).astype(f32)  # :402
+        accumulate_patch(w_sum, mean, s_acc, np.asarray(pred), minmax[(kx, ky)], kx, ky, w, i, p)
     w_c = w_sum[o:a - o, o:a - o]
     m_c = mean[o:a - o, o:a - o].copy()
     s_c = s_acc[o:a - o, o:a - o]
@@ -243,3 +251,66 @@ def process_map(dem: np.ndarray, img: np.ndarray, image_size: int, stride: int, 
         m, s, g = process_tile(dem_c, img_c, geo, xx, yy, batch_size, no_value, model)
         means[(xx, yy)], stds[(xx, yy)], goods[(xx, yy)] = m, s, g
     return (assemble(means, geo, np.float32), assemble(stds, geo, np.float32), assemble(goods, geo, np.uint8))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Dedup mode (mode B): every patch position of the global stride lattice is generated once.
+# Not a restatement of reference code -- the reference recomputes the I - S halo of every tile -- but built from the
+# restated pieces above; for a model whose output does not depend on batch composition it is bit-identical to
+# ``process_map`` (tests/test_oracle_tiling.py), because every pixel receives the same patches in the same order.
+# ----------------------------------------------------------------------------------------------------------------------
+def lattice_counts(geo: Geometry) -> Tuple[int, int]:
+    """(GY, GX): patch origins per axis of the union of all tiles' windows (process_full_tiles.py:453-454 over
+    generateTileList :313-325); needs S | T so that the tiles' lattices coincide."""
+    if geo.tile_size % geo.stride != 0:
+        raise ValueError("dedup mode needs stride | tile_size")
+    t = geo.tile_size
+    n_ty, n_tx = -(-geo.height // t), -(-geo.width // t)
+    return (len(range(0, n_ty * t + geo.off, geo.stride)), len(range(0, n_tx * t + geo.off, geo.stride)))
+
+
+def process_map_dedup(dem: np.ndarray, img: np.ndarray, image_size: int, stride: int, batch_size: int, tile_size: int,
+                      no_value: float = -32768.0, model: Optional[ModelFn] = None,
+                      row_bands: Optional[Sequence[Tuple[int, int]]] = None, return_plan: bool = False):
+    """Global-lattice form of process_map: valid patches visited y outer / x inner over the whole canvas, chopped into
+    batches of ``batch_size`` per band of lattice rows (``row_bands`` = [(j0, j1)], default one band; the last batch of
+    a band is padded with float32 zero inputs), blended into canvas-sized float32 accumulators with the reference's
+    update (accumulate_patch), finalised and cropped like rebuildTile :404-413 / rebuildMap :541-545."""
+    f32 = np.float32
+    geo = Geometry(dem.shape[0], dem.shape[1], image_size, stride, tile_size)
+    i, s, p, o = image_size, stride, geo.purge, geo.off
+    gy, gx = lattice_counts(geo)
+    dem_c, img_c = pad_inputs(dem, img, geo, no_value)
+    w = blend_weights(i)
+    w_sum = np.zeros((geo.canvas_h, geo.canvas_w), f32)
+    mean = np.zeros_like(w_sum)
+    s_acc = np.zeros_like(w_sum)
+    plan_out = []
+    for (j0, j1) in (row_bands if row_bands is not None else [(0, gy)]):
+        keys, inputs, mm = [], {}, {}
+        for yy in range(j0 * s, j1 * s, s):
+            for xx in range(0, gx * s, s):
+                if not patch_is_valid(dem_c, img_c, xx, yy, i, no_value):
+                    continue
+                x, lohi = normalize_patch(img_c[yy:yy + i, xx:xx + i], dem_c[yy:yy + i, xx:xx + i])
+                keys.append((xx, yy))
+                inputs[(xx, yy)] = x
+                mm[(xx, yy)] = lohi
+        batches = batch_plan(keys, batch_size)
+        plan_out.append(batches)
+        for slots in batches:
+            batch = np.array([inputs[k] if k != (-1, -1) else np.zeros((i, i, 2), f32) for k in slots])
+            pred = batch if model is None else model(batch, training=False)
+            pred = (np.array(pred)[:, :, :, -1] + 0.5).astype(f32, copy=False)            # :340
+            for k, y in zip(slots, pred):
+                if k != (-1, -1):
+                    accumulate_patch(w_sum, mean, s_acc, y, mm[k], k[0], k[1], w, i, p)
+    h, wd = geo.height, geo.width
+    w_c, m_c, s_c = w_sum[o:o + h, o:o + wd], mean[o:o + h, o:o + wd].copy(), s_acc[o:o + h, o:o + wd]
+    good = w_c > 0
+    with np.errstate(divide="ignore", invalid="ignore"):
+        std = np.sqrt(s_c / w_c).astype(f32)
+    m_c[~good] = f32(no_value)
+    std[~good] = f32(no_value)
+    out = (m_c, std, good.astype(np.uint8))
+    return (out, plan_out) if return_plan else out

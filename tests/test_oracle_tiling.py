@@ -69,3 +69,26 @@ def test_slot_counts_interior_tile():
         assert len(keys) == patches
         plan = tiling.batch_plan(keys, b)
         assert len(plan) == batches and sum(len(p) for p in plan) == slots
+
+
+@pytest.mark.parametrize("name", ["wobble_200x260", "wobble_1100x1300"])
+def test_dedup_oracle_equals_tile_by_tile_for_per_sample_models(name):
+    """The dedup-mode oracle (global lattice, each patch generated once) is pinned by the pinned tile-by-tile oracle:
+    with a model that does not depend on batch composition every pixel receives the same patches in the same order, so
+    the rasters are bit-identical -- also when the lattice rows are cut into per-rank bands."""
+    import toy_models
+    from moonsuperresolution_b200.planner import Plan
+    case = golden_inputs.CASES[name]
+    dem, img = golden_inputs.make_rasters(case)
+    args = (dem, img, case["I"], case["S"], case["B"], case["T"], case["NV"], toy_models.ripple)
+    with np.errstate(all="ignore"):
+        ref = tiling.process_map(*args)
+        plan = Plan(case["H"], case["W"], case["I"], case["S"], case["T"], case["B"])
+        assert tiling.lattice_counts(tiling.Geometry(case["H"], case["W"], case["I"], case["S"], case["T"])) == \
+            plan.lattice_counts()
+        for world in (1, 3):
+            bands = [(plan.dedup_band(world, r).j0, plan.dedup_band(world, r).j1) for r in range(world)]
+            got, batches = tiling.process_map_dedup(*args, row_bands=bands, return_plan=True)
+            for a, b in zip(got, ref):
+                np.testing.assert_array_equal(a, b)
+            assert len(batches) == world

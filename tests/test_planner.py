@@ -106,3 +106,49 @@ def test_parse_args_mirrors_the_reference_cli():
     assert (cfg.image_size, cfg.stride, cfg.batch_size, cfg.model_path) == (512, 64, 12, "w/")
     with pytest.raises(SystemExit):
         parse_args(["--map_name", "m"])                     # required flags, as in the reference
+
+
+@pytest.mark.parametrize("dims,world", [((15000, 70000, 512, 128, 1024, 16), 8), ((8192, 8192, 512, 128, 1024, 16), 2),
+                                        ((200, 260, 32, 8, 128, 5), 3), ((4096, 4096, 256, 32, 1024, 16), 4),
+                                        ((200, 200, 32, 32, 128, 3), 2)])
+def test_dedup_bands_partition_lattice_and_canvas(dims, world):
+    """Dedup mode (mode B): lattice rows and finalised canvas rows are partitioned once, every band reads a
+    superset of what it finalises, and the strip a rank sends is the strip the next one expects."""
+    plan = Plan(*dims)
+    gy, gx = plan.lattice_counts()
+    i, s, p = plan.image_size, plan.stride, plan.purge
+    assert (gy - 1) * s + i <= plan.canvas_h and (gx - 1) * s + i <= plan.canvas_w
+    bands = [plan.dedup_band(world, r) for r in range(world)]
+    assert bands[0].j0 == 0 and bands[-1].j1 == gy and bands[0].out[0] == 0 and bands[-1].out[1] == plan.canvas_h
+    rows_out = 0
+    for a, b in zip(bands[:-1], bands[1:]):
+        assert a.j1 == b.j0 and a.out[1] == b.out[0]
+        assert a.seam_out == b.seam_in
+        if a.seam_out is not None:
+            # the strip lies inside both ranks' accumulators and below what the sender finalises
+            assert a.read[0] <= a.seam_out[0] and a.seam_out[1] <= a.read[1]
+            assert b.read[0] <= b.seam_in[0] and b.seam_in[1] <= b.read[1]
+            assert a.seam_out[0] == a.out[1]
+            # it ends where the sender's last patch row stops contributing
+            assert a.seam_out[1] == (a.j1 - 1) * s + i - p
+    for k, band in enumerate(bands):
+        assert band.j1 - band.j0 >= 1
+        lo, hi = band.out
+        if k > 0:
+            assert band.read[0] <= lo
+        if k < world - 1:
+            assert hi <= band.read[1]
+        r0, r1 = band.raster_rows(band.out, plan.off, plan.height)
+        rows_out += r1 - r0
+    assert rows_out == plan.height
+    # work balance: lattice rows whose patches lie inside the raster are spread evenly
+    inside = lambda j: j * s >= plan.off and j * s + i <= plan.off + plan.height
+    counts = [sum(inside(j) for j in range(b.j0, b.j1)) for b in bands]
+    assert max(counts) - min(counts) <= 1
+
+
+def test_dedup_rejects_bad_geometry():
+    with pytest.raises(ValueError):
+        Plan(150, 330, 24, 16, 120, 7).lattice_counts()              # S divides T + I but not T
+    with pytest.raises(ValueError):
+        Plan(200, 260, 32, 8, 128, 5).dedup_band(16, 0)              # bands thinner than a patch

@@ -21,3 +21,12 @@ def wobble(x, training=False):
     ortho, dem = x[..., 0], x[..., 1]
     y = dem * np.float32(0.875) + ortho * ortho * np.float32(0.0625) + slot * np.float32(0.03125)
     return y[..., None].astype(np.float32)
+
+
+def ripple(x, training=False):
+    """Per-sample stand-in (no dependence on the slot or on the rest of the batch, float32 out whatever the input dtype):
+    the model class for which dedup mode must equal the reference's tile-by-tile result bit for bit."""
+    x = np.asarray(x, dtype=np.float32)
+    ortho, dem = x[..., 0], x[..., 1]
+    y = dem * np.float32(0.875) + ortho * ortho * np.float32(0.0625) + ortho * dem * np.float32(0.03125)
+    return y[..., None].astype(np.float32)
