@@ -54,7 +54,8 @@ int msr_device_sm_count(void);
 #define MSR_PROF_VALIDITY 8
 #define MSR_PROF_GATHER 9    /* gather + normalise */
 #define MSR_PROF_BLEND 10
-#define MSR_PROF_COUNT 11
+#define MSR_PROF_PREPROCESS 11 /* preprocess: 1/4 area resize, cubic upsampling */
+#define MSR_PROF_COUNT 12
 
 /* Turns event timing on (clears the counters) or off. */
 int msr_profile_enable(int on);
@@ -64,6 +65,26 @@ int msr_profile_read(double* ms, double* work, int64_t* launches);
 /* Per-launch-group records of one family, in launch order: fills up to `capacity` entries of ms / work and returns the
  * total number of records in *count. */
 int msr_profile_records(int family, double* ms, double* work, int64_t capacity, int64_t* count);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * preprocess  (process_full_tiles.py:226-244): DEM -> 1/4 -> (small-hole fill on the host) -> 1/16 -> bicubic to full size
+ * ------------------------------------------------------------------------------------------------------------- */
+
+/* cv2.resize(x, (0, 0), fx=0.25, fy=0.25, interpolation=cv2.INTER_AREA) of a (H, W) float32 raster
+ * (process_full_tiles.py:232, 240) with the bookkeeping around it fused: pixels <= no_value count as NaN (:230, :238), a
+ * NaN result is stored as no_value (:233).  (dh, dw) must be (round(H/4), round(W/4)), rounding half to even as cv2 does.
+ * Bit-exact with OpenCV's own float32 code: 4x4 box mean; windows cut by the raster edge are averaged over the pixels
+ * that exist. */
+int msr_resize_area4(const float* d_src, int H, int W, float* d_dst, int dh, int dw, float no_value, void* stream);
+
+/* cv2.resize(x, (W, H), interpolation=cv2.INTER_CUBIC) of a (h, w) float32 raster (process_full_tiles.py:241), source
+ * pixels <= no_value read as NaN (:238), NaN results stored as no_value (:243).  Per destination column / row the host
+ * supplies the source index of tap 1 (d_xofs (W), d_yofs (H); taps are ofs-1 .. ofs+2, clamped to the raster) and the
+ * four float32 weights (d_xcoef (W, 4), d_ycoef (H, 4), 16-byte aligned) -- moonsuperresolution_b200/preprocess.py
+ * builds them as OpenCV does.  Bit-exact with OpenCV's own code (pip wheels dispatch this call to Intel IPP, which
+ * rounds differently by a few ulp). */
+int msr_resize_cubic(const float* d_src, int h, int w, float* d_dst, int H, int W, const int32_t* d_xofs,
+                     const float* d_xcoef, const int32_t* d_yofs, const float* d_ycoef, float no_value, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Tiling / blending  (process_full_tiles.py)

@@ -29,6 +29,8 @@ SIGNATURES: Dict[str, tuple] = {
     "msr_profile_enable": (_i, [_i]),
     "msr_profile_read": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_i64)]),
     "msr_profile_records": (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_double), _i64, C.POINTER(_i64)]),
+    "msr_resize_area4": (_i, [_vp, _i, _i, _vp, _i, _i, _f, _vp]),
+    "msr_resize_cubic": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _f, _vp]),
     "msr_pad_inputs": (_i, [_vp, _vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "msr_validity_sat": (_i, [_vp, _vp, _i, _i, _f, _vp, _vp]),
     "msr_patch_validity": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _vp]),
@@ -94,7 +96,7 @@ def lib() -> C.CDLL:
 
 
 PROFILE_FAMILIES = ("conv_tc", "conv_f32", "mask_conv", "stats", "elementwise", "dense", "final_conv", "pad",
-                    "validity", "gather", "blend")
+                    "validity", "gather", "blend", "preprocess")
 
 
 def profile_enable(on: bool) -> None:

@@ -54,13 +54,16 @@ class DSRConfig:
     save_tiles: bool = False        # write the per-tile TIFFs of saveTile (process_full_tiles.py:416-429)
     groups_per_call: int = 0        # batches pushed through one generator call (0 = the model's max_groups)
     seed: int = 0                   # seeds the Gaussian sampler's noise (the reference's is unseeded)
+    preprocess: bool = True         # run preprocess() inside processMap like the reference (:577); False = rasters are
+                                    # taken as already filtered
     mode: str = "faithful"          # "faithful": tile by tile like the reference (halo patches recomputed per tile);
                                     # "dedup": every position of the global patch lattice generated once
 
 
 def parse_args(argv=None) -> DSRConfig:
     """process_full_tiles.py:68-127 -- same flags, defaults and help texts' meaning; unknown flags are ignored
-    (parse_known_args, :114).  Additions: --save_tiles, --groups_per_call, --seed, --mode."""
+    (parse_known_args, :114).  Additions: --save_tiles, --groups_per_call, --seed, --mode,
+    --no_preprocess."""
     import argparse
     parser = argparse.ArgumentParser("DEM Super Resolution config parser.")
     parser.add_argument("--source_folder_path", type=str, required=True, default=None,
@@ -81,6 +84,8 @@ def parse_args(argv=None) -> DSRConfig:
     parser.add_argument("--save_tiles", action="store_true", help="Also write the per-tile TIFFs of saveTile.")
     parser.add_argument("--groups_per_call", type=int, default=0, help="Batches per generator call (0 = model's maximum).")
     parser.add_argument("--seed", type=int, default=0, help="Seed of the Gaussian sampler's noise.")
+    parser.add_argument("--no_preprocess", action="store_true",
+                        help="Skip preprocess() (1/16 box filter + cubic upsampling of the DEM) inside processMap.")
     parser.add_argument("--mode", type=str, default="faithful", choices=["faithful", "dedup"],
                         help="faithful: tile by tile like the reference; dedup: every patch position generated once.")
     args, _unknown = parser.parse_known_args(argv)
@@ -88,7 +93,8 @@ def parse_args(argv=None) -> DSRConfig:
                      ortho_image_name=args.ortho_image_name, dem_name=args.dem_name, model_path=args.model_path,
                      image_size=args.image_size, stride=args.stride, batch_size=args.batch_size,
                      tile_size=args.tile_size, no_value=args.no_value, upsample_factor=args.upsample_factor,
-                     save_tiles=args.save_tiles, groups_per_call=args.groups_per_call, seed=args.seed, mode=args.mode)
+                     save_tiles=args.save_tiles, groups_per_call=args.groups_per_call, seed=args.seed, mode=args.mode,
+                     preprocess=not args.no_preprocess)
 
 
 def main(argv=None) -> None:
@@ -136,6 +142,7 @@ class DEMSuperResolution:
         self.rank, self.world_size = int(rank), int(world_size)
         self._groups_cfg = int(getattr(config, "groups_per_call", 0))
         self.mode = str(getattr(config, "mode", "faithful"))
+        self._preprocess_cfg = bool(getattr(config, "preprocess", True))
         if self.mode not in ("faithful", "dedup"):
             raise ValueError("mode must be 'faithful' or 'dedup'")
         if self.mode == "dedup" and self.save_tiles:
@@ -162,12 +169,13 @@ class DEMSuperResolution:
         padInputs) or float32 CUDA tensors already resident on this engine's device.  A rank may hold only the rows
         [row_offset, row_offset + rows) of a raster that is ``full_height`` rows tall (inputs loaded sharded); they
         must cover the rows its band of tiles reads."""
-        if hasattr(dem, "is_cuda"):
-            if not (dem.is_cuda and img.is_cuda and str(dem.dtype) == "torch.float32" and str(img.dtype) == "torch.float32"):
-                raise ValueError("tensor rasters must be float32 CUDA tensors")
-        else:
-            dem = np.ascontiguousarray(dem, dtype=np.float32)
-            img = np.ascontiguousarray(img, dtype=np.float32)
+        def as_raster(a):
+            if hasattr(a, "is_cuda"):
+                if not (a.is_cuda and str(a.dtype) == "torch.float32"):
+                    raise ValueError("tensor rasters must be float32 CUDA tensors")
+                return a
+            return np.ascontiguousarray(a, dtype=np.float32)
+        dem, img = as_raster(dem), as_raster(img)
         if dem.ndim != 2 or tuple(img.shape) != tuple(dem.shape):
             raise ValueError("dem and ortho-image must be 2-D arrays of the same shape")
         self.dem, self.img = dem, img
@@ -223,9 +231,22 @@ class DEMSuperResolution:
         self.setRasters(dem.astype(np.float32), img.astype(np.float32), geo, geo)
 
     def preprocess(self) -> None:
-        """process_full_tiles.py:226-244 (hole filling + /16 blur of the DEM) is the step BEFORE the hot path and is
-        out of scope of this build; inputs are taken as already pre-filtered."""
-        return
+        """process_full_tiles.py:226-244 -- the DEM is low-passed before it is tiled: 1/4 area resize, small-hole fill,
+        1/4 area resize, bicubic back to (H, W), with no_value carried as NaN through the resampling.  Both resampling
+        passes are kernels (msr_resize_area4 / msr_resize_cubic); see preprocess.py for the hole fill and for the two
+        places where this differs from the reference's code (dead ortho half not run; (W, H) / (H, W) mix-up of :241
+        not reproduced).  ``self.dem`` becomes a CUDA tensor.  No-op when the config says ``preprocess=False``."""
+        if not self._preprocess_cfg:
+            return
+        torch = _torch()
+        from . import preprocess as PP
+        if self.dem is None:
+            raise ValueError("no rasters loaded: call loadImages() or setRasters() first")
+        if self._row_offset != 0 or int(self.dem.shape[0]) != self.dem_shape[0]:
+            raise ValueError("preprocess() needs the whole DEM on this rank (it resamples across band boundaries)")
+        dem = self.dem if torch.is_tensor(self.dem) else torch.from_numpy(self.dem).to(self.device)
+        self.dem, n = PP.preprocess_dem(dem, self.no_value)
+        self.launches += n
 
     # ---------------------------------------------------------------------------------------------------------------
     # padInputs (+ validity of every patch)
@@ -266,11 +287,11 @@ class DEMSuperResolution:
             if r1 > r0 and (r0 < ro or r1 > ro + self.dem.shape[0]):
                 raise ValueError(f"rank {self.rank} needs raster rows [{r0}, {r1}) but holds "
                                  f"[{ro}, {ro + self.dem.shape[0]})")
-            if torch.is_tensor(self.dem):
-                d_dem, d_img = self.dem[r0 - ro:r1 - ro].contiguous(), self.img[r0 - ro:r1 - ro].contiguous()
-            else:
-                d_dem = torch.from_numpy(self.dem[r0 - ro:r1 - ro]).to(self.device, non_blocking=True)
-                d_img = torch.from_numpy(self.img[r0 - ro:r1 - ro]).to(self.device, non_blocking=True)
+            def rows_on_device(a):
+                if torch.is_tensor(a):
+                    return a[r0 - ro:r1 - ro].contiguous()
+                return torch.from_numpy(a[r0 - ro:r1 - ro]).to(self.device, non_blocking=True)
+            d_dem, d_img = rows_on_device(self.dem), rows_on_device(self.img)
             self.dem_padded = torch.empty((self._ch, plan.canvas_w), dtype=torch.float32, device=self.device)
             self.img_padded = torch.empty_like(self.dem_padded)
             if r1 > r0:

@@ -30,3 +30,27 @@ def make_rasters(case):
         dem[cy:cy + 4, cx:cx + 6] = nv        # small hole in the DEM
         img[h // 4, w // 2] = nv - 1.0        # single pixel below no_value in the ortho
     return dem, img
+
+
+# ---- preprocess (process_full_tiles.py:226-244) ------------------------------------------------------------------------
+PREPROCESS_CASES = {
+    # small hole (filled on the 1/4 raster by the Clough-Tocher interpolant), large hole and NV stripe (kept -> NaN spreads
+    # through the cubic upsampling), all inside one 256-block of the 1/4 raster
+    "holes_320": dict(N=320, seed=7, holes=True),
+    # clean raster: pure 1/16 box filter + cubic upsampling
+    "clean_192": dict(N=192, seed=8, holes=False),
+}
+
+
+def make_preprocess_case(name):
+    c = PREPROCESS_CASES[name]
+    n = c["N"]
+    rng = np.random.default_rng(c["seed"])
+    dem = (np.cumsum(np.cumsum(rng.standard_normal((n, n)), 0), 1) * 0.5 + 1500.0).astype(np.float32)
+    img = rng.uniform(1, 255, (n, n)).astype(np.float32)
+    if c["holes"]:
+        nv = np.float32(NV)
+        dem[150:158, 160:172] = nv      # 2 x 3 pixels of the 1/4 raster, inside the interior [32:48) of its fill block
+        dem[200:260, 40:120] = nv       # 15 x 20 pixels of the 1/4 raster: too large, stays
+        dem[0:3, :] = nv
+    return dem, img, NV

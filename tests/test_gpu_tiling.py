@@ -264,7 +264,7 @@ def test_save_tiles_and_geotiff_layout(msr, tmp_path):
     geotiff.write(str(tmp_path / "run-DRG.tif"), img)
     cfg = msr.DSRConfig(image_size=case["I"], stride=case["S"], batch_size=case["B"], tile_size=case["T"],
                         no_value=case["NV"], map_name="m", save_path=str(tmp_path / "out"),
-                        source_folder_path=str(tmp_path), save_tiles=True)
+                        source_folder_path=str(tmp_path), save_tiles=True, preprocess=False)
     (tmp_path / "out").mkdir()
     eng = msr.DEMSuperResolution(cfg, model=toy_models.wobble)
     eng.processMap()
