@@ -1,0 +1,33 @@
+"""N > 1 on real GPUs (skipped on a single-GPU box): torchrun, one process per GPU, NCCL.  See multi_gpu_worker.py."""
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def test_sharded_loading_and_seam_exchange_over_nccl():
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    n = min(n, 4)
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "multi_gpu_worker.py")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr",
+           "127.0.0.1", "--master-port", str(_free_port()), worker]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    print(out.stdout[-3000:])
+    print(out.stderr[-3000:])
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert out.stdout.count("bit-identical") == 3
