@@ -76,14 +76,21 @@ class _Generator:
         self._finalized = True
 
     def load(self, *paths: str) -> None:
-        """Reference: ``gaugan.load(path+'generator', path+'discriminator', path+'encoder')``
-        (process_full_tiles.py:30,50; spade/models/model.py:607-610, 822-824) reads Keras SavedModel directories.
-        Here the tensors come from ``<dirname(paths[0])>/weights.npz`` in Keras layout (a
-        SavedModel reader is a later row); the discriminator is never used at inference."""
+        """Reference: ``gaugan.load(path+'generator', path+'discriminator', path+'encoder')`` and, for CNNSpade,
+        ``load(path+'generator', path+'encoder')`` (process_full_tiles.py:30,50; spade/models/model.py:607-610,
+        822-824) -- Keras SavedModel directories written by ``save`` (:569-605).  When the first and last path are such
+        directories their variable bundles are read directly (savedmodel.py, no TensorFlow); the discriminator is never
+        used at inference.  Otherwise the tensors come from ``<dirname(paths[0])>/weights.npz`` in Keras layout."""
+        from . import savedmodel as SM
+        if len(paths) >= 2 and SM.is_saved_model_dir(paths[0]) and SM.is_saved_model_dir(paths[-1]):
+            if self.arch == "pix2pix":
+                raise ValueError("pix2pix weights are loaded from weights.npz (the reference never saves that model)")
+            self.set_weights(SM.load_gaugan_weights(paths[0], paths[-1], self.image_size, self.arch))
+            return
         base = os.path.dirname(os.path.normpath(paths[0])) if paths else ""
         npz = os.path.join(base, "weights.npz")
         if not os.path.exists(npz):
-            raise ValueError(f"weight file {npz} does not exist")
+            raise ValueError(f"neither SavedModel directories {paths[0]!r} / {paths[-1]!r} nor weight file {npz} exist")
         self.set_weights(W.load_npz(npz))
 
     def load_npz(self, path: str) -> None:

@@ -1,6 +1,8 @@
 """Parity of the CUDA generators (through the C ABI) with the torch-CPU oracle on identical weights / inputs / eps.
 Tolerances (BASELINE.json north_star): fp32 mode <= 1e-4, bf16 tensor-core mode <= 1e-2, max abs error on the
 normalised output (outputs are O(1))."""
+import os
+
 import numpy as np
 import pytest
 
@@ -292,3 +294,29 @@ def test_repeated_forward_calls_honour_new_output_buffers(msr, torch):
     torch.cuda.synchronize()
     assert not (out2 == 7.0).any()
     assert torch.equal(out1, out2)
+
+
+def test_load_gan_model_reads_saved_model_directories(msr, tmp_path):
+    """load_GAN_model(path, I, B) (process_full_tiles.py:13-31) on the directory layout GauGAN.save writes
+    (spade/models/model.py:569-605): <path>/generator, <path>/discriminator, <path>/encoder as Keras SavedModel
+    directories, read without TensorFlow (savedmodel.py); falls back to <path>/weights.npz."""
+    import tf_bundle_writer as TW
+    i, b = 64, 2
+    weights = W.random_init("spade", i, seed=11, perturb_affine=True)
+    root = str(tmp_path / "model") + os.sep
+    TW.write_gaugan_saved_models(root, weights, compress=True)
+    x, eps = inputs(i, b, seed=2)
+    want = msr.GauGAN(i, b, precision="fp32", weights=weights, eps_fn=lambda call, n: eps)(x, training=False)
+    loaded = msr.load_GAN_model(root, i, b, precision="fp32", eps_fn=lambda call, n: eps)
+    np.testing.assert_array_equal(loaded(x, training=False), want)
+    cnn = msr.load_CNN_model(root, i, b, precision="fp32")
+    assert cnn(x, training=False).shape == (b, i, i, 1)
+    # npz fallback
+    root2 = str(tmp_path / "model2") + os.sep
+    os.makedirs(root2)
+    W.save_npz(os.path.join(root2, "weights.npz"), weights)
+    again = msr.load_GAN_model(root2, i, b, precision="fp32", eps_fn=lambda call, n: eps)
+    np.testing.assert_array_equal(again(x, training=False), want)
+    os.makedirs(str(tmp_path / "empty"))
+    with pytest.raises(ValueError):
+        msr.load_GAN_model(str(tmp_path / "empty") + os.sep, i, b)

@@ -1,0 +1,82 @@
+"""SavedModel / TensorBundle reader against an independent writer of the same published format
+(tests/tf_bundle_writer.py).  No TensorFlow-written file exists here: PARITY UNPINNED for the container format."""
+import os
+import struct
+
+import numpy as np
+import pytest
+
+import tf_bundle_writer as TW
+from moonsuperresolution_b200 import savedmodel as SM
+from moonsuperresolution_b200 import weights as W
+
+
+def test_crc32c_known_answers():
+    # RFC 3720 B.4 test vectors for CRC-32C
+    assert SM.crc32c(b"123456789") == 0xE3069283
+    assert SM.crc32c(bytes(32)) == 0x8A9136AA
+    assert SM.crc32c(bytes([0xFF] * 32)) == 0x62A8AB43
+    assert SM.crc32c(bytes(range(32))) == 0x46DD794E
+    assert SM.crc32c(b"123456789") == TW.crc32c(b"123456789")
+
+
+def test_snappy_decoder():
+    # hand-assembled stream: literal "abcd", copy(offset 4, len 8, 1-byte-offset form) -> overlapping run, literal "xyz"
+    stream = TW.varint(15) + bytes([(4 - 1) << 2]) + b"abcd" + bytes([1 | ((8 - 4) << 2) | (0 << 5), 4]) + \
+        bytes([(3 - 1) << 2]) + b"xyz"
+    assert SM.snappy_decompress(stream) == b"abcdabcdabcdxyz"
+    # 2-byte-offset copy and a long literal (length byte form)
+    body = bytes(range(200))
+    stream = TW.varint(200 + 10) + bytes([60 << 2, 199]) + body + bytes([2 | ((10 - 1) << 2)]) + struct.pack("<H", 200)
+    assert SM.snappy_decompress(stream) == body + body[:10]
+    rng = np.random.default_rng(0)
+    for blob in (b"", b"a", b"layer_with_weights-1/spade_1/conv/kernel" * 50, rng.integers(0, 4, 5000, dtype=np.uint8).tobytes()):
+        assert SM.snappy_decompress(TW.snappy_compress(blob)) == blob
+    with pytest.raises(SM.BundleError):
+        SM.snappy_decompress(TW.varint(8) + bytes([2 | (7 << 2)]) + struct.pack("<H", 9))      # copy before any output
+
+
+@pytest.mark.parametrize("compress", [False, True])
+def test_bundle_round_trip_many_blocks(tmp_path, compress):
+    rng = np.random.default_rng(1)
+    tensors = {f"layer_with_weights-{k}/sub_{k % 7}/kernel" + TW.SUFFIX: rng.standard_normal((k % 5 + 1, 3, k % 4 + 1)).astype(np.float32)
+               for k in range(300)}                                         # > 4 KB of index: several data blocks
+    tensors["scalar" + TW.SUFFIX] = np.float32(3.5).reshape(())
+    prefix = str(tmp_path / "variables" / "variables")
+    TW.write_bundle(prefix, tensors, compress=compress, with_crc=True, extra_string_keys=("_CHECKPOINTABLE_OBJECT_GRAPH",))
+    got = SM.read_bundle(prefix, verify_blocks=True, verify_tensors=True)
+    assert set(got) == set(tensors)
+    for k, a in tensors.items():
+        np.testing.assert_array_equal(got[k], a)
+    # corruption is detected
+    raw = bytearray(open(prefix + ".index", "rb").read())
+    raw[10] ^= 0x40
+    open(prefix + ".index", "wb").write(raw)
+    with pytest.raises(SM.BundleError):
+        SM.read_bundle(prefix)
+    open(prefix + ".index", "wb").write(b"short")
+    with pytest.raises(SM.BundleError):
+        SM.read_bundle(prefix)
+
+
+def test_gaugan_saved_model_directories_round_trip(tmp_path):
+    """Layout of GauGAN.save (spade/models/model.py:569-605): <path>/generator, <path>/encoder as SavedModel directories
+    with Keras object-graph keys -> the weight dict of weights.model_spec, shapes checked."""
+    i = 64
+    weights = W.random_init("spade", i, seed=3, perturb_affine=True)
+    small = {k: v for k, v in weights.items()}
+    TW.write_gaugan_saved_models(str(tmp_path), small, compress=True)
+    assert SM.is_saved_model_dir(str(tmp_path / "generator")) and not SM.is_saved_model_dir(str(tmp_path))
+    got = SM.load_gaugan_weights(str(tmp_path / "generator"), str(tmp_path / "encoder"), i)
+    assert set(got) == set(weights)
+    for k in weights:
+        np.testing.assert_array_equal(got[k], weights[k])
+    # key inventory: 8 weighted layers in the generator, 7 in the encoder
+    gk = SM.generator_key_map(i)
+    assert len({k.split("/")[0] for k in gk}) == 8 and len(gk) == len(W.spade_generator_spec(i))
+    ek = SM.encoder_key_map()
+    assert len({k.split("/")[0] for k in ek}) == 7 and len(ek) == len(W.encoder_spec(i))
+    # a missing variable is reported by name
+    os.remove(str(tmp_path / "encoder" / "variables" / "variables.index"))
+    with pytest.raises(SM.BundleError):
+        SM.load_gaugan_weights(str(tmp_path / "generator"), str(tmp_path / "encoder"), i)
