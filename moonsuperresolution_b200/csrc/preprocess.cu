@@ -56,11 +56,11 @@ __global__ void __launch_bounds__(256) resize_area4_kernel(const float* __restri
   dst[(int64_t)dy * dw + dx] = nan_to_nv(out, nv);
 }
 
-// One thread owns 4 adjacent destination columns and walks kCubicRows destination rows; the horizontally interpolated
+// One thread owns 4 adjacent destination columns and walks kCubicRows (16) destination rows; the horizontally interpolated
 // values of the 4 source rows under the current destination row are kept in registers and recomputed only when the
 // first-tap row changes (every ~16 rows at the path's x16 upsampling), so a destination pixel costs 4 multiplies and
 // 3 adds plus one 16-byte store.
-constexpr int kCubicRows = 32;
+constexpr int kCubicRows = 16;
 
 __global__ void __launch_bounds__(128) resize_cubic_kernel(const float* __restrict__ src, int h, int w,
                                                            float* __restrict__ dst, int H, int W,
