@@ -53,7 +53,8 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--cpu-sample", type=int, default=2, help="patches per CPU-baseline sample batch")
+    ap.add_argument("--cpu-sample", type=int, default=16,
+                    help="patches per CPU-baseline sample batch (16 = one reference batch: ~10-20 s of host work at 512)")
     ap.add_argument("--alt-tile-size", type=int, default=8192,
                     help="also time one step with this tile_size (0 = skip); reported beside, never as, the headline")
     ap.add_argument("--no-dedup", action="store_true",
@@ -220,7 +221,7 @@ def run_reference(args, rank):
                              "seconds_per_slot": sec_per_slot},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 def config_dict(args, n, plan, slots):
@@ -238,8 +239,32 @@ def config_dict(args, n, plan, slots):
                   (args.rows_per_gpu * plan.width * 4 / 1e6)}
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """stdout must carry exactly ONE JSON line.  Libraries write banners to file descriptor 1 behind Python's back (NCCL
+    prints its version there whatever NCCL_DEBUG_FILE says), so descriptor 1 is pointed at stderr for the whole run and
+    the JSON line goes to a private duplicate of the original stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
     args = parse()
+    claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -493,7 +518,7 @@ def main():
                 "roofline": roofline, "hbm_kernels": hbm_kernels, "cpu_baseline": cpu_baseline,
                 "alt_tile_size": alt, "dedup_mode": dedup,
                 "breakdown_instrumented_step": breakdown}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -320,3 +320,46 @@ def test_load_gan_model_reads_saved_model_directories(msr, tmp_path):
     os.makedirs(str(tmp_path / "empty"))
     with pytest.raises(ValueError):
         msr.load_GAN_model(str(tmp_path / "empty") + os.sep, i, b)
+
+
+def test_command_line_run_end_to_end(msr, tmp_path, capsys):
+    """The reference's ``python3 process_full_tiles.py --source_folder_path ... --model_path ...`` (:589-594) through this
+    package's CLI: GeoTIFF inputs, GauGAN weights from SavedModel directories, preprocess, tiles, three GeoTIFF outputs
+    (mean f32, std f32, good UInt16) with the DEM's extent; the same rasters as driving the engine by hand."""
+    import tf_bundle_writer as TW
+    from moonsuperresolution_b200 import engine, geotiff
+    i, b = 64, 4
+    weights = W.random_init("spade", i, seed=12, perturb_affine=True)
+    root = str(tmp_path / "weights") + os.sep
+    TW.write_gaugan_saved_models(root, weights)
+    rng = np.random.default_rng(6)
+    h = w_ = 256                                             # square, like every raster the reference can preprocess
+    dem = (np.cumsum(np.cumsum(rng.standard_normal((h, w_)), 0), 1) * 0.5 + 1500.0).astype(np.float32)
+    img = rng.uniform(1, 255, (h, w_)).astype(np.float32)
+    src = tmp_path / "in"
+    src.mkdir()
+    geotiff.write(str(src / "run-DEM.tif"), dem)
+    geotiff.write(str(src / "run-DRG.tif"), img)
+    out = tmp_path / "out"
+    out.mkdir()
+    argv = ["--source_folder_path", str(src), "--map_name", "crater", "--save_path", str(out), "--model_path", root,
+            "--image_size", str(i), "--stride", "32", "--batch_size", str(b), "--tile_size", "128", "--seed", "5"]
+    engine.main(argv)
+    assert "Cutting the image in" in capsys.readouterr().out
+    mean, _ = geotiff.read(str(out / "crater_mean.tiff"))
+    std, _ = geotiff.read(str(out / "crater_std.tiff"))
+    good, _ = geotiff.read(str(out / "crater_good.tiff"))
+    assert mean.shape == std.shape == good.shape == (h, w_)
+    assert mean.dtype == np.float32 and std.dtype == np.float32 and good.dtype == np.uint16
+    assert good.any() and np.isfinite(mean[good > 0]).all() and (mean[good == 0] == -32768.0).all()
+    # by hand: same config, same seed
+    cfg = engine.parse_args(argv)
+    eng = msr.DEMSuperResolution(cfg, model=msr.load_GAN_model(root, i, b, max_groups=8))
+    eng.setRasters(dem, img)
+    eng.preprocess()
+    eng.padInputs()
+    eng.processTiles()
+    m2, s2, g2, _ = eng.results()
+    np.testing.assert_array_equal(mean, m2)
+    np.testing.assert_array_equal(std, s2)
+    np.testing.assert_array_equal(good, g2.astype(np.uint16))
