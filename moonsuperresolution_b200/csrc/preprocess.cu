@@ -62,44 +62,37 @@ __global__ void __launch_bounds__(256) resize_area4_kernel(const float* __restri
 // 3 adds plus one 16-byte store.
 constexpr int kCubicRows = 16;
 
-__global__ void __launch_bounds__(128) resize_cubic_kernel(const float* __restrict__ src, int h, int w,
-                                                           float* __restrict__ dst, int H, int W,
-                                                           const int32_t* __restrict__ xofs,
-                                                           const float* __restrict__ xcoef,
-                                                           const int32_t* __restrict__ yofs,
-                                                           const float* __restrict__ ycoef, float nv) {
+__global__ void __launch_bounds__(128, 8) resize_cubic_kernel(const float* __restrict__ src, int h, int w,
+                                                              float* __restrict__ dst, int H, int W,
+                                                              const int32_t* __restrict__ xofs,
+                                                              const float* __restrict__ xcoef,
+                                                              const int32_t* __restrict__ yofs,
+                                                              const float* __restrict__ ycoef, float nv) {
   const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (x0 >= W) return;
   const int y0 = blockIdx.y * kCubicRows;
   const int y1 = min(H, y0 + kCubicRows);
-  int xi[4][4];
-  float xa[4][4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int x = min(x0 + j, W - 1);
-    const int o = __ldg(xofs + x) - 1;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      xi[j][k] = min(max(o + k, 0), w - 1);
-      xa[j][k] = __ldg(xcoef + 4 * x + k);
-    }
-  }
-  float t[4][4];  // [source row tap][column]
+  float t[4][4];  // [source row tap][column]: horizontally interpolated source rows under the current destination row
   int cur = INT_MIN;
   const bool vec_ok = ((W & 3) == 0) && (x0 + 3 < W);
   for (int y = y0; y < y1; ++y) {
     const int yo = __ldg(yofs + y);
-    if (yo != cur) {
+    if (yo != cur) {  // the 4-row source window moved (every ~16 rows at x16): redo the horizontal pass
       cur = yo;
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const float* row = src + (int64_t)min(max(yo - 1 + r, 0), h - 1) * w;
+      for (int j = 0; j < 4; ++j) {
+        const int x = min(x0 + j, W - 1);
+        const int o = __ldg(xofs + x) - 1;
+        const float4 a = __ldg(reinterpret_cast<const float4*>(xcoef) + x);
+        const int i0 = min(max(o, 0), w - 1), i1 = min(max(o + 1, 0), w - 1);
+        const int i2 = min(max(o + 2, 0), w - 1), i3 = min(max(o + 3, 0), w - 1);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float v = __fmul_rn(nv_to_nan(__ldg(row + xi[j][0]), nv), xa[j][0]);
-          v = __fadd_rn(v, __fmul_rn(nv_to_nan(__ldg(row + xi[j][1]), nv), xa[j][1]));
-          v = __fadd_rn(v, __fmul_rn(nv_to_nan(__ldg(row + xi[j][2]), nv), xa[j][2]));
-          v = __fadd_rn(v, __fmul_rn(nv_to_nan(__ldg(row + xi[j][3]), nv), xa[j][3]));
+        for (int r = 0; r < 4; ++r) {
+          const float* row = src + (int64_t)min(max(yo - 1 + r, 0), h - 1) * w;
+          float v = __fmul_rn(nv_to_nan(__ldg(row + i0), nv), a.x);
+          v = __fadd_rn(v, __fmul_rn(nv_to_nan(__ldg(row + i1), nv), a.y));
+          v = __fadd_rn(v, __fmul_rn(nv_to_nan(__ldg(row + i2), nv), a.z));
+          v = __fadd_rn(v, __fmul_rn(nv_to_nan(__ldg(row + i3), nv), a.w));
           t[r][j] = v;
         }
       }
@@ -150,8 +143,9 @@ extern "C" int msr_resize_cubic(const float* d_src, int h, int w, float* d_dst, 
                                 void* stream) {
   MSR_REQUIRE(d_src && d_dst && d_xofs && d_xcoef && d_yofs && d_ycoef, "msr_resize_cubic: null pointer");
   MSR_REQUIRE(h > 0 && w > 0 && H > 0 && W > 0, "msr_resize_cubic: empty raster");
-  MSR_REQUIRE((reinterpret_cast<uintptr_t>(d_ycoef) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_dst) & 15) == 0,
-              "msr_resize_cubic: d_ycoef and d_dst must be 16-byte aligned");
+  MSR_REQUIRE((reinterpret_cast<uintptr_t>(d_ycoef) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_xcoef) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(d_dst) & 15) == 0,
+              "msr_resize_cubic: d_xcoef, d_ycoef and d_dst must be 16-byte aligned");
   ProfileScope prof(MSR_PROF_PREPROCESS, (cudaStream_t)stream, 4.0 * ((double)H * W + (double)h * w));
   resize_cubic_kernel<<<dim3(ceil_div(ceil_div(W, 4), 128), ceil_div(H, kCubicRows)), 128, 0, (cudaStream_t)stream>>>(
       d_src, h, w, d_dst, H, W, d_xofs, d_xcoef, d_yofs, d_ycoef, no_value);

@@ -426,24 +426,48 @@ __global__ void __launch_bounds__(256) blend_accumulate_kernel(
 }
 
 // rebuildTile's tail (:404-413) over a window of the accumulators: good = w_sum > 0, std = sqrt(S / w_sum) in float32,
-// mean / std <- no_value where not good.
+// mean / std <- no_value where not good.  One thread per 4 adjacent pixels of a row: three 16-byte loads, two 16-byte and
+// one 4-byte store when the window is 16-byte aligned (it is whenever off, the canvas width and W are multiples of 4).
+__device__ __forceinline__ void finalize_pixel(float w, float m, float s, float nv, float& mo, float& so, uint8_t& go) {
+  const bool good = w > 0.f;                                          // :409
+  const float sd = __fsqrt_rn(__fdiv_rn(s, w));                       // :411
+  mo = good ? m : nv;                                                 // :412
+  so = good ? sd : nv;                                                // :413
+  go = good ? 1 : 0;
+}
+
 __global__ void __launch_bounds__(256) blend_finalize_kernel(const float* __restrict__ wsum,
                                                              const float* __restrict__ mean,
                                                              const float* __restrict__ sacc, int64_t acc_pitch,
                                                              int rows, int cols, float nv, float* __restrict__ mean_out,
                                                              float* __restrict__ std_out, uint8_t* __restrict__ good_out,
-                                                             int64_t out_pitch) {
-  const int64_t total = (int64_t)rows * cols;
-  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int r = (int)(e / cols), c = (int)(e % cols);
-    const int64_t a = (int64_t)r * acc_pitch + c;
-    const float w = __ldg(wsum + a);
-    const bool good = w > 0.f;                                          // :409
-    const float sd = __fsqrt_rn(__fdiv_rn(__ldg(sacc + a), w));         // :411
-    const int64_t o = (int64_t)r * out_pitch + c;
-    mean_out[o] = good ? __ldg(mean + a) : nv;                          // :412
-    std_out[o] = good ? sd : nv;                                        // :413
-    good_out[o] = good ? 1 : 0;
+                                                             int64_t out_pitch, int vec_ok) {
+  const int c0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int r = blockIdx.y;
+  if (c0 >= cols || r >= rows) return;
+  const int64_t a = (int64_t)r * acc_pitch + c0, o = (int64_t)r * out_pitch + c0;
+  if (vec_ok && c0 + 3 < cols) {
+    const float4 w = __ldcs(reinterpret_cast<const float4*>(wsum + a));
+    const float4 m = __ldcs(reinterpret_cast<const float4*>(mean + a));
+    const float4 s = __ldcs(reinterpret_cast<const float4*>(sacc + a));
+    float4 mo, so;
+    uchar4 go;
+    finalize_pixel(w.x, m.x, s.x, nv, mo.x, so.x, go.x);
+    finalize_pixel(w.y, m.y, s.y, nv, mo.y, so.y, go.y);
+    finalize_pixel(w.z, m.z, s.z, nv, mo.z, so.z, go.z);
+    finalize_pixel(w.w, m.w, s.w, nv, mo.w, so.w, go.w);
+    __stcs(reinterpret_cast<float4*>(mean_out + o), mo);
+    __stcs(reinterpret_cast<float4*>(std_out + o), so);
+    *reinterpret_cast<uchar4*>(good_out + o) = go;
+    return;
+  }
+  for (int j = 0; j < 4 && c0 + j < cols; ++j) {
+    float mo, so;
+    uint8_t go;
+    finalize_pixel(__ldg(wsum + a + j), __ldg(mean + a + j), __ldg(sacc + a + j), nv, mo, so, go);
+    mean_out[o + j] = mo;
+    std_out[o + j] = so;
+    good_out[o + j] = go;
   }
 }
 
@@ -563,9 +587,11 @@ extern "C" int msr_blend_finalize(const float* d_wsum, const float* d_mean_acc, 
   if (rows == 0 || cols == 0) return MSR_OK;
   const int64_t total = (int64_t)rows * cols;
   ProfileScope prof(MSR_PROF_BLEND, (cudaStream_t)stream, (double)total * 21.0);
-  const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 32);
-  blend_finalize_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_wsum, d_mean_acc, d_s, acc_pitch, rows, cols,
-                                                                  no_value, d_mean, d_std, d_good, out_pitch);
+  auto al = [](const void* p, int a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; };
+  const int vec_ok = al(d_wsum, 16) && al(d_mean_acc, 16) && al(d_s, 16) && al(d_mean, 16) && al(d_std, 16) &&
+                     al(d_good, 4) && (acc_pitch % 4 == 0) && (out_pitch % 4 == 0);
+  blend_finalize_kernel<<<dim3(ceil_div(ceil_div(cols, 4), 256), rows), 256, 0, (cudaStream_t)stream>>>(
+      d_wsum, d_mean_acc, d_s, acc_pitch, rows, cols, no_value, d_mean, d_std, d_good, out_pitch, vec_ok);
   count_launch();
   MSR_LAUNCH_CHECK();
   return MSR_OK;

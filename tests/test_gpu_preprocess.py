@@ -156,3 +156,36 @@ def test_non_square_raster_and_process_map(msr, torch, tmp_path):
     eng5.setRasters(dem[10:200], img[10:200], row_offset=10, full_height=h)
     with pytest.raises(ValueError):
         eng5.preprocess()
+
+
+def test_preprocess_large_non_aligned_raster_against_stock_cv2(msr, torch):
+    """A raster whose sides are not multiples of 16 (5003 x 7001: cvRound'ed intermediate extents, edge windows of the
+    box filter, non-integer cubic scale) against the reference's sequence run through stock cv2 on the host, plus
+    size-independent properties: a constant raster comes back constant, no_value regions grow by the filter footprint."""
+    cv2 = pytest.importorskip("cv2")
+    h, w = 5003, 7001
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    dem = (torch.cumsum(torch.randn((h, w), generator=gen, device="cuda"), 1) * 0.7 + 2000.0).contiguous()
+    dem[1000:1400, 2000:2600] = NV                                     # large hole: stays (no fill candidate)
+    host = dem.cpu().numpy()
+    eng = msr.DEMSuperResolution(msr.DSRConfig(no_value=NV))
+    eng.setRasters(dem, dem)
+    eng.preprocess()
+    got = eng.dem.cpu().numpy()
+    assert got.shape == (h, w)
+    with np.errstate(all="ignore"):
+        want = OP.reference_preprocess(host, NV)                        # cv2 (IPP) + scipy, fix_shape=True
+    np.testing.assert_array_equal(got <= NV, want <= NV)
+    ok = want > NV
+    q = host.copy()
+    q[q <= NV] = np.nan
+    q = OP.area4(OP.area4(q))
+    step = max(np.nanmax(np.abs(np.diff(q, axis=0))), np.nanmax(np.abs(np.diff(q, axis=1))))
+    ulp = np.float32(np.abs(want[ok]).max()) * np.float32(2.0 ** -23)
+    assert np.abs(got[ok] - want[ok]).max() <= 8 * ulp + 2.0 ** -21 * max(q.shape) * step
+    assert (got[1100:1300, 2100:2500] == NV).all() and (got[:900, :1900] > NV).all()
+    # constant raster: box mean and cubic weights (which sum to 1 up to rounding) keep it within 2 ulp
+    const = torch.full((h, w), 1234.5, device="cuda")
+    eng.setRasters(const, const)
+    eng.preprocess()
+    assert (eng.dem - 1234.5).abs().max().item() <= 2 * 1234.5 * 2.0 ** -23
