@@ -785,10 +785,17 @@ int forward_spade_bf16(Fwd& f, const float* source, const float* eps, float* out
     a.x = ex; a.w = g->enc_wt[k]; a.n = n; a.r = er; a.cin = kEnc[k - 1]; a.ncols = kEnc[k]; a.stride = 2; a.pad = 0;
     a.split3 = 1;
     a.epilogue = TC_EPI_BIAS_F32; a.y = g->enc_y;
-    if ((rc = tc_conv(f, a))) return rc;
     const int64_t rows = (int64_t)er * er;
-    if ((rc = channel_stats_f32(g->enc_y, kEnc[k], n, rows, kEnc[k], 1e-3f, g->stat_partial, g->enc_stats_mean,
-                                g->enc_stats_rstd, st))) return rc;
+    // InstanceNorm moments (per image, per channel) from the epilogue's per-tile column sums: a 128-pixel tile never
+    // spans two images once r*r >= 128, so image b owns tile rows [b, b + 1) * (r*r / 128) * 4 of the pair buffer
+    const bool fused = rows >= 128 && rows % 128 == 0;
+    a.stat_pairs = fused ? g->stat_pairs : nullptr;
+    if ((rc = tc_conv(f, a))) return rc;
+    if (fused) {
+      if ((rc = channel_stats_from_pairs(g->stat_pairs, n, rows / 128 * 4, rows, kEnc[k], 1e-3f, g->stat_partial,
+                                         g->enc_stats_mean, g->enc_stats_rstd, st))) return rc;
+    } else if ((rc = channel_stats_f32(g->enc_y, kEnc[k], n, rows, kEnc[k], 1e-3f, g->stat_partial, g->enc_stats_mean,
+                                       g->enc_stats_rstd, st))) return rc;
     __nv_bfloat16* eb = (k & 1) ? g->enc_b1 : g->enc_b0;
     if ((rc = affine_act_bf16out(g->enc_y, kEnc[k], g->enc_stats_mean, g->enc_stats_rstd, g->enc_g[k], g->enc_bt[k],
                                  k < 4 ? eb : nullptr, k == 4 ? g->enc_feat : nullptr, (int64_t)n * rows, kEnc[k], rows,
