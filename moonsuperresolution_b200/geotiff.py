@@ -135,7 +135,7 @@ def write(path: str, data: np.ndarray, geo: Optional[Dict[int, Tuple[int, int, b
 
 
 def read(path: str):
-    """Reads band 1 of a little-endian TIFF / BigTIFF: strips or tiles, uncompressed or LZW, predictor 1 / 2 / 3.
+    """Reads band 1 of a little-endian TIFF / BigTIFF: strips or tiles, uncompressed, LZW or Deflate, predictor 1 / 2 / 3.
     Returns (array, geo) where geo maps the GeoTIFF tag numbers present to (type, count, payload bytes)."""
     with open(path, "rb") as f:
         buf = f.read()
@@ -171,8 +171,8 @@ def read(path: str):
 
     w, h = ints(256)[0], ints(257)[0]
     compression = ints(259, [1])[0]
-    if compression not in (1, 5):
-        raise ValueError(f"TIFF compression {compression} is not supported (only none and LZW)")
+    if compression not in (1, 5, 8, 32946):
+        raise ValueError(f"TIFF compression {compression} is not supported (only none, LZW and Deflate)")
     predictor = ints(317, [1])[0]
     spp = ints(277, [1])[0]
     if spp != 1 and ints(284, [1])[0] != 2:
@@ -197,9 +197,24 @@ def read(path: str):
         cols0 = [0] * n
         chunk_rows, chunk_row_bytes = rps, w * itemsize
     out = np.empty((h, w), dtype)
+    offs, cnts = list(offs[:n]), list(cnts[:n])
+    if compression in (8, 32946):
+        # Deflate (GDAL's COMPRESS=DEFLATE): inflate every chunk with zlib (releases the GIL: thread pool), then hand the
+        # inflated image to the native codec as an uncompressed file -- it still undoes the predictor and pastes
+        import zlib
+        from concurrent.futures import ThreadPoolExecutor
+        raw = chunk_rows * chunk_row_bytes
+
+        def inflate(k):
+            if offs[k] < 0 or offs[k] + cnts[k] > len(buf):
+                raise ValueError("TIFF chunk outside the file")
+            return zlib.decompress(buf[offs[k]:offs[k] + cnts[k]])[:raw].ljust(raw, b"\0")
+        with ThreadPoolExecutor(_threads()) as pool:
+            buf = b"".join(pool.map(inflate, range(n)))
+        offs, cnts, compression = [k * raw for k in range(n)], [raw] * n, 1
     fbuf = np.frombuffer(buf, np.uint8)
-    a_off = np.asarray(offs[:n], np.int64)
-    a_cnt = np.asarray(cnts[:n], np.int64)
+    a_off = np.asarray(offs, np.int64)
+    a_cnt = np.asarray(cnts, np.int64)
     a_row = np.asarray(rows0, np.int64)
     a_col = np.asarray(cols0, np.int64)
     _lib.check(_lib.lib().msr_tiff_decode_chunks(fbuf.ctypes.data, fbuf.size, a_off.ctypes.data, a_cnt.ctypes.data,

@@ -65,3 +65,15 @@ def test_geo_tags_pass_through(tmp_path):
     for tag in geo:
         assert g[tag] == geo[tag]
     assert g[geotiff.TAG_GDAL_NODATA][2].rstrip(b"\0") == b"-32768"
+
+
+@pytest.mark.parametrize("name", ["smooth", "mask16", "flat8"])
+@pytest.mark.parametrize("scheme", [8, 32946])
+def test_reads_deflate_compressed_files(tmp_path, name, scheme):
+    """GDAL's COMPRESS=DEFLATE (TIFF compression 8, legacy 32946), written here by libtiff through OpenCV."""
+    a = rasters()[name]
+    path = str(tmp_path / f"{name}_deflate.tif")
+    assert cv2.imwrite(path, a, [cv2.IMWRITE_TIFF_COMPRESSION, scheme])
+    back, _ = geotiff.read(path)
+    assert back.dtype == a.dtype
+    np.testing.assert_array_equal(back, a)
