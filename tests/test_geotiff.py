@@ -67,13 +67,75 @@ def test_geo_tags_pass_through(tmp_path):
     assert g[geotiff.TAG_GDAL_NODATA][2].rstrip(b"\0") == b"-32768"
 
 
-@pytest.mark.parametrize("name", ["smooth", "mask16", "flat8"])
-@pytest.mark.parametrize("scheme", [8, 32946])
-def test_reads_deflate_compressed_files(tmp_path, name, scheme):
-    """GDAL's COMPRESS=DEFLATE (TIFF compression 8, legacy 32946), written here by libtiff through OpenCV."""
+def _write_deflate_tiff(path, a, scheme, rows_per_strip, predictor, tiled=False, tile=64):
+    """Minimal classic-TIFF writer with zlib-compressed strips or tiles (what GDAL's COMPRESS=DEFLATE produces); horizontal
+    differencing (predictor 2) for integer samples.  OpenCV ignores IMWRITE_TIFF_COMPRESSION=8 for these dtypes, so the
+    file is assembled by hand."""
+    import struct
+    import zlib
+    h, w = a.shape
+    fmt = {"f": 3, "u": 1, "i": 2}[a.dtype.kind]
+    chunks = []
+    if tiled:
+        for y in range(0, h, tile):
+            for x in range(0, w, tile):
+                t = np.zeros((tile, tile), a.dtype)
+                blk = a[y:y + tile, x:x + tile]
+                t[:blk.shape[0], :blk.shape[1]] = blk
+                chunks.append(t)
+    else:
+        chunks = [a[y:y + rows_per_strip] for y in range(0, h, rows_per_strip)]
+    payloads = []
+    for c in chunks:
+        c = np.ascontiguousarray(c)
+        if predictor == 2:
+            d = c.copy()
+            d[:, 1:] = c[:, 1:] - c[:, :-1]          # modular arithmetic of the unsigned sample type
+            c = d
+        payloads.append(zlib.compress(c.tobytes(), 6))
+    entries = [(256, 4, w), (257, 4, h), (258, 3, a.dtype.itemsize * 8), (259, 3, scheme), (262, 3, 1), (277, 3, 1),
+               (317, 3, predictor), (339, 3, fmt)]
+    if tiled:
+        entries += [(322, 4, tile), (323, 4, tile)]
+    else:
+        entries += [(278, 4, rows_per_strip)]
+    off_tag, cnt_tag = (324, 325) if tiled else (273, 279)
+    n = len(payloads)
+    n_tags = len(entries) + 2
+    data_off = 8
+    offsets, pos = [], data_off
+    for p_ in payloads:
+        offsets.append(pos)
+        pos += len(p_)
+    pos += pos & 1
+    ifd_off = pos
+    arrays_off = ifd_off + 2 + 12 * n_tags + 4
+    body = b"II" + struct.pack("<HI", 42, ifd_off) + b"".join(payloads)
+    body += b"\0" * (ifd_off - len(body))
+    recs = [(t, ty, 1, struct.pack("<I", v) if ty == 4 else struct.pack("<HH", v, 0)) for t, ty, v in entries]
+    if n == 1:
+        recs += [(off_tag, 4, 1, struct.pack("<I", offsets[0])), (cnt_tag, 4, 1, struct.pack("<I", len(payloads[0])))]
+        tail = b""
+    else:
+        recs += [(off_tag, 4, n, struct.pack("<I", arrays_off)), (cnt_tag, 4, n, struct.pack("<I", arrays_off + 4 * n))]
+        tail = struct.pack("<%dI" % n, *offsets) + struct.pack("<%dI" % n, *[len(p_) for p_ in payloads])
+    recs.sort(key=lambda r: r[0])
+    ifd = struct.pack("<H", n_tags) + b"".join(struct.pack("<HHI", t, ty, c) + v for t, ty, c, v in recs) + struct.pack("<I", 0)
+    with open(path, "wb") as f:
+        f.write(body + ifd + tail)
+
+
+@pytest.mark.parametrize("name,predictor", [("smooth", 1), ("mask16", 2), ("flat8", 2), ("noisy", 1)])
+@pytest.mark.parametrize("scheme,tiled", [(8, False), (32946, False), (8, True)])
+def test_reads_deflate_compressed_files(tmp_path, name, predictor, scheme, tiled):
+    """GDAL's COMPRESS=DEFLATE (TIFF compression 8, legacy 32946), strips and tiles, with and without the horizontal
+    predictor; libtiff (through OpenCV) reads the same hand-assembled file to the same samples."""
     a = rasters()[name]
     path = str(tmp_path / f"{name}_deflate.tif")
-    assert cv2.imwrite(path, a, [cv2.IMWRITE_TIFF_COMPRESSION, scheme])
+    _write_deflate_tiff(path, a, scheme, rows_per_strip=41, predictor=predictor, tiled=tiled)
     back, _ = geotiff.read(path)
     assert back.dtype == a.dtype
     np.testing.assert_array_equal(back, a)
+    other = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+    assert other is not None
+    np.testing.assert_array_equal(other, a)
