@@ -293,27 +293,54 @@ __device__ __forceinline__ void blend_update(BlendState& st, double w, bool is_f
   st.s = __double2float_rn(__dadd_rn((double)st.s, __dmul_rn(__dmul_rn(w, delta_new), delta_new)));
 }
 
+// One patch's contribution to a pixel, split into the loads (issued one contribution ahead of their use: the kernel is
+// bound by the latency of these dependent loads and of the float64 chain, see profiles/r01b_ncu_tiling_summary.md)
+// and the arithmetic.
+struct BlendOperand {
+  double w, v64;
+  float v32, lo, hi;
+  bool is_f64;
+};
+
+__device__ __forceinline__ BlendOperand blend_fetch(const void* const* __restrict__ ptrs,
+                                                    const uint8_t* __restrict__ f64flags,
+                                                    const float* __restrict__ lohi, const double* __restrict__ wtab,
+                                                    int k, int ry, int rx, int I, int p) {
+  // (ry, rx) = position inside patch k, already known to be in [p, I - p)
+  BlendOperand o;
+  const float2 lh = __ldg(reinterpret_cast<const float2*>(lohi) + k);
+  o.lo = lh.x;
+  o.hi = lh.y;
+  o.w = __ldg(wtab + (int64_t)(ry - p) * (I - 2 * p) + (rx - p));
+  o.is_f64 = f64flags != nullptr && f64flags[k] != 0;
+  o.v32 = 0.f;
+  o.v64 = 0.0;
+  if (o.is_f64) o.v64 = reinterpret_cast<const double*>(ptrs[k])[(int64_t)ry * I + rx];
+  else o.v32 = reinterpret_cast<const float*>(ptrs[k])[(int64_t)ry * I + rx];
+  return o;
+}
+
+__device__ __forceinline__ void blend_apply(BlendState& st, const BlendOperand& o, int add_half) {
+  const float range = __fsub_rn(o.hi, o.lo);
+  float d32 = 0.f;
+  double d64 = 0.0;
+  if (o.is_f64) {
+    double v = o.v64;
+    if (add_half) v = __dadd_rn(v, 0.5);
+    d64 = __dadd_rn(__dmul_rn(v, (double)range), (double)o.lo);  // f64 array * f32 scalar + f32 scalar (:396)
+  } else {
+    float v = o.v32;
+    if (add_half) v = __fadd_rn(v, 0.5f);                        // processBatch :340
+    d32 = __fadd_rn(__fmul_rn(v, range), o.lo);                  // :396
+  }
+  blend_update(st, o.w, o.is_f64, d32, d64);
+}
+
 __device__ __forceinline__ void blend_contribution(BlendState& st, const void* const* __restrict__ ptrs,
                                                    const uint8_t* __restrict__ f64flags,
                                                    const float* __restrict__ lohi, const double* __restrict__ wtab,
                                                    int k, int ry, int rx, int I, int p, int add_half) {
-  // (ry, rx) = position inside patch k, already known to be in [p, I - p)
-  const float lo = lohi[2 * k], hi = lohi[2 * k + 1];
-  const float range = __fsub_rn(hi, lo);
-  const double w = wtab[(int64_t)(ry - p) * (I - 2 * p) + (rx - p)];
-  const bool is_f64 = f64flags != nullptr && f64flags[k] != 0;
-  float d32 = 0.f;
-  double d64 = 0.0;
-  if (is_f64) {
-    double v = reinterpret_cast<const double*>(ptrs[k])[(int64_t)ry * I + rx];
-    if (add_half) v = __dadd_rn(v, 0.5);
-    d64 = __dadd_rn(__dmul_rn(v, (double)range), (double)lo);  // f64 array * f32 scalar + f32 scalar (:396)
-  } else {
-    float v = reinterpret_cast<const float*>(ptrs[k])[(int64_t)ry * I + rx];
-    if (add_half) v = __fadd_rn(v, 0.5f);                      // processBatch :340
-    d32 = __fadd_rn(__fmul_rn(v, range), lo);                  // :396
-  }
-  blend_update(st, w, is_f64, d32, d64);
+  blend_apply(st, blend_fetch(ptrs, f64flags, lohi, wtab, k, ry, rx, I, p), add_half);
 }
 
 __global__ void __launch_bounds__(256) blend_tile_kernel(const void* const* __restrict__ ptrs,
@@ -343,13 +370,28 @@ __global__ void __launch_bounds__(256) blend_tile_kernel(const void* const* __re
     if (X - p < 0) gx1 = -1;
     gy1 = min(gy1, G - 1);
     gx1 = min(gx1, G - 1);
-    // (measured: fetching a lattice row's contributions before the sequential float64 Welford chain is SLOWER -- the
-    // kernel is bound by the float64 division / conversion chain that bit-exactness with numpy requires, not by loads)
-    for (int gy = gy0; gy <= gy1; ++gy) {
-      for (int gx = gx0; gx <= gx1; ++gx) {
-        const int k = lattice[gy * G + gx];
-        if (k < 0) continue;
-        blend_contribution(st, ptrs, f64flags, lohi, wtab, k, Y - gy * S, X - gx * S, I, p, add_half);
+    // lattice cells in the reference's order (gy outer, gx inner); the operands of the NEXT contributing cell are
+    // fetched before the float64 chain of the current one runs
+    int gy = gy0, gx = gx0 - 1;
+    auto next_cell = [&]() -> int {
+      for (;;) {
+        if (++gx > gx1) {
+          gx = gx0;
+          if (++gy > gy1) return -1;
+        }
+        const int k = __ldg(lattice + gy * G + gx);
+        if (k >= 0) return k;
+      }
+    };
+    if (gy0 <= gy1 && gx0 <= gx1) {
+      int k = next_cell();
+      BlendOperand nxt;
+      if (k >= 0) nxt = blend_fetch(ptrs, f64flags, lohi, wtab, k, Y - gy * S, X - gx * S, I, p);
+      while (k >= 0) {
+        const BlendOperand cur = nxt;
+        k = next_cell();
+        if (k >= 0) nxt = blend_fetch(ptrs, f64flags, lohi, wtab, k, Y - gy * S, X - gx * S, I, p);
+        blend_apply(st, cur, add_half);
       }
     }
   } else {
@@ -399,24 +441,43 @@ __global__ void __launch_bounds__(256) blend_accumulate_kernel(
   bool touched = false;
   const int64_t II = (int64_t)I * I;
   const int wp = I - 2 * p;
-  for (int gy = gy0; gy <= gy1; ++gy) {
-    const int py = ry - gy * S;
-    for (int gx = gx0; gx <= gx1; ++gx) {
-      const int k = __ldg(lattice + (int64_t)gy * GX + gx) - k0;
-      if (k < 0 || k >= n) continue;
-      if (!touched) {
-        st.wsum = wsum[a];
-        st.mean = mean[a];
-        st.s = sacc[a];
-        touched = true;
+  int gy = gy0, gx = gx0 - 1;
+  auto next_cell = [&]() -> int {   // next lattice cell, in visit order, that holds a patch of this call
+    for (;;) {
+      if (++gx > gx1) {
+        gx = gx0;
+        if (++gy > gy1) return -1;
       }
-      const int px = X - gx * S;
-      const float lo = __ldg(lohi + 2 * k), hi = __ldg(lohi + 2 * k + 1);
-      float v = __ldg(pred + k * II + (int64_t)py * I + px);
-      if (add_half) v = __fadd_rn(v, 0.5f);                                  // processBatch :340
-      const float d = __fadd_rn(__fmul_rn(v, __fsub_rn(hi, lo)), lo);       // :396
-      blend_update(st, __ldg(wtab + (int64_t)(py - p) * wp + (px - p)), false, d, 0.0);
+      const int k = __ldg(lattice + (int64_t)gy * GX + gx) - k0;
+      if (k >= 0 && k < n) return k;
     }
+  };
+  auto fetch = [&](int k) -> BlendOperand {
+    const int py = ry - gy * S, px = X - gx * S;
+    BlendOperand o;
+    const float2 lh = __ldg(reinterpret_cast<const float2*>(lohi) + k);
+    o.lo = lh.x;
+    o.hi = lh.y;
+    o.w = __ldg(wtab + (int64_t)(py - p) * wp + (px - p));
+    o.v32 = __ldg(pred + k * II + (int64_t)py * I + px);
+    o.v64 = 0.0;
+    o.is_f64 = false;
+    return o;
+  };
+  int k = next_cell();
+  BlendOperand nxt;
+  if (k >= 0) {
+    nxt = fetch(k);
+    st.wsum = wsum[a];
+    st.mean = mean[a];
+    st.s = sacc[a];
+    touched = true;
+  }
+  while (k >= 0) {
+    const BlendOperand cur = nxt;
+    k = next_cell();
+    if (k >= 0) nxt = fetch(k);
+    blend_apply(st, cur, add_half);
   }
   if (touched) {
     wsum[a] = st.wsum;
