@@ -224,11 +224,26 @@ def run_reference(args, rank):
     emit(line)
 
 
+def baseline_config_label(args, plan) -> str:
+    """Which entry of BASELINE.json's `configs` the command line reproduces (per-GPU band for the weak-scaling runs)."""
+    key = (args.arch, args.image_size, args.stride, args.batch_size)
+    dims = {plan.height, plan.width}
+    if key == ("spade", 512, 128, 16) and args.rows_per_gpu == 8192 and args.cols == 8192:
+        return "BASELINE.json configs[2]" + (" per GPU (weak scaling)" if plan.height != 8192 else "")
+    if key == ("spade", 512, 128, 16) and dims == {15000, 70000}:
+        return "BASELINE.json configs[4]"
+    if key[0] == "cnn" and key[1] == 512 and dims == {15000, 20000}:
+        return "BASELINE.json configs[3]"
+    if key == ("pix2pix", 256, 32, 16) and dims == {4096}:
+        return "BASELINE.json configs[1]"
+    return "custom configuration"
+
+
 def config_dict(args, n, plan, slots):
     return {"workload": f"{args.arch.upper()}-{args.image_size} tiled inference over {plan.height}x{plan.width} "
                         f"(= {n} band(s) of {args.rows_per_gpu} rows, one per GPU), stride {args.stride} "
                         f"(nominal N={(args.image_size // args.stride) ** 2} generations/pixel), batch "
-                        f"{args.batch_size}, tile {args.tile_size}; BASELINE.json configs[2]",
+                        f"{args.batch_size}, tile {args.tile_size}; " + baseline_config_label(args, plan),
             "raster": [plan.height, plan.width], "image_size": args.image_size, "stride": args.stride,
             "batch_size": args.batch_size, "tile_size": args.tile_size, "tiles": len(plan.tiles()),
             "slots_per_step": slots, "gflop_per_slot": GF_PER_SLOT.get((args.arch, args.image_size)),
