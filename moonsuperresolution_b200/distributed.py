@@ -68,13 +68,13 @@ def exchange_halo_rows(own, plan: Plan, rank: int, world_size: int, group=None, 
         q0, q1 = needs[peer]
         # rows of mine that the peer reads
         s0, s1 = max(r0, q0), min(r1, q1)
-        if s1 > s0 and p1 > p0:
+        if s1 > s0:
             t = own[s0 - r0:s1 - r0].contiguous()
             keep.append(t)
             ops.append(dist.P2POp(dist.isend, t, peer, group))
         # rows of the peer that I read
         g0, g1 = max(p0, n0), min(p1, n1)
-        if g1 > g0 and r1 > r0:
+        if g1 > g0:
             t = torch.empty((g1 - g0, plan.width), dtype=own.dtype, device=own.device)
             keep.append((t, g0, g1))
             ops.append(dist.P2POp(dist.irecv, t, peer, group))

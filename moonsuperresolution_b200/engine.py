@@ -210,12 +210,7 @@ class DEMSuperResolution:
 
     def _rows_dedup(self, plan: Plan, rank: int):
         """Dedup mode: (raster rows this rank finalises, raster rows its patches read -- a superset)."""
-        band = plan.dedup_band(self.world_size, rank)
-        own = band.raster_rows(band.out, plan.off, plan.height)
-        need = band.raster_rows(band.read, plan.off, plan.height)
-        if own[1] > own[0]:
-            need = (min(need[0], own[0]), max(need[1], own[1])) if need[1] > need[0] else own
-        return own, need
+        return plan.dedup_rows(self.world_size, rank)
 
     def loadImages(self) -> None:
         """process_full_tiles.py:158-182 -- band 1 of both GeoTIFFs as float32 plus the DEM's geo-referencing."""

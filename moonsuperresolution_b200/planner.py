@@ -142,6 +142,16 @@ class Plan:
             seam_out=None if last or not overlap else (j1 * s + q, j1 * s + off - p))
 
 
+    def dedup_rows(self, world_size: int, rank: int) -> Tuple[Tuple[int, int], Tuple[int, int]]:
+        """Dedup mode, in RASTER rows: (rows this rank finalises, rows its patches read -- a superset of the former)."""
+        band = self.dedup_band(world_size, rank)
+        own = band.raster_rows(band.out, self.off, self.height)
+        need = band.raster_rows(band.read, self.off, self.height)
+        if own[1] > own[0]:
+            need = (min(need[0], own[0]), max(need[1], own[1])) if need[1] > need[0] else own
+        return own, need
+
+
 @dataclasses.dataclass(frozen=True)
 class DedupBand:
     """One rank's share of the global patch lattice in dedup mode.  ``read``: canvas rows its patches read (= rows of its

@@ -93,3 +93,39 @@ def test_input_halo_exchange_gloo(tmp_path, world):
     import torch.multiprocessing as mp
     mp.spawn(_halo_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     assert all((tmp_path / f"ok{r}").exists() for r in range(world))
+
+
+def _dedup_halo_worker(rank, world, port, out_dir):
+    import torch
+    import torch.distributed as dist
+    from moonsuperresolution_b200.distributed import exchange_halo_rows
+    from moonsuperresolution_b200.planner import Plan
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    h, w = 2900, 37
+    plan = Plan(h, w, 64, 16, 256, 4)
+    full = torch.arange(h * w, dtype=torch.float32).reshape(h, w)
+    rows = [plan.dedup_rows(world, r) for r in range(world)]
+    bounds, needs = [r[0] for r in rows], [r[1] for r in rows]
+    (r0, r1), (n0, n1) = rows[rank]
+    got = exchange_halo_rows(full[r0:r1].clone(), plan, rank, world, bounds=bounds, needs=needs)
+    assert n0 <= r0 and n1 >= r1
+    assert torch.equal(got, full[n0:n1]), f"rank {rank}: rows differ"
+    # a dedup band reads less than a tile-row band: only the I - S rows above its first lattice row
+    band = plan.dedup_band(world, rank)
+    assert n0 == max(0, band.j0 * plan.stride - plan.off)
+    open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_dedup_mode_input_rows_exchange_gloo(tmp_path, world):
+    """Dedup mode's sharded loading: ranks own the raster rows they finalise (a partition of [0, H)) and fetch the rows
+    their first lattice rows read from the rank above."""
+    import torch.multiprocessing as mp
+    from moonsuperresolution_b200.planner import Plan
+    plan = Plan(2900, 37, 64, 16, 256, 4)
+    own = [plan.dedup_rows(world, r)[0] for r in range(world)]
+    assert own[0][0] == 0 and own[-1][1] == 2900 and all(a[1] == b[0] for a, b in zip(own[:-1], own[1:]))
+    mp.spawn(_dedup_halo_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / f"ok{r}").exists() for r in range(world))
