@@ -488,6 +488,22 @@ class DEMSuperResolution:
                                                   _lib.stream_ptr()), "msr_gather_normalize")
         self.launches += 2
 
+    def _sampler_noise(self, slots: int, eps, key: int):
+        """(slots, 256) standard-normal draws for the Gaussian sampler (sampling.py:13-16) of a GauGAN device model: the
+        caller's ``eps`` (parity tests) or a stream seeded by the config's seed and ``key`` (the reference's
+        tf.random.normal is unseeded).  None for models without a sampler."""
+        if getattr(self.model, "arch", None) != "spade":
+            return None
+        torch = _torch()
+        if eps is None:
+            gen = torch.Generator(device=self.device)
+            gen.manual_seed((self.seed * 1000003 + key) & 0x7FFFFFFFFFFF)
+            return torch.randn((slots, 256), generator=gen, dtype=torch.float32, device=self.device)
+        d_eps = torch.as_tensor(np.ascontiguousarray(eps, dtype=np.float32)).to(self.device)
+        if tuple(d_eps.shape) != (slots, 256):
+            raise ValueError(f"eps must have shape {(slots, 256)}")
+        return d_eps
+
     def processTile(self, px: int, py: int, eps=None) -> None:
         """process_full_tiles.py:431-479.  ``eps`` optionally supplies the sampler noise for every slot of the tile,
         shape (slots, 256) (parity tests); by default a seeded per-tile stream is drawn on the device."""
@@ -535,17 +551,7 @@ class DEMSuperResolution:
             pred = torch.empty((slots, i, i), dtype=torch.float32, device=dev)
             src = torch.empty((min(chunk, slots), i, i, 2), dtype=torch.float32, device=dev)
             partial = torch.empty((min(chunk, slots) * 32 * 4,), dtype=torch.float32, device=dev)
-            if self.model.arch == "spade":
-                if eps is None:
-                    gen = torch.Generator(device=dev)
-                    gen.manual_seed((self.seed * 1000003 + py * 131071 + px) & 0x7FFFFFFFFFFF)
-                    d_eps = torch.randn((slots, 256), generator=gen, dtype=torch.float32, device=dev)
-                else:
-                    d_eps = torch.as_tensor(np.ascontiguousarray(eps, dtype=np.float32)).to(dev)
-                    if tuple(d_eps.shape) != (slots, 256):
-                        raise ValueError(f"eps must have shape {(slots, 256)}")
-            else:
-                d_eps = None
+            d_eps = self._sampler_noise(slots, eps, py * 131071 + px)
             for s0 in range(0, slots, chunk):
                 n = min(chunk, slots - s0)
                 self._gather(d_slot_xy[s0:s0 + n], n, src, minmax[s0:s0 + n], partial)
@@ -670,16 +676,7 @@ class DEMSuperResolution:
             chunk, add_half = b, 0
         src = torch.empty((min(chunk, slots), i, i, 2), dtype=torch.float32, device=dev)
         partial = torch.empty((min(chunk, slots) * 32 * 4,), dtype=torch.float32, device=dev)
-        d_eps = None
-        if device_model and self.model.arch == "spade":
-            if eps is None:
-                gen = torch.Generator(device=dev)
-                gen.manual_seed((self.seed * 1000003 + band.j0 * 8191 + 17) & 0x7FFFFFFFFFFF)
-                d_eps = torch.randn((slots, 256), generator=gen, dtype=torch.float32, device=dev)
-            else:
-                d_eps = torch.as_tensor(np.ascontiguousarray(eps, dtype=np.float32)).to(dev)
-                if tuple(d_eps.shape) != (slots, 256):
-                    raise ValueError(f"eps must have shape {(slots, 256)}")
+        d_eps = self._sampler_noise(slots, eps, band.j0 * 8191 + 17) if device_model else None
         for s0 in range(0, slots, chunk):
             n = min(chunk, slots - s0)
             n_real = min(n, n_valid - s0)
