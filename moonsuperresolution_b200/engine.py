@@ -225,6 +225,20 @@ class DEMSuperResolution:
         dem, geo = geotiff.read(dem_path)
         self.setRasters(dem.astype(np.float32), img.astype(np.float32), geo, geo)
 
+    def interpolateMissingValues(self, data: np.ndarray, no_value: int, max_fill_area: int = 256) -> np.ndarray:
+        """process_full_tiles.py:184-212 -- same signature; fills, in place, the connected invalid regions of ``data`` that
+        are smaller than ``max_fill_area`` with the cubic interpolant through its valid pixels (host, scipy + cv2 like
+        the reference; see preprocess.py)."""
+        from . import preprocess as PP
+        return PP._fill_block(data, no_value, max_fill_area)
+
+    def fillNan(self, image: np.ndarray, no_value: int, tile_size: int = 1024, border: int = 128,
+                max_fill_area: int = 256) -> np.ndarray:
+        """process_full_tiles.py:214-224 -- same signature and defaults; block-wise interpolateMissingValues."""
+        from . import preprocess as PP
+        return PP.fill_small_holes(np.asarray(image), no_value, tile=tile_size, border=border,
+                                   max_fill_area=max_fill_area)
+
     def preprocess(self) -> None:
         """process_full_tiles.py:226-244 -- the DEM is low-passed before it is tiled: 1/4 area resize, small-hole fill,
         1/4 area resize, bicubic back to (H, W), with no_value carried as NaN through the resampling.  Both resampling

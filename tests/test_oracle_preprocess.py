@@ -101,3 +101,19 @@ def test_product_tables_and_hole_fill_equal_the_oracle():
     # restricting the work to the blocks that hold invalid pixels changes nothing
     blocks = [(x, y) for (x, y) in P.fill_blocks(h, w) if (d[y:y + 256, x:x + 256] <= nv).any()]
     np.testing.assert_array_equal(P.fill_small_holes(d, nv, origins=blocks), want)
+
+
+def test_engine_exposes_the_reference_hole_fill_methods():
+    """DEMSuperResolution.fillNan / interpolateMissingValues (process_full_tiles.py:184-224) keep the reference's
+    signatures; host code, so callable without a device (unbound here: the constructor needs CUDA)."""
+    from moonsuperresolution_b200.engine import DEMSuperResolution as E
+    rng = np.random.default_rng(4)
+    d = (np.cumsum(np.cumsum(rng.standard_normal((150, 140)), 0), 1) + 1500).astype(np.float32)
+    nv = -32768.0
+    d[70:72, 60:63] = nv
+    d[5:7, 5:7] = nv
+    np.testing.assert_array_equal(E.fillNan(None, d, nv, tile_size=128, border=16, max_fill_area=24),
+                                  OP.fill_nan(d, nv, 128, 16, 24))
+    blk = d[:128, :128]
+    np.testing.assert_array_equal(E.interpolateMissingValues(None, blk.copy(), nv, 24),
+                                  OP.interpolate_missing(blk.copy(), nv, 24))
