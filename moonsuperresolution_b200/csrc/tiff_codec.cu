@@ -291,9 +291,11 @@ extern "C" int msr_tiff_decode_chunks(const uint8_t* h_file, int64_t file_bytes,
     }
     if (predictor == 2) horizontal_predictor(buf.data(), chunk_row_bytes, chunk_rows, sample_bytes, false);
     else if (predictor == 3) float_predictor_decode(buf.data(), chunk_row_bytes, chunk_rows, sample_bytes);
+    // paste, clipped to the raster on every side (a chunk may start above row 0 when only a band of rows is read)
     const int64_t nr = std::min<int64_t>(chunk_rows, rows - dst_row[i]);
     const int64_t nb = std::min<int64_t>(chunk_row_bytes, row_bytes - dst_col[i]);
-    for (int64_t r = 0; r < nr; ++r)
+    if (dst_col[i] < 0 || nb <= 0) return;
+    for (int64_t r = std::max<int64_t>(0, -dst_row[i]); r < nr; ++r)
       memcpy(h_raster + (dst_row[i] + r) * row_bytes + dst_col[i], buf.data() + r * chunk_row_bytes, (size_t)nb);
   });
   if (failed == 1) return fail(MSR_E_INVALID, "tiff_decode: chunk outside the file");

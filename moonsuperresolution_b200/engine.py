@@ -221,6 +221,15 @@ class DEMSuperResolution:
             raise ValueError("The path given for the ortho-image does not exist. Provided path is: " + img_path)
         if not os.path.exists(dem_path):
             raise ValueError("The path given for the dem does not exist. Provided path is: " + dem_path)
+        if self.world_size > 1 and not self._preprocess_cfg:
+            # one process per GPU: decode only the strips / tiles of the rows this rank's band reads (preprocess, when on,
+            # resamples across band boundaries and needs the whole DEM)
+            h, w = geotiff.shape(dem_path)
+            r0, r1 = self.rowsNeeded(h, w)
+            img, _ = geotiff.read(img_path, rows=(r0, r1))
+            dem, geo = geotiff.read(dem_path, rows=(r0, r1))
+            self.setRasters(dem.astype(np.float32), img.astype(np.float32), geo, geo, row_offset=r0, full_height=h)
+            return
         img, _ = geotiff.read(img_path)
         dem, geo = geotiff.read(dem_path)
         self.setRasters(dem.astype(np.float32), img.astype(np.float32), geo, geo)

@@ -134,11 +134,12 @@ def write(path: str, data: np.ndarray, geo: Optional[Dict[int, Tuple[int, int, b
         f.write(extra)
 
 
-def read(path: str):
-    """Reads band 1 of a little-endian TIFF / BigTIFF: strips or tiles, uncompressed, LZW or Deflate, predictor 1 / 2 / 3.
-    Returns (array, geo) where geo maps the GeoTIFF tag numbers present to (type, count, payload bytes)."""
+def _open(path: str):
+    """Maps the file and parses its first IFD: (buffer, {tag: (type, count, payload bytes)}, ints(tag, default))."""
+    import mmap
     with open(path, "rb") as f:
-        buf = f.read()
+        # mapped, not read: a rank that decodes a band of rows only touches the pages of its own strips / tiles
+        buf = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ) if os.fstat(f.fileno()).st_size else b""
     if buf[:2] != b"II":
         raise ValueError("only little-endian TIFF is supported")
     magic = struct.unpack_from("<H", buf, 2)[0]
@@ -168,7 +169,21 @@ def read(path: str):
         typ, cnt, payload = tags[tag]
         code = {1: "B", 3: "H", 4: "I", 16: "Q"}[typ]
         return list(struct.unpack("<" + code * cnt, payload))
+    return buf, tags, ints
 
+
+def shape(path: str) -> Tuple[int, int]:
+    """(rows, cols) of the raster, from the header alone."""
+    _, _, ints = _open(path)
+    return ints(257)[0], ints(256)[0]
+
+
+def read(path: str, rows=None):
+    """Reads band 1 of a little-endian TIFF / BigTIFF: strips or tiles, uncompressed, LZW or Deflate, predictor 1 / 2 / 3.
+    Returns (array, geo) where geo maps the GeoTIFF tag numbers present to (type, count, payload bytes).
+    ``rows`` = (r0, r1) reads only that band of raster rows (a rank of a multi-GPU run decodes only the strips / tiles
+    its band of tiles touches); the array then has r1 - r0 rows."""
+    buf, tags, ints = _open(path)
     w, h = ints(256)[0], ints(257)[0]
     compression = ints(259, [1])[0]
     if compression not in (1, 5, 8, 32946):
@@ -196,8 +211,20 @@ def read(path: str):
         rows0 = [k * rps for k in range(n)]
         cols0 = [0] * n
         chunk_rows, chunk_row_bytes = rps, w * itemsize
-    out = np.empty((h, w), dtype)
     offs, cnts = list(offs[:n]), list(cnts[:n])
+    r_lo, r_hi = 0, h
+    if rows is not None:
+        r_lo, r_hi = int(rows[0]), int(rows[1])
+        if not (0 <= r_lo <= r_hi <= h):
+            raise ValueError(f"rows {rows} outside the raster (0, {h})")
+        keep = [k for k in range(n) if rows0[k] < r_hi and rows0[k] + chunk_rows > r_lo]
+        offs, cnts = [offs[k] for k in keep], [cnts[k] for k in keep]
+        rows0, cols0 = [rows0[k] - r_lo for k in keep], [cols0[k] for k in keep]
+        n = len(keep)
+    out = np.empty((r_hi - r_lo, w), dtype)
+    geo = {t: tags[t] for t in GEO_TAGS + (TAG_GDAL_NODATA,) if t in tags}
+    if n == 0 or out.size == 0:
+        return out, geo
     if compression in (8, 32946):
         # Deflate (GDAL's COMPRESS=DEFLATE): inflate every chunk with zlib (releases the GIL: thread pool), then hand the
         # inflated image to the native codec as an uncompressed file -- it still undoes the predictor and pastes
@@ -219,7 +246,6 @@ def read(path: str):
     a_col = np.asarray(cols0, np.int64)
     _lib.check(_lib.lib().msr_tiff_decode_chunks(fbuf.ctypes.data, fbuf.size, a_off.ctypes.data, a_cnt.ctypes.data,
                                                  a_row.ctypes.data, a_col.ctypes.data, n, chunk_rows, chunk_row_bytes,
-                                                 itemsize, compression, predictor, out.ctypes.data, w * itemsize, h,
-                                                 _threads()), "msr_tiff_decode_chunks")
-    geo = {t: tags[t] for t in GEO_TAGS + (TAG_GDAL_NODATA,) if t in tags}
+                                                 itemsize, compression, predictor, out.ctypes.data, w * itemsize,
+                                                 r_hi - r_lo, _threads()), "msr_tiff_decode_chunks")
     return out, geo

@@ -45,6 +45,35 @@ def main():
                   flush=True)
             ok = ok and same and int(res[2].sum()) > 0
         dist.barrier()
+    # from files: every rank decodes only the strips of the rows its band reads (geotiff.read(rows=...))
+    import tempfile
+    from moonsuperresolution_b200 import geotiff
+    box = [tempfile.mkdtemp() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    folder = box[0]
+    if rank == 0:
+        geotiff.write(os.path.join(folder, "run-DEM.tif"), dem, rows_per_strip=64)
+        geotiff.write(os.path.join(folder, "run-DRG.tif"), img, rows_per_strip=64)
+    dist.barrier()
+    for mode in ("faithful", "dedup"):
+        cfg = msr.DSRConfig(image_size=case["I"], stride=case["S"], batch_size=case["B"], tile_size=case["T"],
+                            no_value=case["NV"], mode=mode, preprocess=False, source_folder_path=folder, map_name="m",
+                            save_path=folder)
+        eng = msr.DEMSuperResolution(cfg, model=toy_models.ripple, rank=rank, world_size=world, device=dev)
+        eng.loadImages()
+        held = eng.dem.shape[0]
+        eng.padInputs()
+        eng.processTiles()
+        res = eng.gatherResults()
+        if rank == 0:
+            cfg1 = msr.DSRConfig(image_size=case["I"], stride=case["S"], batch_size=case["B"], tile_size=case["T"],
+                                 no_value=case["NV"], mode=mode)
+            single = msr.DEMSuperResolution(cfg1, model=toy_models.ripple, device=dev).run(dem, img)
+            same = all(np.array_equal(a, b) for a, b in zip(res, single)) and held < case["H"]
+            print(f"mode={mode} from files, {held} of {case['H']} rows decoded on rank 0, world={world}: "
+                  f"{'bit-identical to the single-process run' if same else 'MISMATCH'}", flush=True)
+            ok = ok and same
+        dist.barrier()
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, 0)
     dist.destroy_process_group()

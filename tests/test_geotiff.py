@@ -139,3 +139,30 @@ def test_reads_deflate_compressed_files(tmp_path, name, predictor, scheme, tiled
     other = cv2.imread(path, cv2.IMREAD_UNCHANGED)
     assert other is not None
     np.testing.assert_array_equal(other, a)
+
+
+@pytest.mark.parametrize("layout", ["lzw_strips", "deflate_tiles", "plain_strips"])
+def test_reading_a_band_of_rows(tmp_path, layout):
+    """read(path, rows=(r0, r1)): only the strips / tiles that intersect the band are decoded; chunks that start above
+    the band are clipped at the top, the last ones at the bottom."""
+    a = rasters()["smooth"]                                   # 301 x 517
+    path = str(tmp_path / "band.tif")
+    if layout == "lzw_strips":
+        geotiff.write(path, a, compress="lzw", predictor=2, rows_per_strip=37)
+    elif layout == "plain_strips":
+        geotiff.write(path, a, compress="none", predictor=1, rows_per_strip=16)
+    else:
+        _write_deflate_tiff(path, a, 8, rows_per_strip=0, predictor=1, tiled=True, tile=64)
+    for r0, r1 in [(0, 301), (0, 1), (40, 41), (36, 38), (100, 250), (290, 301), (300, 301), (120, 120)]:
+        band, geo = geotiff.read(path, rows=(r0, r1))
+        assert band.shape == (r1 - r0, a.shape[1]) and band.dtype == a.dtype
+        np.testing.assert_array_equal(band, a[r0:r1])
+    with pytest.raises(ValueError):
+        geotiff.read(path, rows=(10, 400))
+
+
+def test_shape_from_header(tmp_path):
+    a = rasters()["noisy"]
+    path = str(tmp_path / "s.tif")
+    geotiff.write(path, a)
+    assert geotiff.shape(path) == a.shape

@@ -30,4 +30,4 @@ def test_sharded_loading_and_seam_exchange_over_nccl():
     print(out.stdout[-3000:])
     print(out.stderr[-3000:])
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
-    assert out.stdout.count("bit-identical") == 3
+    assert out.stdout.count("bit-identical") == 5
