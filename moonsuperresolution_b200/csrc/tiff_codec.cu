@@ -42,9 +42,13 @@ struct BitWriter {
 };
 
 int64_t lzw_encode(const uint8_t* src, int64_t len, uint8_t* dst, int64_t cap) {
-  constexpr int kHash = 1 << 14;
-  std::vector<int32_t> hkey(kHash), hval(kHash);
-  auto reset = [&] { std::fill(hkey.begin(), hkey.end(), -1); };
+  // string table: open-addressing hash of (prefix code, byte) -> code.  One 32-bit word per slot -- key (20 bits) above
+  // the code (12 bits) -- in 16384 slots: 64 KB, at most 23 % full (the table is reset at 4094 codes), and
+  // a reset is one 64 KB memset per ~10-20 KB of input.
+  constexpr int kSlots = 1 << 14;
+  constexpr uint32_t kEmpty = 0xFFFFFFFFu;
+  std::vector<uint32_t> table(kSlots);
+  auto reset = [&] { memset(table.data(), 0xFF, sizeof(uint32_t) * kSlots); };
   BitWriter bw{dst, cap};
   reset();
   int next = kFirst, width = 9;
@@ -57,20 +61,20 @@ int64_t lzw_encode(const uint8_t* src, int64_t len, uint8_t* dst, int64_t cap) {
   int prefix = src[0];
   for (int64_t i = 1; i < len; ++i) {
     const int c = src[i];
-    const int32_t key = (prefix << 8) | c;
-    uint32_t h = ((uint32_t)key * 2654435761u) >> 18;
+    const uint32_t key = ((uint32_t)prefix << 8) | (uint32_t)c;
+    uint32_t h = (key * 2654435761u) >> 18;
+    uint32_t e;
     bool found = false;
-    while (hkey[h] != -1) {
-      if (hkey[h] == key) { found = true; break; }
-      h = (h + 1) & (kHash - 1);
+    while ((e = table[h]) != kEmpty) {
+      if ((e >> 12) == key) { found = true; break; }
+      h = (h + 1) & (kSlots - 1);
     }
     if (found) {
-      prefix = hval[h];
+      prefix = (int)(e & 0xFFFu);
       continue;
     }
     bw.put(prefix, width);
-    hkey[h] = key;
-    hval[h] = next++;
+    table[h] = (key << 12) | (uint32_t)next++;
     // libtiff's rule ("early change"): the decoder is one table entry behind the encoder and widens its codes when its
     // next free entry reaches 2^width - 1, i.e. when the encoder's reaches 2^width; the table is reset at 4094
     if (next == kMaxCode) {
