@@ -55,8 +55,9 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=16,
                     help="patches per CPU-baseline sample batch (16 = one reference batch: ~10-20 s of host work at 512)")
-    ap.add_argument("--alt-tile-size", type=int, default=8192,
-                    help="also time one step with this tile_size (0 = skip); reported beside, never as, the headline")
+    ap.add_argument("--alt-tile-size", type=int, default=0,
+                    help="also time one step with this tile_size (0 = skip; e.g. 8192 = one tile per band, which the "
+                         "dedup-mode leg now covers at any tile_size); reported beside, never as, the headline")
     ap.add_argument("--no-dedup", action="store_true",
                     help="skip the extra step in dedup mode (every patch position generated once; SURVEY 8e mode B)")
     return ap.parse_args()
