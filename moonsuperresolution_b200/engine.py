@@ -56,6 +56,8 @@ class DSRConfig:
     seed: int = 0                   # seeds the Gaussian sampler's noise (the reference's is unseeded)
     preprocess: bool = True         # run preprocess() inside processMap like the reference (:577); False = rasters are
                                     # taken as already filtered
+    samples_per_patch: int = 1      # > 1: repeated-sample mode (beyond the reference): every batch is generated this many
+                                    # times (new sampler noise each time) and all generations are blended
     mode: str = "faithful"          # "faithful": tile by tile like the reference (halo patches recomputed per tile);
                                     # "dedup": every position of the global patch lattice generated once
 
@@ -86,6 +88,8 @@ def parse_args(argv=None) -> DSRConfig:
     parser.add_argument("--seed", type=int, default=0, help="Seed of the Gaussian sampler's noise.")
     parser.add_argument("--no_preprocess", action="store_true",
                         help="Skip preprocess() (1/16 box filter + cubic upsampling of the DEM) inside processMap.")
+    parser.add_argument("--samples_per_patch", type=int, default=1,
+                        help="Generations per patch position (N = samples_per_patch * (image_size / stride)^2).")
     parser.add_argument("--mode", type=str, default="faithful", choices=["faithful", "dedup"],
                         help="faithful: tile by tile like the reference; dedup: every patch position generated once.")
     args, _unknown = parser.parse_known_args(argv)
@@ -94,7 +98,7 @@ def parse_args(argv=None) -> DSRConfig:
                      image_size=args.image_size, stride=args.stride, batch_size=args.batch_size,
                      tile_size=args.tile_size, no_value=args.no_value, upsample_factor=args.upsample_factor,
                      save_tiles=args.save_tiles, groups_per_call=args.groups_per_call, seed=args.seed, mode=args.mode,
-                     preprocess=not args.no_preprocess)
+                     preprocess=not args.no_preprocess, samples_per_patch=args.samples_per_patch)
 
 
 def main(argv=None) -> None:
@@ -143,6 +147,9 @@ class DEMSuperResolution:
         self._groups_cfg = int(getattr(config, "groups_per_call", 0))
         self.mode = str(getattr(config, "mode", "faithful"))
         self._preprocess_cfg = bool(getattr(config, "preprocess", True))
+        self.samples_per_patch = int(getattr(config, "samples_per_patch", 1))
+        if self.samples_per_patch < 1:
+            raise ValueError("samples_per_patch must be >= 1")
         if self.mode not in ("faithful", "dedup"):
             raise ValueError("mode must be 'faithful' or 'dedup'")
         if self.mode == "dedup" and self.save_tiles:
@@ -511,20 +518,21 @@ class DEMSuperResolution:
                                                   _lib.stream_ptr()), "msr_gather_normalize")
         self.launches += 2
 
-    def _sampler_noise(self, slots: int, eps, key: int):
-        """(slots, 256) standard-normal draws for the Gaussian sampler (sampling.py:13-16) of a GauGAN device model: the
-        caller's ``eps`` (parity tests) or a stream seeded by the config's seed and ``key`` (the reference's
-        tf.random.normal is unseeded).  None for models without a sampler."""
+    def _sampler_noise(self, slots: int, eps, key: int, repeats: int = 1):
+        """Standard-normal draws for the Gaussian sampler (sampling.py:13-16) of a GauGAN device model, shape (slots, 256)
+        -- (repeats, slots, 256) in repeated-sample mode: the caller's ``eps`` (parity tests) or a stream seeded by the
+        config's seed and ``key`` (the reference's tf.random.normal is unseeded).  None for models without a sampler."""
         if getattr(self.model, "arch", None) != "spade":
             return None
         torch = _torch()
+        shape = (slots, 256) if repeats == 1 else (repeats, slots, 256)
         if eps is None:
             gen = torch.Generator(device=self.device)
             gen.manual_seed((self.seed * 1000003 + key) & 0x7FFFFFFFFFFF)
-            return torch.randn((slots, 256), generator=gen, dtype=torch.float32, device=self.device)
+            return torch.randn(shape, generator=gen, dtype=torch.float32, device=self.device)
         d_eps = torch.as_tensor(np.ascontiguousarray(eps, dtype=np.float32)).to(self.device)
-        if tuple(d_eps.shape) != (slots, 256):
-            raise ValueError(f"eps must have shape {(slots, 256)}")
+        if tuple(d_eps.shape) != shape:
+            raise ValueError(f"eps must have shape {shape}")
         return d_eps
 
     def processTile(self, px: int, py: int, eps=None) -> None:
@@ -534,6 +542,9 @@ class DEMSuperResolution:
         plan = self.plan
         if (px, py) not in self._tile_plan:
             raise ValueError(f"tile ({px}, {py}) is not owned by rank {self.rank}")
+        if self.samples_per_patch > 1:
+            self._process_tile_repeats(px, py, eps)
+            return
         tp = self._tile_plan[(px, py)]
         i, b, t = plan.image_size, plan.batch_size, plan.tile_size
         n_valid = tp["n_valid"]
@@ -653,16 +664,114 @@ class DEMSuperResolution:
         self._band_plan = dict(xy=xy[idx], lattice=lattice, n_valid=int(idx.size), row_of=(idx // gx).astype(np.int32))
 
     def _accumulate(self, pred, lohi, k0: int, n: int, gy_lo: int, gy_hi: int, add_half: int, row_lo: int,
-                    row_hi: int) -> None:
-        plan, band = self.plan, self._dband
-        acc = self._acc
-        _lib.check(self._lib.msr_blend_accumulate(pred.data_ptr(), lohi.data_ptr(), k0, n, self._d_lattice.data_ptr(),
-                                                  band.j1 - band.j0, band.gx, gy_lo, gy_hi, band.j0 * plan.stride,
-                                                  self._blend_weights().data_ptr(), plan.image_size, plan.stride,
-                                                  int(add_half), acc[0].data_ptr(), acc[1].data_ptr(),
-                                                  acc[2].data_ptr(), plan.canvas_w, self._c0, self._ch, plan.canvas_w,
-                                                  row_lo, row_hi, _lib.stream_ptr()), "msr_blend_accumulate")
+                    row_hi: int, target=None) -> None:
+        """msr_blend_accumulate into the band accumulators (dedup mode) or into ``target`` = (acc (3, rows, pitch),
+        d_lattice, GY, GX, lattice_y0, acc_y0): rebuildTile's loop body for patches [k0, k0 + n) of that lattice."""
+        plan = self.plan
+        if target is None:
+            band = self._dband
+            target = (self._acc, self._d_lattice, band.j1 - band.j0, band.gx, band.j0 * plan.stride, self._c0)
+        acc, d_lattice, gy, gx, lattice_y0, acc_y0 = target
+        _lib.check(self._lib.msr_blend_accumulate(pred.data_ptr(), lohi.data_ptr(), k0, n, d_lattice.data_ptr(), gy, gx,
+                                                  gy_lo, gy_hi, lattice_y0, self._blend_weights().data_ptr(),
+                                                  plan.image_size, plan.stride, int(add_half), acc[0].data_ptr(),
+                                                  acc[1].data_ptr(), acc[2].data_ptr(), int(acc.shape[2]), acc_y0,
+                                                  int(acc.shape[1]), int(acc.shape[2]), row_lo, row_hi,
+                                                  _lib.stream_ptr()), "msr_blend_accumulate")
         self.launches += 1
+
+    def _generate_repeats(self, src, n: int, d_eps, s0: int, device_model: bool, n_real: int,
+                          promote_pads: bool = True):
+        """Repeated-sample mode: the ``n`` slots in ``src`` generated ``samples_per_patch`` times -> float32 CUDA tensor
+        (R, n, I, I) and the flag telling the blend whether ``+ 0.5`` (process_full_tiles.py:340) is still to be added.
+        Host plug-ins are called batch by batch, repetition by repetition; tile by tile they see the reference's batch
+        dtype (float64 when the batch carries zero pads, :472), in dedup mode float32."""
+        torch = _torch()
+        plan = self.plan
+        i, b, r_ = plan.image_size, plan.batch_size, self.samples_per_patch
+        preds = torch.empty((r_, n, i, i), dtype=torch.float32, device=self.device)
+        if device_model:
+            for r in range(r_):
+                self.model.forward_device(src[:n], preds[r], None if d_eps is None else d_eps[r, s0:s0 + n], n // b)
+                self.model_launches += self.model.last_launch_count
+            return preds, 1
+        host = src[:n].cpu().numpy()
+        for j in range(0, n, b):
+            batch = host[j:j + b]
+            if promote_pads and j + b > n_real:
+                batch = batch.astype(np.float64)
+            for r in range(r_):
+                y = self.model(batch, training=False)
+                y = (np.array(y)[:, :, :, -1] + 0.5).astype(np.float32)
+                preds[r, j:j + b].copy_(torch.from_numpy(np.ascontiguousarray(y)))
+        return preds, 0
+
+    def _process_tile_repeats(self, px: int, py: int, eps=None) -> None:
+        """processTile in repeated-sample mode (samples_per_patch = R > 1, beyond the reference): every batch of the
+        tile is generated R times; the tile's accumulators (rebuildTile :386-390) are updated batch by batch, repetition
+        by repetition, patch by patch with msr_blend_accumulate, then finalised / pasted / cropped like any tile.
+        ``eps``: optional (R, slots, 256)."""
+        torch = _torch()
+        plan = self.plan
+        if (px, py) not in self._tile_plan:
+            raise ValueError(f"tile ({px}, {py}) is not owned by rank {self.rank}")
+        tp = self._tile_plan[(px, py)]
+        i, b, t, dev = plan.image_size, plan.batch_size, plan.tile_size, self.device
+        r_ = self.samples_per_patch
+        n_valid = tp["n_valid"]
+        slots = plan.batch_slots(n_valid)
+        rows, cols = plan.tile_window(px, py)
+        side = t + 2 * plan.off                                                # :386
+        acc = torch.zeros((3, side, side), dtype=torch.float32, device=dev)
+        g = plan.lattice_side
+        if n_valid:
+            d_lattice = torch.from_numpy(tp["lattice"]).to(dev, non_blocking=True)
+            target = (acc, d_lattice, g, g, 0, 0)
+            slot_xy = np.full((slots, 2), -1, np.int32)
+            slot_xy[:n_valid] = tp["xy"]
+            slot_xy[:n_valid, 1] -= self._c0
+            d_slot_xy = torch.from_numpy(slot_xy).to(dev, non_blocking=True)
+            row_of = ((tp["xy"][:, 1] - py) // plan.stride).astype(np.int32)
+            minmax = torch.empty((slots, 4), dtype=torch.float32, device=dev)
+            device_model = isinstance(self.model, (_Generator, IdentityModel))
+            groups = max(1, min(self._groups_cfg or getattr(self.model, "max_groups", 1),
+                                getattr(self.model, "max_groups", 1))) if device_model else 1
+            chunk = groups * b
+            src = torch.empty((min(chunk, slots), i, i, 2), dtype=torch.float32, device=dev)
+            partial = torch.empty((min(chunk, slots) * 32 * 4,), dtype=torch.float32, device=dev)
+            d_eps = self._sampler_noise(slots, eps, py * 131071 + px, r_) if device_model else None
+            for s0 in range(0, slots, chunk):
+                n = min(chunk, slots - s0)
+                self._gather(d_slot_xy[s0:s0 + n], n, src, minmax[s0:s0 + n], partial)
+                preds, add_half = self._generate_repeats(src, n, d_eps, s0, device_model, n_valid - s0)
+                self.slots_executed += n * r_
+                for j in range(0, n, b):
+                    n_real = min(b, n_valid - (s0 + j))
+                    if n_real <= 0:
+                        break
+                    lohi = minmax[s0 + j:s0 + j + n_real, 2:4].contiguous()
+                    gy_lo, gy_hi = int(row_of[s0 + j]), int(row_of[s0 + j + n_real - 1])
+                    for r in range(r_):
+                        self._accumulate(preds[r, j:j + n_real], lohi, s0 + j, n_real, gy_lo, gy_hi, add_half, 0, side,
+                                         target)
+        first = (plan.off * side + plan.off) * 4
+        out_off = (py - self._out_r0) * plan.width + px
+        nv = float(np.float32(self.no_value))
+        windows = [(self.mean_out.data_ptr() + 4 * out_off, self.std_out.data_ptr() + 4 * out_off,
+                    self.good_out.data_ptr() + out_off, plan.width, rows, cols)]
+        tile_bufs = None
+        if self.save_tiles:
+            tile_bufs = (torch.empty((t, t), dtype=torch.float32, device=dev),
+                         torch.empty((t, t), dtype=torch.float32, device=dev),
+                         torch.empty((t, t), dtype=torch.uint8, device=dev))
+            windows.append((tile_bufs[0].data_ptr(), tile_bufs[1].data_ptr(), tile_bufs[2].data_ptr(), t, t, t))
+        for mean_p, std_p, good_p, pitch, wr, wc in windows:                  # :404-413 + paste / crop (:541-545)
+            _lib.check(self._lib.msr_blend_finalize(acc[0].data_ptr() + first, acc[1].data_ptr() + first,
+                                                    acc[2].data_ptr() + first, side, wr, wc, nv, mean_p, std_p, good_p,
+                                                    pitch, _lib.stream_ptr()), "msr_blend_finalize")
+            self.launches += 1
+        if tile_bufs:
+            self._save_tile_bufs(tile_bufs, px, py)
 
     def bandSlots(self) -> int:
         """Generator slots this rank executes in dedup mode (valid patches rounded up to whole batches)."""
@@ -699,11 +808,25 @@ class DEMSuperResolution:
             chunk, add_half = b, 0
         src = torch.empty((min(chunk, slots), i, i, 2), dtype=torch.float32, device=dev)
         partial = torch.empty((min(chunk, slots) * 32 * 4,), dtype=torch.float32, device=dev)
-        d_eps = self._sampler_noise(slots, eps, band.j0 * 8191 + 17) if device_model else None
+        r_ = self.samples_per_patch
+        d_eps = self._sampler_noise(slots, eps, band.j0 * 8191 + 17, r_) if device_model else None
         for s0 in range(0, slots, chunk):
             n = min(chunk, slots - s0)
             n_real = min(n, n_valid - s0)
             self._gather(d_slot_xy[s0:s0 + n], n, src, minmax[s0:s0 + n], partial)
+            if r_ > 1:   # repeated-sample mode: blend batch by batch, repetition by repetition, patch by patch
+                preds, half = self._generate_repeats(src, n, d_eps, s0, device_model, n_real, promote_pads=False)
+                self.slots_executed += n * r_
+                for j in range(0, n_real, b):
+                    nr = min(b, n_real - j)
+                    lohi = minmax[s0 + j:s0 + j + nr, 2:4].contiguous()
+                    gy_lo, gy_hi = int(row_of[s0 + j]), int(row_of[s0 + j + nr - 1])
+                    for r in range(r_):
+                        pr = preds[r, j:j + nr]
+                        self._accumulate(pr, lohi, s0 + j, nr, gy_lo, gy_hi, half, main_lo, plan.canvas_h)
+                        if gy_lo < seam_rows:
+                            self._retained.append((pr, lohi, s0 + j, nr, gy_lo, min(gy_hi, seam_rows - 1), half))
+                continue
             if device_model:
                 pred = torch.empty((n, i, i), dtype=torch.float32, device=dev)
                 self.model.forward_device(src[:n], pred, None if d_eps is None else d_eps[s0:s0 + n], n // b)

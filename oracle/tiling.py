@@ -165,7 +165,8 @@ def rebuild_tile(generated: Dict[Tuple[int, int], np.ndarray],
     w_sum = np.zeros((a, a), f32)
     mean = np.zeros((a, a), f32)
     s_acc = np.zeros((a, a), f32)
-    for (kx, ky), pred in generated.items():
+    items = generated.items() if isinstance(generated, dict) else generated   # or an ordered [(key, pred)] (repeats)
+    for (kx, ky), pred in items:
         accumulate_patch(w_sum, mean, s_acc, np.asarray(pred), minmax[(kx, ky)], kx, ky, w, i, p)
     w_c = w_sum[o:a - o, o:a - o]
     m_c = mean[o:a - o, o:a - o].copy()
@@ -200,10 +201,14 @@ ModelFn = Callable[..., np.ndarray]   # m(x, training=False)
 
 
 def process_tile(dem_c: np.ndarray, img_c: np.ndarray, geo: Geometry, px: int, py: int, batch_size: int,
-                 no_value: float, model: Optional[ModelFn] = None, return_patches: bool = False):
+                 no_value: float, model: Optional[ModelFn] = None, return_patches: bool = False, repeats: int = 1):
     """process_full_tiles.py:431-479 (+327-345) -- one tile: gather valid patches, normalise, batch, run the model,
     take the last output channel ``+ 0.5``, blend.  ``model(batch[B,I,I,2], training=False) -> [B,I,I,C]``; default
-    identity."""
+    identity.
+
+    ``repeats`` > 1 is the repeated-sample mode (beyond the reference): every batch is
+    generated ``repeats`` times (a stochastic model draws new noise per call) and blended batch by batch, repetition
+    by repetition, patch by patch; predictions enter the blend as float32."""
     i = geo.image_size
     keys, inputs, mm = [], {}, {}
     for xx, yy in patch_origins(geo, px, py):
@@ -214,6 +219,15 @@ def process_tile(dem_c: np.ndarray, img_c: np.ndarray, geo: Geometry, px: int, p
         keys.append(key)
         inputs[key] = x
         mm[key] = lohi
+    if repeats > 1:
+        sequence = []
+        for slots in batch_plan(keys, batch_size):
+            batch = np.array([inputs[k] if k != (-1, -1) else np.zeros((i, i, 2)) for k in slots])
+            for _ in range(repeats):
+                pred = batch if model is None else model(batch, training=False)
+                pred = (np.array(pred)[:, :, :, -1] + 0.5).astype(np.float32)
+                sequence += [(k, y) for k, y in zip(slots, pred) if k != (-1, -1)]
+        return rebuild_tile(sequence, mm, geo, no_value)
     generated: Dict[Tuple[int, int], np.ndarray] = {}
     for slots in batch_plan(keys, batch_size):
         # np.array(batch) (:338): float32, or float64 when float64 zero pads (:472) are present -- Keras casts to
@@ -240,7 +254,7 @@ def assemble(tiles: Dict[Tuple[int, int], np.ndarray], geo: Geometry, dtype) -> 
 
 
 def process_map(dem: np.ndarray, img: np.ndarray, image_size: int, stride: int, batch_size: int, tile_size: int,
-                no_value: float = -32768.0, model: Optional[ModelFn] = None):
+                no_value: float = -32768.0, model: Optional[ModelFn] = None, repeats: int = 1):
     """process_full_tiles.py:568-587 minus file I/O and preprocess(): pad -> tiles -> blend -> assemble.
 
     Returns (mean f32, std f32, good u8), each exactly (H, W)."""
@@ -248,7 +262,7 @@ def process_map(dem: np.ndarray, img: np.ndarray, image_size: int, stride: int, 
     dem_c, img_c = pad_inputs(dem, img, geo, no_value)
     means, stds, goods = {}, {}, {}
     for (xx, yy) in tile_list(geo):
-        m, s, g = process_tile(dem_c, img_c, geo, xx, yy, batch_size, no_value, model)
+        m, s, g = process_tile(dem_c, img_c, geo, xx, yy, batch_size, no_value, model, repeats=repeats)
         means[(xx, yy)], stds[(xx, yy)], goods[(xx, yy)] = m, s, g
     return (assemble(means, geo, np.float32), assemble(stds, geo, np.float32), assemble(goods, geo, np.uint8))
 
@@ -271,7 +285,8 @@ def lattice_counts(geo: Geometry) -> Tuple[int, int]:
 
 def process_map_dedup(dem: np.ndarray, img: np.ndarray, image_size: int, stride: int, batch_size: int, tile_size: int,
                       no_value: float = -32768.0, model: Optional[ModelFn] = None,
-                      row_bands: Optional[Sequence[Tuple[int, int]]] = None, return_plan: bool = False):
+                      row_bands: Optional[Sequence[Tuple[int, int]]] = None, return_plan: bool = False,
+                      repeats: int = 1):
     """Global-lattice form of process_map: valid patches visited y outer / x inner over the whole canvas, chopped into
     batches of ``batch_size`` per band of lattice rows (``row_bands`` = [(j0, j1)], default one band; the last batch of
     a band is padded with float32 zero inputs), blended into canvas-sized float32 accumulators with the reference's
@@ -300,11 +315,12 @@ def process_map_dedup(dem: np.ndarray, img: np.ndarray, image_size: int, stride:
         plan_out.append(batches)
         for slots in batches:
             batch = np.array([inputs[k] if k != (-1, -1) else np.zeros((i, i, 2), f32) for k in slots])
-            pred = batch if model is None else model(batch, training=False)
-            pred = (np.array(pred)[:, :, :, -1] + 0.5).astype(f32, copy=False)            # :340
-            for k, y in zip(slots, pred):
-                if k != (-1, -1):
-                    accumulate_patch(w_sum, mean, s_acc, y, mm[k], k[0], k[1], w, i, p)
+            for _ in range(repeats):                                                       # repeated-sample mode: see process_tile
+                pred = batch if model is None else model(batch, training=False)
+                pred = (np.array(pred)[:, :, :, -1] + 0.5).astype(f32, copy=False)        # :340
+                for k, y in zip(slots, pred):
+                    if k != (-1, -1):
+                        accumulate_patch(w_sum, mean, s_acc, y, mm[k], k[0], k[1], w, i, p)
     h, wd = geo.height, geo.width
     w_c, m_c, s_c = w_sum[o:o + h, o:o + wd], mean[o:o + h, o:o + wd].copy(), s_acc[o:o + h, o:o + wd]
     good = w_c > 0

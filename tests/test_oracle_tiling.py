@@ -92,3 +92,23 @@ def test_dedup_oracle_equals_tile_by_tile_for_per_sample_models(name):
             for a, b in zip(got, ref):
                 np.testing.assert_array_equal(a, b)
             assert len(batches) == world
+
+
+def test_repeats_one_is_the_reference_path_and_more_repeats_shrink_nothing():
+    """oracle ``repeats``: 1 reproduces the pinned path bit for bit; with a deterministic model R identical generations
+    leave the mean where it was (up to float32 rounding of the running update) and keep ``good`` unchanged."""
+    import toy_models
+    case = golden_inputs.CASES["wobble_200x260"]
+    dem, img = golden_inputs.make_rasters(case)
+    args = (dem, img, case["I"], case["S"], case["B"], case["T"], case["NV"], toy_models.ripple)
+    with np.errstate(all="ignore"):
+        base = tiling.process_map(*args)
+        one = tiling.process_map(*args, repeats=1)
+        three = tiling.process_map(*args, repeats=3)
+        flick = tiling.process_map(*args[:-1], toy_models.Flicker(), repeats=3)
+    for a, b in zip(base, one):
+        np.testing.assert_array_equal(a, b)
+    np.testing.assert_array_equal(three[2], base[2])
+    g = base[2].astype(bool)
+    assert np.abs(three[0][g] - base[0][g]).max() <= 1e-3 * np.abs(base[0][g]).max()
+    assert flick[1][g].mean() > base[1][g].mean()          # repetitions that disagree add to the uncertainty

@@ -30,3 +30,17 @@ def ripple(x, training=False):
     ortho, dem = x[..., 0], x[..., 1]
     y = dem * np.float32(0.875) + ortho * ortho * np.float32(0.0625) + ortho * dem * np.float32(0.03125)
     return y[..., None].astype(np.float32)
+
+
+class Flicker:
+    """Stateful stand-in for a stochastic generator: per-sample like ``ripple``, plus an offset that changes with every
+    call (what new sampler noise does), so repeated generations of the same batch disagree."""
+
+    def __init__(self):
+        self.calls = 0
+
+    def __call__(self, x, training=False):
+        y = ripple(x)
+        k = np.float32((self.calls % 7) - 3) * np.float32(0.015625)
+        self.calls += 1
+        return (y + k).astype(np.float32)
