@@ -1,10 +1,18 @@
 """torch-CPU restatement of the reference generators (TEST INFRASTRUCTURE ONLY -- see oracle/__init__.py).
 
-PARITY UNPINNED: the arithmetic of the reference lives in TensorFlow 2.5 / Keras / tensorflow-addons 0.16.1
-(pip-env.py:15,34,36), none of which is installed here, and the reference ships no golden vectors; TensorFlow
-semantics are restated from SURVEY.md Appendix B.  Each function cites the reference lines it follows.  What is
-pinned: parameter counts / shapes (App. A), fp32-vs-fp64 self agreement, and structural invariants
-(tests/test_oracle_generator.py).
+PARITY: pinned to the reference's own graph code, unpinned to TensorFlow's kernels.  The arithmetic of the reference
+lives in TensorFlow 2.5 / Keras / tensorflow-addons 0.16.1 (pip-env.py:15,34,36), none of which is installable here, and
+the reference ships no golden vectors.  What holds this file in place (tests/test_oracle_generator_pinned.py):
+  * the UNMODIFIED reference modules (networks.py, blocks.py, spade.py, sampling.py, pix2pix.py and the ``call`` bodies
+    of GauGAN / CNNSpade cut out of model.py) executed on a numpy op shim (tests/golden/tf_numpy_shim.py) reproduce this
+    file's outputs to float32 rounding -- so the graph (layer order, skips, which statistics, which activations) is the
+    reference's, not one reading of it;
+  * the op semantics the shim and this file share only by documentation (SAME padding, Conv2DTranspose, half-pixel
+    nearest resize, flatten order: SURVEY.md App. B) are each checked against scalar-loop restatements;
+  * tests/golden/make_golden_tf.py writes generator_tf.npz on any TensorFlow-equipped box; the same test then pins this
+    file to TensorFlow itself.  Until that file exists the TensorFlow-kernel level stays "parity unpinned".
+Also pinned: parameter counts / shapes (App. A), fp32-vs-fp64 self agreement, structural invariants
+(tests/test_oracle_generator.py).  Each function cites the reference lines it follows.
 
 Weights arrive in Keras layout (moonsuperresolution_b200/weights.py); activations are NHWC at the interface and NCHW
 internally (torch).  ``dtype`` selects float32 (the reference's precision) or float64 (error-free yardstick).

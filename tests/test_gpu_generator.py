@@ -205,6 +205,58 @@ def test_spade_generator_bf16_tensor_core_mode(msr, arch, i, b):
     assert err <= TOL_BF16 * max(1.0, np.abs(want).max()), err
 
 
+def test_gaugan512_at_the_bench_call_shape_bf16(msr, torch):
+    """BASELINE.json configs[2] at bench.py's own call shape: GauGAN-512, bf16 tensor-core mode, batch 16, EIGHT groups in
+    one generator call (128 patches, the n = 128 plans with CTA pairs / strips on every layer from rb2 on).  Group 5
+    carries 7 zero padding slots, the way processTile pads the last batch of a tile (process_full_tiles.py:468-474): they
+    take part in that group's batch statistics.  Groups 0, 5 and 7 are held to the oracle at north_star's bf16 bar
+    (<= 1e-2 max abs on the O(1) output); every group must equal the same model called on that group alone (batch
+    statistics never cross groups)."""
+    i, b, groups = 512, 16, 8
+    w = W.random_init("spade", i, seed=0, perturb_affine=True)
+    rng = np.random.default_rng(42)
+    x = rng.uniform(-0.5, 0.5, (groups * b, i, i, 2)).astype(np.float32)
+    x[5 * b + 9:6 * b] = 0.0
+    eps = rng.standard_normal((groups * b, 256)).astype(np.float32)
+    model = msr.GauGAN(i, b, precision="bf16", weights=w, max_groups=groups)
+    src = torch.from_numpy(x).cuda()
+    d_eps = torch.from_numpy(eps).cuda()
+    out = torch.empty((groups * b, i, i), dtype=torch.float32, device="cuda")
+    model.forward_device(src, out, d_eps, groups)
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    assert np.isfinite(got).all()
+    worst = 0.0
+    for g in (0, 5, 7):
+        sl = slice(g * b, (g + 1) * b)
+        want = OG.gaugan_call(x[sl], w, eps[sl], "spade")[..., 0]
+        err = np.abs(got[sl] - want).max() / max(1.0, np.abs(want).max())
+        worst = max(worst, err)
+        assert err <= TOL_BF16, (g, err)
+    one = torch.empty((b, i, i), dtype=torch.float32, device="cuda")
+    for g in range(groups):
+        sl = slice(g * b, (g + 1) * b)
+        model.forward_device(src[sl], one, d_eps[sl], 1)
+        torch.cuda.synchronize()
+        # same kernels, same per-group statistics; only the dense layers' split-K shape depends on the row count
+        assert np.abs(one.cpu().numpy() - got[sl]).max() <= 5e-3, g
+    print("GauGAN-512 bf16 B=16 x 8 groups: worst normalised max-abs error vs oracle", worst)
+
+
+def test_gaugan512_fp32_mode(msr):
+    """fp32 parity mode at BASELINE.json's model size (I = 512), batch 2 with one zero padding slot: <= 1e-4."""
+    i, b = 512, 2
+    w = W.random_init("spade", i, seed=5, perturb_affine=True)
+    x, eps = inputs(i, b, seed=9)
+    want, want_latent = OG.gaugan_call(x, w, eps, "spade", return_latent=True)
+    model = msr.GauGAN(i, b, precision="fp32", weights=w)
+    got = model(x, training=False, eps=eps)
+    lat = model.read_activation("latent").reshape(b, 256)
+    assert np.abs(lat - want_latent).max() < 1e-4 * max(1.0, np.abs(want_latent).max())
+    err = np.abs(got - want).max() / max(1.0, np.abs(want).max())
+    assert err <= TOL_FP32, err
+
+
 @pytest.mark.parametrize("b,precision,atol", [(2, "fp32", 1e-6), (9, "fp32", 1e-5), (9, "bf16", 5e-3)])
 def test_groups_have_independent_batch_statistics(msr, torch, b, precision, atol):
     """Two batches pushed through one forward call (max_groups = 2) equal two separate calls (b = 9: 18 rows go through
@@ -251,8 +303,9 @@ def test_engine_with_device_model_matches_oracle_pipeline(msr):
         mean, std, good = eng.run(dem, img)
         np.testing.assert_array_equal(good, ref[2])
         g = good.astype(bool)
-        assert np.abs(mean[g] - ref[0][g]).max() / scale <= 4 * tol
-        assert np.abs(std[g] - ref[1][g]).max() / scale <= 4 * tol
+        # north_star: max abs error <= 1e-2 (bf16) / 1e-4 (fp32) in normalised units, i.e. relative to the DEM's range
+        assert np.abs(mean[g] - ref[0][g]).max() / scale <= tol, (precision, np.abs(mean[g] - ref[0][g]).max() / scale)
+        assert np.abs(std[g] - ref[1][g]).max() / scale <= tol, (precision, np.abs(std[g] - ref[1][g]).max() / scale)
         assert (mean[~g] == cfg.no_value).all()
 
 
@@ -274,8 +327,8 @@ def test_pix2pix_tiled_pipeline_matches_oracle(msr):
     g = good.astype(bool)
     assert g.any()
     scale = float(dem.max() - dem.min())
-    assert np.abs(mean[g] - ref[0][g]).max() / scale <= 4 * TOL_FP32
-    assert np.abs(std[g] - ref[1][g]).max() / scale <= 4 * TOL_FP32
+    assert np.abs(mean[g] - ref[0][g]).max() / scale <= TOL_FP32, np.abs(mean[g] - ref[0][g]).max() / scale
+    assert np.abs(std[g] - ref[1][g]).max() / scale <= TOL_FP32, np.abs(std[g] - ref[1][g]).max() / scale
 
 
 def test_repeated_forward_calls_honour_new_output_buffers(msr, torch):
