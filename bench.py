@@ -60,6 +60,13 @@ def parse():
                          "dedup-mode leg now covers at any tile_size); reported beside, never as, the headline")
     ap.add_argument("--no-dedup", action="store_true",
                     help="skip the extra step in dedup mode (every patch position generated once; SURVEY 8e mode B)")
+    ap.add_argument("--no-multi-gpu-check", action="store_true",
+                    help="N > 1: skip the bit-identity check of the sharded run against a single-process run")
+    ap.add_argument("--extras", default="auto",
+                    help="comma list of the other BASELINE.json configs to time once each beside the headline: cfg1 "
+                         "(SPADE-256 one tile), cfg2 (pix2pix-256 4096^2), cfg4 (CNN-512 15000x20000), cfg5 (SPADE-512 "
+                         "15000x70000), fp32 (parity mode on one tile); auto = cfg1,cfg2,fp32 at N=1, cfg4 at N=2/4, "
+                         "cfg4,cfg5 at N=8; none = skip")
     return ap.parse_args()
 
 
@@ -255,6 +262,167 @@ def config_dict(args, n, plan, slots):
                   (args.rows_per_gpu * plan.width * 4 / 1e6)}
 
 
+
+def multi_gpu_check(torch, dist, args, model, rank, world, dev):
+    """N > 1, before anything is timed: the sharded path (every rank loads only its own rows, halo rows / accumulator
+    seam strips by NCCL send / recv, output bands gathered on rank 0) must reproduce a single-process run of the same
+    engine BIT FOR BIT.  Tile by tile with the bench's own generator (tiles are whole, so batch
+    composition and sampler noise do not depend on the rank count) and in dedup mode with the device identity model
+    (per-sample, so the order-dependent blend is the only thing that could differ).  Returns a dict; raises on rank 0's
+    verdict being a mismatch (all ranks)."""
+    from moonsuperresolution_b200 import DEMSuperResolution, DSRConfig, IdentityModel
+    i, s, b = args.image_size, args.stride, args.batch_size
+    t = 2 * i                                   # small tiles: (2I + I - S) / S lattice rows, a few dozen slots each
+    h, w = t * world + i // 2 + 37, t + i + 19  # ragged: the last band and the last tile column are partial
+    d_dem, d_img = synth_rows(torch, 0, h, w, dev)
+    d_dem[h // 3:h // 3 + 5, w // 2:w // 2 + 9] = -32768.0     # a hole: validity must agree across ranks too
+    report = {"raster": [h, w], "tile_size": t}
+    ok = True
+    for label, mode, mdl in (("faithful_bench_model", "faithful", model),
+                             ("dedup_identity_model", "dedup", IdentityModel(i, b))):
+        cfg = DSRConfig(image_size=i, stride=s, batch_size=b, tile_size=t, groups_per_call=args.groups, mode=mode)
+        eng = DEMSuperResolution(cfg, model=mdl, rank=rank, world_size=world, device=dev)
+        o0, o1 = eng.ownedRows(h, w)
+        eng.setOwnedRows(d_dem[o0:o1].contiguous(), d_img[o0:o1].contiguous(), h)
+        eng.padInputs()
+        eng.processTiles()
+        res = eng.gatherResults()
+        verdict = None
+        if rank == 0:
+            single = DEMSuperResolution(cfg, model=mdl, device=dev)
+            single.setRasters(d_dem, d_img)
+            single.padInputs()
+            single.processTiles()
+            ref = single.results()[:3]
+            same = all(np.array_equal(a, r) for a, r in zip(res, ref)) and int(res[2].sum()) > 0
+            verdict = "bit-identical" if same else "MISMATCH"
+            report[label] = verdict
+            report[label + "_good_pixels"] = int(res[2].sum())
+            ok = ok and same
+        dist.barrier()
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.broadcast(flag, 0)
+    report["ok"] = bool(int(flag.item()))
+    return report
+
+
+def time_config(torch, dist, name, arch, image_size, stride, batch, tile, h, w, mode, model, rank, world, dev, groups,
+                warm=True):
+    """One timed step of another BASELINE.json configuration (device-resident synthetic rasters, sharded like the
+    headline run when world > 1); CUDA events, max over ranks."""
+    from moonsuperresolution_b200 import DEMSuperResolution, DSRConfig
+    cfg = DSRConfig(image_size=image_size, stride=stride, batch_size=batch, tile_size=tile, groups_per_call=groups,
+                    mode=mode)
+    eng = DEMSuperResolution(cfg, model=model, rank=rank, world_size=world, device=dev)
+    if world > 1:
+        o0, o1 = eng.ownedRows(h, w)
+        d_dem, d_img = synth_rows(torch, o0, o1, w, dev)
+    else:
+        q0, q1 = eng.rowsNeeded(h, w)
+        d_dem, d_img = synth_rows(torch, q0, q1, w, dev)
+
+    def step():
+        if world > 1:
+            eng.setOwnedRows(d_dem, d_img, h)
+        else:
+            eng.setRasters(d_dem, d_img, row_offset=q0, full_height=h)
+        eng.padInputs()
+        eng.processTiles()
+    if warm:
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    s_before = eng.slots_executed
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record()
+    step()
+    a1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([a0.elapsed_time(a1)], dtype=torch.float64, device=dev)
+    sl = torch.tensor([eng.slots_executed - s_before], dtype=torch.int64, device=dev)
+    slmax = sl.clone()
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sl, op=dist.ReduceOp.SUM)
+        dist.all_reduce(slmax, op=dist.ReduceOp.MAX)
+    sec = float(t.item()) / 1e3
+    gf = GF_PER_SLOT.get((arch, image_size))
+    out = {"config": name, "mode": mode, "raster": [h, w], "seconds": sec, "value": h * w / 1e6 / sec, "unit": UNIT,
+           "slots": int(sl.item()), "slots_max_per_gpu": int(slmax.item()), "n_gpus": world, "steps": 1,
+           "model_tflops": (int(sl.item()) * gf / 1e3) / sec if gf else None}
+    del eng, d_dem, d_img
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_extras(torch, dist, args, weights, rank, world, dev):
+    """The other BASELINE.json configs, one timed step each (reported beside the headline, never as it)."""
+    from moonsuperresolution_b200 import models as M
+    from moonsuperresolution_b200 import weights as W
+    want = args.extras
+    if want == "auto":
+        want = {1: "cfg1,cfg2,fp32", 2: "cfg4", 4: "cfg4", 8: "cfg4,cfg5"}.get(world, "")
+    names = [x for x in want.split(",") if x and x != "none"]
+    out = {}
+    for name in names:
+        try:
+            if name == "cfg1":      # configs[0]: SPADE-256 generator forward on one 256 x 256 tile, batch 1
+                w256 = W.random_init("spade", 256, seed=0)
+                m = M.GauGAN(256, 1, precision="bf16", weights=w256, max_groups=1)
+                src = torch.rand((1, 256, 256, 2), device=dev) - 0.5
+                eps = torch.randn((1, 256), device=dev)
+                o = torch.empty((1, 256, 256), device=dev)
+                for _ in range(5):
+                    m.forward_device(src, o, eps, 1)
+                torch.cuda.synchronize()
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                for _ in range(20):
+                    m.forward_device(src, o, eps, 1)
+                a1.record()
+                torch.cuda.synchronize()
+                ms = a0.elapsed_time(a1) / 20
+                out[name] = {"config": "BASELINE.json configs[0]: SPADE-256 forward, one 256x256 tile, batch 1",
+                             "ms_per_forward": ms, "value": 256 * 256 / 1e6 / (ms / 1e3), "unit": UNIT,
+                             "model_tflops": GF_PER_SLOT[("spade", 256)] / 1e3 / (ms / 1e3), "steps": 20}
+                m.close()
+            elif name == "cfg2":    # configs[1]: pix2pix-256 over 4096 x 4096, stride 32, batch 16
+                m = M.Pix2Pix(batch_size=16, weights=W.random_init("pix2pix", 256, seed=0), max_groups=args.groups,
+                              precision="bf16")
+                out[name] = time_config(torch, dist, "BASELINE.json configs[1]: pix2pix-256 tiled inference over "
+                                        "4096x4096, stride 32, batch 16, tile 1024", "pix2pix", 256, 32, 16, 1024,
+                                        4096 * world, 4096, "faithful", m, rank, world, dev, args.groups)
+                m.close()
+            elif name in ("cfg4", "cfg5"):
+                arch = "cnn" if name == "cfg4" else "spade"
+                hh, ww = (20000, 15000) if name == "cfg4" else (70000, 15000)     # sharded along the long axis
+                cls = M.CNNSpade if arch == "cnn" else M.GauGAN
+                m = cls(512, 16, precision="bf16", weights=weights, max_groups=args.groups)
+                label = ("BASELINE.json configs[3]: CNN-512 over 15000x20000" if name == "cfg4" else
+                         "BASELINE.json configs[4]: SPADE-512 over 15000x70000 (N=16 nominal samples)")
+                res = {}
+                for mode in ("faithful", "dedup"):
+                    res[mode] = time_config(torch, dist, label + ", stride 128, batch 16, tile 1024", arch, 512, 128,
+                                            16, 1024, hh, ww, mode, m, rank, world, dev, args.groups, warm=False)
+                out[name] = res
+                m.close()
+            elif name == "fp32":    # the parity mode has a number too: one 1024 x 1024 tile, fp32 CUDA-core generator
+                cls = {"spade": M.GauGAN, "cnn": M.CNNSpade}.get(args.arch)
+                if cls is None or world > 1:
+                    continue
+                m = cls(args.image_size, args.batch_size, precision="fp32", weights=weights, max_groups=1)
+                side = 2 * args.image_size
+                out[name] = time_config(torch, dist, f"{args.arch}-{args.image_size} fp32 parity mode, one "
+                                        f"{side}x{side} tile", args.arch, args.image_size, args.stride, args.batch_size,
+                                        side, side, side, "faithful", m, rank, world, dev, 1, warm=False)
+                m.close()
+        except Exception as ex:       # an optional extra must never cost the headline line
+            out[name] = {"error": f"{type(ex).__name__}: {str(ex)[:300]}"}
+        torch.cuda.empty_cache()
+    return out
+
 _JSON_FD = None
 
 
@@ -321,6 +489,17 @@ def main():
     else:
         d_dem, d_img = synth_rows(torch, r0, r1, w, dev)
 
+    mgc = None
+    if world > 1 and not args.no_multi_gpu_check:
+        mgc = multi_gpu_check(torch, dist, args, model, rank, world, dev)
+        if not mgc["ok"]:
+            if rank == 0:
+                emit({"metric": METRIC, "error": "multi-GPU run is not bit-identical to the single-process run",
+                      "multi_gpu_check": mgc, "n_gpus": n})
+            dist.destroy_process_group()
+            raise SystemExit(1)
+        torch.cuda.empty_cache()
+
     def load_resident(e):
         if world > 1:
             e.setOwnedRows(d_dem, d_img, h)
@@ -355,9 +534,11 @@ def main():
     sync_all()
     launches = torch.tensor([eng.launches - l0 + eng.model_launches - m0, eng.slots_executed - s0], dtype=torch.int64,
                             device=dev)
+    slots_max = torch.tensor([eng.slots_executed - s0], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(launches, op=dist.ReduceOp.SUM)
+        dist.all_reduce(slots_max, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
     ms_per_step = ms_total / args.steps
     mp = h * w / 1e6
@@ -375,7 +556,7 @@ def main():
                 eng.padInputs()
                 eng.processTiles()
                 return eng.results()[:3]
-            return eng.run(h_dem, h_img, row_offset=r0, full_height=h)
+            return eng.run(h_dem, h_img, row_offset=r0, full_height=h, copy=False)   # views of the pinned D2H buffers
 
         step_e2e()                                                    # warm (pinned staging, allocator)
         sync_all()
@@ -517,6 +698,8 @@ def main():
         except Exception as ex:   # an optional extra must never cost the headline line
             dedup = {"error": str(ex)[:300]}
 
+    extras = run_extras(torch, dist, args, weights, rank, world, dev)
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sec, cores, desc = cpu_sample_seconds_per_slot(args, weights)
@@ -532,7 +715,14 @@ def main():
                 "gpu_launches": int(launches[0].item()), "slots_executed": int(launches[1].item()),
                 "model_tflops": (int(launches[1].item()) * gf / 1e3) / (ms_total / 1e3) if gf else None,
                 "roofline": roofline, "hbm_kernels": hbm_kernels, "cpu_baseline": cpu_baseline,
-                "alt_tile_size": alt, "dedup_mode": dedup,
+                "alt_tile_size": alt, "dedup_mode": dedup, "multi_gpu_check": mgc, "other_configs": extras,
+                # weak scaling executes MORE slots per GPU on interior bands (two halos instead of one): the
+                # slot-normalised rate separates that from communication / clocks when the driver computes efficiency
+                "slots_per_gpu_max": int(slots_max.item()) // args.steps,
+                "slots_per_sec_per_gpu": (int(slots_max.item()) / (ms_total / 1e3)),
+                "value_note": "device-timed, inputs resident in HBM, up to the assembled rasters in HBM; `e2e` adds the "
+                              "H2D of the inputs and the D2H of the three rasters (SURVEY 8d's definition) and is the "
+                              "headline",
                 "breakdown_instrumented_step": breakdown}
         emit(line)
     if world > 1:

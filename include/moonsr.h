@@ -158,6 +158,22 @@ int msr_blend_finalize(const float* d_wsum, const float* d_mean_acc, const float
                        int cols, float no_value, float* d_mean, float* d_std, uint8_t* d_good, int64_t out_pitch,
                        void* stream);
 
+/* "Fast" variants of msr_blend_tile / msr_blend_accumulate (DSRConfig(blend="fast")): the same update rule
+ * (process_full_tiles.py:395-402), the same patch-to-pixel placement, visiting order and `good` mask, but the running
+ * w_sum / mean / S are updated in float32 (no float64 intermediates), four adjacent pixels per thread with 128-bit
+ * loads and stores, so the kernels are bound by HBM instead of the double-precision pipe.  Values agree with the
+ * bit-exact kernels to float32 rounding of the update (~1e-6 relative; tests/test_gpu_tiling.py).  Restrictions:
+ * predictions are one contiguous float32 array (n, I, I) indexed through d_lattice; I % 64 == 0, S % 4 == 0; the output
+ * window / accumulators are 16-byte aligned with pitches that are multiples of 4.  d_weights_f32 is the float32 copy of
+ * msr_blend_tile's weight table. */
+int msr_blend_tile_fast(const float* d_pred, const float* d_lohi, int n, const int32_t* d_lattice, int G,
+                        const float* d_weights_f32, int I, int S, int T, int add_half, float no_value, float* d_mean,
+                        float* d_std, uint8_t* d_good, int64_t pitch, int rows, int cols, void* stream);
+int msr_blend_accumulate_fast(const float* d_pred, const float* d_lohi, int k0, int n, const int32_t* d_lattice, int GY,
+                              int GX, int gy_lo, int gy_hi, int lattice_y0, const float* d_weights_f32, int I, int S,
+                              int add_half, float* d_wsum, float* d_mean, float* d_s, int64_t pitch, int acc_y0,
+                              int acc_rows, int cols, int row_lo, int row_hi, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * Raster container codec (host side, multi-threaded): what GDAL does for the reference when it reads band 1 of the input
  * GeoTIFFs (process_full_tiles.py:158-182) and writes 'COMPRESS=LZW', 'PREDICTOR=2' GeoTIFFs (:481-531).  The IFD / tags

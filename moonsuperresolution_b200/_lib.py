@@ -40,6 +40,9 @@ SIGNATURES: Dict[str, tuple] = {
     "msr_blend_accumulate": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _i64, _i, _i,
                                   _i, _i, _i, _vp]),
     "msr_blend_finalize": (_i, [_vp, _vp, _vp, _i64, _i, _i, _f, _vp, _vp, _vp, _i64, _vp]),
+    "msr_blend_tile_fast": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _i64, _i, _i, _vp]),
+    "msr_blend_accumulate_fast": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _i64,
+                                       _i, _i, _i, _i, _i, _vp]),
     "msr_tiff_lzw_bound": (_i64, [_i64]),
     "msr_tiff_encode_strips": (_i, [_vp, _i64, _i, _i, _i, _i, _i, _vp, _i64, _vp, _i]),
     "msr_tiff_decode_chunks": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _i, _i, _i64, _i, _i, _i, _vp, _i64, _i64, _i]),

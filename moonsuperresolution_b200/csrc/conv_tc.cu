@@ -893,6 +893,7 @@ struct ConvTC {
   int ctas;   // 1, or 2 = CTA pairs (cluster launch)
   int strip;  // 1 = strip mode (one 130-pixel input strip serves the three kx taps)
   int grid;
+  double alg_flops;   // what the profiler counts for this launch (algorithmic, not padded)
 };
 
 int conv_tc_plan_create(ConvTC** out, const ConvTCArgs& a) {
@@ -1024,6 +1025,7 @@ int conv_tc_plan_create(ConvTC** out, const ConvTCArgs& a) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (p->ctas == 2) p->grid = 2 * std::min((g.n_tiles_m / 2) * g.n_tiles_n, sms / 2);
   else p->grid = std::min(g.n_tiles_m * g.n_tiles_n, sms);
+  p->alg_flops = a.alg_flops > 0.0 ? a.alg_flops : 2.0 * (double)g.n * g.r * g.r * g.ncols * g.taps * g.cin;
   *out = p;
   return MSR_OK;
 }
@@ -1084,7 +1086,7 @@ static int launch_width(const ConvTC* p, cudaStream_t st) {
 
 int conv_tc_launch(const ConvTC* p, cudaStream_t st) {
   MSR_REQUIRE(p, "conv_tc_launch: null plan");
-  ProfileScope prof(MSR_PROF_CONV_TC, st, 2.0 * (double)p->g.n * p->g.r * p->g.r * p->g.ncols * p->g.taps * p->g.cin);
+  ProfileScope prof(MSR_PROF_CONV_TC, st, p->alg_flops);
   int rc;
   switch (p->ep.mode) {
     case TC_EPI_BIAS_F32: rc = launch_width<TC_EPI_BIAS_F32>(p, st); break;

@@ -734,6 +734,7 @@ int spade_bf16(Fwd& f, const SpadeW& s, const float* x, int x_shift, const float
   ConvTCArgs m;
   m.x = g->patches; m.w = s.conv_wt; m.n = n; m.r = r; m.cin = 64; m.ncols = kHidden; m.taps = 1; m.pad = 0;
   m.epilogue = TC_EPI_ACT_BF16; m.bias = s.conv_b; m.act = ACT_RELU; m.out_bf16 = g->a_bf16;
+  m.alg_flops = 2.0 * (double)n * r * r * kHidden * 18;          // 3x3 taps x 2 channels (the GEMM's K is padded to 64)
   if ((rc = tc_conv(f, m))) return rc;
   // gamma | beta convolution with the fused normalise - modulate - LeakyReLU epilogue (spade.py:19-24, blocks.py:30)
   ConvTCArgs a;
@@ -775,6 +776,7 @@ int forward_spade_bf16(Fwd& f, const float* source, const float* eps, float* out
     ConvTCArgs a;
     a.x = g->patches; a.w = g->enc1_wt; a.n = n; a.r = I / 2; a.cin = 64; a.ncols = kEnc[0]; a.taps = 1; a.pad = 0;
     a.epilogue = TC_EPI_ACT_BF16; a.act = ACT_LRELU; a.slope = 0.2f; a.out_bf16 = g->enc_b0; a.split_out = 1;
+    a.alg_flops = 2.0 * (double)n * (I / 2) * (I / 2) * kEnc[0] * 18;
     if ((rc = tc_conv(f, a))) return rc;
   }
   const __nv_bfloat16* ex = g->enc_b0;
@@ -854,6 +856,7 @@ int forward_spade_bf16(Fwd& f, const float* source, const float* eps, float* out
     ConvTCArgs a;
     a.x = g->a_bf16; a.w = g->out_wt; a.n = n; a.r = r / 2; a.cin = 128; a.ncols = 32;
     a.epilogue = TC_EPI_PHASE_F32; a.bias = g->out_b; a.y = out;
+    a.alg_flops = 2.0 * (double)n * I * I * 16 * 128;            // Conv2D(1, 4) on the I x I tensor: 16 taps x 128 channels
     if ((rc = tc_conv(f, a))) return rc;
   }
   g->acts["out"] = {out, (int64_t)n * I * I, 0};
@@ -946,6 +949,7 @@ int forward_pix2pix_bf16(Fwd& f, const float* source, float* out) {
     if (k == 0) { a.taps = 1; a.pad = 0; } else { a.taps = 16; a.stride = 2; a.pad = 1; }
     a.epilogue = TC_EPI_ACT_BF16; a.scale = g->pdt_scale[k]; a.bias = g->pdt_shift[k];   // null for block 1 (no BN)
     a.act = ACT_LRELU; a.slope = 0.3f; a.out_bf16 = y; a.out_pitch = pitch;
+    if (k == 0) a.alg_flops = 2.0 * (double)n * (s / 2) * (s / 2) * cout * 32;   // 4x4 taps x 2 channels (K padded to 64)
     if ((rc = tc_conv(f, a))) return rc;
     s /= 2;
     x = y; cin = cout; x_pitch = pitch;
@@ -958,6 +962,7 @@ int forward_pix2pix_bf16(Fwd& f, const float* source, float* out) {
     a.x = x; a.w = g->put_w[k]; a.n = n; a.r = s; a.cin = cin; a.x_pitch = x_pitch; a.ncols = 4 * cout;
     a.epilogue = TC_EPI_PHASE_ACT_BF16; a.scale = g->put_scale[k]; a.bias = g->put_shift[k]; a.act = ACT_RELU;
     a.phase_cout = cout; a.out_bf16 = g->catb[k]; a.out_pitch = pitch;
+    a.alg_flops = 2.0 * (double)n * (2 * s) * (2 * s) * 4 * cin * cout;   // ConvT 4x4 s2: k^2/s^2 = 4 taps per output pixel
     if ((rc = tc_conv(f, a))) return rc;
     s *= 2;
     x = g->catb[k]; cin = pitch; x_pitch = pitch;
@@ -966,6 +971,7 @@ int forward_pix2pix_bf16(Fwd& f, const float* source, float* out) {
   ConvTCArgs a;
   a.x = x; a.w = g->plt_w; a.n = n; a.r = s; a.cin = cin; a.x_pitch = x_pitch; a.ncols = 32;
   a.epilogue = TC_EPI_PHASE_F32; a.bias = g->pl_b; a.act = ACT_TANH; a.y = out;
+  a.alg_flops = 2.0 * (double)n * (2 * s) * (2 * s) * 4 * cin;
   if ((rc = tc_conv(f, a))) return rc;
   g->acts["out"] = {out, (int64_t)n * 256 * 256, 0};
   return MSR_OK;

@@ -92,6 +92,9 @@ struct ConvTCArgs {
   int out_pitch = 0;                 // channels per output pixel in memory (0 = dense)
   int phase_cout = 0;                // TC_EPI_PHASE_ACT_BF16: channels per phase
   __nv_bfloat16* out_bf16 = nullptr; // [n*r*r][C] (SPADE) / [n*r*r][ncols] (ACT)
+  double alg_flops = 0.0;            // algorithmic FLOPs of the layer this launch computes when they differ from
+                                     // 2*M*ncols*taps*cin (zero-padded K or N: 18 real taps of 64, 4 real columns of 32);
+                                     // 0 = the GEMM formula.  Only the profiler's roofline accounting reads it.
 };
 int conv_tc_plan_create(ConvTC** plan, const ConvTCArgs& a);
 int conv_tc_launch(const ConvTC* plan, cudaStream_t st);

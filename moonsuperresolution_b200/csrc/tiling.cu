@@ -352,8 +352,10 @@ __global__ void __launch_bounds__(256) blend_tile_kernel(const void* const* __re
                                                          int add_half, float nv, float* __restrict__ mean_out,
                                                          float* __restrict__ std_out, uint8_t* __restrict__ good_out,
                                                          int64_t pitch, int rows, int cols) {
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;
-  const int row = blockIdx.y;
+  // 1-D grid: block = (row, column block); gridDim.y would cap the rows at 65535 (a 70000-row band in dedup mode)
+  const int col_blocks = (cols + blockDim.x - 1) / blockDim.x;
+  const int row = blockIdx.x / col_blocks;
+  const int col = (blockIdx.x - row * col_blocks) * blockDim.x + threadIdx.x;
   if (col >= cols || row >= rows) return;
   const int off = I - S, p = I / 16;
   const int Y = row + off, X = col + off;  // accumulator coordinates (:386, :404)
@@ -422,9 +424,11 @@ __global__ void __launch_bounds__(256) blend_accumulate_kernel(
     int gy_lo, int gy_hi, int lat_y0, int k0, int n, const double* __restrict__ wtab, int I, int S, int add_half,
     float* __restrict__ wsum, float* __restrict__ mean, float* __restrict__ sacc, int64_t pitch, int acc_y0, int y_lo,
     int cols) {
-  const int X = blockIdx.x * blockDim.x + threadIdx.x;
+  const int col_blocks = (cols + blockDim.x - 1) / blockDim.x;
+  const int brow = blockIdx.x / col_blocks;
+  const int X = (blockIdx.x - brow * col_blocks) * blockDim.x + threadIdx.x;
   if (X >= cols) return;
-  const int Y = y_lo + blockIdx.y;  // canvas row
+  const int Y = y_lo + brow;  // canvas row
   const int p = I / 16;
   const int ry = Y - lat_y0;        // row relative to the band's first lattice row
   // lattice rows covering Y: gy*S + p <= ry < gy*S + I - p
@@ -503,8 +507,9 @@ __global__ void __launch_bounds__(256) blend_finalize_kernel(const float* __rest
                                                              int rows, int cols, float nv, float* __restrict__ mean_out,
                                                              float* __restrict__ std_out, uint8_t* __restrict__ good_out,
                                                              int64_t out_pitch, int vec_ok) {
-  const int c0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  const int r = blockIdx.y;
+  const int col_blocks = ((cols + 3) / 4 + blockDim.x - 1) / blockDim.x;
+  const int r = blockIdx.x / col_blocks;
+  const int c0 = ((blockIdx.x - r * col_blocks) * blockDim.x + threadIdx.x) * 4;
   if (c0 >= cols || r >= rows) return;
   const int64_t a = (int64_t)r * acc_pitch + c0, o = (int64_t)r * out_pitch + c0;
   if (vec_ok && c0 + 3 < cols) {
@@ -529,6 +534,138 @@ __global__ void __launch_bounds__(256) blend_finalize_kernel(const float* __rest
     mean_out[o + j] = mo;
     std_out[o + j] = so;
     good_out[o + j] = go;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K9f / K10f  "fast" blend (DSRConfig(blend="fast")): the same weighted update (:395-402) in float32 -- no float64
+// chain, no double-precision division -- so the kernels are bound by the prediction reads, not by the XU pipe.  One
+// thread owns FOUR adjacent pixels of a row: 128-bit loads of the predictions and of the (float32) weight table, 128-bit
+// stores.  Which patches reach which pixel (placement), their order and `good` are exactly those of the bit-exact
+// kernels; the values agree with them to float32 rounding of the update (~1e-6 relative).  Needs I, S, I/16 and the
+// window origin to be multiples of 4 (so the four pixels share their set of patches and the loads are aligned).
+// ------------------------------------------------------------------------------------------------------------------
+struct Blend4 {
+  float w[4], m[4], s[4];
+};
+
+__device__ __forceinline__ void blend4_update(Blend4& st, const float4 v, const float4 wt, float lo, float range,
+                                              float half) {
+  const float vv[4] = {v.x, v.y, v.z, v.w}, ww[4] = {wt.x, wt.y, wt.z, wt.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float d = fmaf(vv[j] + half, range, lo);       // :340, :396
+    st.w[j] += ww[j];                                    // :398
+    const float delta = d - st.m[j];
+    st.m[j] = fmaf(__fdividef(ww[j], st.w[j]), delta, st.m[j]);   // :401
+    const float dn = d - st.m[j];                        // :402 (mean_old aliases the updated mean)
+    st.s[j] = fmaf(ww[j] * dn, dn, st.s[j]);
+  }
+}
+
+__global__ void __launch_bounds__(256) blend_tile_fast_kernel(const float* __restrict__ pred,
+                                                              const float* __restrict__ lohi,
+                                                              const int32_t* __restrict__ lattice, int G,
+                                                              const float* __restrict__ wtab, int I, int S,
+                                                              int add_half, float nv, float* __restrict__ mean_out,
+                                                              float* __restrict__ std_out, uint8_t* __restrict__ good_out,
+                                                              int64_t pitch, int rows, int cols) {
+  const int quads = (cols + 3) >> 2;
+  const int qblocks = (quads + blockDim.x - 1) / blockDim.x;
+  const int row = blockIdx.x / qblocks;
+  const int col = ((blockIdx.x - row * qblocks) * blockDim.x + threadIdx.x) * 4;
+  if (col >= cols || row >= rows) return;
+  const int off = I - S, p = I / 16, wp = I - 2 * p;
+  const int Y = row + off, X = col + off;
+  const int64_t II = (int64_t)I * I;
+  const float half = add_half ? 0.5f : 0.f;
+  int gy0 = (Y - (I - p) + 1 <= 0) ? 0 : (Y - (I - p) + S) / S;
+  int gy1 = (Y - p < 0) ? -1 : min((Y - p) / S, G - 1);
+  int gx0 = (X - (I - p) + 1 <= 0) ? 0 : (X - (I - p) + S) / S;
+  int gx1 = (X - p < 0) ? -1 : min((X - p) / S, G - 1);
+  Blend4 st;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) st.w[j] = st.m[j] = st.s[j] = 0.f;
+  for (int gy = gy0; gy <= gy1; ++gy) {
+    const int ry = Y - gy * S;
+    for (int gx = gx0; gx <= gx1; ++gx) {
+      const int k = __ldg(lattice + gy * G + gx);
+      if (k < 0) continue;
+      const int rx = X - gx * S;
+      const float4 v = __ldcs(reinterpret_cast<const float4*>(pred + k * II + (int64_t)ry * I + rx));   // read once
+      const float4 wt = __ldg(reinterpret_cast<const float4*>(wtab + (int64_t)(ry - p) * wp + (rx - p)));
+      const float2 lh = __ldg(reinterpret_cast<const float2*>(lohi) + k);
+      blend4_update(st, v, wt, lh.x, lh.y - lh.x, half);
+    }
+  }
+  float mo[4], so[4];
+  uint8_t go[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) finalize_pixel(st.w[j], st.m[j], st.s[j], nv, mo[j], so[j], go[j]);
+  const int64_t o = (int64_t)row * pitch + col;
+  if (col + 3 < cols && (pitch & 3) == 0) {
+    __stcs(reinterpret_cast<float4*>(mean_out + o), make_float4(mo[0], mo[1], mo[2], mo[3]));
+    __stcs(reinterpret_cast<float4*>(std_out + o), make_float4(so[0], so[1], so[2], so[3]));
+    *reinterpret_cast<uchar4*>(good_out + o) = make_uchar4(go[0], go[1], go[2], go[3]);
+  } else {
+    for (int j = 0; j < 4 && col + j < cols; ++j) {
+      mean_out[o + j] = mo[j];
+      std_out[o + j] = so[j];
+      good_out[o + j] = go[j];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) blend_accumulate_fast_kernel(
+    const float* __restrict__ pred, const float* __restrict__ lohi, const int32_t* __restrict__ lattice, int GX,
+    int gy_lo, int gy_hi, int lat_y0, int k0, int n, const float* __restrict__ wtab, int I, int S, int add_half,
+    float* __restrict__ wsum, float* __restrict__ mean, float* __restrict__ sacc, int64_t pitch, int acc_y0, int y_lo,
+    int cols) {
+  const int quads = cols >> 2;   // cols % 4 == 0 (checked by the launcher)
+  const int qblocks = (quads + blockDim.x - 1) / blockDim.x;
+  const int brow = blockIdx.x / qblocks;
+  const int X = ((blockIdx.x - brow * qblocks) * blockDim.x + threadIdx.x) * 4;
+  if (X >= cols) return;
+  const int Y = y_lo + brow;
+  const int p = I / 16, wp = I - 2 * p;
+  const int ry = Y - lat_y0;
+  int gy0 = (ry - (I - p) + 1 <= 0) ? 0 : (ry - (I - p) + S) / S;
+  int gy1 = (ry - p < 0) ? -1 : (ry - p) / S;
+  gy0 = max(gy0, gy_lo);
+  gy1 = min(gy1, gy_hi);
+  int gx0 = (X - (I - p) + 1 <= 0) ? 0 : (X - (I - p) + S) / S;
+  int gx1 = (X - p < 0) ? -1 : min((X - p) / S, GX - 1);
+  if (gy1 < gy0 || gx1 < gx0) return;
+  const int64_t a = (int64_t)(Y - acc_y0) * pitch + X;
+  const int64_t II = (int64_t)I * I;
+  const float half = add_half ? 0.5f : 0.f;
+  Blend4 st;
+  bool loaded = false;
+  for (int gy = gy0; gy <= gy1; ++gy) {
+    const int py = ry - gy * S;
+    for (int gx = gx0; gx <= gx1; ++gx) {
+      const int k = __ldg(lattice + (int64_t)gy * GX + gx) - k0;
+      if (k < 0 || k >= n) continue;
+      if (!loaded) {
+        const float4 w4 = *reinterpret_cast<const float4*>(wsum + a);
+        const float4 m4 = *reinterpret_cast<const float4*>(mean + a);
+        const float4 s4 = *reinterpret_cast<const float4*>(sacc + a);
+        st.w[0] = w4.x; st.w[1] = w4.y; st.w[2] = w4.z; st.w[3] = w4.w;
+        st.m[0] = m4.x; st.m[1] = m4.y; st.m[2] = m4.z; st.m[3] = m4.w;
+        st.s[0] = s4.x; st.s[1] = s4.y; st.s[2] = s4.z; st.s[3] = s4.w;
+        loaded = true;
+      }
+      const int px = X - gx * S;
+      const float4 v = __ldcs(reinterpret_cast<const float4*>(pred + k * II + (int64_t)py * I + px));
+      const float4 wt = __ldg(reinterpret_cast<const float4*>(wtab + (int64_t)(py - p) * wp + (px - p)));
+      const float2 lh = __ldg(reinterpret_cast<const float2*>(lohi) + k);
+      blend4_update(st, v, wt, lh.x, lh.y - lh.x, half);
+    }
+  }
+  if (loaded) {
+    *reinterpret_cast<float4*>(wsum + a) = make_float4(st.w[0], st.w[1], st.w[2], st.w[3]);
+    *reinterpret_cast<float4*>(mean + a) = make_float4(st.m[0], st.m[1], st.m[2], st.m[3]);
+    *reinterpret_cast<float4*>(sacc + a) = make_float4(st.s[0], st.s[1], st.s[2], st.s[3]);
   }
 }
 
@@ -607,7 +744,8 @@ extern "C" int msr_blend_tile(const void* const* d_patch_ptr, const uint8_t* d_p
   if (rows == 0 || cols == 0) return MSR_OK;
   ProfileScope prof(MSR_PROF_BLEND, (cudaStream_t)stream,
                     (double)n * (I - 2 * (I / 16)) * (I - 2 * (I / 16)) * 4.0 + (double)rows * cols * 9.0);
-  blend_tile_kernel<<<dim3(ceil_div(cols, 256), rows), 256, 0, (cudaStream_t)stream>>>(
+  MSR_REQUIRE((int64_t)ceil_div(cols, 256) * rows < (1ll << 31), "msr_blend_tile: window too large for one launch");
+  blend_tile_kernel<<<dim3((unsigned)(ceil_div(cols, 256) * rows)), 256, 0, (cudaStream_t)stream>>>(
       d_patch_ptr, d_patch_f64, d_patch_lohi, d_patch_xy, n, d_lattice, G, d_weights, I, S, T, add_half, no_value,
       d_mean, d_std, d_good, pitch, rows, cols);
   count_launch();
@@ -632,7 +770,8 @@ extern "C" int msr_blend_accumulate(const float* d_pred, const float* d_lohi, in
   if (y1 <= y0) return MSR_OK;
   const int wp = I - 2 * p;
   ProfileScope prof(MSR_PROF_BLEND, (cudaStream_t)stream, (double)n * wp * wp * (4.0 + 24.0));
-  blend_accumulate_kernel<<<dim3(ceil_div(cols, 256), y1 - y0), 256, 0, (cudaStream_t)stream>>>(
+  MSR_REQUIRE((int64_t)ceil_div(cols, 256) * (y1 - y0) < (1ll << 31), "msr_blend_accumulate: window too large");
+  blend_accumulate_kernel<<<dim3((unsigned)(ceil_div(cols, 256) * (y1 - y0))), 256, 0, (cudaStream_t)stream>>>(
       d_pred, d_lohi, d_lattice, GX, gy_lo, gy_hi, lattice_y0, k0, n, d_weights, I, S, add_half, d_wsum, d_mean, d_s,
       pitch, acc_y0, y0, cols);
   count_launch();
@@ -651,8 +790,68 @@ extern "C" int msr_blend_finalize(const float* d_wsum, const float* d_mean_acc, 
   auto al = [](const void* p, int a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; };
   const int vec_ok = al(d_wsum, 16) && al(d_mean_acc, 16) && al(d_s, 16) && al(d_mean, 16) && al(d_std, 16) &&
                      al(d_good, 4) && (acc_pitch % 4 == 0) && (out_pitch % 4 == 0);
-  blend_finalize_kernel<<<dim3(ceil_div(ceil_div(cols, 4), 256), rows), 256, 0, (cudaStream_t)stream>>>(
+  MSR_REQUIRE((int64_t)ceil_div(ceil_div(cols, 4), 256) * rows < (1ll << 31), "msr_blend_finalize: window too large");
+  blend_finalize_kernel<<<dim3((unsigned)(ceil_div(ceil_div(cols, 4), 256) * rows)), 256, 0, (cudaStream_t)stream>>>(
       d_wsum, d_mean_acc, d_s, acc_pitch, rows, cols, no_value, d_mean, d_std, d_good, out_pitch, vec_ok);
+  count_launch();
+  MSR_LAUNCH_CHECK();
+  return MSR_OK;
+}
+
+static bool fast_blend_geometry_ok(int I, int S) { return I % 64 == 0 && S % 4 == 0 && S > 0 && S <= I; }
+
+extern "C" int msr_blend_tile_fast(const float* d_pred, const float* d_lohi, int n, const int32_t* d_lattice, int G,
+                                   const float* d_weights_f32, int I, int S, int T, int add_half, float no_value,
+                                   float* d_mean, float* d_std, uint8_t* d_good, int64_t pitch, int rows, int cols,
+                                   void* stream) {
+  MSR_REQUIRE(d_weights_f32 && d_mean && d_std && d_good && d_lattice && G > 0, "msr_blend_tile_fast: null pointer");
+  MSR_REQUIRE(n == 0 || (d_pred && d_lohi), "msr_blend_tile_fast: null patch tables");
+  MSR_REQUIRE(fast_blend_geometry_ok(I, S), "msr_blend_tile_fast: needs I % 64 == 0 and S % 4 == 0");
+  MSR_REQUIRE(rows >= 0 && cols >= 0 && rows <= T && cols <= T && pitch >= cols, "msr_blend_tile_fast: bad output window");
+  MSR_REQUIRE(((reinterpret_cast<uintptr_t>(d_pred) | reinterpret_cast<uintptr_t>(d_weights_f32) |
+                reinterpret_cast<uintptr_t>(d_mean) | reinterpret_cast<uintptr_t>(d_std)) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(d_good) & 3) == 0 && (pitch & 3) == 0,
+              "msr_blend_tile_fast: predictions, weights and the output window must be 16-byte aligned (W % 4 == 0)");
+  if (rows == 0 || cols == 0) return MSR_OK;
+  const int wp = I - 2 * (I / 16);
+  // algorithmic bytes: the centre of every prediction read once + 9 bytes written per output pixel
+  ProfileScope prof(MSR_PROF_BLEND, (cudaStream_t)stream, (double)n * wp * wp * 4.0 + (double)rows * cols * 9.0);
+  const int quads = (cols + 3) / 4;
+  MSR_REQUIRE((int64_t)ceil_div(quads, 256) * rows < (1ll << 31), "msr_blend_tile_fast: window too large");
+  blend_tile_fast_kernel<<<dim3((unsigned)(ceil_div(quads, 256) * rows)), 256, 0, (cudaStream_t)stream>>>(
+      d_pred, d_lohi, d_lattice, G, d_weights_f32, I, S, add_half, no_value, d_mean, d_std, d_good, pitch, rows, cols);
+  count_launch();
+  MSR_LAUNCH_CHECK();
+  return MSR_OK;
+}
+
+extern "C" int msr_blend_accumulate_fast(const float* d_pred, const float* d_lohi, int k0, int n,
+                                         const int32_t* d_lattice, int GY, int GX, int gy_lo, int gy_hi, int lattice_y0,
+                                         const float* d_weights_f32, int I, int S, int add_half, float* d_wsum,
+                                         float* d_mean, float* d_s, int64_t pitch, int acc_y0, int acc_rows, int cols,
+                                         int row_lo, int row_hi, void* stream) {
+  MSR_REQUIRE(d_pred && d_lohi && d_lattice && d_weights_f32 && d_wsum && d_mean && d_s,
+              "msr_blend_accumulate_fast: null pointer");
+  MSR_REQUIRE(fast_blend_geometry_ok(I, S), "msr_blend_accumulate_fast: needs I % 64 == 0 and S % 4 == 0");
+  MSR_REQUIRE(GY > 0 && GX > 0 && gy_lo >= 0 && gy_hi < GY && n >= 0 && k0 >= 0, "msr_blend_accumulate_fast: bad lattice range");
+  MSR_REQUIRE(acc_rows > 0 && cols > 0 && pitch >= cols && cols % 4 == 0 && pitch % 4 == 0,
+              "msr_blend_accumulate_fast: accumulator width and pitch must be multiples of 4");
+  MSR_REQUIRE(((reinterpret_cast<uintptr_t>(d_pred) | reinterpret_cast<uintptr_t>(d_weights_f32) |
+                reinterpret_cast<uintptr_t>(d_wsum) | reinterpret_cast<uintptr_t>(d_mean) |
+                reinterpret_cast<uintptr_t>(d_s)) & 15) == 0, "msr_blend_accumulate_fast: pointers must be 16-byte aligned");
+  if (n == 0 || gy_hi < gy_lo) return MSR_OK;
+  const int p = I / 16;
+  int y0 = lattice_y0 + gy_lo * S + p, y1 = lattice_y0 + gy_hi * S + I - p;
+  y0 = std::max(std::max(y0, row_lo), acc_y0);
+  y1 = std::min(std::min(y1, row_hi), acc_y0 + acc_rows);
+  if (y1 <= y0) return MSR_OK;
+  const int wp = I - 2 * p;
+  ProfileScope prof(MSR_PROF_BLEND, (cudaStream_t)stream, (double)n * wp * wp * (4.0 + 24.0));
+  const int quads = cols / 4;
+  MSR_REQUIRE((int64_t)ceil_div(quads, 256) * (y1 - y0) < (1ll << 31), "msr_blend_accumulate_fast: window too large");
+  blend_accumulate_fast_kernel<<<dim3((unsigned)(ceil_div(quads, 256) * (y1 - y0))), 256, 0, (cudaStream_t)stream>>>(
+      d_pred, d_lohi, d_lattice, GX, gy_lo, gy_hi, lattice_y0, k0, n, d_weights_f32, I, S, add_half, d_wsum, d_mean, d_s,
+      pitch, acc_y0, y0, cols);
   count_launch();
   MSR_LAUNCH_CHECK();
   return MSR_OK;

@@ -60,6 +60,9 @@ class DSRConfig:
                                     # times (new sampler noise each time) and all generations are blended
     mode: str = "faithful"          # "faithful": tile by tile like the reference (halo patches recomputed per tile);
                                     # "dedup": every position of the global patch lattice generated once
+    blend: str = "exact"            # "exact": rebuildTile's arithmetic bit for bit (float64 intermediates, :395-402);
+                                    # "fast": same placement / order / good mask, float32 update, 128-bit accesses --
+                                    # HBM-bound, values within float32 rounding (~1e-6 relative) of "exact"
 
 
 def parse_args(argv=None) -> DSRConfig:
@@ -92,13 +95,15 @@ def parse_args(argv=None) -> DSRConfig:
                         help="Generations per patch position (N = samples_per_patch * (image_size / stride)^2).")
     parser.add_argument("--mode", type=str, default="faithful", choices=["faithful", "dedup"],
                         help="faithful: tile by tile like the reference; dedup: every patch position generated once.")
+    parser.add_argument("--blend", type=str, default="exact", choices=["exact", "fast"],
+                        help="exact: the reference's blend arithmetic bit for bit; fast: float32 update, HBM-bound.")
     args, _unknown = parser.parse_known_args(argv)
     return DSRConfig(source_folder_path=args.source_folder_path, map_name=args.map_name, save_path=args.save_path,
                      ortho_image_name=args.ortho_image_name, dem_name=args.dem_name, model_path=args.model_path,
                      image_size=args.image_size, stride=args.stride, batch_size=args.batch_size,
                      tile_size=args.tile_size, no_value=args.no_value, upsample_factor=args.upsample_factor,
                      save_tiles=args.save_tiles, groups_per_call=args.groups_per_call, seed=args.seed, mode=args.mode,
-                     preprocess=not args.no_preprocess, samples_per_patch=args.samples_per_patch)
+                     preprocess=not args.no_preprocess, samples_per_patch=args.samples_per_patch, blend=args.blend)
 
 
 def main(argv=None) -> None:
@@ -152,11 +157,20 @@ class DEMSuperResolution:
             raise ValueError("samples_per_patch must be >= 1")
         if self.mode not in ("faithful", "dedup"):
             raise ValueError("mode must be 'faithful' or 'dedup'")
+        self.blend = str(getattr(config, "blend", "exact"))
+        if self.blend not in ("exact", "fast"):
+            raise ValueError("blend must be 'exact' or 'fast'")
         if self.mode == "dedup" and self.save_tiles:
             raise ValueError("save_tiles needs mode='faithful': dedup mode has no per-tile accumulators to save")
         self._lib = _lib.lib()
         torch = _torch()
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        if self.device.type != "cuda":
+            raise _lib.MoonSRError("DEMSuperResolution runs only on a CUDA device")
+        if self.device.index is not None and self.device.index != torch.cuda.current_device():
+            # the C ABI launches on the CURRENT device's stream: pointers of another device would fault
+            raise ValueError(f"device {self.device} is not the current CUDA device (cuda:{torch.cuda.current_device()}): "
+                             "call torch.cuda.set_device first (one process per GPU)")
         self.dem = self.img = None
         self._row_offset = 0
         self.geo_transform = self.geo_projection = None
@@ -165,6 +179,7 @@ class DEMSuperResolution:
         self.model_launches = 0
         self.slots_executed = 0
         self._weights_dev = None
+        self._weights_dev_f32 = None
         self._host_out = None
 
     # ---------------------------------------------------------------------------------------------------------------
@@ -453,12 +468,31 @@ class DEMSuperResolution:
             self._weights_dev = torch.from_numpy(w).to(self.device)
         return self._weights_dev
 
+    def _blend_weights_f32(self):
+        if self._weights_dev_f32 is None:
+            self._weights_dev_f32 = self._blend_weights().to(_torch().float32).contiguous()
+        return self._weights_dev_f32
+
+    def _fast_blend_ok(self) -> bool:
+        """The float32 / 128-bit blend kernels need 4-pixel groups that share their patches and aligned rows."""
+        return (self.blend == "fast" and self.image_size % 64 == 0 and self.stride % 4 == 0 and
+                self.plan is not None and self.plan.width % 4 == 0)
+
     # ---------------------------------------------------------------------------------------------------------------
     # blend
     # ---------------------------------------------------------------------------------------------------------------
-    def _blend(self, ptrs, f64flags, lohi, pxy, n, lattice, add_half, mean, std, good, pitch, rows, cols) -> None:
+    def _blend(self, ptrs, f64flags, lohi, pxy, n, lattice, add_half, mean, std, good, pitch, rows, cols,
+               pred=None) -> None:
         plan_i, plan_s, plan_t = self.image_size, self.stride, self.tile_size
         g = -(-(plan_t + plan_i - plan_s) // plan_s)
+        if (pred is not None and lattice is not None and f64flags is None and self._fast_blend_ok() and pitch % 4 == 0
+                and mean % 16 == 0 and std % 16 == 0 and good % 4 == 0):
+            _lib.check(self._lib.msr_blend_tile_fast(pred.data_ptr(), _lib.ptr(lohi), n, _lib.ptr(lattice), g,
+                                                     self._blend_weights_f32().data_ptr(), plan_i, plan_s, plan_t,
+                                                     int(add_half), float(np.float32(self.no_value)), mean, std, good,
+                                                     pitch, rows, cols, _lib.stream_ptr()), "msr_blend_tile_fast")
+            self.launches += 1
+            return
         _lib.check(self._lib.msr_blend_tile(_lib.ptr(ptrs), _lib.ptr(f64flags), _lib.ptr(lohi), _lib.ptr(pxy), n,
                                             _lib.ptr(lattice), g, self._blend_weights().data_ptr(), plan_i, plan_s,
                                             plan_t, int(add_half), float(np.float32(self.no_value)), mean, std, good,
@@ -594,16 +628,18 @@ class DEMSuperResolution:
                 self.model_launches += self.model.last_launch_count
             ptrs = pred.data_ptr() + torch.arange(n_valid, dtype=torch.int64, device=dev) * (i * i * 4)
             flags, add_half, keep = None, 1, [pred]
+            pred_base = pred
         else:
             ptrs, flags, keep = self._run_host_model(d_slot_xy, slots, n_valid, minmax)
             add_half = 0
+            pred_base = None
         lohi = minmax[:n_valid, 2:4].contiguous()
         self.slots_executed += slots
         self._blend(ptrs, flags, lohi, d_key_xy, n_valid, d_lattice, add_half, mean_p, std_p, good_p, plan.width, rows,
-                    cols)
+                    cols, pred=pred_base)
         if tile_bufs:
             self._blend(ptrs, flags, lohi, d_key_xy, n_valid, d_lattice, add_half, tile_bufs[0].data_ptr(),
-                        tile_bufs[1].data_ptr(), tile_bufs[2].data_ptr(), t, t, t)
+                        tile_bufs[1].data_ptr(), tile_bufs[2].data_ptr(), t, t, t, pred=pred_base)
             self._save_tile_bufs(tile_bufs, px, py)
         del keep
 
@@ -672,6 +708,17 @@ class DEMSuperResolution:
             band = self._dband
             target = (self._acc, self._d_lattice, band.j1 - band.j0, band.gx, band.j0 * plan.stride, self._c0)
         acc, d_lattice, gy, gx, lattice_y0, acc_y0 = target
+        if (self._fast_blend_ok() and int(acc.shape[2]) % 4 == 0 and pred.dtype == _torch().float32
+                and pred.data_ptr() % 16 == 0):
+            _lib.check(self._lib.msr_blend_accumulate_fast(pred.data_ptr(), lohi.data_ptr(), k0, n, d_lattice.data_ptr(),
+                                                           gy, gx, gy_lo, gy_hi, lattice_y0,
+                                                           self._blend_weights_f32().data_ptr(), plan.image_size,
+                                                           plan.stride, int(add_half), acc[0].data_ptr(),
+                                                           acc[1].data_ptr(), acc[2].data_ptr(), int(acc.shape[2]),
+                                                           acc_y0, int(acc.shape[1]), int(acc.shape[2]), row_lo, row_hi,
+                                                           _lib.stream_ptr()), "msr_blend_accumulate_fast")
+            self.launches += 1
+            return
         _lib.check(self._lib.msr_blend_accumulate(pred.data_ptr(), lohi.data_ptr(), k0, n, d_lattice.data_ptr(), gy, gx,
                                                   gy_lo, gy_hi, lattice_y0, self._blend_weights().data_ptr(),
                                                   plan.image_size, plan.stride, int(add_half), acc[0].data_ptr(),
@@ -935,8 +982,12 @@ class DEMSuperResolution:
             raise ValueError("Data is of incorrect shape. The array must be 2-dimensional at least.")
         elif len(data.shape) > 3:
             raise ValueError("Data is of incorrect shape")
-        geotiff.write(os.path.join(self.save_path, self.map_name + "_" + name + ".tiff"), data, geo=self.geo_transform
-                      if isinstance(self.geo_transform, dict) else None, nodata=self.no_value)
+        geo = self.geo_transform
+        if geo is not None and not isinstance(geo, dict):
+            # the reference's types (:177-178): GDAL's 6-number affine GeoTransform and a WKT projection string
+            geo = geotiff.geo_tags_from_gdal(geo, self.geo_projection)
+        geotiff.write(os.path.join(self.save_path, self.map_name + "_" + name + ".tiff"), data, geo=geo,
+                      nodata=self.no_value)
 
     def results(self):
         """(mean f32, std f32, good u8) of this rank's band as numpy arrays plus the band's first raster row.  The arrays
@@ -1013,9 +1064,11 @@ class DEMSuperResolution:
         c1 = min(plan.canvas_h, max(yy for _, yy in tiles) + plan.tile_size + 2 * plan.off)
         return max(0, c0 - plan.off), min(height, c1 - plan.off)
 
-    def run(self, dem, img, row_offset: int = 0, full_height: Optional[int] = None):
-        """In-memory processMap: rasters in, (mean, std, good) of this rank's band out (numpy)."""
+    def run(self, dem, img, row_offset: int = 0, full_height: Optional[int] = None, copy: bool = True):
+        """In-memory processMap: rasters in, (mean, std, good) of this rank's band out (numpy).  ``copy=False`` hands
+        out views of the engine's pinned staging buffers (valid until the next results() / run() on this engine)."""
         self.setRasters(dem, img, row_offset=row_offset, full_height=full_height)
         self.padInputs()
         self.processTiles()
-        return self.results()[:3]
+        out = self.results()[:3]
+        return tuple(np.array(a) for a in out) if copy else out

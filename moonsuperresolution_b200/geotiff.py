@@ -33,11 +33,44 @@ def _threads() -> int:
     return max(1, len(os.sched_getaffinity(0)))
 
 
+def geo_tags_from_gdal(geo_transform, projection_wkt: Optional[str] = None) -> Dict[int, Tuple[int, int, bytes]]:
+    """GeoTIFF tags for the geo-referencing types the reference holds (process_full_tiles.py:177-178): GDAL's affine
+    ``GetGeoTransform()`` 6-tuple (x0, dx, rx, y0, ry, dy) and the ``GetProjection()`` WKT string.  North-up rasters get
+    ModelPixelScale + ModelTiepoint, rotated ones ModelTransformation; the WKT travels as the GTCitation key of a
+    GeoKeyDirectory (model type from the WKT's root keyword, RasterPixelIsArea) -- no EPSG lookup is attempted."""
+    gt = [float(v) for v in geo_transform]
+    if len(gt) != 6:
+        raise ValueError("geo_transform must be GDAL's 6-number affine transform (or the tag dict geotiff.read returns)")
+    x0, dx, rx, y0, ry, dy = gt
+    tags: Dict[int, Tuple[int, int, bytes]] = {}
+    if rx == 0.0 and ry == 0.0:
+        tags[33550] = (12, 3, struct.pack("<3d", dx, -dy, 0.0))
+        tags[33922] = (12, 6, struct.pack("<6d", 0.0, 0.0, 0.0, x0, y0, 0.0))
+    else:
+        tags[34264] = (12, 16, struct.pack("<16d", dx, rx, 0.0, x0, ry, dy, 0.0, y0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0,
+                                           1.0))
+    keys = [(1025, 0, 1, 1)]                                   # GTRasterTypeGeoKey = RasterPixelIsArea
+    ascii_params = b""
+    if projection_wkt:
+        wkt = str(projection_wkt)
+        model = 1 if wkt.lstrip().upper().startswith("PROJCS") else 2 if wkt.lstrip().upper().startswith("GEOGCS") else 32767
+        keys.insert(0, (1024, 0, 1, model))                    # GTModelTypeGeoKey
+        ascii_params = wkt.encode("ascii", "replace") + b"|"
+        keys.append((1026, 34737, len(ascii_params), 0))       # GTCitationGeoKey -> GeoAsciiParams
+    keys.sort()
+    directory = [1, 1, 0, len(keys)] + [v for k in keys for v in k]
+    tags[34735] = (3, len(directory), struct.pack("<%dH" % len(directory), *directory))
+    if ascii_params:
+        tags[34737] = (2, len(ascii_params) + 1, ascii_params + b"\0")
+    return tags
+
+
 def write(path: str, data: np.ndarray, geo: Optional[Dict[int, Tuple[int, int, bytes]]] = None,
-          nodata: Optional[float] = None, rows_per_strip: int = 64, compress: str = "lzw", predictor: int = 2) -> None:
-    """Writes a 2-D array as a single-band stripped TIFF (BigTIFF when it would not fit in 4 GiB).  Defaults follow the
-    reference's GDAL options ``COMPRESS=LZW, PREDICTOR=2`` (process_full_tiles.py:521); ``compress="none"`` writes raw
-    strips."""
+          nodata: Optional[float] = None, rows_per_strip: int = 64, compress: str = "lzw", predictor: int = 2,
+          bigtiff: Optional[bool] = None) -> None:
+    """Writes a 2-D array as a single-band stripped TIFF (BigTIFF when it would not fit in 4 GiB, or when ``bigtiff`` is
+    True -- GDAL's BIGTIFF=YES).  Defaults follow the reference's GDAL options ``COMPRESS=LZW, PREDICTOR=2``
+    (process_full_tiles.py:521); ``compress="none"`` writes raw strips."""
     a = np.ascontiguousarray(data)
     if a.ndim == 3 and a.shape[2] == 1:
         a = np.ascontiguousarray(a[:, :, 0])
@@ -63,7 +96,9 @@ def write(path: str, data: np.ndarray, geo: Optional[Dict[int, Tuple[int, int, b
                                           predictor, packed.ctypes.data, slot, sizes.ctypes.data, _threads()),
                "msr_tiff_encode_strips")
     counts = [int(c) for c in sizes]
-    big = sum(counts) + 65536 + 16 * n_strips >= (1 << 32)
+    big = sum(counts) + 65536 + 16 * n_strips >= (1 << 32) if bigtiff is None else bool(bigtiff)
+    if not big and sum(counts) + 65536 + 16 * n_strips >= (1 << 32):
+        raise ValueError("raster does not fit a classic TIFF: pass bigtiff=None (auto) or True")
     off_t, off_code = ("<Q", 16) if big else ("<I", 4)
     osz = 8 if big else 4
     header = 16 if big else 8

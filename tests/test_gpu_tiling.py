@@ -277,3 +277,70 @@ def test_save_tiles_and_geotiff_layout(msr, tmp_path):
     tile, _ = geotiff.read(str(tmp_path / "out" / "tile_128_0" / "tile_128_0_mean.tif"))
     assert tile.shape == (case["T"], case["T"])
     np.testing.assert_array_equal(tile, ref[0][:case["T"], 128:128 + case["T"]])
+
+
+@pytest.mark.parametrize("mode", ["faithful", "dedup"])
+def test_fast_blend_matches_exact_blend(msr, mode):
+    """DSRConfig(blend="fast"): float32 update, four pixels per thread, 128-bit accesses (msr_blend_tile_fast /
+    msr_blend_accumulate_fast).  Same predictions (the generator is deterministic), same placement: `good` must be
+    identical and mean / std within float32 rounding of the bit-exact kernels (process_full_tiles.py:395-413)."""
+    from moonsuperresolution_b200 import weights as W
+    i, s, b, t = 64, 16, 4, 256
+    rng = np.random.default_rng(3)
+    h, w_ = 300, 404
+    dem = np.cumsum(np.cumsum(rng.standard_normal((h, w_)), 0), 1).astype(np.float32)
+    img = rng.uniform(1, 255, (h, w_)).astype(np.float32)
+    dem[100:104, 200:207] = -32768.0
+    weights = W.random_init("cnn", i, seed=2, perturb_affine=True)
+    model = msr.CNNSpade(i, b, precision="fp32", weights=weights, max_groups=4)
+    out = {}
+    for blend in ("exact", "fast"):
+        cfg = msr.DSRConfig(image_size=i, stride=s, batch_size=b, tile_size=t, mode=mode, blend=blend)
+        eng = msr.DEMSuperResolution(cfg, model=model)
+        eng.setRasters(dem, img)
+        eng.padInputs()
+        assert eng._fast_blend_ok() == (blend == "fast")
+        eng.processTiles()
+        out[blend] = tuple(np.array(a) for a in eng.results()[:3])
+    (me, se, ge), (mf, sf, gf) = out["exact"], out["fast"]
+    np.testing.assert_array_equal(ge, gf)
+    g = ge.astype(bool)
+    assert g.sum() > 10000 and se[g].max() > 0
+    scale = float(dem[dem > -32768].max() - dem[dem > -32768].min())
+    e_mean = np.abs(mf[g] - me[g]).max() / scale
+    e_std = np.abs(sf[g] - se[g]).max() / scale
+    print(f"fast blend vs exact ({mode}): mean {e_mean:.3g}, std {e_std:.3g} of the DEM range")
+    assert e_mean <= 2e-6 and e_std <= 2e-6
+    assert (mf[~g] == -32768.0).all() and (sf[~g] == -32768.0).all()
+
+
+def test_bands_taller_than_65535_rows(msr, torch):
+    """A single-GPU dedup run of the reference's largest raster (70000 rows) finalises its whole band in one launch:
+    the blend kernels index rows through a flattened 1-D grid (gridDim.y stops at 65535)."""
+    i, s, b, t = 64, 32, 16, 1024
+    h, w_ = 66000, 96
+    y = np.arange(h, dtype=np.float32)[:, None]
+    x = np.arange(w_, dtype=np.float32)[None, :]
+    dem = (np.sin(y / 37.0) * 50.0 + x * 0.25 + (y % 13) * 0.5).astype(np.float32)
+    img = (1.0 + (x * 7 + y * 3) % 250).astype(np.float32)
+    res = {}
+    for mode in ("faithful", "dedup"):
+        cfg = msr.DSRConfig(image_size=i, stride=s, batch_size=b, tile_size=t, mode=mode)
+        eng = msr.DEMSuperResolution(cfg, model=msr.IdentityModel(i, b))
+        res[mode] = eng.run(dem, img)
+    for a, r in zip(res["dedup"], res["faithful"]):
+        np.testing.assert_array_equal(a, r)
+    good = res["dedup"][2].astype(bool)
+    assert good[65990, 40] and good.sum() > 60000 * 80
+    # the finalize entry point on its own, rows > 65535
+    rows, cols = 70000, 8
+    acc = torch.rand((3, rows, cols), device="cuda") + 0.5
+    mean = torch.empty((rows, cols), device="cuda")
+    std = torch.empty_like(mean)
+    gd = torch.empty((rows, cols), dtype=torch.uint8, device="cuda")
+    msr._lib.check(msr._lib.lib().msr_blend_finalize(acc[0].data_ptr(), acc[1].data_ptr(), acc[2].data_ptr(), cols, rows,
+                                                     cols, -32768.0, mean.data_ptr(), std.data_ptr(), gd.data_ptr(), cols,
+                                                     msr._lib.stream_ptr()), "msr_blend_finalize")
+    torch.cuda.synchronize()
+    assert torch.equal(mean, acc[1]) and bool(gd.all())
+    torch.testing.assert_close(std, torch.sqrt(acc[2] / acc[0]), rtol=1e-6, atol=0)
