@@ -64,6 +64,10 @@ struct Geometry {
   int strip_base_offset;     // STRIP: 1 = put the start row's swizzle phase into the descriptor base-offset field
   int pref_boxes;            // > 0: L2-prefetch the next tile's input window with this many channel boxes (map_p)
   int pref_chan;             // channels per prefetch box
+  int ksplit;                // > 1 (1x1 GEMMs with a long K, e.g. the dense layers): the channel blocks of every part are cut
+                             // into ksplit ranges; range ks is a separate work unit that writes its fp32 partial sums to
+                             // y + ks * M * ncols.  n_tiles_n counts (N tile, range) pairs: nt = unit % n_tiles_n_real.
+  int n_tiles_n_real;
 };
 
 struct EpiParams {
@@ -324,7 +328,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   const int total_tiles = (g.n_tiles_m / CTAS) * g.n_tiles_n;
   const int chunks_per_part = g.cin / kBlockK;
   const int k_chunks_per_tap = (g.split ? 3 : 1) * chunks_per_part;
-  const int k_chunks = STRIP ? 3 * chunks_per_part : g.taps * k_chunks_per_tap;   // pipeline stages per tile
+  const int k_chunks = (STRIP ? 3 * chunks_per_part : g.taps * k_chunks_per_tap) / g.ksplit;   // pipeline stages per tile
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::kStages; ++s) {
@@ -377,8 +381,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     b0 = tb * g.NB;
     h0 = th * g.TH;
     w0 = tw * g.TW;
-    n0 = it.nt * BN;
+    n0 = (g.ksplit > 1 ? it.nt % g.n_tiles_n_real : it.nt) * BN;
   };
+  auto split_of = [&](const TileIter& it) { return g.ksplit > 1 ? it.nt / g.n_tiles_n_real : 0; };
 
   if (warp == kEpiWarps) {
     // ===================== TMA producer =====================
@@ -436,7 +441,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             }
           }
         } else {
-          int kcol = 0;   // K coordinate of the weight tile
+          // split-K work unit: channel blocks [cb_lo, cb_hi) of every part
+          const int cb_per = chunks_per_part / g.ksplit;
+          const int cb_lo = split_of(it) * cb_per, cb_hi = cb_lo + cb_per;
           for (int ky = 0; ky < ksz; ++ky) {
             const int ch = h0 * g.stride + ky - g.pad;
             for (int kx = 0; kx < ksz; ++kx) {
@@ -444,7 +451,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
               for (int part = 0; part < n_parts; ++part) {
                 // split-bf16: parts (x_hi, x_hi, x_lo) of A pair with (w_hi, w_lo, w_hi) of B
                 const int a_base = (part == 2) ? g.cin : 0;
-                for (int cb = 0; cb < chunks_per_part; ++cb, kcol += kBlockK) {
+                int kcol = (((ky * ksz + kx) * n_parts + part) * chunks_per_part + cb_lo) * kBlockK;   // K coordinate of B
+                for (int cb = cb_lo; cb < cb_hi; ++cb, kcol += kBlockK) {
                   t_empty += mbar_wait_timed(empty_bar(stage), phase ^ 1u, timed);
                   const uint32_t sa = smem_base + stage * C::kStageBytes;
                   if constexpr (CTAS == 2) {
@@ -597,7 +605,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 for (int q = 0; q < 8; ++q) o[j + q] += rr[q];
               }
             }
-            float* dst = ep.y + m * g.ncols + col;
+            // split-K work units write their partial sums to plane `ks` of y (the caller reduces the planes)
+            const int64_t plane = g.ksplit > 1 ? (int64_t)split_of(it) * ((int64_t)g.n * g.r * g.r) * g.ncols : 0;
+            float* dst = ep.y + plane + m * g.ncols + col;
 #pragma unroll
             for (int j = 0; j < 32; j += 8)
               st_global_v8(dst + j, __float_as_uint(o[j]), __float_as_uint(o[j + 1]), __float_as_uint(o[j + 2]),
@@ -925,12 +935,24 @@ int conv_tc_plan_create(ConvTC** out, const ConvTCArgs& a) {
   while ((1 << g.lh) < g.tiles_h) ++g.lh;
   p->bn = (a.ncols % 256 == 0) ? 256 : (a.ncols % 128 == 0) ? 128 : (a.ncols % 64 == 0) ? 64 : 32;
   if (a.epilogue == TC_EPI_PHASE_F32) p->bn = 32;
-  g.n_tiles_n = a.ncols / p->bn;
+  g.n_tiles_n_real = a.ncols / p->bn;
+  g.ksplit = a.ksplit > 1 ? a.ksplit : 1;
+  g.n_tiles_n = g.n_tiles_n_real * g.ksplit;
+  if (g.ksplit > 1) {
+    const char* why = nullptr;
+    if (a.taps != 1 || a.epilogue != TC_EPI_BIAS_F32) why = "conv_tc: split-K needs a 1x1 GEMM with the fp32 epilogue";
+    else if ((a.cin / 64) % g.ksplit != 0) why = "conv_tc: ksplit must divide cin / 64";
+    else if (a.bias || a.res || a.stat_pairs) why = "conv_tc: split-K planes carry no bias / residual / statistics";
+    if (why) {
+      delete p;
+      return fail(MSR_E_INVALID, why);
+    }
+  }
   // CTA pairs when the layer is large enough to fill the chip with 256-row tiles
   // (and the K loop long enough to amortise the cross-CTA handshakes)
   const int k_chunks = a.taps * (a.split3 ? 3 : 1) * (a.cin / 64);
   p->ctas = (p->bn >= 128 && g.n_tiles_m % 2 == 0 && (g.n_tiles_m / 2) * g.n_tiles_n >= 74 && k_chunks >= 8 &&
-             !g_disable_pairs) ? 2 : 1;
+             g.ksplit == 1 && !g_disable_pairs) ? 2 : 1;
   const int rin = a.r * a.stride;
   // strip mode: 3x3 stride-1 convolutions whose M tile is 128 pixels of one image row, on CTA pairs
   // (single-CTA strip tiles exist only for the final sub-pixel layer, whose 32-column tiles are A-traffic bound)

@@ -87,10 +87,14 @@ struct msr_generator {
   const __nv_bfloat16* out_wt = nullptr;         // [32][9*128] sub-pixel phase weights of the final 4x4 conv
   const __nv_bfloat16* enc1_wt = nullptr;        // [64][64] im2col weights of encoder block 1
   const __nv_bfloat16* enc_wt[5] = {};           // [cout][9*cin] for blocks 2..5
-  const float* enc_head_w = nullptr;             // [feat][512] = mean | variance
+  const __nv_bfloat16* enc_head_wt = nullptr;    // [512 = mean | variance][3 * feat]: split-bf16 rows (w_hi | w_lo | w_hi)
   const float* enc_head_b = nullptr;             // [512]
+  const __nv_bfloat16* dense_wt = nullptr;       // [sw*sw*1024][3 * 256]: generator dense layer, same row structure
+  __nv_bfloat16* enc_feat_split = nullptr;       // [n][2 * feat]: flattened encoder output as hi | lo
+  __nv_bfloat16* latent_split = nullptr;         // [n][2 * 256]
+  int head_ksplit = 1;
   __nv_bfloat16* patches = nullptr;              // im2col'd source [n][r][r][64]
-  __nv_bfloat16* enc_b0 = nullptr; __nv_bfloat16* enc_b1 = nullptr; float* enc_y = nullptr; float* enc_feat = nullptr;
+  __nv_bfloat16* enc_b0 = nullptr; __nv_bfloat16* enc_b1 = nullptr; float* enc_y = nullptr;
   float* lat_mv = nullptr;                       // [n][512] mean | variance
   float2* stat_pairs = nullptr;
   // pix2pix
@@ -104,6 +108,7 @@ struct msr_generator {
   float* lat_mean = nullptr; float* lat_var = nullptr; float* latent = nullptr;
   float* dense_partial = nullptr; int64_t dense_partial_cap = 0;
   double* stat_partial = nullptr;
+  unsigned int* stat_counters = nullptr;   // tickets of the single-launch statistics kernels (zero between launches)
   float* xbuf[2] = {};         // residual stream ping-pong (fp32)
   float* h1 = nullptr; float* s3 = nullptr;
   float* st_mean[3] = {}; float* st_rstd[3] = {};   // stats of: x_prev, h1, (spare)
@@ -319,31 +324,63 @@ int finalize_spade_bf16_extras(msr_generator* g) {
         }
     if ((rc = upload_bf16(g, w, &g->enc_wt[k]))) return rc;
   }
-  {  // encoder heads merged into one weight-bandwidth-bound pass: [feat][512] = mean | variance (fp32 weights)
+  {  // encoder heads (networks.py:31-33) merged into one GEMM [n][feat] x [feat][512 = mean | variance] on the tensor
+     // cores with split-bf16 operands (x = hi + lo, w = hi + lo; products hi*hi + hi*lo + lo*hi ~ fp32): weight rows are
+     // K-major (w_hi | w_lo | w_hi), 3 * feat columns
     const int64_t feat = (int64_t)(I / 32) * (I / 32) * 512;
     const HostTensor *wm, *wv, *bm, *bv;
     if ((rc = need(g, "enc.mean.kernel", {feat, kLatent}, &wm))) return rc;
     if ((rc = need(g, "enc.variance.kernel", {feat, kLatent}, &wv))) return rc;
     if ((rc = need(g, "enc.mean.bias", {kLatent}, &bm))) return rc;
     if ((rc = need(g, "enc.variance.bias", {kLatent}, &bv))) return rc;
-    std::vector<float> w((size_t)feat * 2 * kLatent), b(2 * kLatent);
-    for (int64_t f = 0; f < feat; ++f) {
-      memcpy(&w[(size_t)f * 2 * kLatent], &wm->data[(size_t)f * kLatent], sizeof(float) * kLatent);
-      memcpy(&w[(size_t)f * 2 * kLatent + kLatent], &wv->data[(size_t)f * kLatent], sizeof(float) * kLatent);
+    std::vector<uint16_t> w((size_t)2 * kLatent * 3 * feat);
+    std::vector<float> b(2 * kLatent);
+    for (int head = 0; head < 2; ++head) {
+      const HostTensor* src = head == 0 ? wm : wv;
+      for (int64_t f = 0; f < feat; ++f)
+        for (int c = 0; c < kLatent; ++c) {
+          const float v = src->data[(size_t)f * kLatent + c];
+          const uint16_t hi = f2bf(v);
+          uint16_t* row = &w[(size_t)(head * kLatent + c) * 3 * feat];
+          row[f] = hi;
+          row[feat + f] = f2bf(v - bf2f(hi));
+          row[2 * feat + f] = hi;
+        }
     }
     memcpy(&b[0], bm->data.data(), sizeof(float) * kLatent);
     memcpy(&b[kLatent], bv->data.data(), sizeof(float) * kLatent);
-    if ((rc = upload(g, w, &g->enc_head_w))) return rc;
+    if ((rc = upload_bf16(g, w, &g->enc_head_wt))) return rc;
     if ((rc = upload(g, b, &g->enc_head_b))) return rc;
+    // split-K: ~128 work units; the channel blocks of a part (feat / 64) must divide evenly
+    int ks = 1;
+    while (ks < 64 && (feat / 64) % (2 * ks) == 0) ks *= 2;
+    g->head_ksplit = ks;
+  }
+  {  // generator dense layer (networks.py:41): [n][256] x [256][sw*sw*1024], same split-bf16 structure
+    const int64_t nout = (int64_t)16 * sw * sw * 64;
+    if ((rc = need(g, "gen.dense.kernel", {kLatent, nout}, &t))) return rc;
+    std::vector<uint16_t> w((size_t)nout * 3 * kLatent);
+    for (int k = 0; k < kLatent; ++k)
+      for (int64_t o = 0; o < nout; ++o) {
+        const float v = t->data[(size_t)k * nout + o];
+        const uint16_t hi = f2bf(v);
+        uint16_t* row = &w[(size_t)o * 3 * kLatent];
+        row[k] = hi;
+        row[kLatent + k] = f2bf(v - bf2f(hi));
+        row[2 * kLatent + k] = hi;
+      }
+    if ((rc = upload_bf16(g, w, &g->dense_wt))) return rc;
   }
   if ((rc = ws(g, &g->lat_mv, N * 2 * kLatent))) return rc;
   if ((rc = ws(g, &g->patches, N * half * 64))) return rc;
   if ((rc = ws(g, &g->enc_b0, N * half * 128))) return rc;          // hi | lo halves
   if ((rc = ws(g, &g->enc_b1, N * (half / 4) * 256))) return rc;
   if ((rc = ws(g, &g->enc_y, N * (half / 4) * 128))) return rc;
-  if ((rc = ws(g, &g->enc_feat, N * (int64_t)(I / 32) * (I / 32) * 512))) return rc;
+  if ((rc = ws(g, &g->enc_feat_split, N * 2 * (int64_t)(I / 32) * (I / 32) * 512))) return rc;
+  if ((rc = ws(g, &g->latent_split, N * 2 * kLatent))) return rc;
   if ((rc = ws(g, &g->stat_pairs, 4 * N * half))) return rc;
-  const int64_t need_partial = std::max<int64_t>(296 * N * 2 * kLatent, 4 * N * 16 * sw * sw * 64);
+  // split-K planes of the head GEMM: rows are padded to whole 128-row M tiles by the kernel's masking, not in memory
+  const int64_t need_partial = std::max<int64_t>((int64_t)g->head_ksplit * N * 2 * kLatent, 296 * N * 2 * kLatent);
   if (need_partial > g->dense_partial_cap) {
     g->dense_partial_cap = need_partial;
     if ((rc = ws(g, &g->dense_partial, need_partial))) return rc;
@@ -356,8 +393,8 @@ int finalize_spade(msr_generator* g) {
   const int64_t N = (int64_t)g->B * g->maxG;
   int rc;
   const bool fp32 = g->precision == MSR_PRECISION_FP32;
-  // the dense layers are weight-bandwidth bound and tiny: fp32 weights in both modes
-  if ((rc = upload_named(g, "gen.dense.kernel", {kLatent, 16 * sw * sw * 64}, &g->dense_w))) return rc;
+  // fp32 mode: fp32 dense weights (CUDA cores); bf16 mode: split-bf16 weights for the tensor-core GEMM (extras below)
+  if (fp32 && (rc = upload_named(g, "gen.dense.kernel", {kLatent, 16 * sw * sw * 64}, &g->dense_w))) return rc;
   if ((rc = upload_named(g, "gen.dense.bias", {16 * sw * sw * 64}, &g->dense_b))) return rc;
   int cin = 1024;
   for (int k = 0; k < 6; ++k) {
@@ -412,6 +449,11 @@ int finalize_spade(msr_generator* g) {
   g->dense_partial_cap = std::max<int64_t>(296 * N * kLatent, 4 * N * 16 * sw * sw * 64);
   if ((rc = ws(g, &g->dense_partial, g->dense_partial_cap))) return rc;
   if ((rc = ws(g, &g->stat_partial, (int64_t)std::max<int64_t>(N, g->maxG) * kStatSplit * 1024 * 2))) return rc;
+  {
+    const int64_t slots = std::max<int64_t>(N, g->maxG) * (1024 / 64);
+    if ((rc = ws(g, &g->stat_counters, slots))) return rc;
+    MSR_CUDA_CHECK(cudaMemset(g->stat_counters, 0, (size_t)slots * sizeof(unsigned int)));
+  }
   const int64_t stream_elems = N * half * 128;  // max over blocks of r^2 * cout (and r_prev^2 * cin)
   if ((rc = ws(g, &g->xbuf[0], std::max<int64_t>(stream_elems, N * sw * sw * 1024)))) return rc;
   if ((rc = ws(g, &g->xbuf[1], std::max<int64_t>(stream_elems, N * sw * sw * 1024)))) return rc;
@@ -660,7 +702,7 @@ int forward_spade(Fwd& f, const float* source, const float* eps, float* out) {
     if (k > 0) {  // tfa InstanceNormalization (eps 1e-3, per sample and channel) + LeakyReLU(0.2), blocks.py:62-65
       const int64_t rows = (int64_t)er * er;
       if ((rc = channel_stats_f32(ey, kEnc[k], n, rows, kEnc[k], 1e-3f, g->stat_partial, g->enc_stats_mean,
-                                  g->enc_stats_rstd, st))) return rc;
+                                  g->enc_stats_rstd, st, g->stat_counters))) return rc;
       if ((rc = affine_act_f32(ey, kEnc[k], g->enc_stats_mean, g->enc_stats_rstd, g->enc_g[k], g->enc_bt[k], ey,
                                kEnc[k], (int64_t)n * rows, kEnc[k], rows, ACT_LRELU, 0.2f, st))) return rc;
     }
@@ -686,7 +728,7 @@ int forward_spade(Fwd& f, const float* source, const float* eps, float* out) {
   int r = sw, x_shift = 0;
   // statistics of the block input (shared by spade_1 and spade_3; invariant under nearest upsampling)
   if ((rc = channel_stats_f32(x, 1024, f.groups, (int64_t)g->B * sw * sw, 1024, 1e-5f, g->stat_partial, g->st_mean[0],
-                              g->st_rstd[0], st))) return rc;
+                              g->st_rstd[0], st, g->stat_counters))) return rc;
   for (int k = 0; k < 6; ++k) {
     const BlockW& b = g->rb[k];
     float* y = g->xbuf[(k + 1) & 1];
@@ -695,7 +737,7 @@ int forward_spade(Fwd& f, const float* source, const float* eps, float* out) {
     if ((rc = run_spade(f, b.s1, source, x, x_shift, g->st_mean[0], g->st_rstd[0], r))) return rc;
     if ((rc = run_conv(f, b.c1, r, g->h1, nullptr, 0))) return rc;
     if ((rc = channel_stats_f32(g->h1, b.cout, f.groups, rows, b.cout, 1e-5f, g->stat_partial, g->st_mean[1],
-                                g->st_rstd[1], st))) return rc;
+                                g->st_rstd[1], st, g->stat_counters))) return rc;
     const float* res = x;
     int res_shift = x_shift;
     if (b.learned) {  // skip = conv_3(lrelu(spade_3(in)))             blocks.py:34-36
@@ -711,7 +753,7 @@ int forward_spade(Fwd& f, const float* source, const float* eps, float* out) {
     g->acts["rb" + std::to_string(k + 1) + ".out"] = {y, (int64_t)n * r * r * b.cout, 0};
     if (k < 5) {
       if ((rc = channel_stats_f32(y, b.cout, f.groups, rows, b.cout, 1e-5f, g->stat_partial, g->st_mean[0],
-                                  g->st_rstd[0], st))) return rc;
+                                  g->st_rstd[0], st, g->stat_counters))) return rc;
     }
     x = y;
     x_shift = 1;  // UpSampling2D((2, 2)) after every block (networks.py:44-54), fused into the consumers
@@ -759,9 +801,10 @@ int conv_bf16(Fwd& f, const ConvW& w, int r, float* y, const float* res, int res
   if (fused) {
     const int64_t rows_p = (int64_t)g->B * (r * r / 128) * 4;
     return channel_stats_from_pairs(g->stat_pairs, f.groups, rows_p, (int64_t)g->B * r * r, w.cout, 1e-5f,
-                                    g->stat_partial, mean, rstd, f.st);
+                                    g->stat_partial, mean, rstd, f.st, g->stat_counters);
   }
-  return channel_stats_f32(y, w.cout, f.groups, (int64_t)g->B * r * r, w.cout, 1e-5f, g->stat_partial, mean, rstd, f.st);
+  return channel_stats_f32(y, w.cout, f.groups, (int64_t)g->B * r * r, w.cout, 1e-5f, g->stat_partial, mean, rstd, f.st,
+                           g->stat_counters);
 }
 
 int forward_spade_bf16(Fwd& f, const float* source, const float* eps, float* out) {
@@ -795,30 +838,47 @@ int forward_spade_bf16(Fwd& f, const float* source, const float* eps, float* out
     if ((rc = tc_conv(f, a))) return rc;
     if (fused) {
       if ((rc = channel_stats_from_pairs(g->stat_pairs, n, rows / 128 * 4, rows, kEnc[k], 1e-3f, g->stat_partial,
-                                         g->enc_stats_mean, g->enc_stats_rstd, st))) return rc;
+                                         g->enc_stats_mean, g->enc_stats_rstd, st, g->stat_counters))) return rc;
     } else if ((rc = channel_stats_f32(g->enc_y, kEnc[k], n, rows, kEnc[k], 1e-3f, g->stat_partial, g->enc_stats_mean,
-                                       g->enc_stats_rstd, st))) return rc;
+                                       g->enc_stats_rstd, st, g->stat_counters))) return rc;
     __nv_bfloat16* eb = (k & 1) ? g->enc_b1 : g->enc_b0;
+    // the last block's output is Flatten()ed (NHWC order) into the heads' operand: hi | lo blocks per image
     if ((rc = affine_act_bf16out(g->enc_y, kEnc[k], g->enc_stats_mean, g->enc_stats_rstd, g->enc_g[k], g->enc_bt[k],
-                                 k < 4 ? eb : nullptr, k == 4 ? g->enc_feat : nullptr, (int64_t)n * rows, kEnc[k], rows,
-                                 ACT_LRELU, 0.2f, 1, st))) return rc;
+                                 k < 4 ? eb : g->enc_feat_split, nullptr, (int64_t)n * rows, kEnc[k], rows,
+                                 ACT_LRELU, 0.2f, k < 4 ? 1 : 2, st))) return rc;
     ex = eb;
   }
   const int feat = er * er * 512;
-  if ((rc = dense_f32w(g->enc_feat, g->enc_head_w, g->enc_head_b, g->lat_mv, n, feat, 2 * kLatent, g->dense_partial,
-                       g->dense_partial_cap, st))) return rc;
+  {  // Dense "mean" | Dense "variance" (networks.py:31-33): one split-K tcgen05 GEMM + the plane reduction (+ bias)
+    ConvTCArgs a;
+    a.x = g->enc_feat_split; a.w = g->enc_head_wt; a.n = n; a.r = 1; a.cin = feat; a.ncols = 2 * kLatent; a.taps = 1;
+    a.pad = 0; a.split3 = 1; a.ksplit = g->head_ksplit; a.epilogue = TC_EPI_BIAS_F32;
+    if (g->head_ksplit > 1) {
+      a.y = g->dense_partial;
+      if ((rc = tc_conv(f, a))) return rc;
+      if ((rc = dense_reduce_planes(g->dense_partial, g->enc_head_b, g->lat_mv, n, 2 * kLatent, g->head_ksplit, st)))
+        return rc;
+    } else {
+      a.y = g->lat_mv; a.bias = g->enc_head_b;
+      if ((rc = tc_conv(f, a))) return rc;
+    }
+  }
   // ---- sampler (sampling.py:11-17) or mean + variance (model.py:789-791); rows hold mean | variance
   if ((rc = sampler_strided_f32(g->lat_mv, 2 * kLatent, g->arch == MSR_ARCH_SPADE ? eps : nullptr, g->latent, n, kLatent,
-                                st))) return rc;
+                                st, g->latent_split))) return rc;
   g->acts["latent"] = {g->latent, (int64_t)n * kLatent, 0};
   // ---- generator (networks.py:37-57)
   float* x = g->xbuf[0];
-  if ((rc = dense_f32w(g->latent, g->dense_w, g->dense_b, x, n, kLatent, sw * sw * 1024, g->dense_partial,
-                       g->dense_partial_cap, st))) return rc;
+  {  // Dense(16 * sw * sw * 64) (networks.py:41) on the tensor cores, bias in the epilogue
+    ConvTCArgs a;
+    a.x = g->latent_split; a.w = g->dense_wt; a.n = n; a.r = 1; a.cin = kLatent; a.ncols = sw * sw * 1024; a.taps = 1;
+    a.pad = 0; a.split3 = 1; a.epilogue = TC_EPI_BIAS_F32; a.bias = g->dense_b; a.y = x;
+    if ((rc = tc_conv(f, a))) return rc;
+  }
   g->acts["x0"] = {x, (int64_t)n * sw * sw * 1024, 0};
   int r = sw, x_shift = 0;
   if ((rc = channel_stats_f32(x, 1024, f.groups, (int64_t)g->B * sw * sw, 1024, 1e-5f, g->stat_partial, g->st_mean[0],
-                              g->st_rstd[0], st))) return rc;
+                              g->st_rstd[0], st, g->stat_counters))) return rc;
   for (int k = 0; k < 6; ++k) {
     const BlockW& b = g->rb[k];
     float* y = g->xbuf[(k + 1) & 1];

@@ -28,9 +28,11 @@ int conv_f32(const ConvF32& p, cudaStream_t st);
 
 // Per-(group, channel) mean and 1/sqrt(var + eps) over `rows` consecutive rows of x[groups*rows][ld] (biased variance).
 // `partial` is scratch of groups * kStatSplit * C * 2 doubles.
+// `counters` (optional): groups * ceil(C / 64) zero-initialised uints; with them the second stage runs inside the same
+// launch (the last block of every channel block finalises), without them a second small kernel is launched.
 constexpr int kStatSplit = 64;
 int channel_stats_f32(const float* x, int ld, int groups, int64_t rows, int C, float eps, double* partial, float* mean,
-                      float* rstd, cudaStream_t st);
+                      float* rstd, cudaStream_t st, unsigned int* counters = nullptr);
 
 // SPADE modulation (spade.py:21-24 + blocks.py:30-34): out[m][c] = lrelu(gamma * (x[src(m)][c] - mean) * rstd + beta)
 // gb [M][2C] = gamma | beta; x is [n][r >> x_shift][r >> x_shift][C]; statistics per group of rows_per_group rows of M.
@@ -48,7 +50,9 @@ int affine_act_f32(const float* x, int ldx, const float* mean, const float* rstd
 int sampler_f32(const float* mean, const float* var, const float* eps, float* latent, int64_t count, cudaStream_t st);
 
 // same, with mean | variance stored side by side in rows of pitch ld (mean at [0, L), variance at [L, 2L))
-int sampler_strided_f32(const float* mv, int ld, const float* eps, float* latent, int n, int L, cudaStream_t st);
+// split_out (optional): the latent again as a split-bf16 row hi (L) | lo (L), the A operand of the tensor-core dense layer
+int sampler_strided_f32(const float* mv, int ld, const float* eps, float* latent, int n, int L, cudaStream_t st,
+                        __nv_bfloat16* split_out = nullptr);
 
 // Final generator layer (networks.py:54-56): UpSampling2D(2) -> leaky_relu(0.2) -> Conv2D(1, 4, 'same') on
 // x [n][r][r][128] fp32 -> out [n][2r][2r] fp32.  w [4][4][128] (Keras [4,4,128,1]), bias scalar.
@@ -72,6 +76,8 @@ struct ConvTCArgs {
   int split3 = 0;                    // 1: split-bf16 operands (~fp32 products): x has 2*cin channels (hi | lo), w has
                                      //    3*cin columns per tap (w_hi | w_lo | w_hi) pairing with (x_hi, x_hi, x_lo)
   int split_out = 0;                 // TC_EPI_ACT_BF16: also write lo = bf16(v - hi) at column ncols + c (pitch 2*ncols)
+  int ksplit = 1;                    // > 1 (taps = 1, TC_EPI_BIAS_F32 only): split-K -- the channel blocks are cut into ksplit
+                                     //     ranges, range ks writes its partial sums to y + ks * (n*r*r) * ncols
   int stride = 1, pad = 1;           // input coordinate = out*stride + k - pad
   int epilogue = TC_EPI_BIAS_F32;
   const float* bias = nullptr;       // [ncols]
@@ -119,9 +125,15 @@ int affine_act_bf16out(const float* x, int ldx, const float* mean, const float* 
                        const float* beta, __nv_bfloat16* y_bf16, float* y_f32, int64_t M, int C, int64_t rows_per_group,
                        int act, float slope, int split, cudaStream_t st);
 // split = 1: y_bf16 has row pitch 2C and receives hi = bf16(v) at [0, C) and lo = bf16(v - hi) at [C, 2C)
+// split = 2: flattened-image layout for the dense heads: image b = m / rows_per_group owns 2 * rows_per_group * C values,
+//            hi of (pixel p, channel c) at b*2K + p*C + c and lo at b*2K + K + p*C + c with K = rows_per_group * C
+
+// sum of the `planes` split-K partial planes [planes][M][N] (+ bias[N]) -> out[M][N]
+int dense_reduce_planes(const float* partial, const float* bias, float* out, int M, int N, int planes, cudaStream_t st);
 
 // statistics from the fused (sum, sumsq) pairs written by the tensor-core epilogue: pairs [groups*rows_p][C]
 int channel_stats_from_pairs(const float2* pairs, int groups, int64_t rows_p, int64_t count_per_group, int C, float eps,
-                             double* partial, float* mean, float* rstd, cudaStream_t st);
+                             double* partial, float* mean, float* rstd, cudaStream_t st,
+                             unsigned int* counters = nullptr);
 
 }  // namespace msr

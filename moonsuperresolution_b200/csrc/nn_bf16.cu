@@ -21,10 +21,11 @@ __global__ void __launch_bounds__(256) source_patches_kernel(const float* __rest
                                                              __nv_bfloat16* __restrict__ out, int n, int r, int mode) {
   const int64_t total = (int64_t)n * r * r;
   const int f = I / r, half = f >> 1;
+  const int lr = 31 - __clz(r);                  // r is a power of two (checked by the launcher)
   for (int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; m < total; m += (int64_t)gridDim.x * blockDim.x) {
-    const int nn = (int)(m / ((int64_t)r * r));
-    const int rem = (int)(m % ((int64_t)r * r));
-    const int h = rem / r, x = rem % r;
+    const int nn = (int)(m >> (2 * lr));
+    const int rem = (int)(m & (((int64_t)1 << (2 * lr)) - 1));
+    const int h = rem >> lr, x = rem & (r - 1);
     // split-bf16 operand: channels [0,18) = hi, [18,36) = hi again, [36,54) = lo (v = hi + lo to ~2^-17); the matching
     // weight rows are [w_hi | w_lo | w_hi], so the GEMM evaluates a_hi*w_hi + a_hi*w_lo + a_lo*w_hi ~ fp32 product
     __align__(16) __nv_bfloat16 row[64];
@@ -93,7 +94,8 @@ __global__ void __launch_bounds__(256) source_patches4_kernel(const float* __res
 }
 
 int source_patches_bf16(const float* source, int I, __nv_bfloat16* out, int n, int r, int mode, cudaStream_t st) {
-  MSR_REQUIRE(source && out && n > 0 && r > 0 && I % r == 0, "source_patches: bad arguments");
+  MSR_REQUIRE(source && out && n > 0 && r > 0 && I % r == 0 && (r & (r - 1)) == 0,
+              "source_patches: bad arguments (r must be a power of two dividing I)");
   MSR_REQUIRE(mode == 0 || ((mode == 1 || mode == 2) && r * 2 == I), "source_patches: modes 1, 2 need r = I / 2");
   const int64_t total = (int64_t)n * r * r;
   ProfileScope prof(MSR_PROF_MASK_CONV, st, (double)total * (128.0 + 8.0));
@@ -270,6 +272,15 @@ __global__ void __launch_bounds__(256) dense_gemm_partial_kernel(const float* __
   }
 }
 
+int dense_reduce_planes(const float* partial, const float* bias, float* out, int M, int N, int planes, cudaStream_t st) {
+  MSR_REQUIRE(partial && out && M > 0 && N > 0 && planes > 0, "dense_reduce_planes: bad arguments");
+  ProfileScope prof(MSR_PROF_DENSE, st, (double)M * N * 4.0 * (planes + 1));
+  dense_bf16w_reduce_kernel<<<ceil_div((int64_t)M * N, 256), 256, 0, st>>>(partial, bias, out, M, N, planes);
+  count_launch();
+  MSR_LAUNCH_CHECK();
+  return MSR_OK;
+}
+
 static int dense_gemm_m128(const float* x, const float* w, const float* bias, float* out, int M, int K, int N,
                            float* partial, int64_t partial_capacity, cudaStream_t st) {
   ProfileScope prof(MSR_PROF_DENSE, st, 2.0 * M * (double)K * N, 2);
@@ -362,12 +373,94 @@ __global__ void __launch_bounds__(256) affine_act_bf16_kernel(const float* __res
   }
 }
 
+// Same operation, 8 channels per thread and 32-bit index arithmetic (C a power of two): two 128-bit loads, one 128-bit
+// store per output half.  The generic kernel above spends its time in 64-bit divisions, not on the memory system.
+__global__ void __launch_bounds__(256) affine_act_bf16_vec8_kernel(const float* __restrict__ x, int ldx,
+                                                                   const float* __restrict__ mean,
+                                                                   const float* __restrict__ rstd,
+                                                                   const float* __restrict__ gamma,
+                                                                   const float* __restrict__ beta,
+                                                                   __nv_bfloat16* __restrict__ yb, float* __restrict__ yf,
+                                                                   int M, int C, int rows_per_group, int act, float slope,
+                                                                   int split) {
+  const int c8n = C >> 3;                       // threads per row (power of two, <= 256)
+  const int rpb = 256 / c8n;                    // rows per block
+  const int c = (threadIdx.x & (c8n - 1)) * 8;
+  const int rl = threadIdx.x / c8n;
+  float ga[8], be[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    ga[j] = gamma ? __ldg(gamma + c + j) : 1.f;
+    be[j] = beta ? __ldg(beta + c + j) : 0.f;
+  }
+  for (int m = blockIdx.x * rpb + rl; m < M; m += gridDim.x * rpb) {
+    const float4 a0 = __ldcs(reinterpret_cast<const float4*>(x + (int64_t)m * ldx + c));
+    const float4 a1 = __ldcs(reinterpret_cast<const float4*>(x + (int64_t)m * ldx + c + 4));
+    float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    if (mean) {
+      const int g = m / rows_per_group;
+      const float4 m0 = __ldg(reinterpret_cast<const float4*>(mean + (int64_t)g * C + c));
+      const float4 m1 = __ldg(reinterpret_cast<const float4*>(mean + (int64_t)g * C + c + 4));
+      const float4 r0 = __ldg(reinterpret_cast<const float4*>(rstd + (int64_t)g * C + c));
+      const float4 r1 = __ldg(reinterpret_cast<const float4*>(rstd + (int64_t)g * C + c + 4));
+      const float mu[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+      const float rs[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = (v[j] - mu[j]) * rs[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (gamma) v[j] *= ga[j];          // same operation order as the generic kernel: (x - mu) * rstd, * gamma, + beta
+      if (beta) v[j] += be[j];
+      if (act == ACT_RELU) v[j] = fmaxf(v[j], 0.f);
+      else if (act == ACT_LRELU) v[j] = v[j] > 0.f ? v[j] : v[j] * slope;
+    }
+    if (yf) {
+      *reinterpret_cast<float4*>(yf + (int64_t)m * C + c) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(yf + (int64_t)m * C + c + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    if (yb) {
+      __align__(16) __nv_bfloat16 o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = __float2bfloat16_rn(v[j]);
+      if (!split) {
+        *reinterpret_cast<uint4*>(yb + (int64_t)m * C + c) = *reinterpret_cast<const uint4*>(o);
+      } else {
+        __align__(16) __nv_bfloat16 l[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) l[j] = __float2bfloat16_rn(v[j] - __bfloat162float(o[j]));
+        if (split == 1) {
+          *reinterpret_cast<uint4*>(yb + (int64_t)m * 2 * C + c) = *reinterpret_cast<const uint4*>(o);
+          *reinterpret_cast<uint4*>(yb + (int64_t)m * 2 * C + C + c) = *reinterpret_cast<const uint4*>(l);
+        } else {   // flattened image: hi block (K values) then lo block, K = rows_per_group * C
+          const int b = m / rows_per_group, pp = m - b * rows_per_group;
+          const int64_t K = (int64_t)rows_per_group * C;
+          *reinterpret_cast<uint4*>(yb + (int64_t)b * 2 * K + (int64_t)pp * C + c) = *reinterpret_cast<const uint4*>(o);
+          *reinterpret_cast<uint4*>(yb + (int64_t)b * 2 * K + K + (int64_t)pp * C + c) = *reinterpret_cast<const uint4*>(l);
+        }
+      }
+    }
+  }
+}
+
 int affine_act_bf16out(const float* x, int ldx, const float* mean, const float* rstd, const float* gamma,
                        const float* beta, __nv_bfloat16* y_bf16, float* y_f32, int64_t M, int C, int64_t rows_per_group,
                        int act, float slope, int split, cudaStream_t st) {
   MSR_REQUIRE(x && (y_bf16 || y_f32) && M > 0 && C > 0 && C % 4 == 0 && ldx % 4 == 0 && rows_per_group > 0,
               "affine_act_bf16out: bad arguments");
-  ProfileScope prof(MSR_PROF_ELEMWISE, st, (double)M * C * (4.0 + (y_bf16 ? 2.0 : 0.0) + (y_f32 ? 4.0 : 0.0)));
+  MSR_REQUIRE(split != 2 || (C % 8 == 0 && (C & (C - 1)) == 0 && C / 8 <= 256),
+              "affine_act_bf16out: the flattened split layout needs a power-of-two channel count");
+  ProfileScope prof(MSR_PROF_ELEMWISE, st,
+                    (double)M * C * (4.0 + (y_bf16 ? (split ? 4.0 : 2.0) : 0.0) + (y_f32 ? 4.0 : 0.0)));
+  if (C % 8 == 0 && (C & (C - 1)) == 0 && C / 8 <= 256 && ldx % 4 == 0 && M < (1ll << 31) && rows_per_group < (1ll << 31)) {
+    const int c8n = C / 8, rpb = 256 / c8n;
+    const int blocks = (int)std::min<int64_t>((M + rpb - 1) / rpb, 148 * 16);
+    affine_act_bf16_vec8_kernel<<<blocks, 256, 0, st>>>(x, ldx, mean, rstd, gamma, beta, y_bf16, y_f32, (int)M, C,
+                                                        (int)rows_per_group, act, slope, split);
+    count_launch();
+    MSR_LAUNCH_CHECK();
+    return MSR_OK;
+  }
   const int64_t total = M * (C / 4);
   const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 16);
   affine_act_bf16_kernel<<<blocks, 256, 0, st>>>(x, ldx, mean, rstd, gamma, beta, y_bf16, y_f32, M, C, rows_per_group,
@@ -381,7 +474,9 @@ int affine_act_bf16out(const float* x, int ldx, const float* mean, const float* 
 // batch statistics from the (sum, sumsq) pairs emitted by the tensor-core epilogue (deterministic, fp64 second stage)
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) stats_pairs_partial_kernel(const float2* __restrict__ pairs, int64_t rows_p, int C,
-                                                                  double* __restrict__ partial) {
+                                                                  double* __restrict__ partial, unsigned int* counters,
+                                                                  double count, float eps, float* __restrict__ mean,
+                                                                  float* __restrict__ rstd) {
   // grid (ceil(C/64), kStatSplit, groups); block = 32 channel pairs x 8 row lanes; one 128-bit load = 2 (sum, sumsq) pairs
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int c = (blockIdx.x * 32 + cx) * 2;
@@ -419,6 +514,35 @@ __global__ void __launch_bounds__(256) stats_pairs_partial_kernel(const float2* 
     o[2] = s1;
     o[3] = q1;
   }
+  if (counters != nullptr) {   // single launch: the last block of this (group, channel block) runs the second stage
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int slot = g * gridDim.x + blockIdx.x;
+      const unsigned int prev = atomicAdd(counters + slot, 1u);
+      s_last = (prev == (unsigned int)(kStatSplit - 1));
+      if (s_last) counters[slot] = 0u;
+    }
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      const int cc = blockIdx.x * 64 + threadIdx.x;
+      if (threadIdx.x < 64 && cc < C) {
+        double s = 0.0, q = 0.0;
+        for (int k = 0; k < kStatSplit; ++k) {
+          const double* o = partial + (((int64_t)g * kStatSplit + k) * C + cc) * 2;
+          s += __ldcg(o);
+          q += __ldcg(o + 1);
+        }
+        const double mu = s / count;
+        double var = q / count - mu * mu;
+        if (var < 0.0) var = 0.0;
+        mean[(int64_t)g * C + cc] = (float)mu;
+        rstd[(int64_t)g * C + cc] = (float)(1.0 / sqrt(var + (double)eps));
+      }
+    }
+  }
 }
 
 __global__ void stats_pairs_finalize_kernel(const double* __restrict__ partial, int C, int64_t count, float eps,
@@ -440,14 +564,19 @@ __global__ void stats_pairs_finalize_kernel(const double* __restrict__ partial, 
 }
 
 int channel_stats_from_pairs(const float2* pairs, int groups, int64_t rows_p, int64_t count_per_group, int C, float eps,
-                             double* partial, float* mean, float* rstd, cudaStream_t st) {
+                             double* partial, float* mean, float* rstd, cudaStream_t st, unsigned int* counters) {
   MSR_REQUIRE(pairs && partial && mean && rstd && groups > 0 && rows_p > 0 && C > 0, "stats_from_pairs: bad arguments");
-  ProfileScope prof(MSR_PROF_STATS, st, (double)groups * rows_p * C * 8.0, 2);
-  stats_pairs_partial_kernel<<<dim3(ceil_div(C, 64), kStatSplit, groups), 256, 0, st>>>(pairs, rows_p, C, partial);
+  MSR_REQUIRE(C % 2 == 0, "stats_from_pairs: channel count must be even");
+  ProfileScope prof(MSR_PROF_STATS, st, (double)groups * rows_p * C * 8.0, counters ? 1 : 2);
+  stats_pairs_partial_kernel<<<dim3(ceil_div(C, 64), kStatSplit, groups), 256, 0, st>>>(
+      pairs, rows_p, C, partial, counters, (double)count_per_group, eps, mean, rstd);
   MSR_LAUNCH_CHECK();
-  stats_pairs_finalize_kernel<<<dim3(ceil_div(C, 128), groups), 128, 0, st>>>(partial, C, count_per_group, eps, mean, rstd);
-  MSR_LAUNCH_CHECK();
-  count_launch(2);
+  if (counters == nullptr) {
+    stats_pairs_finalize_kernel<<<dim3(ceil_div(C, 128), groups), 128, 0, st>>>(partial, C, count_per_group, eps, mean,
+                                                                                 rstd);
+    MSR_LAUNCH_CHECK();
+  }
+  count_launch(counters ? 1 : 2);
   return MSR_OK;
 }
 

@@ -175,9 +175,43 @@ int conv_f32(const ConvF32& p, cudaStream_t st) {
 // Channel statistics: deterministic two-stage reduction, fp64 partials.
 // ------------------------------------------------------------------------------------------------------------------
 // grid (ceil(C/128), kStatSplit, groups); block = 32 channel quads x 8 row lanes; 128-bit loads (C % 4 == 0, ld % 4 == 0)
+// `counters` != null: the last of the kStatSplit blocks of a (group, channel block) to finish also does the second stage
+// (fixed summation order, so the result does not depend on which block that is) -- one launch instead of two.
+__device__ __forceinline__ void stats_finalize_channel(const double* __restrict__ partial, int g, int c, int C,
+                                                       double count, float eps, float* __restrict__ mean,
+                                                       float* __restrict__ rstd) {
+  double s = 0.0, q = 0.0;
+  for (int k = 0; k < kStatSplit; ++k) {
+    const double* o = partial + (((int64_t)g * kStatSplit + k) * C + c) * 2;
+    s += __ldcg(o);
+    q += __ldcg(o + 1);
+  }
+  const double mu = s / count;
+  double var = q / count - mu * mu;
+  if (var < 0.0) var = 0.0;
+  mean[(int64_t)g * C + c] = (float)mu;
+  rstd[(int64_t)g * C + c] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+__device__ __forceinline__ bool stats_block_is_last(unsigned int* counters, int slot) {
+  __shared__ int s_last;
+  __threadfence();               // this block's partials are visible device-wide before the ticket is taken
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int prev = atomicAdd(counters + slot, 1u);
+    s_last = (prev == (unsigned int)(kStatSplit - 1));
+    if (s_last) counters[slot] = 0u;   // ready for the next launch (stream order)
+  }
+  __syncthreads();
+  if (s_last) __threadfence();   // acquire side: the other blocks' partials
+  return s_last != 0;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) stats_partial_kernel(const T* __restrict__ x, int ld, int64_t rows, int C,
-                                                            double* __restrict__ partial) {
+                                                            double* __restrict__ partial, unsigned int* counters,
+                                                            float eps, float* __restrict__ mean,
+                                                            float* __restrict__ rstd) {
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int c = (blockIdx.x * 32 + cx) * 4;
   const int split = blockIdx.y, g = blockIdx.z;
@@ -218,6 +252,10 @@ __global__ void __launch_bounds__(256) stats_partial_kernel(const T* __restrict_
       o[1] = qq;
     }
   }
+  if (counters != nullptr && stats_block_is_last(counters, g * gridDim.x + blockIdx.x)) {
+    const int cc = blockIdx.x * 128 + threadIdx.x;
+    if (threadIdx.x < 128 && cc < C) stats_finalize_channel(partial, g, cc, C, (double)rows, eps, mean, rstd);
+  }
 }
 
 __global__ void stats_finalize_kernel(const double* __restrict__ partial, int C, int64_t rows, float eps,
@@ -240,20 +278,23 @@ __global__ void stats_finalize_kernel(const double* __restrict__ partial, int C,
 
 template <typename T>
 static int channel_stats_impl(const T* x, int ld, int groups, int64_t rows, int C, float eps, double* partial,
-                              float* mean, float* rstd, cudaStream_t st) {
+                              float* mean, float* rstd, unsigned int* counters, cudaStream_t st) {
   MSR_REQUIRE(x && partial && mean && rstd && groups > 0 && rows > 0 && C > 0, "channel_stats: bad arguments");
   MSR_REQUIRE(C % 4 == 0 && ld % 4 == 0, "channel_stats: channel count and pitch must be multiples of 4");
-  ProfileScope prof(MSR_PROF_STATS, st, (double)groups * rows * C * sizeof(T), 2);
-  stats_partial_kernel<T><<<dim3(ceil_div(C, 128), kStatSplit, groups), 256, 0, st>>>(x, ld, rows, C, partial);
+  ProfileScope prof(MSR_PROF_STATS, st, (double)groups * rows * C * sizeof(T), counters ? 1 : 2);
+  stats_partial_kernel<T><<<dim3(ceil_div(C, 128), kStatSplit, groups), 256, 0, st>>>(x, ld, rows, C, partial, counters,
+                                                                                      eps, mean, rstd);
   MSR_LAUNCH_CHECK();
-  stats_finalize_kernel<<<dim3(ceil_div(C, 128), groups), 128, 0, st>>>(partial, C, rows, eps, mean, rstd);
-  MSR_LAUNCH_CHECK();
-  count_launch(2);
+  if (counters == nullptr) {
+    stats_finalize_kernel<<<dim3(ceil_div(C, 128), groups), 128, 0, st>>>(partial, C, rows, eps, mean, rstd);
+    MSR_LAUNCH_CHECK();
+  }
+  count_launch(counters ? 1 : 2);
   return MSR_OK;
 }
 int channel_stats_f32(const float* x, int ld, int groups, int64_t rows, int C, float eps, double* partial, float* mean,
-                      float* rstd, cudaStream_t st) {
-  return channel_stats_impl<float>(x, ld, groups, rows, C, eps, partial, mean, rstd, st);
+                      float* rstd, cudaStream_t st, unsigned int* counters) {
+  return channel_stats_impl<float>(x, ld, groups, rows, C, eps, partial, mean, rstd, counters, st);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -359,18 +400,25 @@ int sampler_f32(const float* mean, const float* var, const float* eps, float* la
 }
 
 __global__ void sampler_strided_kernel(const float* __restrict__ mv, int ld, const float* __restrict__ eps,
-                                       float* __restrict__ latent, int n, int L) {
+                                       float* __restrict__ latent, int n, int L, __nv_bfloat16* __restrict__ split) {
   const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (e >= (int64_t)n * L) return;
   const int row = (int)(e / L), c = (int)(e % L);
   const float m = mv[(int64_t)row * ld + c], v = mv[(int64_t)row * ld + L + c];
-  latent[e] = eps ? m + expf(0.5f * v) * eps[e] : m + v;
+  const float z = eps ? m + expf(0.5f * v) * eps[e] : m + v;
+  latent[e] = z;
+  if (split) {   // split-bf16 operand of the tensor-core dense layer: row = hi (L) | lo (L)
+    const __nv_bfloat16 hi = __float2bfloat16_rn(z);
+    split[(int64_t)row * 2 * L + c] = hi;
+    split[(int64_t)row * 2 * L + L + c] = __float2bfloat16_rn(z - __bfloat162float(hi));
+  }
 }
 
-int sampler_strided_f32(const float* mv, int ld, const float* eps, float* latent, int n, int L, cudaStream_t st) {
+int sampler_strided_f32(const float* mv, int ld, const float* eps, float* latent, int n, int L, cudaStream_t st,
+                        __nv_bfloat16* split_out) {
   MSR_REQUIRE(mv && latent && n > 0 && L > 0 && ld >= 2 * L, "sampler: bad arguments");
   ProfileScope prof(MSR_PROF_ELEMWISE, st, (double)n * L * 16.0);
-  sampler_strided_kernel<<<ceil_div((int64_t)n * L, 256), 256, 0, st>>>(mv, ld, eps, latent, n, L);
+  sampler_strided_kernel<<<ceil_div((int64_t)n * L, 256), 256, 0, st>>>(mv, ld, eps, latent, n, L, split_out);
   count_launch();
   MSR_LAUNCH_CHECK();
   return MSR_OK;
