@@ -24,6 +24,15 @@ Checkpoint keys follow Keras' object graph: ``layer_with_weights-<k>/<attribute 
 k counting the weighted layers of ``model.layers`` in construction order, attribute names as written in the
 reference's layer classes (blocks.py:17-26, spade.py:9-11).  ``load_gaugan_weights`` maps them onto this package's
 tensor names (weights.py) and checks every shape.
+
+Which key is which tensor is decided from the bundle's own object graph when it is there: the string tensor
+``_CHECKPOINTABLE_OBJECT_GRAPH`` holds a serialized ``TrackableObjectGraph`` (tensorflow/core/protobuf/
+trackable_object_graph.proto: nodes[] with children {node_id, local_name} and attributes {name, full_name,
+checkpoint_key}).  ``resolve_generator_keys`` / ``resolve_encoder_keys`` walk it from the root: a weighted layer is a
+ResidualBlock when it has the children ``spade_1`` / ``conv_1`` (blocks.py:17-20), a Sequential encoder block when it has
+its own ``layer_with_weights-0``, and the two same-shaped Dense heads are told apart by the variables' ``full_name``
+(``mean/kernel`` vs ``variance/kernel``, networks.py:32-33) -- not by their position.  Only when the bundle carries no
+object graph do the positional maps below (``generator_key_map`` / ``encoder_key_map``) apply.
 """
 from __future__ import annotations
 
@@ -292,7 +301,171 @@ def read_saved_model_variables(directory: str, **kw) -> Dict[str, np.ndarray]:
 
 
 # ----------------------------------------------------------------------------------------------------------------------
-# object-graph keys -> this package's tensor names
+# object graph (trackable_object_graph.proto)
+# ----------------------------------------------------------------------------------------------------------------------
+OBJECT_GRAPH_KEY = "_CHECKPOINTABLE_OBJECT_GRAPH"
+_BOOKKEEPING = {"keras_api", "variables", "trainable_variables", "non_trainable_variables", "regularization_losses",
+                "layers", "signatures", "metrics", "layer_metrics", "layer_regularization_losses", "optimizer",
+                "non_trainable_variables", "call_and_return_all_conditional_losses", "__call__", "_default_save_signature"}
+
+
+def _string_tensor(raw: bytes, count: int) -> List[bytes]:
+    """tensor_bundle.cc WriteStringTensor: [varint64 length] * count, 4-byte checksum of the lengths, then the bytes."""
+    pos, lengths = 0, []
+    for _ in range(count):
+        n, pos = _varint(raw, pos)
+        lengths.append(n)
+    pos += 4
+    out = []
+    for n in lengths:
+        if pos + n > len(raw):
+            raise BundleError("string tensor shorter than its lengths say")
+        out.append(bytes(raw[pos:pos + n]))
+        pos += n
+    return out
+
+
+def read_object_graph(prefix: str):
+    """The TrackableObjectGraph of a bundle as a list of nodes ``{"children": {local_name: node_id}, "attributes":
+    [{"name", "full_name", "checkpoint_key"}]}`` (node 0 = the saved object), or None when the bundle has none."""
+    index_path = prefix + ".index"
+    if not os.path.exists(index_path):
+        raise BundleError(f"{index_path} does not exist")
+    with open(index_path, "rb") as f:
+        pairs = read_table(f.read(), True)
+    num_shards, entry = 1, None
+    for key, value in pairs:
+        if key == b"":
+            for field, _, v in _proto_fields(value):
+                if field == 1:
+                    num_shards = v
+        elif key == OBJECT_GRAPH_KEY.encode():
+            entry = _parse_entry(value)
+    if entry is None or entry["dtype"] != 7:
+        return None
+    path = "%s.data-%05d-of-%05d" % (prefix, entry["shard"], num_shards)
+    if not os.path.exists(path):
+        return None
+    with open(path, "rb") as f:
+        f.seek(entry["offset"])
+        raw = f.read(entry["size"])
+    try:
+        blob = _string_tensor(raw, 1)[0]
+        nodes = []
+        for field, wt, v in _proto_fields(blob):
+            if field != 1 or wt != 2:
+                continue
+            node = {"children": {}, "attributes": []}
+            for f2, w2, v2 in _proto_fields(v):
+                if f2 == 1 and w2 == 2:
+                    ref = {"node_id": 0, "local_name": ""}
+                    for f3, _, v3 in _proto_fields(v2):
+                        if f3 == 1:
+                            ref["node_id"] = v3
+                        elif f3 == 2:
+                            ref["local_name"] = v3.decode("utf-8", "replace")
+                    node["children"][ref["local_name"]] = ref["node_id"]
+                elif f2 == 2 and w2 == 2:
+                    att = {"name": "", "full_name": "", "checkpoint_key": ""}
+                    for f3, _, v3 in _proto_fields(v2):
+                        if f3 in (1, 2, 3) and isinstance(v3, (bytes, bytearray)):
+                            att[("name", "full_name", "checkpoint_key")[f3 - 1]] = v3.decode("utf-8", "replace")
+                    node["attributes"].append(att)
+            nodes.append(node)
+    except (BundleError, struct.error, IndexError):
+        return None
+    return nodes or None
+
+
+def _weighted_children(nodes, node_id: int) -> List[Tuple[int, int]]:
+    """[(k, node_id)] of the ``layer_with_weights-k`` children of a node, by k."""
+    out = []
+    for name, nid in nodes[node_id]["children"].items():
+        m = re.fullmatch(r"layer_with_weights-(\d+)", name)
+        if m and 0 <= nid < len(nodes):
+            out.append((int(m.group(1)), nid))
+    return sorted(out)
+
+
+def _variable_leaves(nodes, node_id: int, prefix: str = "", seen=None) -> Dict[str, Tuple[str, str]]:
+    """attribute path below a node -> (checkpoint key without the .ATTRIBUTES suffix, variable full_name)."""
+    seen = set() if seen is None else seen
+    out: Dict[str, Tuple[str, str]] = {}
+    if node_id in seen:
+        return out
+    seen.add(node_id)
+    for att in nodes[node_id]["attributes"]:
+        if att["name"] == "VARIABLE_VALUE" and att["checkpoint_key"].endswith(SUFFIX):
+            out[prefix.rstrip("/")] = (att["checkpoint_key"][:-len(SUFFIX)], att["full_name"])
+    for name, nid in nodes[node_id]["children"].items():
+        if name in _BOOKKEEPING or name.startswith("layer-") or name.startswith("_") or not (0 <= nid < len(nodes)):
+            continue
+        out.update(_variable_leaves(nodes, nid, prefix + name + "/", seen))
+    return out
+
+
+def resolve_generator_keys(nodes, found: Dict[str, np.ndarray]) -> Dict[str, str]:
+    """checkpoint key -> weights.py name for build_generator (networks.py:37-57), from the object graph: ResidualBlocks
+    by their attribute children (blocks.py:17-26) in layer order, the Dense by its rank-2 kernel, the output Conv2D by
+    its rank-4 kernel."""
+    m: Dict[str, str] = {}
+    rb = 0
+    for _, nid in _weighted_children(nodes, 0):
+        kids = nodes[nid]["children"]
+        leaves = _variable_leaves(nodes, nid)
+        if "spade_1" in kids and "conv_1" in kids:
+            rb += 1
+            for path, (key, _) in leaves.items():
+                m[key] = f"gen.rb{rb}." + path.replace("/", ".")
+        elif "kernel" in leaves:
+            rank = found[leaves["kernel"][0]].ndim if leaves["kernel"][0] in found else 0
+            pre = "gen.dense" if rank == 2 else "gen.out" if rank == 4 else None
+            if pre is None:
+                raise BundleError("generator: a weighted layer is neither Dense, ResidualBlock nor Conv2D")
+            for leaf in ("kernel", "bias"):
+                if leaf in leaves:
+                    m[leaves[leaf][0]] = f"{pre}.{leaf}"
+    if rb != len(W.RB_FILTERS):
+        raise BundleError(f"generator: the object graph holds {rb} ResidualBlocks, expected {len(W.RB_FILTERS)}")
+    return m
+
+
+def resolve_encoder_keys(nodes, found: Dict[str, np.ndarray]) -> Dict[str, str]:
+    """checkpoint key -> weights.py name for build_encoder (networks.py:8-34): Sequential blocks in layer order
+    (Conv2D kernel, then gamma / beta of the InstanceNormalization), Dense heads by variable name (``mean`` /
+    ``variance``, networks.py:32-33) and only if the names are absent by order."""
+    m: Dict[str, str] = {}
+    block, heads = 0, []
+    for _, nid in _weighted_children(nodes, 0):
+        inner = _weighted_children(nodes, nid)
+        if inner:
+            block += 1
+            for j, (_, sub) in enumerate(inner):
+                for path, (key, _) in _variable_leaves(nodes, sub).items():
+                    if path == "kernel":
+                        m[key] = f"enc.down{block}.kernel"
+                    elif path in ("gamma", "beta"):
+                        m[key] = f"enc.down{block}.in_{path}"
+        else:
+            leaves = _variable_leaves(nodes, nid)
+            if "kernel" in leaves:
+                heads.append(leaves)
+    if len(heads) != 2:
+        raise BundleError(f"encoder: expected the two Dense heads, found {len(heads)}")
+    names = [h["kernel"][1].split("/")[0].split(":")[0] for h in heads]
+    if sorted(names) == ["mean", "variance"]:
+        order = names
+    else:                                   # unnamed variables: construction order (mean first, networks.py:32-33)
+        order = ["mean", "variance"]
+    for head, leaves in zip(order, heads):
+        for leaf in ("kernel", "bias"):
+            if leaf in leaves:
+                m[leaves[leaf][0]] = f"enc.{head}.{leaf}"
+    return m
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# positional keys -> this package's tensor names (bundles without an object graph)
 # ----------------------------------------------------------------------------------------------------------------------
 def generator_key_map(image_size: int) -> Dict[str, str]:
     """checkpoint key -> weights.py name for build_generator (networks.py:37-57): weighted layers in construction order
@@ -345,8 +518,20 @@ def load_gaugan_weights(generator_dir: str, encoder_dir: str, image_size: int, a
                         **kw) -> Dict[str, np.ndarray]:
     """The Keras-layout weight dict of weights.model_spec(arch, image_size) from the two SavedModel directories the
     reference writes; every tensor is checked against the spec's shape."""
-    gen = _map_variables(read_saved_model_variables(generator_dir, **kw), generator_key_map(image_size), "generator")
-    enc = _map_variables(read_saved_model_variables(encoder_dir, **kw), encoder_key_map(), "encoder")
+    def load(directory, resolve, positional, what):
+        found = read_saved_model_variables(directory, **kw)
+        nodes = read_object_graph(os.path.join(directory, "variables", "variables"))
+        key_map = None
+        if nodes is not None:
+            resolved = resolve(nodes, found)
+            if sorted(resolved.values()) == sorted(positional.values()):   # every tensor of the spec located by name
+                key_map = resolved
+        if key_map is None:
+            key_map = positional
+        inverse = {name: key for key, name in key_map.items()}
+        return _map_variables(found, {inverse[name]: name for name in positional.values()}, what)
+    gen = load(generator_dir, resolve_generator_keys, generator_key_map(image_size), "generator")
+    enc = load(encoder_dir, resolve_encoder_keys, encoder_key_map(), "encoder")
     gen.update(enc)
     W.check_weights(arch, image_size, gen)
     return gen

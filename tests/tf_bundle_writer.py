@@ -145,8 +145,9 @@ def entry_proto(dtype: int, shape, offset: int, size: int, crc: int) -> bytes:
     return out
 
 
-def write_bundle(prefix: str, tensors: dict, compress=False, with_crc=False, extra_string_keys=()):
-    """tensors: checkpoint key -> float32 ndarray."""
+def write_bundle(prefix: str, tensors: dict, compress=False, with_crc=False, extra_string_keys=(), string_tensors=None):
+    """tensors: checkpoint key -> float32 ndarray; string_tensors: key -> bytes (scalar DT_STRING tensors in
+    tensor_bundle.cc's layout: varint64 length, 4-byte masked CRC-32C of the lengths, the bytes)."""
     os.makedirs(os.path.dirname(prefix), exist_ok=True)
     pairs = [(b"", _field(1, 0, varint(1)) + _field(3, 2, varint(2) + _field(1, 0, varint(1))))]   # header: 1 shard
     offset = 0
@@ -158,10 +159,15 @@ def write_bundle(prefix: str, tensors: dict, compress=False, with_crc=False, ext
             crc = mask(crc32c(raw)) if with_crc else 0
             pairs.append((key.encode(), entry_proto(1, a.shape, offset, len(raw), crc)))
             offset += len(raw)
-        for key in extra_string_keys:                       # e.g. _CHECKPOINTABLE_OBJECT_GRAPH: DT_STRING = 7, skipped by readers
+        for key in extra_string_keys:                       # a DT_STRING (= 7) entry with an unreadable payload
             data.write(b"\x03abc")
             pairs.append((key.encode(), entry_proto(7, (), offset, 4, 0)))
             offset += 4
+        for key, blob in (string_tensors or {}).items():
+            raw = varint(len(blob)) + struct.pack("<I", mask(crc32c(struct.pack("<Q", len(blob))))) + blob
+            data.write(raw)
+            pairs.append((key.encode(), entry_proto(7, (), offset, len(raw), 0)))
+            offset += len(raw)
     pairs.sort(key=lambda kv: kv[0])
     write_table(prefix + ".index", pairs, compress=compress)
 
@@ -204,11 +210,81 @@ def keras_encoder_keys(weights: dict) -> dict:
     return out
 
 
-def write_gaugan_saved_models(root: str, weights: dict, compress=False):
-    """<root>/generator and <root>/encoder as Keras SavedModel directories (variables only + a stub saved_model.pb)."""
-    for sub, keys in (("generator", keras_generator_keys(weights)), ("encoder", keras_encoder_keys(weights))):
+def object_graph_proto(keys: dict, full_names: dict = None) -> bytes:
+    """A serialized TrackableObjectGraph (tensorflow/core/protobuf/trackable_object_graph.proto) for the checkpoint keys
+    ``a/b/c/.ATTRIBUTES/VARIABLE_VALUE``: one node per path component, children {node_id, local_name}, the variable
+    nodes carry attributes {name: VARIABLE_VALUE, full_name, checkpoint_key}.  Every non-leaf node also gets the
+    bookkeeping children Keras adds (``keras_api``, ``variables`` -> a list node that points back at the variables), so
+    that a reader has to skip them."""
+    nodes = [{"children": {}, "attributes": []}]
+
+    def child(parent, name):
+        kids = nodes[parent]["children"]
+        if name not in kids:
+            nodes.append({"children": {}, "attributes": []})
+            kids[name] = len(nodes) - 1
+        return kids[name]
+    for key in sorted(keys):
+        assert key.endswith(SUFFIX)
+        node = 0
+        for part in key[:-len(SUFFIX)].split("/"):
+            node = child(node, part)
+        full = (full_names or {}).get(key, key[:-len(SUFFIX)].replace("layer_with_weights-", "layer_"))
+        nodes[node]["attributes"].append(("VARIABLE_VALUE", full, key))
+    for nid in range(len(nodes)):
+        if nodes[nid]["children"] and not nodes[nid]["attributes"]:
+            variables = [c for c in nodes[nid]["children"].values()]
+            nodes.append({"children": {}, "attributes": []})                   # keras_api
+            nodes[nid]["children"]["keras_api"] = len(nodes) - 1
+            nodes.append({"children": {str(j): c for j, c in enumerate(variables)}, "attributes": []})   # list wrapper
+            nodes[nid]["children"]["variables"] = len(nodes) - 1
+    out = b""
+    for node in nodes:
+        body = b""
+        for name, nid in node["children"].items():
+            ref = _field(1, 0, varint(nid)) + _field(2, 2, varint(len(name.encode())) + name.encode())
+            body += _field(1, 2, varint(len(ref)) + ref)
+        for name, full, ckpt in node["attributes"]:
+            st = b"".join(_field(k, 2, varint(len(v.encode())) + v.encode()) for k, v in ((1, name), (2, full), (3, ckpt)))
+            body += _field(2, 2, varint(len(st)) + st)
+        out += _field(1, 2, varint(len(body)) + body)
+    return out
+
+
+def write_gaugan_saved_models(root: str, weights: dict, compress=False, object_graph=False, swap_heads=False,
+                              shift_generator_layers=0):
+    """<root>/generator and <root>/encoder as Keras SavedModel directories (variables only + a stub saved_model.pb).
+    ``object_graph``: also store the TrackableObjectGraph.  ``swap_heads``: the encoder's Dense heads are numbered the
+    other way round (variance = layer_with_weights-5, mean = -6) and ``shift_generator_layers`` renumbers the
+    generator's weighted layers -- both legal in a checkpoint whose object graph names the variables, both fatal for a
+    reader that goes by position."""
+    gen_keys, enc_keys = keras_generator_keys(weights), keras_encoder_keys(weights)
+    full_names = {}
+    if swap_heads:
+        swapped = {}
+        for key, a in enc_keys.items():
+            if key.startswith("layer_with_weights-5/"):
+                key = key.replace("layer_with_weights-5/", "layer_with_weights-6/")
+            elif key.startswith("layer_with_weights-6/"):
+                key = key.replace("layer_with_weights-6/", "layer_with_weights-5/")
+            swapped[key] = a
+        enc_keys = swapped
+    for key in enc_keys:
+        k = int(key.split("/")[0].split("-")[1])
+        if k >= 5:
+            head = ("mean", "variance")[(k - 5) ^ (1 if swap_heads else 0)]
+            full_names[key] = head + "/" + key.split("/")[1]
+    if shift_generator_layers:
+        import re as _re
+        gen_keys = {_re.sub(r"^layer_with_weights-(\d+)", lambda m: "layer_with_weights-%d" %
+                            (int(m.group(1)) + shift_generator_layers), k): a for k, a in gen_keys.items()}
+    for sub, keys in (("generator", gen_keys), ("encoder", enc_keys)):
         d = os.path.join(root, sub)
-        write_bundle(os.path.join(d, "variables", "variables"), keys, compress=compress,
-                     extra_string_keys=("_CHECKPOINTABLE_OBJECT_GRAPH",))
+        if object_graph:
+            write_bundle(os.path.join(d, "variables", "variables"), keys, compress=compress,
+                         string_tensors={"_CHECKPOINTABLE_OBJECT_GRAPH": object_graph_proto(keys, full_names)})
+        else:
+            write_bundle(os.path.join(d, "variables", "variables"), keys, compress=compress,
+                         extra_string_keys=("_CHECKPOINTABLE_OBJECT_GRAPH",))
         with open(os.path.join(d, "saved_model.pb"), "wb") as f:
             f.write(b"")

@@ -1,0 +1,61 @@
+"""One tensor-core layer of the generator in isolation (optimisation aid for ncu captures, not a bench).
+
+    python tools/one_layer.py mask   [n r]        # SPADE mask conv: K = 64 im2col GEMM -> relu -> bf16 (128 columns)
+    python tools/one_layer.py conv128 [n r]       # rb6.conv_1: 3x3, 256 -> 128, fp32 out
+    python tools/one_layer.py gb [n r]            # rb6.spade_1 gamma|beta conv with the fused SPADE epilogue (C = 256)
+Prints the CUDA-event time of the timed launches and the achieved TFLOP/s / GB/s.
+"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from moonsuperresolution_b200 import _lib
+
+kind = sys.argv[1] if len(sys.argv) > 1 else "mask"
+n = int(sys.argv[2]) if len(sys.argv) > 2 else 128
+r = int(sys.argv[3]) if len(sys.argv) > 3 else 256
+reps = int(sys.argv[4]) if len(sys.argv) > 4 else 3
+L = _lib.lib()
+st = _lib.stream_ptr()
+g = torch.Generator(device="cuda").manual_seed(0)
+
+
+def rnd(*shape, dtype=torch.bfloat16, scale=1.0):
+    return (torch.randn(shape, generator=g, device="cuda") * scale).to(dtype).contiguous()
+
+
+if kind == "mask":
+    x, w, b = rnd(n, r, r, 64), rnd(128, 64, scale=0.1), rnd(128, dtype=torch.float32)
+    y = torch.empty((n, r, r, 128), dtype=torch.bfloat16, device="cuda")
+    run = lambda: _lib.check(L.msr_op_conv_tc(x.data_ptr(), w.data_ptr(), b.data_ptr(), None, y.data_ptr(), n, r, 64, 128,
+                                              1, 1, 0, 1, 0.2, None, st), "mask")
+    flops, byts = 2.0 * n * r * r * 128 * 64, n * r * r * (128.0 + 256.0)
+elif kind == "conv128":
+    x, w, b = rnd(n, r, r, 256), rnd(128, 9 * 256, scale=0.02), rnd(128, dtype=torch.float32)
+    y = torch.empty((n, r, r, 128), dtype=torch.float32, device="cuda")
+    run = lambda: _lib.check(L.msr_op_conv3x3_bf16(x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), n, r, 256, 128,
+                                                   st), "conv128")
+    flops, byts = 2.0 * n * r * r * 128 * 9 * 256, n * r * r * (512.0 + 512.0)
+else:
+    C = 256
+    a, w, b = rnd(n, r, r, 128), rnd(2 * C, 1152, scale=0.03), rnd(2 * C, dtype=torch.float32)
+    xs = rnd(n, r // 2, r // 2, C, dtype=torch.float32)
+    mean, rstd = rnd(n // 16, C, dtype=torch.float32), torch.ones((n // 16, C), device="cuda")
+    y = torch.empty((n, r, r, C), dtype=torch.bfloat16, device="cuda")
+    run = lambda: _lib.check(L.msr_op_spade_tc(a.data_ptr(), w.data_ptr(), b.data_ptr(), xs.data_ptr(), 1, mean.data_ptr(),
+                                               rstd.data_ptr(), 16, y.data_ptr(), n, r, C, st), "gb")
+    flops, byts = 2.0 * n * r * r * 2 * C * 1152, n * r * r * (256.0 + 2 * C) + n * r * r / 4 * C * 4
+for _ in range(2):
+    run()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(reps):
+    run()
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / reps
+print(f"{kind} n={n} r={r}: {ms:.4f} ms  {flops / ms / 1e9:.1f} TFLOP/s  {byts / ms / 1e6:.1f} GB/s (algorithmic)")
