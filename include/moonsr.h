@@ -223,6 +223,20 @@ int msr_generator_finalize(msr_generator* g);
 int msr_generator_forward(msr_generator* g, const float* d_source, const float* d_eps, float* d_out, int n_groups,
                           void* stream);
 
+/* Repeated-sample mode (beyond the reference): the same n_groups * batch_size patches are generated
+ * several times with new sampler noise.  spade.py:19-20's gamma / beta convolutions, the mask convolution (spade.py:18)
+ * and the encoder (networks.py:8-34) depend only on d_source, so:
+ *   MSR_REPEAT_FIRST  computes them, stores gamma | beta of all 15 SPADE layers (bf16) and the encoder's mean | variance,
+ *                     and produces the first generation from the stored values;
+ *   MSR_REPEAT_NEXT   produces a further generation of the SAME d_source from the stored values: only the sampler, the
+ *                     dense layer, the modulation (spade.py:21-24) and the main convolutions (blocks.py:30-36) run;
+ *   MSR_REPEAT_NONE   = msr_generator_forward.
+ * FIRST and NEXT give bit-identical outputs for identical d_eps.  Models without the cache (fp32 mode, pix2pix) treat
+ * every phase as MSR_REPEAT_NONE. */
+enum { MSR_REPEAT_NONE = 0, MSR_REPEAT_FIRST = 1, MSR_REPEAT_NEXT = 2 };
+int msr_generator_forward_repeat(msr_generator* g, const float* d_source, const float* d_eps, float* d_out, int n_groups,
+                                 int repeat_phase, void* stream);
+
 /* Number of kernel launches issued by the last forward call (for bench.py's gpu_launches). */
 int64_t msr_generator_last_launch_count(const msr_generator* g);
 

@@ -18,6 +18,7 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "moonsr.h")
 MSR_OK = 0
 ARCH = {"spade": 0, "cnn": 1, "pix2pix": 2}
 PRECISION = {"fp32": 0, "bf16": 1}
+REPEAT_NONE, REPEAT_FIRST, REPEAT_NEXT = 0, 1, 2
 
 _vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 
@@ -50,6 +51,7 @@ SIGNATURES: Dict[str, tuple] = {
     "msr_generator_set_weight": (_i, [_vp, C.c_char_p, _vp, C.POINTER(_i64), _i]),
     "msr_generator_finalize": (_i, [_vp]),
     "msr_generator_forward": (_i, [_vp, _vp, _vp, _vp, _i, _vp]),
+    "msr_generator_forward_repeat": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
     "msr_generator_last_launch_count": (_i64, [_vp]),
     "msr_generator_device_bytes": (_i64, [_vp]),
     "msr_generator_read_activation": (_i, [_vp, C.c_char_p, _vp, _i64, C.POINTER(_i64)]),

@@ -114,7 +114,11 @@ struct msr_generator {
   float* st_mean[3] = {}; float* st_rstd[3] = {};   // stats of: x_prev, h1, (spare)
   float* a_f32 = nullptr; float* gb_f32 = nullptr; float* act_f32 = nullptr;      // fp32 mode
   __nv_bfloat16* a_bf16 = nullptr; __nv_bfloat16* act_bf16 = nullptr;               // bf16 mode
-  std::map<int, std::vector<ConvTC*>> plans;   // n_groups -> plans in launch order
+  std::map<int, std::vector<ConvTC*>> plans;   // (n_groups, repeat phase) -> plans in launch order
+  // repeated-sample mode: gamma | beta of the 15 SPADE layers for the batch being repeated (allocated on first use)
+  __nv_bfloat16* gb_cache[15] = {};
+  int64_t gb_cache_slots = 0;                  // patches the cache was allocated for
+  int gb_cache_valid_groups = 0;               // groups of the batch whose gamma | beta the cache currently holds
   // pix2pix workspace
   float* cat[7] = {}; float* d8 = nullptr; float* p2p_raw = nullptr;
   // pix2pix, bf16 tensor-core mode: weights [N][K] bf16, BatchNorm folded into per-channel scale / shift
@@ -625,6 +629,9 @@ struct Fwd {
   cudaStream_t st;
   int groups;
   int64_t N;
+  int phase = 0;        // MSR_REPEAT_*: 0 plain forward, 1 first generation of a repeated batch (fills the gamma | beta
+                        // cache), 2 further generation (encoder, mask convs and gamma | beta convs are reused)
+  int spade_index = 0;  // running index of the SPADE layer (cache slot)
   std::vector<ConvTC*>* plans = nullptr;
   size_t plan_cursor = 0;
   bool building = false;
@@ -772,6 +779,25 @@ int spade_bf16(Fwd& f, const SpadeW& s, const float* x, int x_shift, const float
   msr_generator* g = f.g;
   const int n = (int)f.N;
   int rc;
+  const int layer = f.spade_index++;
+  if (f.phase != MSR_REPEAT_NONE) {
+    // repeated-sample mode: gamma | beta (spade.py:19-20) depend only on the source -> computed once per batch
+    // (phase 1, raw bf16 columns into the cache), every generation modulates from the cache (spade.py:21-24)
+    __nv_bfloat16* cache = g->gb_cache[layer];
+    MSR_REQUIRE(cache != nullptr, "internal: gamma | beta cache not allocated");
+    if (f.phase == MSR_REPEAT_FIRST) {
+      ConvTCArgs m;
+      m.x = g->patches; m.w = s.conv_wt; m.n = n; m.r = r; m.cin = 64; m.ncols = kHidden; m.taps = 1; m.pad = 0;
+      m.epilogue = TC_EPI_ACT_BF16; m.bias = s.conv_b; m.act = ACT_RELU; m.out_bf16 = g->a_bf16;
+      m.alg_flops = 2.0 * (double)n * r * r * kHidden * 18;
+      if ((rc = tc_conv(f, m))) return rc;
+      ConvTCArgs a;
+      a.x = g->a_bf16; a.w = s.gb_wt; a.n = n; a.r = r; a.cin = kHidden; a.ncols = 2 * s.C;
+      a.epilogue = TC_EPI_ACT_BF16; a.bias = s.gb_bt; a.act = ACT_NONE; a.out_bf16 = cache;
+      if ((rc = tc_conv(f, a))) return rc;
+    }
+    return spade_modulate_cached_bf16(cache, x, x_shift, mean, rstd, g->act_bf16, n, r, s.C, g->B, 0.2f, f.st);
+  }
   // a = relu(conv3x3(resized mask)) as a K = 64 GEMM on the im2col'd source (spade.py:17-18)
   ConvTCArgs m;
   m.x = g->patches; m.w = s.conv_wt; m.n = n; m.r = r; m.cin = 64; m.ncols = kHidden; m.taps = 1; m.pad = 0;
@@ -812,7 +838,10 @@ int forward_spade_bf16(Fwd& f, const float* source, const float* eps, float* out
   const int I = g->I, sw = I / 64, n = (int)f.N;
   cudaStream_t st = f.st;
   int rc;
-  // ---- encoder (networks.py:8-34)
+  f.spade_index = 0;
+  const bool reuse = f.phase == MSR_REPEAT_NEXT;   // a further generation of the same batch: only the noise is new
+  // ---- encoder (networks.py:8-34); its mean | variance rows (lat_mv) are kept across the generations of a batch
+  if (!reuse) {
   // block 1: conv3x3 s2 (2 -> 64, no bias, no norm) + LeakyReLU(0.2) as an im2col GEMM
   if ((rc = source_patches_bf16(source, I, g->patches, n, I / 2, 1, st))) return rc;
   {
@@ -863,6 +892,7 @@ int forward_spade_bf16(Fwd& f, const float* source, const float* eps, float* out
       if ((rc = tc_conv(f, a))) return rc;
     }
   }
+  }  // !reuse
   // ---- sampler (sampling.py:11-17) or mean + variance (model.py:789-791); rows hold mean | variance
   if ((rc = sampler_strided_f32(g->lat_mv, 2 * kLatent, g->arch == MSR_ARCH_SPADE ? eps : nullptr, g->latent, n, kLatent,
                                 st, g->latent_split))) return rc;
@@ -882,7 +912,7 @@ int forward_spade_bf16(Fwd& f, const float* source, const float* eps, float* out
   for (int k = 0; k < 6; ++k) {
     const BlockW& b = g->rb[k];
     float* y = g->xbuf[(k + 1) & 1];
-    if ((rc = source_patches_bf16(source, I, g->patches, n, r, 0, st))) return rc;   // shared by the block's SPADEs
+    if (!reuse && (rc = source_patches_bf16(source, I, g->patches, n, r, 0, st))) return rc;   // shared by the block's SPADEs
     // x = conv_1(lrelu(spade_1(in)))                                  blocks.py:29-30
     if ((rc = spade_bf16(f, b.s1, x, x_shift, g->st_mean[0], g->st_rstd[0], r))) return rc;
     if ((rc = conv_bf16(f, b.c1, r, g->h1, nullptr, 0, g->st_mean[1], g->st_rstd[1]))) return rc;
@@ -1083,18 +1113,53 @@ extern "C" int msr_generator_finalize(msr_generator* g) {
   return MSR_OK;
 }
 
-extern "C" int msr_generator_forward(msr_generator* g, const float* d_source, const float* d_eps, float* d_out,
-                                     int n_groups, void* stream) {
+// gamma | beta cache of repeated-sample mode: one [n * r * r][2C] bf16 tensor per SPADE layer, in call order
+// (spade_1, spade_3 when the block has a learned skip, spade_2)
+static int ensure_gb_cache(msr_generator* g, int64_t n) {
+  if (g->gb_cache_slots >= n) return MSR_OK;
+  MSR_REQUIRE(g->gb_cache_slots == 0, "internal: gamma | beta cache cannot grow (it is sized for batch_size * max_groups)");
+  const int64_t N = (int64_t)g->B * g->maxG;
+  int layer = 0, r = g->I / 64, rc;
+  for (int k = 0; k < 6; ++k, r *= 2) {
+    const BlockW& b = g->rb[k];
+    const int chans[3] = {b.cin, b.learned ? b.cin : 0, b.cout};
+    for (int c : chans) {
+      if (c == 0) continue;
+      if ((rc = ws(g, &g->gb_cache[layer], N * r * r * 2 * c))) return rc;
+      ++layer;
+    }
+  }
+  g->gb_cache_slots = N;
+  return MSR_OK;
+}
+
+extern "C" int msr_generator_forward_repeat(msr_generator* g, const float* d_source, const float* d_eps, float* d_out,
+                                            int n_groups, int repeat_phase, void* stream) {
   MSR_REQUIRE(g && d_source && d_out, "msr_generator_forward: null pointer");
   if (!g->finalized) return fail(MSR_E_STATE, "forward before finalize");
   MSR_REQUIRE(n_groups >= 1 && n_groups <= g->maxG, "n_groups out of range");
+  MSR_REQUIRE(repeat_phase == MSR_REPEAT_NONE || repeat_phase == MSR_REPEAT_FIRST || repeat_phase == MSR_REPEAT_NEXT,
+              "repeat_phase must be MSR_REPEAT_NONE, _FIRST or _NEXT");
   if (g->arch == MSR_ARCH_SPADE) MSR_REQUIRE(d_eps, "GauGAN forward needs eps (sampling.py:13-16)");
   Fwd f;
   f.g = g; f.st = (cudaStream_t)stream; f.groups = n_groups; f.N = (int64_t)n_groups * g->B;
+  // only the bf16 SPADE graphs have the cache; every other model simply recomputes (same results as MSR_REPEAT_NONE)
+  const bool cached = g->precision == MSR_PRECISION_BF16 && g->arch != MSR_ARCH_PIX2PIX;
+  f.phase = cached ? repeat_phase : MSR_REPEAT_NONE;
+  if (f.phase != MSR_REPEAT_NONE) {
+    int rc = ensure_gb_cache(g, f.N);
+    if (rc) return rc;
+    if (f.phase == MSR_REPEAT_FIRST) g->gb_cache_valid_groups = n_groups;
+    else if (g->gb_cache_valid_groups != n_groups)
+      return fail(MSR_E_STATE, "MSR_REPEAT_NEXT without a preceding MSR_REPEAT_FIRST call of the same size");
+  } else if (cached) {
+    g->gb_cache_valid_groups = 0;   // a plain forward overwrites the encoder outputs the cache belongs to
+  }
   if (g->precision == MSR_PRECISION_BF16) {
-    auto it = g->plans.find(n_groups);
+    const int key = n_groups * 4 + f.phase;
+    auto it = g->plans.find(key);
     f.building = (it == g->plans.end());
-    f.plans = &g->plans[n_groups];
+    f.plans = &g->plans[key];
   }
   const int64_t before = g_launch_count;
   int rc = (g->arch == MSR_ARCH_PIX2PIX)          ? (g->precision == MSR_PRECISION_BF16 ? forward_pix2pix_bf16(f, d_source, d_out)
@@ -1104,9 +1169,14 @@ extern "C" int msr_generator_forward(msr_generator* g, const float* d_source, co
   g->last_launches = g_launch_count - before;
   if (rc && f.building) {  // never keep a half-built plan list
     for (auto* p : *f.plans) conv_tc_plan_destroy(p);
-    g->plans.erase(n_groups);
+    g->plans.erase(n_groups * 4 + f.phase);
   }
   return rc;
+}
+
+extern "C" int msr_generator_forward(msr_generator* g, const float* d_source, const float* d_eps, float* d_out,
+                                     int n_groups, void* stream) {
+  return msr_generator_forward_repeat(g, d_source, d_eps, d_out, n_groups, MSR_REPEAT_NONE, stream);
 }
 
 extern "C" int64_t msr_generator_last_launch_count(const msr_generator* g) { return g ? g->last_launches : -1; }

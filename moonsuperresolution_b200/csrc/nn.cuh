@@ -131,6 +131,11 @@ int affine_act_bf16out(const float* x, int ldx, const float* mean, const float* 
 // sum of the `planes` split-K partial planes [planes][M][N] (+ bias[N]) -> out[M][N]
 int dense_reduce_planes(const float* partial, const float* bias, float* out, int M, int N, int planes, cudaStream_t st);
 
+// SPADE modulation + LeakyReLU from cached gamma | beta columns (bf16, [n*r*r][2C], 64 gamma | 64 beta per channel block)
+int spade_modulate_cached_bf16(const __nv_bfloat16* gb, const float* x, int x_shift, const float* mean, const float* rstd,
+                               __nv_bfloat16* out, int n, int r, int C, int samples_per_group, float slope,
+                               cudaStream_t st);
+
 // statistics from the fused (sum, sumsq) pairs written by the tensor-core epilogue: pairs [groups*rows_p][C]
 int channel_stats_from_pairs(const float2* pairs, int groups, int64_t rows_p, int64_t count_per_group, int C, float eps,
                              double* partial, float* mean, float* rstd, cudaStream_t st,

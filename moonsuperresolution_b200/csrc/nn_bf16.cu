@@ -580,4 +580,71 @@ int channel_stats_from_pairs(const float2* pairs, int groups, int64_t rows_p, in
   return MSR_OK;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// SPADE modulation from CACHED gamma | beta (repeated-sample mode): spade.py:19-20's two
+// convolutions depend only on the source, so across the R generations of one batch they are computed once
+// (TC_EPI_ACT_BF16 epilogue, raw bf16 columns in the interleaved 64 gamma | 64 beta order) and every generation only
+// runs  act = lrelu(gamma * (x - mean) * rstd + beta)  (spade.py:21-24, blocks.py:30) -- HBM-bound: per pixel and 8
+// channels one 16-byte load each of gamma and beta, 32 bytes of x (shared by 4 pixels when x is stored at half
+// resolution), one 16-byte store.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) spade_modulate_cached_kernel(const __nv_bfloat16* __restrict__ gb,
+                                                                    const float* __restrict__ x, int x_shift,
+                                                                    const float* __restrict__ mean,
+                                                                    const float* __restrict__ rstd,
+                                                                    __nv_bfloat16* __restrict__ out, int n, int lr, int C,
+                                                                    int samples_per_group, float slope) {
+  const int c8n = C >> 3;                      // threads per pixel (C is a multiple of 64)
+  const int64_t total = ((int64_t)n << (2 * lr)) * c8n;
+  const int r = 1 << lr, rs = r >> x_shift;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e % c8n) * 8;          // c8n is small; 64-bit modulo by a 32-bit value only once per 8 channels
+    const int64_t m = e / c8n;
+    const int b = (int)(m >> (2 * lr));
+    const int rem = (int)(m & (((int64_t)1 << (2 * lr)) - 1));
+    const int h = rem >> lr, w = rem & (r - 1);
+    const int j = c >> 6, t = c & 63;          // channel block of 64: columns [128 j, 128 j + 64) gamma, then beta
+    const __nv_bfloat16* gp = gb + m * (2 * (int64_t)C) + 128 * j + t;
+    const uint4 gq = __ldcs(reinterpret_cast<const uint4*>(gp));
+    const uint4 bq = __ldcs(reinterpret_cast<const uint4*>(gp + 64));
+    const int64_t xr = ((int64_t)b * rs + (h >> x_shift)) * rs + (w >> x_shift);
+    const float4 x0 = __ldg(reinterpret_cast<const float4*>(x + xr * C + c));
+    const float4 x1 = __ldg(reinterpret_cast<const float4*>(x + xr * C + c + 4));
+    const int g = b / samples_per_group;
+    const float4 m0 = __ldg(reinterpret_cast<const float4*>(mean + (int64_t)g * C + c));
+    const float4 m1 = __ldg(reinterpret_cast<const float4*>(mean + (int64_t)g * C + c + 4));
+    const float4 r0 = __ldg(reinterpret_cast<const float4*>(rstd + (int64_t)g * C + c));
+    const float4 r1 = __ldg(reinterpret_cast<const float4*>(rstd + (int64_t)g * C + c + 4));
+    const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+    const float mu[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+    const float rsd[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+    const __nv_bfloat16* gv = reinterpret_cast<const __nv_bfloat16*>(&gq);
+    const __nv_bfloat16* bv = reinterpret_cast<const __nv_bfloat16*>(&bq);
+    __align__(16) __nv_bfloat16 o[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      float v = fmaf(__bfloat162float(gv[q]), (xv[q] - mu[q]) * rsd[q], __bfloat162float(bv[q]));
+      v = v > 0.f ? v : v * slope;
+      o[q] = __float2bfloat16_rn(v);
+    }
+    *reinterpret_cast<uint4*>(out + m * C + c) = *reinterpret_cast<const uint4*>(o);
+  }
+}
+
+int spade_modulate_cached_bf16(const __nv_bfloat16* gb, const float* x, int x_shift, const float* mean, const float* rstd,
+                               __nv_bfloat16* out, int n, int r, int C, int samples_per_group, float slope,
+                               cudaStream_t st) {
+  MSR_REQUIRE(gb && x && mean && rstd && out && n > 0 && r > 0 && (r & (r - 1)) == 0 && C % 64 == 0 &&
+                  samples_per_group > 0, "spade_modulate_cached: bad arguments");
+  int lr = 0;
+  while ((1 << lr) < r) ++lr;
+  const int64_t total = (int64_t)n * r * r * (C / 8);
+  ProfileScope prof(MSR_PROF_ELEMWISE, st, (double)n * r * r * C * (4.0 + 2.0 + 4.0 / (1 << (2 * x_shift))));
+  const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 16);
+  spade_modulate_cached_kernel<<<blocks, 256, 0, st>>>(gb, x, x_shift, mean, rstd, out, n, lr, C, samples_per_group, slope);
+  count_launch();
+  MSR_LAUNCH_CHECK();
+  return MSR_OK;
+}
+
 }  // namespace msr

@@ -106,9 +106,12 @@ class _Generator:
             raise ValueError(f"eps must be ({n}, {self.latent_dim})")
         return e
 
-    def forward_device(self, source, out, eps=None, n_groups: int = 1, stream=None) -> None:
+    def forward_device(self, source, out, eps=None, n_groups: int = 1, stream=None, repeat_phase: int = 0) -> None:
         """source (n_groups*B, I, I, 2) f32 CUDA, out (n_groups*B, I, I) f32 CUDA, eps (n_groups*B, 256) f32 CUDA or
-        None.  Each group of B samples has its own SPADE batch statistics (spade.py:21)."""
+        None.  Each group of B samples has its own SPADE batch statistics (spade.py:21).  ``repeat_phase``
+        (_lib.REPEAT_FIRST / REPEAT_NEXT): repeated-sample mode -- the first generation of a batch stores the encoder
+        outputs and every SPADE layer's gamma | beta, further generations of the same ``source`` reuse them (include/
+        moonsr.h, msr_generator_forward_repeat)."""
         if not self._finalized:
             raise _lib.MoonSRError("model has no weights: call set_weights / load first")
         torch = _torch()
@@ -126,8 +129,9 @@ class _Generator:
         else:
             eps = None
         self._calls += 1
-        _lib.check(self._lib.msr_generator_forward(self._handle, source.data_ptr(), _lib.ptr(eps), out.data_ptr(),
-                                                   n_groups, _lib.stream_ptr(stream)), "msr_generator_forward")
+        _lib.check(self._lib.msr_generator_forward_repeat(self._handle, source.data_ptr(), _lib.ptr(eps), out.data_ptr(),
+                                                          n_groups, int(repeat_phase), _lib.stream_ptr(stream)),
+                   "msr_generator_forward")
 
     def __call__(self, x, training=False, eps=None):
         """Reference plug-in signature (process_full_tiles.py:338).  ``x`` (B, I, I, 2), any float dtype (the
@@ -191,7 +195,7 @@ class IdentityModel:
     def __call__(self, x, training=False):
         return x
 
-    def forward_device(self, source, out, eps=None, n_groups: int = 1, stream=None) -> None:
+    def forward_device(self, source, out, eps=None, n_groups: int = 1, stream=None, repeat_phase: int = 0) -> None:
         out.view(source.shape[0], self.image_size, self.image_size).copy_(source[..., 1])
 
 

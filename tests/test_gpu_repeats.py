@@ -142,3 +142,72 @@ def test_dedup_repeats_across_ranks(msr, world):
     g = ref[2].astype(bool)
     np.testing.assert_array_equal(single[2], ref[2])
     assert np.abs(single[0][g] - ref[0][g]).max() <= 1e-5 * np.abs(ref[0][g]).max()
+
+
+def test_spade_reuse_across_generations(msr, torch):
+    """Repeated-sample mode with the bf16 GauGAN: the first generation of a batch stores the encoder's mean | variance
+    and gamma | beta of all 15 SPADE layers (spade.py:18-20 depend only on the patch), the next ones reuse them
+    (msr_generator_forward_repeat).  FIRST and NEXT are the same arithmetic, so identical noise gives identical
+    output; against the plain forward the only difference is the bf16 rounding of the stored gamma | beta, which must
+    stay far inside north_star's bf16 bar when measured against the oracle."""
+    from moonsuperresolution_b200 import _lib
+    from moonsuperresolution_b200 import weights as W
+    from oracle import generator as OG
+    i, b, groups = 128, 4, 2
+    w = W.random_init("spade", i, seed=31, perturb_affine=True)
+    rng = np.random.default_rng(2)
+    x = rng.uniform(-0.5, 0.5, (groups * b, i, i, 2)).astype(np.float32)
+    x[-1] = 0.0
+    eps = rng.standard_normal((3, groups * b, 256)).astype(np.float32)
+    model = msr.GauGAN(i, b, precision="bf16", weights=w, max_groups=groups)
+    src = torch.from_numpy(x).cuda()
+    d_eps = torch.from_numpy(eps).cuda()
+    out = {k: torch.empty((groups * b, i, i), device="cuda") for k in ("plain0", "first0", "next0", "next1", "plain1")}
+    model.forward_device(src, out["plain0"], d_eps[0], groups)
+    model.forward_device(src, out["first0"], d_eps[0], groups, repeat_phase=_lib.REPEAT_FIRST)
+    n_first = model.last_launch_count
+    model.forward_device(src, out["next1"], d_eps[1], groups, repeat_phase=_lib.REPEAT_NEXT)
+    n_next = model.last_launch_count
+    model.forward_device(src, out["next0"], d_eps[0], groups, repeat_phase=_lib.REPEAT_NEXT)
+    model.forward_device(src, out["plain1"], d_eps[1], groups)
+    torch.cuda.synchronize()
+    assert torch.equal(out["first0"], out["next0"])                    # reuse changes nothing
+    assert n_next < n_first - 30                                        # encoder + 15 x (mask conv, gamma | beta conv) gone
+    for g in range(groups):
+        sl = slice(g * b, (g + 1) * b)
+        for k, e in (("first0", 0), ("next1", 1)):
+            want = OG.gaugan_call(x[sl], w, eps[e, sl], "spade")[..., 0]
+            err = np.abs(out[k][sl].cpu().numpy() - want).max() / max(1.0, np.abs(want).max())
+            assert err <= 1e-2, (k, g, err)
+    assert (out["plain0"] - out["first0"]).abs().max().item() <= 1e-2
+    assert (out["plain1"] - out["next1"]).abs().max().item() <= 1e-2
+    # a NEXT call without its FIRST is refused
+    model.forward_device(src, out["plain0"], d_eps[0], groups)
+    with pytest.raises(_lib.MoonSRError):
+        model.forward_device(src, out["next0"], d_eps[0], groups, repeat_phase=_lib.REPEAT_NEXT)
+
+
+def test_repeated_sample_engine_with_and_without_reuse(msr):
+    """DSRConfig(samples_per_patch=3) with the bf16 GauGAN, reuse on (default) and off: same `good`, mean / std within
+    the bf16 budget of each other (the stored gamma | beta are bf16), and fewer generator launches with reuse."""
+    from moonsuperresolution_b200 import weights as W
+    i, s, b, t = 64, 32, 4, 128
+    rng = np.random.default_rng(5)
+    h, w_ = 150, 170
+    dem = np.cumsum(np.cumsum(rng.standard_normal((h, w_)), 0), 1).astype(np.float32)
+    img = rng.uniform(1, 255, (h, w_)).astype(np.float32)
+    weights = W.random_init("spade", i, seed=3, perturb_affine=True)
+    model = msr.GauGAN(i, b, precision="bf16", weights=weights, max_groups=2)
+    res, launches = {}, {}
+    for reuse in (True, False):
+        cfg = msr.DSRConfig(image_size=i, stride=s, batch_size=b, tile_size=t, samples_per_patch=3, seed=9,
+                            reuse_spade=reuse)
+        eng = msr.DEMSuperResolution(cfg, model=model)
+        res[reuse] = eng.run(dem, img)
+        launches[reuse] = eng.model_launches
+    np.testing.assert_array_equal(res[True][2], res[False][2])
+    g = res[True][2].astype(bool)
+    scale = float(dem.max() - dem.min())
+    assert np.abs(res[True][0][g] - res[False][0][g]).max() / scale <= 1e-2
+    assert np.abs(res[True][1][g] - res[False][1][g]).max() / scale <= 1e-2
+    assert res[True][1][g].max() > 0 and launches[True] < launches[False]
