@@ -307,12 +307,12 @@ def multi_gpu_check(torch, dist, args, model, rank, world, dev):
 
 
 def time_config(torch, dist, name, arch, image_size, stride, batch, tile, h, w, mode, model, rank, world, dev, groups,
-                warm=True):
+                warm=True, **cfg_kw):
     """One timed step of another BASELINE.json configuration (device-resident synthetic rasters, sharded like the
     headline run when world > 1); CUDA events, max over ranks."""
     from moonsuperresolution_b200 import DEMSuperResolution, DSRConfig
     cfg = DSRConfig(image_size=image_size, stride=stride, batch_size=batch, tile_size=tile, groups_per_call=groups,
-                    mode=mode)
+                    mode=mode, **cfg_kw)
     eng = DEMSuperResolution(cfg, model=model, rank=rank, world_size=world, device=dev)
     if world > 1:
         o0, o1 = eng.ownedRows(h, w)
@@ -363,7 +363,7 @@ def run_extras(torch, dist, args, weights, rank, world, dev):
     from moonsuperresolution_b200 import weights as W
     want = args.extras
     if want == "auto":
-        want = {1: "cfg1,cfg2,fp32", 2: "cfg4", 4: "cfg4", 8: "cfg4,cfg5"}.get(world, "")
+        want = {1: "cfg1,cfg2,fp32,repeat4", 2: "cfg4", 4: "cfg4", 8: "cfg4,cfg5"}.get(world, "")
     names = [x for x in want.split(",") if x and x != "none"]
     out = {}
     for name in names:
@@ -406,6 +406,25 @@ def run_extras(torch, dist, args, weights, rank, world, dev):
                 for mode in ("faithful", "dedup"):
                     res[mode] = time_config(torch, dist, label + ", stride 128, batch 16, tile 1024", arch, 512, 128,
                                             16, 1024, hh, ww, mode, m, rank, world, dev, args.groups, warm=False)
+                out[name] = res
+                m.close()
+            elif name == "repeat4":   # repeated-sample mode: 4 generations per patch position, with and
+                                      # without reusing the noise-independent half of the graph across generations
+                cls = {"spade": M.GauGAN, "cnn": M.CNNSpade}.get(args.arch)
+                if cls is None or world > 1 or args.precision != "bf16":
+                    continue
+                m = cls(args.image_size, args.batch_size, precision="bf16", weights=weights, max_groups=args.groups)
+                side = 4 * args.image_size
+                res = {}
+                for reuse in (False, True):
+                    res["reuse" if reuse else "recompute"] = time_config(
+                        torch, dist, f"{args.arch}-{args.image_size}, {side}x{side}, samples_per_patch=4", args.arch,
+                        args.image_size, args.stride, args.batch_size, args.tile_size, side, side, "faithful", m, rank,
+                        world, dev, args.groups, warm=True, samples_per_patch=4, reuse_spade=reuse)
+                res["speedup"] = res["recompute"]["seconds"] / res["reuse"]["seconds"]
+                res["bound"] = ("4 / (1 + 3 * (1 - f)) with f = share of a forward that does not depend on the noise "
+                                "(encoder + mask convs + gamma|beta convs, ~0.55 of the time): ~1.7x; the reuse pass reads "
+                                "305 MB of stored gamma|beta per patch instead of computing 352 GFLOP")
                 out[name] = res
                 m.close()
             elif name == "fp32":    # the parity mode has a number too: one 1024 x 1024 tile, fp32 CUDA-core generator
@@ -610,11 +629,39 @@ def main():
                      "rate": (v["work"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 else None}
                  for k, v in prof.items() if v["launches"]}
     hbm_kernels = {}
-    for fam in ("blend", "gather", "stats", "mask_conv", "final_conv"):
+    for fam in ("blend", "gather", "stats", "mask_conv", "elementwise", "pad"):
         v = prof[fam]
         if v["launches"] and v["ms"] > 0:
             gbs = v["work"] / (v["ms"] * 1e-3) / 1e9
             hbm_kernels[fam] = {"achieved_gbs": gbs, "frac_of_measured_hbm": gbs / pk["hbm"]}
+
+    # ---- the blend in its HBM-bound form (DSRConfig(blend="fast"): float32 update, 128-bit accesses), instrumented on a
+    # 2 x 2-tile raster in both modes; the headline step above runs the bit-exact blend (parity default)
+    if world == 1:
+        try:
+            side = 2 * args.tile_size
+            for mode_ in ("faithful", "dedup"):
+                if mode_ == "dedup" and args.tile_size % args.stride:
+                    continue
+                cfgf = DSRConfig(image_size=args.image_size, stride=args.stride, batch_size=args.batch_size,
+                                 tile_size=args.tile_size, groups_per_call=args.groups, mode=mode_, blend="fast")
+                engf = DEMSuperResolution(cfgf, model=model, device=dev)
+                f_dem, f_img = synth_rows(torch, 0, side, side, dev)
+                for k in range(2):
+                    if k == 1:
+                        _lib.profile_enable(True)
+                    engf.setRasters(f_dem, f_img)
+                    engf.padInputs()
+                    engf.processTiles()
+                pf = _lib.profile_read()["blend"]
+                _lib.profile_enable(False)
+                if pf["launches"] and pf["ms"] > 0:
+                    gbs = pf["work"] / (pf["ms"] * 1e-3) / 1e9
+                    hbm_kernels["blend_fast_" + mode_] = {"achieved_gbs": gbs, "frac_of_measured_hbm": gbs / pk["hbm"],
+                                                         "launches": pf["launches"], "ms": pf["ms"]}
+                del engf, f_dem, f_img
+        except Exception as ex:
+            hbm_kernels["blend_fast_error"] = str(ex)[:200]
 
     # ---- the same raster with one tile per band: tile_size is a free parameter of the reference (its tiles only bound
     # host RAM); with T = band size no halo patch is generated twice.  Reported beside the headline, not as it.
