@@ -636,10 +636,10 @@ def main():
             hbm_kernels[fam] = {"achieved_gbs": gbs, "frac_of_measured_hbm": gbs / pk["hbm"]}
 
     # ---- the blend in its HBM-bound form (DSRConfig(blend="fast"): float32 update, 128-bit accesses), instrumented on a
-    # 2 x 2-tile raster in both modes; the headline step above runs the bit-exact blend (parity default)
+    # 4 x 4-tile raster in both modes; the headline step above runs the bit-exact blend (parity default)
     if world == 1:
         try:
-            side = 2 * args.tile_size
+            side = 4 * args.tile_size          # 16 tiles, the 4 interior ones carry the full 121 patches
             for mode_ in ("faithful", "dedup"):
                 if mode_ == "dedup" and args.tile_size % args.stride:
                     continue

@@ -30,7 +30,11 @@ int conv_f32(const ConvF32& p, cudaStream_t st);
 // `partial` is scratch of groups * kStatSplit * C * 2 doubles.
 // `counters` (optional): groups * ceil(C / 64) zero-initialised uints; with them the second stage runs inside the same
 // launch (the last block of every channel block finalises), without them a second small kernel is launched.
-constexpr int kStatSplit = 64;
+constexpr int kStatSplit = 64;   // upper bound of the row splits (sizes the `partial` scratch)
+static inline int stat_splits(int64_t rows, int64_t rows_per_block) {
+  const int64_t s = (rows + rows_per_block - 1) / rows_per_block;
+  return (int)(s < 1 ? 1 : (s > kStatSplit ? kStatSplit : s));
+}
 int channel_stats_f32(const float* x, int ld, int groups, int64_t rows, int C, float eps, double* partial, float* mean,
                       float* rstd, cudaStream_t st, unsigned int* counters = nullptr);
 

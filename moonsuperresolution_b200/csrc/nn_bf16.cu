@@ -480,8 +480,8 @@ __global__ void __launch_bounds__(256) stats_pairs_partial_kernel(const float2* 
   // grid (ceil(C/64), kStatSplit, groups); block = 32 channel pairs x 8 row lanes; one 128-bit load = 2 (sum, sumsq) pairs
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int c = (blockIdx.x * 32 + cx) * 2;
-  const int split = blockIdx.y, g = blockIdx.z;
-  const int64_t per = (rows_p + kStatSplit - 1) / kStatSplit;
+  const int split = blockIdx.y, g = blockIdx.z, splits = gridDim.y;
+  const int64_t per = (rows_p + splits - 1) / splits;
   const int64_t r0 = split * per, r1 = min(rows_p, r0 + per);
   double s0 = 0.0, q0 = 0.0, s1 = 0.0, q1 = 0.0;
   if (c < C) {
@@ -508,7 +508,7 @@ __global__ void __launch_bounds__(256) stats_pairs_partial_kernel(const float2* 
       s1 += sh[2][k][cx];
       q1 += sh[3][k][cx];
     }
-    double* o = partial + (((int64_t)g * kStatSplit + split) * C + c) * 2;
+    double* o = partial + (((int64_t)g * splits + split) * C + c) * 2;
     o[0] = s0;
     o[1] = q0;
     o[2] = s1;
@@ -521,7 +521,7 @@ __global__ void __launch_bounds__(256) stats_pairs_partial_kernel(const float2* 
     if (threadIdx.x == 0) {
       const int slot = g * gridDim.x + blockIdx.x;
       const unsigned int prev = atomicAdd(counters + slot, 1u);
-      s_last = (prev == (unsigned int)(kStatSplit - 1));
+      s_last = (prev == gridDim.y - 1);
       if (s_last) counters[slot] = 0u;
     }
     __syncthreads();
@@ -530,10 +530,11 @@ __global__ void __launch_bounds__(256) stats_pairs_partial_kernel(const float2* 
       const int cc = blockIdx.x * 64 + threadIdx.x;
       if (threadIdx.x < 64 && cc < C) {
         double s = 0.0, q = 0.0;
-        for (int k = 0; k < kStatSplit; ++k) {
-          const double* o = partial + (((int64_t)g * kStatSplit + k) * C + cc) * 2;
-          s += __ldcg(o);
-          q += __ldcg(o + 1);
+#pragma unroll 8
+        for (int k = 0; k < splits; ++k) {
+          const double2 o = __ldcg(reinterpret_cast<const double2*>(partial + (((int64_t)g * splits + k) * C + cc) * 2));
+          s += o.x;
+          q += o.y;
         }
         const double mu = s / count;
         double var = q / count - mu * mu;
@@ -546,13 +547,13 @@ __global__ void __launch_bounds__(256) stats_pairs_partial_kernel(const float2* 
 }
 
 __global__ void stats_pairs_finalize_kernel(const double* __restrict__ partial, int C, int64_t count, float eps,
-                                            float* __restrict__ mean, float* __restrict__ rstd) {
+                                            float* __restrict__ mean, float* __restrict__ rstd, int splits) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const int g = blockIdx.y;
   if (c >= C) return;
   double s = 0.0, q = 0.0;
-  for (int k = 0; k < kStatSplit; ++k) {
-    const double* o = partial + (((int64_t)g * kStatSplit + k) * C + c) * 2;
+  for (int k = 0; k < splits; ++k) {
+    const double* o = partial + (((int64_t)g * splits + k) * C + c) * 2;
     s += o[0];
     q += o[1];
   }
@@ -568,12 +569,13 @@ int channel_stats_from_pairs(const float2* pairs, int groups, int64_t rows_p, in
   MSR_REQUIRE(pairs && partial && mean && rstd && groups > 0 && rows_p > 0 && C > 0, "stats_from_pairs: bad arguments");
   MSR_REQUIRE(C % 2 == 0, "stats_from_pairs: channel count must be even");
   ProfileScope prof(MSR_PROF_STATS, st, (double)groups * rows_p * C * 8.0, counters ? 1 : 2);
-  stats_pairs_partial_kernel<<<dim3(ceil_div(C, 64), kStatSplit, groups), 256, 0, st>>>(
+  const int splits = stat_splits(rows_p, 8 * 32);   // >= 32 rows per row lane and block
+  stats_pairs_partial_kernel<<<dim3(ceil_div(C, 64), splits, groups), 256, 0, st>>>(
       pairs, rows_p, C, partial, counters, (double)count_per_group, eps, mean, rstd);
   MSR_LAUNCH_CHECK();
   if (counters == nullptr) {
     stats_pairs_finalize_kernel<<<dim3(ceil_div(C, 128), groups), 128, 0, st>>>(partial, C, count_per_group, eps, mean,
-                                                                                 rstd);
+                                                                                 rstd, splits);
     MSR_LAUNCH_CHECK();
   }
   count_launch(counters ? 1 : 2);

@@ -180,11 +180,13 @@ int conv_f32(const ConvF32& p, cudaStream_t st) {
 __device__ __forceinline__ void stats_finalize_channel(const double* __restrict__ partial, int g, int c, int C,
                                                        double count, float eps, float* __restrict__ mean,
                                                        float* __restrict__ rstd) {
+  const int splits = gridDim.y;
   double s = 0.0, q = 0.0;
-  for (int k = 0; k < kStatSplit; ++k) {
-    const double* o = partial + (((int64_t)g * kStatSplit + k) * C + c) * 2;
-    s += __ldcg(o);
-    q += __ldcg(o + 1);
+#pragma unroll 8
+  for (int k = 0; k < splits; ++k) {
+    const double2 o = __ldcg(reinterpret_cast<const double2*>(partial + (((int64_t)g * splits + k) * C + c) * 2));
+    s += o.x;
+    q += o.y;
   }
   const double mu = s / count;
   double var = q / count - mu * mu;
@@ -199,7 +201,7 @@ __device__ __forceinline__ bool stats_block_is_last(unsigned int* counters, int 
   __syncthreads();
   if (threadIdx.x == 0) {
     const unsigned int prev = atomicAdd(counters + slot, 1u);
-    s_last = (prev == (unsigned int)(kStatSplit - 1));
+    s_last = (prev == gridDim.y - 1);
     if (s_last) counters[slot] = 0u;   // ready for the next launch (stream order)
   }
   __syncthreads();
@@ -214,8 +216,8 @@ __global__ void __launch_bounds__(256) stats_partial_kernel(const T* __restrict_
                                                             float* __restrict__ rstd) {
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int c = (blockIdx.x * 32 + cx) * 4;
-  const int split = blockIdx.y, g = blockIdx.z;
-  const int64_t per = (rows + kStatSplit - 1) / kStatSplit;
+  const int split = blockIdx.y, g = blockIdx.z, splits = gridDim.y;
+  const int64_t per = (rows + splits - 1) / splits;
   const int64_t r0 = split * per, r1 = min(rows, r0 + per);
   double s[4] = {0.0, 0.0, 0.0, 0.0}, q[4] = {0.0, 0.0, 0.0, 0.0};
   if (c < C) {
@@ -247,7 +249,7 @@ __global__ void __launch_bounds__(256) stats_partial_kernel(const T* __restrict_
         ss += sh[0][k][cx * 4 + j];
         qq += sh[1][k][cx * 4 + j];
       }
-      double* o = partial + (((int64_t)g * kStatSplit + split) * C + c + j) * 2;
+      double* o = partial + (((int64_t)g * splits + split) * C + c + j) * 2;
       o[0] = ss;
       o[1] = qq;
     }
@@ -259,13 +261,13 @@ __global__ void __launch_bounds__(256) stats_partial_kernel(const T* __restrict_
 }
 
 __global__ void stats_finalize_kernel(const double* __restrict__ partial, int C, int64_t rows, float eps,
-                                      float* __restrict__ mean, float* __restrict__ rstd) {
+                                      float* __restrict__ mean, float* __restrict__ rstd, int splits) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const int g = blockIdx.y;
   if (c >= C) return;
   double s = 0.0, q = 0.0;
-  for (int k = 0; k < kStatSplit; ++k) {
-    const double* o = partial + (((int64_t)g * kStatSplit + k) * C + c) * 2;
+  for (int k = 0; k < splits; ++k) {
+    const double* o = partial + (((int64_t)g * splits + k) * C + c) * 2;
     s += o[0];
     q += o[1];
   }
@@ -282,11 +284,14 @@ static int channel_stats_impl(const T* x, int ld, int groups, int64_t rows, int 
   MSR_REQUIRE(x && partial && mean && rstd && groups > 0 && rows > 0 && C > 0, "channel_stats: bad arguments");
   MSR_REQUIRE(C % 4 == 0 && ld % 4 == 0, "channel_stats: channel count and pitch must be multiples of 4");
   ProfileScope prof(MSR_PROF_STATS, st, (double)groups * rows * C * sizeof(T), counters ? 1 : 2);
-  stats_partial_kernel<T><<<dim3(ceil_div(C, 128), kStatSplit, groups), 256, 0, st>>>(x, ld, rows, C, partial, counters,
-                                                                                      eps, mean, rstd);
+  // a block walks >= 64 rows per row lane (8 lanes): few fat blocks instead of kStatSplit thin ones when the per-group
+  // row count is small (per-image moments of the encoder, the 8 x 8 first generator block)
+  const int splits = stat_splits(rows, 8 * 64);
+  stats_partial_kernel<T><<<dim3(ceil_div(C, 128), splits, groups), 256, 0, st>>>(x, ld, rows, C, partial, counters, eps,
+                                                                                  mean, rstd);
   MSR_LAUNCH_CHECK();
   if (counters == nullptr) {
-    stats_finalize_kernel<<<dim3(ceil_div(C, 128), groups), 128, 0, st>>>(partial, C, rows, eps, mean, rstd);
+    stats_finalize_kernel<<<dim3(ceil_div(C, 128), groups), 128, 0, st>>>(partial, C, rows, eps, mean, rstd, splits);
     MSR_LAUNCH_CHECK();
   }
   count_launch(counters ? 1 : 2);

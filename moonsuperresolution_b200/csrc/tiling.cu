@@ -586,16 +586,28 @@ __global__ void __launch_bounds__(256) blend_tile_fast_kernel(const float* __res
   Blend4 st;
 #pragma unroll
   for (int j = 0; j < 4; ++j) st.w[j] = st.m[j] = st.s[j] = 0.f;
+  // four lattice cells of a row at a time: their lattice entries, then their (independent) prediction / weight / range
+  // loads are all in flight before the dependent update chain of the first one starts
   for (int gy = gy0; gy <= gy1; ++gy) {
     const int ry = Y - gy * S;
-    for (int gx = gx0; gx <= gx1; ++gx) {
-      const int k = __ldg(lattice + gy * G + gx);
-      if (k < 0) continue;
-      const int rx = X - gx * S;
-      const float4 v = __ldcs(reinterpret_cast<const float4*>(pred + k * II + (int64_t)ry * I + rx));   // read once
-      const float4 wt = __ldg(reinterpret_cast<const float4*>(wtab + (int64_t)(ry - p) * wp + (rx - p)));
-      const float2 lh = __ldg(reinterpret_cast<const float2*>(lohi) + k);
-      blend4_update(st, v, wt, lh.x, lh.y - lh.x, half);
+    for (int gxb = gx0; gxb <= gx1; gxb += 4) {
+      int k[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) k[u] = (gxb + u <= gx1) ? __ldg(lattice + gy * G + gxb + u) : -1;
+      float4 v[4], wt[4];
+      float2 lh[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (k[u] >= 0) {
+          const int rx = X - (gxb + u) * S;
+          v[u] = __ldcs(reinterpret_cast<const float4*>(pred + k[u] * II + (int64_t)ry * I + rx));   // read once
+          wt[u] = __ldg(reinterpret_cast<const float4*>(wtab + (int64_t)(ry - p) * wp + (rx - p)));
+          lh[u] = __ldg(reinterpret_cast<const float2*>(lohi) + k[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (k[u] >= 0) blend4_update(st, v[u], wt[u], lh[u].x, lh[u].y - lh[u].x, half);
     }
   }
   float mo[4], so[4];
