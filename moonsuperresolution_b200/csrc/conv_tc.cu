@@ -303,7 +303,10 @@ __host__ __device__ constexpr uint32_t make_idesc(int bn, int m = kBlockM) {
 }
 
 // ---- the kernel -------------------------------------------------------------------------------------------------------
-template <int BN, int CTAS, bool STRIP, int EPI>
+// KSPLIT (dense layers only) is a template parameter so that the convolution instantiations carry none of its index
+// arithmetic: the single producer thread's issue rate bounds the non-strip pipeline (measured: the run-time variant cost
+// the r <= 64 layers 5-10 %).
+template <int BN, int CTAS, bool STRIP, int EPI, bool KSPLIT = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                   const __grid_constant__ CUtensorMap map_p, const Geometry g, const EpiParams ep) {
@@ -328,7 +331,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   const int total_tiles = (g.n_tiles_m / CTAS) * g.n_tiles_n;
   const int chunks_per_part = g.cin / kBlockK;
   const int k_chunks_per_tap = (g.split ? 3 : 1) * chunks_per_part;
-  const int k_chunks = (STRIP ? 3 * chunks_per_part : g.taps * k_chunks_per_tap) / g.ksplit;   // pipeline stages per tile
+  const int k_chunks = KSPLIT ? g.taps * k_chunks_per_tap / g.ksplit
+                              : (STRIP ? 3 * chunks_per_part : g.taps * k_chunks_per_tap);   // pipeline stages per tile
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::kStages; ++s) {
@@ -381,9 +385,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     b0 = tb * g.NB;
     h0 = th * g.TH;
     w0 = tw * g.TW;
-    n0 = (g.ksplit > 1 ? it.nt % g.n_tiles_n_real : it.nt) * BN;
+    n0 = (KSPLIT ? it.nt % g.n_tiles_n_real : it.nt) * BN;
   };
-  auto split_of = [&](const TileIter& it) { return g.ksplit > 1 ? it.nt / g.n_tiles_n_real : 0; };
+  auto split_of = [&](const TileIter& it) { return KSPLIT ? it.nt / g.n_tiles_n_real : 0; };
 
   if (warp == kEpiWarps) {
     // ===================== TMA producer =====================
@@ -441,9 +445,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             }
           }
         } else {
-          // split-K work unit: channel blocks [cb_lo, cb_hi) of every part
-          const int cb_per = chunks_per_part / g.ksplit;
-          const int cb_lo = split_of(it) * cb_per, cb_hi = cb_lo + cb_per;
+          // split-K work unit (KSPLIT): channel blocks [cb_lo, cb_hi) of every part; otherwise all of them
+          const int cb_per = KSPLIT ? chunks_per_part / g.ksplit : chunks_per_part;
+          const int cb_lo = KSPLIT ? split_of(it) * cb_per : 0, cb_hi = cb_lo + cb_per;
+          int kcol = 0;   // K coordinate of the weight tile
           for (int ky = 0; ky < ksz; ++ky) {
             const int ch = h0 * g.stride + ky - g.pad;
             for (int kx = 0; kx < ksz; ++kx) {
@@ -451,7 +456,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
               for (int part = 0; part < n_parts; ++part) {
                 // split-bf16: parts (x_hi, x_hi, x_lo) of A pair with (w_hi, w_lo, w_hi) of B
                 const int a_base = (part == 2) ? g.cin : 0;
-                int kcol = (((ky * ksz + kx) * n_parts + part) * chunks_per_part + cb_lo) * kBlockK;   // K coordinate of B
+                if constexpr (KSPLIT) kcol = (((ky * ksz + kx) * n_parts + part) * chunks_per_part + cb_lo) * kBlockK;
                 for (int cb = cb_lo; cb < cb_hi; ++cb, kcol += kBlockK) {
                   t_empty += mbar_wait_timed(empty_bar(stage), phase ^ 1u, timed);
                   const uint32_t sa = smem_base + stage * C::kStageBytes;
@@ -606,7 +611,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
               }
             }
             // split-K work units write their partial sums to plane `ks` of y (the caller reduces the planes)
-            const int64_t plane = g.ksplit > 1 ? (int64_t)split_of(it) * ((int64_t)g.n * g.r * g.r) * g.ncols : 0;
+            const int64_t plane = KSPLIT ? (int64_t)split_of(it) * ((int64_t)g.n * g.r * g.r) * g.ncols : 0;
             float* dst = ep.y + plane + m * g.ncols + col;
 #pragma unroll
             for (int j = 0; j < 32; j += 8)
@@ -942,6 +947,7 @@ int conv_tc_plan_create(ConvTC** out, const ConvTCArgs& a) {
     const char* why = nullptr;
     if (a.taps != 1 || a.epilogue != TC_EPI_BIAS_F32) why = "conv_tc: split-K needs a 1x1 GEMM with the fp32 epilogue";
     else if ((a.cin / 64) % g.ksplit != 0) why = "conv_tc: ksplit must divide cin / 64";
+    else if (p->bn != 256) why = "conv_tc: split-K is instantiated for 256-column tiles only";
     else if (a.bias || a.res || a.stat_pairs) why = "conv_tc: split-K planes carry no bias / residual / statistics";
     if (why) {
       delete p;
@@ -1053,10 +1059,10 @@ int conv_tc_plan_create(ConvTC** out, const ConvTCArgs& a) {
 }
 
 // one instantiation per (tile width, CTAs per tile, strip mode, epilogue) that the graphs actually use
-template <int BN, int CTAS, bool STRIP, int EPI>
+template <int BN, int CTAS, bool STRIP, int EPI, bool KSPLIT = false>
 static int launch_variant(const ConvTC* p, cudaStream_t st) {
   using C = tc::Cfg<BN, CTAS, STRIP>;
-  auto kernel = tc::conv3x3_tc_kernel<BN, CTAS, STRIP, EPI>;
+  auto kernel = tc::conv3x3_tc_kernel<BN, CTAS, STRIP, EPI, KSPLIT>;
   static bool attr_set = false;
   if (!attr_set) {
     MSR_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
@@ -1086,6 +1092,9 @@ static int launch_schedule(const ConvTC* p, cudaStream_t st) {
   }
   if constexpr (EPI == TC_EPI_PHASE_F32) {
     if (p->strip) return launch_variant<BN, 1, true, EPI>(p, st);
+  }
+  if constexpr (EPI == TC_EPI_BIAS_F32 && BN == 256) {
+    if (p->g.ksplit > 1) return launch_variant<BN, 1, false, EPI, true>(p, st);
   }
   return launch_variant<BN, 1, false, EPI>(p, st);
 }
