@@ -357,7 +357,7 @@ def time_config(torch, dist, name, arch, image_size, stride, batch, tile, h, w, 
     return out
 
 
-def run_extras(torch, dist, args, weights, rank, world, dev):
+def run_extras(torch, dist, args, weights, rank, world, dev, main_model=None):
     """The other BASELINE.json configs, one timed step each (reported beside the headline, never as it)."""
     from moonsuperresolution_b200 import models as M
     from moonsuperresolution_b200 import weights as W
@@ -399,7 +399,9 @@ def run_extras(torch, dist, args, weights, rank, world, dev):
                 arch = "cnn" if name == "cfg4" else "spade"
                 hh, ww = (20000, 15000) if name == "cfg4" else (70000, 15000)     # sharded along the long axis
                 cls = M.CNNSpade if arch == "cnn" else M.GauGAN
-                m = cls(512, 16, precision="bf16", weights=weights, max_groups=args.groups)
+                own = not (main_model is not None and main_model.arch == arch and args.image_size == 512 and
+                           args.batch_size == 16 and args.precision == "bf16")
+                m = cls(512, 16, precision="bf16", weights=weights, max_groups=args.groups) if own else main_model
                 label = ("BASELINE.json configs[3]: CNN-512 over 15000x20000" if name == "cfg4" else
                          "BASELINE.json configs[4]: SPADE-512 over 15000x70000 (N=16 nominal samples)")
                 res = {}
@@ -407,7 +409,8 @@ def run_extras(torch, dist, args, weights, rank, world, dev):
                     res[mode] = time_config(torch, dist, label + ", stride 128, batch 16, tile 1024", arch, 512, 128,
                                             16, 1024, hh, ww, mode, m, rank, world, dev, args.groups, warm=False)
                 out[name] = res
-                m.close()
+                if own:
+                    m.close()
             elif name == "repeat4":   # repeated-sample mode: 4 generations per patch position, with and
                                       # without reusing the noise-independent half of the graph across generations
                 cls = {"spade": M.GauGAN, "cnn": M.CNNSpade}.get(args.arch)
@@ -745,7 +748,7 @@ def main():
         except Exception as ex:   # an optional extra must never cost the headline line
             dedup = {"error": str(ex)[:300]}
 
-    extras = run_extras(torch, dist, args, weights, rank, world, dev)
+    extras = run_extras(torch, dist, args, weights, rank, world, dev, main_model=model)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
