@@ -39,18 +39,22 @@ constexpr int kThreads = (kEpiWarps + 2) * 32;   // + TMA producer warp + MMA is
 // K = 1152 / 2304 layers) by 3.
 constexpr int kStripRows = kBlockM + 2;
 constexpr int kStripBytes = ((kStripRows * 128 + 1023) / 1024) * 1024;   // 17 KB, keeps the weight tiles 1024-aligned
-template <int BN, int CTAS = 1, bool STRIP = false>
+// Staging area of the row-transposing epilogue (TC_EPI_RELU_BF16_T): per TMEM lane quarter 32 rows of 256 bytes, rows
+// padded by 16 bytes so that 8 lanes writing / reading 16 bytes each at consecutive rows hit distinct banks.
+constexpr int kTRowPitch = 256 + 16;
+constexpr int kTStageBytes = 4 * 32 * kTRowPitch;
+template <int BN, int CTAS = 1, bool STRIP = false, int EXTRA = 0>
 struct Cfg {
   static constexpr int kBBytes = (BN / CTAS) * kBlockK * 2;
   static constexpr int kAStage = STRIP ? kStripBytes : kABytes;
   static constexpr int kStageBytes = kAStage + (STRIP ? 3 : 1) * kBBytes;
   static constexpr int kTxBytes = (STRIP ? kStripRows * 128 : kABytes) + (STRIP ? 3 : 1) * kBBytes;   // bytes TMA reports
   // as many stages as fit in 227 KB (the TMA latency of ~3000 cycles must be covered by stages x MMA time per stage)
-  static constexpr int kStagesFit = (227 * 1024 - 1024 - 256) / kStageBytes;
+  static constexpr int kStagesFit = (227 * 1024 - 1024 - 256 - EXTRA) / kStageBytes;
   static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
   static constexpr int kAcc = (BN >= 256) ? 2 : 4;   // accumulator buffers in TMEM (epilogue of tile i overlaps i+1..)
   static constexpr int kTmemCols = (kAcc * BN < 32) ? 32 : kAcc * BN;   // power of two >= 32, <= 512
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + EXTRA;
 };
 
 struct Geometry {
@@ -310,7 +314,7 @@ template <int BN, int CTAS, bool STRIP, int EPI, bool KSPLIT = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                   const __grid_constant__ CUtensorMap map_p, const Geometry g, const EpiParams ep) {
-  using C = Cfg<BN, CTAS, STRIP>;
+  using C = Cfg<BN, CTAS, STRIP, (EPI == TC_EPI_RELU_BF16_T ? kTStageBytes : 0)>;
   const uint32_t cta_rank = (CTAS == 2) ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
   // work unit: a 128 x BN tile (CTAS == 1) or a 256 x BN tile shared by the pair (CTAS == 2)
@@ -709,6 +713,71 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             }
           }
         }
+      } else if constexpr (EPI == TC_EPI_RELU_BF16_T) {
+        // out_bf16 = act(acc + bias), 128 columns, written as WHOLE 256-byte rows: the TMEM layout gives a lane one row,
+        // so the direct epilogue above stores 32 bytes per lane into 32 different cache lines per instruction -- for a
+        // K = 64 GEMM (one MMA group per tile) that store pattern, not DRAM, bounds the kernel (ncu: L1/TEX 76 %, DRAM
+        // 51 %).  Here the two warps of a lane quarter park their 32-column chunks in shared memory, then each writes
+        // 16 complete rows: 2 rows = 4 full lines per instruction.  The tile's 128 rows are consecutive pixels of the
+        // NHWC output (checked by the plan), so row i of the tile is pixel m0 + i.
+        if constexpr (BN == 128) {
+        uint8_t* stg = smem_gen + C::kStages * C::kStageBytes + 256 + quarter * (32 * kTRowPitch);
+#pragma unroll 1
+        for (int c0 = csel * 32; c0 < BN; c0 += 64) {
+          uint32_t v[32];
+          tmem_ld32(t_row + (uint32_t)c0, v);
+          tmem_ld_wait();
+          const int col = n0 + c0;
+          float o[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(v[j]);
+          if (ep.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(ep.bias + col + j));
+              o[j] += bb.x; o[j + 1] += bb.y; o[j + 2] += bb.z; o[j + 3] += bb.w;
+            }
+          }
+          if (ep.act == ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] = fmaxf(o[j], 0.f);
+          } else if (ep.act == ACT_LRELU) {
+            const float sl = ep.slope;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] = fmaxf(o[j], o[j] * sl);
+          }
+          uint4* dst = reinterpret_cast<uint4*>(stg + lane * kTRowPitch + c0 * 2);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const __nv_bfloat162 t2 = __floats2bfloat162_rn(o[8 * q + 2 * j], o[8 * q + 2 * j + 1]);
+              pk[j] = *reinterpret_cast<const uint32_t*>(&t2);
+            }
+            dst[q] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+        }
+        // the accumulator is in registers / shared memory now: hand it back before the global stores
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");     // both warps of the quarter have parked
+        {
+          const int64_t m0 = ((int64_t)b0 * g.r + h0) * g.r + w0;           // pixel of tile row 0
+          const int rows_ok = min(128, (g.n - b0) * g.TW * g.TH);           // rows of images that exist
+          const int sub = lane >> 4, cb16 = (lane & 15) * 16;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rq = csel * 16 + 2 * it + sub;                        // row inside the quarter
+            const int row_t = quarter * 32 + rq;
+            const uint4 val = *reinterpret_cast<const uint4*>(stg + rq * kTRowPitch + cb16);
+            if (row_t < rows_ok)
+              *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(ep.out_bf16) + ((m0 + row_t) * BN + n0) * 2 + cb16) = val;
+          }
+        }
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");     // staging may be overwritten by the next tile
+        }  // BN == 128
       } else if constexpr (EPI == TC_EPI_PHASE_F32) {
         // a 4x4 conv on the x2-upsampled tensor, or a 4x4 stride-2 transposed conv, as a 3x3 convolution to 4 sub-pixel
         // phases (columns 0..3 = (py, px)) + pixel shuffle:  y[b][2h + py][2w + px] = act(acc[py*2 + px] + bias[0])
@@ -836,12 +905,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         }
         }  // BN >= 128
       }
-      // release the accumulator buffer
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if constexpr (CTAS == 2) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));   // the leader's MMA warp waits
-        else mbar_arrive(tempty_bar(acc));
+      // release the accumulator buffer (the row-transposing epilogue has already done so)
+      if constexpr (EPI != TC_EPI_RELU_BF16_T) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (CTAS == 2) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));   // the leader's MMA warp waits
+          else mbar_arrive(tempty_bar(acc));
+        }
       }
       if (++acc == C::kAcc) {
         acc = 0;
@@ -892,6 +963,10 @@ static const bool g_disable_prefetch = [] {
 static const int g_strip_mode = [] {
   const char* e = getenv("MSR_TC_STRIP");
   return e != nullptr ? atoi(e) : 1;
+}();
+static const bool g_disable_tstore = [] {
+  const char* e = getenv("MSR_TC_TSTORE");
+  return e != nullptr && e[0] == '0';
 }();
 static const bool g_disable_pairs = [] {
   const char* e = getenv("MSR_TC_PAIRS");
@@ -1021,6 +1096,12 @@ int conv_tc_plan_create(ConvTC** out, const ConvTCArgs& a) {
   }
   tc::EpiParams& e = p->ep;
   e.mode = a.epilogue;
+  // bf16 GEMM outputs of exactly one 128-column tile with a plain bias / activation epilogue (the SPADE mask
+  // convolutions): whole-row stores through shared memory.  MSR_TC_TSTORE=0 keeps the direct epilogue (A/B runs).
+  if (a.epilogue == TC_EPI_ACT_BF16 && p->bn == 128 && a.ncols == 128 && p->ctas == 1 && !p->strip && g.ksplit == 1 &&
+      !a.res && !a.scale && !a.split_out && a.out_pitch == 0 && a.act != ACT_TANH && !g_disable_tstore &&
+      (g.TW == a.r && (g.TH == a.r || g.NB == 1) || (g.TW == 128 && g.TH == 1 && g.NB == 1)))
+    e.mode = TC_EPI_RELU_BF16_T;
   e.bias = a.bias; e.y = a.y; e.res = a.res; e.res_shift = a.res_shift; e.stat_pairs = a.stat_pairs;
   e.sx = a.sx; e.sx_shift = a.sx_shift; e.mean = a.mean; e.rstd = a.rstd;
   e.samples_per_group = a.samples_per_group > 0 ? a.samples_per_group : 1;
@@ -1034,7 +1115,7 @@ int conv_tc_plan_create(ConvTC** out, const ConvTCArgs& a) {
   } else if (a.epilogue == TC_EPI_SPADE_BF16) {
     if (!(a.sx && a.mean && a.rstd && a.out_bf16 && a.bias)) bad = "conv_tc: SPADE epilogue needs sx, mean, rstd, bias, out_bf16";
     if (a.ncols % 128 != 0) bad = "conv_tc: SPADE epilogue needs a multiple of 128 columns";
-  } else if (a.epilogue == TC_EPI_ACT_BF16) {
+  } else if (a.epilogue == TC_EPI_ACT_BF16 || a.epilogue == TC_EPI_RELU_BF16_T) {
     if (!a.out_bf16) bad = "conv_tc: out_bf16 is null";
   } else if (a.epilogue == TC_EPI_PHASE_F32) {
     if (!a.y || a.ncols != 32) bad = "conv_tc: phase epilogue needs y and exactly 32 (padded) columns";
@@ -1061,7 +1142,7 @@ int conv_tc_plan_create(ConvTC** out, const ConvTCArgs& a) {
 // one instantiation per (tile width, CTAs per tile, strip mode, epilogue) that the graphs actually use
 template <int BN, int CTAS, bool STRIP, int EPI, bool KSPLIT = false>
 static int launch_variant(const ConvTC* p, cudaStream_t st) {
-  using C = tc::Cfg<BN, CTAS, STRIP>;
+  using C = tc::Cfg<BN, CTAS, STRIP, (EPI == TC_EPI_RELU_BF16_T ? tc::kTStageBytes : 0)>;
   auto kernel = tc::conv3x3_tc_kernel<BN, CTAS, STRIP, EPI, KSPLIT>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -1123,6 +1204,7 @@ int conv_tc_launch(const ConvTC* p, cudaStream_t st) {
     case TC_EPI_BIAS_F32: rc = launch_width<TC_EPI_BIAS_F32>(p, st); break;
     case TC_EPI_SPADE_BF16: rc = launch_width<TC_EPI_SPADE_BF16>(p, st); break;
     case TC_EPI_ACT_BF16: rc = launch_width<TC_EPI_ACT_BF16>(p, st); break;
+    case TC_EPI_RELU_BF16_T: rc = launch_variant<128, 1, false, TC_EPI_RELU_BF16_T>(p, st); break;
     case TC_EPI_PHASE_ACT_BF16: rc = launch_width<TC_EPI_PHASE_ACT_BF16>(p, st); break;
     default: rc = launch_width<TC_EPI_PHASE_F32>(p, st);
   }

@@ -70,6 +70,7 @@ enum TcEpilogue {
   TC_EPI_ACT_BF16 = 2,    // out_bf16 = act(acc + bias (+ residual))
   TC_EPI_PHASE_F32 = 3,   // 4 sub-pixel phase columns -> y[b][2h+py][2w+px] (final generator layer)
   TC_EPI_PHASE_ACT_BF16 = 4,  // 4 * cout phase columns -> out_bf16[b][2h+py][2w+px][c] (transposed 4x4 s2 convolution)
+  TC_EPI_RELU_BF16_T = 5,     // internal: TC_EPI_ACT_BF16 for one 128-column tile, whole-row stores through shared memory
 };
 struct ConvTCArgs {
   const __nv_bfloat16* x = nullptr;  // [n][r*stride][r*stride][cin] bf16

@@ -111,11 +111,14 @@ def parse_args(argv=None) -> DSRConfig:
 
 def main(argv=None) -> None:
     """process_full_tiles.py:589-594; without --model_path the identity model runs (the reference's own CLI cannot reach
-    its identity mode)."""
-    from .models import IdentityModel, load_GAN_model
+    its identity mode).  It is the reference's host callable (``lambda x, training=False: x``, :143),
+    fed numpy batches exactly as the reference would -- including the float64 promotion of the zero-padded last batch of
+    a tile (:472) -- so the identity round trip is bit-faithful; ``IdentityModel`` is the same check at device speed
+    (float32 throughout) for callers that construct the engine themselves."""
+    from .models import load_GAN_model
     cfg = parse_args(argv)
     if cfg.model_path is None:
-        model = IdentityModel(cfg.image_size, cfg.batch_size)
+        model = _identity
     else:
         model = load_GAN_model(cfg.model_path, cfg.image_size, cfg.batch_size, max_groups=max(1, cfg.groups_per_call or 8))
     DEMSuperResolution(cfg, model=model).processMap()
