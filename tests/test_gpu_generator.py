@@ -418,3 +418,64 @@ def test_command_line_run_end_to_end(msr, tmp_path, capsys):
     np.testing.assert_array_equal(mean, m2)
     np.testing.assert_array_equal(std, s2)
     np.testing.assert_array_equal(good, g2.astype(np.uint16))
+
+
+@pytest.mark.parametrize("kind", ["bias_f32", "act_bf16_t", "act_bf16", "spade", "stats"])
+def test_tensor_core_epilogues_write_only_their_output(torch, kind):
+    """Bounds check of our own (compute-sanitizer is closed on the GPU pool, profiles/r02_compute_sanitizer_closed.txt):
+    every output of the tcgen05 kernel's epilogues sits between two guard regions filled with a canary; ragged shapes
+    (3 images of 8 x 8: the last 128-row tile is half empty; 5 images of 16 x 16) exercise the row masks.  The guards
+    must come back untouched and the payload fully written."""
+    from moonsuperresolution_b200 import _lib
+    L, st = _lib.lib(), _lib.stream_ptr()
+    guard = 1 << 16
+    rng = np.random.default_rng(7)
+
+    def guarded(count, dtype):
+        buf = torch.full((count + 2 * guard,), -7777.0, dtype=dtype, device="cuda")
+        return buf, buf[guard:guard + count]
+
+    def check(buf, count, what):
+        assert bool((buf[:guard] == -7777.0).all()) and bool((buf[guard + count:] == -7777.0).all()), what + ": guard overwritten"
+        assert not bool((buf[guard:guard + count] == -7777.0).any()), what + ": output not fully written"
+
+    for (n, r) in ((3, 8), (5, 16), (1, 128)):
+        if kind in ("bias_f32", "stats"):
+            cin, cout = 64, 128
+            x = torch.from_numpy(rng.standard_normal((n, r, r, cin)).astype(np.float32)).cuda().to(torch.bfloat16)
+            w = torch.from_numpy((rng.standard_normal((cout, 9 * cin)) * 0.05).astype(np.float32)).cuda().to(torch.bfloat16)
+            b = torch.zeros(cout, device="cuda") + 0.5
+            ybuf, y = guarded(n * r * r * cout, torch.float32)
+            pairs_n = n * r * r // 128 * 4 * cout * 2
+            use_stats = kind == "stats" and r * r >= 128
+            pbuf, pairs = guarded(max(pairs_n, 1), torch.float32)
+            _lib.check(L.msr_op_conv_tc(x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), None, n, r, cin, cout, 9, 1,
+                                        1, 0, 0.2, pairs.data_ptr() if use_stats else None, st), kind)
+            torch.cuda.synchronize()
+            check(ybuf, n * r * r * cout, kind)
+            if use_stats:
+                check(pbuf, pairs_n, kind + " pairs")
+        elif kind in ("act_bf16_t", "act_bf16"):
+            cout = 128 if kind == "act_bf16_t" else 64          # 128 columns: whole-row stores through shared memory
+            x = torch.from_numpy(rng.standard_normal((n, r, r, 64)).astype(np.float32)).cuda().to(torch.bfloat16)
+            w = torch.from_numpy((rng.standard_normal((cout, 64)) * 0.1).astype(np.float32)).cuda().to(torch.bfloat16)
+            b = torch.ones(cout, device="cuda")
+            ybuf, y = guarded(n * r * r * cout, torch.bfloat16)
+            _lib.check(L.msr_op_conv_tc(x.data_ptr(), w.data_ptr(), b.data_ptr(), None, y.data_ptr(), n, r, 64, cout, 1, 1,
+                                        0, 2, 0.2, None, st), kind)
+            torch.cuda.synchronize()
+            check(ybuf, n * r * r * cout, kind)
+            want = torch.nn.functional.leaky_relu(x.float().reshape(-1, 64) @ w.float().T + 1.0, 0.2)
+            assert (y.float().reshape(-1, cout) - want).abs().max().item() < 0.05
+        else:
+            C = 64
+            a = torch.from_numpy(np.maximum(rng.standard_normal((n, r, r, 128)), 0).astype(np.float32)).cuda().to(torch.bfloat16)
+            w = torch.from_numpy((rng.standard_normal((2 * C, 1152)) * 0.03).astype(np.float32)).cuda().to(torch.bfloat16)
+            b = torch.zeros(2 * C, device="cuda") + 0.25
+            xs = torch.randn((n, r, r, C), device="cuda")
+            mean, rstd = torch.zeros((n, C), device="cuda"), torch.ones((n, C), device="cuda")
+            ybuf, y = guarded(n * r * r * C, torch.bfloat16)
+            _lib.check(L.msr_op_spade_tc(a.data_ptr(), w.data_ptr(), b.data_ptr(), xs.data_ptr(), 0, mean.data_ptr(),
+                                         rstd.data_ptr(), 1, y.data_ptr(), n, r, C, st), kind)
+            torch.cuda.synchronize()
+            check(ybuf, n * r * r * C, kind)
