@@ -613,17 +613,22 @@ def main():
         traffic = None
         tensor_pct = None
         tpath = os.path.join(ROOT, "profiles", "conv_tc_traffic.json")
+        traffic_note = None
         if os.path.exists(tpath) and args.arch in ("spade", "cnn") and args.image_size == 512:
-            # ncu capture of a forward over 16 patches; a bench launch covers groups * batch patches
+            # ncu --set full capture of ONE forward at the bench batch (128 patches = groups 8 x batch 16): all 53 tcgen05
+            # launches (profiles/r02_ncu_conv_bench_batch.md); scaled only if the command line changes the call size
             tj = json.load(open(tpath))
-            traffic = tj.get("dram_bytes_per_launch") * (args.groups * args.batch_size / 16.0)
+            traffic = tj.get("dram_bytes_per_launch") * (args.groups * args.batch_size / float(tj.get("patches_per_forward", 128)))
             tensor_pct = tj.get("tensor_pipe_active_pct_time_weighted")
+            traffic_note = ("dram__bytes_read + write per launch and time-weighted sm__pipe_tensor_cycles_active from "
+                            "profiles/conv_tc_traffic.json: ncu --set full over the 53 tcgen05 launches of one 128-patch "
+                            "forward (kernels replayed alone at boost clocks, where DRAM / L2 weigh more against the tensor "
+                            "pipe than in the power-capped step at ~1.39 GHz; `frac` is the steady-state figure)")
         roofline = {"bound": "tensor", "kernel": "conv3x3_tc_kernel (tcgen05 implicit GEMM, all launches of one step)",
                     "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
                     "peak_source": f"MEASURED_PEAKS.json bf16 sustained ({pk['source']})", "traffic": traffic,
                     "ncu_tensor_pipe_active_pct": tensor_pct,
-                    "traffic_note": "DRAM bytes per launch from profiles/conv_tc_traffic.json (ncu --set full, mean over the "
-                                    "rb4..final launches of a 16-patch forward) scaled to the patches per bench launch",
+                    "traffic_note": traffic_note,
                     "launches": tc["launches"], "avg_launch_ms": tc["ms"] / tc["launches"],
                     "flops_per_launch_avg": tc["work"] / tc["launches"]}
     total_prof_ms = sum(v["ms"] for v in prof.values())
