@@ -60,6 +60,67 @@ __global__ void __launch_bounds__(256) source_patches_kernel(const float* __rest
   }
 }
 
+// The same rows, stored as whole cache lines: a thread's 128-byte row goes through shared memory (row pitch 144 bytes:
+// eight lanes writing 16 bytes at consecutive rows hit distinct banks), then every warp instruction writes 4 complete
+// rows (512 contiguous bytes).  One thread per pixel storing its own row issues 32-byte pieces into 32 different lines per
+// instruction, and the L1 store path, not DRAM, bounds the kernel (2.8 TB/s).  Grid = ceil(total / 256) blocks exactly.
+constexpr int kPatchPitch = 128 + 16;
+__global__ void __launch_bounds__(256) source_patches_lines_kernel(const float* __restrict__ src, int I,
+                                                                   __nv_bfloat16* __restrict__ out, int n, int r, int mode) {
+  __shared__ __align__(16) uint8_t stage[256 * kPatchPitch];
+  const int64_t total = (int64_t)n * r * r;
+  const int f = I / r, half = f >> 1;
+  const int lr = 31 - __clz(r);
+  const int64_t m0 = (int64_t)blockIdx.x * 256;
+  const int64_t m = m0 + threadIdx.x;
+  if (m < total) {
+    const int nn = (int)(m >> (2 * lr));
+    const int rem = (int)(m & (((int64_t)1 << (2 * lr)) - 1));
+    const int h = rem >> lr, x = rem & (r - 1);
+    __align__(16) __nv_bfloat16 row[64];
+#pragma unroll
+    for (int j = 54; j < 64; ++j) row[j] = __float2bfloat16_rn(0.f);
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        float2 s = make_float2(0.f, 0.f);
+        if (mode == 0) {
+          const int hh = h + ky - 1, xx = x + kx - 1;
+          if (hh >= 0 && hh < r && xx >= 0 && xx < r)
+            s = __ldg(reinterpret_cast<const float2*>(src + (((int64_t)nn * I + hh * f + half) * I + xx * f + half) * 2));
+        } else {
+          const int sy = 2 * h + ky, sx = 2 * x + kx;
+          if (sy < I && sx < I) s = __ldg(reinterpret_cast<const float2*>(src + (((int64_t)nn * I + sy) * I + sx) * 2));
+        }
+        const int j = (ky * 3 + kx) * 2;
+        const __nv_bfloat16 hx = __float2bfloat16_rn(s.x), hy = __float2bfloat16_rn(s.y);
+        row[j] = hx;
+        row[j + 1] = hy;
+        row[18 + j] = hx;
+        row[18 + j + 1] = hy;
+        row[36 + j] = __float2bfloat16_rn(s.x - __bfloat162float(hx));
+        row[36 + j + 1] = __float2bfloat16_rn(s.y - __bfloat162float(hy));
+      }
+    }
+    const uint4* rp = reinterpret_cast<const uint4*>(row);
+    uint4* sp = reinterpret_cast<uint4*>(stage + threadIdx.x * kPatchPitch);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) sp[q] = rp[q];
+  }
+  __syncthreads();
+  // 256 rows x 8 chunks of 16 bytes; consecutive threads take consecutive chunks of the block's contiguous 32 KB
+  const int rows_here = (total - m0 < 256) ? (int)(total - m0) : 256;
+  uint8_t* dst = reinterpret_cast<uint8_t*>(out + m0 * 64);
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int e = it * 256 + threadIdx.x;       // 16-byte chunk index inside the block's output
+    const int rr = e >> 3, cc = e & 7;
+    if (rr < rows_here)
+      *reinterpret_cast<uint4*>(dst + (int64_t)e * 16) = *reinterpret_cast<const uint4*>(stage + rr * kPatchPitch + cc * 16);
+  }
+}
+
 // pix2pix block 1 (pix2pix.py:64-72): Conv2D(64, 4, strides=2, 'same') on the 2-channel source = taps (2y + ky - 1,
 // 2x + kx - 1), ky, kx in 0..3.  Row = 32 tap-channel values as hi (channels 0..31) | lo (32..63); with weight rows
 // [w | w] the GEMM evaluates (x_hi + x_lo) * w, i.e. the exact input against bf16 weights.
@@ -101,6 +162,8 @@ int source_patches_bf16(const float* source, int I, __nv_bfloat16* out, int n, i
   ProfileScope prof(MSR_PROF_MASK_CONV, st, (double)total * (128.0 + 8.0));
   const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 16);
   if (mode == 2) source_patches4_kernel<<<blocks, 256, 0, st>>>(source, I, out, n, r);
+  else if (total >= 4096 && total / 256 < (1ll << 31))
+    source_patches_lines_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(source, I, out, n, r, mode);
   else source_patches_kernel<<<blocks, 256, 0, st>>>(source, I, out, n, r, mode);
   count_launch();
   MSR_LAUNCH_CHECK();
