@@ -344,3 +344,35 @@ def test_bands_taller_than_65535_rows(msr, torch):
     torch.cuda.synchronize()
     assert torch.equal(mean, acc[1]) and bool(gd.all())
     torch.testing.assert_close(std, torch.sqrt(acc[2] / acc[0]), rtol=1e-6, atol=0)
+
+
+def test_maximum_size_identity_round_trip(msr, torch):
+    """BASELINE.json configs[4] geometry -- the largest raster the reference is said to handle, 15000 x 70000 (README.md:13)
+    with I = 512, S = 128, B = 16, T = 1024 -- on ONE GPU with the identity model, tile by tile (1035 tiles, 123 792
+    slots) and in dedup mode (61 902 positions): the two rasters must be bit-identical, `good` is exactly
+    the rectangle the patch lattice covers, the mean reproduces the DEM there and everything else is no_value."""
+    h, w = 70000, 15000
+    i, s_, b, t = 512, 128, 16, 1024
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    dem = (torch.cumsum(torch.randn((h, w), generator=gen, device="cuda"), 1) * 2.0 + 1200.0).contiguous()
+    img = (torch.rand((h, w), generator=gen, device="cuda") * 254.0 + 1.0).contiguous()
+    res = {}
+    for mode in ("faithful", "dedup"):
+        cfg = msr.DSRConfig(image_size=i, stride=s_, batch_size=b, tile_size=t, mode=mode)
+        eng = msr.DEMSuperResolution(cfg, model=msr.IdentityModel(i, b))
+        eng.setRasters(dem, img)
+        eng.padInputs()
+        eng.processTiles()
+        res[mode] = (eng.mean_out, eng.std_out, eng.good_out, eng.slots_executed)
+        del eng
+    assert res["faithful"][3] == 123792 and res["dedup"][3] == 61904        # 61 902 positions in whole batches of 16
+    for k in range(3):
+        assert torch.equal(res["faithful"][k], res["dedup"][k])
+    mean, std, good = res["dedup"][0], res["dedup"][1], res["dedup"][2].bool()
+    p = i // 16
+    want = torch.zeros((h, w), dtype=torch.bool, device="cuda")
+    want[p:((h - i) // s_) * s_ + i - p, p:((w - i) // s_) * s_ + i - p] = True
+    assert torch.equal(good, want)
+    assert (mean - dem).abs()[good].max().item() <= 2e-3
+    assert 0.0 <= std[good].min().item() and std[good].max().item() <= 2e-3
+    assert bool((mean[~good] == -32768.0).all()) and bool((std[~good] == -32768.0).all())
