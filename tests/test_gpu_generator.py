@@ -479,3 +479,25 @@ def test_tensor_core_epilogues_write_only_their_output(torch, kind):
                                          rstd.data_ptr(), 1, y.data_ptr(), n, r, C, st), kind)
             torch.cuda.synchronize()
             check(ybuf, n * r * r * C, kind)
+
+
+def test_pix2pix_at_the_cfg2_call_shape_bf16(msr, torch):
+    """BASELINE.json configs[1] at its call shape: pix2pix-256, bf16 tensor-core mode, batch 16, eight groups per call
+    (128 patches); pix2pix has no batch coupling at inference, so every group must equal the oracle within the bf16 bar
+    and a zero padding slot must not disturb its batch-mates."""
+    b, groups = 16, 8
+    w = W.random_init("pix2pix", 256, seed=6, perturb_affine=True)
+    rng = np.random.default_rng(12)
+    x = rng.uniform(-0.5, 0.5, (groups * b, 256, 256, 2)).astype(np.float32)
+    x[3 * b + 5:4 * b] = 0.0
+    model = msr.Pix2Pix(batch_size=b, weights=w, precision="bf16", max_groups=groups)
+    src = torch.from_numpy(x).cuda()
+    out = torch.empty((groups * b, 256, 256), dtype=torch.float32, device="cuda")
+    model.forward_device(src, out, None, groups)
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    for g in (0, 3, 7):
+        sl = slice(g * b, (g + 1) * b)
+        want = OG.pix2pix_call(x[sl], w)[..., 0]
+        err = np.abs(got[sl] - want).max()
+        assert err <= TOL_BF16, (g, err)
