@@ -1,16 +1,22 @@
 """torch-CPU restatement of the reference generators (TEST INFRASTRUCTURE ONLY -- see oracle/__init__.py).
 
-PARITY: pinned to the reference's own graph code, unpinned to TensorFlow's kernels.  The arithmetic of the reference
-lives in TensorFlow 2.5 / Keras / tensorflow-addons 0.16.1 (pip-env.py:15,34,36), none of which is installable here, and
-the reference ships no golden vectors.  What holds this file in place (tests/test_oracle_generator_pinned.py):
-  * the UNMODIFIED reference modules (networks.py, blocks.py, spade.py, sampling.py, pix2pix.py and the ``call`` bodies
-    of GauGAN / CNNSpade cut out of model.py) executed on a numpy op shim (tests/golden/tf_numpy_shim.py) reproduce this
-    file's outputs to float32 rounding -- so the graph (layer order, skips, which statistics, which activations) is the
-    reference's, not one reading of it;
-  * the op semantics the shim and this file share only by documentation (SAME padding, Conv2DTranspose, half-pixel
-    nearest resize, flatten order: SURVEY.md App. B) are each checked against scalar-loop restatements;
-  * tests/golden/make_golden_tf.py writes generator_tf.npz on any TensorFlow-equipped box; the same test then pins this
-    file to TensorFlow itself.  Until that file exists the TensorFlow-kernel level stays "parity unpinned".
+PARITY: PINNED to the reference's own generator code executed by a third-party TensorFlow-graph executor; not pinned to
+TensorFlow's own kernels.  The arithmetic of the reference lives in TensorFlow 2.5 / Keras / tensorflow-addons 0.16.1
+(pip-env.py:15,34,36), none of which is installable here, and the reference ships no golden vectors.  What holds this
+file in place:
+  * tests/test_tf_semantics_opencv.py -- the bodies of GauGAN.call / CNNSpade.call (cut out of model.py) and the UNMODIFIED
+    networks.py, blocks.py, spade.py, sampling.py, pix2pix.py are run on traced tensors, every op they perform is written
+    down as a TensorFlow GraphDef node, and the graph is EXECUTED BY OpenCV's TensorFlow importer
+    (cv2.dnn.readNetFromTensorflow), an implementation of TensorFlow's graph semantics written by neither the reference's
+    nor this repository's authors.  Whole GauGAN-64 / CNNSpade-64 calls (batch of one) and the whole pix2pix-256 generator
+    agree with this file to 6e-6 (tests/golden/generator_opencv_tf.npz, tests/golden/make_golden_tf.py --opencv); so do the
+    single ops with silent-mismatch potential (SAME padding k3 / k4, stride 1 / 2, even / odd sizes; Conv2DBackpropInput;
+    half-pixel nearest resize; FusedBatchNorm inference; LeakyRelu);
+  * tests/test_oracle_generator_pinned.py -- the same reference modules executed on a numpy op shim
+    (tests/golden/tf_numpy_shim.py) with batches of 2-3 (tf.nn.moments over the batch axis, zero padding slots) and at
+    I = 128 reproduce this file to float32 rounding; the shim's ops are checked against scalar-loop restatements;
+  * tests/golden/make_golden_tf.py (no flag) writes generator_tf.npz on any TensorFlow-equipped box; the same test file
+    then holds this oracle to TensorFlow itself (skipped while that file is absent).
 Also pinned: parameter counts / shapes (App. A), fp32-vs-fp64 self agreement, structural invariants
 (tests/test_oracle_generator.py).  Each function cites the reference lines it follows.
 

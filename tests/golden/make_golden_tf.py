@@ -23,6 +23,12 @@ for p in (ROOT, HERE):
     if p not in sys.path:
         sys.path.insert(0, p)
 
+# batch-of-one cases executed by OpenCV's TensorFlow importer on the graph traced from the reference's code (--opencv)
+# (I = 64 only for the SPADE nets: OpenCV reads a 2-D -> 4-D Reshape as NCHW, so Reshape((sw, sw, 1024)) with sw > 1 --
+# networks.py:42 at I >= 128 -- is outside what its importer can represent; sw = 1 is layout-free.)
+OPENCV_CASES = [("spade64b1", "spade", 64, 1, 25, 9), ("cnn64b1", "cnn", 64, 1, 26, 10), ("spade64b1_s2", "spade", 64, 1, 28, 12),
+                ("pix2pix", "pix2pix", 256, 1, 24, 8)]
+
 # (name, arch, image_size, batch, weight seed, input seed)
 CASES = [("cnn64", "cnn", 64, 3, 21, 5), ("spade64", "spade", 64, 2, 22, 6), ("spade128", "spade", 128, 2, 23, 7),
          ("pix2pix", "pix2pix", 256, 1, 24, 8)]
@@ -42,9 +48,29 @@ def case_inputs(arch, image_size, batch, wseed, xseed):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--shim", action="store_true")
+    ap.add_argument("--opencv", action="store_true",
+                    help="trace the reference's code into TensorFlow GraphDefs and execute them with OpenCV's TensorFlow "
+                         "importer -> tests/golden/generator_opencv_tf.npz")
     ap.add_argument("--out", default=None)
     args = ap.parse_args()
     import reference_graph as RG
+    if args.opencv:
+        import tempfile
+        ref = RG.Reference(backend="shim", dtype=np.float32)
+        out = {}
+        with tempfile.TemporaryDirectory() as tmp:
+            for name, arch, i, b, ws, xs in OPENCV_CASES:
+                w, x, eps = case_inputs(arch, i, b, ws, xs)
+                got, shim = ref.run_pix2pix_opencv(w, x, tmp) if arch == "pix2pix" else ref.run_spade_opencv(arch, i, w, x, eps, tmp)
+                out[f"{name}.out"] = np.asarray(got, np.float32)
+                print(name, got.shape, "max |opencv - shim| =", float(np.abs(got - shim).max()), "max |out| =", float(np.abs(got).max()))
+        ref.close()
+        import cv2
+        out["backend"] = np.array("opencv-dnn-tensorflow-importer " + cv2.__version__)
+        path = args.out or os.path.join(HERE, "generator_opencv_tf.npz")
+        np.savez_compressed(path, **out)
+        print("wrote", path)
+        return
     backend = "shim" if args.shim else "tf"
     ref = RG.Reference(backend=backend, dtype=np.float64)
     out = {}

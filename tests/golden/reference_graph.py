@@ -171,3 +171,50 @@ class Reference:
     def run_pix2pix(self, weights, x: np.ndarray):
         gen = self.build_pix2pix(weights)
         return {"out": self._np(gen(np.asarray(x, np.float32), training=False))}
+
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # third-party TensorFlow executor: trace the reference's code into a GraphDef, run it with OpenCV's importer
+    # ------------------------------------------------------------------------------------------------------------------
+    def run_spade_opencv(self, arch: str, image_size: int, weights, x: np.ndarray, eps: np.ndarray, workdir: str):
+        """GauGAN.call / CNNSpade.call (the bodies cut out of model.py) executed on the shim with TRACED tensors: every
+        op the reference's code performs -- inside build_encoder, GaussianSampler.call, build_generator,
+        ResidualBlock.call, SPADE.call -- is written down as a TensorFlow GraphDef node (tests/golden/tf_graphdef.py) and
+        the graph is then executed by cv2.dnn.readNetFromTensorflow.  Batch of one (OpenCV reduces over spatial axes
+        only; with one sample tf.nn.moments over (0, 1, 2) is that reduction); the sampler's noise enters as a second
+        Placeholder, as tf.random.normal's output would.  Returns (OpenCV output, shim output), both (1, I, I, 1)."""
+        assert self.backend == "shim" and x.shape[0] == 1
+        import tf_graphdef as TG
+        SH = self._shim
+        m = self.build_spade(image_size, 1, weights)
+        x = np.asarray(x, np.float32)
+        eps = np.asarray(eps, np.float32).reshape(1, 256)
+        call = self.call_gaugan if arch == "spade" else self.call_cnn
+        rnd = self.tf.random
+        saved = rnd.normal
+        try:
+            rnd.normal = lambda shape, mean=0.0, stddev=1.0, **k: eps.reshape(shape)
+            want = np.asarray(call(m, x))
+            tx = SH.start_trace(TG, x, "input")
+            teps = SH.trace_input(eps, "eps")
+            rnd.normal = lambda shape, mean=0.0, stddev=1.0, **k: teps
+            y = call(m, tx)
+            graph = SH.stop_trace()
+        finally:
+            rnd.normal = saved
+            SH.TRACER = None
+        feeds = {"input": x, "eps": eps} if arch == "spade" else {"input": x}
+        if arch != "spade":      # the unused Placeholder would be an unconnected input
+            graph = graph.replace(TG.placeholder("eps"), b"", 1)
+        got = TG.run_opencv(graph, feeds, os.path.join(workdir, f"{arch}{image_size}.pb"), output=y.tf)
+        return got, want
+
+    def run_pix2pix_opencv(self, weights, x: np.ndarray, workdir: str):
+        """Pix2Pix.buildGenerator's functional graph (as recorded by the shim from the unmodified pix2pix.py) emitted
+        layer by layer as a GraphDef and executed by OpenCV's TensorFlow importer."""
+        assert self.backend == "shim"
+        import tf_graphdef as TG
+        gen = self.build_pix2pix(weights)
+        graph, final = TG.emit_functional_model(gen, self._shim, batch=x.shape[0], in_hw=256)
+        want = self._np(gen(np.asarray(x, np.float32), training=False))
+        return TG.run_opencv(graph, x, os.path.join(workdir, "pix2pix.pb")), want

@@ -98,6 +98,110 @@ def _arr(x):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
+# tracing: while the reference's code runs on arrays, also write down the TensorFlow graph it would have built
+# ----------------------------------------------------------------------------------------------------------------------
+class Tracer:
+    """Collects TensorFlow GraphDef nodes (tests/golden/tf_graphdef.py) for every op executed on traced tensors, so that
+    a third-party TensorFlow-graph executor (OpenCV's importer) can run the graph the reference's ``call`` bodies
+    describe.  Tracing is value-carrying: every traced tensor also holds the shim's numpy result."""
+
+    def __init__(self, tg):
+        self.tg, self.nodes, self.count = tg, [], 0
+
+    def fresh(self, tag):
+        self.count += 1
+        return f"{tag}_{self.count}"
+
+    def emit(self, b):
+        self.nodes.append(b)
+
+    def name_of(self, x):
+        """TF node name of an operand: traced tensors carry one, anything else becomes a Const."""
+        if isinstance(x, TT):
+            return x.tf
+        n = self.fresh("const")
+        self.emit(self.tg.const(n, np.asarray(x, np.float32)))
+        return n
+
+    def graph(self):
+        return b"".join(self.nodes)
+
+
+TRACER = None
+
+
+class TT(np.ndarray):
+    """Traced tensor: an ndarray that knows the name of the TF node producing it.  numpy ufuncs are switched off on it
+    (``__array_ufunc__ = None``), so only the operations spelled out here -- each of which emits its TF node -- can
+    consume one; anything else raises instead of silently dropping out of the trace."""
+    __array_ufunc__ = None
+
+    def __new__(cls, arr, name):
+        obj = np.asarray(arr).view(cls)
+        obj.tf = name
+        return obj
+
+    def __array_finalize__(self, obj):
+        self.tf = getattr(obj, "tf", None)
+
+    def _bin(self, o, op, fn, swap=False):
+        a, b = (o, self) if swap else (self, o)
+        n = TRACER.fresh(op.lower())
+        # AddV2 / Mul commute: the traced operand goes first (TensorFlow writes `0.5 * t` as Mul(t, 0.5) too once the
+        # constant is folded to the right; OpenCV's importer only accepts a constant as the second input)
+        ga, gb = (b, a) if (swap and op in ("AddV2", "Mul")) else (a, b)
+        TRACER.emit(TRACER.tg.binary(n, op, TRACER.name_of(ga), TRACER.name_of(gb)))
+        return TT(fn(np.asarray(a, _DTYPE), np.asarray(b, _DTYPE)), n)
+
+    def __add__(self, o):
+        return self._bin(o, "AddV2", np.add)
+
+    def __radd__(self, o):
+        return self._bin(o, "AddV2", np.add, swap=True)
+
+    def __sub__(self, o):
+        return self._bin(o, "Sub", np.subtract)
+
+    def __mul__(self, o):
+        return self._bin(o, "Mul", np.multiply)
+
+    def __rmul__(self, o):
+        return self._bin(o, "Mul", np.multiply, swap=True)
+
+    def __truediv__(self, o):
+        return self._bin(o, "RealDiv", np.divide)
+
+
+def start_trace(tg, x, name="input"):
+    """Begins a trace: returns ``x`` as the traced Placeholder ``name``."""
+    global TRACER
+    TRACER = Tracer(tg)
+    return trace_input(x, name)
+
+
+def trace_input(x, name):
+    """A further Placeholder of the running trace."""
+    TRACER.emit(TRACER.tg.placeholder(name))
+    return TT(_arr(x), name)
+
+
+def stop_trace():
+    global TRACER
+    g, TRACER = TRACER.graph(), None
+    return g
+
+
+def _traced(x):
+    return TRACER is not None and isinstance(x, TT)
+
+
+def _unary_traced(op, x, value):
+    n = TRACER.fresh(op.lower())
+    TRACER.emit(TRACER.tg.unary(n, op, x.tf))
+    return TT(value, n)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
 # ops
 # ----------------------------------------------------------------------------------------------------------------------
 def same_padding(n_in: int, k: int, s: int):
@@ -210,6 +314,7 @@ class Conv2D(Layer):
         self.filters, self.k = int(filters), int(kernel_size if np.isscalar(kernel_size) else kernel_size[0])
         self.s = int(strides if np.isscalar(strides) else strides[0])
         self.padding, self.act, self.use_bias = padding, _activation(activation), use_bias
+        self.act_name = activation
 
     def build(self, input_shape):
         self.kernel = np.zeros((self.k, self.k, input_shape[-1], self.filters), _DTYPE)
@@ -222,7 +327,18 @@ class Conv2D(Layer):
         y = conv2d(x, self.kernel, self.s, self.padding)
         if self.use_bias:
             y = y + self.bias
-        return self.act(y)
+        y = self.act(y)
+        if _traced(x):
+            tg, n = TRACER.tg, TRACER.fresh("conv")
+            TRACER.emit(tg.conv2d(n, x.tf, np.asarray(self.kernel, np.float32), self.s, self.padding.upper().encode()))
+            if self.use_bias:
+                TRACER.emit(tg.bias_add(n + "_bias", n, np.asarray(self.bias, np.float32)))
+                n += "_bias"
+            if self.act_name in ("relu", "tanh"):
+                TRACER.emit(tg.unary(n + "_act", self.act_name.capitalize(), n))
+                n += "_act"
+            return TT(y, n)
+        return y
 
 
 class Conv2DTranspose(Conv2D):
@@ -243,7 +359,7 @@ class Conv2DTranspose(Conv2D):
 class Dense(Layer):
     def __init__(self, units, activation=None, **kwargs):
         super().__init__(**kwargs)
-        self.units, self.act = int(units), _activation(activation)
+        self.units, self.act, self.act_name = int(units), _activation(activation), activation
 
     def build(self, input_shape):
         self.kernel = np.zeros((input_shape[-1], self.units), _DTYPE)
@@ -251,7 +367,14 @@ class Dense(Layer):
         self.weights_ = ["kernel", "bias"]
 
     def call(self, x):
-        return self.act(_arr(x) @ self.kernel + self.bias)
+        y = self.act(_arr(x) @ self.kernel + self.bias)
+        if _traced(x):
+            assert self.act_name is None
+            tg, n = TRACER.tg, TRACER.fresh("dense")
+            TRACER.emit(tg.matmul(n, x.tf, np.asarray(self.kernel, np.float32)) +       # Keras Dense: MatMul + BiasAdd
+                        tg.bias_add(n + "_bias", n, np.asarray(self.bias, np.float32)))
+            return TT(y, n + "_bias")
+        return y
 
 
 class Reshape(Layer):
@@ -260,12 +383,22 @@ class Reshape(Layer):
         self.target = tuple(target_shape)
 
     def call(self, x):
-        return _arr(x).reshape((np.shape(x)[0],) + self.target)
+        y = _arr(x).reshape((np.shape(x)[0],) + self.target)
+        if _traced(x):
+            n = TRACER.fresh("reshape")
+            TRACER.emit(TRACER.tg.reshape(n, x.tf, (-1,) + self.target))
+            return TT(y, n)
+        return y
 
 
 class Flatten(Layer):
     def call(self, x):
-        return _arr(x).reshape(np.shape(x)[0], -1)
+        y = _arr(x).reshape(np.shape(x)[0], -1)
+        if _traced(x):
+            n = TRACER.fresh("flatten")
+            TRACER.emit(TRACER.tg.reshape(n, x.tf, (-1, y.shape[1])))
+            return TT(y, n)
+        return y
 
 
 class UpSampling2D(Layer):
@@ -275,7 +408,12 @@ class UpSampling2D(Layer):
         self.size = (size, size) if np.isscalar(size) else tuple(size)
 
     def call(self, x):
-        return np.repeat(np.repeat(_arr(x), self.size[0], axis=1), self.size[1], axis=2)
+        y = np.repeat(np.repeat(_arr(x), self.size[0], axis=1), self.size[1], axis=2)
+        if _traced(x):   # Keras: backend.resize_images(..., interpolation="nearest") -> ResizeNearestNeighbor
+            n = TRACER.fresh("upsample")
+            TRACER.emit(TRACER.tg.resize_nearest(n, x.tf, [y.shape[1], y.shape[2]], half_pixel_centers=True))
+            return TT(y, n)
+        return y
 
 
 class LeakyReLU(Layer):
@@ -284,8 +422,7 @@ class LeakyReLU(Layer):
         self.alpha = alpha
 
     def call(self, x):
-        x = _arr(x)
-        return np.where(x > 0, x, self.alpha * x)
+        return _leaky_relu(x, self.alpha)
 
 
 class ReLU(Layer):
@@ -343,6 +480,11 @@ class InstanceNormalization(Layer):
         self.weights_ = ["gamma", "beta"]
 
     def call(self, x):
+        if _traced(x):   # the same arithmetic through the traced operators: every step lands in the graph
+            mu, var = _moments(x, (1, 2), keepdims=True)
+            std = var + self.epsilon
+            std = _unary_traced("Sqrt", std, np.sqrt(_arr(std)))
+            return (x - mu) / std * np.asarray(self.gamma, np.float32) + np.asarray(self.beta, np.float32)
         x = _arr(x)
         mu = x.mean(axis=(1, 2), keepdims=True)
         var = ((x - mu) ** 2).mean(axis=(1, 2), keepdims=True)
@@ -402,7 +544,7 @@ class Model(Layer):
     def call(self, x):
         xs = x if isinstance(x, (list, tuple)) else [x]
         assert len(xs) == len(self.inputs)
-        env = {id(s): _arr(v) for s, v in zip(self.inputs, xs)}
+        env = {id(s): (v if isinstance(v, TT) else _arr(v)) for s, v in zip(self.inputs, xs)}
         return _evaluate(self.outputs, env)
 
 
@@ -451,13 +593,10 @@ def install() -> types.ModuleType:
     keras.losses = types.SimpleNamespace(BinaryCrossentropy=_Anything)
     keras.metrics = types.SimpleNamespace(Mean=_Anything)
     tf.keras = keras
-    tf.nn = types.SimpleNamespace(
-        leaky_relu=_symbolic(lambda x, alpha=0.2: np.where(_arr(x) > 0, _arr(x), alpha * _arr(x))),
-        moments=lambda x, axes, keepdims=False: (_arr(x).mean(axis=tuple(axes), keepdims=keepdims),
-                                                  _arr(x).var(axis=tuple(axes), keepdims=keepdims)))
+    tf.nn = types.SimpleNamespace(leaky_relu=_symbolic(_leaky_relu), moments=_moments)
     tf.image = types.SimpleNamespace(resize=lambda x, size, method="bilinear": _resize(x, size, method))
-    tf.sqrt = _symbolic(lambda x: np.sqrt(_arr(x)))
-    tf.exp = _symbolic(lambda x: np.exp(_arr(x)))
+    tf.sqrt = _symbolic(lambda x: _unary_traced("Sqrt", x, np.sqrt(_arr(x))) if _traced(x) else np.sqrt(_arr(x)))
+    tf.exp = _symbolic(lambda x: _unary_traced("Exp", x, np.exp(_arr(x))) if _traced(x) else np.exp(_arr(x)))
     tf.random = types.SimpleNamespace(normal=_normal)
     tf.random_normal_initializer = _Anything
     tf.function = lambda f=None, **k: f if f is not None else (lambda g: g)
@@ -470,7 +609,37 @@ def install() -> types.ModuleType:
 def _resize(x, size, method):
     if method != "nearest":
         raise ValueError("only method='nearest' is in the shim (spade.py:17)")
-    return resize_nearest(x, size)
+    y = resize_nearest(x, size)
+    if _traced(x):
+        n = TRACER.fresh("resize")
+        TRACER.emit(TRACER.tg.resize_nearest(n, x.tf, [int(size[0]), int(size[1])], half_pixel_centers=True))
+        return TT(y, n)
+    return y
+
+
+def _leaky_relu(x, alpha=0.2):
+    a = _arr(x)
+    y = np.where(a > 0, a, alpha * a)
+    if _traced(x):
+        n = TRACER.fresh("lrelu")
+        TRACER.emit(TRACER.tg.leaky_relu(n, x.tf, alpha))
+        return TT(y, n)
+    return y
+
+
+def _moments(x, axes, keepdims=False):
+    a = _arr(x)
+    m, v = a.mean(axis=tuple(axes), keepdims=keepdims), a.var(axis=tuple(axes), keepdims=keepdims)
+    if _traced(x):
+        # tf.nn.moments = Mean, SquaredDifference, Mean.  The executor at hand (OpenCV) reduces over the spatial axes only,
+        # so traces run with a batch of ONE, where axes (0, 1, 2) and (1, 2) are the same reduction.
+        axes = tuple(axes)
+        assert keepdims and (axes == (1, 2) or (axes == (0, 1, 2) and a.shape[0] == 1)), "trace moments with batch 1"
+        tg, nm, nd, ns, nv = TRACER.tg, TRACER.fresh("mean"), TRACER.fresh("diff"), TRACER.fresh("sq"), TRACER.fresh("var")
+        TRACER.emit(tg.mean(nm, x.tf, [1, 2]) + tg.binary(nd, "Sub", x.tf, nm) + tg.binary(ns, "Mul", nd, nd) +
+                    tg.mean(nv, ns, [1, 2]))
+        return TT(m, nm), TT(v, nv)
+    return m, v
 
 
 def uninstall() -> None:
