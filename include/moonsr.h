@@ -165,10 +165,13 @@ int msr_blend_finalize(const float* d_wsum, const float* d_mean_acc, const float
  * bit-exact kernels to float32 rounding of the update (~1e-6 relative; tests/test_gpu_tiling.py).  Restrictions:
  * predictions are one contiguous float32 array (n, I, I) indexed through d_lattice; I % 64 == 0, S % 4 == 0; the output
  * window / accumulators are 16-byte aligned with pitches that are multiples of 4.  d_weights_f32 is the float32 copy of
- * msr_blend_tile's weight table. */
+ * msr_blend_tile's weight table; the tile form rebuilds the weight from the separable part of makeGaussianKernel
+ * (process_full_tiles.py:347-361): w(ry, rx) = d_weights_1d[ry - p] * d_weights_1d[rx - p] * c1 + c0 with
+ * d_weights_1d[i] = exp(-x_i^2 / 2 s^2) over the purge-cropped axis (I - 2p floats). */
 int msr_blend_tile_fast(const float* d_pred, const float* d_lohi, int n, const int32_t* d_lattice, int G,
-                        const float* d_weights_f32, int I, int S, int T, int add_half, float no_value, float* d_mean,
-                        float* d_std, uint8_t* d_good, int64_t pitch, int rows, int cols, void* stream);
+                        const float* d_weights_1d, float c1, float c0, int I, int S, int T, int add_half,
+                        float no_value, float* d_mean, float* d_std, uint8_t* d_good, int64_t pitch, int rows, int cols,
+                        void* stream);
 int msr_blend_accumulate_fast(const float* d_pred, const float* d_lohi, int k0, int n, const int32_t* d_lattice, int GY,
                               int GX, int gy_lo, int gy_hi, int lattice_y0, const float* d_weights_f32, int I, int S,
                               int add_half, float* d_wsum, float* d_mean, float* d_s, int64_t pitch, int acc_y0,

@@ -41,7 +41,8 @@ SIGNATURES: Dict[str, tuple] = {
     "msr_blend_accumulate": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _i64, _i, _i,
                                   _i, _i, _i, _vp]),
     "msr_blend_finalize": (_i, [_vp, _vp, _vp, _i64, _i, _i, _f, _vp, _vp, _vp, _i64, _vp]),
-    "msr_blend_tile_fast": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _i64, _i, _i, _vp]),
+    "msr_blend_tile_fast": (_i, [_vp, _vp, _i, _vp, _i, _vp, _f, _f, _i, _i, _i, _i, _f, _vp, _vp, _vp, _i64, _i, _i,
+                                 _vp]),
     "msr_blend_accumulate_fast": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _i64,
                                        _i, _i, _i, _i, _i, _vp]),
     "msr_tiff_lzw_bound": (_i64, [_i64]),

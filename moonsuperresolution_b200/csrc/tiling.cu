@@ -563,11 +563,15 @@ __device__ __forceinline__ void blend4_update(Blend4& st, const float4 v, const 
   }
 }
 
+// The weight of patch pixel (ry, rx) is rebuilt from the SEPARABLE part of makeGaussianKernel (:347-361):
+// w = e[ry] * e[rx] * c1 + c0 with e[i] = exp(-x_i^2 / 2s^2), c1 = A / (kmax - kmin), c0 = 1e-7 - kmin / (kmax - kmin), so
+// the 800 KB 2-D table (as many L2 bytes per contribution as the prediction itself) is replaced by a 1.8 KB 1-D table
+// that lives in L1; the result differs from the float32 cast of the float64 table by ~1e-7 relative.
 __global__ void __launch_bounds__(256) blend_tile_fast_kernel(const float* __restrict__ pred,
                                                               const float* __restrict__ lohi,
                                                               const int32_t* __restrict__ lattice, int G,
-                                                              const float* __restrict__ wtab, int I, int S,
-                                                              int add_half, float nv, float* __restrict__ mean_out,
+                                                              const float* __restrict__ w1d, float c1, float c0, int I,
+                                                              int S, int add_half, float nv, float* __restrict__ mean_out,
                                                               float* __restrict__ std_out, uint8_t* __restrict__ good_out,
                                                               int64_t pitch, int rows, int cols) {
   const int quads = (cols + 3) >> 2;
@@ -575,7 +579,7 @@ __global__ void __launch_bounds__(256) blend_tile_fast_kernel(const float* __res
   const int row = blockIdx.x / qblocks;
   const int col = ((blockIdx.x - row * qblocks) * blockDim.x + threadIdx.x) * 4;
   if (col >= cols || row >= rows) return;
-  const int off = I - S, p = I / 16, wp = I - 2 * p;
+  const int off = I - S, p = I / 16;
   const int Y = row + off, X = col + off;
   const int64_t II = (int64_t)I * I;
   const float half = add_half ? 0.5f : 0.f;
@@ -590,6 +594,7 @@ __global__ void __launch_bounds__(256) blend_tile_fast_kernel(const float* __res
   // loads are all in flight before the dependent update chain of the first one starts
   for (int gy = gy0; gy <= gy1; ++gy) {
     const int ry = Y - gy * S;
+    const float ey = __ldg(w1d + (ry - p)) * c1;
     for (int gxb = gx0; gxb <= gx1; gxb += 4) {
       int k[4];
 #pragma unroll
@@ -601,7 +606,8 @@ __global__ void __launch_bounds__(256) blend_tile_fast_kernel(const float* __res
         if (k[u] >= 0) {
           const int rx = X - (gxb + u) * S;
           v[u] = __ldcs(reinterpret_cast<const float4*>(pred + k[u] * II + (int64_t)ry * I + rx));   // read once
-          wt[u] = __ldg(reinterpret_cast<const float4*>(wtab + (int64_t)(ry - p) * wp + (rx - p)));
+          const float4 ex = __ldg(reinterpret_cast<const float4*>(w1d + (rx - p)));
+          wt[u] = make_float4(fmaf(ex.x, ey, c0), fmaf(ex.y, ey, c0), fmaf(ex.z, ey, c0), fmaf(ex.w, ey, c0));
           lh[u] = __ldg(reinterpret_cast<const float2*>(lohi) + k[u]);
         }
       }
@@ -813,9 +819,10 @@ extern "C" int msr_blend_finalize(const float* d_wsum, const float* d_mean_acc, 
 static bool fast_blend_geometry_ok(int I, int S) { return I % 64 == 0 && S % 4 == 0 && S > 0 && S <= I; }
 
 extern "C" int msr_blend_tile_fast(const float* d_pred, const float* d_lohi, int n, const int32_t* d_lattice, int G,
-                                   const float* d_weights_f32, int I, int S, int T, int add_half, float no_value,
-                                   float* d_mean, float* d_std, uint8_t* d_good, int64_t pitch, int rows, int cols,
-                                   void* stream) {
+                                   const float* d_weights_1d, float c1, float c0, int I, int S, int T, int add_half,
+                                   float no_value, float* d_mean, float* d_std, uint8_t* d_good, int64_t pitch, int rows,
+                                   int cols, void* stream) {
+  const float* d_weights_f32 = d_weights_1d;
   MSR_REQUIRE(d_weights_f32 && d_mean && d_std && d_good && d_lattice && G > 0, "msr_blend_tile_fast: null pointer");
   MSR_REQUIRE(n == 0 || (d_pred && d_lohi), "msr_blend_tile_fast: null patch tables");
   MSR_REQUIRE(fast_blend_geometry_ok(I, S), "msr_blend_tile_fast: needs I % 64 == 0 and S % 4 == 0");
@@ -831,7 +838,8 @@ extern "C" int msr_blend_tile_fast(const float* d_pred, const float* d_lohi, int
   const int quads = (cols + 3) / 4;
   MSR_REQUIRE((int64_t)ceil_div(quads, 256) * rows < (1ll << 31), "msr_blend_tile_fast: window too large");
   blend_tile_fast_kernel<<<dim3((unsigned)(ceil_div(quads, 256) * rows)), 256, 0, (cudaStream_t)stream>>>(
-      d_pred, d_lohi, d_lattice, G, d_weights_f32, I, S, add_half, no_value, d_mean, d_std, d_good, pitch, rows, cols);
+      d_pred, d_lohi, d_lattice, G, d_weights_1d, c1, c0, I, S, add_half, no_value, d_mean, d_std, d_good, pitch, rows,
+      cols);
   count_launch();
   MSR_LAUNCH_CHECK();
   return MSR_OK;

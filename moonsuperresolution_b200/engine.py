@@ -480,6 +480,22 @@ class DEMSuperResolution:
             self._weights_dev_f32 = self._blend_weights().to(_torch().float32).contiguous()
         return self._weights_dev_f32
 
+    def _blend_weights_separable(self):
+        """makeGaussianKernel (:347-361) is A * e(x) * e(y) before its min-max normalisation, so the purge-cropped weight
+        is e[ry] * e[rx] * c1 + c0: (device float32 e over the cropped axis, c1, c0), constants formed in float64."""
+        if getattr(self, "_weights_sep", None) is None:
+            torch = _torch()
+            i = self.image_size
+            p, s = i // 16, i / 5
+            x = np.linspace(-i / 2, i / 2, i)
+            e = np.exp(-(x ** 2.) / (2. * s ** 2.))
+            a = 1. / (2. * np.pi * s * s)
+            kmin, kmax = a * e.min() ** 2, a * e.max() ** 2
+            c1, c0 = a / (kmax - kmin), 1e-7 - kmin / (kmax - kmin)
+            e_dev = torch.from_numpy(np.ascontiguousarray(e[p:i - p], dtype=np.float32)).to(self.device)
+            self._weights_sep = (e_dev, float(c1), float(c0))
+        return self._weights_sep
+
     def _fast_blend_ok(self) -> bool:
         """The float32 / 128-bit blend kernels need 4-pixel groups that share their patches and aligned rows."""
         return (self.blend == "fast" and self.image_size % 64 == 0 and self.stride % 4 == 0 and
@@ -494,8 +510,9 @@ class DEMSuperResolution:
         g = -(-(plan_t + plan_i - plan_s) // plan_s)
         if (pred is not None and lattice is not None and f64flags is None and self._fast_blend_ok() and pitch % 4 == 0
                 and mean % 16 == 0 and std % 16 == 0 and good % 4 == 0):
+            e_dev, c1, c0 = self._blend_weights_separable()
             _lib.check(self._lib.msr_blend_tile_fast(pred.data_ptr(), _lib.ptr(lohi), n, _lib.ptr(lattice), g,
-                                                     self._blend_weights_f32().data_ptr(), plan_i, plan_s, plan_t,
+                                                     e_dev.data_ptr(), c1, c0, plan_i, plan_s, plan_t,
                                                      int(add_half), float(np.float32(self.no_value)), mean, std, good,
                                                      pitch, rows, cols, _lib.stream_ptr()), "msr_blend_tile_fast")
             self.launches += 1
