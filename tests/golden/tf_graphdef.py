@@ -9,6 +9,8 @@ reference code builds a functional Keras model (e.g. Pix2Pix.buildGenerator, pix
 chain per Keras layer -- the graph structure comes from the reference's source, the op semantics from OpenCV."""
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 DT_FLOAT, DT_INT32 = 1, 3
@@ -164,6 +166,10 @@ def run_opencv(graph: bytes, x_nhwc, path: str, output: str = None) -> np.ndarra
     with open(path, "wb") as f:
         f.write(graph)
     net = cv2.dnn.readNetFromTensorflow(path)
+    try:
+        os.remove(path)          # the graphs of whole generators are hundreds of MB: do not leave them in pytest's tmp dirs
+    except OSError:
+        pass
     feeds = x_nhwc if isinstance(x_nhwc, dict) else {"input": x_nhwc}
     for name, a in feeds.items():
         a = np.asarray(a, np.float32)

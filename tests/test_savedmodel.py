@@ -121,3 +121,57 @@ def test_user_supplied_keras_checkpoint(tmp_path):
     got = SM.load_gaugan_weights(os.path.join(root, "generator"), os.path.join(root, "encoder"), i)
     W.check_weights("spade", i, got)
     assert SM.read_object_graph(os.path.join(root, "generator", "variables", "variables")) is not None
+
+
+def test_against_tensorflows_own_proto_schema_and_crc(tmp_path):
+    """tensorboard ships TensorFlow's compiled .proto schemas and a TensorFlow-team implementation of the masked CRC-32C
+    (its TFRecord writer): independent of this repository.  (1) the reader's CRC equals theirs; (2) a TrackableObjectGraph
+    built and serialised with the OFFICIAL trackable_object_graph_pb2 classes -- heads numbered the 'wrong' way round --
+    is embedded in a bundle and resolved correctly by savedmodel.py's hand-written parser; (3) the test writer's own
+    object graph parses under the official schema to the same structure."""
+    pw = pytest.importorskip("tensorboard.compat.tensorflow_stub.pywrap_tensorflow")
+    tog = pytest.importorskip("tensorboard.compat.proto.trackable_object_graph_pb2")
+    rng = np.random.default_rng(3)
+    for n in (0, 1, 7, 4096):
+        blob = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        assert SM.crc32c(blob) == pw.crc32c(blob) and SM.masked_crc(blob) == pw.masked_crc32c(blob)
+    i = 64
+    weights = W.random_init("spade", i, seed=6, perturb_affine=True)
+    enc_keys = TW.keras_encoder_keys(weights)
+    swapped = {}
+    for key, a in enc_keys.items():                       # variance = layer_with_weights-5, mean = -6
+        key = key.replace("layer_with_weights-5/", "layer_with_weights-X/").replace("layer_with_weights-6/", "layer_with_weights-5/")
+        swapped[key.replace("layer_with_weights-X/", "layer_with_weights-6/")] = a
+    graph = tog.TrackableObjectGraph()
+    graph.nodes.add()                                      # root
+    ids = {(): 0}
+    for key in sorted(swapped):
+        parts = tuple(key[:-len(TW.SUFFIX)].split("/"))
+        for depth in range(1, len(parts) + 1):
+            path = parts[:depth]
+            if path not in ids:
+                graph.nodes.add()
+                ids[path] = len(graph.nodes) - 1
+                ref = graph.nodes[ids[path[:-1]]].children.add()
+                ref.node_id, ref.local_name = ids[path], path[-1]
+        att = graph.nodes[ids[parts]].attributes.add()
+        att.name, att.checkpoint_key = "VARIABLE_VALUE", key
+        top = int(parts[0].split("-")[1])
+        att.full_name = (("variance/" if top == 5 else "mean/") + parts[-1]) if top >= 5 else "/".join(parts)
+    d = tmp_path / "encoder"
+    TW.write_bundle(str(d / "variables" / "variables"), swapped,
+                    string_tensors={"_CHECKPOINTABLE_OBJECT_GRAPH": graph.SerializeToString()})
+    nodes = SM.read_object_graph(str(d / "variables" / "variables"))
+    assert nodes is not None and len(nodes) == len(graph.nodes)
+    found = SM.read_saved_model_variables(str(d))
+    resolved = SM.resolve_encoder_keys(nodes, found)
+    assert resolved["layer_with_weights-5/kernel"] == "enc.variance.kernel"
+    assert resolved["layer_with_weights-6/bias"] == "enc.mean.bias"
+    assert sorted(resolved.values()) == sorted(SM.encoder_key_map().values())
+    # and the other direction: the writer's hand-encoded graph under the official schema
+    mine = tog.TrackableObjectGraph()
+    mine.ParseFromString(TW.object_graph_proto(TW.keras_generator_keys(weights)))
+    names = {c.local_name for c in mine.nodes[0].children}
+    assert {f"layer_with_weights-{k}" for k in range(8)} <= names and "keras_api" in names
+    keys = {a.checkpoint_key for n in mine.nodes for a in n.attributes}
+    assert keys == set(TW.keras_generator_keys(weights))

@@ -173,3 +173,34 @@ def test_reference_residual_block_with_learned_skip_run_by_opencv(tmp_path):
         ref.close()
     got = TG.run_opencv(graph, {"input": x, "mask": mask}, str(tmp_path / "rb.pb"), output=y.tf)
     assert np.abs(got - want).max() <= 2e-5 * np.abs(want).max()
+
+
+def test_hand_encoded_graphdefs_parse_under_tensorflows_own_schema(tmp_path):
+    """tests/golden/tf_graphdef.py writes the GraphDef wire format by hand; tensorboard ships TensorFlow's compiled
+    graph.proto / node_def.proto / attr_value.proto / tensor.proto.  Parsed with those, the nodes carry the intended ops,
+    inputs, attributes and tensor contents -- so what OpenCV executes is what TensorFlow would read."""
+    gp = pytest.importorskip("tensorboard.compat.proto.graph_pb2")
+    rng = np.random.default_rng(2)
+    k = rng.standard_normal((4, 4, 3, 2)).astype(np.float32)
+    raw = (TG.placeholder("input") + TG.conv2d("c", "input", k, 2) + TG.bias_add("cb", "c", np.arange(2, dtype=np.float32)) +
+           TG.leaky_relu("l", "cb", 0.2) + TG.resize_nearest("r", "l", [8, 8]) + TG.mean("m", "r", [1, 2]) +
+           TG.concat("cat", ["r", "r"]) + TG.conv2d_transpose("t", "cat", rng.standard_normal((4, 4, 1, 4)).astype(np.float32), 2,
+                                                               [1, 16, 16, 1]))
+    g = gp.GraphDef()
+    g.ParseFromString(raw)
+    nodes = {n.name: n for n in g.node}
+    assert [nodes[n].op for n in ("input", "c", "cb", "l", "r", "m", "cat", "t")] == \
+        ["Placeholder", "Conv2D", "BiasAdd", "LeakyRelu", "ResizeNearestNeighbor", "Mean", "ConcatV2", "Conv2DBackpropInput"]
+    c = nodes["c"]
+    assert list(c.input) == ["input", "c/w"] and list(c.attr["strides"].list.i) == [1, 2, 2, 1]
+    assert c.attr["padding"].s == b"SAME" and c.attr["data_format"].s == b"NHWC" and c.attr["T"].type == 1
+    w = nodes["c/w"].attr["value"].tensor
+    assert [d.size for d in w.tensor_shape.dim] == [4, 4, 3, 2] and w.dtype == 1
+    np.testing.assert_array_equal(np.frombuffer(w.tensor_content, np.float32).reshape(4, 4, 3, 2), k)
+    assert abs(nodes["l"].attr["alpha"].f - 0.2) < 1e-7
+    assert nodes["r"].attr["half_pixel_centers"].b is True and nodes["r"].attr["align_corners"].b is False
+    assert nodes["m"].attr["keep_dims"].b is True
+    assert list(np.frombuffer(nodes["m/axes"].attr["value"].tensor.tensor_content, np.int32)) == [1, 2]
+    assert nodes["cat"].attr["N"].i == 2 and list(nodes["cat/axis"].attr["value"].tensor.int_val) == [3]
+    assert list(nodes["t"].input) == ["t/shape", "t/w", "cat"]
+    assert list(np.frombuffer(nodes["t/shape"].attr["value"].tensor.tensor_content, np.int32)) == [1, 16, 16, 1]
