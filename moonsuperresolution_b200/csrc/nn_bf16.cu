@@ -549,8 +549,20 @@ __global__ void __launch_bounds__(256) stats_pairs_partial_kernel(const float2* 
   double s0 = 0.0, q0 = 0.0, s1 = 0.0, q1 = 0.0;
   if (c < C) {
     const float2* base = pairs + ((int64_t)g * rows_p) * C + c;
-    for (int64_t r = r0 + ry; r < r1; r += 8) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(base + r * C));
+    int64_t r = r0 + ry;
+    // four independent 16-byte loads in flight per thread (the sums stay in row order: a, b, c, d are added in turn)
+    for (; r + 24 < r1; r += 32) {
+      const float4 a = __ldcs(reinterpret_cast<const float4*>(base + r * C));
+      const float4 b = __ldcs(reinterpret_cast<const float4*>(base + (r + 8) * C));
+      const float4 cc = __ldcs(reinterpret_cast<const float4*>(base + (r + 16) * C));
+      const float4 d = __ldcs(reinterpret_cast<const float4*>(base + (r + 24) * C));
+      s0 += (double)a.x; q0 += (double)a.y; s1 += (double)a.z; q1 += (double)a.w;
+      s0 += (double)b.x; q0 += (double)b.y; s1 += (double)b.z; q1 += (double)b.w;
+      s0 += (double)cc.x; q0 += (double)cc.y; s1 += (double)cc.z; q1 += (double)cc.w;
+      s0 += (double)d.x; q0 += (double)d.y; s1 += (double)d.z; q1 += (double)d.w;
+    }
+    for (; r < r1; r += 8) {
+      const float4 v = __ldcs(reinterpret_cast<const float4*>(base + r * C));
       s0 += (double)v.x;
       q0 += (double)v.y;
       s1 += (double)v.z;

@@ -222,6 +222,7 @@ __global__ void __launch_bounds__(256) stats_partial_kernel(const T* __restrict_
   double s[4] = {0.0, 0.0, 0.0, 0.0}, q[4] = {0.0, 0.0, 0.0, 0.0};
   if (c < C) {
     const T* base = x + ((int64_t)g * rows) * ld + c;
+#pragma unroll 4
     for (int64_t r = r0 + ry; r < r1; r += 8) {
       const float4 v4 = __ldg(reinterpret_cast<const float4*>(base + r * ld));
       const float v[4] = {v4.x, v4.y, v4.z, v4.w};

@@ -28,6 +28,7 @@ _lib.profile_enable(True)
 m.forward_device(src, out, eps, G)
 fam = _lib.profile_read()
 rec = _lib.profile_records("conv_tc")
+other = {f: _lib.profile_records(f) for f in ("stats", "mask_conv", "elementwise", "dense")}
 _lib.profile_enable(False)
 tot = sum(v["ms"] for v in fam.values())
 for k, v in fam.items():
@@ -36,3 +37,7 @@ for k, v in fam.items():
 print("conv_tc launches in order: idx ms GFLOP TFLOP/s")
 for k, (ms, wk) in enumerate(rec):
     print("%3d %8.4f %9.2f %8.1f" % (k, ms, wk / 1e9, wk / ms / 1e9 if ms > 0 else 0))
+for f, rs in other.items():
+    print(f + " launches in order: idx ms MB GB/s")
+    for k, (ms, wk) in enumerate(rs):
+        print("%3d %8.4f %9.2f %8.1f" % (k, ms, wk / 1e6, wk / ms / 1e6 if ms > 0 else 0))
