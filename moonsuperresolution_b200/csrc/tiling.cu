@@ -822,12 +822,11 @@ extern "C" int msr_blend_tile_fast(const float* d_pred, const float* d_lohi, int
                                    const float* d_weights_1d, float c1, float c0, int I, int S, int T, int add_half,
                                    float no_value, float* d_mean, float* d_std, uint8_t* d_good, int64_t pitch, int rows,
                                    int cols, void* stream) {
-  const float* d_weights_f32 = d_weights_1d;
-  MSR_REQUIRE(d_weights_f32 && d_mean && d_std && d_good && d_lattice && G > 0, "msr_blend_tile_fast: null pointer");
+  MSR_REQUIRE(d_weights_1d && d_mean && d_std && d_good && d_lattice && G > 0, "msr_blend_tile_fast: null pointer");
   MSR_REQUIRE(n == 0 || (d_pred && d_lohi), "msr_blend_tile_fast: null patch tables");
   MSR_REQUIRE(fast_blend_geometry_ok(I, S), "msr_blend_tile_fast: needs I % 64 == 0 and S % 4 == 0");
   MSR_REQUIRE(rows >= 0 && cols >= 0 && rows <= T && cols <= T && pitch >= cols, "msr_blend_tile_fast: bad output window");
-  MSR_REQUIRE(((reinterpret_cast<uintptr_t>(d_pred) | reinterpret_cast<uintptr_t>(d_weights_f32) |
+  MSR_REQUIRE(((reinterpret_cast<uintptr_t>(d_pred) | reinterpret_cast<uintptr_t>(d_weights_1d) |
                 reinterpret_cast<uintptr_t>(d_mean) | reinterpret_cast<uintptr_t>(d_std)) & 15) == 0 &&
                   (reinterpret_cast<uintptr_t>(d_good) & 3) == 0 && (pitch & 3) == 0,
               "msr_blend_tile_fast: predictions, weights and the output window must be 16-byte aligned (W % 4 == 0)");
