@@ -280,6 +280,15 @@ int msr_op_spade_tc(const uint16_t* d_a, const uint16_t* d_w, const float* d_bia
                     const float* d_mean, const float* d_rstd, int samples_per_group, uint16_t* d_out, int n, int r,
                     int C, void* stream);
 
+/* The one-channel sub-pixel phase layer (networks.py:54-56 / pix2pix.py:91-95 after the phase decomposition) in its
+ * "contract once per pixel, then stencil" form (csrc/phase_tc.cu).  d_x (n, r, r, cin) bf16 on the device; h_w4 (4, 9*cin)
+ * bf16 bits on the HOST: row q = py*2 + px holds the 3x3 filter of sub-pixel phase q, k = (ky*3 + kx)*cin + c (all-zero
+ * taps are dropped); d_bias one float32 or NULL; act 0 none / 3 tanh; d_y (n, 2r, 2r) float32 with
+ * y[b][2h+py][2w+px] = act(bias + sum_{ky,kx,c} x[b][h+ky-1][w+kx-1][c] * w4[q][ky][kx][c]), zero outside the tensor.
+ * r must be 128 or 256, cin 64 or 128.  Synchronises the stream before it returns. */
+int msr_op_phase_tc(const uint16_t* d_x, const uint16_t* h_w4, const float* d_bias, float* d_y, int n, int r, int cin,
+                    int act, void* stream);
+
 /* Optimisation aid: when d_counters != NULL (148 * 8 int64, zero-initialised by the caller), every tensor-core convolution
  * planned afterwards records per-CTA cycle counts: [0] producer wait on empty stages, [1] producer total, [2] MMA issuer
  * wait on full stages, [3] MMA issuer wait on free accumulators, [4] MMA issuer total, [5] epilogue wait on accumulators.

@@ -171,6 +171,34 @@ extern "C" int msr_op_conv_tc(const uint16_t* d_x, const uint16_t* d_w, const fl
   return rc;
 }
 
+extern "C" int msr_op_phase_tc(const uint16_t* d_x, const uint16_t* h_w4, const float* d_bias, float* d_y, int n, int r,
+                               int cin, int act, void* stream) {
+  MSR_REQUIRE(d_x && h_w4 && d_y, "msr_op_phase_tc: null pointer");
+  MSR_REQUIRE(phase_tc_supported(r, cin), "msr_op_phase_tc: needs r in {128, 256} and cin in {64, 128}");
+  std::vector<uint16_t> wg;
+  PhaseTable tab;
+  if (phase_tc_pack(h_w4, cin, &wg, &tab) <= 0)
+    return fail(MSR_E_INVALID, "msr_op_phase_tc: no or too many non-zero (tap, phase) filters");
+  void* d_wg = nullptr;
+  MSR_CUDA_CHECK(cudaMalloc(&d_wg, wg.size() * 2));
+  int rc = MSR_OK;
+  PhaseTC* plan = nullptr;
+  if (cudaMemcpy(d_wg, wg.data(), wg.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) {
+    rc = fail(MSR_E_CUDA, "msr_op_phase_tc: weight upload failed");
+  } else {
+    PhaseTCArgs a;
+    a.x = reinterpret_cast<const __nv_bfloat16*>(d_x);
+    a.wg = reinterpret_cast<const __nv_bfloat16*>(d_wg);
+    a.tab = &tab; a.bias = d_bias; a.y = d_y; a.n = n; a.r = r; a.cin = cin; a.act = act;
+    rc = phase_tc_plan_create(&plan, a);
+    if (!rc) rc = phase_tc_launch(plan, (cudaStream_t)stream);
+    if (!rc && cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) rc = fail(MSR_E_CUDA, "msr_op_phase_tc: kernel failed");
+  }
+  if (plan) phase_tc_plan_destroy(plan);
+  cudaFree(d_wg);
+  return rc;
+}
+
 extern "C" int msr_op_conv3x3_f32(const float* d_x, const float* d_w, const float* d_bias, float* d_y, int n, int r,
                                   int cin, int cout, void* stream) {
   ConvF32 c;

@@ -115,6 +115,11 @@ struct msr_generator {
   float* a_f32 = nullptr; float* gb_f32 = nullptr; float* act_f32 = nullptr;      // fp32 mode
   __nv_bfloat16* a_bf16 = nullptr; __nv_bfloat16* act_bf16 = nullptr;               // bf16 mode
   std::map<int, std::vector<ConvTC*>> plans;   // (n_groups, repeat phase) -> plans in launch order
+  // last layer (one output channel, 4 sub-pixel phases) in its "contract once per pixel, then stencil" form (phase_tc.cu)
+  const __nv_bfloat16* ph_wg = nullptr;        // [32][cin] columns = (tap, phase) pairs with a non-zero filter
+  PhaseTable ph_tab;
+  bool ph_ok = false;
+  std::map<int64_t, PhaseTC*> phase_plans;     // patches per call -> plan
   // repeated-sample mode: gamma | beta of the 15 SPADE layers for the batch being repeated (allocated on first use)
   __nv_bfloat16* gb_cache[15] = {};
   int64_t gb_cache_slots = 0;                  // patches the cache was allocated for
@@ -130,6 +135,7 @@ struct msr_generator {
   ~msr_generator() {
     for (auto& kv : plans)
       for (auto* p : kv.second) conv_tc_plan_destroy(p);
+    for (auto& kv : phase_plans) phase_tc_plan_destroy(kv.second);
     for (void* p : allocs) cudaFree(p);
   }
 };
@@ -195,6 +201,45 @@ int upload_bf16(msr_generator* g, const std::vector<uint16_t>& h, const __nv_bfl
   MSR_CUDA_CHECK(cudaMemcpy(p, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
   *out = reinterpret_cast<const __nv_bfloat16*>(p);
   return MSR_OK;
+}
+
+// MSR_TC_PHASE=0 keeps the last layer on the 9-tap implicit GEMM of conv_tc.cu (A/B runs)
+static const bool g_disable_phase_tc = [] {
+  const char* e = getenv("MSR_TC_PHASE");
+  return e != nullptr && e[0] == '0';
+}();
+
+// last layer: columns of the per-pixel GEMM from the [32][9 * cin] phase-combined filters (rows 0..3 real)
+int pack_phase_layer(msr_generator* g, const std::vector<uint16_t>& w32, int cin) {
+  g->ph_ok = false;
+  if (g_disable_phase_tc || (cin != 64 && cin != 128)) return MSR_OK;
+  std::vector<uint16_t> wg;
+  if (phase_tc_pack(w32.data(), cin, &wg, &g->ph_tab) <= 0) return MSR_OK;   // the 9-tap form stays
+  int rc = upload_bf16(g, wg, &g->ph_wg);
+  if (rc) return rc;
+  g->ph_ok = true;
+  return MSR_OK;
+}
+
+// the last layer through phase_tc.cu when its shape allows (r = 128 / 256); false = the caller runs the 9-tap form
+int run_phase_layer(msr_generator* g, const __nv_bfloat16* x, int n, int r, int cin, int x_pitch, const float* bias,
+                    int act, float* out, double alg_flops, cudaStream_t st, bool* done) {
+  *done = false;
+  if (!g->ph_ok || !phase_tc_supported(r, cin)) return MSR_OK;
+  PhaseTC*& plan = g->phase_plans[n];
+  if (plan == nullptr) {
+    PhaseTCArgs a;
+    a.x = x; a.wg = g->ph_wg; a.tab = &g->ph_tab; a.bias = bias; a.y = out; a.n = n; a.r = r; a.cin = cin;
+    a.x_pitch = x_pitch; a.act = act; a.alg_flops = alg_flops;
+    int rc = phase_tc_plan_create(&plan, a);
+    if (rc) {
+      g->phase_plans.erase(n);
+      return rc;
+    }
+  }
+  phase_tc_set_output(plan, out);
+  *done = true;
+  return phase_tc_launch(plan, st);
 }
 
 int load_spade(msr_generator* g, const std::string& pre, int C, SpadeW* s) {
@@ -297,6 +342,7 @@ int finalize_spade_bf16_extras(msr_generator* g) {
     std::vector<uint16_t> w(acc.size());
     for (size_t e = 0; e < w.size(); ++e) w[e] = f2bf(acc[e]);
     if ((rc = upload_bf16(g, w, &g->out_wt))) return rc;
+    if ((rc = pack_phase_layer(g, w, 128))) return rc;
   }
   {  // encoder block 1: im2col GEMM weights [64][64]
     if ((rc = need(g, "enc.down1.kernel", {3, 3, 2, kEnc[0]}, &t))) return rc;
@@ -532,7 +578,9 @@ int finalize_pix2pix_bf16(msr_generator* g) {
     cin = cout;
   }
   // transposed convs: Keras kernel [ky][kx][cout][cin] -> phase weights [(py*2+px)*cout + co][(ty*3+tx)*cin + ci]
-  auto phase_weights = [&](const std::string& name, int cout, int cin_, int rows_padded, const __nv_bfloat16** out) -> int {
+  std::vector<uint16_t> last_pw;
+  auto phase_weights = [&](const std::string& name, int cout, int cin_, int rows_padded, const __nv_bfloat16** out,
+                           std::vector<uint16_t>* keep = nullptr) -> int {
     const HostTensor* w;
     int r = need(g, name, {4, 4, cout, cin_}, &w);
     if (r) return r;
@@ -551,6 +599,7 @@ int finalize_pix2pix_bf16(msr_generator* g) {
               for (int ci = 0; ci < cin_; ++ci) dst[ci] = f2bf(src[ci]);
             }
           }
+    if (keep) *keep = pw;
     return upload_bf16(g, pw, out);
   };
   for (int k = 0; k < 7; ++k) {
@@ -559,7 +608,8 @@ int finalize_pix2pix_bf16(msr_generator* g) {
     if ((rc = fold_bn(pre, kP2PUp[k], &g->put_scale[k], &g->put_shift[k]))) return rc;
     cin = kP2PUp[k] + kP2PDown[6 - k];
   }
-  if ((rc = phase_weights("p2p.last.kernel", 1, cin, 32, &g->plt_w))) return rc;
+  if ((rc = phase_weights("p2p.last.kernel", 1, cin, 32, &g->plt_w, &last_pw))) return rc;
+  if ((rc = pack_phase_layer(g, last_pw, cin))) return rc;
   if ((rc = upload_named(g, "p2p.last.bias", {1}, &g->pl_b))) return rc;
   // cat[k] (k = 0..6) holds [up_{k+1} | down_{7-k}] at spatial side 2^(k+1), bf16
   for (int k = 0; k < 7; ++k) {
@@ -942,7 +992,10 @@ int forward_spade_bf16(Fwd& f, const float* source, const float* eps, float* out
     r *= 2;
   }
   // UpSampling2D -> leaky_relu(0.2) -> Conv2D(1, 4, 'same') == 3x3 conv to 4 sub-pixel phases on the low-res tensor
-  {
+  bool phase_done = false;
+  if ((rc = run_phase_layer(g, g->a_bf16, n, r / 2, 128, 0, g->out_b, ACT_NONE, out, 2.0 * (double)n * I * I * 16 * 128, st,
+                            &phase_done))) return rc;
+  if (!phase_done) {
     ConvTCArgs a;
     a.x = g->a_bf16; a.w = g->out_wt; a.n = n; a.r = r / 2; a.cin = 128; a.ncols = 32;
     a.epilogue = TC_EPI_PHASE_F32; a.bias = g->out_b; a.y = out;
@@ -1058,11 +1111,16 @@ int forward_pix2pix_bf16(Fwd& f, const float* source, float* out) {
     x = g->catb[k]; cin = pitch; x_pitch = pitch;
   }
   // ---- last ConvT(1, 4, s2) + bias + tanh
-  ConvTCArgs a;
-  a.x = x; a.w = g->plt_w; a.n = n; a.r = s; a.cin = cin; a.x_pitch = x_pitch; a.ncols = 32;
-  a.epilogue = TC_EPI_PHASE_F32; a.bias = g->pl_b; a.act = ACT_TANH; a.y = out;
-  a.alg_flops = 2.0 * (double)n * (2 * s) * (2 * s) * 4 * cin;
-  if ((rc = tc_conv(f, a))) return rc;
+  bool phase_done = false;
+  if ((rc = run_phase_layer(g, x, n, s, cin, x_pitch, g->pl_b, ACT_TANH, out, 2.0 * (double)n * (2 * s) * (2 * s) * 4 * cin,
+                            st, &phase_done))) return rc;
+  if (!phase_done) {
+    ConvTCArgs a;
+    a.x = x; a.w = g->plt_w; a.n = n; a.r = s; a.cin = cin; a.x_pitch = x_pitch; a.ncols = 32;
+    a.epilogue = TC_EPI_PHASE_F32; a.bias = g->pl_b; a.act = ACT_TANH; a.y = out;
+    a.alg_flops = 2.0 * (double)n * (2 * s) * (2 * s) * 4 * cin;
+    if ((rc = tc_conv(f, a))) return rc;
+  }
   g->acts["out"] = {out, (int64_t)n * 256 * 256, 0};
   return MSR_OK;
 }

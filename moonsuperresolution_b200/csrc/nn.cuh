@@ -1,5 +1,7 @@
 // Device-side operator launchers shared by the generator graphs (declarations).
 #pragma once
+#include <vector>
+
 #include "common.cuh"
 
 namespace msr {
@@ -111,6 +113,33 @@ int conv_tc_plan_create(ConvTC** plan, const ConvTCArgs& a);
 int conv_tc_launch(const ConvTC* plan, cudaStream_t st);
 void conv_tc_update_pointers(ConvTC* plan, const ConvTCArgs& a);   // refresh the epilogue pointers of a cached plan
 void conv_tc_plan_destroy(ConvTC* plan);
+
+// ---- one-channel sub-pixel phase layers (phase_tc.cu): 1x1 GEMM per pixel + 3x3 stencil of scalars ---------------------
+// networks.py:54-56 (UpSampling2D -> leaky_relu -> Conv2D(1, 4)) and pix2pix.py:91-95 (Conv2DTranspose(1, 4, s2) + tanh)
+constexpr int kPhaseMaxCols = 25;    // (tap, phase) pairs with a non-zero filter: 25 for the former, 16 for the latter
+struct PhaseTable {
+  int kind = -1;                     // 0: 4x4 conv of the x2-upsampled tensor, 1: 4x4 stride-2 transposed conv
+  int ncols = 0;                     // 25 / 16 columns, ordered phase-major, then ty, then tx
+};
+struct PhaseTC;  // opaque plan
+struct PhaseTCArgs {
+  const __nv_bfloat16* x = nullptr;   // [n][r][r][x_pitch] bf16, channels [0, cin) are read
+  const __nv_bfloat16* wg = nullptr;  // [32][cin] bf16: row j = the cin weights of column j (phase_tc_pack), rest zero
+  const PhaseTable* tab = nullptr;
+  const float* bias = nullptr;        // one value or null
+  float* y = nullptr;                 // [n][2r][2r] fp32
+  int n = 0, r = 0, cin = 0, x_pitch = 0;
+  int act = ACT_NONE;                 // ACT_NONE or ACT_TANH
+  double alg_flops = 0.0;
+};
+bool phase_tc_supported(int r, int cin);
+// w4: the [4][9*cin] bf16 phase-combined 3x3 filters (the real rows of the TC_EPI_PHASE_F32 weight matrix) -> wg, table.
+// Returns the number of columns, or -1 when the non-zero pattern is neither of the two layer kinds.
+int phase_tc_pack(const uint16_t* w4, int cin, std::vector<uint16_t>* wg, PhaseTable* tab);
+int phase_tc_plan_create(PhaseTC** plan, const PhaseTCArgs& a);
+int phase_tc_launch(const PhaseTC* plan, cudaStream_t st);
+void phase_tc_set_output(PhaseTC* plan, float* y);
+void phase_tc_plan_destroy(PhaseTC* plan);
 
 // ---- small helpers for the bf16 path (nn_bf16.cu) -----------------------------------------------------------------
 // im2col of the 2-channel source for a 3x3 convolution at output side r: out [n][r][r][64] bf16, channel (ky*3+kx)*2+c

@@ -107,6 +107,78 @@ def test_conv_tc_general_operator(torch, n, r_out, cin, cout, taps, stride, pad,
         np.testing.assert_allclose(p[5, :, 0], flat[5 * 32:6 * 32].sum(0), rtol=1e-5, atol=1e-4)
 
 
+def _phase_filters(kernel, transposed):
+    """(4, 4, cin) kernel of the one-channel last layer -> (4, 3, 3, cin) sub-pixel phase filters on the LOW-resolution
+    tensor.  transposed=False: UpSampling2D(2) -> Conv2D(1, 4, 'same') (networks.py:54-56; SAME pads 1 before, 2 after);
+    transposed=True: Conv2DTranspose(1, 4, strides=2, 'same') (pix2pix.py:91-95)."""
+    cin = kernel.shape[-1]
+    w4 = np.zeros((4, 3, 3, cin), np.float32)
+    for py in range(2):
+        for px in range(2):
+            if not transposed:
+                for ky in range(4):
+                    for kx in range(4):
+                        ty, tx = (py - 1 + ky) // 2 + 1, (px - 1 + kx) // 2 + 1
+                        w4[py * 2 + px, ty, tx] += kernel[ky, kx]
+            else:
+                for ty in range(3):
+                    for tx in range(3):
+                        ky, kx = py + 1 - 2 * (ty - 1), px + 1 - 2 * (tx - 1)
+                        if 0 <= ky <= 3 and 0 <= kx <= 3:
+                            w4[py * 2 + px, ty, tx] = kernel[ky, kx]
+    return w4
+
+
+@pytest.mark.parametrize("n,r,cin,transposed", [
+    (2, 128, 64, True),       # few patches: 2 output rows per work unit
+    (3, 256, 128, False),     # ragged batch, r = 256: one image row per 256-pixel group
+    (5, 128, 128, True),      # pix2pix's last layer (two image rows per group), tanh
+    (40, 256, 128, False),    # the bench call shape's schedule: 16 output rows per work unit, several units per CTA
+    (80, 128, 128, False),
+])
+def test_phase_layer_tensor_core_operator(torch, n, r, cin, transposed):
+    """The last layer in its "contract once per pixel, then 3x3 stencil of scalars" form (csrc/phase_tc.cu) against
+    torch's float64 convolution at FULL resolution on bf16-rounded operands (the phase filters are summed in float32 and
+    rounded to bf16 before both sides use them, as generator.cu does)."""
+    from moonsuperresolution_b200 import _lib
+    import torch.nn.functional as F
+    rng = np.random.default_rng(n * 1000 + r + cin)
+    x = bf16_round(rng.standard_normal((n, r, r, cin)).astype(np.float32), torch)
+    x[0, 0, :, :] = 3.0                                  # borders carry weight: SAME padding must be zeros there
+    x[-1, :, -1, :] = -2.0
+    kernel = (rng.standard_normal((4, 4, cin)) / np.sqrt(16 * cin)).astype(np.float32)
+    w4 = bf16_round(_phase_filters(kernel, transposed), torch)              # (4, 3, 3, cin)
+    bias = np.array([0.3], np.float32)
+    # reference: the 4 phase filters as a 3x3 convolution to 4 channels + pixel shuffle, float64 on the device
+    xt = torch.from_numpy(x).cuda().double().permute(0, 3, 1, 2)
+    wt = torch.from_numpy(w4).cuda().double().permute(0, 3, 1, 2)           # (4, cin, 3, 3)
+    ph = F.conv2d(xt, wt, padding=1) + float(bias[0])                       # (n, 4, r, r)
+    want = F.pixel_shuffle(ph, 2)[:, 0]                                     # channel py*2+px -> (2h+py, 2w+px)
+    if transposed:
+        want = torch.tanh(want)
+    # and the phase decomposition itself against the full-resolution layer it stands for (unrounded kernel, small n)
+    if n <= 3:
+        kt = torch.from_numpy(kernel).cuda().double()
+        xs = xt[:1]
+        if transposed:
+            full = F.conv_transpose2d(xs, kt.permute(2, 0, 1)[:, None], stride=2, padding=1)[:, 0]
+        else:
+            up = F.interpolate(xs, scale_factor=2, mode="nearest")
+            full = F.conv2d(F.pad(up, (1, 2, 1, 2)), kt.permute(2, 0, 1)[None])[:, 0]
+        w4f = torch.from_numpy(_phase_filters(kernel, transposed)).cuda().double().permute(0, 3, 1, 2)
+        dec = F.pixel_shuffle(F.conv2d(xs, w4f, padding=1), 2)[:, 0]
+        assert (full - dec).abs().max().item() < 1e-5       # the phase filters are summed in float32
+    d_x = torch.from_numpy(x).cuda().to(torch.bfloat16).contiguous()
+    h_w4 = torch.from_numpy(w4.reshape(4, 9 * cin)).to(torch.bfloat16).contiguous().view(torch.int16).numpy()
+    d_b = torch.from_numpy(bias).cuda()
+    d_y = torch.full((n, 2 * r, 2 * r), float("nan"), dtype=torch.float32, device="cuda")
+    _lib.check(_lib.lib().msr_op_phase_tc(d_x.data_ptr(), h_w4.ctypes.data, d_b.data_ptr(), d_y.data_ptr(), n, r, cin,
+                                          3 if transposed else 0, _lib.stream_ptr()), "msr_op_phase_tc")
+    torch.cuda.synchronize()
+    err = (d_y.double() - want).abs().max().item()
+    assert err < 1e-4, err
+
+
 @pytest.mark.parametrize("n,r,C,x_shift,spg", [(4, 16, 128, 1, 2), (2, 64, 256, 0, 2), (2, 128, 128, 1, 1), (3, 4, 64, 0, 3)])
 def test_fused_spade_operator(torch, n, r, C, x_shift, spg):
     """gamma|beta conv + normalise + modulate + LeakyReLU(0.2) (spade.py:19-24, blocks.py:30) with the nearest x2

@@ -3,6 +3,7 @@
     python tools/one_layer.py mask   [n r]        # SPADE mask conv: K = 64 im2col GEMM -> relu -> bf16 (128 columns)
     python tools/one_layer.py conv128 [n r]       # rb6.conv_1: 3x3, 256 -> 128, fp32 out
     python tools/one_layer.py gb [n r]            # rb6.spade_1 gamma|beta conv with the fused SPADE epilogue (C = 256)
+    python tools/one_layer.py phase [n r]         # last layer (4x4 conv of the x2-upsampled tensor), csrc/phase_tc.cu
 Prints the CUDA-event time of the timed launches and the achieved TFLOP/s / GB/s.
 """
 import os
@@ -39,6 +40,21 @@ elif kind == "conv128":
     run = lambda: _lib.check(L.msr_op_conv3x3_bf16(x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), n, r, 256, 128,
                                                    st), "conv128")
     flops, byts = 2.0 * n * r * r * 128 * 9 * 256, n * r * r * (512.0 + 512.0)
+elif kind == "phase":
+    cin = 128
+    x = rnd(n, r, r, cin)
+    w4 = torch.zeros((4, 3, 3, cin))
+    for q in range(4):
+        for ty in range(3):
+            for tx in range(3):
+                if (q >> 1 == 0 or ty >= 1) and (q & 1 == 0 or tx >= 1):
+                    w4[q, ty, tx] = torch.randn(cin) * 0.02
+    h_w4 = w4.reshape(4, 9 * cin).to(torch.bfloat16).contiguous().view(torch.int16).numpy()
+    b = rnd(1, dtype=torch.float32)
+    y = torch.empty((n, 2 * r, 2 * r), dtype=torch.float32, device="cuda")
+    run = lambda: _lib.check(L.msr_op_phase_tc(x.data_ptr(), h_w4.ctypes.data, b.data_ptr(), y.data_ptr(), n, r, cin, 0, st),
+                             "phase")
+    flops, byts = 2.0 * n * (2 * r) ** 2 * 16 * cin, n * r * r * (2.0 * cin + 16.0)
 else:
     C = 256
     a, w, b = rnd(n, r, r, 128), rnd(2 * C, 1152, scale=0.03), rnd(2 * C, dtype=torch.float32)
