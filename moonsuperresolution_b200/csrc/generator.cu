@@ -48,6 +48,7 @@ struct SpadeW {
   const __nv_bfloat16* gb_wt = nullptr;  // bf16 [2C][1152], rows interleaved per 64 channels
   const float* gb_bt = nullptr;          // fp32 [2C] in the interleaved order
   const __nv_bfloat16* conv_wt = nullptr;  // bf16 [128][64]: k = (ky*3+kx)*2 + c for k < 18, zero beyond (im2col GEMM)
+  const __nv_bfloat16* conv_wm = nullptr;  // bf16 [128][64] in the K layout of mask_tc.cu (A tile built inside the kernel)
   int C = 0;
 };
 
@@ -209,6 +210,12 @@ static const bool g_disable_phase_tc = [] {
   return e != nullptr && e[0] == '0';
 }();
 
+// MSR_TC_MASK=0 keeps SPADE's mask convolution on the im2col buffer + K = 64 GEMM of conv_tc.cu (A/B runs)
+static const bool g_disable_mask_tc = [] {
+  const char* e = getenv("MSR_TC_MASK");
+  return e != nullptr && e[0] == '0';
+}();
+
 // last layer: columns of the per-pixel GEMM from the [32][9 * cin] phase-combined filters (rows 0..3 real)
 int pack_phase_layer(msr_generator* g, const std::vector<uint16_t>& w32, int cin) {
   g->ph_ok = false;
@@ -291,6 +298,9 @@ int load_spade(msr_generator* g, const std::string& pre, int C, SpadeW* s) {
         cwt[(size_t)co * 64 + 36 + k] = hi;
       }
     if ((rc = upload_bf16(g, cwt, &s->conv_wt))) return rc;
+    std::vector<uint16_t> cwm;
+    mask_tc_pack_weights(cw->data.data(), &cwm);
+    if ((rc = upload_bf16(g, cwm, &s->conv_wm))) return rc;
   }
   return MSR_OK;
 }
@@ -682,6 +692,7 @@ struct Fwd {
   int phase = 0;        // MSR_REPEAT_*: 0 plain forward, 1 first generation of a repeated batch (fills the gamma | beta
                         // cache), 2 further generation (encoder, mask convs and gamma | beta convs are reused)
   int spade_index = 0;  // running index of the SPADE layer (cache slot)
+  const float* source = nullptr;   // the call's input patches [N][I][I][2] (read by the mask convolutions)
   std::vector<ConvTC*>* plans = nullptr;
   size_t plan_cursor = 0;
   bool building = false;
@@ -825,6 +836,21 @@ int forward_spade(Fwd& f, const float* source, const float* eps, float* out) {
 // ------------------------------------------------------------------------------------------------------------------
 // bf16 tensor-core mode: every convolution and the im2col'd 2-channel convolutions run in conv_tc.cu
 // ------------------------------------------------------------------------------------------------------------------
+// a = relu(conv3x3(resized mask)) (spade.py:17-18) -> g->a_bf16: mask_tc.cu builds the operand tile from the source inside
+// the kernel; the older form is a K = 64 GEMM on the im2col rows that forward_spade_bf16 writes once per resolution
+bool mask_in_kernel(const msr_generator* g, int r) { return !g_disable_mask_tc && mask_tc_supported(g->I, r); }
+
+int mask_bf16(Fwd& f, const SpadeW& s, int r) {
+  msr_generator* g = f.g;
+  const int n = (int)f.N;
+  if (mask_in_kernel(g, r)) return mask_conv_tc(f.source, g->I, s.conv_wm, s.conv_b, g->a_bf16, n, r, f.st);
+  ConvTCArgs m;
+  m.x = g->patches; m.w = s.conv_wt; m.n = n; m.r = r; m.cin = 64; m.ncols = kHidden; m.taps = 1; m.pad = 0;
+  m.epilogue = TC_EPI_ACT_BF16; m.bias = s.conv_b; m.act = ACT_RELU; m.out_bf16 = g->a_bf16;
+  m.alg_flops = 2.0 * (double)n * r * r * kHidden * 18;          // 3x3 taps x 2 channels (the GEMM's K is padded to 64)
+  return tc_conv(f, m);
+}
+
 int spade_bf16(Fwd& f, const SpadeW& s, const float* x, int x_shift, const float* mean, const float* rstd, int r) {
   msr_generator* g = f.g;
   const int n = (int)f.N;
@@ -836,11 +862,7 @@ int spade_bf16(Fwd& f, const SpadeW& s, const float* x, int x_shift, const float
     __nv_bfloat16* cache = g->gb_cache[layer];
     MSR_REQUIRE(cache != nullptr, "internal: gamma | beta cache not allocated");
     if (f.phase == MSR_REPEAT_FIRST) {
-      ConvTCArgs m;
-      m.x = g->patches; m.w = s.conv_wt; m.n = n; m.r = r; m.cin = 64; m.ncols = kHidden; m.taps = 1; m.pad = 0;
-      m.epilogue = TC_EPI_ACT_BF16; m.bias = s.conv_b; m.act = ACT_RELU; m.out_bf16 = g->a_bf16;
-      m.alg_flops = 2.0 * (double)n * r * r * kHidden * 18;
-      if ((rc = tc_conv(f, m))) return rc;
+      if ((rc = mask_bf16(f, s, r))) return rc;
       ConvTCArgs a;
       a.x = g->a_bf16; a.w = s.gb_wt; a.n = n; a.r = r; a.cin = kHidden; a.ncols = 2 * s.C;
       a.epilogue = TC_EPI_ACT_BF16; a.bias = s.gb_bt; a.act = ACT_NONE; a.out_bf16 = cache;
@@ -848,12 +870,7 @@ int spade_bf16(Fwd& f, const SpadeW& s, const float* x, int x_shift, const float
     }
     return spade_modulate_cached_bf16(cache, x, x_shift, mean, rstd, g->act_bf16, n, r, s.C, g->B, 0.2f, f.st);
   }
-  // a = relu(conv3x3(resized mask)) as a K = 64 GEMM on the im2col'd source (spade.py:17-18)
-  ConvTCArgs m;
-  m.x = g->patches; m.w = s.conv_wt; m.n = n; m.r = r; m.cin = 64; m.ncols = kHidden; m.taps = 1; m.pad = 0;
-  m.epilogue = TC_EPI_ACT_BF16; m.bias = s.conv_b; m.act = ACT_RELU; m.out_bf16 = g->a_bf16;
-  m.alg_flops = 2.0 * (double)n * r * r * kHidden * 18;          // 3x3 taps x 2 channels (the GEMM's K is padded to 64)
-  if ((rc = tc_conv(f, m))) return rc;
+  if ((rc = mask_bf16(f, s, r))) return rc;
   // gamma | beta convolution with the fused normalise - modulate - LeakyReLU epilogue (spade.py:19-24, blocks.py:30)
   ConvTCArgs a;
   a.x = g->a_bf16; a.w = s.gb_wt; a.n = n; a.r = r; a.cin = kHidden; a.ncols = 2 * s.C;
@@ -889,6 +906,7 @@ int forward_spade_bf16(Fwd& f, const float* source, const float* eps, float* out
   cudaStream_t st = f.st;
   int rc;
   f.spade_index = 0;
+  f.source = source;
   const bool reuse = f.phase == MSR_REPEAT_NEXT;   // a further generation of the same batch: only the noise is new
   // ---- encoder (networks.py:8-34); its mean | variance rows (lat_mv) are kept across the generations of a batch
   if (!reuse) {
@@ -962,7 +980,9 @@ int forward_spade_bf16(Fwd& f, const float* source, const float* eps, float* out
   for (int k = 0; k < 6; ++k) {
     const BlockW& b = g->rb[k];
     float* y = g->xbuf[(k + 1) & 1];
-    if (!reuse && (rc = source_patches_bf16(source, I, g->patches, n, r, 0, st))) return rc;   // shared by the block's SPADEs
+    // im2col rows of the source at this resolution, shared by the block's SPADEs (only when the mask convolution is
+    // not the kernel that builds its operand itself)
+    if (!reuse && !mask_in_kernel(g, r) && (rc = source_patches_bf16(source, I, g->patches, n, r, 0, st))) return rc;
     // x = conv_1(lrelu(spade_1(in)))                                  blocks.py:29-30
     if ((rc = spade_bf16(f, b.s1, x, x_shift, g->st_mean[0], g->st_rstd[0], r))) return rc;
     if ((rc = conv_bf16(f, b.c1, r, g->h1, nullptr, 0, g->st_mean[1], g->st_rstd[1]))) return rc;

@@ -1,0 +1,319 @@
+// SPADE's mask convolution on the tensor cores WITHOUT an im2col buffer in HBM.
+//
+//   mask = tf.image.resize(raw_mask, x.shape[1:3], 'nearest');  a = relu(conv3x3(mask, 2 -> 128))     spade/models/spade.py:17-18
+//
+// conv_tc.cu runs this layer as a K = 64 GEMM on rows that source_patches_bf16 writes to HBM first (128 bytes per pixel,
+// written once per resolution and read by each of the block's two or three SPADE layers).  Here the A operand never
+// leaves the SM: four producer warps build every 128-pixel x 64 tile directly in shared memory -- each thread reads the
+// 9 taps of its pixel from the float32 source at the resized position (8 bytes per tap, served by L1 / L2), splits them
+// into bf16 hi + lo, and writes its 128-byte row in the 128-byte-swizzled K-major layout a TMA load would have produced
+// (16-byte chunk c of row i at chunk position c ^ (i & 7)); fence.proxy.async makes the generic-proxy stores visible to
+// tcgen05.mma.  The weights (128 x 64 bf16, 16 KB) stay in shared memory for the whole kernel.  What remains is the
+// unavoidable part: 256 bytes written per pixel (whole rows, through a staging buffer as in TC_EPI_RELU_BF16_T).
+//
+// Split-bf16 K layout (the three products x_hi*w_hi + x_lo*w_hi + x_hi*w_lo ~ a float32 product; mask_tc_pack_weights):
+//   k = 4t + {0, 1, 2, 3}   tap t = ky*3 + kx:  x = (hi0, hi1, lo0, lo1)   w = (whi0, whi1, whi0, whi1)
+//   k = 36 + 2t + {0, 1}                        x = (hi0, hi1)             w = (wlo0, wlo1)
+//   k = 54 .. 63                                zero
+#include <cstring>
+#include <vector>
+
+#include "nn.cuh"
+#include "tc_ptx.cuh"
+
+namespace msr {
+
+namespace tc {
+
+constexpr int kMkStages = 6;                          // A tiles (16 KB each) in flight between producers and the MMA thread
+constexpr int kMkAcc = 4;                             // 128-column accumulators in TMEM
+constexpr int kMkN = 128;
+constexpr int kMkEpiWarps = 8, kMkProdWarps = 4;
+constexpr int kMkThreads = (kMkEpiWarps + kMkProdWarps + 1) * 32;
+constexpr int kMkABytes = kBlockM * kBlockK * 2;      // 16 KB
+constexpr int kMkBBytes = kMkN * kBlockK * 2;         // 16 KB
+constexpr int kMkRowPitch = 256 + 16;                 // staging rows of the whole-row epilogue (see conv_tc.cu)
+constexpr int kMkStageOut = 4 * 32 * kMkRowPitch;
+constexpr int kMkSmemBytes = 1024 + kMkBBytes + kMkStages * kMkABytes + kMkStageOut + 256;
+
+struct MaskGeom {
+  int n, r, lr;            // output side r = 2^lr
+  int I, f, half;          // source side, I / r, (I / r) / 2: mask pixel (h, w) = source pixel (h*f + half, w*f + half)
+  int64_t M;               // n * r * r pixels
+  int n_tiles;             // ceil(M / 128)
+  const float* src;        // [n][I][I][2] float32
+  const float* bias;       // [128]
+  __nv_bfloat16* out;      // [M][128]
+};
+
+__device__ __forceinline__ void mbar_arrive_release(uint32_t bar) {
+  asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__global__ void __launch_bounds__(kMkThreads, 1)
+mask_conv_tc_kernel(const __grid_constant__ CUtensorMap map_b, const MaskGeom g) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  constexpr int kOffA = kMkBBytes;
+  constexpr int kOffOut = kOffA + kMkStages * kMkABytes;
+  constexpr int kOffBar = kOffOut + kMkStageOut;
+  const uint32_t bar_base = smem_base + kOffBar;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kMkStages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kMkStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kMkStages + kMkAcc + a); };
+  const uint32_t w_bar = bar_base + 8u * (2 * kMkStages + 2 * kMkAcc);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + kOffBar + 8 * (2 * kMkStages + 2 * kMkAcc + 1));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kMkStages; ++s) {
+      mbar_init(full_bar(s), kMkProdWarps * 32);   // every producer thread arrives once its row is written
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < kMkAcc; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), kMkEpiWarps);
+    }
+    mbar_init(w_bar, 1);
+    fence_barrier_init();
+  }
+  constexpr int kMmaWarp = kMkEpiWarps + kMkProdWarps;
+  if (warp == kMmaWarp) {
+    if (lane == 0) tma_prefetch_desc(&map_b);
+    tmem_alloc(smem_u32((const void*)tmem_slot), kMkAcc * kMkN);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= kMkEpiWarps && warp < kMmaWarp) {
+    // ===================== producers: one thread per tile row (pixel) =====================
+    const int i = threadIdx.x - kMkEpiWarps * 32;   // 0..127
+    const int r = g.r, lr = g.lr, f = g.f, I = g.I;
+    const uint32_t row_off = (uint32_t)i * 128u, sw = (uint32_t)(i & 7);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
+      const int64_t m = (int64_t)tile * kBlockM + i;
+      uint32_t ex[9], ey[9];   // per tap: (hi0 | hi1 << 16), (lo0 | lo1 << 16)
+#pragma unroll
+      for (int t = 0; t < 9; ++t) ex[t] = ey[t] = 0u;
+      if (m < g.M) {
+        const int b = (int)(m >> (2 * lr));
+        const int rem = (int)(m & (((int64_t)1 << (2 * lr)) - 1));
+        const int h = rem >> lr, w = rem & (r - 1);
+        const float* img = g.src + (int64_t)b * I * I * 2;
+        float2 s[9];
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const int hh = h + ky - 1, ww = w + kx - 1;   // SAME padding (1, 1) on the resized mask
+            s[ky * 3 + kx] = (hh >= 0 && hh < r && ww >= 0 && ww < r)
+                                 ? __ldg(reinterpret_cast<const float2*>(img + ((int64_t)(hh * f + g.half) * I + ww * f + g.half) * 2))
+                                 : make_float2(0.f, 0.f);
+          }
+        }
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const __nv_bfloat16 hx = __float2bfloat16_rn(s[t].x), hy = __float2bfloat16_rn(s[t].y);
+          const __nv_bfloat16 lx = __float2bfloat16_rn(s[t].x - __bfloat162float(hx));
+          const __nv_bfloat16 ly = __float2bfloat16_rn(s[t].y - __bfloat162float(hy));
+          ex[t] = (uint32_t)__bfloat16_as_ushort(hx) | ((uint32_t)__bfloat16_as_ushort(hy) << 16);
+          ey[t] = (uint32_t)__bfloat16_as_ushort(lx) | ((uint32_t)__bfloat16_as_ushort(ly) << 16);
+        }
+      }
+      mbar_wait(empty_bar(stage), phase ^ 1u);
+      uint8_t* row = smem_gen + kOffA + stage * kMkABytes + row_off;
+      auto put = [&](uint32_t c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3) {
+        *reinterpret_cast<uint4*>(row + ((c ^ sw) << 4)) = make_uint4(a0, a1, a2, a3);
+      };
+      put(0, ex[0], ey[0], ex[1], ey[1]);
+      put(1, ex[2], ey[2], ex[3], ey[3]);
+      put(2, ex[4], ey[4], ex[5], ey[5]);
+      put(3, ex[6], ey[6], ex[7], ey[7]);
+      put(4, ex[8], ey[8], ex[0], ex[1]);
+      put(5, ex[2], ex[3], ex[4], ex[5]);
+      put(6, ex[6], ex[7], ex[8], 0u);
+      put(7, 0u, 0u, 0u, 0u);
+      fence_proxy_async_smem();            // generic-proxy stores -> visible to the tensor core's async-proxy reads
+      mbar_arrive_release(full_bar(stage));
+      if (++stage == kMkStages) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ===================== MMA issuer (+ the one-off weight load) =====================
+    if (lane == 0) {
+      mbar_expect_tx(w_bar, kMkBBytes);
+      tma_load_2d(smem_base, &map_b, w_bar, 0, 0);
+      constexpr uint32_t idesc = make_idesc(kMkN, kBlockM);
+      mbar_wait(w_bar, 0);
+      tc_fence_after();
+      const uint64_t bdesc = make_smem_desc(smem_base);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint64_t adesc = make_smem_desc(smem_base + kOffA + stage * kMkABytes);
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k)
+          umma_bf16(tmem_base + (uint32_t)(acc * kMkN), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                    k != 0 ? 1u : 0u);
+        umma_commit(empty_bar(stage));
+        umma_commit(tfull_bar(acc));
+        if (++stage == kMkStages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+        if (++acc == kMkAcc) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps 0..7: relu(acc + bias) -> bf16, whole 256-byte rows =====================
+    const int quarter = warp & 3, csel = warp >> 2;
+    uint8_t* stg = smem_gen + kOffOut + quarter * (32 * kMkRowPitch);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kMkN);
+#pragma unroll 1
+      for (int c0 = csel * 32; c0 < kMkN; c0 += 64) {
+        uint32_t v[32];
+        tmem_ld32(t_row + (uint32_t)c0, v);
+        tmem_ld_wait();
+        uint4* dst = reinterpret_cast<uint4*>(stg + lane * kMkRowPitch + c0 * 2);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(g.bias + c0 + 8 * q));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(g.bias + c0 + 8 * q + 4));
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          uint32_t pk[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float o0 = fmaxf(__uint_as_float(v[8 * q + 2 * j]) + bb[2 * j], 0.f);
+            const float o1 = fmaxf(__uint_as_float(v[8 * q + 2 * j + 1]) + bb[2 * j + 1], 0.f);
+            const __nv_bfloat162 t2 = __floats2bfloat162_rn(o0, o1);
+            pk[j] = *reinterpret_cast<const uint32_t*>(&t2);
+          }
+          dst[q] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
+      // the accumulator is in shared memory now: hand it back before the global stores
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");   // both warps of the quarter have parked
+      {
+        const int64_t m0 = (int64_t)tile * kBlockM;
+        const int rows_ok = (int)min((int64_t)kBlockM, g.M - m0);
+        const int sub = lane >> 4, cb16 = (lane & 15) * 16;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int rq = csel * 16 + 2 * it + sub;                        // row inside the quarter
+          const int row_t = quarter * 32 + rq;
+          const uint4 val = *reinterpret_cast<const uint4*>(stg + rq * kMkRowPitch + cb16);
+          if (row_t < rows_ok)
+            *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(g.out) + (m0 + row_t) * (kMkN * 2) + cb16) = val;
+        }
+      }
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");   // staging may be overwritten by the next tile
+      if (++acc == kMkAcc) {
+        acc = 0;
+        acc_phase ^= 1u;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kMkAcc * kMkN);
+  }
+}
+
+}  // namespace tc
+
+// ---- host side ----------------------------------------------------------------------------------------------------------
+void mask_tc_pack_weights(const float* w, std::vector<uint16_t>* out) {
+  auto f2bf = [](float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    return (uint16_t)((u + 0x7fffu + ((u >> 16) & 1u)) >> 16);   // round to nearest even (finite inputs)
+  };
+  auto bf2f = [](uint16_t h) {
+    const uint32_t u = (uint32_t)h << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+  };
+  out->assign((size_t)128 * 64, 0);
+  for (int t = 0; t < 9; ++t)
+    for (int c = 0; c < 2; ++c)
+      for (int co = 0; co < 128; ++co) {
+        const float v = w[(size_t)(t * 2 + c) * 128 + co];
+        const uint16_t hi = f2bf(v), lo = f2bf(v - bf2f(hi));
+        uint16_t* row = out->data() + (size_t)co * 64;
+        row[4 * t + c] = hi;          // pairs with x_hi
+        row[4 * t + 2 + c] = hi;      // pairs with x_lo
+        row[36 + 2 * t + c] = lo;     // pairs with x_hi
+      }
+}
+
+bool mask_tc_supported(int I, int r) { return r >= 1 && (r & (r - 1)) == 0 && r <= I && I % r == 0; }
+
+int mask_conv_tc(const float* source, int I, const __nv_bfloat16* wm, const float* bias, __nv_bfloat16* out, int n, int r,
+                 cudaStream_t st) {
+  MSR_REQUIRE(source && wm && bias && out && n > 0, "mask_conv_tc: bad arguments");
+  MSR_REQUIRE(mask_tc_supported(I, r), "mask_conv_tc: r must be a power of two dividing I");
+  MSR_REQUIRE((reinterpret_cast<uintptr_t>(wm) & 127) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(source) & 7) == 0, "mask_conv_tc: misaligned operand");
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail(MSR_E_CUDA, "mask_conv_tc: cuTensorMapEncodeTiled entry point not available");
+  CUtensorMap map_b;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)tc::kBlockK, (cuuint64_t)tc::kMkN};
+    cuuint64_t strides[1] = {(cuuint64_t)tc::kBlockK * 2};
+    cuuint32_t box[2] = {(cuuint32_t)tc::kBlockK, (cuuint32_t)tc::kMkN};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult rc = enc(&map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(wm), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) return fail(MSR_E_CUDA, "mask_conv_tc: cuTensorMapEncodeTiled failed with " + std::to_string((int)rc));
+  }
+  tc::MaskGeom g;
+  g.n = n; g.r = r; g.lr = 0;
+  while ((1 << g.lr) < r) ++g.lr;
+  g.I = I; g.f = I / r; g.half = g.f >> 1;
+  g.M = (int64_t)n * r * r;
+  g.n_tiles = (int)((g.M + tc::kBlockM - 1) / tc::kBlockM);
+  g.src = source; g.bias = bias; g.out = out;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  ProfileScope prof(MSR_PROF_CONV_TC, st, 2.0 * (double)g.M * 128 * 18);
+  static bool attr_set = false;
+  if (!attr_set) {
+    MSR_CUDA_CHECK(cudaFuncSetAttribute(tc::mask_conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kMkSmemBytes));
+    attr_set = true;
+  }
+  tc::mask_conv_tc_kernel<<<std::min(g.n_tiles, sms), tc::kMkThreads, tc::kMkSmemBytes, st>>>(map_b, g);
+  count_launch();
+  MSR_LAUNCH_CHECK();
+  return MSR_OK;
+}
+
+}  // namespace msr

@@ -179,6 +179,40 @@ def test_phase_layer_tensor_core_operator(torch, n, r, cin, transposed):
     assert err < 1e-4, err
 
 
+@pytest.mark.parametrize("n,i,r", [(3, 64, 8), (2, 128, 128), (5, 256, 64), (16, 512, 256), (1, 64, 4), (7, 64, 1)])
+def test_mask_convolution_tensor_core_operator(torch, n, i, r):
+    """SPADE's mask convolution with the operand tile built inside the kernel (csrc/mask_tc.cu) against torch float64:
+    nearest resize with half-pixel centres (source pixel h * I/r + I/(2r)), 3x3 SAME conv 2 -> 128, bias, ReLU.  The
+    split-bf16 operands give ~float32 products, so the only visible rounding is the bf16 output (2^-9 relative)."""
+    from moonsuperresolution_b200 import _lib
+    import torch.nn.functional as F
+    rng = np.random.default_rng(n * 100 + r)
+    src = rng.uniform(-0.5, 0.5, (n, i, i, 2)).astype(np.float32)
+    src[0, :, 0] = 0.5                                   # values on the border: SAME padding must contribute zeros
+    w = (rng.standard_normal((3, 3, 2, 128)) / np.sqrt(18)).astype(np.float32)
+    b = (0.1 * rng.standard_normal(128)).astype(np.float32)
+    f = i // r
+    idx = np.arange(r) * f + f // 2
+    mask = torch.from_numpy(src[:, idx][:, :, idx]).cuda().double().permute(0, 3, 1, 2)
+    want = torch.relu(F.conv2d(mask, torch.from_numpy(w).cuda().double().permute(3, 2, 0, 1), torch.from_numpy(b).cuda().double(),
+                               padding=1)).permute(0, 2, 3, 1)
+    d_src = torch.from_numpy(src).cuda()
+    d_b = torch.from_numpy(b).cuda()
+    d_y = torch.full((n, r, r, 128), float("nan"), dtype=torch.bfloat16, device="cuda")
+    guard = torch.full((4096,), 7.0, dtype=torch.bfloat16, device="cuda")     # nothing may be written past the output
+    _lib.check(_lib.lib().msr_op_mask_tc(d_src.data_ptr(), i, w.ctypes.data, d_b.data_ptr(), d_y.data_ptr(), n, r,
+                                         _lib.stream_ptr()), "msr_op_mask_tc")
+    torch.cuda.synchronize()
+    got = d_y.double()
+    assert torch.isfinite(got).all()
+    err = ((got - want).abs() / (1.0 + want.abs())).max().item()
+    assert err < 2.0 ** -8, err
+    # against the bf16 rounding of the exact result: at most one bf16 step away (products are ~float32 exact)
+    exact_bf16 = want.float().to(torch.bfloat16).double()
+    assert ((got - exact_bf16).abs() <= 2.0 ** -7 * (want.abs() + 1e-3)).all()
+    assert (guard == 7.0).all()
+
+
 @pytest.mark.parametrize("n,r,C,x_shift,spg", [(4, 16, 128, 1, 2), (2, 64, 256, 0, 2), (2, 128, 128, 1, 1), (3, 4, 64, 0, 3)])
 def test_fused_spade_operator(torch, n, r, C, x_shift, spg):
     """gamma|beta conv + normalise + modulate + LeakyReLU(0.2) (spade.py:19-24, blocks.py:30) with the nearest x2
