@@ -290,11 +290,11 @@ int msr_op_phase_tc(const uint16_t* d_x, const uint16_t* h_w4, const float* d_bi
                     int act, void* stream);
 
 /* SPADE's mask convolution (spade.py:17-18) with the operand tile built inside the kernel (csrc/mask_tc.cu):
- * d_out (n, r, r, 128) bf16 = relu(conv3x3_same(nearest_resize(d_source (n, I, I, 2) float32 -> r x r), h_w) + d_bias),
+ * d_out (n, r, r, 128) bf16 = relu(conv3x3_same(nearest_resize(d_source (n, I, I, 2) float32 -> r x r), h_w) + h_bias),
  * nearest resize with half-pixel centres (mask pixel (h, w) = source pixel (h*I/r + I/(2r), ...)); h_w (3, 3, 2, 128)
- * float32 Keras kernel on the HOST, d_bias (128) float32; split-bf16 operands (~float32 products).  r a power of two
- * dividing I.  Synchronises the stream before it returns. */
-int msr_op_mask_tc(const float* d_source, int I, const float* h_w, const float* d_bias, uint16_t* d_out, int n, int r,
+ * float32 Keras kernel and h_bias (128) float32, both on the HOST (the bias is folded into the packed weights);
+ * split-bf16 operands (~float32 products).  r a power of two dividing I.  Synchronises the stream before it returns. */
+int msr_op_mask_tc(const float* d_source, int I, const float* h_w, const float* h_bias, uint16_t* d_out, int n, int r,
                    void* stream);
 
 /* Optimisation aid: when d_counters != NULL (148 * 8 int64, zero-initialised by the caller), every tensor-core convolution

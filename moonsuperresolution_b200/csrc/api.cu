@@ -199,18 +199,18 @@ extern "C" int msr_op_phase_tc(const uint16_t* d_x, const uint16_t* h_w4, const 
   return rc;
 }
 
-extern "C" int msr_op_mask_tc(const float* d_source, int I, const float* h_w, const float* d_bias, uint16_t* d_out, int n,
+extern "C" int msr_op_mask_tc(const float* d_source, int I, const float* h_w, const float* h_bias, uint16_t* d_out, int n,
                               int r, void* stream) {
-  MSR_REQUIRE(d_source && h_w && d_bias && d_out, "msr_op_mask_tc: null pointer");
+  MSR_REQUIRE(d_source && h_w && h_bias && d_out, "msr_op_mask_tc: null pointer");
   std::vector<uint16_t> wm;
-  mask_tc_pack_weights(h_w, &wm);
+  mask_tc_pack_weights(h_w, h_bias, &wm);
   void* d_wm = nullptr;
   MSR_CUDA_CHECK(cudaMalloc(&d_wm, wm.size() * 2));
   int rc = MSR_OK;
   if (cudaMemcpy(d_wm, wm.data(), wm.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess)
     rc = fail(MSR_E_CUDA, "msr_op_mask_tc: weight upload failed");
-  if (!rc) rc = mask_conv_tc(d_source, I, reinterpret_cast<const __nv_bfloat16*>(d_wm), d_bias,
-                             reinterpret_cast<__nv_bfloat16*>(d_out), n, r, (cudaStream_t)stream);
+  if (!rc) rc = mask_conv_tc(d_source, I, reinterpret_cast<const __nv_bfloat16*>(d_wm), reinterpret_cast<__nv_bfloat16*>(d_out),
+                             n, r, (cudaStream_t)stream);
   if (!rc && cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) rc = fail(MSR_E_CUDA, "msr_op_mask_tc: kernel failed");
   cudaFree(d_wm);
   return rc;

@@ -299,7 +299,9 @@ int load_spade(msr_generator* g, const std::string& pre, int C, SpadeW* s) {
       }
     if ((rc = upload_bf16(g, cwt, &s->conv_wt))) return rc;
     std::vector<uint16_t> cwm;
-    mask_tc_pack_weights(cw->data.data(), &cwm);
+    const HostTensor* cb;
+    if ((rc = need(g, pre + ".conv.bias", {kHidden}, &cb))) return rc;
+    mask_tc_pack_weights(cw->data.data(), cb->data.data(), &cwm);
     if ((rc = upload_bf16(g, cwm, &s->conv_wm))) return rc;
   }
   return MSR_OK;
@@ -843,7 +845,7 @@ bool mask_in_kernel(const msr_generator* g, int r) { return !g_disable_mask_tc &
 int mask_bf16(Fwd& f, const SpadeW& s, int r) {
   msr_generator* g = f.g;
   const int n = (int)f.N;
-  if (mask_in_kernel(g, r)) return mask_conv_tc(f.source, g->I, s.conv_wm, s.conv_b, g->a_bf16, n, r, f.st);
+  if (mask_in_kernel(g, r)) return mask_conv_tc(f.source, g->I, s.conv_wm, g->a_bf16, n, r, f.st);
   ConvTCArgs m;
   m.x = g->patches; m.w = s.conv_wt; m.n = n; m.r = r; m.cin = 64; m.ncols = kHidden; m.taps = 1; m.pad = 0;
   m.epilogue = TC_EPI_ACT_BF16; m.bias = s.conv_b; m.act = ACT_RELU; m.out_bf16 = g->a_bf16;

@@ -4,17 +4,20 @@
 //
 // conv_tc.cu runs this layer as a K = 64 GEMM on rows that source_patches_bf16 writes to HBM first (128 bytes per pixel,
 // written once per resolution and read by each of the block's two or three SPADE layers).  Here the A operand never
-// leaves the SM: four producer warps build every 128-pixel x 64 tile directly in shared memory -- each thread reads the
+// leaves the SM: producer warps build every 128-pixel x 64 tile directly in shared memory -- each thread reads the
 // 9 taps of its pixel from the float32 source at the resized position (8 bytes per tap, served by L1 / L2), splits them
 // into bf16 hi + lo, and writes its 128-byte row in the 128-byte-swizzled K-major layout a TMA load would have produced
 // (16-byte chunk c of row i at chunk position c ^ (i & 7)); fence.proxy.async makes the generic-proxy stores visible to
 // tcgen05.mma.  The weights (128 x 64 bf16, 16 KB) stay in shared memory for the whole kernel.  What remains is the
-// unavoidable part: 256 bytes written per pixel (whole rows, through a staging buffer as in TC_EPI_RELU_BF16_T).
+// unavoidable part: 256 bytes written per pixel -- the eight epilogue warps park relu(acc + bias) as bf16 rows in a
+// double-buffered staging area and four store warps write whole rows from there, so that reading the next accumulator
+// out of TMEM overlaps the previous tile's stores.
 //
 // Split-bf16 K layout (the three products x_hi*w_hi + x_lo*w_hi + x_hi*w_lo ~ a float32 product; mask_tc_pack_weights):
 //   k = 4t + {0, 1, 2, 3}   tap t = ky*3 + kx:  x = (hi0, hi1, lo0, lo1)   w = (whi0, whi1, whi0, whi1)
 //   k = 36 + 2t + {0, 1}                        x = (hi0, hi1)             w = (wlo0, wlo1)
-//   k = 54 .. 63                                zero
+//   k = 54, 55                                  x = (1, 1)                 w = (bias_hi, bias_lo): the bias rides in the GEMM
+//   k = 56 .. 63                                zero
 #include <cstring>
 #include <vector>
 
@@ -28,13 +31,14 @@ namespace tc {
 constexpr int kMkStages = 6;                          // A tiles (16 KB each) in flight between producers and the MMA thread
 constexpr int kMkAcc = 4;                             // 128-column accumulators in TMEM
 constexpr int kMkN = 128;
-constexpr int kMkEpiWarps = 8, kMkProdWarps = 4;
-constexpr int kMkThreads = (kMkEpiWarps + kMkProdWarps + 1) * 32;
+constexpr int kMkEpiWarps = 8, kMkProdWarps = 4;       // producers: one thread per tile row
+constexpr int kMkStoreWarps = 4, kMkOutBufs = 2;       // one store warp per TMEM lane quarter; double-buffered staging
+constexpr int kMkThreads = (kMkEpiWarps + kMkStoreWarps + kMkProdWarps + 1) * 32;
 constexpr int kMkABytes = kBlockM * kBlockK * 2;      // 16 KB
 constexpr int kMkBBytes = kMkN * kBlockK * 2;         // 16 KB
 constexpr int kMkRowPitch = 256 + 16;                 // staging rows of the whole-row epilogue (see conv_tc.cu)
 constexpr int kMkStageOut = 4 * 32 * kMkRowPitch;
-constexpr int kMkSmemBytes = 1024 + kMkBBytes + kMkStages * kMkABytes + kMkStageOut + 256;
+constexpr int kMkSmemBytes = 1024 + kMkBBytes + kMkStages * kMkABytes + kMkOutBufs * kMkStageOut + 256;
 
 struct MaskGeom {
   int n, r, lr;            // output side r = 2^lr
@@ -42,7 +46,6 @@ struct MaskGeom {
   int64_t M;               // n * r * r pixels
   int n_tiles;             // ceil(M / 128)
   const float* src;        // [n][I][I][2] float32
-  const float* bias;       // [128]
   __nv_bfloat16* out;      // [M][128]
 };
 
@@ -58,19 +61,22 @@ mask_conv_tc_kernel(const __grid_constant__ CUtensorMap map_b, const MaskGeom g)
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   constexpr int kOffA = kMkBBytes;
   constexpr int kOffOut = kOffA + kMkStages * kMkABytes;
-  constexpr int kOffBar = kOffOut + kMkStageOut;
+  constexpr int kOffBar = kOffOut + kMkOutBufs * kMkStageOut;
   const uint32_t bar_base = smem_base + kOffBar;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kMkStages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kMkStages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kMkStages + kMkAcc + a); };
   const uint32_t w_bar = bar_base + 8u * (2 * kMkStages + 2 * kMkAcc);
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + kOffBar + 8 * (2 * kMkStages + 2 * kMkAcc + 1));
+  auto sfull_bar = [&](int b) { return bar_base + 8u * (2 * kMkStages + 2 * kMkAcc + 1 + b); };
+  auto sempty_bar = [&](int b) { return bar_base + 8u * (2 * kMkStages + 2 * kMkAcc + 1 + kMkOutBufs + b); };
+  volatile uint32_t* tmem_slot =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + kOffBar + 8 * (2 * kMkStages + 2 * kMkAcc + 1 + 2 * kMkOutBufs));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < kMkStages; ++s) {
-      mbar_init(full_bar(s), kMkProdWarps * 32);   // every producer thread arrives once its row is written
+      mbar_init(full_bar(s), kBlockM);             // every thread of the group that builds the tile arrives once
       mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < kMkAcc; ++a) {
@@ -78,9 +84,13 @@ mask_conv_tc_kernel(const __grid_constant__ CUtensorMap map_b, const MaskGeom g)
       mbar_init(tempty_bar(a), kMkEpiWarps);
     }
     mbar_init(w_bar, 1);
+    for (int b = 0; b < kMkOutBufs; ++b) {
+      mbar_init(sfull_bar(b), kMkEpiWarps);      // all eight (quarter, column half) pieces of the tile are parked
+      mbar_init(sempty_bar(b), kMkStoreWarps);
+    }
     fence_barrier_init();
   }
-  constexpr int kMmaWarp = kMkEpiWarps + kMkProdWarps;
+  constexpr int kProdWarp0 = kMkEpiWarps + kMkStoreWarps, kMmaWarp = kProdWarp0 + kMkProdWarps;
   if (warp == kMmaWarp) {
     if (lane == 0) tma_prefetch_desc(&map_b);
     tmem_alloc(smem_u32((const void*)tmem_slot), kMkAcc * kMkN);
@@ -90,43 +100,49 @@ mask_conv_tc_kernel(const __grid_constant__ CUtensorMap map_b, const MaskGeom g)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp >= kMkEpiWarps && warp < kMmaWarp) {
+  if (warp >= kProdWarp0 && warp < kMmaWarp) {
     // ===================== producers: one thread per tile row (pixel) =====================
-    const int i = threadIdx.x - kMkEpiWarps * 32;   // 0..127
+    // Every thread keeps the 9 taps of its next TWO tiles in flight while it converts and stores the current one: a tile
+    // costs one L2 round trip (~800 clk) of latency against ~250 clk of work, so an unpipelined producer starves the
+    // tensor core and the epilogue.
+    const int i = threadIdx.x - kProdWarp0 * 32;     // tile row 0..127
     const int r = g.r, lr = g.lr, f = g.f, I = g.I;
     const uint32_t row_off = (uint32_t)i * 128u, sw = (uint32_t)(i & 7);
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
+    auto load_taps = [&](int tile, float2 (&s)[9]) {
       const int64_t m = (int64_t)tile * kBlockM + i;
-      uint32_t ex[9], ey[9];   // per tap: (hi0 | hi1 << 16), (lo0 | lo1 << 16)
 #pragma unroll
-      for (int t = 0; t < 9; ++t) ex[t] = ey[t] = 0u;
-      if (m < g.M) {
+      for (int t = 0; t < 9; ++t) s[t] = make_float2(0.f, 0.f);
+      if (tile < g.n_tiles && m < g.M) {
         const int b = (int)(m >> (2 * lr));
         const int rem = (int)(m & (((int64_t)1 << (2 * lr)) - 1));
         const int h = rem >> lr, w = rem & (r - 1);
         const float* img = g.src + (int64_t)b * I * I * 2;
-        float2 s[9];
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
           for (int kx = 0; kx < 3; ++kx) {
             const int hh = h + ky - 1, ww = w + kx - 1;   // SAME padding (1, 1) on the resized mask
-            s[ky * 3 + kx] = (hh >= 0 && hh < r && ww >= 0 && ww < r)
-                                 ? __ldg(reinterpret_cast<const float2*>(img + ((int64_t)(hh * f + g.half) * I + ww * f + g.half) * 2))
-                                 : make_float2(0.f, 0.f);
+            if (hh >= 0 && hh < r && ww >= 0 && ww < r)
+              s[ky * 3 + kx] = __ldg(reinterpret_cast<const float2*>(img + ((int64_t)(hh * f + g.half) * I + ww * f + g.half) * 2));
           }
         }
-#pragma unroll
-        for (int t = 0; t < 9; ++t) {
-          const __nv_bfloat16 hx = __float2bfloat16_rn(s[t].x), hy = __float2bfloat16_rn(s[t].y);
-          const __nv_bfloat16 lx = __float2bfloat16_rn(s[t].x - __bfloat162float(hx));
-          const __nv_bfloat16 ly = __float2bfloat16_rn(s[t].y - __bfloat162float(hy));
-          ex[t] = (uint32_t)__bfloat16_as_ushort(hx) | ((uint32_t)__bfloat16_as_ushort(hy) << 16);
-          ey[t] = (uint32_t)__bfloat16_as_ushort(lx) | ((uint32_t)__bfloat16_as_ushort(ly) << 16);
-        }
       }
+    };
+    const int tile_step = (int)gridDim.x;
+    int stage = 0;
+    uint32_t phase = 0;
+    // converts the taps in `s` (tile `tile`), refills `s` with the taps of the tile two steps ahead, writes the row
+    auto produce = [&](int tile, float2 (&s)[9]) {
+      uint32_t ex[9], ey[9];   // per tap: (hi0 | hi1 << 16), (lo0 | lo1 << 16); x = hi + lo to ~2^-17
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const __nv_bfloat162 hi = __floats2bfloat162_rn(s[t].x, s[t].y);
+        const float2 hf = __bfloat1622float2(hi);
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(s[t].x - hf.x, s[t].y - hf.y);
+        ex[t] = *reinterpret_cast<const uint32_t*>(&hi);
+        ey[t] = *reinterpret_cast<const uint32_t*>(&lo);
+      }
+      load_taps(tile + 2 * tile_step, s);            // in flight during the wait and the stores below and the next tile
       mbar_wait(empty_bar(stage), phase ^ 1u);
       uint8_t* row = smem_gen + kOffA + stage * kMkABytes + row_off;
       auto put = [&](uint32_t c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3) {
@@ -138,7 +154,7 @@ mask_conv_tc_kernel(const __grid_constant__ CUtensorMap map_b, const MaskGeom g)
       put(3, ex[6], ey[6], ex[7], ey[7]);
       put(4, ex[8], ey[8], ex[0], ex[1]);
       put(5, ex[2], ex[3], ex[4], ex[5]);
-      put(6, ex[6], ex[7], ex[8], 0u);
+      put(6, ex[6], ex[7], ex[8], 0x3f803f80u);   // k = 54, 55: bf16 ones against the bias rows of the weights
       put(7, 0u, 0u, 0u, 0u);
       fence_proxy_async_smem();            // generic-proxy stores -> visible to the tensor core's async-proxy reads
       mbar_arrive_release(full_bar(stage));
@@ -146,6 +162,17 @@ mask_conv_tc_kernel(const __grid_constant__ CUtensorMap map_b, const MaskGeom g)
         stage = 0;
         phase ^= 1u;
       }
+    };
+    float2 s0[9], s1[9];
+    int tile = blockIdx.x;
+    load_taps(tile, s0);
+    load_taps(tile + tile_step, s1);
+    while (tile < g.n_tiles) {
+      produce(tile, s0);
+      tile += tile_step;
+      if (tile >= g.n_tiles) break;
+      produce(tile, s1);
+      tile += tile_step;
     }
   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer (+ the one-off weight load) =====================
@@ -179,60 +206,84 @@ mask_conv_tc_kernel(const __grid_constant__ CUtensorMap map_b, const MaskGeom g)
         }
       }
     }
-  } else {
-    // ===================== epilogue warps 0..7: relu(acc + bias) -> bf16, whole 256-byte rows =====================
+  } else if (warp < kMkEpiWarps) {
+    // ===================== epilogue warps 0..7: relu(acc + bias) -> bf16 rows in the staging buffer =================
+    // warp = (TMEM lane quarter, column half): lane l owns tile row quarter*32 + l and columns [64*csel, 64*csel + 64).
+    // The global stores are the store warps' job (below), so this chain is TMEM -> registers -> shared memory only and
+    // the next tile's accumulator can be read while the previous tile's rows are still on their way out.
     const int quarter = warp & 3, csel = warp >> 2;
-    uint8_t* stg = smem_gen + kOffOut + quarter * (32 * kMkRowPitch);
-    int acc = 0;
-    uint32_t acc_phase = 0;
+    int acc = 0, buf = 0;
+    uint32_t acc_phase = 0, buf_phase = 0;
     for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kMkN);
-#pragma unroll 1
-      for (int c0 = csel * 32; c0 < kMkN; c0 += 64) {
-        uint32_t v[32];
-        tmem_ld32(t_row + (uint32_t)c0, v);
-        tmem_ld_wait();
-        uint4* dst = reinterpret_cast<uint4*>(stg + lane * kMkRowPitch + c0 * 2);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(g.bias + c0 + 8 * q));
-          const float4 b1 = __ldg(reinterpret_cast<const float4*>(g.bias + c0 + 8 * q + 4));
-          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-          uint32_t pk[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float o0 = fmaxf(__uint_as_float(v[8 * q + 2 * j]) + bb[2 * j], 0.f);
-            const float o1 = fmaxf(__uint_as_float(v[8 * q + 2 * j + 1]) + bb[2 * j + 1], 0.f);
-            const __nv_bfloat162 t2 = __floats2bfloat162_rn(o0, o1);
-            pk[j] = *reinterpret_cast<const uint32_t*>(&t2);
-          }
-          dst[q] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        }
-      }
-      // the accumulator is in shared memory now: hand it back before the global stores
+      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kMkN + csel * 64);
+      uint32_t v0[32], v1[32];
+      tmem_ld32(t_row, v0);
+      tmem_ld32(t_row + 32u, v1);
+      tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");   // both warps of the quarter have parked
-      {
-        const int64_t m0 = (int64_t)tile * kBlockM;
-        const int rows_ok = (int)min((int64_t)kBlockM, g.M - m0);
-        const int sub = lane >> 4, cb16 = (lane & 15) * 16;
+      if (lane == 0) mbar_arrive(tempty_bar(acc));     // the accumulator is in registers: the tensor core may reuse it
+      mbar_wait(sempty_bar(buf), buf_phase ^ 1u);      // the store warps have read this staging buffer's previous tile
+      uint8_t* stg = smem_gen + kOffOut + buf * kMkStageOut + quarter * (32 * kMkRowPitch);
+      uint4* dst = reinterpret_cast<uint4*>(stg + lane * kMkRowPitch + csel * 128);
+      auto pack8 = [&](const uint32_t* v, int q) {   // relu (the bias is already in the accumulator) -> 8 bf16
+        uint32_t pk[4];
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int rq = csel * 16 + 2 * it + sub;                        // row inside the quarter
-          const int row_t = quarter * 32 + rq;
-          const uint4 val = *reinterpret_cast<const uint4*>(stg + rq * kMkRowPitch + cb16);
-          if (row_t < rows_ok)
-            *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(g.out) + (m0 + row_t) * (kMkN * 2) + cb16) = val;
+        for (int j = 0; j < 4; ++j) {
+          const __nv_bfloat162 t2 = __floats2bfloat162_rn(fmaxf(__uint_as_float(v[8 * q + 2 * j]), 0.f),
+                                                          fmaxf(__uint_as_float(v[8 * q + 2 * j + 1]), 0.f));
+          pk[j] = *reinterpret_cast<const uint32_t*>(&t2);
         }
-      }
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");   // staging may be overwritten by the next tile
+        return make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      };
+#pragma unroll
+      for (int q = 0; q < 4; ++q) dst[q] = pack8(v0, q);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) dst[4 + q] = pack8(v1, q);
+      __syncwarp();
+      if (lane == 0) mbar_arrive_release(sfull_bar(buf));
       if (++acc == kMkAcc) {
         acc = 0;
         acc_phase ^= 1u;
+      }
+      if (++buf == kMkOutBufs) {
+        buf = 0;
+        buf_phase ^= 1u;
+      }
+    }
+  } else {
+    // ===================== store warps: staging buffer -> whole 256-byte rows in HBM =====================
+    // store warp q writes the 32 rows of TMEM lane quarter q: 16 lanes per row, two rows (four full lines) per instruction
+    const int quarter = warp - kMkEpiWarps;
+    const int sub = lane >> 4, cb16 = (lane & 15) * 16;
+    int buf = 0;
+    uint32_t buf_phase = 0;
+    for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
+      const int64_t m0 = (int64_t)tile * kBlockM;
+      const int rows_ok = (int)min((int64_t)kBlockM, g.M - m0);
+      uint8_t* out_rows = reinterpret_cast<uint8_t*>(g.out) + (m0 + quarter * 32) * (kMkN * 2) + cb16;
+      mbar_wait(sfull_bar(buf), buf_phase);
+      const uint8_t* stg = smem_gen + kOffOut + buf * kMkStageOut + quarter * (32 * kMkRowPitch) + cb16;
+      uint4 val[8];
+#pragma unroll
+      for (int it = 0; it < 8; ++it) val[it] = *reinterpret_cast<const uint4*>(stg + (2 * it + sub) * kMkRowPitch);
+#pragma unroll
+      for (int it = 0; it < 8; ++it)
+        if (quarter * 32 + 2 * it + sub < rows_ok)
+          *reinterpret_cast<uint4*>(out_rows + (int64_t)(2 * it + sub) * (kMkN * 2)) = val[it];
+#pragma unroll
+      for (int it = 0; it < 8; ++it) val[it] = *reinterpret_cast<const uint4*>(stg + (16 + 2 * it + sub) * kMkRowPitch);
+      __syncwarp();
+      if (lane == 0) mbar_arrive_release(sempty_bar(buf));   // all rows of the buffer are in registers or on their way
+#pragma unroll
+      for (int it = 0; it < 8; ++it)
+        if (quarter * 32 + 16 + 2 * it + sub < rows_ok)
+          *reinterpret_cast<uint4*>(out_rows + (int64_t)(16 + 2 * it + sub) * (kMkN * 2)) = val[it];
+      if (++buf == kMkOutBufs) {
+        buf = 0;
+        buf_phase ^= 1u;
       }
     }
   }
@@ -248,7 +299,7 @@ mask_conv_tc_kernel(const __grid_constant__ CUtensorMap map_b, const MaskGeom g)
 }  // namespace tc
 
 // ---- host side ----------------------------------------------------------------------------------------------------------
-void mask_tc_pack_weights(const float* w, std::vector<uint16_t>* out) {
+void mask_tc_pack_weights(const float* w, const float* bias, std::vector<uint16_t>* out) {
   auto f2bf = [](float f) {
     uint32_t u;
     memcpy(&u, &f, 4);
@@ -271,13 +322,17 @@ void mask_tc_pack_weights(const float* w, std::vector<uint16_t>* out) {
         row[4 * t + 2 + c] = hi;      // pairs with x_lo
         row[36 + 2 * t + c] = lo;     // pairs with x_hi
       }
+  for (int co = 0; co < 128; ++co) {  // bias as two more K rows against constant ones in the operand
+    const uint16_t hi = f2bf(bias[co]);
+    (*out)[(size_t)co * 64 + 54] = hi;
+    (*out)[(size_t)co * 64 + 55] = f2bf(bias[co] - bf2f(hi));
+  }
 }
 
 bool mask_tc_supported(int I, int r) { return r >= 1 && (r & (r - 1)) == 0 && r <= I && I % r == 0; }
 
-int mask_conv_tc(const float* source, int I, const __nv_bfloat16* wm, const float* bias, __nv_bfloat16* out, int n, int r,
-                 cudaStream_t st) {
-  MSR_REQUIRE(source && wm && bias && out && n > 0, "mask_conv_tc: bad arguments");
+int mask_conv_tc(const float* source, int I, const __nv_bfloat16* wm, __nv_bfloat16* out, int n, int r, cudaStream_t st) {
+  MSR_REQUIRE(source && wm && out && n > 0, "mask_conv_tc: bad arguments");
   MSR_REQUIRE(mask_tc_supported(I, r), "mask_conv_tc: r must be a power of two dividing I");
   MSR_REQUIRE((reinterpret_cast<uintptr_t>(wm) & 127) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
                   (reinterpret_cast<uintptr_t>(source) & 7) == 0, "mask_conv_tc: misaligned operand");
@@ -300,7 +355,7 @@ int mask_conv_tc(const float* source, int I, const __nv_bfloat16* wm, const floa
   g.I = I; g.f = I / r; g.half = g.f >> 1;
   g.M = (int64_t)n * r * r;
   g.n_tiles = (int)((g.M + tc::kBlockM - 1) / tc::kBlockM);
-  g.src = source; g.bias = bias; g.out = out;
+  g.src = source; g.out = out;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

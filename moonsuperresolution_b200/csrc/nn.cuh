@@ -143,11 +143,11 @@ void phase_tc_plan_destroy(PhaseTC* plan);
 
 // ---- SPADE mask convolution without an im2col buffer (mask_tc.cu) --------------------------------------------------------
 // out[n][r][r][128] bf16 = relu(conv3x3(nearest_resize(source [n][I][I][2] fp32 -> r x r), w) + bias)   (spade.py:17-18)
-// wm: [128][64] bf16 from mask_tc_pack_weights (w: Keras kernel [3][3][2][128] float32), split-bf16 K layout.
-void mask_tc_pack_weights(const float* w, std::vector<uint16_t>* out);
+// wm: [128][64] bf16 from mask_tc_pack_weights (w: Keras kernel [3][3][2][128] float32, bias [128]): split-bf16 K layout,
+// the bias folded in as two more K rows.
+void mask_tc_pack_weights(const float* w, const float* bias, std::vector<uint16_t>* out);
 bool mask_tc_supported(int I, int r);
-int mask_conv_tc(const float* source, int I, const __nv_bfloat16* wm, const float* bias, __nv_bfloat16* out, int n, int r,
-                 cudaStream_t st);
+int mask_conv_tc(const float* source, int I, const __nv_bfloat16* wm, __nv_bfloat16* out, int n, int r, cudaStream_t st);
 
 // ---- small helpers for the bf16 path (nn_bf16.cu) -----------------------------------------------------------------
 // im2col of the 2-channel source for a 3x3 convolution at output side r: out [n][r][r][64] bf16, channel (ky*3+kx)*2+c

@@ -197,10 +197,9 @@ def test_mask_convolution_tensor_core_operator(torch, n, i, r):
     want = torch.relu(F.conv2d(mask, torch.from_numpy(w).cuda().double().permute(3, 2, 0, 1), torch.from_numpy(b).cuda().double(),
                                padding=1)).permute(0, 2, 3, 1)
     d_src = torch.from_numpy(src).cuda()
-    d_b = torch.from_numpy(b).cuda()
     d_y = torch.full((n, r, r, 128), float("nan"), dtype=torch.bfloat16, device="cuda")
     guard = torch.full((4096,), 7.0, dtype=torch.bfloat16, device="cuda")     # nothing may be written past the output
-    _lib.check(_lib.lib().msr_op_mask_tc(d_src.data_ptr(), i, w.ctypes.data, d_b.data_ptr(), d_y.data_ptr(), n, r,
+    _lib.check(_lib.lib().msr_op_mask_tc(d_src.data_ptr(), i, w.ctypes.data, b.ctypes.data, d_y.data_ptr(), n, r,
                                          _lib.stream_ptr()), "msr_op_mask_tc")
     torch.cuda.synchronize()
     got = d_y.double()

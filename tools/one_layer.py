@@ -3,6 +3,7 @@
     python tools/one_layer.py mask   [n r]        # SPADE mask conv: K = 64 im2col GEMM -> relu -> bf16 (128 columns)
     python tools/one_layer.py conv128 [n r]       # rb6.conv_1: 3x3, 256 -> 128, fp32 out
     python tools/one_layer.py gb [n r]            # rb6.spade_1 gamma|beta conv with the fused SPADE epilogue (C = 256)
+    python tools/one_layer.py maskk [n r]         # the same layer with the operand tile built in the kernel, csrc/mask_tc.cu
     python tools/one_layer.py phase [n r]         # last layer (4x4 conv of the x2-upsampled tensor), csrc/phase_tc.cu
 Prints the CUDA-event time of the timed launches and the achieved TFLOP/s / GB/s.
 """
@@ -40,6 +41,14 @@ elif kind == "conv128":
     run = lambda: _lib.check(L.msr_op_conv3x3_bf16(x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), n, r, 256, 128,
                                                    st), "conv128")
     flops, byts = 2.0 * n * r * r * 128 * 9 * 256, n * r * r * (512.0 + 512.0)
+elif kind == "maskk":
+    src = (torch.rand((n, 2 * r, 2 * r, 2), generator=g, device="cuda") - 0.5).contiguous()
+    h_w = (np.random.default_rng(0).standard_normal((3, 3, 2, 128)) / 4).astype(np.float32)
+    h_b = np.zeros(128, np.float32)
+    y = torch.empty((n, r, r, 128), dtype=torch.bfloat16, device="cuda")
+    run = lambda: _lib.check(L.msr_op_mask_tc(src.data_ptr(), 2 * r, h_w.ctypes.data, h_b.ctypes.data, y.data_ptr(), n, r, st),
+                             "maskk")
+    flops, byts = 2.0 * n * r * r * 128 * 18, n * r * r * (8.0 + 256.0)
 elif kind == "phase":
     cin = 128
     x = rnd(n, r, r, cin)
