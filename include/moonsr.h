@@ -297,6 +297,12 @@ int msr_op_phase_tc(const uint16_t* d_x, const uint16_t* h_w4, const float* d_bi
 int msr_op_mask_tc(const float* d_source, int I, const float* h_w, const float* h_bias, uint16_t* d_out, int n, int r,
                    void* stream);
 
+/* Encoder block 1 (blocks.py:53-60 without the norm, networks.py:12) with the same kernel: d_out (n, I/2, I/2, 128) bf16 =
+ * hi (64 channels) | lo (64 channels) of v = leaky_relu(conv3x3(d_source (n, I, I, 2) float32, strides 2, SAME = pad
+ * (0, 1), h_w (3, 3, 2, 64) float32 Keras kernel on the HOST, no bias), slope), hi = bf16(v), lo = bf16(v - hi): the
+ * split-bf16 operand of the next encoder convolution.  Synchronises the stream before it returns. */
+int msr_op_enc1_tc(const float* d_source, int I, const float* h_w, uint16_t* d_out, int n, float slope, void* stream);
+
 /* Optimisation aid: when d_counters != NULL (148 * 8 int64, zero-initialised by the caller), every tensor-core convolution
  * planned afterwards records per-CTA cycle counts: [0] producer wait on empty stages, [1] producer total, [2] MMA issuer
  * wait on full stages, [3] MMA issuer wait on free accumulators, [4] MMA issuer total, [5] epilogue wait on accumulators.

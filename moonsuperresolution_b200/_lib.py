@@ -59,6 +59,7 @@ SIGNATURES: Dict[str, tuple] = {
     "msr_generator_destroy": (_i, [_vp]),
     "msr_op_conv3x3_bf16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "msr_op_conv_tc": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp]),
+    "msr_op_enc1_tc": (_i, [_vp, _i, _vp, _vp, _i, _f, _vp]),
     "msr_op_mask_tc": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _vp]),
     "msr_op_phase_tc": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "msr_op_spade_tc": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _i, _i, _i, _vp]),

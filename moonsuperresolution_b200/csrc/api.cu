@@ -203,7 +203,7 @@ extern "C" int msr_op_mask_tc(const float* d_source, int I, const float* h_w, co
                               int r, void* stream) {
   MSR_REQUIRE(d_source && h_w && h_bias && d_out, "msr_op_mask_tc: null pointer");
   std::vector<uint16_t> wm;
-  mask_tc_pack_weights(h_w, h_bias, &wm);
+  mask_tc_pack_weights(h_w, h_bias, 128, &wm);
   void* d_wm = nullptr;
   MSR_CUDA_CHECK(cudaMalloc(&d_wm, wm.size() * 2));
   int rc = MSR_OK;
@@ -212,6 +212,23 @@ extern "C" int msr_op_mask_tc(const float* d_source, int I, const float* h_w, co
   if (!rc) rc = mask_conv_tc(d_source, I, reinterpret_cast<const __nv_bfloat16*>(d_wm), reinterpret_cast<__nv_bfloat16*>(d_out),
                              n, r, (cudaStream_t)stream);
   if (!rc && cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) rc = fail(MSR_E_CUDA, "msr_op_mask_tc: kernel failed");
+  cudaFree(d_wm);
+  return rc;
+}
+
+extern "C" int msr_op_enc1_tc(const float* d_source, int I, const float* h_w, uint16_t* d_out, int n, float slope,
+                              void* stream) {
+  MSR_REQUIRE(d_source && h_w && d_out, "msr_op_enc1_tc: null pointer");
+  std::vector<uint16_t> wm;
+  mask_tc_pack_weights(h_w, nullptr, 64, &wm);
+  void* d_wm = nullptr;
+  MSR_CUDA_CHECK(cudaMalloc(&d_wm, wm.size() * 2));
+  int rc = MSR_OK;
+  if (cudaMemcpy(d_wm, wm.data(), wm.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess)
+    rc = fail(MSR_E_CUDA, "msr_op_enc1_tc: weight upload failed");
+  if (!rc) rc = enc1_conv_tc(d_source, I, reinterpret_cast<const __nv_bfloat16*>(d_wm), reinterpret_cast<__nv_bfloat16*>(d_out),
+                             n, slope, (cudaStream_t)stream);
+  if (!rc && cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) rc = fail(MSR_E_CUDA, "msr_op_enc1_tc: kernel failed");
   cudaFree(d_wm);
   return rc;
 }

@@ -87,6 +87,7 @@ struct msr_generator {
   // bf16 mode extras
   const __nv_bfloat16* out_wt = nullptr;         // [32][9*128] sub-pixel phase weights of the final 4x4 conv
   const __nv_bfloat16* enc1_wt = nullptr;        // [64][64] im2col weights of encoder block 1
+  const __nv_bfloat16* enc1_wm = nullptr;        // the same in the K layout of mask_tc.cu (operand tile built in the kernel)
   const __nv_bfloat16* enc_wt[5] = {};           // [cout][9*cin] for blocks 2..5
   const __nv_bfloat16* enc_head_wt = nullptr;    // [512 = mean | variance][3 * feat]: split-bf16 rows (w_hi | w_lo | w_hi)
   const float* enc_head_b = nullptr;             // [512]
@@ -301,7 +302,7 @@ int load_spade(msr_generator* g, const std::string& pre, int C, SpadeW* s) {
     std::vector<uint16_t> cwm;
     const HostTensor* cb;
     if ((rc = need(g, pre + ".conv.bias", {kHidden}, &cb))) return rc;
-    mask_tc_pack_weights(cw->data.data(), cb->data.data(), &cwm);
+    mask_tc_pack_weights(cw->data.data(), cb->data.data(), kHidden, &cwm);
     if ((rc = upload_bf16(g, cwm, &s->conv_wm))) return rc;
   }
   return MSR_OK;
@@ -368,6 +369,9 @@ int finalize_spade_bf16_extras(msr_generator* g) {
         w[(size_t)co * 64 + 36 + k] = hi;
       }
     if ((rc = upload_bf16(g, w, &g->enc1_wt))) return rc;
+    std::vector<uint16_t> wm;
+    mask_tc_pack_weights(t->data.data(), nullptr, kEnc[0], &wm);
+    if ((rc = upload_bf16(g, wm, &g->enc1_wm))) return rc;
   }
   for (int k = 1; k < 5; ++k) {
     const int cin = kEnc[k - 1], cout = kEnc[k], K = 9 * cin;
@@ -913,8 +917,10 @@ int forward_spade_bf16(Fwd& f, const float* source, const float* eps, float* out
   // ---- encoder (networks.py:8-34); its mean | variance rows (lat_mv) are kept across the generations of a batch
   if (!reuse) {
   // block 1: conv3x3 s2 (2 -> 64, no bias, no norm) + LeakyReLU(0.2) as an im2col GEMM
-  if ((rc = source_patches_bf16(source, I, g->patches, n, I / 2, 1, st))) return rc;
-  {
+  if (mask_in_kernel(g, I / 2)) {
+    if ((rc = enc1_conv_tc(source, I, g->enc1_wm, g->enc_b0, n, 0.2f, st))) return rc;
+  } else {
+    if ((rc = source_patches_bf16(source, I, g->patches, n, I / 2, 1, st))) return rc;
     ConvTCArgs a;
     a.x = g->patches; a.w = g->enc1_wt; a.n = n; a.r = I / 2; a.cin = 64; a.ncols = kEnc[0]; a.taps = 1; a.pad = 0;
     a.epilogue = TC_EPI_ACT_BF16; a.act = ACT_LRELU; a.slope = 0.2f; a.out_bf16 = g->enc_b0; a.split_out = 1;

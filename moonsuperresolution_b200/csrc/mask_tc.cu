@@ -13,6 +13,10 @@
 // double-buffered staging area and four store warps write whole rows from there, so that reading the next accumulator
 // out of TMEM overlaps the previous tile's stores.
 //
+// MODE 1 of the same kernel is the encoder's first block (blocks.py:53-60 with apply_norm=False, networks.py:12): Conv2D(64, 3,
+// strides=2, 'same', no bias) on the full-resolution source (taps (2h + ky, 2w + kx), SAME padding (0, 1)) -> LeakyReLU(0.2)
+// -> split-bf16 row hi (64) | lo (64), the operand of the next encoder convolution.
+//
 // Split-bf16 K layout (the three products x_hi*w_hi + x_lo*w_hi + x_hi*w_lo ~ a float32 product; mask_tc_pack_weights):
 //   k = 4t + {0, 1, 2, 3}   tap t = ky*3 + kx:  x = (hi0, hi1, lo0, lo1)   w = (whi0, whi1, whi0, whi1)
 //   k = 36 + 2t + {0, 1}                        x = (hi0, hi1)             w = (wlo0, wlo1)
@@ -45,8 +49,9 @@ struct MaskGeom {
   int I, f, half;          // source side, I / r, (I / r) / 2: mask pixel (h, w) = source pixel (h*f + half, w*f + half)
   int64_t M;               // n * r * r pixels
   int n_tiles;             // ceil(M / 128)
+  float slope;             // MODE 1: LeakyReLU slope
   const float* src;        // [n][I][I][2] float32
-  __nv_bfloat16* out;      // [M][128]
+  __nv_bfloat16* out;      // [M][128]: MODE 0 the 128 channels; MODE 1 hi (64) | lo (64)
 };
 
 __device__ __forceinline__ void mbar_arrive_release(uint32_t bar) {
@@ -54,8 +59,10 @@ __device__ __forceinline__ void mbar_arrive_release(uint32_t bar) {
 }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+template <int MODE>
 __global__ void __launch_bounds__(kMkThreads, 1)
 mask_conv_tc_kernel(const __grid_constant__ CUtensorMap map_b, const MaskGeom g) {
+  constexpr int kN = MODE == 0 ? kMkN : 64;          // GEMM columns
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -93,7 +100,7 @@ mask_conv_tc_kernel(const __grid_constant__ CUtensorMap map_b, const MaskGeom g)
   constexpr int kProdWarp0 = kMkEpiWarps + kMkStoreWarps, kMmaWarp = kProdWarp0 + kMkProdWarps;
   if (warp == kMmaWarp) {
     if (lane == 0) tma_prefetch_desc(&map_b);
-    tmem_alloc(smem_u32((const void*)tmem_slot), kMkAcc * kMkN);
+    tmem_alloc(smem_u32((const void*)tmem_slot), kMkAcc * kN);
   }
   tc_fence_before();
   __syncthreads();
@@ -121,9 +128,19 @@ mask_conv_tc_kernel(const __grid_constant__ CUtensorMap map_b, const MaskGeom g)
         for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
           for (int kx = 0; kx < 3; ++kx) {
-            const int hh = h + ky - 1, ww = w + kx - 1;   // SAME padding (1, 1) on the resized mask
-            if (hh >= 0 && hh < r && ww >= 0 && ww < r)
-              s[ky * 3 + kx] = __ldg(reinterpret_cast<const float2*>(img + ((int64_t)(hh * f + g.half) * I + ww * f + g.half) * 2));
+            int sy, sx;
+            bool ok;
+            if constexpr (MODE == 0) {   // SAME padding (1, 1) on the resized mask; nearest resize, half-pixel centres
+              const int hh = h + ky - 1, ww = w + kx - 1;
+              ok = hh >= 0 && hh < r && ww >= 0 && ww < r;
+              sy = hh * f + g.half;
+              sx = ww * f + g.half;
+            } else {                     // stride-2 taps on the source itself, SAME padding (0, 1)
+              sy = 2 * h + ky;
+              sx = 2 * w + kx;
+              ok = sy < I && sx < I;
+            }
+            if (ok) s[ky * 3 + kx] = __ldg(reinterpret_cast<const float2*>(img + ((int64_t)sy * I + sx) * 2));
           }
         }
       }
@@ -177,9 +194,9 @@ mask_conv_tc_kernel(const __grid_constant__ CUtensorMap map_b, const MaskGeom g)
   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer (+ the one-off weight load) =====================
     if (lane == 0) {
-      mbar_expect_tx(w_bar, kMkBBytes);
+      mbar_expect_tx(w_bar, kN * kBlockK * 2);
       tma_load_2d(smem_base, &map_b, w_bar, 0, 0);
-      constexpr uint32_t idesc = make_idesc(kMkN, kBlockM);
+      constexpr uint32_t idesc = make_idesc(kN, kBlockM);
       mbar_wait(w_bar, 0);
       tc_fence_after();
       const uint64_t bdesc = make_smem_desc(smem_base);
@@ -192,7 +209,7 @@ mask_conv_tc_kernel(const __grid_constant__ CUtensorMap map_b, const MaskGeom g)
         const uint64_t adesc = make_smem_desc(smem_base + kOffA + stage * kMkABytes);
 #pragma unroll
         for (int k = 0; k < kBlockK / 16; ++k)
-          umma_bf16(tmem_base + (uint32_t)(acc * kMkN), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+          umma_bf16(tmem_base + (uint32_t)(acc * kN), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
                     k != 0 ? 1u : 0u);
         umma_commit(empty_bar(stage));
         umma_commit(tfull_bar(acc));
@@ -217,31 +234,54 @@ mask_conv_tc_kernel(const __grid_constant__ CUtensorMap map_b, const MaskGeom g)
     for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kMkN + csel * 64);
+      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kN + csel * (kN / 2));
       uint32_t v0[32], v1[32];
       tmem_ld32(t_row, v0);
-      tmem_ld32(t_row + 32u, v1);
+      if constexpr (MODE == 0) tmem_ld32(t_row + 32u, v1);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));     // the accumulator is in registers: the tensor core may reuse it
       mbar_wait(sempty_bar(buf), buf_phase ^ 1u);      // the store warps have read this staging buffer's previous tile
       uint8_t* stg = smem_gen + kOffOut + buf * kMkStageOut + quarter * (32 * kMkRowPitch);
-      uint4* dst = reinterpret_cast<uint4*>(stg + lane * kMkRowPitch + csel * 128);
-      auto pack8 = [&](const uint32_t* v, int q) {   // relu (the bias is already in the accumulator) -> 8 bf16
-        uint32_t pk[4];
+      if constexpr (MODE == 0) {
+        uint4* dst = reinterpret_cast<uint4*>(stg + lane * kMkRowPitch + csel * 128);
+        auto pack8 = [&](const uint32_t* v, int q) {   // relu (the bias is already in the accumulator) -> 8 bf16
+          uint32_t pk[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const __nv_bfloat162 t2 = __floats2bfloat162_rn(fmaxf(__uint_as_float(v[8 * q + 2 * j]), 0.f),
-                                                          fmaxf(__uint_as_float(v[8 * q + 2 * j + 1]), 0.f));
-          pk[j] = *reinterpret_cast<const uint32_t*>(&t2);
+          for (int j = 0; j < 4; ++j) {
+            const __nv_bfloat162 t2 = __floats2bfloat162_rn(fmaxf(__uint_as_float(v[8 * q + 2 * j]), 0.f),
+                                                            fmaxf(__uint_as_float(v[8 * q + 2 * j + 1]), 0.f));
+            pk[j] = *reinterpret_cast<const uint32_t*>(&t2);
+          }
+          return make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        };
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dst[q] = pack8(v0, q);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dst[4 + q] = pack8(v1, q);
+      } else {
+        // columns [32*csel, 32*csel + 32): leaky_relu -> hi at bytes [64*csel, +64) of the row, lo = v - hi at 128 + the same
+        uint4* dhi = reinterpret_cast<uint4*>(stg + lane * kMkRowPitch + csel * 64);
+        uint4* dlo = reinterpret_cast<uint4*>(stg + lane * kMkRowPitch + 128 + csel * 64);
+        const float sl = g.slope;   // 0 < slope < 1: leaky_relu(x) = max(x, slope * x)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t ph[4], pl[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float a0 = __uint_as_float(v0[8 * q + 2 * j]), a1 = __uint_as_float(v0[8 * q + 2 * j + 1]);
+            const float o0 = fmaxf(a0, a0 * sl), o1 = fmaxf(a1, a1 * sl);
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(o0, o1);
+            const float2 hf = __bfloat1622float2(h2);
+            const __nv_bfloat162 l2 = __floats2bfloat162_rn(o0 - hf.x, o1 - hf.y);
+            ph[j] = *reinterpret_cast<const uint32_t*>(&h2);
+            pl[j] = *reinterpret_cast<const uint32_t*>(&l2);
+          }
+          dhi[q] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+          dlo[q] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
         }
-        return make_uint4(pk[0], pk[1], pk[2], pk[3]);
-      };
-#pragma unroll
-      for (int q = 0; q < 4; ++q) dst[q] = pack8(v0, q);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) dst[4 + q] = pack8(v1, q);
+      }
       __syncwarp();
       if (lane == 0) mbar_arrive_release(sfull_bar(buf));
       if (++acc == kMkAcc) {
@@ -292,14 +332,14 @@ mask_conv_tc_kernel(const __grid_constant__ CUtensorMap map_b, const MaskGeom g)
   __syncthreads();
   if (warp == kMmaWarp) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kMkAcc * kMkN);
+    tmem_dealloc(tmem_base, kMkAcc * kN);
   }
 }
 
 }  // namespace tc
 
 // ---- host side ----------------------------------------------------------------------------------------------------------
-void mask_tc_pack_weights(const float* w, const float* bias, std::vector<uint16_t>* out) {
+void mask_tc_pack_weights(const float* w, const float* bias, int cout, std::vector<uint16_t>* out) {
   auto f2bf = [](float f) {
     uint32_t u;
     memcpy(&u, &f, 4);
@@ -311,43 +351,47 @@ void mask_tc_pack_weights(const float* w, const float* bias, std::vector<uint16_
     memcpy(&f, &u, 4);
     return f;
   };
-  out->assign((size_t)128 * 64, 0);
+  out->assign((size_t)cout * 64, 0);
   for (int t = 0; t < 9; ++t)
     for (int c = 0; c < 2; ++c)
-      for (int co = 0; co < 128; ++co) {
-        const float v = w[(size_t)(t * 2 + c) * 128 + co];
+      for (int co = 0; co < cout; ++co) {
+        const float v = w[(size_t)(t * 2 + c) * cout + co];
         const uint16_t hi = f2bf(v), lo = f2bf(v - bf2f(hi));
         uint16_t* row = out->data() + (size_t)co * 64;
         row[4 * t + c] = hi;          // pairs with x_hi
         row[4 * t + 2 + c] = hi;      // pairs with x_lo
         row[36 + 2 * t + c] = lo;     // pairs with x_hi
       }
-  for (int co = 0; co < 128; ++co) {  // bias as two more K rows against constant ones in the operand
-    const uint16_t hi = f2bf(bias[co]);
-    (*out)[(size_t)co * 64 + 54] = hi;
-    (*out)[(size_t)co * 64 + 55] = f2bf(bias[co] - bf2f(hi));
-  }
+  if (bias != nullptr)
+    for (int co = 0; co < cout; ++co) {  // bias as two more K rows against constant ones in the operand
+      const uint16_t hi = f2bf(bias[co]);
+      (*out)[(size_t)co * 64 + 54] = hi;
+      (*out)[(size_t)co * 64 + 55] = f2bf(bias[co] - bf2f(hi));
+    }
 }
 
 bool mask_tc_supported(int I, int r) { return r >= 1 && (r & (r - 1)) == 0 && r <= I && I % r == 0; }
 
-int mask_conv_tc(const float* source, int I, const __nv_bfloat16* wm, __nv_bfloat16* out, int n, int r, cudaStream_t st) {
-  MSR_REQUIRE(source && wm && out && n > 0, "mask_conv_tc: bad arguments");
-  MSR_REQUIRE(mask_tc_supported(I, r), "mask_conv_tc: r must be a power of two dividing I");
+// mode 0: SPADE mask convolution at side r; mode 1: encoder block 1 (r = I / 2)
+static int source_conv_tc(int mode, const float* source, int I, const __nv_bfloat16* wm, __nv_bfloat16* out, int n, int r,
+                          float slope, cudaStream_t st) {
+  MSR_REQUIRE(source && wm && out && n > 0, "source_conv_tc: bad arguments");
+  MSR_REQUIRE(mask_tc_supported(I, r), "source_conv_tc: r must be a power of two dividing I");
   MSR_REQUIRE((reinterpret_cast<uintptr_t>(wm) & 127) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
-                  (reinterpret_cast<uintptr_t>(source) & 7) == 0, "mask_conv_tc: misaligned operand");
+                  (reinterpret_cast<uintptr_t>(source) & 7) == 0, "source_conv_tc: misaligned operand");
   EncodeTiledFn enc = get_encode_fn();
-  if (!enc) return fail(MSR_E_CUDA, "mask_conv_tc: cuTensorMapEncodeTiled entry point not available");
+  if (!enc) return fail(MSR_E_CUDA, "source_conv_tc: cuTensorMapEncodeTiled entry point not available");
+  const int cols = mode == 0 ? tc::kMkN : 64;
   CUtensorMap map_b;
   {
-    cuuint64_t dims[2] = {(cuuint64_t)tc::kBlockK, (cuuint64_t)tc::kMkN};
+    cuuint64_t dims[2] = {(cuuint64_t)tc::kBlockK, (cuuint64_t)cols};
     cuuint64_t strides[1] = {(cuuint64_t)tc::kBlockK * 2};
-    cuuint32_t box[2] = {(cuuint32_t)tc::kBlockK, (cuuint32_t)tc::kMkN};
+    cuuint32_t box[2] = {(cuuint32_t)tc::kBlockK, (cuuint32_t)cols};
     cuuint32_t estr[2] = {1, 1};
     CUresult rc = enc(&map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(wm), dims, strides, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (rc != CUDA_SUCCESS) return fail(MSR_E_CUDA, "mask_conv_tc: cuTensorMapEncodeTiled failed with " + std::to_string((int)rc));
+    if (rc != CUDA_SUCCESS) return fail(MSR_E_CUDA, "source_conv_tc: cuTensorMapEncodeTiled failed with " + std::to_string((int)rc));
   }
   tc::MaskGeom g;
   g.n = n; g.r = r; g.lr = 0;
@@ -355,20 +399,33 @@ int mask_conv_tc(const float* source, int I, const __nv_bfloat16* wm, __nv_bfloa
   g.I = I; g.f = I / r; g.half = g.f >> 1;
   g.M = (int64_t)n * r * r;
   g.n_tiles = (int)((g.M + tc::kBlockM - 1) / tc::kBlockM);
+  g.slope = slope;
   g.src = source; g.out = out;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  ProfileScope prof(MSR_PROF_CONV_TC, st, 2.0 * (double)g.M * 128 * 18);
+  ProfileScope prof(MSR_PROF_CONV_TC, st, 2.0 * (double)g.M * cols * 18);
   static bool attr_set = false;
   if (!attr_set) {
-    MSR_CUDA_CHECK(cudaFuncSetAttribute(tc::mask_conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kMkSmemBytes));
+    MSR_CUDA_CHECK(cudaFuncSetAttribute(tc::mask_conv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kMkSmemBytes));
+    MSR_CUDA_CHECK(cudaFuncSetAttribute(tc::mask_conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kMkSmemBytes));
     attr_set = true;
   }
-  tc::mask_conv_tc_kernel<<<std::min(g.n_tiles, sms), tc::kMkThreads, tc::kMkSmemBytes, st>>>(map_b, g);
+  const int grid = std::min(g.n_tiles, sms);
+  if (mode == 0) tc::mask_conv_tc_kernel<0><<<grid, tc::kMkThreads, tc::kMkSmemBytes, st>>>(map_b, g);
+  else tc::mask_conv_tc_kernel<1><<<grid, tc::kMkThreads, tc::kMkSmemBytes, st>>>(map_b, g);
   count_launch();
   MSR_LAUNCH_CHECK();
   return MSR_OK;
+}
+
+int mask_conv_tc(const float* source, int I, const __nv_bfloat16* wm, __nv_bfloat16* out, int n, int r, cudaStream_t st) {
+  return source_conv_tc(0, source, I, wm, out, n, r, 0.f, st);
+}
+
+int enc1_conv_tc(const float* source, int I, const __nv_bfloat16* wm, __nv_bfloat16* out, int n, float slope, cudaStream_t st) {
+  MSR_REQUIRE(I >= 2 && I % 2 == 0, "enc1_conv_tc: the source side must be even");
+  return source_conv_tc(1, source, I, wm, out, n, I / 2, slope, st);
 }
 
 }  // namespace msr

@@ -145,9 +145,12 @@ void phase_tc_plan_destroy(PhaseTC* plan);
 // out[n][r][r][128] bf16 = relu(conv3x3(nearest_resize(source [n][I][I][2] fp32 -> r x r), w) + bias)   (spade.py:17-18)
 // wm: [128][64] bf16 from mask_tc_pack_weights (w: Keras kernel [3][3][2][128] float32, bias [128]): split-bf16 K layout,
 // the bias folded in as two more K rows.
-void mask_tc_pack_weights(const float* w, const float* bias, std::vector<uint16_t>* out);
+void mask_tc_pack_weights(const float* w, const float* bias, int cout, std::vector<uint16_t>* out);
 bool mask_tc_supported(int I, int r);
 int mask_conv_tc(const float* source, int I, const __nv_bfloat16* wm, __nv_bfloat16* out, int n, int r, cudaStream_t st);
+// Encoder block 1 with the same kernel (blocks.py:53-60, no norm; networks.py:12): out [n][I/2][I/2][128] bf16 = hi (64) |
+// lo (64) of leaky_relu(conv3x3 stride 2, SAME (0, 1), 2 -> 64, no bias); wm [64][64] from mask_tc_pack_weights(w, null, 64).
+int enc1_conv_tc(const float* source, int I, const __nv_bfloat16* wm, __nv_bfloat16* out, int n, float slope, cudaStream_t st);
 
 // ---- small helpers for the bf16 path (nn_bf16.cu) -----------------------------------------------------------------
 // im2col of the 2-channel source for a 3x3 convolution at output side r: out [n][r][r][64] bf16, channel (ky*3+kx)*2+c

@@ -212,6 +212,34 @@ def test_mask_convolution_tensor_core_operator(torch, n, i, r):
     assert (guard == 7.0).all()
 
 
+@pytest.mark.parametrize("n,i", [(3, 64), (2, 256), (16, 512), (1, 8)])
+def test_encoder_block1_tensor_core_operator(torch, n, i):
+    """Encoder block 1 (Conv2D(64, 3, strides=2, 'same', no bias) -> LeakyReLU(0.2)) with the operand tile built inside the
+    kernel (csrc/mask_tc.cu, MODE 1) against torch float64; SAME on an even input with stride 2 pads (0, 1).  The output is
+    the split-bf16 pair hi | lo: hi must be the bf16 rounding of the value (one step at most), hi + lo the value to ~2^-16."""
+    from moonsuperresolution_b200 import _lib
+    import torch.nn.functional as F
+    rng = np.random.default_rng(n * 10 + i)
+    src = rng.uniform(-0.5, 0.5, (n, i, i, 2)).astype(np.float32)
+    src[0, -1, :] = 0.5                                  # the padded side (bottom / right) carries weight
+    src[0, :, -1] = -0.5
+    w = (rng.standard_normal((3, 3, 2, 64)) / np.sqrt(18)).astype(np.float32)
+    xt = F.pad(torch.from_numpy(src).cuda().double().permute(0, 3, 1, 2), (0, 1, 0, 1))
+    want = F.leaky_relu(F.conv2d(xt, torch.from_numpy(w).cuda().double().permute(3, 2, 0, 1), stride=2), 0.2).permute(0, 2, 3, 1)
+    r = i // 2
+    assert want.shape == (n, r, r, 64)
+    d_src = torch.from_numpy(src).cuda()
+    d_y = torch.full((n, r, r, 128), float("nan"), dtype=torch.bfloat16, device="cuda")
+    _lib.check(_lib.lib().msr_op_enc1_tc(d_src.data_ptr(), i, w.ctypes.data, d_y.data_ptr(), n, 0.2, _lib.stream_ptr()),
+               "msr_op_enc1_tc")
+    torch.cuda.synchronize()
+    hi, lo = d_y[..., :64].double(), d_y[..., 64:].double()
+    assert torch.isfinite(hi).all() and torch.isfinite(lo).all()
+    assert ((hi - want).abs() <= 2.0 ** -7 * (want.abs() + 1e-3)).all()
+    err = ((hi + lo - want).abs() / (1.0 + want.abs())).max().item()
+    assert err < 3e-5, err
+
+
 @pytest.mark.parametrize("n,r,C,x_shift,spg", [(4, 16, 128, 1, 2), (2, 64, 256, 0, 2), (2, 128, 128, 1, 1), (3, 4, 64, 0, 3)])
 def test_fused_spade_operator(torch, n, r, C, x_shift, spg):
     """gamma|beta conv + normalise + modulate + LeakyReLU(0.2) (spade.py:19-24, blocks.py:30) with the nearest x2
