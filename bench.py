@@ -615,16 +615,18 @@ def main():
         tpath = os.path.join(ROOT, "profiles", "conv_tc_traffic.json")
         traffic_note = None
         if os.path.exists(tpath) and args.arch in ("spade", "cnn") and args.image_size == 512:
-            # ncu --set full capture of ONE forward at the bench batch (128 patches = groups 8 x batch 16): all 53 tcgen05
-            # launches (profiles/r02_ncu_conv_bench_batch.md); scaled only if the command line changes the call size
+            # ncu capture of ONE forward at the bench batch (128 patches = groups 8 x batch 16): all 53 tcgen05 launches
+            # (profiles/r02b_ncu_tc_bench_batch.md); scaled only if the command line changes the call size
             tj = json.load(open(tpath))
             traffic = tj.get("dram_bytes_per_launch") * (args.groups * args.batch_size / float(tj.get("patches_per_forward", 128)))
             tensor_pct = tj.get("tensor_pipe_active_pct_time_weighted")
             traffic_note = ("dram__bytes_read + write per launch and time-weighted sm__pipe_tensor_cycles_active from "
-                            "profiles/conv_tc_traffic.json: ncu --set full over the 53 tcgen05 launches of one 128-patch "
+                            "profiles/conv_tc_traffic.json: ncu over the 53 tcgen05 launches of one 128-patch "
                             "forward (kernels replayed alone at boost clocks, where DRAM / L2 weigh more against the tensor "
                             "pipe than in the power-capped step at ~1.39 GHz; `frac` is the steady-state figure)")
-        roofline = {"bound": "tensor", "kernel": "conv3x3_tc_kernel (tcgen05 implicit GEMM, all launches of one step)",
+        roofline = {"bound": "tensor",
+                    "kernel": "tcgen05 kernels of the generator, all launches of one step: conv3x3_tc_kernel (implicit GEMM), "
+                              "mask_conv_tc_kernel (operand tile built in the kernel), phase_stencil_tc_kernel (last layer)",
                     "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
                     "peak_source": f"MEASURED_PEAKS.json bf16 sustained ({pk['source']})", "traffic": traffic,
                     "ncu_tensor_pipe_active_pct": tensor_pct,

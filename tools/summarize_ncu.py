@@ -44,7 +44,9 @@ def conv(path, prefix):
                  "second": 1.0}.get(unit, 1.0)
         d[r["Metric Name"]] = val * scale
     tot_t = sum(d["gpu__time_duration.sum"] for d in launches.values())
-    tp = "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed"
+    tp = "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"
+    if not any(tp in d for d in launches.values()):   # the triage variant (part of --set full only)
+        tp = "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed"
     lines = ["| # | kernel | ms | tensor pipe active % | DRAM read MB | DRAM write MB | L2 bytes MB | DRAM % | SM % |", "|---|---|---|---|---|---|---|---|---|"]
     dram = 0.0
     for k, d in enumerate(launches.values()):
@@ -56,16 +58,20 @@ def conv(path, prefix):
             d.get("sm__throughput.avg.pct_of_peak_sustained_elapsed", 0.0)))
     weighted = sum(d.get(tp, 0.0) * d["gpu__time_duration.sum"] for d in launches.values()) / tot_t
     n = len(launches)
-    summary = {"source": "ncu --metrics ... -k regex:conv3x3_tc -s 53 -c 53 python tools/ncu_forward.py 512 16 8 "
-                         "(one GauGAN-512 forward over 128 patches = one bench launch group; kernels run alone, cold L2)",
+    summary = {"source": "ncu --metrics ... -k regex:'conv3x3_tc|mask_conv_tc|phase_stencil_tc' -s 53 -c 53 python "
+                         "tools/ncu_forward.py 512 16 8 (second GauGAN-512 forward over 128 patches = one bench launch "
+                         "group; kernels replayed alone, cold L2, boost clocks)",
                "launches": n, "patches_per_forward": 128, "total_ms_under_ncu": tot_t * 1e3,
                "dram_bytes_per_forward": dram, "dram_bytes_per_launch": dram / n,
                "tensor_pipe_active_pct_time_weighted": weighted}
     open(prefix + ".md", "w").write(
-        "# tcgen05 convolution launches of one GauGAN-512 forward at the bench batch (128 patches), ncu metrics\n\n"
+        "# tcgen05 launches of one GauGAN-512 forward at the bench batch (128 patches), ncu metrics\n\n"
         "%s\n\ntime-weighted tensor-pipe activity %.1f %%, DRAM traffic %.1f GB per forward (%.1f MB per launch), "
         "%d launches, %.2f ms under ncu (serialised, cold cache, boost clocks: compare shares, not absolutes)\n\n" %
         (summary["source"], weighted, dram / 1e9, dram / n / 1e6, n, tot_t * 1e3) + "\n".join(lines) + "\n")
+    big = [d for d in launches.values() if d["gpu__time_duration.sum"] > 0.3e-3]
+    summary["tensor_pipe_active_pct_time_weighted_launches_over_0.3ms"] = (
+        sum(d.get(tp, 0.0) * d["gpu__time_duration.sum"] for d in big) / max(sum(d["gpu__time_duration.sum"] for d in big), 1e-12))
     json.dump(summary, open("profiles/conv_tc_traffic.json", "w"), indent=1)
     print(json.dumps(summary, indent=1))
 
@@ -89,7 +95,7 @@ def launches(path, out):
             "", "| kernel | launches | ms | share |", "|---|---|---|---|"]
     for name, (cnt, t) in rows:
         text.append("| `%s` | %d | %.2f | %.2f %% |" % (name, cnt, t * 1e3, 100 * t / tot))
-    tc = sum(t for name, (cnt, t) in rows if "conv3x3_tc" in name)
+    tc = sum(t for name, (cnt, t) in rows if any(k in name for k in ("conv3x3_tc", "mask_conv_tc", "phase_stencil_tc")))
     text += ["", "tcgen05 convolution family: %.2f %% of the kernel time" % (100 * tc / tot)]
     open(out, "w").write("\n".join(text) + "\n")
     print("\n".join(text[:14]))
