@@ -9,9 +9,9 @@
 // into bf16 hi + lo, and writes its 128-byte row in the 128-byte-swizzled K-major layout a TMA load would have produced
 // (16-byte chunk c of row i at chunk position c ^ (i & 7)); fence.proxy.async makes the generic-proxy stores visible to
 // tcgen05.mma.  The weights (128 x 64 bf16, 16 KB) stay in shared memory for the whole kernel.  What remains is the
-// unavoidable part: 256 bytes written per pixel -- the eight epilogue warps park relu(acc + bias) as bf16 rows in a
-// double-buffered staging area and four store warps write whole rows from there, so that reading the next accumulator
-// out of TMEM overlaps the previous tile's stores.
+// unavoidable part: 256 bytes written per pixel -- the eight epilogue warps park relu(acc + bias) as bf16 rows in shared
+// memory (swizzled box layout) and one thread hands each tile to the TMA store engine, so the next accumulator is read
+// out of TMEM while the previous tiles are still on their way to HBM.
 //
 // MODE 1 of the same kernel is the encoder's first block (blocks.py:53-60 with apply_norm=False, networks.py:12): Conv2D(64, 3,
 // strides=2, 'same', no bias) on the full-resolution source (taps (2h + ky, 2w + kx), SAME padding (0, 1)) -> LeakyReLU(0.2)
@@ -32,16 +32,15 @@ namespace msr {
 
 namespace tc {
 
-constexpr int kMkStages = 6;                          // A tiles (16 KB each) in flight between producers and the MMA thread
+constexpr int kMkStages = 5;                          // A tiles (16 KB each) in flight between producers and the MMA thread
 constexpr int kMkAcc = 4;                             // 128-column accumulators in TMEM
 constexpr int kMkN = 128;
 constexpr int kMkEpiWarps = 8, kMkProdWarps = 4;       // producers: one thread per tile row
-constexpr int kMkStoreWarps = 4, kMkOutBufs = 2;       // one store warp per TMEM lane quarter; double-buffered staging
-constexpr int kMkThreads = (kMkEpiWarps + kMkStoreWarps + kMkProdWarps + 1) * 32;
+constexpr int kMkOutBufs = 3;                          // staging buffers of the TMA store (two stores may be in flight)
+constexpr int kMkThreads = (kMkEpiWarps + kMkProdWarps + 1) * 32;
 constexpr int kMkABytes = kBlockM * kBlockK * 2;      // 16 KB
 constexpr int kMkBBytes = kMkN * kBlockK * 2;         // 16 KB
-constexpr int kMkRowPitch = 256 + 16;                 // staging rows of the whole-row epilogue (see conv_tc.cu)
-constexpr int kMkStageOut = 4 * 32 * kMkRowPitch;
+constexpr int kMkStageOut = 2 * kBlockM * 128;        // one output tile: two 128-row x 128-byte boxes (128-byte swizzle)
 constexpr int kMkSmemBytes = 1024 + kMkBBytes + kMkStages * kMkABytes + kMkOutBufs * kMkStageOut + 256;
 
 struct MaskGeom {
@@ -58,10 +57,19 @@ __device__ __forceinline__ void mbar_arrive_release(uint32_t bar) {
   asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// TMA store of one box (shared -> global, bulk async-group completion)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 template <int MODE>
 __global__ void __launch_bounds__(kMkThreads, 1)
-mask_conv_tc_kernel(const __grid_constant__ CUtensorMap map_b, const MaskGeom g) {
+mask_conv_tc_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_o, const MaskGeom g) {
   constexpr int kN = MODE == 0 ? kMkN : 64;          // GEMM columns
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -75,10 +83,7 @@ mask_conv_tc_kernel(const __grid_constant__ CUtensorMap map_b, const MaskGeom g)
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kMkStages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kMkStages + kMkAcc + a); };
   const uint32_t w_bar = bar_base + 8u * (2 * kMkStages + 2 * kMkAcc);
-  auto sfull_bar = [&](int b) { return bar_base + 8u * (2 * kMkStages + 2 * kMkAcc + 1 + b); };
-  auto sempty_bar = [&](int b) { return bar_base + 8u * (2 * kMkStages + 2 * kMkAcc + 1 + kMkOutBufs + b); };
-  volatile uint32_t* tmem_slot =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + kOffBar + 8 * (2 * kMkStages + 2 * kMkAcc + 1 + 2 * kMkOutBufs));
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + kOffBar + 8 * (2 * kMkStages + 2 * kMkAcc + 1));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -91,15 +96,14 @@ mask_conv_tc_kernel(const __grid_constant__ CUtensorMap map_b, const MaskGeom g)
       mbar_init(tempty_bar(a), kMkEpiWarps);
     }
     mbar_init(w_bar, 1);
-    for (int b = 0; b < kMkOutBufs; ++b) {
-      mbar_init(sfull_bar(b), kMkEpiWarps);      // all eight (quarter, column half) pieces of the tile are parked
-      mbar_init(sempty_bar(b), kMkStoreWarps);
-    }
     fence_barrier_init();
   }
-  constexpr int kProdWarp0 = kMkEpiWarps + kMkStoreWarps, kMmaWarp = kProdWarp0 + kMkProdWarps;
+  constexpr int kProdWarp0 = kMkEpiWarps, kMmaWarp = kProdWarp0 + kMkProdWarps;
   if (warp == kMmaWarp) {
-    if (lane == 0) tma_prefetch_desc(&map_b);
+    if (lane == 0) {
+      tma_prefetch_desc(&map_b);
+      tma_prefetch_desc(&map_o);
+    }
     tmem_alloc(smem_u32((const void*)tmem_slot), kMkAcc * kN);
   }
   tc_fence_before();
@@ -223,14 +227,19 @@ mask_conv_tc_kernel(const __grid_constant__ CUtensorMap map_b, const MaskGeom g)
         }
       }
     }
-  } else if (warp < kMkEpiWarps) {
-    // ===================== epilogue warps 0..7: relu(acc + bias) -> bf16 rows in the staging buffer =================
-    // warp = (TMEM lane quarter, column half): lane l owns tile row quarter*32 + l and columns [64*csel, 64*csel + 64).
-    // The global stores are the store warps' job (below), so this chain is TMEM -> registers -> shared memory only and
-    // the next tile's accumulator can be read while the previous tile's rows are still on their way out.
+  } else {
+    // ===================== epilogue warps 0..7: relu(acc + bias) -> bf16 -> TMA store =====================
+    // warp = (TMEM lane quarter, column half): lane l owns tile row i = quarter*32 + l.  The tile leaves as two TMA stores
+    // of 128 rows x 128 bytes (columns [0, 64) and [64, 128)), so the rows are parked in shared memory in the 128-byte
+    // swizzled box layout (chunk c of row i at c ^ (i & 7)): no bank conflicts on the way in, no shared-memory reads or
+    // global store instructions on the way out (the L1 / LSU path, not HBM, bounded the version that copied the rows
+    // out with LDS + STG: l1tex 87 % busy at 4.0 TB/s).  Three staging buffers: thread 0 lets at most one store be
+    // pending before the barrier of tile k, so the buffer of tile k + 1 (last used by tile k - 2) is free after it.
     const int quarter = warp & 3, csel = warp >> 2;
+    const int i = quarter * 32 + lane;
+    const uint32_t row_off = (uint32_t)i * 128u, sw = (uint32_t)(i & 7);
     int acc = 0, buf = 0;
-    uint32_t acc_phase = 0, buf_phase = 0;
+    uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
@@ -242,10 +251,11 @@ mask_conv_tc_kernel(const __grid_constant__ CUtensorMap map_b, const MaskGeom g)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));     // the accumulator is in registers: the tensor core may reuse it
-      mbar_wait(sempty_bar(buf), buf_phase ^ 1u);      // the store warps have read this staging buffer's previous tile
-      uint8_t* stg = smem_gen + kOffOut + buf * kMkStageOut + quarter * (32 * kMkRowPitch);
+      uint8_t* stg = smem_gen + kOffOut + buf * kMkStageOut;
+      auto put = [&](int box, uint32_t c, uint4 val) {  // 16-byte chunk c of this thread's row in box 0 / 1
+        *reinterpret_cast<uint4*>(stg + box * (kBlockM * 128) + row_off + ((c ^ sw) << 4)) = val;
+      };
       if constexpr (MODE == 0) {
-        uint4* dst = reinterpret_cast<uint4*>(stg + lane * kMkRowPitch + csel * 128);
         auto pack8 = [&](const uint32_t* v, int q) {   // relu (the bias is already in the accumulator) -> 8 bf16
           uint32_t pk[4];
 #pragma unroll
@@ -256,14 +266,13 @@ mask_conv_tc_kernel(const __grid_constant__ CUtensorMap map_b, const MaskGeom g)
           }
           return make_uint4(pk[0], pk[1], pk[2], pk[3]);
         };
+        // columns [64*csel, 64*csel + 64) = box csel, chunks 0..7
 #pragma unroll
-        for (int q = 0; q < 4; ++q) dst[q] = pack8(v0, q);
+        for (int q = 0; q < 4; ++q) put(csel, q, pack8(v0, q));
 #pragma unroll
-        for (int q = 0; q < 4; ++q) dst[4 + q] = pack8(v1, q);
+        for (int q = 0; q < 4; ++q) put(csel, 4 + q, pack8(v1, q));
       } else {
-        // columns [32*csel, 32*csel + 32): leaky_relu -> hi at bytes [64*csel, +64) of the row, lo = v - hi at 128 + the same
-        uint4* dhi = reinterpret_cast<uint4*>(stg + lane * kMkRowPitch + csel * 64);
-        uint4* dlo = reinterpret_cast<uint4*>(stg + lane * kMkRowPitch + 128 + csel * 64);
+        // columns [32*csel, 32*csel + 32): leaky_relu -> hi into box 0, lo = v - hi into box 1, chunks 4*csel .. + 3
         const float sl = g.slope;   // 0 < slope < 1: leaky_relu(x) = max(x, slope * x)
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -278,54 +287,26 @@ mask_conv_tc_kernel(const __grid_constant__ CUtensorMap map_b, const MaskGeom g)
             ph[j] = *reinterpret_cast<const uint32_t*>(&h2);
             pl[j] = *reinterpret_cast<const uint32_t*>(&l2);
           }
-          dhi[q] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-          dlo[q] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+          put(0, (uint32_t)(4 * csel + q), make_uint4(ph[0], ph[1], ph[2], ph[3]));
+          put(1, (uint32_t)(4 * csel + q), make_uint4(pl[0], pl[1], pl[2], pl[3]));
         }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive_release(sfull_bar(buf));
+      fence_proxy_async_smem();                         // generic-proxy stores -> visible to the TMA store
+      if (threadIdx.x == 0) tma_store_wait_read<1>();   // the store issued two tiles ago has finished reading its buffer
+      asm volatile("bar.sync 1, %0;" ::"n"(kMkEpiWarps * 32) : "memory");
+      if (threadIdx.x == 0) {
+        const uint32_t s0 = smem_base + kOffOut + buf * kMkStageOut;
+        tma_store_2d(&map_o, s0, 0, tile * kBlockM);                       // rows beyond M are clipped by the tensor map
+        tma_store_2d(&map_o, s0 + kBlockM * 128, 64, tile * kBlockM);
+        tma_store_commit();
+      }
       if (++acc == kMkAcc) {
         acc = 0;
         acc_phase ^= 1u;
       }
-      if (++buf == kMkOutBufs) {
-        buf = 0;
-        buf_phase ^= 1u;
-      }
+      if (++buf == kMkOutBufs) buf = 0;
     }
-  } else {
-    // ===================== store warps: staging buffer -> whole 256-byte rows in HBM =====================
-    // store warp q writes the 32 rows of TMEM lane quarter q: 16 lanes per row, two rows (four full lines) per instruction
-    const int quarter = warp - kMkEpiWarps;
-    const int sub = lane >> 4, cb16 = (lane & 15) * 16;
-    int buf = 0;
-    uint32_t buf_phase = 0;
-    for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
-      const int64_t m0 = (int64_t)tile * kBlockM;
-      const int rows_ok = (int)min((int64_t)kBlockM, g.M - m0);
-      uint8_t* out_rows = reinterpret_cast<uint8_t*>(g.out) + (m0 + quarter * 32) * (kMkN * 2) + cb16;
-      mbar_wait(sfull_bar(buf), buf_phase);
-      const uint8_t* stg = smem_gen + kOffOut + buf * kMkStageOut + quarter * (32 * kMkRowPitch) + cb16;
-      uint4 val[8];
-#pragma unroll
-      for (int it = 0; it < 8; ++it) val[it] = *reinterpret_cast<const uint4*>(stg + (2 * it + sub) * kMkRowPitch);
-#pragma unroll
-      for (int it = 0; it < 8; ++it)
-        if (quarter * 32 + 2 * it + sub < rows_ok)
-          *reinterpret_cast<uint4*>(out_rows + (int64_t)(2 * it + sub) * (kMkN * 2)) = val[it];
-#pragma unroll
-      for (int it = 0; it < 8; ++it) val[it] = *reinterpret_cast<const uint4*>(stg + (16 + 2 * it + sub) * kMkRowPitch);
-      __syncwarp();
-      if (lane == 0) mbar_arrive_release(sempty_bar(buf));   // all rows of the buffer are in registers or on their way
-#pragma unroll
-      for (int it = 0; it < 8; ++it)
-        if (quarter * 32 + 16 + 2 * it + sub < rows_ok)
-          *reinterpret_cast<uint4*>(out_rows + (int64_t)(16 + 2 * it + sub) * (kMkN * 2)) = val[it];
-      if (++buf == kMkOutBufs) {
-        buf = 0;
-        buf_phase ^= 1u;
-      }
-    }
+    if (threadIdx.x == 0) tma_store_wait_all();         // all rows are in global memory before the CTA retires
   }
 
   tc_fence_before();
@@ -393,6 +374,17 @@ static int source_conv_tc(int mode, const float* source, int I, const __nv_bfloa
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (rc != CUDA_SUCCESS) return fail(MSR_E_CUDA, "source_conv_tc: cuTensorMapEncodeTiled failed with " + std::to_string((int)rc));
   }
+  const int64_t M_rows = (int64_t)n * r * r;
+  CUtensorMap map_o;   // output [M][128] bf16, stored as boxes of 128 rows x 64 columns
+  {
+    cuuint64_t dims[2] = {128, (cuuint64_t)M_rows};
+    cuuint64_t strides[1] = {256};
+    cuuint32_t box[2] = {64, (cuuint32_t)tc::kBlockM};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult rc = enc(&map_o, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) return fail(MSR_E_CUDA, "source_conv_tc: cuTensorMapEncodeTiled(out) failed with " + std::to_string((int)rc));
+  }
   tc::MaskGeom g;
   g.n = n; g.r = r; g.lr = 0;
   while ((1 << g.lr) < r) ++g.lr;
@@ -412,8 +404,8 @@ static int source_conv_tc(int mode, const float* source, int I, const __nv_bfloa
     attr_set = true;
   }
   const int grid = std::min(g.n_tiles, sms);
-  if (mode == 0) tc::mask_conv_tc_kernel<0><<<grid, tc::kMkThreads, tc::kMkSmemBytes, st>>>(map_b, g);
-  else tc::mask_conv_tc_kernel<1><<<grid, tc::kMkThreads, tc::kMkSmemBytes, st>>>(map_b, g);
+  if (mode == 0) tc::mask_conv_tc_kernel<0><<<grid, tc::kMkThreads, tc::kMkSmemBytes, st>>>(map_b, map_o, g);
+  else tc::mask_conv_tc_kernel<1><<<grid, tc::kMkThreads, tc::kMkSmemBytes, st>>>(map_b, map_o, g);
   count_launch();
   MSR_LAUNCH_CHECK();
   return MSR_OK;
