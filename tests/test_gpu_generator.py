@@ -34,7 +34,8 @@ def bf16_round(a, torch):
 
 @pytest.mark.parametrize("n,r,cin,cout", [(1, 8, 64, 128), (2, 16, 128, 256), (3, 4, 128, 128), (1, 32, 256, 384),
                                            (5, 2, 64, 128), (1, 128, 64, 128), (2, 1, 128, 256),
-                                           (2, 128, 64, 256), (8, 64, 64, 128), (3, 128, 64, 512)])   # CTA-pair schedule
+                                           (2, 128, 64, 256), (8, 64, 64, 128), (3, 128, 64, 512),    # CTA-pair schedule
+                                           (2, 256, 256, 128), (3, 128, 128, 128)])   # two output rows per work unit
 def test_conv3x3_tensor_core_operator(torch, n, r, cin, cout):
     """tcgen05 implicit GEMM vs torch fp32 convolution on bf16-rounded operands."""
     from moonsuperresolution_b200 import _lib
@@ -62,6 +63,8 @@ def test_conv3x3_tensor_core_operator(torch, n, r, cin, cout):
     (2, 32, 64, 128, 1, 1, 0, 1),      # 1x1, relu, bf16 out
     (1, 16, 128, 32, 9, 1, 1, 0),      # 32 columns
     (2, 16, 64, 128, 9, 1, 1, 0),      # fp32 out + fused statistics
+    (2, 256, 64, 128, 9, 1, 1, 0),     # the same on the two-rows-per-unit strip schedule (statistics rows per tile)
+    (5, 128, 64, 128, 9, 1, 1, 0),
 ])
 def test_conv_tc_general_operator(torch, n, r_out, cin, cout, taps, stride, pad, act):
     from moonsuperresolution_b200 import _lib
@@ -105,6 +108,9 @@ def test_conv_tc_general_operator(torch, n, r_out, cin, cout, taps, stride, pad,
         np.testing.assert_allclose(p[:, :, 1].sum(0), (flat ** 2).sum(0), rtol=1e-5, atol=1e-3)
         # each (tile, warp) row covers 32 consecutive pixels
         np.testing.assert_allclose(p[5, :, 0], flat[5 * 32:6 * 32].sum(0), rtol=1e-5, atol=1e-4)
+        for row in (0, 7, p.shape[0] // 2 + 3, p.shape[0] - 1):
+            np.testing.assert_allclose(p[row, :, 0], flat[row * 32:(row + 1) * 32].sum(0), rtol=1e-5, atol=1e-4)
+            np.testing.assert_allclose(p[row, :, 1], (flat[row * 32:(row + 1) * 32] ** 2).sum(0), rtol=1e-5, atol=1e-4)
 
 
 def _phase_filters(kernel, transposed):
