@@ -303,6 +303,16 @@ int msr_op_mask_tc(const float* d_source, int I, const float* h_w, const float* 
  * split-bf16 operand of the next encoder convolution.  Synchronises the stream before it returns. */
 int msr_op_enc1_tc(const float* d_source, int I, const float* h_w, uint16_t* d_out, int n, float slope, void* stream);
 
+/* Host-only halves of the two layers above (no GPU involved; the CPU test suite checks them against numpy):
+ * msr_host_pack_mask_weights: Keras kernel h_w (3, 3, 2, cout) float32 (+ h_bias (cout) or NULL), cout 64 or 128 ->
+ *   h_out (cout, 64) bf16 bits in the split-bf16 K layout of csrc/mask_tc.cu: k = 4t + {0,1,2,3} -> (whi0, whi1, whi0, whi1)
+ *   of tap t = ky*3 + kx, k = 36 + 2t + {0,1} -> (wlo0, wlo1), k = 54 / 55 -> bias hi / lo, rest zero.
+ * msr_host_pack_phase_weights: h_w4 (4, 9*cin) bf16 bits -> h_wg (32, cin): one row per (phase, tap) pair with a non-zero
+ *   filter, phase-major then tap order; *kind 0 (4x4 conv of the x2-upsampled tensor: 25 rows), 1 (4x4 stride-2
+ *   transposed conv: 16 rows) or -1 (neither pattern: nothing written). */
+int msr_host_pack_mask_weights(const float* h_w, const float* h_bias, int cout, uint16_t* h_out);
+int msr_host_pack_phase_weights(const uint16_t* h_w4, int cin, uint16_t* h_wg, int* kind, int* ncols);
+
 /* Optimisation aid: when d_counters != NULL (148 * 8 int64, zero-initialised by the caller), every tensor-core convolution
  * planned afterwards records per-CTA cycle counts: [0] producer wait on empty stages, [1] producer total, [2] MMA issuer
  * wait on full stages, [3] MMA issuer wait on free accumulators, [4] MMA issuer total, [5] epilogue wait on accumulators.

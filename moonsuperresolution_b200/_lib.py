@@ -59,6 +59,8 @@ SIGNATURES: Dict[str, tuple] = {
     "msr_generator_destroy": (_i, [_vp]),
     "msr_op_conv3x3_bf16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "msr_op_conv_tc": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp]),
+    "msr_host_pack_mask_weights": (_i, [_vp, _vp, _i, _vp]),
+    "msr_host_pack_phase_weights": (_i, [_vp, _i, _vp, C.POINTER(_i), C.POINTER(_i)]),
     "msr_op_enc1_tc": (_i, [_vp, _i, _vp, _vp, _i, _f, _vp]),
     "msr_op_mask_tc": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _vp]),
     "msr_op_phase_tc": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),

@@ -233,6 +233,30 @@ extern "C" int msr_op_enc1_tc(const float* d_source, int I, const float* h_w, ui
   return rc;
 }
 
+// ---- host-only halves of the tensor-core layers (no GPU needed): exported so that the CPU test suite covers them -------
+extern "C" int msr_host_pack_mask_weights(const float* h_w, const float* h_bias, int cout, uint16_t* h_out) {
+  MSR_REQUIRE(h_w && h_out && (cout == 64 || cout == 128), "msr_host_pack_mask_weights: bad arguments");
+  std::vector<uint16_t> wm;
+  mask_tc_pack_weights(h_w, h_bias, cout, &wm);
+  std::copy(wm.begin(), wm.end(), h_out);
+  return MSR_OK;
+}
+
+extern "C" int msr_host_pack_phase_weights(const uint16_t* h_w4, int cin, uint16_t* h_wg, int* kind, int* ncols) {
+  MSR_REQUIRE(h_w4 && h_wg && kind && ncols && cin > 0, "msr_host_pack_phase_weights: bad arguments");
+  std::vector<uint16_t> wg;
+  PhaseTable tab;
+  if (phase_tc_pack(h_w4, cin, &wg, &tab) <= 0) {
+    *kind = -1;
+    *ncols = 0;
+    return MSR_OK;   // neither layer kind: the caller keeps the 9-tap form
+  }
+  std::copy(wg.begin(), wg.end(), h_wg);
+  *kind = tab.kind;
+  *ncols = tab.ncols;
+  return MSR_OK;
+}
+
 extern "C" int msr_op_conv3x3_f32(const float* d_x, const float* d_w, const float* d_bias, float* d_y, int n, int r,
                                   int cin, int cout, void* stream) {
   ConvF32 c;
