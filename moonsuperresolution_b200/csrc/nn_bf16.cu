@@ -550,7 +550,20 @@ __global__ void __launch_bounds__(256) stats_pairs_partial_kernel(const float2* 
   if (c < C) {
     const float2* base = pairs + ((int64_t)g * rows_p) * C + c;
     int64_t r = r0 + ry;
-    // four independent 16-byte loads in flight per thread (the sums stay in row order: a, b, c, d are added in turn)
+    // sixteen independent 16-byte loads in flight per thread (the sums stay in row order): the small launches are one
+    // DRAM round trip instead of four, the large ones keep 256 bytes per thread in flight
+    for (; r + 15 * 8 < r1; r += 16 * 8) {
+      float4 v[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) v[k] = __ldcs(reinterpret_cast<const float4*>(base + (r + 8 * k) * C));
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        s0 += (double)v[k].x;
+        q0 += (double)v[k].y;
+        s1 += (double)v[k].z;
+        q1 += (double)v[k].w;
+      }
+    }
     for (; r + 24 < r1; r += 32) {
       const float4 a = __ldcs(reinterpret_cast<const float4*>(base + r * C));
       const float4 b = __ldcs(reinterpret_cast<const float4*>(base + (r + 8) * C));
@@ -602,17 +615,29 @@ __global__ void __launch_bounds__(256) stats_pairs_partial_kernel(const float2* 
     __syncthreads();
     if (s_last) {
       __threadfence();
-      const int cc = blockIdx.x * 64 + threadIdx.x;
-      if (threadIdx.x < 64 && cc < C) {
-        double s = 0.0, q = 0.0;
-#pragma unroll 8
-        for (int k = 0; k < splits; ++k) {
+      // second stage over all 256 threads: thread = (split range q of 4, channel): its partial sums are added in split
+      // order, the four ranges in range order -> a fixed summation order, one round trip to L2 instead of eight
+      const int ch = threadIdx.x & 63, q = threadIdx.x >> 6;
+      const int cc = blockIdx.x * 64 + ch;
+      const int per_q = (splits + 3) >> 2, k0 = q * per_q, k1 = min(splits, k0 + per_q);
+      double s = 0.0, sq = 0.0;
+      if (cc < C) {
+#pragma unroll 16
+        for (int k = k0; k < k1; ++k) {
           const double2 o = __ldcg(reinterpret_cast<const double2*>(partial + (((int64_t)g * splits + k) * C + cc) * 2));
           s += o.x;
-          q += o.y;
+          sq += o.y;
         }
-        const double mu = s / count;
-        double var = q / count - mu * mu;
+      }
+      __shared__ double fin[2][4][64];
+      fin[0][q][ch] = s;
+      fin[1][q][ch] = sq;
+      __syncthreads();
+      if (threadIdx.x < 64 && cc < C) {
+        const double st = ((fin[0][0][ch] + fin[0][1][ch]) + fin[0][2][ch]) + fin[0][3][ch];
+        const double qt = ((fin[1][0][ch] + fin[1][1][ch]) + fin[1][2][ch]) + fin[1][3][ch];
+        const double mu = st / count;
+        double var = qt / count - mu * mu;
         if (var < 0.0) var = 0.0;
         mean[(int64_t)g * C + cc] = (float)mu;
         rstd[(int64_t)g * C + cc] = (float)(1.0 / sqrt(var + (double)eps));

@@ -287,7 +287,14 @@ static int channel_stats_impl(const T* x, int ld, int groups, int64_t rows, int 
   ProfileScope prof(MSR_PROF_STATS, st, (double)groups * rows * C * sizeof(T), counters ? 1 : 2);
   // a block walks >= 64 rows per row lane (8 lanes): few fat blocks instead of kStatSplit thin ones when the per-group
   // row count is small (per-image moments of the encoder, the 8 x 8 first generator block)
-  const int splits = stat_splits(rows, 8 * 64);
+  int splits = stat_splits(rows, 8 * 64);
+  {  // ... but never fewer blocks than fill the chip a few times over when the rows allow it (>= 8 rows per row lane): the
+     // 8 x 8 first generator block (8 groups x 1024 channels, 1024 rows each) used to run on 128 blocks
+    const int base_blocks = ceil_div(C, 128) * groups;
+    const int want = ceil_div(4 * 148, base_blocks);
+    const int by_rows = (int)std::max<int64_t>(1, rows / 64);
+    splits = std::min(kStatSplit, std::max(splits, std::min(want, by_rows)));
+  }
   stats_partial_kernel<T><<<dim3(ceil_div(C, 128), splits, groups), 256, 0, st>>>(x, ld, rows, C, partial, counters, eps,
                                                                                   mean, rstd);
   MSR_LAUNCH_CHECK();
