@@ -1101,10 +1101,15 @@ int forward_pix2pix_bf16(Fwd& f, const float* source, float* out) {
   cudaStream_t st = f.st;
   int rc;
   // ---- down path; skip d_{k+1} lives in cat[6-k] behind the up-sampled channels
-  if ((rc = source_patches_bf16(source, 256, g->patches, n, 128, 2, st))) return rc;
-  const __nv_bfloat16* x = g->patches;
-  int cin = 64, x_pitch = 64, s = 256;
-  for (int k = 0; k < 8; ++k) {
+  // block 1 (2 input channels): the operand tile is built inside the kernel when the skip half of its concat buffer is
+  // channels [64, 128) of a 128-channel tensor (mask_tc.cu MODE 2); otherwise im2col rows + a K = 64 GEMM
+  const bool b1_in_kernel = !g_disable_mask_tc && kP2PUp[6] == 64 && kP2PDown[0] == 64;
+  if (b1_in_kernel) {
+    if ((rc = p2p1_conv_tc(source, 256, g->pdt_w[0], g->catb[6], n, 0.3f, st))) return rc;
+  } else if ((rc = source_patches_bf16(source, 256, g->patches, n, 128, 2, st))) return rc;
+  const __nv_bfloat16* x = b1_in_kernel ? g->catb[6] + kP2PUp[6] : g->patches;
+  int cin = 64, x_pitch = b1_in_kernel ? kP2PUp[6] + kP2PDown[0] : 64, s = b1_in_kernel ? 128 : 256;
+  for (int k = b1_in_kernel ? 1 : 0; k < 8; ++k) {
     const int cout = kP2PDown[k];
     __nv_bfloat16* y;
     int pitch;

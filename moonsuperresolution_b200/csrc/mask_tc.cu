@@ -17,7 +17,12 @@
 // strides=2, 'same', no bias) on the full-resolution source (taps (2h + ky, 2w + kx), SAME padding (0, 1)) -> LeakyReLU(0.2)
 // -> split-bf16 row hi (64) | lo (64), the operand of the next encoder convolution.
 //
-// Split-bf16 K layout (the three products x_hi*w_hi + x_lo*w_hi + x_hi*w_lo ~ a float32 product; mask_tc_pack_weights):
+// MODE 2 is pix2pix's first block (pix2pix.py:64-72 without the norm): Conv2D(64, 4, strides=2, 'same', no bias) -> LeakyReLU(0.3)
+// (taps (2h + ky - 1, 2w + kx - 1), ky, kx in 0..3), written as 64 bf16 channels into the skip half of a 128-channel
+// concat buffer.  Its K layout is the one of the im2col form it replaces: k = 2t + c -> x_hi, k = 32 + 2t + c -> x_lo of
+// tap t = ky*4 + kx against [w | w] (the exact input against bf16 weights).
+//
+// Split-bf16 K layout of MODE 0 / 1 (the three products x_hi*w_hi + x_lo*w_hi + x_hi*w_lo ~ a float32 product; mask_tc_pack_weights):
 //   k = 4t + {0, 1, 2, 3}   tap t = ky*3 + kx:  x = (hi0, hi1, lo0, lo1)   w = (whi0, whi1, whi0, whi1)
 //   k = 36 + 2t + {0, 1}                        x = (hi0, hi1)             w = (wlo0, wlo1)
 //   k = 54, 55                                  x = (1, 1)                 w = (bias_hi, bias_lo): the bias rides in the GEMM
@@ -50,7 +55,7 @@ struct MaskGeom {
   int n_tiles;             // ceil(M / 128)
   float slope;             // MODE 1: LeakyReLU slope
   const float* src;        // [n][I][I][2] float32
-  __nv_bfloat16* out;      // [M][128]: MODE 0 the 128 channels; MODE 1 hi (64) | lo (64)
+  __nv_bfloat16* out;      // [M][128]: MODE 0 the 128 channels; MODE 1 hi (64) | lo (64); MODE 2 channels [64, 128)
 };
 
 __device__ __forceinline__ void mbar_arrive_release(uint32_t bar) {
@@ -71,6 +76,7 @@ template <int MODE>
 __global__ void __launch_bounds__(kMkThreads, 1)
 mask_conv_tc_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_o, const MaskGeom g) {
   constexpr int kN = MODE == 0 ? kMkN : 64;          // GEMM columns
+  constexpr int kTaps = MODE == 2 ? 16 : 9, kSide = MODE == 2 ? 4 : 3;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -119,19 +125,19 @@ mask_conv_tc_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_cons
     const int i = threadIdx.x - kProdWarp0 * 32;     // tile row 0..127
     const int r = g.r, lr = g.lr, f = g.f, I = g.I;
     const uint32_t row_off = (uint32_t)i * 128u, sw = (uint32_t)(i & 7);
-    auto load_taps = [&](int tile, float2 (&s)[9]) {
+    auto load_taps = [&](int tile, float2 (&s)[kTaps]) {
       const int64_t m = (int64_t)tile * kBlockM + i;
 #pragma unroll
-      for (int t = 0; t < 9; ++t) s[t] = make_float2(0.f, 0.f);
+      for (int t = 0; t < kTaps; ++t) s[t] = make_float2(0.f, 0.f);
       if (tile < g.n_tiles && m < g.M) {
         const int b = (int)(m >> (2 * lr));
         const int rem = (int)(m & (((int64_t)1 << (2 * lr)) - 1));
         const int h = rem >> lr, w = rem & (r - 1);
         const float* img = g.src + (int64_t)b * I * I * 2;
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
+        for (int ky = 0; ky < kSide; ++ky) {
 #pragma unroll
-          for (int kx = 0; kx < 3; ++kx) {
+          for (int kx = 0; kx < kSide; ++kx) {
             int sy, sx;
             bool ok;
             if constexpr (MODE == 0) {   // SAME padding (1, 1) on the resized mask; nearest resize, half-pixel centres
@@ -139,12 +145,16 @@ mask_conv_tc_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_cons
               ok = hh >= 0 && hh < r && ww >= 0 && ww < r;
               sy = hh * f + g.half;
               sx = ww * f + g.half;
-            } else {                     // stride-2 taps on the source itself, SAME padding (0, 1)
+            } else if constexpr (MODE == 1) {   // stride-2 taps on the source itself, SAME padding (0, 1)
               sy = 2 * h + ky;
               sx = 2 * w + kx;
               ok = sy < I && sx < I;
+            } else {                     // 4x4 stride-2 taps, SAME padding (1, 1)
+              sy = 2 * h + ky - 1;
+              sx = 2 * w + kx - 1;
+              ok = sy >= 0 && sy < I && sx >= 0 && sx < I;
             }
-            if (ok) s[ky * 3 + kx] = __ldg(reinterpret_cast<const float2*>(img + ((int64_t)sy * I + sx) * 2));
+            if (ok) s[ky * kSide + kx] = __ldg(reinterpret_cast<const float2*>(img + ((int64_t)sy * I + sx) * 2));
           }
         }
       }
@@ -153,10 +163,10 @@ mask_conv_tc_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_cons
     int stage = 0;
     uint32_t phase = 0;
     // converts the taps in `s` (tile `tile`), refills `s` with the taps of the tile two steps ahead, writes the row
-    auto produce = [&](int tile, float2 (&s)[9]) {
-      uint32_t ex[9], ey[9];   // per tap: (hi0 | hi1 << 16), (lo0 | lo1 << 16); x = hi + lo to ~2^-17
+    auto produce = [&](int tile, float2 (&s)[kTaps]) {
+      uint32_t ex[kTaps], ey[kTaps];   // per tap: (hi0 | hi1 << 16), (lo0 | lo1 << 16); x = hi + lo to ~2^-17
 #pragma unroll
-      for (int t = 0; t < 9; ++t) {
+      for (int t = 0; t < kTaps; ++t) {
         const __nv_bfloat162 hi = __floats2bfloat162_rn(s[t].x, s[t].y);
         const float2 hf = __bfloat1622float2(hi);
         const __nv_bfloat162 lo = __floats2bfloat162_rn(s[t].x - hf.x, s[t].y - hf.y);
@@ -169,14 +179,22 @@ mask_conv_tc_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_cons
       auto put = [&](uint32_t c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3) {
         *reinterpret_cast<uint4*>(row + ((c ^ sw) << 4)) = make_uint4(a0, a1, a2, a3);
       };
-      put(0, ex[0], ey[0], ex[1], ey[1]);
-      put(1, ex[2], ey[2], ex[3], ey[3]);
-      put(2, ex[4], ey[4], ex[5], ey[5]);
-      put(3, ex[6], ey[6], ex[7], ey[7]);
-      put(4, ex[8], ey[8], ex[0], ex[1]);
-      put(5, ex[2], ex[3], ex[4], ex[5]);
-      put(6, ex[6], ex[7], ex[8], 0x3f803f80u);   // k = 54, 55: bf16 ones against the bias rows of the weights
-      put(7, 0u, 0u, 0u, 0u);
+      if constexpr (MODE == 2) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          put(q, ex[4 * q], ex[4 * q + 1], ex[4 * q + 2], ex[4 * q + 3]);       // k = 2t + c: hi
+          put(4 + q, ey[4 * q], ey[4 * q + 1], ey[4 * q + 2], ey[4 * q + 3]);   // k = 32 + 2t + c: lo
+        }
+      } else {
+        put(0, ex[0], ey[0], ex[1], ey[1]);
+        put(1, ex[2], ey[2], ex[3], ey[3]);
+        put(2, ex[4], ey[4], ex[5], ey[5]);
+        put(3, ex[6], ey[6], ex[7], ey[7]);
+        put(4, ex[8], ey[8], ex[0], ex[1]);
+        put(5, ex[2], ex[3], ex[4], ex[5]);
+        put(6, ex[6], ex[7], ex[8], 0x3f803f80u);   // k = 54, 55: bf16 ones against the bias rows of the weights
+        put(7, 0u, 0u, 0u, 0u);
+      }
       fence_proxy_async_smem();            // generic-proxy stores -> visible to the tensor core's async-proxy reads
       mbar_arrive_release(full_bar(stage));
       if (++stage == kMkStages) {
@@ -184,7 +202,7 @@ mask_conv_tc_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_cons
         phase ^= 1u;
       }
     };
-    float2 s0[9], s1[9];
+    float2 s0[kTaps], s1[kTaps];
     int tile = blockIdx.x;
     load_taps(tile, s0);
     load_taps(tile + tile_step, s1);
@@ -271,6 +289,20 @@ mask_conv_tc_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_cons
         for (int q = 0; q < 4; ++q) put(csel, q, pack8(v0, q));
 #pragma unroll
         for (int q = 0; q < 4; ++q) put(csel, 4 + q, pack8(v1, q));
+      } else if constexpr (MODE == 2) {
+        // columns [32*csel, 32*csel + 32): leaky_relu -> bf16 into the one box, chunks 4*csel .. + 3
+        const float sl = g.slope;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float a0 = __uint_as_float(v0[8 * q + 2 * j]), a1 = __uint_as_float(v0[8 * q + 2 * j + 1]);
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(fmaxf(a0, a0 * sl), fmaxf(a1, a1 * sl));
+            pk[j] = *reinterpret_cast<const uint32_t*>(&h2);
+          }
+          put(0, (uint32_t)(4 * csel + q), make_uint4(pk[0], pk[1], pk[2], pk[3]));
+        }
       } else {
         // columns [32*csel, 32*csel + 32): leaky_relu -> hi into box 0, lo = v - hi into box 1, chunks 4*csel .. + 3
         const float sl = g.slope;   // 0 < slope < 1: leaky_relu(x) = max(x, slope * x)
@@ -296,8 +328,12 @@ mask_conv_tc_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_cons
       asm volatile("bar.sync 1, %0;" ::"n"(kMkEpiWarps * 32) : "memory");
       if (threadIdx.x == 0) {
         const uint32_t s0 = smem_base + kOffOut + buf * kMkStageOut;
-        tma_store_2d(&map_o, s0, 0, tile * kBlockM);                       // rows beyond M are clipped by the tensor map
-        tma_store_2d(&map_o, s0 + kBlockM * 128, 64, tile * kBlockM);
+        if constexpr (MODE == 2) {
+          tma_store_2d(&map_o, s0, 64, tile * kBlockM);                    // the skip half of the concat buffer
+        } else {
+          tma_store_2d(&map_o, s0, 0, tile * kBlockM);                     // rows beyond M are clipped by the tensor map
+          tma_store_2d(&map_o, s0 + kBlockM * 128, 64, tile * kBlockM);
+        }
         tma_store_commit();
       }
       if (++acc == kMkAcc) {
@@ -353,7 +389,7 @@ void mask_tc_pack_weights(const float* w, const float* bias, int cout, std::vect
 
 bool mask_tc_supported(int I, int r) { return r >= 1 && (r & (r - 1)) == 0 && r <= I && I % r == 0; }
 
-// mode 0: SPADE mask convolution at side r; mode 1: encoder block 1 (r = I / 2)
+// mode 0: SPADE mask convolution at side r; mode 1: encoder block 1 (r = I / 2); mode 2: pix2pix block 1 (r = I / 2)
 static int source_conv_tc(int mode, const float* source, int I, const __nv_bfloat16* wm, __nv_bfloat16* out, int n, int r,
                           float slope, cudaStream_t st) {
   MSR_REQUIRE(source && wm && out && n > 0, "source_conv_tc: bad arguments");
@@ -396,16 +432,18 @@ static int source_conv_tc(int mode, const float* source, int I, const __nv_bfloa
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  ProfileScope prof(MSR_PROF_CONV_TC, st, 2.0 * (double)g.M * cols * 18);
+  ProfileScope prof(MSR_PROF_CONV_TC, st, 2.0 * (double)g.M * cols * (mode == 2 ? 32 : 18));
   static bool attr_set = false;
   if (!attr_set) {
     MSR_CUDA_CHECK(cudaFuncSetAttribute(tc::mask_conv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kMkSmemBytes));
     MSR_CUDA_CHECK(cudaFuncSetAttribute(tc::mask_conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kMkSmemBytes));
+    MSR_CUDA_CHECK(cudaFuncSetAttribute(tc::mask_conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kMkSmemBytes));
     attr_set = true;
   }
   const int grid = std::min(g.n_tiles, sms);
   if (mode == 0) tc::mask_conv_tc_kernel<0><<<grid, tc::kMkThreads, tc::kMkSmemBytes, st>>>(map_b, map_o, g);
-  else tc::mask_conv_tc_kernel<1><<<grid, tc::kMkThreads, tc::kMkSmemBytes, st>>>(map_b, map_o, g);
+  else if (mode == 1) tc::mask_conv_tc_kernel<1><<<grid, tc::kMkThreads, tc::kMkSmemBytes, st>>>(map_b, map_o, g);
+  else tc::mask_conv_tc_kernel<2><<<grid, tc::kMkThreads, tc::kMkSmemBytes, st>>>(map_b, map_o, g);
   count_launch();
   MSR_LAUNCH_CHECK();
   return MSR_OK;
@@ -413,6 +451,12 @@ static int source_conv_tc(int mode, const float* source, int I, const __nv_bfloa
 
 int mask_conv_tc(const float* source, int I, const __nv_bfloat16* wm, __nv_bfloat16* out, int n, int r, cudaStream_t st) {
   return source_conv_tc(0, source, I, wm, out, n, r, 0.f, st);
+}
+
+int p2p1_conv_tc(const float* source, int I, const __nv_bfloat16* wm, __nv_bfloat16* out128, int n, float slope,
+                 cudaStream_t st) {
+  MSR_REQUIRE(I >= 2 && I % 2 == 0, "p2p1_conv_tc: the source side must be even");
+  return source_conv_tc(2, source, I, wm, out128, n, I / 2, slope, st);
 }
 
 int enc1_conv_tc(const float* source, int I, const __nv_bfloat16* wm, __nv_bfloat16* out, int n, float slope, cudaStream_t st) {

@@ -151,6 +151,10 @@ int mask_conv_tc(const float* source, int I, const __nv_bfloat16* wm, __nv_bfloa
 // Encoder block 1 with the same kernel (blocks.py:53-60, no norm; networks.py:12): out [n][I/2][I/2][128] bf16 = hi (64) |
 // lo (64) of leaky_relu(conv3x3 stride 2, SAME (0, 1), 2 -> 64, no bias); wm [64][64] from mask_tc_pack_weights(w, null, 64).
 int enc1_conv_tc(const float* source, int I, const __nv_bfloat16* wm, __nv_bfloat16* out, int n, float slope, cudaStream_t st);
+// pix2pix block 1 with the same kernel (pix2pix.py:64-72, no norm): channels [64, 128) of out128 [n][I/2][I/2][128] bf16 =
+// leaky_relu(conv4x4 stride 2, SAME (1, 1), 2 -> 64, no bias); wm [64][64]: k = (ky*4 + kx)*2 + c, columns [w | w].
+int p2p1_conv_tc(const float* source, int I, const __nv_bfloat16* wm, __nv_bfloat16* out128, int n, float slope,
+                 cudaStream_t st);
 
 // ---- small helpers for the bf16 path (nn_bf16.cu) -----------------------------------------------------------------
 // im2col of the 2-channel source for a 3x3 convolution at output side r: out [n][r][r][64] bf16, channel (ky*3+kx)*2+c
